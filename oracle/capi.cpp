@@ -1,0 +1,102 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ops.h).  C entry points for tests/ (ctypes) and bench.py's cpu_baseline.
+#include "rx11a.h"
+#include <thread>
+#include <atomic>
+#include <vector>
+
+using namespace sbo;
+
+extern "C" {
+
+struct sbo_frame_result {           // mirrors sbo::FrameResult; keep in sync with tests/oracle_py.py
+    uint32_t status, rate_kbps, length, crc32, nsym, sample_index, detect_index;
+    int16_t cfo_est; uint16_t peak_index;
+};
+
+int sbo_rx11a_run(const int16_t* iq, uint64_t nsamples, int max_frames, sbo_frame_result* res,
+                  uint8_t* out, uint64_t out_stride) {
+    Rx11a rx;
+    return rx.run((const c16*)iq, (size_t)nsamples, (FrameResult*)res, out, (size_t)out_stride, max_frames);
+}
+
+// Batched "one capture slot per frame" mode: slot i = iq[off[i] .. off[i]+len[i]) decoded from a fresh context,
+// first event reported (status E_NO_FRAME if none).  nthreads host threads over independent slots.
+void sbo_rx11a_batch(const int16_t* iq, const uint64_t* off, const uint32_t* len, uint32_t nframes,
+                     sbo_frame_result* res, uint8_t* out, uint64_t out_stride, int nthreads) {
+    std::atomic<uint32_t> next(0);
+    auto work = [&]() {
+        Rx11a rx;
+        for (;;) {
+            uint32_t i = next.fetch_add(1); if (i >= nframes) break;
+            FrameResult r; memset(&r, 0, sizeof r);
+            int n = rx.run((const c16*)iq + off[i], len[i], &r, out ? out + (size_t)i * out_stride : nullptr, (size_t)out_stride, 1);
+            if (n == 0) { memset(&r, 0, sizeof r); r.status = E_NO_FRAME; }
+            memcpy(&res[i], &r, sizeof r);
+        }
+    };
+    if (nthreads <= 1) { work(); return; }
+    std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+}
+
+// Stage taps of the first frame in a buffer.  Buffers sized by the caller: coeffs 64 c16 each;
+// per-symbol arrays max_sym*64 c16; soft max_sym*288 bytes.  Returns number of symbols captured (incl. SIGNAL).
+int sbo_rx11a_taps(const int16_t* iq, uint64_t nsamples, sbo_frame_result* res,
+                   int16_t* freq_coeffs, int16_t* chan_coeffs, int16_t* fft_out, int16_t* equalized, int16_t* tracked,
+                   uint8_t* soft, uint32_t* soft_off, int max_sym) {
+    Rx11a rx; rx.taps.enable = true;
+    FrameResult r; memset(&r, 0, sizeof r);
+    int n = rx.run((const c16*)iq, (size_t)nsamples, &r, nullptr, 0, 1);
+    if (n == 0) r.status = E_NO_FRAME;
+    memcpy(res, &r, sizeof r);
+    const Taps& t = rx.taps;
+    if (t.freq_coeffs.size() == 64) { memcpy(freq_coeffs, t.freq_coeffs.data(), 256); memcpy(chan_coeffs, t.chan_coeffs.data(), 256); }
+    int ns = (int)(t.fft_out.size() / 64); if (ns > max_sym) ns = max_sym;
+    memcpy(fft_out, t.fft_out.data(), (size_t)ns * 256); memcpy(equalized, t.equalized.data(), (size_t)ns * 256);
+    memcpy(tracked, t.tracked.data(), (size_t)ns * 256);
+    for (int i = 0; i < ns; i++) {
+        soft_off[i] = t.soft_off[i];
+        size_t end = (i + 1 < (int)t.soft_off.size()) ? t.soft_off[i + 1] : t.soft.size();
+        memcpy(soft + t.soft_off[i], t.soft.data() + t.soft_off[i], end - t.soft_off[i]);
+    }
+    soft_off[ns] = (uint32_t)(ns < (int)t.soft_off.size() ? t.soft_off[ns] : t.soft.size());
+    return ns;
+}
+
+// Standalone Viterbi block decode (BASELINE config #5): soft = nsoft coded soft values (0..7) at code_rate,
+// frame_len_bytes L defines the flush point 8L+16+6; writes L+2 bytes... (SERVICE + PSDU, still scrambled).
+uint64_t sbo_viterbi_block(const uint8_t* soft, uint64_t nsoft, int code_rate, uint32_t frame_len_bytes,
+                           uint32_t depth, uint32_t lookahead, uint8_t* out) {
+    ViterbiCore v; v.max_steps = (uint32_t)nsoft + 8; v.reset();
+    uint32_t ob = 0;
+    return viterbi_decode_block(v, soft, (size_t)nsoft, code_rate, frame_len_bytes, depth, lookahead, out, ob);
+}
+void sbo_viterbi_blocks(const uint8_t* soft, uint64_t nsoft_per_block, uint32_t nblocks, int code_rate, uint32_t frame_len_bytes,
+                        uint32_t depth, uint32_t lookahead, uint8_t* out, uint64_t out_stride, int nthreads) {
+    std::atomic<uint32_t> next(0);
+    auto work = [&]() {
+        ViterbiCore v; v.max_steps = (uint32_t)nsoft_per_block + 8;
+        for (;;) { uint32_t i = next.fetch_add(1); if (i >= nblocks) break;
+            v.reset(); uint32_t ob = 0;
+            viterbi_decode_block(v, soft + (size_t)i * nsoft_per_block, (size_t)nsoft_per_block, code_rate, frame_len_bytes, depth, lookahead, out + (size_t)i * out_stride, ob); }
+    };
+    if (nthreads <= 1) { work(); return; }
+    std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+}
+uint32_t sbo_viterbi_signal(const uint8_t* soft48) { return viterbi_signal(soft48); }
+
+void sbo_fft64(const int16_t* in, int16_t* out) { alignas(16) c16 t[64]; memcpy(t, in, 256); alignas(16) c16 o[64]; fft64((v128*)t, (v128*)o); memcpy(out, o, 256); }
+void sbo_ifft64(const int16_t* in, int16_t* out) { alignas(16) c16 t[64]; memcpy(t, in, 256); alignas(16) c16 o[64]; ifft64((v128*)t, (v128*)o); memcpy(out, o, 256); }
+int16_t sbo_uatan2(int y, int x) { return uatan2(y, x); }
+int16_t sbo_usin(int16_t r) { return usin(r); }
+int16_t sbo_ucos(int16_t r) { return ucos(r); }
+void sbo_demap(const int16_t* eq, uint8_t* out, int nbpsc) { demap_symbol((const c16*)eq, out, nbpsc); }
+void sbo_deinterleave(const uint8_t* in, uint8_t* out, int ncbps) { deinterleave(in, out, ncbps); }
+const int16_t* sbo_sts_pattern() { return (const int16_t*)tables().sts_pattern; }
+void sbo_tables(const uint8_t** vit_ma, const uint8_t** vit_mb, const uint8_t** demap4 /*4x256*/) {
+    const Tables& T = tables(); *vit_ma = &T.vit_ma[0][0]; *vit_mb = &T.vit_mb[0][0]; *demap4 = T.demap_bpsk;
+}
+uint32_t sbo_crc32(const uint8_t* p, uint64_t n) { uint32_t c = 0xFFFFFFFFu; for (uint64_t i = 0; i < n; i++) c = (c >> 8) ^ tables().crc32_lut[p[i] ^ (c & 0xFF)]; return ~c; }
+
+} // extern "C"

@@ -1,0 +1,82 @@
+"""ctypes binding of oracle/libsora_oracle.so — TEST INFRASTRUCTURE (checker only, never the product path)."""
+import ctypes as C, os, subprocess, numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+class FrameResult(C.Structure):
+    _fields_ = [("status", C.c_uint32), ("rate_kbps", C.c_uint32), ("length", C.c_uint32), ("crc32", C.c_uint32),
+                ("nsym", C.c_uint32), ("sample_index", C.c_uint32), ("detect_index", C.c_uint32),
+                ("cfo_est", C.c_int16), ("peak_index", C.c_uint16)]
+
+RES_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("nsym", "<u4"),
+                      ("sample_index", "<u4"), ("detect_index", "<u4"), ("cfo_est", "<i2"), ("peak_index", "<u2")])
+
+E_FRAME_OK, E_CRC32_FAIL, E_PLCP_FAIL, E_NO_FRAME = 1, 0x80000006, 0x80000005, 0x8000F001
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(ROOT, "oracle", "libsora_oracle.so")
+        srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle")) if f.endswith((".cpp", ".h", ".inc"))]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _LIB = C.CDLL(so)
+        _LIB.sbo_viterbi_block.restype = C.c_uint64
+        _LIB.sbo_uatan2.restype = C.c_int16; _LIB.sbo_usin.restype = C.c_int16; _LIB.sbo_ucos.restype = C.c_int16
+        _LIB.sbo_uatan2.argtypes = [C.c_int, C.c_int]; _LIB.sbo_usin.argtypes = [C.c_int16]; _LIB.sbo_ucos.argtypes = [C.c_int16]
+        _LIB.sbo_sts_pattern.restype = C.POINTER(C.c_int16)
+        _LIB.sbo_crc32.restype = C.c_uint32
+        _LIB.sbo_viterbi_signal.restype = C.c_uint32
+    return _LIB
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t)
+
+def rx11a_run(iq, max_frames=16, out_stride=4096):
+    """iq: int16 array [n,2] (40 Msps). Returns (results structured array, bytes [nf, stride])."""
+    iq = np.ascontiguousarray(iq, dtype=np.int16)
+    res = np.zeros(max_frames, dtype=RES_DTYPE); out = np.zeros((max_frames, out_stride), dtype=np.uint8)
+    n = lib().sbo_rx11a_run(_p(iq), C.c_uint64(iq.shape[0]), C.c_int(max_frames), _p(res), _p(out), C.c_uint64(out_stride))
+    return res[:n], out[:n]
+
+def rx11a_batch(iq, off, length, out_stride=2048, nthreads=1):
+    iq = np.ascontiguousarray(iq, dtype=np.int16)
+    off = np.ascontiguousarray(off, dtype=np.uint64); length = np.ascontiguousarray(length, dtype=np.uint32)
+    nf = len(off)
+    res = np.zeros(nf, dtype=RES_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+    lib().sbo_rx11a_batch(_p(iq), _p(off), _p(length), C.c_uint32(nf), _p(res), _p(out), C.c_uint64(out_stride), C.c_int(nthreads))
+    return res, out
+
+def rx11a_taps(iq, max_sym=600):
+    iq = np.ascontiguousarray(iq, dtype=np.int16)
+    res = np.zeros(1, dtype=RES_DTYPE)
+    fc = np.zeros((64, 2), np.int16); cc = np.zeros((64, 2), np.int16)
+    fo = np.zeros((max_sym, 64, 2), np.int16); eq = np.zeros_like(fo); tr = np.zeros_like(fo)
+    soft = np.zeros(max_sym * 288, np.uint8); so = np.zeros(max_sym + 1, np.uint32)
+    ns = lib().sbo_rx11a_taps(_p(iq), C.c_uint64(iq.shape[0]), _p(res), _p(fc), _p(cc), _p(fo), _p(eq), _p(tr), _p(soft), _p(so), C.c_int(max_sym))
+    return dict(res=res[0], freq_coeffs=fc, chan_coeffs=cc, fft_out=fo[:ns], equalized=eq[:ns], tracked=tr[:ns],
+                soft=soft[:so[ns]], soft_off=so[:ns + 1], nsym=ns)
+
+def viterbi_block(soft, code_rate, frame_len_bytes, depth=256, lookahead=24):
+    soft = np.ascontiguousarray(soft, dtype=np.uint8)
+    out = np.zeros(frame_len_bytes + 2 + 64, dtype=np.uint8)
+    n = lib().sbo_viterbi_block(_p(soft), C.c_uint64(len(soft)), C.c_int(code_rate), C.c_uint32(frame_len_bytes),
+                                C.c_uint32(depth), C.c_uint32(lookahead), _p(out))
+    return out[:n]
+
+def viterbi_blocks(soft2d, code_rate, frame_len_bytes, depth=256, lookahead=24, nthreads=1):
+    soft2d = np.ascontiguousarray(soft2d, dtype=np.uint8)
+    nb, ns = soft2d.shape
+    stride = frame_len_bytes + 2
+    out = np.zeros((nb, stride), dtype=np.uint8)
+    lib().sbo_viterbi_blocks(_p(soft2d), C.c_uint64(ns), C.c_uint32(nb), C.c_int(code_rate), C.c_uint32(frame_len_bytes),
+                             C.c_uint32(depth), C.c_uint32(lookahead), _p(out), C.c_uint64(stride), C.c_int(nthreads))
+    return out
+
+def fft64(x):
+    x = np.ascontiguousarray(x, dtype=np.int16); o = np.zeros((64, 2), np.int16); lib().sbo_fft64(_p(x), _p(o)); return o
+def ifft64(x):
+    x = np.ascontiguousarray(x, dtype=np.int16); o = np.zeros((64, 2), np.int16); lib().sbo_ifft64(_p(x), _p(o)); return o
+def crc32(b):
+    b = np.ascontiguousarray(b, dtype=np.uint8); return int(lib().sbo_crc32(_p(b), C.c_uint64(len(b))))
