@@ -1,0 +1,103 @@
+/* sora_b200 — C ABI of the Blackwell (sm_100a) 802.11 receive baseband.
+ *
+ * This is the drop-in boundary for Sora's dot11 RX hot path.  Every entry point states which reference
+ * interface it stands behind (paths relative to the reference tree):
+ *
+ *   sb200_create / sb200_destroy   <->  BB11ARxContextInit            kernel/inc/bb/bba.h:191-201
+ *                                       BB11aDemodContext::Init       kernel/bb/demod11/fb11ademod_config.hpp:105-121
+ *   sb200_rx11a_batch              <->  the sub-graph ds2 .. fsink of CreateDemodGraph11a_40M
+ *                                       kernel/bb/demod11/fb11ademod_config.hpp:169-242, driven like RxThread
+ *                                       kernel/bb/demod11/fb11a_demod.cpp:29-81; legacy shape BB11ARxCarrierSense +
+ *                                       BB11ARxFrameDemod, kernel/inc/bb/bba.h:203-262
+ *   sb200_viterbi_k7               <->  T11aViterbi<TR_MAX,N_IN,DEPTH,LOOKAHEAD>::Filter
+ *                                       kernel/bb/Brick11/src/viterbi.hpp:104-237 (BASELINE config #5)
+ *   sb200_rx11a_taps               <->  BB_DEBUG `_dump_symbol` taps  kernel/brick/inc/bb_debug.h:5-41
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative SB200_E_* code
+ * and never throws.  Sample and result buffers may live in host or device memory (detected per pointer); host
+ * buffers are staged through the handle's pinned/device workspaces on `stream`.  Calls are asynchronous on
+ * `stream` when all buffers are device buffers, and synchronise the stream before returning when a result buffer
+ * is host memory.  One handle may be used by one host thread at a time.
+ * There is NO CPU fallback: if no CUDA device is usable the create call fails.
+ */
+#ifndef SORA_B200_H
+#define SORA_B200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_OK              0
+#define SB200_E_INVALID      (-1)
+#define SB200_E_CUDA         (-2)
+#define SB200_E_NOMEM        (-3)
+#define SB200_E_NODEVICE     (-4)
+
+/* Frame status values = CF_Error::error_code of the reference (brick/inc/stdfacade.h:10-12,
+ * Brick11/src/ieee80211facade.hpp:10-19) plus one engine-only code. */
+#define SB200_FRAME_OK            0x00000001u  /* E_ERROR_FRAME_OK */
+#define SB200_FRAME_FAILED        0x8000FFFFu  /* E_ERROR_FAILED */
+#define SB200_FRAME_PLCP_FAIL     0x80000005u  /* E_ERROR_PLCP_HEADER_FAIL */
+#define SB200_FRAME_CRC32_FAIL    0x80000006u  /* E_ERROR_CRC32_FAIL */
+#define SB200_FRAME_NONE          0x8000F001u  /* slot exhausted before any frame event (the reference just runs out of samples) */
+
+#define SB200_CR_12 0   /* Brick11/src/ieee80211const.h:13-18 */
+#define SB200_CR_23 1
+#define SB200_CR_34 2
+
+typedef struct sb200_handle sb200_handle;
+
+typedef struct sb200_cfg {
+    uint32_t cca_pwr_threshold;   /* CF_11CCA::cca_pwr_threshold, 0 = reference default 1000*1000 (fb11ademod_config.hpp:107) */
+    uint32_t reserved[7];
+} sb200_cfg;
+
+typedef struct sb200_frame_result {   /* CF_11aRxVector + CF_Error + CF_11CCA + CF_CFOffset after the first event of a slot */
+    uint32_t status;       /* SB200_FRAME_* */
+    uint32_t rate_kbps;    /* CF_11aRxVector::data_rate_kbps */
+    uint32_t length;       /* CF_11aRxVector::frame_length (PSDU bytes incl. FCS) */
+    uint32_t crc32;        /* CF_11aRxVector::crc32: the received FCS */
+    uint32_t nsym;         /* CF_11aRxVector::total_symbols (SIGNAL + data) */
+    uint32_t detect_index; /* 20 Msps sample index, relative to the slot, of the first sample routed to the demod branch */
+    int16_t  cfo_est;      /* CF_CFOffset::CFO_est (FP_RAD per 20 Msps sample) */
+    uint16_t peak_index;   /* CF_11CCA::cca_peak_index */
+} sb200_frame_result;
+
+int  sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out);
+void sb200_destroy(sb200_handle* h);
+const char* sb200_last_error(const sb200_handle* h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+uint64_t sb200_launch_count(const sb200_handle* h);
+/* device time (ms) of the kernels of the most recent *_batch / viterbi call, measured with CUDA events on `stream` */
+float sb200_last_kernel_ms(sb200_handle* h);
+
+/* Decode `nframes` independent capture slots.  Slot i is iq[2*frame_off[i] .. 2*(frame_off[i]+frame_len[i])) int16
+ * (interleaved I,Q; 40 Msps COMPLEX16 stream as TMemSamples would feed it), processed from a fresh context exactly as
+ * the reference graph processes a dump file, up to its first frame event.  out_bytes row i (out_stride bytes) receives
+ * the PSDU (FCS included), res[i] the verdict.  iq_total_samples bounds the iq buffer. */
+int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples,
+                      const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
+                      uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, void* cuda_stream);
+
+/* Standalone K=7 Viterbi over `nblocks` independent blocks of `nsoft` soft values (uint8 0..7, one per coded bit after
+ * puncturing; block b starts at soft + b*soft_stride).  frame_len_bytes L sets the flush point 8L+16+6 exactly like
+ * CF_11aRxVector::frame_length; each block yields L+2 bytes (SERVICE + PSDU, not descrambled) at out + b*out_stride.
+ * depth/lookahead = TRELLIS_DEPTH/TRELLIS_LOOKAHEAD (256/24 for 11a, 192/36 for 11n). */
+int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t soft_stride, uint32_t nsoft, uint32_t nblocks,
+                     int code_rate, uint32_t frame_len_bytes, uint32_t depth, uint32_t lookahead,
+                     uint8_t* out, uint64_t out_stride, void* cuda_stream);
+
+/* Stage taps for parity tests: decodes the slots like sb200_rx11a_batch and additionally returns, per slot,
+ * FreqCoeffs / ChannelCoeffs (64 COMPLEX16 each) and per symbol (0 = SIGNAL) the FFT output, the equalised and the
+ * pilot-tracked symbol (64 COMPLEX16 each, FFT bin order) and the de-interleaved soft bits of the data symbols.
+ * All tap buffers are host memory; any may be NULL.  soft rows are soft_stride bytes, data symbols back to back. */
+int sb200_rx11a_taps(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples,
+                     const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes, uint32_t max_sym,
+                     sb200_frame_result* res, int16_t* freq_coeffs, int16_t* chan_coeffs,
+                     int16_t* fft_out, int16_t* equalized, int16_t* tracked, uint8_t* soft, uint64_t soft_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,123 @@
+"""Python binding of the product C ABI (include/sora_b200.h) — thin ctypes, no compute here.
+
+The CUDA library is the only implementation: a missing `libsora_b200.so` or a box without a usable GPU raises.
+There is deliberately no CPU fallback (oracle/ is test infrastructure and is never imported from this package).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsora_b200.so")
+
+FRAME_OK, FRAME_FAILED, FRAME_PLCP_FAIL, FRAME_CRC32_FAIL, FRAME_NONE = 1, 0x8000FFFF, 0x80000005, 0x80000006, 0x8000F001
+CR_12, CR_23, CR_34 = 0, 1, 2
+
+RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("nsym", "<u4"),
+                         ("detect_index", "<u4"), ("cfo_est", "<i2"), ("peak_index", "<u2")])
+
+EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
+           "sb200_rx11a_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+
+class Sb200Error(RuntimeError):
+    pass
+
+_lib = None
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Sb200Error(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+        lib = C.CDLL(LIB_PATH)
+        lib.sb200_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]; lib.sb200_create.restype = C.c_int
+        lib.sb200_destroy.argtypes = [C.c_void_p]; lib.sb200_destroy.restype = None
+        lib.sb200_last_error.argtypes = [C.c_void_p]; lib.sb200_last_error.restype = C.c_char_p
+        lib.sb200_launch_count.argtypes = [C.c_void_p]; lib.sb200_launch_count.restype = C.c_uint64
+        lib.sb200_last_kernel_ms.argtypes = [C.c_void_p]; lib.sb200_last_kernel_ms.restype = C.c_float
+        lib.sb200_rx11a_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                          C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.sb200_rx11a_batch.restype = C.c_int
+        lib.sb200_viterbi_k7.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.sb200_viterbi_k7.restype = C.c_int
+        lib.sb200_rx11a_taps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                         C.c_void_p] + [C.c_void_p] * 6 + [C.c_uint64]
+        lib.sb200_rx11a_taps.restype = C.c_int
+        _lib = lib
+    return _lib
+
+def _ptr(a):
+    """numpy array -> host pointer; torch tensor / int -> raw (device or pinned) pointer."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+class Engine:
+    """One sb200 handle = one GPU context (BB11aDemodContext analogue: fb11ademod_config.hpp:20-123)."""
+    def __init__(self, device=0, cca_pwr_threshold=0):
+        lib = load_library()
+        cfg = (C.c_uint32 * 8)(cca_pwr_threshold, 0, 0, 0, 0, 0, 0, 0)
+        h = C.c_void_p()
+        rc = lib.sb200_create(device, C.cast(cfg, C.c_void_p), C.byref(h))
+        if rc != 0:
+            raise Sb200Error(f"sb200_create(device={device}) failed with {rc} (no CUDA device / no CPU fallback)")
+        self._h, self._lib, self.device = h, lib, device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sb200_destroy(self._h); self._h = None
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise Sb200Error(f"{what} failed ({rc}): {self._lib.sb200_last_error(self._h).decode()}")
+
+    @property
+    def launches(self):
+        return int(self._lib.sb200_launch_count(self._h))
+    def last_kernel_ms(self):
+        return float(self._lib.sb200_last_kernel_ms(self._h))
+
+    def rx11a_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
+        """Pointer-level call (host or device pointers), used by bench.py with torch buffers."""
+        self._check(self._lib.sb200_rx11a_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11a_batch")
+
+    def rx11a_batch(self, iq, frame_off, frame_len, out_stride=2560):
+        """iq: int16 [n,2] numpy; returns (results structured array [F], bytes uint8 [F, out_stride])."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32)
+        nf = len(off)
+        res = np.zeros(nf, dtype=RESULT_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+        self.rx11a_raw(_ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
+        return res, out
+
+    def rx11a_taps(self, iq, frame_off, frame_len, max_sym):
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32)
+        nf = len(off)
+        res = np.zeros(nf, dtype=RESULT_DTYPE)
+        fc = np.zeros((nf, 64, 2), np.int16); cc = np.zeros_like(fc)
+        fo = np.zeros((nf, max_sym, 64, 2), np.int16); eq = np.zeros_like(fo); tr = np.zeros_like(fo)
+        sstride = max_sym * 288
+        soft = np.zeros((nf, sstride), np.uint8)
+        self._check(self._lib.sb200_rx11a_taps(self._h, _ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, max_sym, _ptr(res),
+                                               _ptr(fc), _ptr(cc), _ptr(fo), _ptr(eq), _ptr(tr), _ptr(soft), sstride), "sb200_rx11a_taps")
+        return dict(res=res, freq_coeffs=fc, chan_coeffs=cc, fft_out=fo, equalized=eq, tracked=tr, soft=soft)
+
+    def viterbi_raw(self, soft_ptr, soft_stride, nsoft, nblocks, code_rate, frame_len, out_ptr, out_stride, depth=256, lookahead=24, stream=0):
+        self._check(self._lib.sb200_viterbi_k7(self._h, soft_ptr, soft_stride, nsoft, nblocks, code_rate, frame_len, depth, lookahead,
+                                               out_ptr, out_stride, stream), "sb200_viterbi_k7")
+
+    def viterbi_k7(self, soft, code_rate, frame_len_bytes, depth=256, lookahead=24):
+        """soft: uint8 [nblocks, nsoft]; returns uint8 [nblocks, frame_len_bytes+2] (SERVICE + PSDU, still scrambled)."""
+        soft = np.ascontiguousarray(soft, dtype=np.uint8)
+        nb, ns = soft.shape
+        out = np.zeros((nb, frame_len_bytes + 2), np.uint8)
+        self.viterbi_raw(_ptr(soft), ns, ns, nb, code_rate, frame_len_bytes, _ptr(out), frame_len_bytes + 2, depth, lookahead)
+        return out

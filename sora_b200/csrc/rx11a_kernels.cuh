@@ -1,0 +1,388 @@
+// sora_b200 — 802.11a receive kernels (sm_100a).
+//
+//   k_sync11a    one thread per capture slot: 2:1 decimation, DC removal/estimation and the STS carrier-sense
+//                state machine, up to the vector where the reference switches to the demod branch.
+//                Reference: samples.hpp:27-49 (TDownSample2), dc.hpp:48-166, cca.hpp:106-441 (TCCA11a),
+//                fb11a_demod.cpp:29-81 (per-28-sample-block error polling, CS-timeout reset).
+//   k_front11a   one warp per slot: LTS (fine CFO, FFT, channel estimate), then per OFDM symbol
+//                CP strip -> freq comp -> FFT64 -> equalise -> phase comp -> pilot track -> soft demap ->
+//                de-interleave; SIGNAL decoded in-warp (K=7 Viterbi, 24 steps) and parsed.
+//                Reference: channel_11a.hpp:34-230,534-653, fft.hpp:110-135, freqoffset.hpp:16-65,
+//                pilot.hpp:123-269, demapper11a.hpp:11-73, deinterleaver.hpp, viterbicore.h:36-261,
+//                PHY_11a.hpp:363-430,520-604.
+// Data layout: IQ is the caller's interleaved int16 (I,Q) stream, one 32-bit word per 40 Msps sample; the
+// 20 Msps stream is "every other word".  Soft bits leave this stage as one byte per coded bit (0..7),
+// N_CBPS per symbol, contiguous per frame, ready for viterbi_k7.cuh.
+#pragma once
+#include "tables.cuh"
+
+namespace sb {
+
+enum : uint32_t {
+    E_SUCCESS = 0, E_FRAME_OK = 1, E_FAILED = 0x8000FFFFu, E_PLCP_HEADER_FAIL = 0x80000005u,
+    E_CRC32_FAIL = 0x80000006u, E_CS_TIMEOUT = 0x80000007u, E_NO_FRAME = 0x8000F001u,
+};
+enum { CR_12 = 0, CR_23 = 1, CR_34 = 2 };
+
+struct FrameInfo {            // per-slot state handed from kernel to kernel (device memory)
+    uint32_t status;          // E_SUCCESS while decoding proceeds, else terminal code
+    uint32_t detect_vec;      // index of the first 20 Msps 4-sample vector routed to the demod branch
+    uint32_t rate_kbps, length, nsym_total, code_rate, ncbps;
+    uint32_t soft_bytes;      // deinterleaved soft values written for this frame
+    int32_t cfo_est; uint32_t peak_index;
+};
+
+__device__ __forceinline__ int d_uatan2(const DevTables& T, int y, int x) {       // intalg.h:96-108
+    unsigned ay = y > 0 ? (unsigned)y : 0u - (unsigned)y, ax = x > 0 ? (unsigned)x : 0u - (unsigned)x;
+    int ys = ay > 1 ? 31 - __clz(ay) : 0, xs = ax > 1 ? 31 - __clz(ax) : 0;
+    int shift = max(xs, ys) - 6;
+    if (shift > 0) { y >>= shift; x >>= shift; }
+    return (int)__ldg(&T.atan2_lut[((unsigned)y & 0xFF) * 256 + ((unsigned)x & 0xFF)]);
+}
+__device__ __forceinline__ cs16 d_rot(const DevTables& T, int th) {               // (ucos(th), -usin(th))
+    unsigned i = (unsigned)th & 0xFFFF;
+    return mk((int)__ldg(&T.cos_lut[i]), -(int)__ldg(&T.sin_lut[i]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// carrier sense
+// ------------------------------------------------------------------------------------------------
+struct CcaState {
+    uint32_t his[4][4];       // CMovingWindow<vcs,4> of (x - DC) >> 2, packed c16
+    int acr[4], aci[4], eng[4];
+    int his_idx, acc_i, acr_reg, aci_reg, eng_reg;
+    unsigned auto_count, sense_count, high_count; int sync_state, peak_corr, peak_index;
+    unsigned dc_cnt; int dc_sum_re, dc_sum_im;
+    __device__ void reset() {
+        for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) his[i][j] = 0; acr[i] = aci[i] = eng[i] = 0; }
+        his_idx = acc_i = 0; acr_reg = aci_reg = eng_reg = 0;
+        auto_count = sense_count = high_count = 0; sync_state = 0; peak_corr = 0; peak_index = 0;
+        dc_cnt = 8; dc_sum_re = dc_sum_im = 0;
+    }
+};
+
+__device__ __forceinline__ int cca_xcorr(const CcaState& s, const uint32_t* __restrict__ pat) {   // cca.hpp:196-213
+    int sre = 0, sim = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int slot = (s.his_idx + j) & 3;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int re, im; cmul_conj32(re, im, unpack(__ldg(pat + 4 * j + k)), unpack(s.his[slot][k]));
+            sre = wadd(sre, re); sim = wadd(sim, im);
+        }
+    }
+    return abs(sre) + abs(sim);
+}
+
+__global__ void __launch_bounds__(128) k_sync11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
+                                                  const uint32_t* __restrict__ len, uint32_t nframes, uint32_t cca_thr,
+                                                  DevTables T, FrameInfo* __restrict__ info) {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const uint32_t* x = iq + off[f];
+    const uint32_t nblk = len[f] / 28u;               // memsource.hpp:87: whole 28-sample source blocks only
+    const uint32_t nvec = nblk * 28u / 8u;
+    CcaState s; s.reset();
+    int dc_re = 0, dc_im = 0;                          // CF_VecDC, zero at Init
+    bool timeout = false; uint32_t cur_blk = 0; uint32_t detect = 0xFFFFFFFFu;
+    for (uint32_t v = 0; v < nvec; v++) {
+        uint32_t blk = (8u * v + 7u) / 28u;
+        if (blk != cur_blk) {                          // driver polls error_code once per source block (fb11a_demod.cpp:35-58)
+            if (timeout) { s.reset(); timeout = false; }
+            cur_blk = blk;
+        }
+        cs16 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = subw(unpack(__ldg(x + 8u * v + 2u * k)), mk(dc_re, dc_im));   // dc.hpp:48-85
+        if (s.sync_state == 0) {                       // cca.hpp:326-398
+            int sr = 0, si = 0, se = 0; uint32_t pk[4];
+            const int oldest = s.his_idx;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                cs16 q = sra(p[k], 2); pk[k] = pack(q);
+                int re, im; cmul_conj32(re, im, q, unpack(s.his[oldest][k]));
+                sr = wadd(sr, re >> 4); si = wadd(si, im >> 4);
+                se = wadd(se, wadd(q.re * q.re, q.im * q.im) >> 4);
+            }
+            int a = s.acc_i;
+            s.acr_reg = s.acr_reg + sr - s.acr[a]; s.acr[a] = sr;
+            s.aci_reg = s.aci_reg + si - s.aci[a]; s.aci[a] = si;
+            s.eng_reg = s.eng_reg + se - s.eng[a]; s.eng[a] = se;
+            s.acc_i = (a + 1) & 3;
+            int iAuto = abs(s.acr_reg) + abs(s.aci_reg), iEnergy = s.eng_reg;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s.his[oldest][k] = pk[k];
+            s.his_idx = (oldest + 1) & 3;
+            s.sense_count += 4;
+            if (iEnergy > (int)cca_thr && iAuto >= iEnergy - (iEnergy >> 3)) {
+                s.auto_count++; s.sense_count = 0;
+                if (s.auto_count >= 4) {               // establish_sync, cca.hpp:220-243
+                    int sum = 0; s.peak_corr = 0;
+                    for (int i = 0; i < 16; i++) {
+                        int c = cca_xcorr(s, T.sts + 16 * i);
+                        if (c > s.peak_corr) { s.peak_corr = c; s.peak_index = i; }
+                        sum += c;
+                    }
+                    if (s.peak_corr > (sum >> 3)) {
+                        s.sync_state = 1; s.high_count = 0;
+                        if (s.peak_index > 3) { s.high_count = (unsigned)(s.peak_index / 4); s.peak_index &= 3; }
+                    }
+                }
+            } else s.auto_count = 0;
+        } else {                                       // cca.hpp:399-418
+            const int oldest = s.his_idx;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s.his[oldest][k] = pack(sra(p[k], 2));
+            s.his_idx = (oldest + 1) & 3;
+            s.high_count++;
+            if ((s.high_count & 3) == 0) {
+                int c = cca_xcorr(s, T.sts + 16 * s.peak_index);     // check_sync, cca.hpp:245-263
+                if (c < (s.peak_corr >> 1)) {
+                    if (s.high_count > 8) { detect = v + 1; break; }
+                    s.sync_state = 0; s.sense_count = 0;
+                } else if (c > s.peak_corr) s.peak_corr = c;
+            }
+        }
+        if (s.sync_state == 0) {                       // TDCEstimator behind the energy gate (dc.hpp:101-166)
+            int hr = 0, hi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { hr += p[k].re >> 5; hi += p[k].im >> 5; }
+            s.dc_sum_re = sx16(s.dc_sum_re + sx16(hr)); s.dc_sum_im = sx16(s.dc_sum_im + sx16(hi));
+            if (s.dc_cnt == 0) {
+                dc_re = sx16(dc_re + (s.dc_sum_re >> 2)); dc_im = sx16(dc_im + (s.dc_sum_im >> 2));
+                s.dc_cnt = 8; s.dc_sum_re = s.dc_sum_im = 0;
+            }
+            s.dc_cnt--;
+            if (s.sense_count >= 84) timeout = true;   // cca.hpp:431-437
+        }
+    }
+    FrameInfo fi;
+    fi.status = detect == 0xFFFFFFFFu ? (uint32_t)E_NO_FRAME : (uint32_t)E_SUCCESS;
+    fi.detect_vec = detect; fi.rate_kbps = 6000; fi.length = 0; fi.nsym_total = 0; fi.code_rate = CR_12; fi.ncbps = 48;
+    fi.soft_bytes = 0; fi.cfo_est = 0; fi.peak_index = (uint32_t)s.peak_index;
+    info[f] = fi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-wide helpers for the per-symbol front end
+// ------------------------------------------------------------------------------------------------
+// 64-point fixed-point FFT on a warp-private 64-word shared buffer (packed c16), in place, natural-order
+// input -> bit-reversed storage (fft_r4dif.h:134-141; the caller reads bin i from slot bitrev6(i)).
+__device__ __forceinline__ void warp_fft64(uint32_t* x, const DevTables& T, int lane) {
+    __syncwarp();
+    if (lane < 16) {                                   // FFTSSE<64>: 16 radix-4 butterflies at stride 16
+        cs16 a = unpack(x[lane]), b = unpack(x[lane + 16]), c = unpack(x[lane + 32]), d = unpack(x[lane + 48]);
+        r4_butterfly(a, b, c, d, unpack(__ldg(T.tw64 + lane)), unpack(__ldg(T.tw64 + 16 + lane)), unpack(__ldg(T.tw64 + 32 + lane)));
+        x[lane] = pack(a); x[lane + 16] = pack(b); x[lane + 32] = pack(c); x[lane + 48] = pack(d);
+    }
+    __syncwarp();
+    if (lane < 16) {                                   // 4 x FFTSSE<16>: stride 4 inside each quarter
+        int base = (lane >> 2) * 16, fidx = lane & 3;
+        cs16 a = unpack(x[base + fidx]), b = unpack(x[base + fidx + 4]), c = unpack(x[base + fidx + 8]), d = unpack(x[base + fidx + 12]);
+        r4_butterfly(a, b, c, d, unpack(__ldg(T.tw16 + fidx)), unpack(__ldg(T.tw16 + 4 + fidx)), unpack(__ldg(T.tw16 + 8 + fidx)));
+        x[base + fidx] = pack(a); x[base + fidx + 4] = pack(b); x[base + fidx + 8] = pack(c); x[base + fidx + 12] = pack(d);
+    }
+    __syncwarp();
+    if (lane < 16) {                                   // 16 x FFTSSEEx<4>
+        cs16 a = unpack(x[4 * lane]), b = unpack(x[4 * lane + 1]), c = unpack(x[4 * lane + 2]), d = unpack(x[4 * lane + 3]);
+        dft4(a, b, c, d);
+        x[4 * lane] = pack(a); x[4 * lane + 1] = pack(b); x[4 * lane + 2] = pack(c); x[4 * lane + 3] = pack(d);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int bitrev6(int i) { return (int)(__brev((unsigned)i) >> 26); }
+
+// SIGNAL-field Viterbi, one warp: lane l owns the butterfly (l, l+32) -> (2l, 2l+1).  uint8 metrics with the
+// reference's wrap/mark/min/normalise rules (viterbicore.h:36-261).  `soft` = 48 deinterleaved values in shared.
+__device__ __forceinline__ uint32_t warp_viterbi_signal(const uint8_t* soft, int lane) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int cA = ((lane >> 1) ^ (lane >> 2) ^ (lane >> 4)) & 1;          // 133o taps on the predecessor bits
+    const int cB = (lane ^ (lane >> 1) ^ (lane >> 2)) & 1;                 // 171o
+    int m0 = lane == 0 ? 0x00 : 0x30, m1 = 0x30;                           // viterbilut.h:22-32
+    uint32_t decE[24], decO[24];
+#pragma unroll
+    for (int t = 0; t < 24; t++) {
+        int tA = 2 * soft[2 * t], tB = 2 * soft[2 * t + 1];
+        int alpha = (cA ? 14 - tA : tA) + (cB ? 14 - tB : tB), beta = 28 - alpha;
+        int n0 = min((m0 + alpha) & 0xFE, ((m1 + beta) & 0xFF) | 1);
+        int n1 = min((m0 + beta) & 0xFE, ((m1 + alpha) & 0xFF) | 1);
+        decE[t] = __ballot_sync(FULL, n0 & 1); decO[t] = __ballot_sync(FULL, n1 & 1);
+        int w = n0 | (n1 << 8);
+        int wa = __shfl_sync(FULL, w, lane >> 1), wb = __shfl_sync(FULL, w, 16 + (lane >> 1));
+        int sh = 8 * (lane & 1);
+        m0 = (wa >> sh) & 0xFF; m1 = (wb >> sh) & 0xFF;
+        if (((t + 1) & 7) == 0) {
+            int mn = __reduce_min_sync(FULL, min(m0, m1)) & 0xFE;
+            m0 = (m0 - mn) & 0xFF; m1 = (m1 - mn) & 0xFF;
+        }
+    }
+    // the extra normalise before the traceback (viterbicore.h:176-188) only subtracts a constant: order unchanged
+    unsigned key = min(((unsigned)m0 << 8) | ((unsigned)lane << 2), ((unsigned)m1 << 8) | ((unsigned)(lane + 32) << 2));
+    key = __reduce_min_sync(FULL, key);
+    int pos = (int)(key >> 2) & 0x7F;
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 24; i++) {                     // viterbicore.h:244-260; bit i of the result is time 23-i
+        word |= (uint32_t)((pos >> 6) & 1) << (23 - i);
+        pos = (pos >> 1) & 0x3F;
+        int col = 23 - i;                              // decisions of column `col` (1-based col = t+1 -> index t), column 0 = init (all even)
+        int bit = 0;
+        if (col >= 1) { uint32_t wsel = (pos & 1) ? decO[col - 1] : decE[col - 1]; bit = (wsel >> (pos >> 1)) & 1; }
+        pos |= bit << 6;
+    }
+    return word >> 6;                                  // viterbi.hpp:39
+}
+
+// ------------------------------------------------------------------------------------------------
+// front end: one warp per slot
+// ------------------------------------------------------------------------------------------------
+struct FrontTaps {            // optional stage taps (device pointers, nullptr = off); per slot, per symbol, 64 packed c16
+    uint32_t* freq_coeffs; uint32_t* chan_coeffs; uint32_t* fft_out; uint32_t* equalized; uint32_t* tracked; uint32_t max_sym;
+};
+
+__device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 subcarrier order; -1 for non-data bins
+    if (bin >= 38) { if (bin == 43 || bin == 57) return -1; return bin - 38 - (bin > 43) - (bin > 57); }
+    if (bin >= 1 && bin <= 26) { if (bin == 7 || bin == 21) return -1; return 24 + bin - 1 - (bin > 7) - (bin > 21); }
+    return -1;
+}
+
+#define SB_FRONT_WARPS 4
+__global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
+        const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, FrameInfo* __restrict__ info,
+        uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps) {
+    __shared__ uint32_t s_fft[SB_FRONT_WARPS][64];
+    __shared__ uint8_t s_soft[SB_FRONT_WARPS][288];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t f = blockIdx.x * SB_FRONT_WARPS + wib;
+    if (f >= nframes) return;
+    FrameInfo fi = info[f];
+    if (fi.status != E_SUCCESS) return;
+    uint32_t* xb = s_fft[wib]; uint8_t* sb = s_soft[wib];
+    const uint32_t* x = iq + off[f];
+    const uint32_t nvec = (len[f] / 28u) * 28u / 8u;
+    const uint32_t s0 = fi.detect_vec * 4u;            // first 20 Msps sample of the 144-sample LTS block
+    // ---- T11aLTS ---------------------------------------------------------------------------------
+    if (fi.detect_vec + 36u > nvec) { if (lane == 0) info[f].status = E_NO_FRAME; return; }
+    const int b0 = lane, b1 = lane + 32;               // this lane's two FFT bins / time samples
+    cs16 l0 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b0))), 1), l1 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b1))), 1);   // LTS1 >> 1
+    cs16 h0 = unpack(__ldg(x + 2u * (s0 + 72u + b0))), h1 = unpack(__ldg(x + 2u * (s0 + 72u + b1)));                 // LTS2 (unshifted)
+    {   // FreqOffsetEstimate<16> (dspalg.hpp:227-243): per 4-sample vector sum of (x >> 5), then summed over vectors
+        int re0, im0, re1, im1; cmul_conj32(re0, im0, h0, l0); cmul_conj32(re1, im1, h1, l1);
+        int sr = wadd(re0 >> 5, re1 >> 5), si = wadd(im0 >> 5, im1 >> 5);
+        for (int o = 16; o; o >>= 1) { sr = wadd(sr, __shfl_xor_sync(FULL, sr, o)); si = wadd(si, __shfl_xor_sync(FULL, si, o)); }
+        int arg = d_uatan2(T, si, sr);
+        fi.cfo_est = (int)(short)(((uint32_t)arg) / 64u);                  // short / size_t (dspalg.hpp:242)
+    }
+    const cs16 fc0 = d_rot(T, fi.cfo_est * b0), fc1 = d_rot(T, fi.cfo_est * b1);   // dspalg.hpp:201-208 (phase accumulates mod 2^16)
+    xb[b0] = pack(cmul_q15(l0, fc0)); xb[b1] = pack(cmul_q15(l1, fc1));
+    warp_fft64(xb, T, lane);
+    cs16 ch0, ch1;
+    {   // channel_11a.hpp:124-171: H^-1 = (+-1600 conj(Y)) / (|Y|^2 >> 8), C integer division
+        cs16 y0 = unpack(xb[bitrev6(b0)]), y1 = unpack(xb[bitrev6(b1)]);
+        auto inv = [&](cs16 y, int bin) -> cs16 {
+            if (bin >= 28 && bin <= 35) return mk(0, 0);
+            int e = wadd(y.re * y.re, y.im * y.im) >> 8;
+            int L = __ldg(T.lts_pos + bin) ? 1600 : -1600;
+            int re, im; cmul_conj32(re, im, mk(L, 0), y);
+            return e ? mk(sx16(re / e), sx16(im / e)) : mk(0, 0);
+        };
+        ch0 = inv(y0, b0); ch1 = inv(y1, b1);
+    }
+    if (taps.freq_coeffs) { taps.freq_coeffs[(size_t)f * 64 + b0] = pack(fc0); taps.freq_coeffs[(size_t)f * 64 + b1] = pack(fc1);
+                            taps.chan_coeffs[(size_t)f * 64 + b0] = pack(ch0); taps.chan_coeffs[(size_t)f * 64 + b1] = pack(ch1); }
+    // ---- symbols -----------------------------------------------------------------------------------
+    const int k0 = b0, k1 = b1 - 64;                   // signed subcarrier numbers of this lane's bins
+    const bool v0 = (k0 >= 1 && k0 <= 26), v1 = (k1 >= -26 && k1 <= -1);
+    const bool z0 = (b0 >= 28), z1 = (b1 <= 35);       // bins 28..35 (SSE vectors 7,8) are forced to zero
+    const int d0 = data_index(b0), d1 = data_index(b1);
+    cs16 comp0 = mk(0x7fff, 0), comp1 = mk(0x7fff, 0);
+    int CFO_comp = 0, SFO_comp = 0, CFO_tr = 0, SFO_tr = 0; unsigned symbol_count = 127;
+    int plcp_data = 0; uint32_t remain = 0; uint32_t soft_bytes = 0; int nbpsc = 1;
+    uint8_t* sout = soft_out + (size_t)f * soft_stride;
+    uint32_t status = E_SUCCESS;
+    for (uint32_t sym = 0;; sym++) {
+        const uint32_t sbeg = s0 + 144u + 80u * sym;
+        if ((sbeg + 80u) / 4u > nvec) { status = E_NO_FRAME; break; }      // slot exhausted before the symbol completed
+        cs16 a0 = sra(unpack(__ldg(x + 2u * (sbeg + 8u + b0))), 1), a1 = sra(unpack(__ldg(x + 2u * (sbeg + 8u + b1))), 1);
+        xb[b0] = pack(cmul_q15(a0, fc0)); xb[b1] = pack(cmul_q15(a1, fc1));          // channel_11a.hpp:640-641
+        warp_fft64(xb, T, lane);
+        cs16 F0 = unpack(xb[bitrev6(b0)]), F1 = unpack(xb[bitrev6(b1)]);
+        __syncwarp();
+        cs16 E0 = mk(0, 0), E1 = mk(0, 0);
+        if (!z0) { int re, im; cmul32(re, im, F0, ch0); E0 = mk(sx16(re >> 8), sx16(im >> 8)); }   // channel_11a.hpp:551-579
+        if (!z1) { int re, im; cmul32(re, im, F1, ch1); E1 = mk(sx16(re >> 8), sx16(im >> 8)); }
+        cs16 C0 = cmul_q15(E0, comp0), C1 = cmul_q15(E1, comp1);                      // freqoffset.hpp:28-30
+        // pilot.hpp:168-232
+        int th = 0;
+        if (lane == 11) th = d_uatan2(T, C1.im, C1.re);            // bin 43 = -21
+        if (lane == 25) th = d_uatan2(T, C1.im, C1.re);            // bin 57 = -7
+        if (lane == 7)  th = d_uatan2(T, C0.im, C0.re);            // bin 7
+        if (lane == 21) th = d_uatan2(T, -C0.im, -C0.re);          // bin 21 (pilot sent negated)
+        if (__ldg(T.pilot_neg + symbol_count)) th = sx16(th + 0x8000);
+        int th1 = __shfl_sync(FULL, th, 11), th2 = __shfl_sync(FULL, th, 25), th3 = __shfl_sync(FULL, th, 7), th4 = __shfl_sync(FULL, th, 21);
+        symbol_count++; if (symbol_count >= 127) symbol_count = 0;
+        int avg = sx16((th1 + th2 + th3 + th4) / 4);
+        int del = sx16(((th3 - th1) / 28 + (th4 - th2) / 28) >> 1);
+        cs16 R0 = mk(0, 0), R1 = mk(0, 0);
+        if (!z0) R0 = cmul_q15(C0, v0 ? d_rot(T, avg + k0 * del) : mk(0, 0));
+        if (!z1) R1 = cmul_q15(C1, v1 ? d_rot(T, avg + k1 * del) : mk(0, 0));
+        CFO_tr = sx16(CFO_tr + (avg >> 2)); SFO_tr = sx16(SFO_tr + (del >> 2));
+        CFO_comp = sx16(CFO_comp + avg + CFO_tr); SFO_comp = sx16(SFO_comp + del + SFO_tr);
+        if (v0) comp0 = d_rot(T, CFO_comp + k0 * SFO_comp);
+        if (v1) comp1 = d_rot(T, CFO_comp + k1 * SFO_comp);
+        if (taps.fft_out && sym < taps.max_sym) {
+            size_t o = ((size_t)f * taps.max_sym + sym) * 64;
+            taps.fft_out[o + b0] = pack(F0); taps.fft_out[o + b1] = pack(F1);
+            taps.equalized[o + b0] = pack(E0); taps.equalized[o + b1] = pack(E1);
+            taps.tracked[o + b0] = pack(R0); taps.tracked[o + b1] = pack(R1);
+        }
+        // soft demap + de-interleave into shared (demapper.h:141-151 limit, LUTs; deinterleaver.hpp)
+        const int ncbps = 48 * nbpsc;
+        const uint16_t* inv = inv_deint + (nbpsc == 1 ? 0 : nbpsc == 2 ? 48 : nbpsc == 4 ? 144 : 336);
+        auto demap = [&](cs16 r, int d) {
+            if (d < 0) return;
+            unsigned re = (unsigned)min(max(r.re >> 4, -128), 127) & 0xFF, im = (unsigned)min(max(r.im >> 4, -128), 127) & 0xFF;
+            const uint8_t* L0 = T.demap;
+            int j = d * nbpsc;
+            if (nbpsc == 1) { sb[__ldg(inv + j)] = __ldg(L0 + re); }
+            else if (nbpsc == 2) { sb[__ldg(inv + j)] = __ldg(L0 + re); sb[__ldg(inv + j + 1)] = __ldg(L0 + im); }
+            else if (nbpsc == 4) { sb[__ldg(inv + j)] = __ldg(L0 + re); sb[__ldg(inv + j + 1)] = __ldg(L0 + 256 + re);
+                                   sb[__ldg(inv + j + 2)] = __ldg(L0 + im); sb[__ldg(inv + j + 3)] = __ldg(L0 + 256 + im); }
+            else { sb[__ldg(inv + j)] = __ldg(L0 + re); sb[__ldg(inv + j + 1)] = __ldg(L0 + 512 + re); sb[__ldg(inv + j + 2)] = __ldg(L0 + 768 + re);
+                   sb[__ldg(inv + j + 3)] = __ldg(L0 + im); sb[__ldg(inv + j + 4)] = __ldg(L0 + 512 + im); sb[__ldg(inv + j + 5)] = __ldg(L0 + 768 + im); }
+        };
+        demap(R0, d0); demap(R1, d1);
+        __syncwarp();
+        if (!plcp_data) {                              // PHY_11a.hpp:520-604
+            uint32_t sig = warp_viterbi_signal(sb, lane) & 0xFFFFFFu;
+            bool ok = !(sig & 0xFC0010u);
+            uint32_t par = (sig >> 16) ^ sig; par ^= par >> 8; par ^= par >> 4; par ^= par >> 2; par ^= par >> 1;
+            ok = ok && !(par & 1);
+            uint32_t rate = 0; int nd = 0, nb = 1, cr = CR_12;
+            switch (sig & 0xF) {                       // ieee80211a_cmn.h:97-157
+                case 0xB: rate = 6000; nd = 24; nb = 1; cr = CR_12; break;   case 0xF: rate = 9000; nd = 36; nb = 1; cr = CR_34; break;
+                case 0xA: rate = 12000; nd = 48; nb = 2; cr = CR_12; break;  case 0xE: rate = 18000; nd = 72; nb = 2; cr = CR_34; break;
+                case 0x9: rate = 24000; nd = 96; nb = 4; cr = CR_12; break;  case 0xD: rate = 36000; nd = 144; nb = 4; cr = CR_34; break;
+                case 0x8: rate = 48000; nd = 192; nb = 6; cr = CR_23; break; case 0xC: rate = 54000; nd = 216; nb = 6; cr = CR_34; break;
+                default: ok = false;
+            }
+            uint32_t L = (sig >> 5) & 0xFFF;
+            if (ok && rate) { fi.rate_kbps = rate; fi.code_rate = cr; }
+            if (ok) { fi.length = L; ok = L <= 2500; }
+            if (!ok) { status = E_PLCP_HEADER_FAIL; break; }
+            fi.nsym_total = (L * 8 + 16 + 6 + nd - 1) / nd + 1;
+            remain = fi.nsym_total; plcp_data = 1; nbpsc = nb; fi.ncbps = 48 * nb;
+        } else {
+            for (int i = lane * 4; i < ncbps; i += 128) *(uint32_t*)(sout + soft_bytes + i) = *(const uint32_t*)(sb + i);
+            soft_bytes += ncbps;
+        }
+        __syncwarp();
+        remain--;
+        if (remain == 0) break;
+    }
+    if (lane == 0) { fi.status = status; fi.soft_bytes = soft_bytes; info[f] = fi; }
+}
+
+} // namespace sb

@@ -1,0 +1,266 @@
+// sora_b200 — host side of the C ABI (include/sora_b200.h): workspaces, table upload, kernel launches.
+// Single translation unit: the kernels live in the .cuh files included below.
+#include "../../include/sora_b200.h"
+#include "viterbi_k7.cuh"
+#include <string>
+#include <new>
+#include <stdio.h>
+
+using namespace sb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+__global__ void k_pack_results(const FrameInfo* __restrict__ info, const uint32_t* __restrict__ status,
+                               const uint32_t* __restrict__ crc, uint32_t n, sb200_frame_result* __restrict__ res) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FrameInfo fi = info[i];
+    sb200_frame_result r;
+    r.status = status[i]; r.rate_kbps = fi.rate_kbps; r.length = fi.length; r.crc32 = crc[i]; r.nsym = fi.nsym_total;
+    r.detect_index = fi.detect_vec == 0xFFFFFFFFu ? 0u : fi.detect_vec * 4u;
+    r.cfo_est = (int16_t)fi.cfo_est; r.peak_index = (uint16_t)fi.peak_index;
+    res[i] = r;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+} // namespace
+
+struct sb200_handle {
+    int device = 0;
+    uint32_t cca_thr = 1000 * 1000;
+    DevTables T{};
+    DevBuf tab, iq, off, len, info, soft, out, status, crc, res, taps[5];
+    uint16_t* inv_deint = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+    std::string err;
+    int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+        err = what; if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
+        return code;
+    }
+};
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return h->fail(SB200_E_CUDA, #call, _e); } while (0)
+
+static int upload_tables(sb200_handle* h) {
+    HostTables* H = new (std::nothrow) HostTables();
+    if (!H) return h->fail(SB200_E_NOMEM, "host tables");
+    build_host_tables(*H);
+    uint16_t inv[624];
+    const int offs[4] = {0, 48, 144, 336}, n[4] = {48, 96, 192, 288};
+    for (int m = 0; m < 4; m++) for (int k = 0; k < n[m]; k++) inv[offs[m] + H->deint[offs[m] + k]] = (uint16_t)k;
+    // one arena, 256-byte aligned slices
+    size_t o = 0; auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    size_t o_sin = take(131072), o_cos = take(131072), o_at = take(131072), o_tw64 = take(sizeof H->tw64), o_tw16 = take(sizeof H->tw16),
+           o_sts = take(sizeof H->sts), o_deint = take(sizeof H->deint), o_inv = take(sizeof inv), o_demap = take(sizeof H->demap),
+           o_pil = take(128), o_lts = take(64), o_scr = take(128), o_crc = take(1024);
+    cudaError_t e = h->tab.need(o);
+    if (e != cudaSuccess) { delete H; return h->fail(SB200_E_NOMEM, "cudaMalloc tables", e); }
+    char* base = (char*)h->tab.p;
+    auto up = [&](size_t off, const void* src, size_t bytes) { return cudaMemcpy(base + off, src, bytes, cudaMemcpyHostToDevice); };
+    e = up(o_sin, H->sin_lut.data(), 131072);
+    if (e == cudaSuccess) e = up(o_cos, H->cos_lut.data(), 131072);
+    if (e == cudaSuccess) e = up(o_at, H->atan2_lut.data(), 131072);
+    if (e == cudaSuccess) e = up(o_tw64, H->tw64, sizeof H->tw64);
+    if (e == cudaSuccess) e = up(o_tw16, H->tw16, sizeof H->tw16);
+    if (e == cudaSuccess) e = up(o_sts, H->sts, sizeof H->sts);
+    if (e == cudaSuccess) e = up(o_deint, H->deint, sizeof H->deint);
+    if (e == cudaSuccess) e = up(o_inv, inv, sizeof inv);
+    if (e == cudaSuccess) e = up(o_demap, H->demap, sizeof H->demap);
+    if (e == cudaSuccess) e = up(o_pil, H->pilot_neg, 128);
+    if (e == cudaSuccess) e = up(o_lts, H->lts_pos, 64);
+    if (e == cudaSuccess) e = up(o_scr, H->scramble, 128);
+    if (e == cudaSuccess) e = up(o_crc, H->crc32, 1024);
+    delete H;
+    if (e != cudaSuccess) return h->fail(SB200_E_CUDA, "table upload", e);
+    DevTables& T = h->T;
+    T.sin_lut = (const int16_t*)(base + o_sin); T.cos_lut = (const int16_t*)(base + o_cos); T.atan2_lut = (const int16_t*)(base + o_at);
+    T.tw64 = (const uint32_t*)(base + o_tw64); T.tw16 = (const uint32_t*)(base + o_tw16); T.sts = (const uint32_t*)(base + o_sts);
+    T.deint = (const uint16_t*)(base + o_deint); T.demap = (const uint8_t*)(base + o_demap); T.pilot_neg = (const uint8_t*)(base + o_pil);
+    T.lts_pos = (const uint8_t*)(base + o_lts); T.scramble = (const uint8_t*)(base + o_scr); T.crc32 = (const uint32_t*)(base + o_crc);
+    h->inv_deint = (uint16_t*)(base + o_inv);
+    return SB200_OK;
+}
+
+extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out) {
+    if (!out) return SB200_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return SB200_E_NODEVICE; }
+    sb200_handle* h = new (std::nothrow) sb200_handle();
+    if (!h) return SB200_E_NOMEM;
+    h->device = device;
+    if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
+    int rc = upload_tables(h);
+    if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
+    if (rc != SB200_OK) { sb200_destroy(h); return rc; }
+    *out = h;
+    return SB200_OK;
+}
+
+extern "C" void sb200_destroy(sb200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
+                     &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
+    for (DevBuf* b : all) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+extern "C" const char* sb200_last_error(const sb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" uint64_t sb200_launch_count(const sb200_handle* h) { return h ? h->launches : 0; }
+extern "C" float sb200_last_kernel_ms(sb200_handle* h) {
+    if (!h || !h->timed) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+// shared body of sb200_rx11a_batch / sb200_rx11a_taps
+static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                     uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, cudaStream_t st,
+                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride) {
+    if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (nframes == 0) return SB200_OK;
+    CK(cudaSetDevice(h->device));
+    // slot table (host copy needed for sizing; a device-resident table is copied back once)
+    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len);
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+        if (lenh[i] > max_len) max_len = lenh[i];
+    }
+    const uint32_t* d_iq;
+    if (is_device_ptr(iq)) d_iq = (const uint32_t*)iq;
+    else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
+    const uint64_t* d_off; const uint32_t* d_len;
+    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
+    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
+    // workspaces
+    const uint64_t max_sym = (max_len / 2u) / 80u + 1u;
+    const uint64_t soft_stride = ((max_sym * 288ull) + 15ull) & ~15ull;
+    const uint64_t row = 2560;                         // >= 2500 (MTU, PHY_11a.hpp:571) + SERVICE
+    CK(h->info.need(nframes * sizeof(FrameInfo)));
+    CK(h->soft.need(nframes * soft_stride));
+    CK(h->out.need(nframes * row));
+    CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result)));
+    FrameInfo* d_info = (FrameInfo*)h->info.p;
+    CK(cudaEventRecord(h->ev0, st));
+    k_sync11a<<<(nframes + 127) / 128, 128, 0, st>>>(d_iq, d_off, d_len, nframes, h->cca_thr, h->T, d_info);
+    k_front11a<<<(nframes + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, st>>>(d_iq, d_off, d_len, nframes, h->T, d_info,
+            (uint8_t*)h->soft.p, soft_stride, h->inv_deint, taps);
+    VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
+    k_viterbi_k7<<<(nframes + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T,
+            (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    const bool res_dev = is_device_ptr(res);
+    sb200_frame_result* d_res = res_dev ? res : (sb200_frame_result*)h->res.p;
+    k_pack_results<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->launches += 4;
+    CK(cudaGetLastError());
+    bool host_out = false;
+    if (out_bytes && out_stride) {
+        const size_t w = out_stride < row ? out_stride : row;
+        const bool od = is_device_ptr(out_bytes);
+        CK(cudaMemcpy2DAsync(out_bytes, out_stride, h->out.p, row, w, nframes, od ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        host_out |= !od;
+    }
+    if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nframes * sizeof(sb200_frame_result), cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (host_out) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+extern "C" int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples, const uint64_t* frame_off,
+                                 const uint32_t* frame_len, uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride,
+                                 sb200_frame_result* res, void* cuda_stream) {
+    FrontTaps taps{};
+    return rx11a_run(h, iq, iq_total_samples, frame_off, frame_len, nframes, out_bytes, out_stride, res, (cudaStream_t)cuda_stream, taps, nullptr, 0);
+}
+
+extern "C" int sb200_rx11a_taps(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples, const uint64_t* frame_off,
+                                const uint32_t* frame_len, uint32_t nframes, uint32_t max_sym, sb200_frame_result* res,
+                                int16_t* freq_coeffs, int16_t* chan_coeffs, int16_t* fft_out, int16_t* equalized, int16_t* tracked,
+                                uint8_t* soft, uint64_t soft_stride) {
+    if (!h) return SB200_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const size_t c = (size_t)nframes * 64 * 4, s = (size_t)nframes * max_sym * 64 * 4;
+    CK(h->taps[0].need(c)); CK(h->taps[1].need(c)); CK(h->taps[2].need(s ? s : 4)); CK(h->taps[3].need(s ? s : 4)); CK(h->taps[4].need(s ? s : 4));
+    for (int i = 0; i < 5; i++) CK(cudaMemset(h->taps[i].p, 0, i < 2 ? c : (s ? s : 4)));
+    FrontTaps taps{};
+    taps.freq_coeffs = (uint32_t*)h->taps[0].p; taps.chan_coeffs = (uint32_t*)h->taps[1].p;
+    taps.fft_out = (uint32_t*)h->taps[2].p; taps.equalized = (uint32_t*)h->taps[3].p; taps.tracked = (uint32_t*)h->taps[4].p; taps.max_sym = max_sym;
+    int rc = rx11a_run(h, iq, iq_total_samples, frame_off, frame_len, nframes, nullptr, 0, res, 0, taps, soft, soft_stride);
+    if (rc != SB200_OK) return rc;
+    CK(cudaDeviceSynchronize());
+    if (freq_coeffs) CK(cudaMemcpy(freq_coeffs, h->taps[0].p, c, cudaMemcpyDeviceToHost));
+    if (chan_coeffs) CK(cudaMemcpy(chan_coeffs, h->taps[1].p, c, cudaMemcpyDeviceToHost));
+    if (fft_out && s) CK(cudaMemcpy(fft_out, h->taps[2].p, s, cudaMemcpyDeviceToHost));
+    if (equalized && s) CK(cudaMemcpy(equalized, h->taps[3].p, s, cudaMemcpyDeviceToHost));
+    if (tracked && s) CK(cudaMemcpy(tracked, h->taps[4].p, s, cudaMemcpyDeviceToHost));
+    return SB200_OK;
+}
+
+extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t soft_stride, uint32_t nsoft, uint32_t nblocks,
+                                int code_rate, uint32_t frame_len_bytes, uint32_t depth, uint32_t lookahead,
+                                uint8_t* out, uint64_t out_stride, void* cuda_stream) {
+    if (!h || !soft || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (code_rate < 0 || code_rate > 2 || depth == 0 || (depth & 7) || depth + lookahead + 24 > SB_VIT_RING - 8 || depth > 320)
+        return h->fail(SB200_E_INVALID, "unsupported code_rate/depth/lookahead");
+    if (soft_stride < nsoft || out_stride < frame_len_bytes + 2ull) return h->fail(SB200_E_INVALID, "stride too small");
+    if (nblocks == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    const uint8_t* d_soft; uint64_t d_stride = soft_stride;
+    const bool aligned = ((uintptr_t)soft & 15) == 0 && (soft_stride & 15) == 0;
+    if (is_device_ptr(soft) && aligned) d_soft = soft;
+    else {
+        d_stride = ((uint64_t)nsoft + 15ull) & ~15ull;
+        CK(h->soft.need(nblocks * d_stride + 16));
+        CK(cudaMemcpy2DAsync(h->soft.p, d_stride, soft, soft_stride, nsoft, nblocks, is_device_ptr(soft) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        d_soft = (const uint8_t*)h->soft.p;
+    }
+    const bool od = is_device_ptr(out);
+    uint8_t* d_out = out; uint64_t d_ostride = out_stride;
+    if (!od) { d_ostride = (frame_len_bytes + 2ull + 15ull) & ~15ull; CK(h->out.need(nblocks * d_ostride)); d_out = (uint8_t*)h->out.p; }
+    CK(h->status.need(nblocks * 4ull)); CK(h->crc.need(nblocks * 4ull));
+    VitJob job{}; job.code_rate = (uint32_t)code_rate; job.frame_len = frame_len_bytes; job.nsoft = nsoft; job.depth = depth; job.lookahead = lookahead; job.raw = 1;
+    CK(cudaEventRecord(h->ev0, st));
+    k_viterbi_k7<<<(nblocks + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T,
+            d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->launches += 1;
+    CK(cudaGetLastError());
+    if (!od) {
+        CK(cudaMemcpy2DAsync(out, out_stride, d_out, d_ostride, frame_len_bytes + 2ull, nblocks, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return SB200_OK;
+}

@@ -1,0 +1,186 @@
+"""Synthetic 802.11a PPDU generator (numpy, float IFFT) in the reference's amplitude convention.
+
+Test/bench infrastructure: produces int16 interleaved IQ at 40 Msps exactly shaped like the output of the
+reference's offline modulator after `ConvertModFile2DumpFile_8b`:
+  * pre-IFFT BPSK amplitude 10720, QPSK/16/64-QAM scaled by 1/sqrt(2,10,42)   (Brick11/src/mapper11a.hpp:8-11)
+  * 128-point IFFT (2x oversampled), result / 16                                (Brick11/src/fft.hpp:51-58)
+  * saturate to int8, then << 8 into COMPLEX16                                  (brick/inc/stdbrick.hpp:437, demod11/modulate11a.cpp:178-179)
+  * STS amplitude 1.472 x BPSK, LTS = BPSK amplitude                            (Brick11/src/preamble11a.hpp:15-16)
+The bit pipeline is 802.11a-1999 clause 17 (scramble x^7+x^4+1, K=7 133/171, puncture, interleave, Gray map, pilots).
+It is a float modulator, not a restatement of the reference's fixed-point TX, so it never serves as a parity oracle —
+only as an input source; parity is always GPU-vs-oracle on the same IQ.
+"""
+import numpy as np
+import zlib
+
+RATES = {  # kbps: (rate bits R1-R4 as SIGNAL[3:0] value, N_BPSC, coding 'num/den', N_DBPS)
+    6000: (0xB, 1, (1, 2), 24), 9000: (0xF, 1, (3, 4), 36), 12000: (0xA, 2, (1, 2), 48), 18000: (0xE, 2, (3, 4), 72),
+    24000: (0x9, 4, (1, 2), 96), 36000: (0xD, 4, (3, 4), 144), 48000: (0x8, 6, (2, 3), 192), 54000: (0xC, 6, (3, 4), 216),
+}
+BPSK_MOD = 10720
+KMOD = {1: 10720, 2: int(10720 / 1.414), 4: int(10720 / 3.162), 6: int(10720 / 6.481)}
+_LTS = np.array([1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,0,
+                 1,-1,-1,1,1,-1,1,-1,1,-1,-1,-1,-1,-1,1,1,-1,-1,1,-1,1,-1,1,1,1,1], dtype=np.float64)
+
+def scrambler_seq(seed, n):
+    """seed: 7-bit initial state, bit6 = x7 ... bit0 = x1.  Returns n output bits."""
+    st = seed & 0x7F
+    out = np.zeros(127, np.uint8)
+    for i in range(127):
+        b = ((st >> 6) ^ (st >> 3)) & 1
+        st = ((st << 1) | b) & 0x7F
+        out[i] = b
+    return np.resize(out, n)
+
+_PILOT_POL = 1 - 2 * scrambler_seq(0x7F, 127).astype(np.int64)   # p_0..p_126
+
+def interleave_map(ncbps, nbpsc):
+    s = max(nbpsc // 2, 1)
+    k = np.arange(ncbps)
+    i = (ncbps // 16) * (k % 16) + k // 16
+    return s * (i // s) + (i + ncbps - (16 * i) // ncbps) % s      # j = position on air of coded bit k
+
+def conv_encode(bits):
+    """bits [..., n] uint8 -> (A, B) each [..., n]; encoder starts from the all-zero state."""
+    pad = np.zeros(bits.shape[:-1] + (6,), np.uint8)
+    x = np.concatenate([pad, bits], -1)
+    n = bits.shape[-1]
+    d = lambda k: x[..., 6 - k: 6 - k + n]
+    A = d(0) ^ d(2) ^ d(3) ^ d(5) ^ d(6)
+    B = d(0) ^ d(1) ^ d(2) ^ d(3) ^ d(6)
+    return A, B
+
+def puncture(A, B, rate):
+    n = A.shape[-1]
+    if rate == (1, 2):
+        return np.stack([A, B], -1).reshape(A.shape[:-1] + (2 * n,))
+    if rate == (3, 4):
+        a = A.reshape(A.shape[:-1] + (n // 3, 3)); b = B.reshape(B.shape[:-1] + (n // 3, 3))
+        return np.stack([a[..., 0], b[..., 0], a[..., 1], b[..., 2]], -1).reshape(A.shape[:-1] + (n // 3 * 4,))
+    a = A.reshape(A.shape[:-1] + (n // 2, 2)); b = B.reshape(B.shape[:-1] + (n // 2, 2))
+    return np.stack([a[..., 0], b[..., 0], a[..., 1]], -1).reshape(A.shape[:-1] + (n // 2 * 3,))
+
+_GRAY = {1: np.array([-1, 1.]), 2: np.array([-3, 3, -1, 1.]),  # index = b0 | b1<<1 ... (first bit in LSB)
+         3: np.array([-7, 7, -1, 1, -5, 5, -3, 3.])}
+# 16-QAM: b0b1 = 00->-3, 01->-1, 11->+1, 10->+3 ; index b0|b1<<1: 0:-3, 1(b0=1,b1=0):+3, 2(b0=0,b1=1):-1, 3:+1
+# 64-QAM: b0b1b2: 000:-7 001:-5 011:-3 010:-1 110:+1 111:+3 101:+5 100:+7 ; index b0|b1<<1|b2<<2:
+#   0:-7, 1(100):+7, 2(010):-1, 3(110):+1, 4(001):-5, 5(101):+5, 6(011):-3, 7(111):+3
+
+def map_symbols(bits_air, nbpsc):
+    """bits_air [..., nsym, 48*nbpsc] -> complex [..., nsym, 48] (unscaled levels x kmod)."""
+    sh = bits_air.shape[:-1]
+    b = bits_air.reshape(sh + (48, nbpsc)).astype(np.int64)
+    if nbpsc == 1:
+        return (_GRAY[1][b[..., 0]] + 0j) * KMOD[1]
+    h = nbpsc // 2
+    w = (1 << np.arange(h))
+    ii = (b[..., :h] * w).sum(-1); qq = (b[..., h:] * w).sum(-1)
+    return (_GRAY[h][ii] + 1j * _GRAY[h][qq]) * KMOD[nbpsc]
+
+def _ofdm_td(freq64):
+    """freq64 [..., 64] complex in FFT order -> [..., 160] time samples at 40 Msps incl. 32-sample GI."""
+    X = np.zeros(freq64.shape[:-1] + (128,), np.complex128)
+    X[..., :32] = freq64[..., :32]; X[..., 96:] = freq64[..., 32:]
+    td = np.fft.ifft(X, axis=-1) / 16.0          # ifft already divides by 128 (3 radix stages of the fixed-point IFFT<128>)
+    out = np.concatenate([td[..., 96:], td], -1)
+    return out
+
+def _place(data48, pilot_pol):
+    """data48 [..., nsym, 48] complex, pilot_pol [nsym] (+1/-1) -> [..., nsym, 64] FFT-order."""
+    f = np.zeros(data48.shape[:-1] + (64,), np.complex128)
+    neg = [k for k in range(-26, 0) if k not in (-21, -7)]
+    pos = [k for k in range(1, 27) if k not in (7, 21)]
+    idx = np.array([k % 64 for k in neg + pos])
+    f[..., idx] = data48
+    pp = pilot_pol.reshape((1,) * (data48.ndim - 2) + (-1,))
+    f[..., 7] = BPSK_MOD * pp; f[..., 21] = -BPSK_MOD * pp; f[..., 64 - 7] = BPSK_MOD * pp; f[..., 64 - 21] = BPSK_MOD * pp
+    return f
+
+def preamble_td():
+    S = np.zeros(64, np.complex128)
+    a = BPSK_MOD * 1.472 * (1 + 1j)
+    for k, s in ((4, -1), (8, -1), (12, 1), (16, 1), (20, 1), (24, 1), (-24, 1), (-20, -1), (-16, 1), (-12, -1), (-8, -1), (-4, 1)):
+        S[k % 64] = s * a
+    X = np.zeros(128, np.complex128); X[:32] = S[:32]; X[96:] = S[32:]
+    sts = np.fft.ifft(X) / 16.0
+    sts = np.tile(sts, 3)[:320]
+    L = np.zeros(64, np.complex128)
+    for k in range(-26, 27):
+        L[k % 64] = _LTS[k + 26] * BPSK_MOD
+    X = np.zeros(128, np.complex128); X[:32] = L[:32]; X[96:] = L[32:]
+    lt = np.fft.ifft(X) / 16.0
+    lts = np.concatenate([lt[64:], lt, lt])
+    return np.concatenate([sts, lts])               # 640 samples @ 40 Msps
+
+def psdu_with_fcs(payload):
+    payload = np.asarray(payload, np.uint8)
+    fcs = zlib.crc32(payload.tobytes()) & 0xFFFFFFFF
+    return np.concatenate([payload, np.frombuffer(fcs.to_bytes(4, "little"), np.uint8)])
+
+def modulate(psdus, rate_kbps=54000, scramble_seeds=None, window=True):
+    """psdus: uint8 [F, L] (L bytes each, FCS already included).  Returns complex128 [F, nsamp] time signal in
+    int8-LSB units (i.e. what TPackSample16to8 would saturate), 640 + 160*(1+Nsym) samples at 40 Msps."""
+    psdus = np.atleast_2d(np.asarray(psdus, np.uint8))
+    F, L = psdus.shape
+    rbits, nbpsc, cr, ndbps = RATES[rate_kbps]
+    nsym = -(-(16 + 8 * L + 6) // ndbps)
+    ndata = nsym * ndbps
+    if scramble_seeds is None:
+        scramble_seeds = 1 + (np.arange(F) % 127)
+    bits = np.zeros((F, ndata), np.uint8)
+    bits[:, 16:16 + 8 * L] = np.unpackbits(psdus, axis=1, bitorder="little")
+    seq = np.stack([scrambler_seq(int(s), ndata) for s in np.asarray(scramble_seeds).reshape(-1)])
+    bits ^= seq
+    bits[:, 16 + 8 * L: 16 + 8 * L + 6] = 0            # tail bits forced to zero after scrambling
+    A, B = conv_encode(bits)
+    coded = puncture(A, B, cr).reshape(F, nsym, 48 * nbpsc)
+    jmap = interleave_map(48 * nbpsc, nbpsc)
+    air = np.zeros_like(coded); air[..., jmap] = coded
+    data = map_symbols(air, nbpsc)
+    pol = _PILOT_POL[(np.arange(nsym) + 1) % 127]
+    td_data = _ofdm_td(_place(data, pol))               # [F, nsym, 160]
+    # SIGNAL
+    sig = np.zeros(24, np.uint8)
+    sig[0:4] = [(rbits >> i) & 1 for i in range(4)]
+    sig[5:17] = [(L >> i) & 1 for i in range(12)]
+    sig[17] = sig[:17].sum() & 1
+    As, Bs = conv_encode(sig)
+    cs = puncture(As, Bs, (1, 2))
+    j48 = interleave_map(48, 1)
+    airs = np.zeros(48, np.uint8); airs[j48] = cs
+    td_sig = _ofdm_td(_place(map_symbols(airs[None, :], 1), _PILOT_POL[:1]))[0]   # [160]
+    syms = np.concatenate([np.broadcast_to(td_sig, (F, 1, 160)), td_data], 1)
+    if window:
+        syms = syms.copy(); syms[..., :2] *= 0.5; syms[..., 158:] *= 0.5
+    pre = preamble_td()
+    return np.concatenate([np.broadcast_to(pre, (F, 640)), syms.reshape(F, -1)], 1)
+
+def to_iq16(td, gain=1.0, lead=32, trail=32, snr_db=None, cfo_hz=0.0, rng=None, phase=0.0):
+    """complex time signal (int8 units) -> int16 IQ [F, lead+n+trail, 2]: saturate to int8, << 8, plus optional
+    CFO (Hz at 40 Msps), AWGN at snr_db relative to the signal power, a constant gain and silent gaps."""
+    td = np.atleast_2d(td)
+    F, n = td.shape
+    x = td * gain
+    if cfo_hz or phase:
+        x = x * np.exp(1j * (2 * np.pi * cfo_hz * np.arange(n) / 40e6 + phase))
+    re = np.clip(np.round(x.real), -128, 127) * 256.0
+    im = np.clip(np.round(x.imag), -128, 127) * 256.0
+    out = np.zeros((F, lead + n + trail, 2), np.float64)
+    out[:, lead:lead + n, 0] = re; out[:, lead:lead + n, 1] = im
+    if snr_db is not None:
+        rng = rng or np.random.default_rng(0)
+        p = (re ** 2 + im ** 2).mean()
+        sigma = np.sqrt(p / (10 ** (snr_db / 10)) / 2)
+        out += rng.normal(0, sigma, out.shape)
+    return np.clip(np.round(out), -32768, 32767).astype(np.int16)
+
+def make_frames(nframes, psdu_len=1500, rate_kbps=54000, seed0=0x5EED0000, snr_db=None, lead=32, trail=32, cfo_hz=0.0, gain=1.0):
+    """BASELINE config #2 shaped frames: PSDU = (psdu_len-4) random bytes from mt19937(seed0+i) + CRC-32,
+    scrambler seed 1 + i % 127.  Returns (iq int16 [F, slot, 2], psdus uint8 [F, psdu_len])."""
+    ps = np.zeros((nframes, psdu_len), np.uint8)
+    for i in range(nframes):
+        r = np.random.RandomState(seed=(seed0 + i) & 0xFFFFFFFF)
+        ps[i] = psdu_with_fcs(r.randint(0, 256, psdu_len - 4).astype(np.uint8))
+    td = modulate(ps, rate_kbps)
+    rng = np.random.default_rng(seed0 & 0xFFFFFFFF)
+    return to_iq16(td, gain=gain, lead=lead, trail=trail, snr_db=snr_db, cfo_hz=cfo_hz, rng=rng), ps

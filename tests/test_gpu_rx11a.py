@@ -1,0 +1,105 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same IQ."""
+import numpy as np, pytest
+import oracle_py
+from sora_b200 import api, synth
+from sora_b200.dumpfile import load_dump
+import os
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+@pytest.fixture(scope="module")
+def eng():
+    return api.Engine(0)
+
+def _slots(iq):
+    F, slot, _ = iq.shape
+    return iq.reshape(-1, 2), np.arange(F, dtype=np.uint64) * slot, np.full(F, slot, np.uint32)
+
+def _compare(eng, iq2, off, ln, expect_ok=None):
+    res, out = eng.rx11a_batch(iq2, off, ln)
+    ores, oout = oracle_py.rx11a_batch(iq2, off, ln, out_stride=out.shape[1])
+    for k in ("status", "rate_kbps", "length", "crc32", "nsym", "detect_index", "cfo_est"):
+        m = (ores["status"] != oracle_py.E_NO_FRAME) if k != "status" else np.ones(len(res), bool)
+        assert (res[k][m] == ores[k][m]).all(), (k, res[k], ores[k])
+    for i in range(len(res)):
+        if ores["status"][i] in (1, oracle_py.E_CRC32_FAIL):
+            L = int(ores["length"][i])
+            assert (out[i, :L] == oout[i, :L]).all(), f"frame {i} bytes differ"
+    if expect_ok is not None:
+        assert (res["status"] == 1).sum() >= expect_ok
+    return res, out
+
+@pytest.mark.parametrize("rate", sorted(synth.RATES))
+def test_all_rates_clean_and_noisy(eng, rate):
+    for snr in (None, 22):
+        iq, ps = synth.make_frames(6, psdu_len=257, rate_kbps=rate, snr_db=snr, seed0=0x1000 + rate)
+        res, out = _compare(eng, *_slots(iq), expect_ok=6 if snr is None else 0)
+        if snr is None:
+            for i in range(6):
+                assert (out[i, :257] == ps[i]).all()
+
+def test_fsample6_golden(eng):
+    iq = load_dump(os.path.join(GOLD, "fsample-6.dmp"))
+    iq = (iq.astype(np.int32) << 2).astype(np.int16)     # 14-bit sample sign adjust (arx_fd.c:530 xmmAdjustSignBit)
+    off = np.array([0], np.uint64); ln = np.array([len(iq)], np.uint32)
+    res, out = _compare(eng, iq, off, ln, expect_ok=1)
+    assert res["rate_kbps"][0] == 6000 and res["length"][0] == 1392
+
+def test_low_snr_and_garbage(eng):
+    rng = np.random.default_rng(7)
+    iq, _ = synth.make_frames(16, psdu_len=120, rate_kbps=36000, snr_db=9, seed0=0x77)
+    _compare(eng, *_slots(iq))
+    noise = rng.normal(0, 3000, (4, 6000, 2)).astype(np.int16)
+    _compare(eng, *_slots(noise))
+    zeros = np.zeros((2, 2800, 2), np.int16)
+    _compare(eng, *_slots(zeros))
+
+def test_ragged_and_truncated(eng):
+    iq, _ = synth.make_frames(5, psdu_len=400, rate_kbps=24000, snr_db=28, seed0=0x99)
+    F, slot, _ = iq.shape
+    flat = iq.reshape(-1, 2)
+    off = np.arange(F, dtype=np.uint64) * slot
+    ln = np.array([slot, slot - 1000, slot // 2, 700, 27], np.uint32)
+    _compare(eng, flat, off, ln)
+
+def test_cfo_and_gain(eng):
+    for cfo in (-120e3, 40e3, 200e3):
+        for gain in (0.5, 1.0):
+            iq, _ = synth.make_frames(4, psdu_len=333, rate_kbps=54000, snr_db=30, cfo_hz=cfo, gain=gain, seed0=int(abs(cfo)) + 5)
+            _compare(eng, *_slots(iq))
+
+def test_stage_taps(eng):
+    iq, _ = synth.make_frames(3, psdu_len=500, rate_kbps=54000, snr_db=27, cfo_hz=55e3, seed0=0x4242)
+    flat, off, ln = _slots(iq)
+    t = eng.rx11a_taps(flat, off, ln, max_sym=40)
+    for i in range(3):
+        o = oracle_py.rx11a_taps(iq[i], max_sym=40)
+        ns = o["nsym"]
+        assert (t["freq_coeffs"][i] == o["freq_coeffs"]).all()
+        assert (t["chan_coeffs"][i] == o["chan_coeffs"]).all()
+        assert (t["fft_out"][i, :ns] == o["fft_out"]).all()
+        assert (t["equalized"][i, :ns] == o["equalized"]).all()
+        used = [b for b in range(64) if (1 <= b <= 26) or (38 <= b <= 63)]
+        assert (t["tracked"][i, :ns][:, used] == o["tracked"][:, used]).all()
+        nsoft = len(o["soft"]) - 48          # oracle soft includes the 48 SIGNAL values first
+        assert (t["soft"][i, :nsoft] == o["soft"][48:]).all()
+
+def test_viterbi_standalone(eng):
+    rng = np.random.default_rng(3)
+    for cr, (num, den) in ((api.CR_12, (1, 2)), (api.CR_23, (2, 3)), (api.CR_34, (3, 4))):
+        L = 700
+        nbits = 8 * L + 16 + 6
+        nbits += (-nbits) % (6 * 8)
+        bits = rng.integers(0, 2, (5, nbits)).astype(np.uint8); bits[:, 8 * L + 16:] = 0
+        A, B = synth.conv_encode(bits)
+        coded = synth.puncture(A, B, (num, den))
+        for flip in (0.0, 0.06, 0.5):
+            soft = np.where(coded > 0, rng.integers(5, 8, coded.shape), rng.integers(0, 3, coded.shape)).astype(np.uint8)
+            noise = rng.random(coded.shape) < flip
+            soft = np.where(noise, rng.integers(0, 8, coded.shape), soft).astype(np.uint8)
+            g = eng.viterbi_k7(soft, cr, L)
+            o = oracle_py.viterbi_blocks(soft, cr, L)
+            assert (g == o).all(), (cr, flip)
+            if flip == 0.0:
+                assert (np.unpackbits(g, axis=1, bitorder="little")[:, :8 * L + 16] == bits[:, :8 * L + 16]).all()
