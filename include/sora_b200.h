@@ -71,6 +71,9 @@ const char* sb200_last_error(const sb200_handle* h);
 uint64_t sb200_launch_count(const sb200_handle* h);
 /* device time (ms) of the kernels of the most recent *_batch / viterbi call, measured with CUDA events on `stream` */
 float sb200_last_kernel_ms(sb200_handle* h);
+/* per-kernel device times (ms) of the most recent sb200_rx11a_batch: [0] carrier sense, [1] OFDM front end,
+ * [2] Viterbi+descramble+CRC, [3] result pack */
+int sb200_last_kernel_times(sb200_handle* h, float* ms4);
 
 /* Decode `nframes` independent capture slots.  Slot i is iq[2*frame_off[i] .. 2*(frame_off[i]+frame_len[i])) int16
  * (interleaved I,Q; 40 Msps COMPLEX16 stream as TMemSamples would feed it), processed from a fresh context exactly as

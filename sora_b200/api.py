@@ -17,7 +17,7 @@ RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u
                          ("detect_index", "<u4"), ("cfo_est", "<i2"), ("peak_index", "<u2")])
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_rx11a_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+           "sb200_last_kernel_times", "sb200_rx11a_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -34,6 +34,7 @@ def load_library():
         lib.sb200_last_error.argtypes = [C.c_void_p]; lib.sb200_last_error.restype = C.c_char_p
         lib.sb200_launch_count.argtypes = [C.c_void_p]; lib.sb200_launch_count.restype = C.c_uint64
         lib.sb200_last_kernel_ms.argtypes = [C.c_void_p]; lib.sb200_last_kernel_ms.restype = C.c_float
+        lib.sb200_last_kernel_times.argtypes = [C.c_void_p, C.c_void_p]; lib.sb200_last_kernel_times.restype = C.c_int
         lib.sb200_rx11a_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.sb200_rx11a_batch.restype = C.c_int
@@ -83,6 +84,11 @@ class Engine:
         return int(self._lib.sb200_launch_count(self._h))
     def last_kernel_ms(self):
         return float(self._lib.sb200_last_kernel_ms(self._h))
+
+    def last_kernel_times(self):
+        t = (C.c_float * 4)()
+        self._check(self._lib.sb200_last_kernel_times(self._h, C.cast(t, C.c_void_p)), "sb200_last_kernel_times")
+        return [float(x) for x in t]
 
     def rx11a_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         """Pointer-level call (host or device pointers), used by bench.py with torch buffers."""

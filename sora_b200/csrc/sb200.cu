@@ -1,7 +1,8 @@
 // sora_b200 — host side of the C ABI (include/sora_b200.h): workspaces, table upload, kernel launches.
 // Single translation unit: the kernels live in the .cuh files included below.
 #include "../../include/sora_b200.h"
-#include "viterbi_k7.cuh"
+#include "viterbi_k7_quad.cuh"
+#include <stdlib.h>
 #include <string>
 #include <new>
 #include <stdio.h>
@@ -30,7 +31,8 @@ __global__ void k_pack_results(const FrameInfo* __restrict__ info, const uint32_
     if (i >= n) return;
     FrameInfo fi = info[i];
     sb200_frame_result r;
-    r.status = status[i]; r.rate_kbps = fi.rate_kbps; r.length = fi.length; r.crc32 = crc[i]; r.nsym = fi.nsym_total;
+    const bool decoded = fi.status == E_SUCCESS;       // otherwise the front end already reached a terminal code
+    r.status = decoded ? status[i] : fi.status; r.rate_kbps = fi.rate_kbps; r.length = fi.length; r.crc32 = decoded ? crc[i] : 0u; r.nsym = fi.nsym_total;
     r.detect_index = fi.detect_vec == 0xFFFFFFFFu ? 0u : fi.detect_vec * 4u;
     r.cfo_est = (int16_t)fi.cfo_est; r.peak_index = (uint16_t)fi.peak_index;
     res[i] = r;
@@ -51,8 +53,11 @@ struct sb200_handle {
     DevBuf tab, iq, off, len, info, soft, out, status, crc, res, taps[5];
     uint16_t* inv_deint = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // boundaries of sync | front | viterbi | pack
+    int nk = 0;
     bool timed = false;
     uint64_t launches = 0;
+    bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
     std::string err;
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         err = what; if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
@@ -111,9 +116,11 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
+    { const char* e = getenv("SB200_VITERBI"); h->use_v1 = e && e[0] == 'v' && e[1] == '1'; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
+    for (int i = 0; i < 5 && rc == SB200_OK; i++) if (cudaEventCreate(&h->evk[i]) != cudaSuccess) rc = SB200_E_CUDA;
     if (rc != SB200_OK) { sb200_destroy(h); return rc; }
     *out = h;
     return SB200_OK;
@@ -127,6 +134,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     for (DevBuf* b : all) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     delete h;
 }
 extern "C" const char* sb200_last_error(const sb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -137,6 +145,13 @@ extern "C" float sb200_last_kernel_ms(sb200_handle* h) {
     if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
     return ms;
+}
+
+extern "C" int sb200_last_kernel_times(sb200_handle* h, float* ms4) {
+    if (!h || !ms4 || !h->timed || h->nk != 4) return SB200_E_INVALID;
+    if (cudaEventSynchronize(h->evk[4]) != cudaSuccess) return SB200_E_CUDA;
+    for (int i = 0; i < 4; i++) if (cudaEventElapsedTime(&ms4[i], h->evk[i], h->evk[i + 1]) != cudaSuccess) return SB200_E_CUDA;
+    return SB200_OK;
 }
 
 // shared body of sb200_rx11a_batch / sb200_rx11a_taps
@@ -172,18 +187,30 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     CK(h->out.need(nframes * row));
     CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result)));
     FrameInfo* d_info = (FrameInfo*)h->info.p;
-    CK(cudaEventRecord(h->ev0, st));
+    CK(cudaEventRecord(h->ev0, st)); CK(cudaEventRecord(h->evk[0], st));
     k_sync11a<<<(nframes + 127) / 128, 128, 0, st>>>(d_iq, d_off, d_len, nframes, h->cca_thr, h->T, d_info);
+    CK(cudaEventRecord(h->evk[1], st));
     k_front11a<<<(nframes + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, st>>>(d_iq, d_off, d_len, nframes, h->T, d_info,
             (uint8_t*)h->soft.p, soft_stride, h->inv_deint, taps);
+    CK(cudaEventRecord(h->evk[2], st));
     VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
-    k_viterbi_k7<<<(nframes + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T,
-            (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    int nvit = 1;
+    if (h->use_v1) {
+        k_viterbi_k7<<<(nframes + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T,
+                (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    } else {                                           // one launch per code rate; quads of other rates exit at once
+        const unsigned g = (nframes + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
+        k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        k_viterbi_quad<CR_23><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        nvit = 3;
+    }
+    CK(cudaEventRecord(h->evk[3], st));
     const bool res_dev = is_device_ptr(res);
     sb200_frame_result* d_res = res_dev ? res : (sb200_frame_result*)h->res.p;
     k_pack_results<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
-    CK(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->launches += 4;
+    CK(cudaEventRecord(h->evk[4], st)); CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 4; h->launches += 3 + nvit;
     CK(cudaGetLastError());
     bool host_out = false;
     if (out_bytes && out_stride) {
@@ -232,7 +259,7 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
                                 int code_rate, uint32_t frame_len_bytes, uint32_t depth, uint32_t lookahead,
                                 uint8_t* out, uint64_t out_stride, void* cuda_stream) {
     if (!h || !soft || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
-    if (code_rate < 0 || code_rate > 2 || depth == 0 || (depth & 7) || depth + lookahead + 24 > SB_VIT_RING - 8 || depth > 320)
+    if (code_rate < 0 || code_rate > 2 || depth == 0 || (depth & 7) || depth + lookahead + 24 > SB_VQ_RING || depth > 256)
         return h->fail(SB200_E_INVALID, "unsupported code_rate/depth/lookahead");
     if (soft_stride < nsoft || out_stride < frame_len_bytes + 2ull) return h->fail(SB200_E_INVALID, "stride too small");
     if (nblocks == 0) return SB200_OK;
@@ -253,10 +280,17 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
     CK(h->status.need(nblocks * 4ull)); CK(h->crc.need(nblocks * 4ull));
     VitJob job{}; job.code_rate = (uint32_t)code_rate; job.frame_len = frame_len_bytes; job.nsoft = nsoft; job.depth = depth; job.lookahead = lookahead; job.raw = 1;
     CK(cudaEventRecord(h->ev0, st));
-    k_viterbi_k7<<<(nblocks + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T,
-            d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    if (h->use_v1) {
+        k_viterbi_k7<<<(nblocks + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T,
+                d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    } else {
+        const unsigned g = (nblocks + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
+        if (code_rate == CR_34) k_viterbi_quad<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        else if (code_rate == CR_12) k_viterbi_quad<CR_12><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        else k_viterbi_quad<CR_23><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    }
     CK(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->launches += 1;
+    h->timed = true; h->nk = 0; h->launches += 1;
     CK(cudaGetLastError());
     if (!od) {
         CK(cudaMemcpy2DAsync(out, out_stride, d_out, d_ostride, frame_len_bytes + 2ull, nblocks, cudaMemcpyDeviceToHost, st));

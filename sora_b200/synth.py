@@ -22,14 +22,19 @@ KMOD = {1: 10720, 2: int(10720 / 1.414), 4: int(10720 / 3.162), 6: int(10720 / 6
 _LTS = np.array([1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,0,
                  1,-1,-1,1,1,-1,1,-1,1,-1,-1,-1,-1,-1,1,1,-1,-1,1,-1,1,-1,1,1,1,1], dtype=np.float64)
 
+_SCR_CACHE = {}
 def scrambler_seq(seed, n):
     """seed: 7-bit initial state, bit6 = x7 ... bit0 = x1.  Returns n output bits."""
-    st = seed & 0x7F
-    out = np.zeros(127, np.uint8)
-    for i in range(127):
-        b = ((st >> 6) ^ (st >> 3)) & 1
-        st = ((st << 1) | b) & 0x7F
-        out[i] = b
+    seed &= 0x7F
+    out = _SCR_CACHE.get(seed)
+    if out is None:
+        st = seed
+        out = np.zeros(127, np.uint8)
+        for i in range(127):
+            b = ((st >> 6) ^ (st >> 3)) & 1
+            st = ((st << 1) | b) & 0x7F
+            out[i] = b
+        _SCR_CACHE[seed] = out
     return np.resize(out, n)
 
 _PILOT_POL = 1 - 2 * scrambler_seq(0x7F, 127).astype(np.int64)   # p_0..p_126
