@@ -1,0 +1,145 @@
+"""CPU suite (pytest -m "not gpu"): the oracle against the reference's golden fixtures and closed-form tables, the host
+logic, the ABI surface.  No CUDA compute is called here."""
+import os, re, sys, subprocess, ctypes
+import numpy as np, pytest
+import oracle_py
+from sora_b200 import synth
+from sora_b200.dumpfile import load_dump, write_dump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+def _fs6():
+    iq = load_dump(os.path.join(GOLD, "fsample-6.dmp"))
+    return (iq.astype(np.int32) << 2).astype(np.int16)   # xmmAdjustSignBit: 14-bit samples to the top of 16 (dot11a/dot11/arx_fd.c:530)
+
+def test_fsample6_golden_frame():
+    """SURVEY.md §8c pin (1): kernel/test-data/fsample-6.dmp must decode to one CRC-good 6 Mbps, LENGTH 1392 frame."""
+    res, out = oracle_py.rx11a_run(_fs6())
+    assert len(res) == 1
+    r = res[0]
+    assert r["status"] == oracle_py.E_FRAME_OK and r["rate_kbps"] == 6000 and r["length"] == 1392 and r["nsym"] == 466
+    psdu = out[0, :1392]
+    assert oracle_py.crc32(psdu[:-4]) == int(r["crc32"]) == int.from_bytes(psdu[-4:].tobytes(), "little")
+    gold = np.fromfile(os.path.join(GOLD, "fsample-6.psdu.bin"), np.uint8)
+    assert (psdu == gold).all()
+    if os.path.exists(os.path.join(REF, "kernel/test-data/fsample-6.dmp")):
+        assert open(os.path.join(REF, "kernel/test-data/fsample-6.dmp"), "rb").read() == open(os.path.join(GOLD, "fsample-6.dmp"), "rb").read()
+
+def test_dump_roundtrip(tmp_path):
+    iq = _fs6()[:28 * 40]
+    p = tmp_path / "x.dmp"; write_dump(str(p), iq)
+    assert (load_dump(str(p)) == iq).all()
+
+@pytest.mark.parametrize("rate", sorted(synth.RATES))
+def test_roundtrip_all_rates(rate):
+    iq, ps = synth.make_frames(3, psdu_len=211, rate_kbps=rate, snr_db=28, seed0=rate)
+    F, slot, _ = iq.shape
+    res, out = oracle_py.rx11a_batch(iq.reshape(-1, 2), np.arange(F) * slot, np.full(F, slot))
+    assert (res["status"] == 1).all() and (res["rate_kbps"] == rate).all() and (res["length"] == 211).all()
+    assert (out[:, :211] == ps).all()
+
+def test_stream_mode_multiple_frames():
+    """RxThread semantics: several frames in one capture are found one after another (fb11a_demod.cpp:29-81)."""
+    iq, ps = synth.make_frames(4, psdu_len=150, rate_kbps=24000, snr_db=30, lead=400, trail=300)
+    res, out = oracle_py.rx11a_run(iq.reshape(-1, 2), max_frames=8)
+    assert len(res) == 4 and (res["status"] == 1).all()
+    assert (out[:4, :150] == ps).all()
+
+def test_edge_inputs():
+    z = np.zeros((3000, 2), np.int16)
+    res, _ = oracle_py.rx11a_run(z); assert len(res) == 0
+    res, _ = oracle_py.rx11a_run(np.zeros((5, 2), np.int16)); assert len(res) == 0
+    rng = np.random.default_rng(1)
+    res, _ = oracle_py.rx11a_run(rng.normal(0, 4000, (20000, 2)).astype(np.int16))
+    assert all(r["status"] != 1 for r in res)
+    iq, _ = synth.make_frames(1, psdu_len=2500, rate_kbps=54000)          # MTU (PHY_11a.hpp:571)
+    res, _ = oracle_py.rx11a_run(iq[0]); assert res[0]["status"] == 1 and res[0]["length"] == 2500
+    iq, _ = synth.make_frames(1, psdu_len=2501, rate_kbps=54000)
+    res, _ = oracle_py.rx11a_run(iq[0]); assert res[0]["status"] == oracle_py.E_PLCP_FAIL
+
+def test_fft64_close_to_float():
+    rng = np.random.default_rng(0)
+    x = rng.integers(-6000, 6000, (64, 2)).astype(np.int16)
+    y = oracle_py.fft64(x).astype(np.float64)
+    ref = np.fft.fft(x[:, 0] + 1j * x[:, 1]) / 64.0
+    err = np.abs((y[:, 0] + 1j * y[:, 1]) - ref)
+    assert err.max() < 8.0            # fixed point, 3 truncating stages and one's-complement negations: a few LSB
+    z = oracle_py.ifft64(oracle_py.fft64(x)).astype(np.float64)
+    assert np.abs(z / 1.0 - x / 64.0).max() < 12.0    # two fixed-point transforms back to back (each 2^-6): sanity bound only
+
+def test_viterbi_known_answer():
+    rng = np.random.default_rng(5)
+    for cr, rate in ((0, (1, 2)), (1, (2, 3)), (2, (3, 4))):
+        L = 100; n = 8 * L + 16 + 6; n += (-n) % 48
+        bits = rng.integers(0, 2, (1, n)).astype(np.uint8); bits[:, 8 * L + 16:] = 0
+        A, B = synth.conv_encode(bits); coded = synth.puncture(A, B, rate)[0]
+        soft = np.where(coded > 0, 7, 0).astype(np.uint8)
+        out = oracle_py.viterbi_block(soft, cr, L)
+        assert (np.unpackbits(out, bitorder="little")[:8 * L + 16] == bits[0, :8 * L + 16]).all()
+
+def test_signal_field_known_answer():
+    sig = np.zeros(24, np.uint8); sig[0:4] = [1, 1, 0, 1]; L = 1392
+    sig[5:17] = [(L >> i) & 1 for i in range(12)]; sig[17] = sig[:17].sum() & 1
+    A, B = synth.conv_encode(sig); coded = synth.puncture(A, B, (1, 2))
+    soft = np.where(coded > 0, 7, 0).astype(np.uint8)
+    w = oracle_py.lib().sbo_viterbi_signal(soft.ctypes.data_as(ctypes.c_void_p))
+    assert (w & 0xF) == 0xB and ((w >> 5) & 0xFFF) == 1392
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_tables_vs_reference_headers():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import refcheck as rc
+    for N in (16, 64):
+        for M in (1, 2, 3):
+            assert (rc.ref_twiddle(N, M)[: N // 4] == rc.gen_twiddle(N, M)).all()
+    assert (rc.ref_bitrev(64) == np.array([int(f"{i:06b}"[::-1], 2) for i in range(64)])).all()
+    s, c, a = rc.ref_trig()
+    assert (s == rc.gen_sin()).all() and (c == rc.gen_cos()).all() and (a == rc.gen_atan2()).all()
+    ra, rb = rc.ref_vit(); ga, gb = rc.gen_vit()
+    assert (ra == ga).all() and (rb == gb).all()
+    for cls, n, b in (("BPSK", 48, 1), ("QPSK", 96, 2), ("QAM16", 192, 4), ("QAM64", 288, 6)):
+        assert (rc.ref_deinterleave(cls) == rc.gen_deinterleave(n, b)).all()
+    # LTS signs and pilot polarity used by oracle/rx11a.cpp and csrc/tables.cuh
+    t = rc._read("kernel/bb/Brick11/src/channel_11a.hpp")
+    lts = np.array(rc.parse_array(t, "LTS_Sequence_11a"))
+    exp = np.array([1 if (-26 <= (i if i < 32 else i - 64) <= 26 and synth._LTS[(i if i < 32 else i - 64) + 26] > 0) else 0 for i in range(64)])
+    assert (lts == exp).all()
+    t = rc._read("kernel/bb/Brick11/src/pilot.hpp")
+    pil = np.array(rc.parse_array(t, "PilotSgn"))
+    pol = synth._PILOT_POL
+    exp = np.array([0 if pol[(i + 1) % 127] > 0 else -1 for i in range(127)] + [0])
+    assert (pil == exp).all()
+    # demap tables shipped as data
+    luts = rc.ref_demap_luts()
+    tb = ctypes.POINTER(ctypes.c_uint8)
+    a_, b_, d_ = tb(), tb(), tb()
+    oracle_py.lib().sbo_tables(ctypes.byref(a_), ctypes.byref(b_), ctypes.byref(d_))
+    got = np.ctypeslib.as_array(d_, shape=(1024,))
+    assert (got == np.concatenate([luts["m_bpsk_lut"], luts["m_qam16_lut2"], luts["m_qam64_lut2"], luts["m_qam64_lut3"]])).all()
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sora_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 8
+    from sora_b200 import api
+    lib = api.load_library()            # loads without a GPU; no compute entry point is called
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(api.EXPORTS) == declared
+
+def test_product_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sora_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_py" not in txt and "libsora_oracle" not in txt and 'oracle/' not in txt.replace("oracle/ is test", ""), f
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from sora_b200 import api
+    with pytest.raises(api.Sb200Error):
+        api.Engine(0)
