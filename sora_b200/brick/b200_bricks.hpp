@@ -1,0 +1,92 @@
+// GPU bricks: drop-in replacements for CPU sub-graphs of the reference's dot11 demod graphs, forwarding to the
+// C ABI in include/sora_b200.h.  Header-only templates, compiled into the caller exactly like any other brick.
+//
+//   TB200Dot11aRx<T_CTX, T_NEXT>   replaces ds2 .. fsink of CreateDemodGraph11a_40M
+//       (kernel/bb/demod11/fb11ademod_config.hpp:169-242: TDownSample2, TBB11bRxSwitch, TDCRemoveEx, TCCA11a,
+//        TDCEstimator, T11aLTS, T11aDataSymbol, TFreqCompensation, TFFT64, TChannelEqualization, TPhaseCompensate,
+//        TPilotTrack, TBB11aRxRateSel, T11aDemap*, T11aDeinterleave*, T11aViterbiSig, T11aPLCPParser,
+//        TThreadSeparator, T11aViterbi, T11aDesc, TBB11aFrameSink)
+//     iport  COMPLEX16 x 28  (what TMemSamples / TRxStream emit: memsource.hpp:33, rxstream.hpp)
+//     oport  uchar x 1       (decoded PSDU bytes, as T11aDesc would hand to the frame sink)
+//     context facades: CF_Error, CF_11aRxVector, CF_RxFrameBuffer, CF_11CCA, CF_CFOffset — written exactly when and
+//     how the CPU bricks write them: after a frame event error_code() becomes E_ERROR_FRAME_OK / E_ERROR_CRC32_FAIL /
+//     E_ERROR_PLCP_HEADER_FAIL and the driver loop (fb11a_demod.cpp:29-81) does its Flush()/Reset() as before.
+//
+// Batching: the GPU decodes whole capture slots.  The brick buffers incoming 28-sample blocks and submits a slot when
+// `slot_samples` samples have arrived or on Flush(); one graph instance therefore trades latency for throughput.  A
+// throughput-oriented caller uses sb200_rx11a_batch directly with thousands of slots per call.
+#pragma once
+#include "facades.hpp"
+#include "../../include/sora_b200.h"
+#include <vector>
+#ifndef SB200_BRICK_DEVICE
+#define SB200_BRICK_DEVICE 0      /* CUDA device ordinal the bricks of this translation unit bind to */
+#endif
+
+DEFINE_LOCAL_CONTEXT(TB200Dot11aRx, CF_Error, CF_11aRxVector, CF_RxFrameBuffer, CF_11CCA, CF_CFOffset);
+template <TFILTER_ARGS>
+class TB200Dot11aRx : public TFilter<TFILTER_PARAMS> {
+    CTX_VAR_RW(ulong, error_code)
+    CTX_VAR_RW(ushort, frame_length) CTX_VAR_RW(ushort, total_symbols) CTX_VAR_RW(ulong, data_rate_kbps) CTX_VAR_RW(ushort, code_rate) CTX_VAR_RW(ulong, frame_crc32)
+    CTX_VAR_RO(uchar*, rx_frame_buf) CTX_VAR_RO(uint, rx_frame_buf_size)
+    CTX_VAR_RO(uint, cca_pwr_threshold) CTX_VAR_RW(uint, cca_peak_index) CTX_VAR_RW(CF_11CCA::CCAState, cca_state)
+    CTX_VAR_RW(short, CFO_est)
+    sb200_handle* h_;
+    std::vector<COMPLEX16> slot_;
+    std::vector<uchar> bytes_;
+    size_t slot_samples_;
+public:
+    DEFINE_IPORT(COMPLEX16, 28);
+    DEFINE_OPORT(uchar, 1);
+    REFERENCE_LOCAL_CONTEXT(TB200Dot11aRx);
+    STD_TFILTER_CONSTRUCTOR(TB200Dot11aRx)
+        BIND_CONTEXT(CF_Error::error_code, error_code)
+        BIND_CONTEXT(CF_11aRxVector::frame_length, frame_length) BIND_CONTEXT(CF_11aRxVector::total_symbols, total_symbols)
+        BIND_CONTEXT(CF_11aRxVector::data_rate_kbps, data_rate_kbps) BIND_CONTEXT(CF_11aRxVector::code_rate, code_rate)
+        BIND_CONTEXT(CF_11aRxVector::crc32, frame_crc32)
+        BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
+        BIND_CONTEXT(CF_11CCA::cca_pwr_threshold, cca_pwr_threshold) BIND_CONTEXT(CF_11CCA::cca_peak_index, cca_peak_index)
+        BIND_CONTEXT(CF_11CCA::cca_state, cca_state) BIND_CONTEXT(CF_CFOffset::CFO_est, CFO_est)
+        , h_(nullptr), slot_samples_(0)
+    {
+        sb200_cfg cfg; memset(&cfg, 0, sizeof cfg); cfg.cca_pwr_threshold = cca_pwr_threshold;
+        if (sb200_create(SB200_BRICK_DEVICE, &cfg, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }   // no CPU fallback
+        bytes_.resize(4096);
+    }
+    ~TB200Dot11aRx() { sb200_destroy(h_); }
+    // capture-slot size in 40 Msps samples; 0 = submit only on Flush() (whole dump file = one slot, like demod11 -d)
+    void SetSlotSamples(size_t n) { slot_samples_ = n; }
+
+    STD_TFILTER_RESET() { slot_.clear(); }
+    STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) Submit(); }
+
+    BOOL_FUNC_PROCESS(ipin) {
+        while (ipin.check_read()) {
+            const COMPLEX16* p = ipin.peek();
+            slot_.insert(slot_.end(), p, p + 28);
+            ipin.pop();
+            if (slot_samples_ && slot_.size() >= slot_samples_) { if (!Submit()) return false; }
+        }
+        return true;
+    }
+private:
+    bool Submit() {
+        if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        if (slot_.empty()) return true;
+        uint64_t off = 0; uint32_t len = (uint32_t)slot_.size(); sb200_frame_result r;
+        int rc = sb200_rx11a_batch(h_, (const int16_t*)slot_.data(), slot_.size(), &off, &len, 1, bytes_.data(), (uint32_t)bytes_.size(), &r, nullptr);
+        slot_.clear();
+        if (rc != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
+        if (r.status == SB200_FRAME_NONE) return true;             // nothing detected in this slot: keep sensing
+        frame_length = (ushort)r.length; total_symbols = (ushort)r.nsym; data_rate_kbps = r.rate_kbps; frame_crc32 = r.crc32;
+        code_rate = (ushort)(r.rate_kbps == 48000 ? CR_23 : (r.rate_kbps == 9000 || r.rate_kbps == 18000 || r.rate_kbps == 36000 || r.rate_kbps == 54000) ? CR_34 : CR_12);
+        cca_peak_index = r.peak_index; cca_state = CF_11CCA::power_detected; CFO_est = r.cfo_est;
+        if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) {
+            uint n = r.length;
+            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, bytes_.data(), n);
+            for (uint i = 0; i < n; i++) { *opin().append() = bytes_[i]; this->Next()->Process(opin()); }
+        }
+        error_code = r.status;                                     // the driver polls this after Process() (fb11a_demod.cpp:35)
+        return false;                                              // frame complete: stop pumping (PHY_11a.hpp:694)
+    }
+};

@@ -103,3 +103,15 @@ def test_viterbi_standalone(eng):
             assert (g == o).all(), (cr, flip)
             if flip == 0.0:
                 assert (np.unpackbits(g, axis=1, bitorder="little")[:, :8 * L + 16] == bits[:, :8 * L + 16]).all()
+
+def test_brick_adaptor_graph(eng):
+    """The header-only GPU brick inside a CREATE_BRICK_* graph driven like RxThread (sora_b200/brick/demo_graph.cpp)."""
+    import subprocess, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sora_b200", "brick", "demo_graph")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    p = subprocess.run([exe, os.path.join(GOLD, "fsample-6.dmp"), "legacy14"], capture_output=True, text=True, timeout=120)
+    ev = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert ev and ev[0]["error_code"] == "0x00000001" and ev[0]["rate_kbps"] == 6000 and ev[0]["length"] == 1392
+    assert ev[0]["crc32"] == "0x80EF9B11" and ev[0]["bytes_out"] == 1392
