@@ -74,6 +74,11 @@ float sb200_last_kernel_ms(sb200_handle* h);
 /* per-kernel device times (ms) of the most recent sb200_rx11a_batch: [0] carrier sense, [1] OFDM front end,
  * [2] Viterbi+descramble+CRC, [3] result pack */
 int sb200_last_kernel_times(sb200_handle* h, float* ms4);
+/* Tunables.  "chunk_frames" (default 8192): when the IQ buffer is HOST memory, calls with more slots are cut into chunks whose
+ * host->device copy, OFDM front end and Viterbi overlap on three streams; 0 = one pass on the caller's stream.
+ * "chunk_frames_device" (default 0 = off): the same for device-resident IQ.  sb200_last_kernel_times needs an un-chunked call.  A device-resident slot table (frame_off/frame_len) is
+ * read back once and assumed unchanged while the same pointers are passed again. */
+int sb200_set_option(sb200_handle* h, const char* name, uint64_t value);
 
 /* Decode `nframes` independent capture slots.  Slot i is iq[2*frame_off[i] .. 2*(frame_off[i]+frame_len[i])) int16
  * (interleaved I,Q; 40 Msps COMPLEX16 stream as TMemSamples would feed it), processed from a fresh context exactly as

@@ -17,7 +17,7 @@ RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u
                          ("detect_index", "<u4"), ("cfo_est", "<i2"), ("peak_index", "<u2")])
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_last_kernel_times", "sb200_rx11a_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -35,6 +35,7 @@ def load_library():
         lib.sb200_launch_count.argtypes = [C.c_void_p]; lib.sb200_launch_count.restype = C.c_uint64
         lib.sb200_last_kernel_ms.argtypes = [C.c_void_p]; lib.sb200_last_kernel_ms.restype = C.c_float
         lib.sb200_last_kernel_times.argtypes = [C.c_void_p, C.c_void_p]; lib.sb200_last_kernel_times.restype = C.c_int
+        lib.sb200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]; lib.sb200_set_option.restype = C.c_int
         lib.sb200_rx11a_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.sb200_rx11a_batch.restype = C.c_int
@@ -84,6 +85,9 @@ class Engine:
         return int(self._lib.sb200_launch_count(self._h))
     def last_kernel_ms(self):
         return float(self._lib.sb200_last_kernel_ms(self._h))
+
+    def set_option(self, name, value):
+        self._check(self._lib.sb200_set_option(self._h, name.encode(), int(value)), "sb200_set_option")
 
     def last_kernel_times(self):
         t = (C.c_float * 4)()

@@ -4,6 +4,8 @@
 #include "viterbi_k7_quad.cuh"
 #include <stdlib.h>
 #include <string>
+#include <vector>
+#include <string.h>
 #include <new>
 #include <stdio.h>
 
@@ -57,6 +59,13 @@ struct sb200_handle {
     int nk = 0;
     bool timed = false;
     uint64_t launches = 0;
+    uint32_t chunk_frames_device = 0;
+    uint32_t chunk_frames = 8192;                      // slots per pipeline chunk (0 = one chunk, everything on the caller's stream)
+    cudaStream_t s_copy = nullptr, s_front = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
+    DevBuf stage[2];
+    std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
+    const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
     std::string err;
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -121,6 +130,9 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
     for (int i = 0; i < 5 && rc == SB200_OK; i++) if (cudaEventCreate(&h->evk[i]) != cudaSuccess) rc = SB200_E_CUDA;
+    if (rc == SB200_OK && (cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_front, cudaStreamNonBlocking) != cudaSuccess)) rc = SB200_E_CUDA;
+    if (rc == SB200_OK && cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) != cudaSuccess) rc = SB200_E_CUDA;
+    for (int i = 0; i < 2 && rc == SB200_OK; i++) if (cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_front[i], cudaEventDisableTiming) != cudaSuccess) rc = SB200_E_CUDA;
     if (rc != SB200_OK) { sb200_destroy(h); return rc; }
     *out = h;
     return SB200_OK;
@@ -135,6 +147,10 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    for (int i = 0; i < 2; i++) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); h->stage[i].release(); }
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->s_front) cudaStreamDestroy(h->s_front);
     delete h;
 }
 extern "C" const char* sb200_last_error(const sb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -154,27 +170,66 @@ extern "C" int sb200_last_kernel_times(sb200_handle* h, float* ms4) {
     return SB200_OK;
 }
 
-// shared body of sb200_rx11a_batch / sb200_rx11a_taps
+// Launch the decode kernels for frames [f0, f1) of a call.  `iq_base + off[f]` must address slot f.
+// sync + front end go to `sf`, the Viterbi launches to `sv` (sv waits for `front_done` when the streams differ).
+static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t f0, uint32_t f1,
+                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed) {
+    const uint32_t n = f1 - f0;
+    FrameInfo* d_info = (FrameInfo*)h->info.p + f0;
+    uint8_t* d_soft = (uint8_t*)h->soft.p + (size_t)f0 * soft_stride;
+    uint8_t* d_out = (uint8_t*)h->out.p + (size_t)f0 * row;
+    uint32_t* d_status = (uint32_t*)h->status.p + f0; uint32_t* d_crc = (uint32_t*)h->crc.p + f0;
+    if (timed) CK(cudaEventRecord(h->evk[0], sf));
+    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info);
+    if (timed) CK(cudaEventRecord(h->evk[1], sf));
+    k_front11a<<<(n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info,
+            d_soft, soft_stride, h->inv_deint, taps);
+    if (timed) CK(cudaEventRecord(h->evk[2], sf));
+    if (sv != sf) { CK(cudaEventRecord(front_done, sf)); CK(cudaStreamWaitEvent(sv, front_done, 0)); }
+    VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
+    if (h->use_v1) {
+        k_viterbi_k7<<<(n + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
+        h->launches += 3;
+    } else {                                           // one launch per code rate; quads of other rates exit at once
+        const unsigned g = (n + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
+        k_viterbi_quad<CR_34><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
+        k_viterbi_quad<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
+        k_viterbi_quad<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
+        h->launches += 5;
+    }
+    if (timed) CK(cudaEventRecord(h->evk[3], sv));
+    return SB200_OK;
+}
+
+// shared body of sb200_rx11a_batch / sb200_rx11a_taps.
+// Large calls are cut into chunks of h->chunk_frames slots and pipelined over three streams: host->device copy of chunk
+// k+1 (copy stream) | carrier sense + OFDM front end of chunk k+1 (front stream) | Viterbi of chunk k (caller's stream).
+// The front end is latency bound and the Viterbi integer-issue bound, so they overlap well on the same SMs.
 static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
                      uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, cudaStream_t st,
                      FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride) {
     if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
     if (nframes == 0) return SB200_OK;
     CK(cudaSetDevice(h->device));
-    // slot table (host copy needed for sizing; a device-resident table is copied back once)
-    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    // slot table (host copy needed for sizing; a device-resident table is copied back once per distinct table)
     const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len);
-    if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
-    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
-    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
-    uint32_t max_len = 0;
-    for (uint32_t i = 0; i < nframes; i++) {
-        if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
-        if (lenh[i] > max_len) max_len = lenh[i];
+    std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
+    const bool cached = off_dev && len_dev && h->tab_off == frame_off && h->tab_len == frame_len && h->tab_n == nframes && h->tab_total == iq_total;
+    if (!cached) {
+        offh.resize(nframes); lenh.resize(nframes);
+        if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
+        if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
+        if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+        h->tab_max_len = 0;
+        for (uint32_t i = 0; i < nframes; i++) {
+            if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+            if (lenh[i] > h->tab_max_len) h->tab_max_len = lenh[i];
+        }
+        // a device-resident slot table is assumed immutable between calls that pass the same pointers (documented in the header)
+        if (off_dev && len_dev) { h->tab_off = frame_off; h->tab_len = frame_len; h->tab_n = nframes; h->tab_total = iq_total; } else h->tab_off = nullptr;
     }
-    const uint32_t* d_iq;
-    if (is_device_ptr(iq)) d_iq = (const uint32_t*)iq;
-    else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
+    const uint32_t max_len = h->tab_max_len;
+    const bool iq_dev = is_device_ptr(iq);
     const uint64_t* d_off; const uint32_t* d_len;
     if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
     if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
@@ -186,31 +241,57 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     CK(h->soft.need(nframes * soft_stride));
     CK(h->out.need(nframes * row));
     CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result)));
-    FrameInfo* d_info = (FrameInfo*)h->info.p;
-    CK(cudaEventRecord(h->ev0, st)); CK(cudaEventRecord(h->evk[0], st));
-    k_sync11a<<<(nframes + 127) / 128, 128, 0, st>>>(d_iq, d_off, d_len, nframes, h->cca_thr, h->T, d_info);
-    CK(cudaEventRecord(h->evk[1], st));
-    k_front11a<<<(nframes + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, st>>>(d_iq, d_off, d_len, nframes, h->T, d_info,
-            (uint8_t*)h->soft.p, soft_stride, h->inv_deint, taps);
-    CK(cudaEventRecord(h->evk[2], st));
-    VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
-    int nvit = 1;
-    if (h->use_v1) {
-        k_viterbi_k7<<<(nframes + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T,
-                (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-    } else {                                           // one launch per code rate; quads of other rates exit at once
-        const unsigned g = (nframes + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
-        k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-        k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-        k_viterbi_quad<CR_23><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-        nvit = 3;
+    const bool tapping = taps.freq_coeffs || taps.fft_out || soft_host;
+    // device-resident IQ gains nothing from chunking (a chunk's Viterbi grid no longer fills 148 SMs x 5 CTAs); host IQ does:
+    // the PCIe copy of chunk k+1 hides behind the kernels of chunk k.  chunk_frames_device lets a caller force it anyway.
+    const uint32_t want = iq_dev ? h->chunk_frames_device : h->chunk_frames;
+    const uint32_t chunk = (want == 0 || tapping || nframes <= want) ? nframes : want;
+    const bool pipelined = chunk < nframes;
+    CK(cudaEventRecord(h->ev0, st));
+    if (!pipelined) {
+        const uint32_t* d_iq;
+        if (iq_dev) d_iq = (const uint32_t*)iq;
+        else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
+        int rc = launch_chunk(h, d_iq, d_off, d_len, 0, nframes, soft_stride, row, st, st, nullptr, taps, true);
+        if (rc != SB200_OK) return rc;
+        h->nk = 4;
+    } else {
+        // host IQ: per-chunk sample range [lo, hi) staged through two device buffers
+        uint64_t stage_samples = 0;
+        if (!iq_dev) {
+            for (uint32_t f0 = 0; f0 < nframes; f0 += chunk) {
+                uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; uint64_t lo = ~0ull, hi = 0;
+                for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
+                if (hi - lo > stage_samples) stage_samples = hi - lo;
+            }
+            CK(h->stage[0].need(stage_samples * 4ull + 16)); CK(h->stage[1].need(stage_samples * 4ull + 16));
+        }
+        CK(cudaEventRecord(h->ev_start, st));
+        CK(cudaStreamWaitEvent(h->s_copy, h->ev_start, 0)); CK(cudaStreamWaitEvent(h->s_front, h->ev_start, 0));
+        uint32_t k = 0;
+        for (uint32_t f0 = 0; f0 < nframes; f0 += chunk, k++) {
+            const uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; const int b = k & 1;
+            const uint32_t* base = (const uint32_t*)iq;
+            if (!iq_dev) {
+                uint64_t lo = ~0ull, hi = 0;
+                for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
+                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));        // buffer b free once chunk k-2's front end has read it
+                CK(cudaMemcpyAsync(h->stage[b].p, (const uint32_t*)iq + lo, (hi - lo) * 4ull, cudaMemcpyHostToDevice, h->s_copy));
+                CK(cudaEventRecord(h->ev_h2d[b], h->s_copy));
+                CK(cudaStreamWaitEvent(h->s_front, h->ev_h2d[b], 0));
+                base = (const uint32_t*)h->stage[b].p - lo;
+            }
+            int rc = launch_chunk(h, base, d_off, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false);
+            if (rc != SB200_OK) return rc;
+        }
+        h->nk = 0;
     }
-    CK(cudaEventRecord(h->evk[3], st));
     const bool res_dev = is_device_ptr(res);
     sb200_frame_result* d_res = res_dev ? res : (sb200_frame_result*)h->res.p;
-    k_pack_results<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
-    CK(cudaEventRecord(h->evk[4], st)); CK(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->nk = 4; h->launches += 3 + nvit;
+    k_pack_results<<<(nframes + 255) / 256, 256, 0, st>>>((const FrameInfo*)h->info.p, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
+    if (!pipelined) CK(cudaEventRecord(h->evk[4], st));
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->launches += 1;
     CK(cudaGetLastError());
     bool host_out = false;
     if (out_bytes && out_stride) {
@@ -223,6 +304,13 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
     return SB200_OK;
+}
+
+extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t value) {
+    if (!h || !name) return SB200_E_INVALID;
+    if (!strcmp(name, "chunk_frames")) { h->chunk_frames = (uint32_t)value; return SB200_OK; }
+    if (!strcmp(name, "chunk_frames_device")) { h->chunk_frames_device = (uint32_t)value; return SB200_OK; }
+    return h->fail(SB200_E_INVALID, "unknown option");
 }
 
 extern "C" int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples, const uint64_t* frame_off,
