@@ -4,112 +4,119 @@
 // kernel/bb/Brick11/src/viterbi.hpp:104-237), different machine mapping:
 //
 //   * 4 lanes decode one code block; each lane keeps 16 of the 64 path metrics in 8 registers, two per register as
-//     16-bit halves, so add / compare-select run on Blackwell's native 16x2 integer SIMD (VIADD.16x2, VIMNMX.U16x2);
-//     the reference's uint8 wrap is "& 0x00FE00FE" / "(& 0x00FF00FF) | 0x00010001" folded into one LOP3 each.
-//   * The trellis is processed IN PLACE: the butterfly (p, p+32) -> (2p, 2p+1) writes its two results into the two
-//     slots its inputs came from.  A state index is therefore a 6-bit rotation of its physical address
-//     A = lane[2] | reg[3] | half[1]:  state(A, t) = rol6(A, t mod 6).  The pairing dimension walks through the address
-//     bits with period 6:  t%6 = 0,1 -> partner lane (one __shfl_xor per register: the path-metric exchange),
-//     2,3,4 -> another register of the same lane (pure SIMD, no data movement), 5 -> the two halves of one register.
-//   * Branch metrics: the 4 possible values of a step live as bytes of one register; each 2-state operand is one
-//     PRMT with a compile-time selector (lane-dependent part applied once per step by a second PRMT).
-//   * Survivor bits: the LSB of every new metric, 16 per lane per step, stored as one 16-bit word into a
-//     [column][block-in-CTA] shared-memory ring (conflict-free, 8 B per code block per step); traceback reads
-//     bit ror6(state, column mod 6) of the 64-bit column word.
+//     16-bit halves, so compare-select is Blackwell's native 16x2 SIMD (VIMNMX.U16x2).
+//   * Metrics sit in the HIGH byte of each half: the reference's uint8 wrap is the natural carry-out of the half (a plain
+//     32-bit IMAD.IADD on the FMA pipe is a 16x2 add; the carry of the low half only lands in a dead byte), and the
+//     survivor mark costs one LOP3 per *input* register (even role: & 0xFE00FE00, odd role: (& 0xFF00FF00) | 0x01000100).
+//     The dead bytes are cleared by those masks every step and cannot decide a compare: the candidates' marks differ.
+//   * The trellis is processed IN PLACE: butterfly (p, p+32) -> (2p, 2p+1) writes its results into the slots it read.
+//     A slot's physical address is A = lane[2] | half[1] | reg[3]; its state index at time t is rol6(A, t mod 6), so the
+//     pairing dimension walks through the address bits with period 6:
+//         t%6 = 0,1 -> partner lane (one SHFL.BFLY per register: the path-metric exchange)
+//         t%6 = 2   -> the two halves of one register
+//         t%6 = 3,4,5 -> another register of the same lane (pure SIMD, no data movement).
+//   * Branch metrics: the 4 possible values of a step are bytes of one register (two IDP4A + two IMAD straight from the
+//     packed soft bytes); each 2-state operand is one PRMT with a compile-time selector.
+//   * Survivor bits: the LSB of every new metric, 16 per lane per step -> one 16-bit word in a [column][block] shared
+//     memory ring; bit index == physical address, so the traceback never leaves address space: the predecessor of slot A
+//     at column c is A with bit (6 - c%6)%6 replaced by the survivor bit.
 //   * One lane of the quad runs the windowed traceback, the x^7+x^4+1 descrambler and the CRC-32 / verdict.
 #pragma once
 #include "viterbi_k7.cuh"
 
 namespace sb {
 
-#define SB_VQ_WARPS 2                      // warps per CTA
+#define SB_VQ_WARPS 1                      // warps per CTA
 #define SB_VQ_FR (8 * SB_VQ_WARPS)         // code blocks per CTA
-#define SB_VQ_RING 304                     // columns kept per code block (>= depth + lookahead + 7 + 3 + slack)
+#define SB_VQ_RING 288                     // columns kept per code block: needs depth + lookahead + 4 (283 for 256/24); multiple of 6
 
 __host__ __device__ constexpr int vq_rol6(int a, int t) { return ((a << t) | (a >> (6 - t))) & 63; }
 __host__ __device__ constexpr int vq_cls(int p) {            // (cA << 1) | cB of predecessor index p (bit 5 ignored)
     return ((((p >> 1) ^ (p >> 2) ^ (p >> 4)) & 1) << 1) | ((p ^ (p >> 1) ^ (p >> 2)) & 1);
 }
 // static class of (reg r, half h) at phase T, lane part excluded (GF(2)-linear, so the lane part is XORed in later)
-__host__ __device__ constexpr int vq_scls(int T, int r, int h) { return vq_cls(vq_rol6((r << 1) | h, T) & 31); }
+__host__ __device__ constexpr int vq_scls(int T, int r, int h) { return vq_cls(vq_rol6((h << 3) | r, T) & 31); }
 __host__ __device__ constexpr int vq_lcls(int T, int q) { return vq_cls(vq_rol6(q << 4, T) & 31); }
-// PRMT selector building [byte i0, 0, byte i1, 0] from (Cb, 0)
-__host__ __device__ constexpr unsigned vq_sel(int i0, int i1) { return (unsigned)(i0 | (4 << 4) | (i1 << 8) | (4 << 12)); }
+// PRMT selector building [0, byte i0, 0, byte i1] from (Cb, 0): the branch metric lands in the high byte of each half
+__host__ __device__ constexpr unsigned vq_sel(int i0, int i1) { return (unsigned)(4 | (i0 << 4) | (4 << 8) | (i1 << 12)); }
 
 struct VqLane {
     unsigned swz[6];       // per-phase byte swizzle applying this lane's class contribution
-    unsigned m1[2], o1[2], m2[2], o2[2];   // lane-phase masks: which of (own, partner) is the even branch
+    unsigned lm[2], lo[2]; // lane-phase role mask of this lane's own registers (even: & EV, odd: (& FF) | ONE)
 };
 
-// one trellis step at compile-time phase T.  Cbase bytes = metric for class (a,b) at byte (a<<1|b) for the even branch
-// of the *upper* output (new state with input bit 0); complement class = 3 - index.
+// one trellis step at compile-time phase T.  Cbase byte (cA<<1|cB) = metric of the even candidate for a predecessor of
+// that class; the complement class (3 - index) is the odd candidate's.
 template <int T>
 __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
     const uint32_t Cb = __byte_perm(Cbase, 0, L.swz[T]);
-    const uint32_t EV = 0x00FE00FEu, FF = 0x00FF00FFu, ONE = 0x00010001u;
+    const uint32_t EV = 0xFE00FE00u, FF = 0xFF00FF00u, ONE = 0x01000100u;
     if (T <= 1) {                                       // pair = partner lane (xor 2 at T=0, xor 1 at T=1)
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int c0 = vq_scls(T, r, 0), c1 = vq_scls(T, r, 1);
             uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
-            uint32_t Z = __shfl_xor_sync(qmask, R[r], T == 0 ? 2 : 1);
-            uint32_t t1 = R[r] + av, t2 = Z + bv;            // halves stay < 2^16: a plain 32-bit add is a 16x2 add
-            // lane holding p (pair bit 0): out = min(t1 & EV, (t2 & FF) | 1);  lane holding p+32: roles swapped
-            R[r] = __vminu2((t1 & L.m1[T]) | L.o1[T], (t2 & L.m2[T]) | L.o2[T]);
+            uint32_t own = (R[r] & L.lm[T]) | L.lo[T];  // marked according to this lane's role; the partner did the same
+            uint32_t Z = __shfl_xor_sync(qmask, own, T == 0 ? 2 : 1);
+            R[r] = __vminu2(own + av, Z + bv);
         }
-    } else if (T <= 4) {                                // pair = register r ^ d inside the lane
-        const int d = T == 2 ? 4 : T == 3 ? 2 : 1;
+    } else if (T == 2) {                                // pair = the two halves of each register
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int c = vq_scls(2, r, 0);             // class of p (low half); the high half is p+32: complement
+            uint32_t ab = __byte_perm(Cb, 0, vq_sel(c, 3 - c)), ba = __byte_perm(Cb, 0, vq_sel(3 - c, c));
+            uint32_t m = (R[r] & 0xFF00FE00u) | 0x01000000u;              // low half = even role, high half = odd role
+            uint32_t t1 = m + ab, t2 = m + ba;          // t1 = [p+a, p32+b], t2 = [p+b, p32+a]
+            R[r] = __vminu2(__byte_perm(t1, t2, 0x5410), __byte_perm(t1, t2, 0x7632));   // [t1.lo, t2.lo] vs [t1.hi, t2.hi]
+        }
+    } else {                                            // pair = register r ^ d inside the lane
+        const int d = T == 3 ? 4 : T == 4 ? 2 : 1;
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             if (r & d) continue;
             const int c0 = vq_scls(T, r, 0), c1 = vq_scls(T, r, 1);
             uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
-            uint32_t X = R[r], Y = R[r + d];
-            R[r]     = __vminu2((X + av) & EV, ((Y + bv) & FF) | ONE);
-            R[r + d] = __vminu2((X + bv) & EV, ((Y + av) & FF) | ONE);
-        }
-    } else {                                            // pair = the two halves of each register
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int c = vq_scls(5, r, 0);             // class of p (low half); the high half is p+32: complement
-            uint32_t ab = __byte_perm(Cb, 0, vq_sel(c, 3 - c)), ba = __byte_perm(Cb, 0, vq_sel(3 - c, c));
-            uint32_t t1 = R[r] + ab, t2 = R[r] + ba;      // t1 = [p+a, p32+b], t2 = [p+b, p32+a]
-            uint32_t lo = __byte_perm(t1, t2, 0x5410), hi = __byte_perm(t1, t2, 0x7632);   // [t1.lo, t2.lo], [t1.hi, t2.hi]
-            R[r] = __vminu2(lo & EV, (hi & FF) | ONE);
+            uint32_t X = R[r] & EV, Y = (R[r + d] & FF) | ONE;
+            R[r]     = __vminu2(X + av, Y + bv);
+            R[r + d] = __vminu2(X + bv, Y + av);
         }
     }
 }
-__device__ __forceinline__ void vq_step_rt(int T, uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned lane) {
-    switch (T) { case 0: vq_step<0>(R, Cbase, L, lane); break; case 1: vq_step<1>(R, Cbase, L, lane); break;
-                 case 2: vq_step<2>(R, Cbase, L, lane); break; case 3: vq_step<3>(R, Cbase, L, lane); break;
-                 case 4: vq_step<4>(R, Cbase, L, lane); break; default: vq_step<5>(R, Cbase, L, lane); }
-}
-__device__ __forceinline__ uint32_t vq_decisions(const uint32_t (&R)[8]) {   // bit (2r+h) = LSB of half h of R[r]
-    uint32_t acc = R[0] & 0x00010001u;
+__device__ __forceinline__ uint32_t vq_decisions(const uint32_t (&R)[8]) {   // survivor bit of (reg r, half h) -> bit 8h + r
+    uint32_t acc = 0;
 #pragma unroll
-    for (int r = 1; r < 8; r++) acc |= (R[r] << (2 * r)) & (0x00010001u << (2 * r));
-    return (acc | (acc >> 15)) & 0xFFFFu;
+    for (int r = 0; r < 8; r++) acc |= (R[r] << r) & (0x01000100u << r);      // left shifts only: IMAD.SHL on the FMA pipe
+    return ((acc >> 8) & 0xFFu) | ((acc >> 16) & 0xFF00u);
 }
-// branch-metric byte vectors (index = cA<<1 | cB)
-__device__ __forceinline__ uint32_t vq_bm_ab(int sA, int sB) {
-    int x = 2 * (sA + sB), y = 2 * (sA - sB) + 14;          // c00 = tA+tB, c01 = tA+14-tB, c10 = 28-c01, c11 = 28-c00
-    return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)(28 - y) << 16) | ((uint32_t)(28 - x) << 24);
+// branch-metric byte vectors (byte index = cA<<1 | cB) from soft values in bytes B0 (A) and B0+1 (B) of the packed word w
+__device__ __forceinline__ int vq_dp4a_us(uint32_t a, int b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+template <int B0> __device__ __forceinline__ uint32_t vq_bm_ab(uint32_t w) {
+    // x = tA + tB, y = tA - tB + 14;  bytes [x, y, 28 - y, 28 - x] = c00, c01, c10, c11
+    const int x = vq_dp4a_us(w, (int)(0x0202u << (8 * B0)), 0);
+    const int y = vq_dp4a_us(w, (int)(0xFE02u << (8 * B0)), 14);
+    return 0x1C1C0000u + (uint32_t)x * 0xFF000001u + (uint32_t)y * 0xFFFF0100u;
 }
-__device__ __forceinline__ uint32_t vq_bm_a(int s) { uint32_t c0 = 2 * s, c1 = 14 - 2 * s; return c0 | (c0 << 8) | (c1 << 16) | (c1 << 24); }
-__device__ __forceinline__ uint32_t vq_bm_b(int s) { uint32_t c0 = 2 * s, c1 = 14 - 2 * s; return c0 | (c1 << 8) | (c0 << 16) | (c1 << 24); }
+template <int B0> __device__ __forceinline__ uint32_t vq_bm_a(uint32_t w) {      // only A present: bytes [c0, c0, c1, c1]
+    const int s = vq_dp4a_us(w, (int)(0x01u << (8 * B0)), 0);
+    return 0x0E0E0000u + (uint32_t)s * (0x00000202u - 0x02020000u);
+}
+template <int B0> __device__ __forceinline__ uint32_t vq_bm_b(uint32_t w) {      // only B present: bytes [c0, c1, c0, c1]
+    const int s = vq_dp4a_us(w, (int)(0x01u << (8 * B0)), 0);
+    return 0x0E000E00u + (uint32_t)s * (0x00020002u - 0x02000200u);
+}
 
 template <int CODE_RATE>
 __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t* __restrict__ soft, uint64_t soft_stride,
         uint32_t nframes, const FrameInfo* __restrict__ info, VitJob job, DevTables T,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t* __restrict__ status_out, uint32_t* __restrict__ crc_out) {
     __shared__ unsigned long long s_ring[SB_VQ_RING][SB_VQ_FR];
-    __shared__ uint32_t s_crc[256];
+    __shared__ uint32_t s_crc[16];                     // CRC-32 (reflected 0xEDB88320, core/inc/CRC32.h:76) four bits at a time
     __shared__ uint8_t s_scr[128];
     __shared__ uint8_t s_win[SB_VQ_FR][48];
     const int lane = threadIdx.x & 31, q = lane & 3;
     const unsigned QM = 0xFu << (lane & 28);           // the 4 lanes of this code block: quads run as independent sub-warps
     const int fb = (threadIdx.x >> 2);                 // code block within the CTA
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = __ldg(T.crc32 + i);
+    if (threadIdx.x < 16) { uint32_t c = threadIdx.x; for (int k = 0; k < 4; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; s_crc[threadIdx.x] = c; }
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_scr[i] = __ldg(T.scramble + i);
     __syncthreads();
     const uint32_t f = blockIdx.x * SB_VQ_FR + fb;
@@ -127,7 +134,6 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
     const uint8_t* sp = soft + (size_t)f * soft_stride;
     uint8_t* op = out + (size_t)f * out_stride;
     const uint32_t out_cap = (uint32_t)(out_stride < 0xFFFFFFFFull ? out_stride : 0xFFFFFFFFull);
-    // lane constants
     VqLane LC;
 #pragma unroll
     for (int t = 0; t < 6; t++) {
@@ -135,74 +141,76 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         LC.swz[t] = (unsigned)((0 ^ lc) | ((1 ^ lc) << 4) | ((2 ^ lc) << 8) | ((3 ^ lc) << 12));
     }
     {
-        const uint32_t EV = 0x00FE00FEu, FF = 0x00FF00FFu, ONE = 0x00010001u;
+        const uint32_t EV = 0xFE00FE00u, FF = 0xFF00FF00u, ONE = 0x01000100u;
         int b0 = (q >> 1) & 1, b1 = q & 1;              // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
-        LC.m1[0] = b0 ? FF : EV; LC.o1[0] = b0 ? ONE : 0u; LC.m2[0] = b0 ? EV : FF; LC.o2[0] = b0 ? 0u : ONE;
-        LC.m1[1] = b1 ? FF : EV; LC.o1[1] = b1 ? ONE : 0u; LC.m2[1] = b1 ? EV : FF; LC.o2[1] = b1 ? 0u : ONE;
+        LC.lm[0] = b0 ? FF : EV; LC.lo[0] = b0 ? ONE : 0u;
+        LC.lm[1] = b1 ? FF : EV; LC.lo[1] = b1 ? ONE : 0u;
     }
     // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address
     uint32_t R[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) R[r] = 0x00300030u;
-    if (q == 0) R[0] = 0x00300000u;
+    for (int r = 0; r < 8; r++) R[r] = 0x30003000u;
+    if (q == 0) R[0] = 0x30000000u;
     const uint32_t end = L * 8u + 16u + 6u;
-    uint32_t t = 0, ob = 0, tmod = 0;                   // tmod = t % 6
+    uint32_t t = 0, ob = 0;
     uint32_t wcol = 0;                                  // ring slot of column t (t % SB_VQ_RING)
     uint32_t desc_count = 0, desc_reg = 0, byte_count = 0, crc = 0xFFFFFFFFu, fcs = 0, verdict = E_SUCCESS, nraw = 0;
     bool done = false;
-    uint16_t* ring16 = (uint16_t*)&s_ring[0][0];
+    uint16_t* ring16 = (uint16_t*)&s_ring[0][0] + fb * 4 + q;      // + col * (4 * SB_VQ_FR)
     uint32_t pos_soft = 0;
 
-    auto after_group = [&]() {
+    // normalisation + traceback triggers, evaluated after every puncture group; tm = t % 6 (compile time in the main loop),
+    // cslot = ring slot of column t
+    auto after_group = [&](const uint32_t tm, const uint32_t cslot) {
         if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465
             uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
-            m = min(m & 0xFFFFu, m >> 16);
+            m = min(m & 0xFFFFu, m >> 16) >> 8;         // smallest metric byte of this lane
             m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            m &= 0xFEu;
-            const uint32_t mv = m * 0x00010001u;
+            const uint32_t mv = (m & 0xFEu) * 0x01000100u;
 #pragma unroll
-            for (int r = 0; r < 8; r++) R[r] -= mv;        // every half >= m: no borrow between halves
+            for (int r = 0; r < 8; r++) R[r] -= mv;        // every metric byte >= m: no borrow between halves
         }
         uint32_t nout = 0, la = 0;                      // viterbi.hpp:182-203
-        if (!done) {
-            if (t >= end) { nout = end - ob - 6u; la = t - end; }
-            else if (t >= ob + depth + look + 6u) { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
-        }
-        if (nout) {                                    // nout is uniform inside the quad
-            // best state: smallest (metric, state) key over the 64 states (viterbicore.h:468-520)
+        if (t >= end) { nout = end - ob - 6u; la = t - end; }
+        else if (t >= ob + depth + look + 6u) { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
+        if (nout) {                                     // uniform inside the quad
+            // best state: smallest (metric, state index) over the 64 slots (viterbicore.h:468-520)
             uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
-            m = min(m & 0xFFFFu, m >> 16);
+            m = min(m & 0xFFFFu, m >> 16) >> 8;
             m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            uint32_t best = 64;
+            uint32_t best = 0xFFFFu;                    // (state index << 8) | address
 #pragma unroll
             for (int r = 0; r < 8; r++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    uint32_t v = h ? (R[r] >> 16) : (R[r] & 0xFFFFu);
-                    uint32_t A = ((uint32_t)q << 4) | (r << 1) | h;
-                    uint32_t n = ((A << tmod) | (A >> (6u - tmod))) & 63u;     // state index of this slot at time t
-                    if (v == m && n < best) best = n;
+                    uint32_t v = h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu);
+                    uint32_t A = ((uint32_t)q << 4) | (h << 3) | r;
+                    uint32_t n = ((A << tm) | (A >> (6u - tm))) & 63u;         // state index of this slot at time t
+                    uint32_t key = (n << 8) | A;
+                    if (v == m && key < best) best = key;
                 }
             }
             best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
             __syncwarp(QM);
             if (q == 0) {
-                int pos = (int)(best | ((m & 1u) << 6));
-                uint32_t col = wcol, cm = tmod;         // ring slot / phase of the column being read
-                auto back = [&]() {
+                // traceback in address space: survivor bit d of slot A at column c = bit A of that column's word;
+                // the predecessor slot is A with bit (6 - c%6)%6 replaced by d; d is also the decoded bit of column c.
+                uint32_t A = best & 63u, col = cslot, cm = tm;
+                auto back = [&]() -> uint32_t {
+                    const unsigned long long w = s_ring[col][fb];
+                    const uint32_t d = (uint32_t)(w >> A) & 1u;
+                    const uint32_t j = cm ? 6u - cm : 0u;
+                    A = (A & ~(1u << j)) | (d << j);
                     col = col ? col - 1 : SB_VQ_RING - 1; cm = cm ? cm - 1 : 5;
-                    pos = (pos >> 1) & 0x3F;
-                    unsigned long long w = s_ring[col][fb];
-                    uint32_t A = (((uint32_t)pos | ((uint32_t)pos << 6)) >> cm) & 63u;   // ror6(pos, cm)
-                    pos |= (int)((w >> A) & 1ull) << 6;
+                    return d;
                 };
                 for (uint32_t i = 0; i < la; i++) back();
-                const uint32_t nbytes = nout >> 3;
-                uint8_t* win = s_win[fb];
+                const uint32_t nbytes = nout >> 3;      // <= 35 (final flush)
+                uint8_t* win = s_win[fb];               // bytes come out last-first; the sink needs them first-first
                 for (uint32_t b = 0; b < nbytes; b++) {
                     uint32_t ch = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { ch = (ch << 1) | (uint32_t)((pos >> 6) & 1); back(); }
+                    for (int j = 0; j < 8; j++) ch = (ch << 1) | back();
                     win[nbytes - 1 - b] = (uint8_t)ch;
                 }
                 if (job.raw) {
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
                         if (byte_count < (uint32_t)((int)L - 4)) {
                             if (byte_count < out_cap) op[byte_count] = (uint8_t)o;
                             byte_count++;
-                            crc = (crc >> 8) ^ s_crc[(o ^ crc) & 0xFF];
+                            crc ^= o; crc = (crc >> 4) ^ s_crc[crc & 15]; crc = (crc >> 4) ^ s_crc[crc & 15];
                         } else if (byte_count < L) {
                             if (byte_count < out_cap) op[byte_count] = (uint8_t)o;
                             byte_count++;
@@ -234,9 +242,12 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
             __syncwarp(QM);
         }
     };
-    auto commit = [&]() {                               // after a step: store survivor bits of the new column
-        t++; tmod = tmod == 5 ? 0 : tmod + 1; wcol = wcol == SB_VQ_RING - 1 ? 0 : wcol + 1;
-        ring16[(wcol * SB_VQ_FR + fb) * 4 + q] = (uint16_t)vq_decisions(R);
+    // store the survivor bits of the new column; k = position inside the 6-step chunk (0 in the tail); returns its slot
+    auto commit = [&](const uint32_t k) -> uint32_t {
+        t++;
+        uint32_t slot = wcol + k + 1; if (slot >= SB_VQ_RING) slot -= SB_VQ_RING;
+        ring16[slot * (4 * SB_VQ_FR)] = (uint16_t)vq_decisions(R);
+        return slot;
     };
 
     // main loop: 6 trellis steps (one phase cycle) per iteration; the next chunk's soft values are prefetched
@@ -249,47 +260,60 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         else { uint32_t b[9];
 #pragma unroll
                for (int i = 0; i < 9; i++) b[i] = __ldg(sp + pos + i);
-               a0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); a1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24); a2 = b[8]; }
+               // keep every puncture group inside one word: w0 = b0 b1 b2 -, w1 = b3 b4 b5 -, w2 = b6 b7 b8 -
+               a0 = b[0] | (b[1] << 8) | (b[2] << 16); a1 = b[3] | (b[4] << 8) | (b[5] << 16); a2 = b[6] | (b[7] << 8) | (b[8] << 16); }
     };
     fetch(0, w0, w1, w2);
-#define SV(i) ((int)(((i) < 4 ? w0 >> (8 * (i)) : (i) < 8 ? w1 >> (8 * ((i) - 4)) : w2 >> (8 * ((i) - 8))) & 0xFFu))
     while (!done && pos_soft + CHUNK_BYTES <= nsoft) {
         uint32_t n0, n1, n2; fetch(pos_soft + CHUNK_BYTES, n0, n1, n2);
         pos_soft += CHUNK_BYTES;
+        uint32_t sl;
         if (CODE_RATE == CR_12) {
-            vq_step<0>(R, vq_bm_ab(SV(0), SV(1)), LC, QM);   commit(); after_group();
-            vq_step<1>(R, vq_bm_ab(SV(2), SV(3)), LC, QM);   commit(); after_group();
-            vq_step<2>(R, vq_bm_ab(SV(4), SV(5)), LC, QM);   commit(); after_group();
-            vq_step<3>(R, vq_bm_ab(SV(6), SV(7)), LC, QM);   commit(); after_group();
-            vq_step<4>(R, vq_bm_ab(SV(8), SV(9)), LC, QM);   commit(); after_group();
-            vq_step<5>(R, vq_bm_ab(SV(10), SV(11)), LC, QM); commit(); after_group();
+            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); sl = commit(0); after_group(1, sl);
+            vq_step<1>(R, vq_bm_ab<2>(w0), LC, QM); sl = commit(1); after_group(2, sl);
+            vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); sl = commit(2); after_group(3, sl);
+            vq_step<3>(R, vq_bm_ab<2>(w1), LC, QM); sl = commit(3); after_group(4, sl);
+            vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); sl = commit(4); after_group(5, sl);
+            vq_step<5>(R, vq_bm_ab<2>(w2), LC, QM); sl = commit(5); after_group(0, sl);
         } else if (CODE_RATE == CR_34) {
-            vq_step<0>(R, vq_bm_ab(SV(0), SV(1)), LC, QM); commit();
-            vq_step<1>(R, vq_bm_a(SV(2)), LC, QM);         commit();
-            vq_step<2>(R, vq_bm_b(SV(3)), LC, QM);         commit(); after_group();
-            vq_step<3>(R, vq_bm_ab(SV(4), SV(5)), LC, QM); commit();
-            vq_step<4>(R, vq_bm_a(SV(6)), LC, QM);         commit();
-            vq_step<5>(R, vq_bm_b(SV(7)), LC, QM);         commit(); after_group();
+            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
+            vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  commit(1);
+            vq_step<2>(R, vq_bm_b<3>(w0), LC, QM);  sl = commit(2); after_group(3, sl);
+            vq_step<3>(R, vq_bm_ab<0>(w1), LC, QM); commit(3);
+            vq_step<4>(R, vq_bm_a<2>(w1), LC, QM);  commit(4);
+            vq_step<5>(R, vq_bm_b<3>(w1), LC, QM);  sl = commit(5); after_group(0, sl);
         } else {
-            vq_step<0>(R, vq_bm_ab(SV(0), SV(1)), LC, QM); commit();
-            vq_step<1>(R, vq_bm_a(SV(2)), LC, QM);         commit(); after_group();
-            vq_step<2>(R, vq_bm_ab(SV(3), SV(4)), LC, QM); commit();
-            vq_step<3>(R, vq_bm_a(SV(5)), LC, QM);         commit(); after_group();
-            vq_step<4>(R, vq_bm_ab(SV(6), SV(7)), LC, QM); commit();
-            vq_step<5>(R, vq_bm_a(SV(8)), LC, QM);         commit(); after_group();
+            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
+            vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  sl = commit(1); after_group(2, sl);
+            vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); commit(2);
+            vq_step<3>(R, vq_bm_a<2>(w1), LC, QM);  sl = commit(3); after_group(4, sl);
+            vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); commit(4);
+            vq_step<5>(R, vq_bm_a<2>(w2), LC, QM);  sl = commit(5); after_group(0, sl);
         }
+        wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING;
         w0 = n0; w1 = n1; w2 = n2;
     }
-#undef SV
-    // tail: remaining whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft)
-    while (!done && pos_soft + GROUP <= nsoft) {
-        int s0 = __ldg(sp + pos_soft), s1 = __ldg(sp + pos_soft + 1);
-        int s2 = GROUP > 2 ? (int)__ldg(sp + pos_soft + 2) : 0, s3 = GROUP > 3 ? (int)__ldg(sp + pos_soft + 3) : 0;
-        pos_soft += GROUP;
-        vq_step_rt((int)tmod, R, vq_bm_ab(s0, s1), LC, QM); commit();
-        if (GSTEPS >= 2) { vq_step_rt((int)tmod, R, vq_bm_a(s2), LC, QM); commit(); }
-        if (GSTEPS >= 3) { vq_step_rt((int)tmod, R, vq_bm_b(s3), LC, QM); commit(); }
-        after_group();
+    // tail: whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft).
+    // Rare and short, so phases are dispatched at run time.
+    {
+        uint32_t tm = 0, sl = wcol;                     // t % 6 (the main loop always leaves it at 0)
+        auto step_rt = [&](uint32_t Cbase) {
+            switch (tm) { case 0: vq_step<0>(R, Cbase, LC, QM); break; case 1: vq_step<1>(R, Cbase, LC, QM); break;
+                          case 2: vq_step<2>(R, Cbase, LC, QM); break; case 3: vq_step<3>(R, Cbase, LC, QM); break;
+                          case 4: vq_step<4>(R, Cbase, LC, QM); break; default: vq_step<5>(R, Cbase, LC, QM); }
+            sl = commit(0); wcol = sl;
+            tm = tm == 5 ? 0 : tm + 1;
+        };
+        while (!done && pos_soft + GROUP <= nsoft) {
+            uint32_t w = __ldg(sp + pos_soft) | ((uint32_t)__ldg(sp + pos_soft + 1) << 8);
+            if (GROUP > 2) w |= (uint32_t)__ldg(sp + pos_soft + 2) << 16;
+            if (GROUP > 3) w |= (uint32_t)__ldg(sp + pos_soft + 3) << 24;
+            pos_soft += GROUP;
+            step_rt(vq_bm_ab<0>(w));
+            if (GSTEPS >= 2) step_rt(vq_bm_a<2>(w));
+            if (GSTEPS >= 3) step_rt(vq_bm_b<3>(w));
+            after_group(tm, sl);
+        }
     }
     if (q == 0) {
         if (!job.raw) { if (verdict == E_SUCCESS) verdict = E_FAILED; status_out[f] = verdict; crc_out[f] = fcs; }
