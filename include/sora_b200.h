@@ -9,6 +9,10 @@
  *                                       kernel/bb/demod11/fb11ademod_config.hpp:169-242, driven like RxThread
  *                                       kernel/bb/demod11/fb11a_demod.cpp:29-81; legacy shape BB11ARxCarrierSense +
  *                                       BB11ARxFrameDemod, kernel/inc/bb/bba.h:203-262
+ *   sb200_rx11b_batch              <->  the whole graph behind TMemSamples of CreateDemodGraph (802.11b)
+ *                                       kernel/bb/demod11/fb11bdemod_config.hpp:123-180, driven like MAC11b_Receive
+ *                                       kernel/bb/demod11/fb11b_demod.cpp:26-79; legacy shape BB11BSpd + BB11BRx,
+ *                                       kernel/inc/bb/bbb.h:176-248
  *   sb200_viterbi_k7               <->  T11aViterbi<TR_MAX,N_IN,DEPTH,LOOKAHEAD>::Filter
  *                                       kernel/bb/Brick11/src/viterbi.hpp:104-237 (BASELINE config #5)
  *   sb200_rx11a_taps               <->  BB_DEBUG `_dump_symbol` taps  kernel/brick/inc/bb_debug.h:5-41
@@ -40,6 +44,9 @@ extern "C" {
 #define SB200_FRAME_FAILED        0x8000FFFFu  /* E_ERROR_FAILED */
 #define SB200_FRAME_PLCP_FAIL     0x80000005u  /* E_ERROR_PLCP_HEADER_FAIL */
 #define SB200_FRAME_CRC32_FAIL    0x80000006u  /* E_ERROR_CRC32_FAIL */
+#define SB200_FRAME_SFD_FAIL      0x80000004u  /* E_ERROR_SFD_FAIL */
+#define SB200_FRAME_SFD_TIMEOUT   0x80000008u  /* E_ERROR_SFD_TIMEOUT */
+#define SB200_FRAME_SYNC_TIMEOUT  0x80000009u  /* E_ERROR_SYNC_TIMEOUT */
 #define SB200_FRAME_NONE          0x8000F001u  /* slot exhausted before any frame event (the reference just runs out of samples) */
 
 #define SB200_CR_12 0   /* Brick11/src/ieee80211const.h:13-18 */
@@ -87,6 +94,21 @@ int sb200_set_option(sb200_handle* h, const char* name, uint64_t value);
 int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples,
                       const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
                       uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, void* cuda_stream);
+
+/* 802.11b (DSSS 1/2 Mbps, CCK 5.5/11 Mbps, long preamble).  Same slot convention as sb200_rx11a_batch but 44 Msps samples.
+ * out_bytes row i receives frame_length-1 PSDU bytes: like TBB11bFrameSink (PHY_11b.hpp:721-739) the verdict is taken on the
+ * first three FCS bytes and the fourth is never delivered; crc32 holds those three bytes (little endian, top byte 0). */
+typedef struct sb200_frame_result_11b {
+    uint32_t status;        /* SB200_FRAME_* */
+    uint32_t rate_kbps;     /* CF_11bRxVector::data_rate_kbps: 1000 / 2000 / 5500 / 11000 */
+    uint32_t length;        /* CF_11bRxVector::frame_length (PSDU bytes incl. FCS) */
+    uint32_t crc32;         /* first three FCS bytes as received */
+    uint32_t sample_index;  /* CF_MemSamples::mem_sample_index at the event (44 Msps samples into the slot) */
+    uint32_t detect_vec;    /* index of the first 4-sample vector routed to the demod branch */
+} sb200_frame_result_11b;
+int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples,
+                      const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
+                      uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, void* cuda_stream);
 
 /* Standalone K=7 Viterbi over `nblocks` independent blocks of `nsoft` soft values (uint8 0..7, one per coded bit after
  * puncturing; block b starts at soft + b*soft_stride).  frame_len_bytes L sets the flush point 8L+16+6 exactly like

@@ -1,5 +1,5 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see ops.h).  C entry points for tests/ (ctypes) and bench.py's cpu_baseline.
-#include "rx11a.h"
+#include "rx11b.h"
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -97,6 +97,31 @@ const int16_t* sbo_sts_pattern() { return (const int16_t*)tables().sts_pattern; 
 void sbo_tables(const uint8_t** vit_ma, const uint8_t** vit_mb, const uint8_t** demap4 /*4x256*/) {
     const Tables& T = tables(); *vit_ma = &T.vit_ma[0][0]; *vit_mb = &T.vit_mb[0][0]; *demap4 = T.demap_bpsk;
 }
+// ---- 802.11b ----
+struct sbo_frame_result_11b { uint32_t status, rate_kbps, length, crc32, sample_index, detect_vec; };
+int sbo_rx11b_run(const int16_t* iq, uint64_t nsamples, int max_frames, sbo_frame_result_11b* res, uint8_t* out, uint64_t out_stride) {
+    Rx11b rx;
+    return rx.run((const c16*)iq, (size_t)nsamples, (FrameResult11b*)res, out, (size_t)out_stride, max_frames);
+}
+void sbo_rx11b_batch(const int16_t* iq, const uint64_t* off, const uint32_t* len, uint32_t nframes,
+                     sbo_frame_result_11b* res, uint8_t* out, uint64_t out_stride, int nthreads) {
+    std::atomic<uint32_t> next(0);
+    auto work = [&]() {
+        Rx11b rx;
+        for (;;) {
+            uint32_t i = next.fetch_add(1); if (i >= nframes) break;
+            FrameResult11b r; memset(&r, 0, sizeof r);
+            int n = rx.run((const c16*)iq + off[i], len[i], &r, out ? out + (size_t)i * out_stride : nullptr, (size_t)out_stride, 1);
+            if (n == 0) { memset(&r, 0, sizeof r); r.status = E_NO_FRAME; }
+            memcpy(&res[i], &r, sizeof r);
+        }
+    };
+    if (nthreads <= 1) { work(); return; }
+    std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+}
+uint8_t sbo_cck11_decode(const int16_t* chips8, int16_t* last2, int* even) { c16 l{last2[0], last2[1]}; uint8_t b = cck11_decode((const c16*)chips8, l, *even); last2[0] = l.re; last2[1] = l.im; return b; }
+
 uint32_t sbo_crc32(const uint8_t* p, uint64_t n) { uint32_t c = 0xFFFFFFFFu; for (uint64_t i = 0; i < n; i++) c = (c >> 8) ^ tables().crc32_lut[p[i] ^ (c & 0xFF)]; return ~c; }
 
 } // extern "C"

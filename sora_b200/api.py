@@ -16,8 +16,10 @@ CR_12, CR_23, CR_34 = 0, 1, 2
 RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("nsym", "<u4"),
                          ("detect_index", "<u4"), ("cfo_est", "<i2"), ("peak_index", "<u2")])
 
+RESULT11B_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("sample_index", "<u4"), ("detect_vec", "<u4")])
+
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -39,6 +41,7 @@ def load_library():
         lib.sb200_rx11a_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.sb200_rx11a_batch.restype = C.c_int
+        lib.sb200_rx11b_batch.argtypes = lib.sb200_rx11a_batch.argtypes; lib.sb200_rx11b_batch.restype = C.c_int
         lib.sb200_viterbi_k7.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.sb200_viterbi_k7.restype = C.c_int
@@ -105,6 +108,18 @@ class Engine:
         nf = len(off)
         res = np.zeros(nf, dtype=RESULT_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
         self.rx11a_raw(_ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
+        return res, out
+
+    def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
+        self._check(self._lib.sb200_rx11b_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11b_batch")
+
+    def rx11b_batch(self, iq, frame_off, frame_len, out_stride=4096):
+        """802.11b: iq int16 [n,2] at 44 Msps; returns (results RESULT11B_DTYPE [F], bytes uint8 [F, out_stride])."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32)
+        nf = len(off)
+        res = np.zeros(nf, dtype=RESULT11B_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+        self.rx11b_raw(_ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
         return res, out
 
     def rx11a_taps(self, iq, frame_off, frame_len, max_sym):

@@ -2,6 +2,7 @@
 // Single translation unit: the kernels live in the .cuh files included below.
 #include "../../include/sora_b200.h"
 #include "viterbi_k7_quad.cuh"
+#include "rx11b_kernels.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -302,6 +303,41 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     }
     if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nframes * sizeof(sb200_frame_result), cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (host_out) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+extern "C" int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                                 uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, void* cuda_stream) {
+    static_assert(sizeof(sb200_frame_result_11b) == sizeof(Result11b), "result layout");
+    if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (nframes == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len), iq_dev = is_device_ptr(iq);
+    if (!off_dev || !len_dev || !iq_dev) {              // bounds are checked on the host copy of the slot table when there is one
+        if (!off_dev && !len_dev) for (uint32_t i = 0; i < nframes; i++) if (frame_off[i] + frame_len[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+    }
+    const uint32_t* d_iq; const uint64_t* d_off; const uint32_t* d_len;
+    if (iq_dev) d_iq = (const uint32_t*)iq; else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
+    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, frame_off, nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
+    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, frame_len, nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
+    const uint64_t row = 4096;
+    CK(h->out.need(nframes * row)); CK(h->res.need(nframes * sizeof(Result11b)));
+    const bool res_dev = is_device_ptr(res);
+    Result11b* d_res = res_dev ? (Result11b*)res : (Result11b*)h->res.p;
+    CK(cudaEventRecord(h->ev0, st));
+    k_rx11b<<<(nframes + 63) / 64, 64, 0, st>>>(d_iq, d_off, d_len, nframes, h->cca_thr, (uint8_t*)h->out.p, row, d_res);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 0; h->launches += 1;
+    CK(cudaGetLastError());
+    bool host_out = false;
+    if (out_bytes && out_stride) {
+        const size_t w = out_stride < row ? out_stride : row; const bool od = is_device_ptr(out_bytes);
+        CK(cudaMemcpy2DAsync(out_bytes, out_stride, h->out.p, row, w, nframes, od ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        host_out |= !od;
+    }
+    if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nframes * sizeof(Result11b), cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
     return SB200_OK;
 }

@@ -189,3 +189,104 @@ def make_frames(nframes, psdu_len=1500, rate_kbps=54000, seed0=0x5EED0000, snr_d
     td = modulate(ps, rate_kbps)
     rng = np.random.default_rng(seed0 & 0xFFFFFFFF)
     return to_iq16(td, gain=gain, lead=lead, trail=trail, snr_db=snr_db, cfo_hz=cfo_hz, rng=rng), ps
+
+
+# =====================================================================================================================
+# 802.11b (DSSS / CCK) PPDUs at 44 Msps (4 samples per chip), long preamble — IEEE 802.11b-1999 clause 18.
+# Float modulator for test input only (same role as the 11a generator above).
+# =====================================================================================================================
+_BARKER = np.array([1, -1, 1, 1, -1, 1, 1, 1, -1, -1, -1], dtype=np.float64)
+_SIGNAL_11B = {1000: 0x0A, 2000: 0x14, 5500: 0x37, 11000: 0x6E}
+
+def _crc16_ccitt_reflected(data):
+    c = 0xFFFF
+    for b in data:
+        c ^= b
+        for _ in range(8):
+            c = (c >> 1) ^ 0x8408 if c & 1 else c >> 1
+    return (~c) & 0xFFFF
+
+def _scramble_11b(bits, state=0x1B):
+    """Self-synchronising scrambler s[k] = b[k] ^ s[k-4] ^ s[k-7]; `state` bit i = s[k-1-i]."""
+    out = np.zeros_like(bits)
+    st = state
+    for k, b in enumerate(bits):
+        s = int(b) ^ ((st >> 3) & 1) ^ ((st >> 6) & 1)
+        out[k] = s
+        st = ((st << 1) | s) & 0x7F
+    return out
+
+_DQPSK = {(0, 0): 0, (0, 1): 1, (1, 1): 2, (1, 0): 3}          # (d0, d1) -> quarter turns, counter-clockwise
+_QPSK = {(0, 0): 0, (0, 1): 1, (1, 0): 2, (1, 1): 3}           # CCK phi2..phi4 encoding (Table 18-?): 00,01,10,11 -> 0, pi/2, pi, 3pi/2
+
+def modulate_11b(psdu, rate_kbps=11000, amp=90.0, shape=True):
+    """psdu: uint8 [L] (FCS included).  Returns complex chips-domain waveform at 44 Msps in int8 units."""
+    psdu = np.asarray(psdu, np.uint8)
+    L = len(psdu)
+    service = 0x04                                      # locked clocks
+    if rate_kbps == 11000:
+        lp = L * 8 / 11.0; length = int(np.ceil(lp))
+        if length - lp >= 8 / 11.0 - 1e-12: service |= 0x80
+    elif rate_kbps == 5500:
+        length = int(np.ceil(L * 8 / 5.5))
+    else:
+        length = L * 8 * 1000 // rate_kbps
+    hdr = bytes([_SIGNAL_11B[rate_kbps], service, length & 0xFF, length >> 8])
+    crc = _crc16_ccitt_reflected(hdr)
+    hdr = hdr + bytes([crc & 0xFF, crc >> 8])
+    bits = np.concatenate([np.ones(128, np.uint8),
+                           np.unpackbits(np.frombuffer((0xF3A0).to_bytes(2, "little"), np.uint8), bitorder="little"),
+                           np.unpackbits(np.frombuffer(hdr, np.uint8), bitorder="little"),
+                           np.unpackbits(psdu, bitorder="little")])
+    sb = _scramble_11b(bits)
+    npre = 128 + 16 + 48
+    chips = []
+    ph = 0                                              # current phase in quarter turns
+    for b in sb[:npre]:                                 # DBPSK 1 Mbps preamble + header
+        ph = (ph + 2 * int(b)) & 3
+        chips.append(_BARKER * np.exp(1j * np.pi / 2 * ph))
+    d = sb[npre:]
+    if rate_kbps == 1000:
+        for b in d:
+            ph = (ph + 2 * int(b)) & 3; chips.append(_BARKER * np.exp(1j * np.pi / 2 * ph))
+    elif rate_kbps == 2000:
+        for i in range(0, len(d), 2):
+            ph = (ph + _DQPSK[(int(d[i]), int(d[i + 1]))]) & 3; chips.append(_BARKER * np.exp(1j * np.pi / 2 * ph))
+    else:
+        nb = 4 if rate_kbps == 5500 else 8
+        for k, i in enumerate(range(0, len(d), nb)):
+            w = [int(x) for x in d[i:i + nb]]
+            ph = (ph + _DQPSK[(w[0], w[1])] + (2 if (k & 1) else 0)) & 3
+            if nb == 4:
+                p2 = 2 * w[2] + 1; p3 = 0; p4 = 2 * w[3]
+            else:
+                p2 = _QPSK[(w[2], w[3])]; p3 = _QPSK[(w[4], w[5])]; p4 = _QPSK[(w[6], w[7])]
+            e = lambda q: np.exp(1j * np.pi / 2 * (q & 3))
+            p1 = ph
+            chips.append(np.array([e(p1 + p2 + p3 + p4), e(p1 + p3 + p4), e(p1 + p2 + p4), -e(p1 + p4),
+                                   e(p1 + p2 + p3), e(p1 + p3), -e(p1 + p2), e(p1)]))
+    c = np.concatenate(chips)
+    x = np.repeat(c, 4)                                 # 4 samples per chip
+    if shape:                                           # raised cosine, beta 0.5, +-3 chips: zero ISI at the chip centres
+        n = np.arange(-12, 13); t = n / 4.0; beta = 0.5
+        den = 1.0 - (2 * beta * t) ** 2
+        h = np.sinc(t) * np.cos(np.pi * beta * t) / np.where(np.abs(den) < 1e-9, 1.0, den)
+        h[np.abs(den) < 1e-9] = np.pi / 4 * np.sinc(1 / (2 * beta))
+        imp = np.zeros(len(c) * 4, np.complex128); imp[::4] = c            # impulses at chip centres
+        x = np.convolve(imp, h, mode="same")
+    return x * amp
+
+def make_frames_11b(nframes, psdu_len=1500, rate_kbps=11000, seed0=0xB11B0000, snr_db=None, lead=400, trail=200, gain=1.0, cfo_hz=0.0):
+    """Returns (iq int16 [F, slot, 2], psdus uint8 [F, psdu_len]); slot length is a multiple of 28."""
+    ps = np.zeros((nframes, psdu_len), np.uint8); tds = []
+    for i in range(nframes):
+        r = np.random.RandomState(seed=(seed0 + i) & 0xFFFFFFFF)
+        ps[i] = psdu_with_fcs(r.randint(0, 256, psdu_len - 4).astype(np.uint8))
+        tds.append(modulate_11b(ps[i], rate_kbps))
+    n = len(tds[0])
+    tot = lead + n + trail; trail += (-tot) % 28
+    rng = np.random.default_rng(seed0 & 0xFFFFFFFF)
+    td = np.stack(tds)
+    if cfo_hz:
+        td = td * np.exp(2j * np.pi * cfo_hz * np.arange(n) / 44e6)
+    return to_iq16(td, gain=gain, lead=lead, trail=trail, snr_db=snr_db, rng=rng), ps

@@ -80,3 +80,19 @@ def ifft64(x):
     x = np.ascontiguousarray(x, dtype=np.int16); o = np.zeros((64, 2), np.int16); lib().sbo_ifft64(_p(x), _p(o)); return o
 def crc32(b):
     b = np.ascontiguousarray(b, dtype=np.uint8); return int(lib().sbo_crc32(_p(b), C.c_uint64(len(b))))
+
+RES11B_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("sample_index", "<u4"), ("detect_vec", "<u4")])
+
+def rx11b_run(iq, max_frames=8, out_stride=4096):
+    iq = np.ascontiguousarray(iq, dtype=np.int16)
+    res = np.zeros(max_frames, dtype=RES11B_DTYPE); out = np.zeros((max_frames, out_stride), dtype=np.uint8)
+    n = lib().sbo_rx11b_run(_p(iq), C.c_uint64(iq.shape[0]), C.c_int(max_frames), _p(res), _p(out), C.c_uint64(out_stride))
+    return res[:n], out[:n]
+
+def rx11b_batch(iq, off, length, out_stride=4096, nthreads=1):
+    iq = np.ascontiguousarray(iq, dtype=np.int16)
+    off = np.ascontiguousarray(off, dtype=np.uint64); length = np.ascontiguousarray(length, dtype=np.uint32)
+    nf = len(off)
+    res = np.zeros(nf, dtype=RES11B_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+    lib().sbo_rx11b_batch(_p(iq), _p(off), _p(length), C.c_uint32(nf), _p(res), _p(out), C.c_uint64(out_stride), C.c_int(nthreads))
+    return res, out
