@@ -222,7 +222,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        try: traffic = json.load(open(tp)).get("k_viterbi_k7_dram_bytes_per_launch")
+        try: tj = json.load(open(tp)); traffic = tj.get("k_viterbi_quad_dram_bytes_per_frame", 0) * F or None
         except Exception: traffic = None
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -232,7 +232,7 @@ def main():
                        "parallelism": f"independent slots, {world} GPU(s), no data-path collective",
                        "l2_policy": "input 2.6 GB per step >> 126 MB L2 (no flush needed)" if F * SLOT * 4 > 4e8 else "input smaller than L2: increase --frames"},
             "kernel_ms": {"carrier_sense": float(ktimes[0]), "ofdm_front_end": float(ktimes[1]), "viterbi_descramble_crc": vit_ms, "pack": float(ktimes[3])},
-            "roofline": {"bound": "hbm", "kernel": "k_viterbi_k7", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "k_viterbi_quad<CR_34>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": how,
                          "note": "achieved = 4.154 B/sample x samples per launch / Viterbi kernel time; the chain is integer-ALU/issue bound, not HBM bound (DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e}

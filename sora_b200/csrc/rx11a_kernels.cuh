@@ -248,39 +248,72 @@ __device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 
 }
 
 #define SB_FRONT_WARPS 4
+// Two OFDM symbols are transformed at once: lanes 0-15 run the three radix stages of symbol A, lanes 16-31 those of
+// symbol B (16 butterflies per stage = 16 lanes, so every lane is busy); the first stage consumes the freq-compensated
+// time samples straight from registers.  Only the part behind the FFT (phase compensation from the pilot recurrence)
+// is serial across symbols, and there every lane owns two subcarriers.
 __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
         const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, FrameInfo* __restrict__ info,
         uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps) {
-    __shared__ uint32_t s_fft[SB_FRONT_WARPS][64];
-    __shared__ uint8_t s_soft[SB_FRONT_WARPS][288];
+    __shared__ uint32_t s_fft[SB_FRONT_WARPS][2][64];
+    __shared__ __align__(16) uint8_t s_soft[SB_FRONT_WARPS][288];
+    __shared__ uint8_t s_demap[1024];
+    __shared__ uint8_t s_pilot[128];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_demap[i] = __ldg(T.demap + i);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_pilot[i] = __ldg(T.pilot_neg + i);
+    __syncthreads();
     const uint32_t f = blockIdx.x * SB_FRONT_WARPS + wib;
     if (f >= nframes) return;
     FrameInfo fi = info[f];
     if (fi.status != E_SUCCESS) return;
-    uint32_t* xb = s_fft[wib]; uint8_t* sb = s_soft[wib];
+    uint8_t* sb = s_soft[wib];
     const uint32_t* x = iq + off[f];
     const uint32_t nvec = (len[f] / 28u) * 28u / 8u;
     const uint32_t s0 = fi.detect_vec * 4u;            // first 20 Msps sample of the 144-sample LTS block
-    // ---- T11aLTS ---------------------------------------------------------------------------------
     if (fi.detect_vec + 36u > nvec) { if (lane == 0) info[f].status = E_NO_FRAME; return; }
-    const int b0 = lane, b1 = lane + 32;               // this lane's two FFT bins / time samples
-    cs16 l0 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b0))), 1), l1 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b1))), 1);   // LTS1 >> 1
-    cs16 h0 = unpack(__ldg(x + 2u * (s0 + 72u + b0))), h1 = unpack(__ldg(x + 2u * (s0 + 72u + b1)));                 // LTS2 (unshifted)
-    {   // FreqOffsetEstimate<16> (dspalg.hpp:227-243): per 4-sample vector sum of (x >> 5), then summed over vectors
+    const int half = lane >> 4, hl = lane & 15;        // FFT role: which of the two symbols, which butterfly
+    const int b0 = lane, b1 = lane + 32;               // post-FFT role: this lane's two bins
+    const int r0 = bitrev6(b0), r1 = bitrev6(b1);
+    const cs16 w64_1 = unpack(__ldg(T.tw64 + hl)), w64_2 = unpack(__ldg(T.tw64 + 16 + hl)), w64_3 = unpack(__ldg(T.tw64 + 32 + hl));
+    const cs16 w16_1 = unpack(__ldg(T.tw16 + (hl & 3))), w16_2 = unpack(__ldg(T.tw16 + 4 + (hl & 3))), w16_3 = unpack(__ldg(T.tw16 + 8 + (hl & 3)));
+    // 64-point FFT of four freq-compensated time samples per lane (n = hl + 16 j), this half-warp's buffer
+    auto fft_from_regs = [&](cs16 a, cs16 b, cs16 c, cs16 d) {
+        uint32_t* xb = s_fft[wib][half];
+        r4_butterfly(a, b, c, d, w64_1, w64_2, w64_3);                      // FFTSSE<64>, butterfly e = hl
+        xb[hl] = pack(a); xb[hl + 16] = pack(b); xb[hl + 32] = pack(c); xb[hl + 48] = pack(d);
+        __syncwarp();
+        {   const int base = (hl >> 2) * 16 + (hl & 3);                    // 4 x FFTSSE<16>
+            cs16 p = unpack(xb[base]), q = unpack(xb[base + 4]), r = unpack(xb[base + 8]), t = unpack(xb[base + 12]);
+            r4_butterfly(p, q, r, t, w16_1, w16_2, w16_3);
+            xb[base] = pack(p); xb[base + 4] = pack(q); xb[base + 8] = pack(r); xb[base + 12] = pack(t); }
+        __syncwarp();
+        {   cs16 p = unpack(xb[4 * hl]), q = unpack(xb[4 * hl + 1]), r = unpack(xb[4 * hl + 2]), t = unpack(xb[4 * hl + 3]);
+            dft4(p, q, r, t);                                               // 16 x FFTSSEEx<4>
+            xb[4 * hl] = pack(p); xb[4 * hl + 1] = pack(q); xb[4 * hl + 2] = pack(r); xb[4 * hl + 3] = pack(t); }
+        __syncwarp();
+    };
+    // ---- T11aLTS (channel_11a.hpp:34-230) -----------------------------------------------------------
+    {   // FreqOffsetEstimate<16> (dspalg.hpp:227-243): sum over the 64 samples of (LTS2 * conj(LTS1 >> 1)) >> 5
+        cs16 l0 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b0))), 1), l1 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b1))), 1);
+        cs16 h0 = unpack(__ldg(x + 2u * (s0 + 72u + b0))), h1 = unpack(__ldg(x + 2u * (s0 + 72u + b1)));
         int re0, im0, re1, im1; cmul_conj32(re0, im0, h0, l0); cmul_conj32(re1, im1, h1, l1);
         int sr = wadd(re0 >> 5, re1 >> 5), si = wadd(im0 >> 5, im1 >> 5);
         for (int o = 16; o; o >>= 1) { sr = wadd(sr, __shfl_xor_sync(FULL, sr, o)); si = wadd(si, __shfl_xor_sync(FULL, si, o)); }
-        int arg = d_uatan2(T, si, sr);
-        fi.cfo_est = (int)(short)(((uint32_t)arg) / 64u);                  // short / size_t (dspalg.hpp:242)
+        fi.cfo_est = (int)(short)(((uint32_t)d_uatan2(T, si, sr)) / 64u);  // short / size_t (dspalg.hpp:242)
     }
-    const cs16 fc0 = d_rot(T, fi.cfo_est * b0), fc1 = d_rot(T, fi.cfo_est * b1);   // dspalg.hpp:201-208 (phase accumulates mod 2^16)
-    xb[b0] = pack(cmul_q15(l0, fc0)); xb[b1] = pack(cmul_q15(l1, fc1));
-    warp_fft64(xb, T, lane);
+    cs16 fcv[4];                                       // FreqCoeffs of this lane's four time samples (dspalg.hpp:201-208)
+#pragma unroll
+    for (int j = 0; j < 4; j++) fcv[j] = d_rot(T, fi.cfo_est * (hl + 16 * j));
+    auto load4 = [&](uint32_t first, cs16 (&v)[4]) {    // (x >> 1) * FreqCoeffs for samples first + hl + 16 j
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = cmul_q15(sra(unpack(__ldg(x + 2u * (first + hl + 16u * j))), 1), fcv[j]);
+    };
+    {   cs16 v[4]; load4(s0 + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]); }     // both halves transform LTS1 (same data)
     cs16 ch0, ch1;
     {   // channel_11a.hpp:124-171: H^-1 = (+-1600 conj(Y)) / (|Y|^2 >> 8), C integer division
-        cs16 y0 = unpack(xb[bitrev6(b0)]), y1 = unpack(xb[bitrev6(b1)]);
+        const uint32_t* xb = s_fft[wib][0];
         auto inv = [&](cs16 y, int bin) -> cs16 {
             if (bin >= 28 && bin <= 35) return mk(0, 0);
             int e = wadd(y.re * y.re, y.im * y.im) >> 8;
@@ -288,9 +321,10 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
             int re, im; cmul_conj32(re, im, mk(L, 0), y);
             return e ? mk(sx16(re / e), sx16(im / e)) : mk(0, 0);
         };
-        ch0 = inv(y0, b0); ch1 = inv(y1, b1);
+        ch0 = inv(unpack(xb[r0]), b0); ch1 = inv(unpack(xb[r1]), b1);
     }
-    if (taps.freq_coeffs) { taps.freq_coeffs[(size_t)f * 64 + b0] = pack(fc0); taps.freq_coeffs[(size_t)f * 64 + b1] = pack(fc1);
+    __syncwarp();
+    if (taps.freq_coeffs) { taps.freq_coeffs[(size_t)f * 64 + b0] = pack(d_rot(T, fi.cfo_est * b0)); taps.freq_coeffs[(size_t)f * 64 + b1] = pack(d_rot(T, fi.cfo_est * b1));
                             taps.chan_coeffs[(size_t)f * 64 + b0] = pack(ch0); taps.chan_coeffs[(size_t)f * 64 + b1] = pack(ch1); }
     // ---- symbols -----------------------------------------------------------------------------------
     const int k0 = b0, k1 = b1 - 64;                   // signed subcarrier numbers of this lane's bins
@@ -302,25 +336,29 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
     int plcp_data = 0; uint32_t remain = 0; uint32_t soft_bytes = 0; int nbpsc = 1;
     uint8_t* sout = soft_out + (size_t)f * soft_stride;
     uint32_t status = E_SUCCESS;
-    for (uint32_t sym = 0;; sym++) {
-        const uint32_t sbeg = s0 + 144u + 80u * sym;
-        if ((sbeg + 80u) / 4u > nvec) { status = E_NO_FRAME; break; }      // slot exhausted before the symbol completed
-        cs16 a0 = sra(unpack(__ldg(x + 2u * (sbeg + 8u + b0))), 1), a1 = sra(unpack(__ldg(x + 2u * (sbeg + 8u + b1))), 1);
-        xb[b0] = pack(cmul_q15(a0, fc0)); xb[b1] = pack(cmul_q15(a1, fc1));          // channel_11a.hpp:640-641
-        warp_fft64(xb, T, lane);
-        cs16 F0 = unpack(xb[bitrev6(b0)]), F1 = unpack(xb[bitrev6(b1)]);
-        __syncwarp();
+    unsigned short pos0[6], pos1[6];                   // where this lane's soft bits go after de-interleaving
+    auto load_positions = [&](int nb) {
+        const uint16_t* inv = inv_deint + (nb == 1 ? 0 : nb == 2 ? 48 : nb == 4 ? 144 : 336);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            pos0[i] = (d0 >= 0 && i < nb) ? __ldg(inv + d0 * nb + i) : (unsigned short)0;
+            pos1[i] = (d1 >= 0 && i < nb) ? __ldg(inv + d1 * nb + i) : (unsigned short)0;
+        }
+    };
+    load_positions(1);
+    // everything behind the FFT for one symbol whose spectrum sits in s_fft[wib][h]; returns false when the frame ended
+    auto post_fft = [&](int h, uint32_t sym) -> bool {
+        const uint32_t* xb = s_fft[wib][h];
+        cs16 F0 = unpack(xb[r0]), F1 = unpack(xb[r1]);
         cs16 E0 = mk(0, 0), E1 = mk(0, 0);
         if (!z0) { int re, im; cmul32(re, im, F0, ch0); E0 = mk(sx16(re >> 8), sx16(im >> 8)); }   // channel_11a.hpp:551-579
         if (!z1) { int re, im; cmul32(re, im, F1, ch1); E1 = mk(sx16(re >> 8), sx16(im >> 8)); }
         cs16 C0 = cmul_q15(E0, comp0), C1 = cmul_q15(E1, comp1);                      // freqoffset.hpp:28-30
-        // pilot.hpp:168-232
-        int th = 0;
-        if (lane == 11) th = d_uatan2(T, C1.im, C1.re);            // bin 43 = -21
-        if (lane == 25) th = d_uatan2(T, C1.im, C1.re);            // bin 57 = -7
-        if (lane == 7)  th = d_uatan2(T, C0.im, C0.re);            // bin 7
-        if (lane == 21) th = d_uatan2(T, -C0.im, -C0.re);          // bin 21 (pilot sent negated)
-        if (__ldg(T.pilot_neg + symbol_count)) th = sx16(th + 0x8000);
+        int th = 0;                                                                    // pilot.hpp:168-232
+        if (lane == 11 || lane == 25) th = d_uatan2(T, C1.im, C1.re);      // bins 43 (-21) and 57 (-7)
+        if (lane == 7)  th = d_uatan2(T, C0.im, C0.re);                    // bin 7
+        if (lane == 21) th = d_uatan2(T, -C0.im, -C0.re);                  // bin 21 (pilot sent negated)
+        if (s_pilot[symbol_count]) th = sx16(th + 0x8000);
         int th1 = __shfl_sync(FULL, th, 11), th2 = __shfl_sync(FULL, th, 25), th3 = __shfl_sync(FULL, th, 7), th4 = __shfl_sync(FULL, th, 21);
         symbol_count++; if (symbol_count >= 127) symbol_count = 0;
         int avg = sx16((th1 + th2 + th3 + th4) / 4);
@@ -338,22 +376,18 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
             taps.equalized[o + b0] = pack(E0); taps.equalized[o + b1] = pack(E1);
             taps.tracked[o + b0] = pack(R0); taps.tracked[o + b1] = pack(R1);
         }
-        // soft demap + de-interleave into shared (demapper.h:141-151 limit, LUTs; deinterleaver.hpp)
+        // soft demap (demapper.h:141-151 limit + LUTs) scattered through the inverse de-interleaver map
         const int ncbps = 48 * nbpsc;
-        const uint16_t* inv = inv_deint + (nbpsc == 1 ? 0 : nbpsc == 2 ? 48 : nbpsc == 4 ? 144 : 336);
-        auto demap = [&](cs16 r, int d) {
+        auto demap = [&](cs16 r, int d, const unsigned short (&pos)[6]) {
             if (d < 0) return;
-            unsigned re = (unsigned)min(max(r.re >> 4, -128), 127) & 0xFF, im = (unsigned)min(max(r.im >> 4, -128), 127) & 0xFF;
-            const uint8_t* L0 = T.demap;
-            int j = d * nbpsc;
-            if (nbpsc == 1) { sb[__ldg(inv + j)] = __ldg(L0 + re); }
-            else if (nbpsc == 2) { sb[__ldg(inv + j)] = __ldg(L0 + re); sb[__ldg(inv + j + 1)] = __ldg(L0 + im); }
-            else if (nbpsc == 4) { sb[__ldg(inv + j)] = __ldg(L0 + re); sb[__ldg(inv + j + 1)] = __ldg(L0 + 256 + re);
-                                   sb[__ldg(inv + j + 2)] = __ldg(L0 + im); sb[__ldg(inv + j + 3)] = __ldg(L0 + 256 + im); }
-            else { sb[__ldg(inv + j)] = __ldg(L0 + re); sb[__ldg(inv + j + 1)] = __ldg(L0 + 512 + re); sb[__ldg(inv + j + 2)] = __ldg(L0 + 768 + re);
-                   sb[__ldg(inv + j + 3)] = __ldg(L0 + im); sb[__ldg(inv + j + 4)] = __ldg(L0 + 512 + im); sb[__ldg(inv + j + 5)] = __ldg(L0 + 768 + im); }
+            const unsigned re = (unsigned)min(max(r.re >> 4, -128), 127) & 0xFF, im = (unsigned)min(max(r.im >> 4, -128), 127) & 0xFF;
+            if (nbpsc == 1) { sb[pos[0]] = s_demap[re]; }
+            else if (nbpsc == 2) { sb[pos[0]] = s_demap[re]; sb[pos[1]] = s_demap[im]; }
+            else if (nbpsc == 4) { sb[pos[0]] = s_demap[re]; sb[pos[1]] = s_demap[256 + re]; sb[pos[2]] = s_demap[im]; sb[pos[3]] = s_demap[256 + im]; }
+            else { sb[pos[0]] = s_demap[re]; sb[pos[1]] = s_demap[512 + re]; sb[pos[2]] = s_demap[768 + re];
+                   sb[pos[3]] = s_demap[im]; sb[pos[4]] = s_demap[512 + im]; sb[pos[5]] = s_demap[768 + im]; }
         };
-        demap(R0, d0); demap(R1, d1);
+        demap(R0, d0, pos0); demap(R1, d1, pos1);
         __syncwarp();
         if (!plcp_data) {                              // PHY_11a.hpp:520-604
             uint32_t sig = warp_viterbi_signal(sb, lane) & 0xFFFFFFu;
@@ -371,16 +405,36 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
             uint32_t L = (sig >> 5) & 0xFFF;
             if (ok && rate) { fi.rate_kbps = rate; fi.code_rate = cr; }
             if (ok) { fi.length = L; ok = L <= 2500; }
-            if (!ok) { status = E_PLCP_HEADER_FAIL; break; }
+            if (!ok) { status = E_PLCP_HEADER_FAIL; return false; }
             fi.nsym_total = (L * 8 + 16 + 6 + nd - 1) / nd + 1;
             remain = fi.nsym_total; plcp_data = 1; nbpsc = nb; fi.ncbps = 48 * nb;
+            load_positions(nb);
         } else {
             for (int i = lane * 4; i < ncbps; i += 128) *(uint32_t*)(sout + soft_bytes + i) = *(const uint32_t*)(sb + i);
             soft_bytes += ncbps;
         }
         __syncwarp();
         remain--;
-        if (remain == 0) break;
+        return remain != 0;
+    };
+    auto sym_ready = [&](uint32_t sym) { return (s0 + 144u + 80u * sym + 80u) / 4u <= nvec; };   // all 80 samples arrived
+    // SIGNAL symbol alone, then the data symbols two at a time
+    bool more = true;
+    if (!sym_ready(0)) { status = E_NO_FRAME; more = false; }
+    if (more) {
+        cs16 v[4]; load4(s0 + 144u + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]);
+        more = post_fft(0, 0);
+    }
+    for (uint32_t sym = 1; more; sym += 2) {
+        const bool haveA = sym_ready(sym), haveB = remain >= 2 && sym_ready(sym + 1);
+        if (!haveA) { status = E_NO_FRAME; break; }
+        {   cs16 v[4];
+            const uint32_t mine = (half && haveB) ? sym + 1 : sym;          // without a second symbol both halves transform A
+            load4(s0 + 144u + 80u * mine + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]); }
+        more = post_fft(0, sym);
+        if (!more) break;
+        if (!haveB) { if (remain >= 1 && !sym_ready(sym + 1)) { status = E_NO_FRAME; break; } sym -= 1; continue; }
+        more = post_fft(1, sym + 1);
     }
     if (lane == 0) { fi.status = status; fi.soft_bytes = soft_bytes; info[f] = fi; }
 }
