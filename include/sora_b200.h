@@ -95,6 +95,14 @@ int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samp
                       const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
                       uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, void* cuda_stream);
 
+/* Same as sb200_rx11a_batch for captures at `sample_rate_mhz` = 40 or 44.  44 Msps slots first pass the reference's 11:10 linear
+ * resampler (TDownSample44_40 / Down44to40, Brick11/src/sampling.hpp:37-65, 44MTo40M.hpp:63-123; graph
+ * CreateDemodGraph11a_44M, fb11ademod_config.hpp:244-317), each slot starting the interpolator afresh; detect_index then
+ * refers to the resampled 20 Msps stream. */
+int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples,
+                         const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes, uint32_t sample_rate_mhz,
+                         uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, void* cuda_stream);
+
 /* 802.11b (DSSS 1/2 Mbps, CCK 5.5/11 Mbps, long preamble).  Same slot convention as sb200_rx11a_batch but 44 Msps samples.
  * out_bytes row i receives frame_length-1 PSDU bytes: like TBB11bFrameSink (PHY_11b.hpp:721-739) the verdict is taken on the
  * first three FCS bytes and the fourth is never delivered; crc32 holds those three bytes (little endian, top byte 0). */

@@ -97,6 +97,8 @@ const int16_t* sbo_sts_pattern() { return (const int16_t*)tables().sts_pattern; 
 void sbo_tables(const uint8_t** vit_ma, const uint8_t** vit_mb, const uint8_t** demap4 /*4x256*/) {
     const Tables& T = tables(); *vit_ma = &T.vit_ma[0][0]; *vit_mb = &T.vit_mb[0][0]; *demap4 = T.demap_bpsk;
 }
+uint64_t sbo_resample_44_40(const int16_t* in, uint64_t n_in, int16_t* out) { return resample_44_40((const c16*)in, (size_t)n_in, (c16*)out); }
+
 // ---- 802.11b ----
 struct sbo_frame_result_11b { uint32_t status, rate_kbps, length, crc32, sample_index, detect_vec; };
 int sbo_rx11b_run(const int16_t* iq, uint64_t nsamples, int max_frames, sbo_frame_result_11b* res, uint8_t* out, uint64_t out_stride) {

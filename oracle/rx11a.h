@@ -94,5 +94,6 @@ private:
 // Standalone stage entry points used by the stage-level parity tests and the Viterbi benchmark
 void deinterleave(const uint8_t* in, uint8_t* out, int ncbps);
 void demap_symbol(const c16* eq /*64*/, uint8_t* out, int nbpsc);
+size_t resample_44_40(const c16* in, size_t n_in, c16* out);   // out must hold n_in samples
 
 } // namespace sbo

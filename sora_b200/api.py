@@ -19,7 +19,7 @@ RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u
 RESULT11B_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("sample_index", "<u4"), ("detect_vec", "<u4")])
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -41,6 +41,9 @@ def load_library():
         lib.sb200_rx11a_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.sb200_rx11a_batch.restype = C.c_int
+        lib.sb200_rx11a_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                             C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.sb200_rx11a_batch_ex.restype = C.c_int
         lib.sb200_rx11b_batch.argtypes = lib.sb200_rx11a_batch.argtypes; lib.sb200_rx11b_batch.restype = C.c_int
         lib.sb200_viterbi_k7.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -101,13 +104,16 @@ class Engine:
         """Pointer-level call (host or device pointers), used by bench.py with torch buffers."""
         self._check(self._lib.sb200_rx11a_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11a_batch")
 
-    def rx11a_batch(self, iq, frame_off, frame_len, out_stride=2560):
+    def rx11a_batch(self, iq, frame_off, frame_len, out_stride=2560, sample_rate_mhz=40):
         """iq: int16 [n,2] numpy; returns (results structured array [F], bytes uint8 [F, out_stride])."""
         iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
         off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32)
         nf = len(off)
         res = np.zeros(nf, dtype=RESULT_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
-        self.rx11a_raw(_ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
+        if sample_rate_mhz == 40:
+            self.rx11a_raw(_ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
+        else:
+            self._check(self._lib.sb200_rx11a_batch_ex(self._h, _ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, sample_rate_mhz, _ptr(out), out_stride, _ptr(res), 0), "sb200_rx11a_batch_ex")
         return res, out
 
     def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):

@@ -439,4 +439,35 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
     if (lane == 0) { fi.status = status; fi.soft_bytes = soft_bytes; info[f] = fi; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 44 -> 40 Msps front end (Brick11/src/44MTo40M.hpp:63-123 Down44to40, sampling.hpp:37-65 TDownSample44_40)
+// ------------------------------------------------------------------------------------------------
+// The reference's running interpolator is a pure function of the sample index inside the slot:
+//   out[10k]     = in[11k]
+//   out[10k + r] = (in[11k + r] * R[r] + in[11k + r + 1] * L[r + 1]) >> 7,  r = 1..9
+// so it is a gather: one thread per output sample, coalesced reads (each input word is read by at most two threads).
+__host__ __device__ inline uint32_t resampled_len_40(uint32_t len44) {      // whole 28-blocks in, whole 28-blocks out
+    const uint32_t n = len44 / 28u * 28u, q = n / 11u, rem = n % 11u;
+    const uint32_t m = 10u * q + (rem >= 1u ? 1u : 0u) + (rem > 2u ? rem - 2u : 0u);
+    return m / 28u * 28u;
+}
+__global__ void __launch_bounds__(256) k_resample_44_40(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
+                                                        uint32_t nframes, uint32_t* __restrict__ out, uint64_t out_stride /*samples per slot*/,
+                                                        uint64_t* __restrict__ off40, uint32_t* __restrict__ len40) {
+    const uint32_t f = blockIdx.y;
+    if (f >= nframes) return;
+    const uint32_t n40 = resampled_len_40(len[f]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { off40[f] = (uint64_t)f * out_stride; len40[f] = n40; }
+    const uint32_t* x = iq + off[f];
+    uint32_t* y = out + (size_t)f * out_stride;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n40; m += gridDim.x * blockDim.x) {
+        const uint32_t k = m / 10u, r = m - 10u * k;
+        if (r == 0) { y[m] = __ldg(x + 11u * k); continue; }
+        const int R = r == 1 ? 115 : r == 2 ? 102 : r == 3 ? 90 : r == 4 ? 77 : r == 5 ? 64 : r == 6 ? 51 : r == 7 ? 38 : r == 8 ? 26 : 13;
+        const int L = r == 1 ? 13 : r == 2 ? 26 : r == 3 ? 38 : r == 4 ? 51 : r == 5 ? 64 : r == 6 ? 77 : r == 7 ? 90 : r == 8 ? 102 : 115;
+        const cs16 a = unpack(__ldg(x + 11u * k + r)), b = unpack(__ldg(x + 11u * k + r + 1u));
+        y[m] = pack(mk(sx16((a.re * R + b.re * L) >> 7), sx16((a.im * R + b.im * L) >> 7)));
+    }
+}
+
 } // namespace sb

@@ -64,7 +64,7 @@ struct sb200_handle {
     uint32_t chunk_frames = 8192;                      // slots per pipeline chunk (0 = one chunk, everything on the caller's stream)
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
-    DevBuf stage[2];
+    DevBuf stage[2], iq40, off40, len40;
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
@@ -145,6 +145,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
+    h->iq40.release(); h->off40.release(); h->len40.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -305,6 +306,42 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
     return SB200_OK;
+}
+
+extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                                    uint32_t nframes, uint32_t sample_rate_mhz, uint8_t* out_bytes, uint32_t out_stride,
+                                    sb200_frame_result* res, void* cuda_stream) {
+    if (!h) return SB200_E_INVALID;
+    if (sample_rate_mhz == 40) return sb200_rx11a_batch(h, iq, iq_total, frame_off, frame_len, nframes, out_bytes, out_stride, res, cuda_stream);
+    if (sample_rate_mhz != 44) return h->fail(SB200_E_INVALID, "sample_rate_mhz must be 40 or 44");
+    if (!iq || !frame_off || !frame_len || !res) return h->fail(SB200_E_INVALID, "null argument");
+    if (nframes == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    // slot table on the host (sizing) and on the device (kernel)
+    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len), iq_dev = is_device_ptr(iq);
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    uint32_t max40 = 28;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+        const uint32_t n40 = resampled_len_40(lenh[i]); if (n40 > max40) max40 = n40;
+    }
+    const uint64_t stride40 = ((uint64_t)max40 + 3ull) & ~3ull;
+    const uint32_t* d_iq; const uint64_t* d_off; const uint32_t* d_len;
+    if (iq_dev) d_iq = (const uint32_t*)iq; else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
+    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
+    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
+    CK(h->iq40.need(nframes * stride40 * 4ull)); CK(h->off40.need(nframes * 8ull)); CK(h->len40.need(nframes * 4ull));
+    dim3 grid((unsigned)((max40 + 255) / 256 > 64 ? 64 : (max40 + 255) / 256), nframes);
+    k_resample_44_40<<<grid, 256, 0, st>>>(d_iq, d_off, d_len, nframes, (uint32_t*)h->iq40.p, stride40, (uint64_t*)h->off40.p, (uint32_t*)h->len40.p);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->tab_off = nullptr;                                  // the resampled slot table changes with every call: no caching
+    return sb200_rx11a_batch(h, (const int16_t*)h->iq40.p, nframes * stride40, (const uint64_t*)h->off40.p, (const uint32_t*)h->len40.p, nframes,
+                             out_bytes, out_stride, res, cuda_stream);
 }
 
 extern "C" int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,

@@ -96,3 +96,10 @@ def rx11b_batch(iq, off, length, out_stride=4096, nthreads=1):
     res = np.zeros(nf, dtype=RES11B_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
     lib().sbo_rx11b_batch(_p(iq), _p(off), _p(length), C.c_uint32(nf), _p(res), _p(out), C.c_uint64(out_stride), C.c_int(nthreads))
     return res, out
+
+def resample_44_40(iq44):
+    iq44 = np.ascontiguousarray(iq44, dtype=np.int16)
+    out = np.zeros_like(iq44)
+    lib().sbo_resample_44_40.restype = C.c_uint64
+    n = lib().sbo_resample_44_40(_p(iq44), C.c_uint64(iq44.shape[0]), _p(out))
+    return out[:n].copy()

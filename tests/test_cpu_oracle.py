@@ -143,3 +143,25 @@ def test_engine_fails_loudly_without_gpu():
     from sora_b200 import api
     with pytest.raises(api.Sb200Error):
         api.Engine(0)
+
+def _capture_44(rate, psdu_len, seed, snr_db=None):
+    """An 802.11a PPDU captured at 44 Msps: the 40 Msps float waveform band-limited-interpolated by 11/10."""
+    r = np.random.RandomState(seed); ps = synth.psdu_with_fcs(r.randint(0, 256, psdu_len - 4).astype(np.uint8))
+    td = synth.modulate(ps[None, :], rate)[0]
+    X = np.fft.fft(np.concatenate([np.zeros(100), td, np.zeros(100)])); N = len(X); M = N * 11 // 10
+    Y = np.zeros(M, complex); h = N // 2; Y[:h] = X[:h]; Y[-h:] = X[-h:]
+    td44 = np.fft.ifft(Y) * M / N
+    iq = synth.to_iq16(td44[None, :], lead=44, trail=300 + (-(344 + len(td44))) % 28, snr_db=snr_db, rng=np.random.default_rng(seed))[0]
+    return iq, ps
+
+def test_44msps_resampler_and_decode():
+    """fb11ademod_config.hpp:244-317 (CreateDemodGraph11a_44M): 11:10 linear resampler in front of the 40 Msps graph."""
+    x = np.zeros((28 * 11, 2), np.int16); x[:, 0] = np.arange(len(x)) * 37 % 2001 - 1000; x[:, 1] = 7
+    y = oracle_py.resample_44_40(x)
+    assert len(y) == 280 and (y[0] == x[0]).all() and (y[10] == x[11]).all()
+    xi = x.astype(np.int64)
+    assert y[1, 0] == (xi[1, 0] * 115 + xi[2, 0] * 13) >> 7 and y[9, 0] == (xi[9, 0] * 13 + xi[10, 0] * 115) >> 7
+    for rate in (6000, 24000, 54000):
+        iq, ps = _capture_44(rate, 150, rate)
+        res, out = oracle_py.rx11a_run(oracle_py.resample_44_40(iq))
+        assert len(res) == 1 and res[0]["status"] == 1 and res[0]["rate_kbps"] == rate and (out[0, :150] == ps).all()

@@ -136,3 +136,20 @@ def test_chunked_pipeline_host_and_device(eng):
         assert (t_out.cpu().numpy()[:, :180] == ps).all()
     finally:
         eng.set_option("chunk_frames", 8192); eng.set_option("chunk_frames_device", 0)
+
+def test_44msps_capture(eng):
+    """sb200_rx11a_batch_ex(sample_rate_mhz=44): on-device 11:10 resampler + the 40 Msps chain == oracle doing the same."""
+    from test_cpu_oracle import _capture_44
+    caps = [_capture_44(rate, 150 + 10 * i, 50 + i, snr_db=(None if i % 2 else 30)) for i, rate in enumerate((6000, 12000, 36000, 54000))]
+    L = max(len(c[0]) for c in caps)
+    flat = np.zeros((len(caps), L, 2), np.int16); ln = np.zeros(len(caps), np.uint32)
+    for i, (iq, _) in enumerate(caps): flat[i, :len(iq)] = iq; ln[i] = len(iq)
+    off = np.arange(len(caps), dtype=np.uint64) * L
+    res, out = eng.rx11a_batch(flat.reshape(-1, 2), off, ln, sample_rate_mhz=44)
+    for i, (iq, ps) in enumerate(caps):
+        ores, oout = oracle_py.rx11a_run(oracle_py.resample_44_40(iq), max_frames=1)
+        assert len(ores) == 1
+        for k in ("status", "rate_kbps", "length", "crc32", "nsym", "detect_index", "cfo_est"):
+            assert res[k][i] == ores[k][0], (i, k, res[k][i], ores[k][0])
+        n = int(ores["length"][0]); assert (out[i, :n] == oout[0, :n]).all()
+        if ores["status"][0] == 1: assert (out[i, :n] == ps).all()
