@@ -107,6 +107,6 @@ if __name__ == "__main__":
     ap.add_argument("--config", choices=["viterbi", "11b"], required=True)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--blocks", type=int, default=32768)
-    ap.add_argument("--frames", type=int, default=8192)
+    ap.add_argument("--frames", type=int, default=32768)
     a = ap.parse_args()
     bench_viterbi(a) if a.config == "viterbi" else bench_11b(a)

@@ -95,6 +95,13 @@ int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samp
                       const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
                       uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, void* cuda_stream);
 
+/* One continuous capture holding any number of frames: frames are reported in order exactly as the
+ * reference's RxThread finds them (fb11a_demod.cpp:29-81) — after each event the graph restarts on the next 28-sample block and
+ * only the DC estimate carries over.  res / out_bytes / sample_index are HOST arrays of max_frames entries; sample_index[i] =
+ * CF_MemSamples::mem_sample_index (40 Msps samples consumed) when event i was seen; detect_index is relative to the restart. */
+int sb200_rx11a_stream(sb200_handle* h, const int16_t* iq, uint64_t nsamples, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride,
+                       sb200_frame_result* res, uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream);
+
 /* Same as sb200_rx11a_batch for captures at `sample_rate_mhz` = 40 or 44.  44 Msps slots first pass the reference's 11:10 linear
  * resampler (TDownSample44_40 / Down44to40, Brick11/src/sampling.hpp:37-65, 44MTo40M.hpp:63-123; graph
  * CreateDemodGraph11a_44M, fb11ademod_config.hpp:244-317), each slot starting the interpolator afresh; detect_index then

@@ -19,7 +19,7 @@ RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u
 RESULT11B_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("sample_index", "<u4"), ("detect_vec", "<u4")])
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -44,6 +44,8 @@ def load_library():
         lib.sb200_rx11a_batch_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                              C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.sb200_rx11a_batch_ex.restype = C.c_int
+        lib.sb200_rx11a_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.sb200_rx11a_stream.restype = C.c_int
         lib.sb200_rx11b_batch.argtypes = lib.sb200_rx11a_batch.argtypes; lib.sb200_rx11b_batch.restype = C.c_int
         lib.sb200_viterbi_k7.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -115,6 +117,14 @@ class Engine:
         else:
             self._check(self._lib.sb200_rx11a_batch_ex(self._h, _ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, sample_rate_mhz, _ptr(out), out_stride, _ptr(res), 0), "sb200_rx11a_batch_ex")
         return res, out
+
+    def rx11a_stream(self, iq, max_frames=16, out_stride=2560):
+        """One continuous capture -> (results [n], bytes [n, out_stride], sample_index [n]) in RxThread order."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        res = np.zeros(max_frames, dtype=RESULT_DTYPE); out = np.zeros((max_frames, out_stride), dtype=np.uint8)
+        sidx = np.zeros(max_frames, np.uint32); n = C.c_uint32(0)
+        self._check(self._lib.sb200_rx11a_stream(self._h, _ptr(iq), iq.shape[0], max_frames, _ptr(out), out_stride, _ptr(res), _ptr(sidx), C.addressof(n), 0), "sb200_rx11a_stream")
+        return res[:n.value], out[:n.value], sidx[:n.value]
 
     def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         self._check(self._lib.sb200_rx11b_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11b_batch")

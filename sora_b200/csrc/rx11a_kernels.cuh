@@ -30,6 +30,7 @@ struct FrameInfo {            // per-slot state handed from kernel to kernel (de
     uint32_t rate_kbps, length, nsym_total, code_rate, ncbps;
     uint32_t soft_bytes;      // deinterleaved soft values written for this frame
     int32_t cfo_est; uint32_t peak_index;
+    int32_t dc_re, dc_im;     // CF_VecDC when the carrier sense ended (it persists across frames of one stream)
 };
 
 __device__ __forceinline__ int d_uatan2(const DevTables& T, int y, int x) {       // intalg.h:96-108
@@ -77,14 +78,14 @@ __device__ __forceinline__ int cca_xcorr(const CcaState& s, const uint32_t* __re
 
 __global__ void __launch_bounds__(128) k_sync11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
                                                   const uint32_t* __restrict__ len, uint32_t nframes, uint32_t cca_thr,
-                                                  DevTables T, FrameInfo* __restrict__ info) {
+                                                  DevTables T, FrameInfo* __restrict__ info, const int2* __restrict__ dc_init) {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const uint32_t* x = iq + off[f];
     const uint32_t nblk = len[f] / 28u;               // memsource.hpp:87: whole 28-sample source blocks only
     const uint32_t nvec = nblk * 28u / 8u;
     CcaState s; s.reset();
-    int dc_re = 0, dc_im = 0;                          // CF_VecDC, zero at Init
+    int dc_re = dc_init ? dc_init[f].x : 0, dc_im = dc_init ? dc_init[f].y : 0;   // CF_VecDC: zero at Init, carried along a stream
     bool timeout = false; uint32_t cur_blk = 0; uint32_t detect = 0xFFFFFFFFu;
     for (uint32_t v = 0; v < nvec; v++) {
         uint32_t blk = (8u * v + 7u) / 28u;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128) k_sync11a(const uint32_t* __restrict__ iq
     FrameInfo fi;
     fi.status = detect == 0xFFFFFFFFu ? (uint32_t)E_NO_FRAME : (uint32_t)E_SUCCESS;
     fi.detect_vec = detect; fi.rate_kbps = 6000; fi.length = 0; fi.nsym_total = 0; fi.code_rate = CR_12; fi.ncbps = 48;
-    fi.soft_bytes = 0; fi.cfo_est = 0; fi.peak_index = (uint32_t)s.peak_index;
+    fi.soft_bytes = 0; fi.cfo_est = 0; fi.peak_index = (uint32_t)s.peak_index; fi.dc_re = dc_re; fi.dc_im = dc_im;
     info[f] = fi;
 }
 

@@ -64,7 +64,7 @@ struct sb200_handle {
     uint32_t chunk_frames = 8192;                      // slots per pipeline chunk (0 = one chunk, everything on the caller's stream)
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
-    DevBuf stage[2], iq40, off40, len40;
+    DevBuf stage[2], iq40, off40, len40, dcbuf;
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
@@ -145,7 +145,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -175,14 +175,14 @@ extern "C" int sb200_last_kernel_times(sb200_handle* h, float* ms4) {
 // Launch the decode kernels for frames [f0, f1) of a call.  `iq_base + off[f]` must address slot f.
 // sync + front end go to `sf`, the Viterbi launches to `sv` (sv waits for `front_done` when the streams differ).
 static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t f0, uint32_t f1,
-                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed) {
+                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr) {
     const uint32_t n = f1 - f0;
     FrameInfo* d_info = (FrameInfo*)h->info.p + f0;
     uint8_t* d_soft = (uint8_t*)h->soft.p + (size_t)f0 * soft_stride;
     uint8_t* d_out = (uint8_t*)h->out.p + (size_t)f0 * row;
     uint32_t* d_status = (uint32_t*)h->status.p + f0; uint32_t* d_crc = (uint32_t*)h->crc.p + f0;
     if (timed) CK(cudaEventRecord(h->evk[0], sf));
-    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info);
+    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info, dc_init ? dc_init + f0 : nullptr);
     if (timed) CK(cudaEventRecord(h->evk[1], sf));
     k_front11a<<<(n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info,
             d_soft, soft_stride, h->inv_deint, taps);
@@ -209,7 +209,7 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
 // The front end is latency bound and the Viterbi integer-issue bound, so they overlap well on the same SMs.
 static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
                      uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, cudaStream_t st,
-                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride) {
+                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride, const int2* dc_init = nullptr) {
     if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
     if (nframes == 0) return SB200_OK;
     CK(cudaSetDevice(h->device));
@@ -243,7 +243,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     CK(h->soft.need(nframes * soft_stride));
     CK(h->out.need(nframes * row));
     CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result)));
-    const bool tapping = taps.freq_coeffs || taps.fft_out || soft_host;
+    const bool tapping = taps.freq_coeffs || taps.fft_out || soft_host || dc_init;
     // device-resident IQ gains nothing from chunking (a chunk's Viterbi grid no longer fills 148 SMs x 5 CTAs); host IQ does:
     // the PCIe copy of chunk k+1 hides behind the kernels of chunk k.  chunk_frames_device lets a caller force it anyway.
     const uint32_t want = iq_dev ? h->chunk_frames_device : h->chunk_frames;
@@ -254,7 +254,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         const uint32_t* d_iq;
         if (iq_dev) d_iq = (const uint32_t*)iq;
         else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
-        int rc = launch_chunk(h, d_iq, d_off, d_len, 0, nframes, soft_stride, row, st, st, nullptr, taps, true);
+        int rc = launch_chunk(h, d_iq, d_off, d_len, 0, nframes, soft_stride, row, st, st, nullptr, taps, true, dc_init);
         if (rc != SB200_OK) return rc;
         h->nk = 4;
     } else {
@@ -306,6 +306,46 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
     return SB200_OK;
+}
+
+// Continuous capture: frames are found one after another exactly like RxThread does (fb11a_demod.cpp:29-81): after every
+// event the graph is flushed and reset, the source continues with the next 28-sample block, and only the DC estimate
+// (CF_VecDC) survives.  Each frame is one pass of the batch pipeline over the remaining samples with that DC.
+extern "C" int sb200_rx11a_stream(sb200_handle* h, const int16_t* iq, uint64_t nsamples, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride,
+                                  sb200_frame_result* res, uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream) {
+    if (!h || !iq || !res || !nframes_out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    *nframes_out = 0;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    if (is_device_ptr(res) || (out_bytes && is_device_ptr(out_bytes))) return h->fail(SB200_E_INVALID, "stream mode returns results in host memory");
+    const int16_t* d_iq = iq;
+    if (!is_device_ptr(iq)) { CK(h->iq.need(nsamples * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, nsamples * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const int16_t*)h->iq.p; }
+    CK(h->dcbuf.need(sizeof(int2)));
+    uint64_t pos = 0; int2 dc = make_int2(0, 0);
+    const uint32_t saved_chunk = h->chunk_frames_device; h->chunk_frames_device = 0;
+    int rc = SB200_OK;
+    while (*nframes_out < max_frames && pos + 28 <= nsamples) {
+        const uint64_t off = pos; const uint64_t remain = nsamples - pos;
+        const uint32_t len = remain > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)remain;
+        CK(cudaMemcpyAsync(h->dcbuf.p, &dc, sizeof dc, cudaMemcpyHostToDevice, st));
+        sb200_frame_result r; FrontTaps taps{};
+        h->tab_off = nullptr;
+        uint8_t* ob = out_bytes ? out_bytes + (size_t)(*nframes_out) * out_stride : nullptr;
+        rc = rx11a_run(h, d_iq, nsamples, &off, &len, 1, ob, ob ? out_stride : 0, &r, st, taps, nullptr, 0, (const int2*)h->dcbuf.p);
+        if (rc != SB200_OK) break;
+        if (r.status == SB200_FRAME_NONE) break;          // ran out of samples: the reference's RxThread returns
+        FrameInfo fi; CK(cudaMemcpy(&fi, h->info.p, sizeof fi, cudaMemcpyDeviceToHost));
+        dc = make_int2(fi.dc_re, fi.dc_im);
+        const uint32_t consumed = r.status == SB200_FRAME_PLCP_FAIL ? 1u : r.nsym;      // OFDM symbols that went through the graph
+        const uint64_t e20 = (uint64_t)r.detect_index + 144ull + 80ull * consumed;      // 20 Msps samples up to the end of the last symbol
+        const uint64_t v_last = e20 / 4ull - 1ull, blk = (8ull * v_last + 7ull) / 28ull;
+        pos += (blk + 1ull) * 28ull;                        // the driver sees the event after that source block
+        res[*nframes_out] = r;
+        if (sample_index) sample_index[*nframes_out] = (uint32_t)pos;
+        (*nframes_out)++;
+    }
+    h->chunk_frames_device = saved_chunk;
+    return rc;
 }
 
 extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,

@@ -153,3 +153,44 @@ def test_44msps_capture(eng):
             assert res[k][i] == ores[k][0], (i, k, res[k][i], ores[k][0])
         n = int(ores["length"][0]); assert (out[i, :n] == oout[0, :n]).all()
         if ores["status"][0] == 1: assert (out[i, :n] == ps).all()
+
+def _mixed_stream(seed=5, dc=(180, -140)):
+    """A continuous capture: frames of different rates / lengths back to back with gaps, a DC offset (so the carried
+    CF_VecDC matters), one frame with a corrupted payload (CRC fail) and a bad SIGNAL field (PLCP fail)."""
+    rng = np.random.default_rng(seed); parts = []
+    specs = [(54000, 700), (6000, 120), (24000, 1500), (36000, 64), (48000, 2300), (9000, 333), (12000, 40), (18000, 999)]
+    for i, (rate, L) in enumerate(specs):
+        iq, _ = synth.make_frames(1, psdu_len=L, rate_kbps=rate, seed0=0x77000000 + i, snr_db=32, lead=int(rng.integers(40, 400)), trail=int(rng.integers(60, 500)), gain=0.5)
+        s = iq[0].copy()
+        if i == 2: s[5000:5200] = rng.integers(-3000, 3000, (200, 2))       # payload hit -> CRC32 fail
+        if i == 4:
+            lead_guess = np.nonzero(np.abs(s[:, 0].astype(np.int32)) > 400)[0][0]
+            s[lead_guess + 640:lead_guess + 800] = rng.integers(-3000, 3000, (160, 2))   # SIGNAL symbol hit
+        parts.append(s)
+    st = np.concatenate(parts).astype(np.int32) + np.array(dc, np.int32)
+    return np.clip(st, -32768, 32767).astype(np.int16)
+
+def test_stream_mode_matches_rxthread(eng):
+    for seed in (5, 6):
+        st = _mixed_stream(seed)
+        ores, oout = oracle_py.rx11a_run(st, max_frames=16, out_stride=2560)
+        res, out, sidx = eng.rx11a_stream(st, max_frames=16)
+        assert len(ores) >= 7 and len(res) == len(ores), (len(res), len(ores))
+        for k in ("status", "rate_kbps", "length", "crc32", "nsym", "cfo_est"):
+            assert (res[k] == ores[k]).all(), (k, res[k], ores[k])
+        assert (sidx == ores["sample_index"]).all(), (sidx, ores["sample_index"])
+        # the oracle counts 20 Msps vectors since the start of the capture, the library since the restart: each earlier
+        # segment of n 40 Msps samples contributed 4*floor(n/8) of them (the decimator's queue is dropped on reset)
+        seg = np.diff(np.concatenate([[0], ores["sample_index"].astype(np.int64)]))
+        cum = np.concatenate([[0], np.cumsum(4 * (seg // 8))[:-1]])
+        assert (res["detect_index"] + cum == ores["detect_index"]).all(), (res["detect_index"], cum, ores["detect_index"])
+        for i in range(len(res)):
+            if ores["status"][i] in (1, oracle_py.E_CRC32_FAIL):
+                L = int(ores["length"][i]); assert (out[i, :L] == oout[i, :L]).all(), i
+        assert (res["status"] == 1).sum() >= 5
+    # max_frames bound and an empty / too-short capture
+    res, _, _ = eng.rx11a_stream(_mixed_stream(5), max_frames=3); assert len(res) == 3
+    res, _, _ = eng.rx11a_stream(np.zeros((2000, 2), np.int16)); assert len(res) == 0
+    noise = np.random.default_rng(1).normal(0, 4000, (20000, 2)).astype(np.int16)      # spurious detections, no frames
+    ores, _ = oracle_py.rx11a_run(noise, max_frames=32); res, _, sidx = eng.rx11a_stream(noise, max_frames=32)
+    assert len(res) == len(ores) and (res["status"] == ores["status"]).all() and (sidx == ores["sample_index"]).all()
