@@ -1,5 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see ops.h).  C entry points for tests/ (ctypes) and bench.py's cpu_baseline.
 #include "rx11b.h"
+#include "rx11n.h"
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -123,6 +124,59 @@ void sbo_rx11b_batch(const int16_t* iq, const uint64_t* off, const uint32_t* len
     for (auto& t : th) t.join();
 }
 uint8_t sbo_cck11_decode(const int16_t* chips8, int16_t* last2, int* even) { c16 l{last2[0], last2[1]}; uint8_t b = cck11_decode((const c16*)chips8, l, *even); last2[0] = l.re; last2[1] = l.im; return b; }
+
+// ---- 802.11n 2x2 -----------------------------------------------------------------------------------------------------
+int sbo_rx11n_run(const int16_t* iq0, const int16_t* iq1, uint64_t nsamples, int max_frames, void* res, uint8_t* out, uint64_t out_stride) {
+    Rx11n rx;
+    return rx.run((const c16*)iq0, (const c16*)iq1, (size_t)nsamples, (FrameResult11n*)res, out, (size_t)out_stride, max_frames);
+}
+void sbo_rx11n_batch(const int16_t* iq0, const int16_t* iq1, const uint64_t* off, const uint32_t* len, uint32_t nframes,
+                     void* res_, uint8_t* out, uint64_t out_stride, int nthreads) {
+    FrameResult11n* res = (FrameResult11n*)res_;
+    std::atomic<uint32_t> next(0);
+    auto work = [&]() {
+        Rx11n rx;
+        for (;;) {
+            uint32_t i = next.fetch_add(1); if (i >= nframes) break;
+            FrameResult11n r; memset(&r, 0, sizeof r);
+            int n = rx.run((const c16*)iq0 + off[i], (const c16*)iq1 + off[i], len[i], &r, out ? out + (size_t)i * out_stride : nullptr, (size_t)out_stride, 1);
+            if (n == 0) { memset(&r, 0, sizeof r); r.status = E_NO_FRAME; }
+            memcpy(&res[i], &r, sizeof r);
+        }
+    };
+    if (nthreads <= 1) { work(); return; }
+    std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+}
+// stage taps of the first frame: siso [2][64], hinv [4][64], fft_out [2][max_sym][64] (every 64-point FFT in order: 2 L-LTF + symbols),
+// eq [2][max_sym][64] (data symbols), soft (stream-parsed, concatenated), theta per data symbol, sig 9 bytes.  Returns #data symbols.
+int sbo_rx11n_taps(const int16_t* iq0, const int16_t* iq1, uint64_t nsamples, void* res, int16_t* siso, int16_t* hinv, int16_t* fft_out, int16_t* eq,
+                   uint8_t* soft, uint32_t* nsoft, int16_t* theta, uint8_t* sig, int max_sym, int* nfft) {
+    Rx11n rx; rx.taps.enable = true;
+    FrameResult11n r; memset(&r, 0, sizeof r);
+    int n = rx.run((const c16*)iq0, (const c16*)iq1, (size_t)nsamples, &r, nullptr, 0, 1);
+    if (n == 0) r.status = E_NO_FRAME;
+    memcpy(res, &r, sizeof r);
+    const Taps11n& t = rx.taps;
+    for (int a = 0; a < 2; a++) {
+        if (t.siso[a].size() == 64) memcpy(siso + a * 128, t.siso[a].data(), 256);
+        size_t nf = t.fft_out[a].size() / 64; if (nf > (size_t)max_sym) nf = max_sym;
+        memcpy(fft_out + (size_t)a * max_sym * 128, t.fft_out[a].data(), nf * 256); *nfft = (int)nf;
+        size_t ne = t.eq[a].size() / 64; if (ne > (size_t)max_sym) ne = max_sym;
+        memcpy(eq + (size_t)a * max_sym * 128, t.eq[a].data(), ne * 256);
+    }
+    if (t.hinv.size() == 256) memcpy(hinv, t.hinv.data(), 1024);
+    size_t ns = t.soft.size(); memcpy(soft, t.soft.data(), ns); *nsoft = (uint32_t)ns;
+    size_t nd = t.theta.size(); if (nd > (size_t)max_sym) nd = max_sym;
+    memcpy(theta, t.theta.data(), nd * 2); memcpy(sig, t.sig, 9);
+    return (int)nd;
+}
+int16_t sbo_dsp_atan(int x, int y) { return dsp_atan(x, y); }
+void sbo_tables11n(int16_t* sincos, int16_t* atan_lut, uint8_t* demap, uint8_t* crc8, uint8_t* deint, uint8_t* lltf_sign, uint8_t* htltf_sign) {
+    const Tables11n& T = tables11n();
+    memcpy(sincos, T.sincos, sizeof T.sincos); memcpy(atan_lut, T.atan_lut, sizeof T.atan_lut); memcpy(demap, T.demap, 256); memcpy(crc8, T.crc8, 256);
+    memcpy(deint, T.deint, sizeof T.deint); memcpy(lltf_sign, T.lltf_sign, 64); memcpy(htltf_sign, T.htltf_sign, 64);
+}
 
 uint32_t sbo_crc32(const uint8_t* p, uint64_t n) { uint32_t c = 0xFFFFFFFFu; for (uint64_t i = 0; i < n; i++) c = (c >> 8) ^ tables().crc32_lut[p[i] ^ (c & 0xFF)]; return ~c; }
 

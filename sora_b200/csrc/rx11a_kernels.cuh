@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
                 case 0xA: rate = 12000; nd = 48; nb = 2; cr = CR_12; break;  case 0xE: rate = 18000; nd = 72; nb = 2; cr = CR_34; break;
                 case 0x9: rate = 24000; nd = 96; nb = 4; cr = CR_12; break;  case 0xD: rate = 36000; nd = 144; nb = 4; cr = CR_34; break;
                 case 0x8: rate = 48000; nd = 192; nb = 6; cr = CR_23; break; case 0xC: rate = 54000; nd = 216; nb = 6; cr = CR_34; break;
-                default: ok = false;
+                default: if (ok) fi.rate_kbps = 0; ok = false;    // BB11aParseDataRate() == 0 is stored before the parser gives up
             }
             uint32_t L = (sig >> 5) & 0xFFF;
             if (ok && rate) { fi.rate_kbps = rate; fi.code_rate = cr; }

@@ -290,3 +290,113 @@ def make_frames_11b(nframes, psdu_len=1500, rate_kbps=11000, seed0=0xB11B0000, s
     if cfo_hz:
         td = td * np.exp(2j * np.pi * cfo_hz * np.arange(n) / 44e6)
     return to_iq16(td, gain=gain, lead=lead, trail=trail, snr_db=snr_db, rng=rng), ps
+
+
+# =====================================================================================================================
+# 802.11n HT mixed format, 20 MHz, 2 spatial streams, direct mapping onto 2 transmit chains (IEEE 802.11n-2009 clause 20),
+# MCS 8..10 — the only ones the reference receiver accepts (Brick11/src/PHY_11n.hpp:496-501).  Float modulator, test input only.
+# =====================================================================================================================
+HT_MCS = {8: (1, (1, 2), 52), 9: (2, (1, 2), 104), 10: (2, (3, 4), 156)}     # mcs: (N_BPSC per stream, code rate, N_DBPS)
+
+def _crc8_htsig(b, nbytes=4, tail_bits=2):
+    """CRC-8 x^8+x^2+x+1 as the reference computes it (core/inc/CRC8.h:29-50): reflected, init 0xFF, inverted."""
+    crc = 0xFF
+    def step(c, nb):
+        for _ in range(nb): c = (c >> 1) ^ 0xE0 if c & 1 else c >> 1
+        return c
+    for i in range(nbytes): crc = step(crc ^ int(b[i]), 8)
+    crc = step(crc ^ (int(b[nbytes]) & ((1 << tail_bits) - 1)), tail_bits)
+    return (~crc) & 0xFF
+
+def ht_interleave_map(nbpsc, iss):
+    """position on air of coded bit k of spatial stream iss (0-based), 20 MHz: N_COL 13, N_ROW 4*N_BPSC, N_ROT 11."""
+    ncbpss = 52 * nbpsc; s = max(nbpsc // 2, 1); k = np.arange(ncbpss)
+    i = 4 * nbpsc * (k % 13) + k // 13
+    j = s * (i // s) + (i + ncbpss - (13 * i) // ncbpss) % s
+    return (j - ((iss * 2) % 3 + 3 * (iss // 3)) * 11 * nbpsc) % ncbpss
+
+def _csd(freq64, shift20):
+    """cyclic shift by -shift20 samples at 20 Msps (advance), applied per carrier in FFT order."""
+    k = np.fft.fftfreq(64, 1 / 64.0)
+    return freq64 * np.exp(2j * np.pi * k * shift20 / 64.0)
+
+def _td_plain(freq64, n):
+    """n-sample periodic extension (40 Msps) of one 128-sample IFFT period, ending at the period end."""
+    X = np.zeros(128, np.complex128); X[:32] = freq64[:32]; X[96:] = freq64[32:]
+    p = np.fft.ifft(X) / 16.0
+    reps = -(-n // 128) + 1
+    return np.tile(p, reps)[-n:]
+
+def modulate_11n(psdus, mcs=8, scramble_seeds=None):
+    """psdus uint8 [F, L] (FCS included) -> complex128 [F, 2, nsamp]: the two transmit chains at 40 Msps, int8 units."""
+    psdus = np.atleast_2d(np.asarray(psdus, np.uint8)); F, L = psdus.shape
+    nbpsc, cr, ndbps = HT_MCS[mcs]
+    nsym = -(-(16 + 8 * L + 6) // ndbps); ndata = nsym * ndbps
+    if scramble_seeds is None: scramble_seeds = 1 + (np.arange(F) % 127)
+    A0 = BPSK_MOD / np.sqrt(2.0)                                    # per-chain tone amplitude
+    # ---- legacy preamble + L-SIG + HT-SIG (chain 2: 200 ns = 4-sample cyclic shift) ----
+    S = np.zeros(64, np.complex128)
+    for k, s in ((4, -1), (8, -1), (12, 1), (16, 1), (20, 1), (24, 1), (-24, 1), (-20, -1), (-16, 1), (-12, -1), (-8, -1), (-4, 1)):
+        S[k % 64] = s * 1.472 * (1 + 1j)
+    Lf = np.zeros(64, np.complex128)
+    for k in range(-26, 27): Lf[k % 64] = _LTS[k + 26]
+    nt = nsym + 5
+    lsig_len = (nt * 24 - 22) // 8
+    sig = np.zeros(24, np.uint8); sig[0:4] = [1, 1, 0, 1]; sig[5:17] = [(lsig_len >> i) & 1 for i in range(12)]; sig[17] = sig[:17].sum() & 1
+    j48 = interleave_map(48, 1)
+    def bpsk48(bits24_or_48):
+        a, b = conv_encode(bits24_or_48); c = puncture(a, b, (1, 2)).reshape(-1, 48)
+        air = np.zeros_like(c); air[:, j48] = c
+        return 2.0 * air - 1.0
+    lsig_f = _place(bpsk48(sig)[None, :, :] * BPSK_MOD, _PILOT_POL[:1])[0, 0] / BPSK_MOD
+    td = np.zeros((F, 2, 640 + 160 * (nt + 1)), np.complex128)
+    for fidx in range(F):
+        hb = np.zeros(6, np.uint8); hb[0] = mcs; hb[1] = L & 0xFF; hb[2] = L >> 8; hb[3] = 0x07
+        c8 = _crc8_htsig(hb); hb[4] |= (c8 << 2) & 0xFF; hb[5] |= c8 >> 6
+        hbits = np.unpackbits(hb, bitorder="little")
+        hs = _place(bpsk48(hbits)[None, :, :] * BPSK_MOD, _PILOT_POL[1:3])[0] / BPSK_MOD          # [2, 64]
+        hs = np.where(np.abs(hs) > 0, hs, 0); data_mask = np.ones(64, bool); data_mask[[7, 21, 57, 43]] = False
+        hs[:, data_mask] = hs[:, data_mask] * 1j                                                   # QBPSK on the data tones
+        # ---- data field ----
+        bits = np.zeros(ndata, np.uint8); bits[16:16 + 8 * L] = np.unpackbits(psdus[fidx], bitorder="little")
+        bits ^= scrambler_seq(int(np.asarray(scramble_seeds).reshape(-1)[fidx]), ndata); bits[16 + 8 * L:16 + 8 * L + 6] = 0
+        a, b = conv_encode(bits); coded = puncture(a, b, cr).reshape(nsym, 2 * 52 * nbpsc)
+        for ch in range(2):
+            sh_leg, sh_ht = (0, 0) if ch == 0 else (4, 8)
+            parts = [_td_plain(_csd(S, sh_leg) * A0, 320), _td_plain(_csd(Lf, sh_leg) * A0, 320)]
+            for f in (lsig_f, hs[0], hs[1]): parts.append(_ofdm_td(_csd(f, sh_leg) * A0))
+            parts.append(_ofdm_td(_csd(S, sh_ht) * A0))                                            # HT-STF
+            H = Lf.copy(); H[27] = H[28] = -1; H[64 - 28] = H[64 - 27] = 1
+            P = ((1, -1), (1, 1))[ch]
+            for n in range(2): parts.append(_ofdm_td(_csd(H, sh_ht) * A0 * P[n]))
+            sb = coded[:, ch::2]                                                                    # stream parser, s = 1
+            jm = ht_interleave_map(nbpsc, ch)
+            air = np.zeros_like(sb); air[:, jm] = sb
+            if nbpsc == 1: pts = 2.0 * air - 1.0 + 0j
+            else: q = air.reshape(nsym, 52, 2); pts = ((2.0 * q[..., 0] - 1) + 1j * (2.0 * q[..., 1] - 1)) / np.sqrt(2.0)
+            fr = np.zeros((nsym, 64), np.complex128)
+            idx = np.array([k % 64 for k in list(range(-28, 0)) + list(range(1, 29)) if k not in (-21, -7, 7, 21)])
+            fr[:, idx] = pts
+            psi = ((1, 1, -1, -1), (1, -1, -1, 1))[ch]
+            for n in range(nsym):
+                pol = _PILOT_POL[(n + 3) % 127]
+                for m, k in enumerate((-21, -7, 7, 21)): fr[n, k % 64] = pol * psi[(n + m) % 4]
+            parts.append(_ofdm_td(_csd(fr, sh_ht) * A0).reshape(-1))
+            sig_td = np.concatenate(parts)
+            td[fidx, ch, :len(sig_td)] = sig_td
+    return td
+
+def make_frames_11n(nframes, psdu_len=1500, mcs=8, seed0=0x11A0000, snr_db=None, lead=64, trail=64, cfo_hz=0.0, gain=1.0,
+                    chan=((1.0, 0.3j), (-0.2, 0.9))):
+    """2x2 frames through a flat channel `chan` (rx = chan @ tx).  Returns (iq0, iq1 int16 [F, slot, 2], psdus [F, L])."""
+    ps = np.zeros((nframes, psdu_len), np.uint8)
+    for i in range(nframes):
+        r = np.random.RandomState(seed=(seed0 + i) & 0xFFFFFFFF)
+        ps[i] = psdu_with_fcs(r.randint(0, 256, psdu_len - 4).astype(np.uint8))
+    tx = modulate_11n(ps, mcs)
+    Hm = np.asarray(chan, np.complex128)
+    rx = np.einsum("ab,fbn->fan", Hm, tx)
+    rng = np.random.default_rng(seed0 & 0xFFFFFFFF)
+    iq0 = to_iq16(rx[:, 0], gain=gain, lead=lead, trail=trail, snr_db=snr_db, cfo_hz=cfo_hz, rng=rng)
+    iq1 = to_iq16(rx[:, 1], gain=gain, lead=lead, trail=trail, snr_db=snr_db, cfo_hz=cfo_hz, rng=rng)
+    return iq0, iq1, ps

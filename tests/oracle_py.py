@@ -103,3 +103,37 @@ def resample_44_40(iq44):
     lib().sbo_resample_44_40.restype = C.c_uint64
     n = lib().sbo_resample_44_40(_p(iq44), C.c_uint64(iq44.shape[0]), _p(out))
     return out[:n].copy()
+
+
+# ---- 802.11n 2x2 ------------------------------------------------------------------------------------------------------
+RES11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("nsym", "<u4"),
+                         ("sample_index", "<u4"), ("detect_index", "<u4"), ("cfo_est", "<i2"), ("lsig_length", "<u2")])
+
+def rx11n_run(iq0, iq1, max_frames=8, out_stride=2048):
+    iq0 = np.ascontiguousarray(iq0, dtype=np.int16); iq1 = np.ascontiguousarray(iq1, dtype=np.int16)
+    res = np.zeros(max_frames, dtype=RES11N_DTYPE); out = np.zeros((max_frames, out_stride), dtype=np.uint8)
+    n = lib().sbo_rx11n_run(_p(iq0), _p(iq1), C.c_uint64(iq0.reshape(-1, 2).shape[0]), C.c_int(max_frames), _p(res), _p(out), C.c_uint64(out_stride))
+    return res[:n], out[:n]
+
+def rx11n_batch(iq0, iq1, off, length, out_stride=1536, nthreads=1):
+    iq0 = np.ascontiguousarray(iq0, dtype=np.int16); iq1 = np.ascontiguousarray(iq1, dtype=np.int16)
+    off = np.ascontiguousarray(off, dtype=np.uint64); length = np.ascontiguousarray(length, dtype=np.uint32); nf = len(off)
+    res = np.zeros(nf, dtype=RES11N_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+    lib().sbo_rx11n_batch(_p(iq0), _p(iq1), _p(off), _p(length), C.c_uint32(nf), _p(res), _p(out), C.c_uint64(out_stride), C.c_int(nthreads))
+    return res, out
+
+def rx11n_taps(iq0, iq1, max_sym=300):
+    iq0 = np.ascontiguousarray(iq0, dtype=np.int16); iq1 = np.ascontiguousarray(iq1, dtype=np.int16)
+    res = np.zeros(1, dtype=RES11N_DTYPE)
+    siso = np.zeros((2, 64, 2), np.int16); hinv = np.zeros((4, 64, 2), np.int16)
+    fo = np.zeros((2, max_sym, 64, 2), np.int16); eq = np.zeros((2, max_sym, 64, 2), np.int16)
+    soft = np.zeros(max_sym * 208, np.uint8); nsoft = C.c_uint32(0); theta = np.zeros(max_sym, np.int16); sig = np.zeros(9, np.uint8); nfft = C.c_int(0)
+    nd = lib().sbo_rx11n_taps(_p(iq0), _p(iq1), C.c_uint64(iq0.reshape(-1, 2).shape[0]), _p(res), _p(siso), _p(hinv), _p(fo), _p(eq), _p(soft),
+                              C.byref(nsoft), _p(theta), _p(sig), C.c_int(max_sym), C.byref(nfft))
+    return dict(res=res[0], siso=siso, hinv=hinv, fft_out=fo[:, :nfft.value], eq=eq[:, :nd], soft=soft[:nsoft.value], theta=theta[:nd], sig=sig, ndata=nd)
+
+def tables11n():
+    sc = np.zeros((65536, 2), np.int16); at = np.zeros(4097, np.int16); dm = np.zeros(256, np.uint8); c8 = np.zeros(256, np.uint8)
+    di = np.zeros((2, 2, 104), np.uint8); ls = np.zeros(64, np.uint8); hs = np.zeros(64, np.uint8)
+    lib().sbo_tables11n(_p(sc), _p(at), _p(dm), _p(c8), _p(di), _p(ls), _p(hs))
+    return dict(sincos=sc, atan=at, demap=dm, crc8=c8, deint=di, lltf_sign=ls, htltf_sign=hs)
