@@ -112,6 +112,37 @@ def gen_deinterleave(ncbps, nbpsc):
     j = s * (i // s) + (i + ncbps - (16 * i) // ncbps) % s
     return j
 
+# ---- 802.11n tables -----------------------------------------------------------------------------------------------------
+def ref_deinterleave_11n(cls):
+    """cls e.g. 'BPSK_S0', 'QPSK_S1' (Brick11/src/deinterleaver_11n.hpp)."""
+    t = _read("kernel/bb/Brick11/src/deinterleaver_11n.hpp")
+    i0 = t.index("class T11nDeinterleave" + cls)
+    nxt = t.find("DEFINE_LOCAL_CONTEXT", i0)
+    seg = t[i0: nxt if nxt > 0 else len(t)]
+    out = {int(o): int(i) for o, i in re.findall(r"pbOutput\[(\d+)\]\s*=\s*pbInput\[(\d+)\]", seg)}
+    return np.array([out[k] for k in range(max(out) + 1)])
+
+def ref_demap_11n():
+    t = _read("kernel/bb/Brick11/src/dsp_demap.h")
+    t = t[t.index("This LUT is constructed"):]
+    return {n: np.array(parse_array(t, "dsp_demapper::lookup_table_" + n), dtype=np.int64) for n in ("bpsk", "qpsk")}
+
+def ref_crc8():
+    return np.array(parse_array(_read("kernel/core/inc/CRC8.h"), "LUT_CRC8"), dtype=np.int64)
+
+def ref_ltf_masks():
+    """-> (lltf_plus[64], htltf_plus[64]) booleans: carriers whose training symbol is +1 (channel_11n.hpp:7-32, 300-325)."""
+    t = _read("kernel/bb/Brick11/src/channel_11n.hpp")
+    l = np.array(parse_array(t, "_80211_LLTFMask"), dtype=np.int64) & 0xFFFFFFFF
+    h = np.array(parse_array(t, "_80211n_HTLTFMask"), dtype=np.int64) & 0xFFFFFFFF
+    assert set(l.tolist()) <= {0x0000FFFF, 0xFFFF0000} and set(h.tolist()) <= {0, 0xFFFFFFFF}
+    return l == 0xFFFF0000, h == 0
+
+def ref_ht_ndbps():
+    """{mcs: (N_CBPS, N_DBPS)} from DOT11N_RATE_PARAMS (ieee80211const.h:35-55)."""
+    v = parse_array(_read("kernel/bb/Brick11/src/ieee80211const.h"), "DOT11N_RATE_PARAMS")
+    return {m: (v[2 * m], v[2 * m + 1]) for m in range(16)}
+
 def ref_demap_luts():
     t = _read("kernel/bb/Brick11/src/demapper.h")
     return {n: np.array(parse_array(t, "DemapperCore::" + n), dtype=np.uint8)
