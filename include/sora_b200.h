@@ -125,6 +125,33 @@ int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samp
                       const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
                       uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, void* cuda_stream);
 
+/* 802.11n 2x2 receive path (HT mixed format, 20 MHz, two spatial streams; the reference accepts MCS 8, 9 and 10 only,
+ * PHY_11n.hpp:496-501).  Replaces the graph of kernel/bb/demod11/fb11ndemod_config.hpp:167-262 (CreateDemodGraph11n) driven like
+ * kernel/bb/demod11/fb11n_demod.cpp:29-81: TMemSamples2 -> TDownSample2 -> TCCA11n | TFreqEstimator_11n ... TSisoChannelEst |
+ * TFreqComp_11n -> T11nDataSymbol -> 2 x TFFT64 -> {SIG: TSisoChannelComp, TMrcCombine, T11nSigDemap, T11nViterbiSig, T11nSigParser |
+ * HT-LTF: TMimoChannelEst | data: TMimoChannelComp, TPilotTrack_11n, T11nDemap*, T11nDeinterleave*_S0/_S1, TStreamJoin/Concat,
+ * T11aViterbi<40000,312,192,36>, T11aDesc, TBB11aFrameSink}.  iq0 / iq1 are the two antenna captures (40 Msps, interleaved int16
+ * I,Q), both host or both device; slot i covers samples [frame_off[i], frame_off[i]+frame_len[i]) of BOTH captures. */
+typedef struct sb200_frame_result_11n {
+    uint32_t status;        /* SB200_FRAME_* */
+    uint32_t mcs;           /* CF_HTRxVector::ht_frame_mcs */
+    uint32_t length;        /* CF_11aRxVector::frame_length: HT LENGTH once HT-SIG parsed, else 2 x L-SIG LENGTH, else 0 */
+    uint32_t crc32;         /* received FCS */
+    uint32_t nsym;          /* CF_11aRxVector::total_symbols: data symbols + 4 (PHY_11n.hpp:508) */
+    uint32_t detect_index;  /* 20 Msps sample index, relative to the slot, of the first sample routed to the L-LTF branch */
+    int16_t  cfo_est;       /* CF_CFOffset::CFO_est: 2^16/2pi radians per 20 Msps sample */
+    uint16_t lsig_length;   /* 2 x L-SIG LENGTH (PHY_11n.hpp:476) */
+} sb200_frame_result_11n;
+int sb200_rx11n_batch(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples,
+                      const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
+                      uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11n* res, void* cuda_stream);
+/* Stage taps for parity tests (host outputs, any may be NULL): siso [n][2][64][2] legacy channel per antenna, hinv [n][4][64][2]
+ * inverse 2x2 channel (11,12,21,22), eq [n][2][max_sym][64][2] per-stream equalised data symbols, theta [n][max_sym] NCO phase
+ * after each data symbol, sig [n][16] the nine L-SIG/HT-SIG bytes, soft [n][soft_stride] stream-parsed soft values. */
+int sb200_rx11n_taps(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples, const uint64_t* frame_off,
+                     const uint32_t* frame_len, uint32_t nframes, uint32_t max_sym, sb200_frame_result_11n* res,
+                     int16_t* siso, int16_t* hinv, int16_t* eq, int16_t* theta, uint8_t* sig, uint8_t* soft, uint64_t soft_stride);
+
 /* Standalone K=7 Viterbi over `nblocks` independent blocks of `nsoft` soft values (uint8 0..7, one per coded bit after
  * puncturing; block b starts at soft + b*soft_stride).  frame_len_bytes L sets the flush point 8L+16+6 exactly like
  * CF_11aRxVector::frame_length; each block yields L+2 bytes (SERVICE + PSDU, not descrambled) at out + b*out_stride.

@@ -18,8 +18,12 @@ RESULT_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u
 
 RESULT11B_DTYPE = np.dtype([("status", "<u4"), ("rate_kbps", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("sample_index", "<u4"), ("detect_vec", "<u4")])
 
+RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4"), ("crc32", "<u4"), ("nsym", "<u4"),
+                            ("detect_index", "<u4"), ("cfo_est", "<i2"), ("lsig_length", "<u2")])
+
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps"]
+           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
+           "sb200_rx11n_batch", "sb200_rx11n_taps"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -128,6 +132,30 @@ class Engine:
 
     def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         self._check(self._lib.sb200_rx11b_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11b_batch")
+
+    def rx11n_raw(self, iq0_ptr, iq1_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
+        self._check(self._lib.sb200_rx11n_batch(self._h, C.c_void_p(iq0_ptr), C.c_void_p(iq1_ptr), C.c_uint64(iq_total), C.c_void_p(off_ptr), C.c_void_p(len_ptr),
+                                                C.c_uint32(nframes), C.c_void_p(out_ptr), C.c_uint32(out_stride), C.c_void_p(res_ptr), C.c_void_p(stream)), "sb200_rx11n_batch")
+
+    def rx11n_batch(self, iq0, iq1, frame_off, frame_len, out_stride=1536):
+        """802.11n 2x2: iq0 / iq1 int16 [n,2] at 40 Msps (the two antennas); returns (results RESULT11N_DTYPE [F], bytes [F, out_stride])."""
+        iq0 = np.ascontiguousarray(iq0, dtype=np.int16).reshape(-1, 2); iq1 = np.ascontiguousarray(iq1, dtype=np.int16).reshape(-1, 2)
+        assert iq0.shape == iq1.shape
+        off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32); nf = len(off)
+        res = np.zeros(nf, dtype=RESULT11N_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+        self.rx11n_raw(_ptr(iq0), _ptr(iq1), iq0.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
+        return res, out
+
+    def rx11n_taps(self, iq0, iq1, frame_off, frame_len, max_sym=300):
+        iq0 = np.ascontiguousarray(iq0, dtype=np.int16).reshape(-1, 2); iq1 = np.ascontiguousarray(iq1, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32); nf = len(off)
+        res = np.zeros(nf, dtype=RESULT11N_DTYPE)
+        siso = np.zeros((nf, 2, 64, 2), np.int16); hinv = np.zeros((nf, 4, 64, 2), np.int16); eq = np.zeros((nf, 2, max_sym, 64, 2), np.int16)
+        theta = np.zeros((nf, max_sym), np.int16); sig = np.zeros((nf, 16), np.uint8); sstride = max_sym * 208; soft = np.zeros((nf, sstride), np.uint8)
+        self._check(self._lib.sb200_rx11n_taps(self._h, C.c_void_p(_ptr(iq0)), C.c_void_p(_ptr(iq1)), C.c_uint64(iq0.shape[0]), C.c_void_p(_ptr(off)), C.c_void_p(_ptr(ln)),
+                                               C.c_uint32(nf), C.c_uint32(max_sym), C.c_void_p(_ptr(res)), C.c_void_p(_ptr(siso)), C.c_void_p(_ptr(hinv)), C.c_void_p(_ptr(eq)),
+                                               C.c_void_p(_ptr(theta)), C.c_void_p(_ptr(sig)), C.c_void_p(_ptr(soft)), C.c_uint64(sstride)), "sb200_rx11n_taps")
+        return dict(res=res, siso=siso, hinv=hinv, eq=eq, theta=theta, sig=sig[:, :9], soft=soft)
 
     def rx11b_batch(self, iq, frame_off, frame_len, out_stride=4096):
         """802.11b: iq int16 [n,2] at 44 Msps; returns (results RESULT11B_DTYPE [F], bytes uint8 [F, out_stride])."""

@@ -3,6 +3,7 @@
 #include "../../include/sora_b200.h"
 #include "viterbi_k7_quad.cuh"
 #include "rx11b_kernels.cuh"
+#include "rx11n_kernels.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -65,6 +66,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
+    DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
@@ -145,7 +147,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -416,6 +418,139 @@ extern "C" int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq
     }
     if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nframes * sizeof(Result11b), cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+// ---- 802.11n 2x2 ----------------------------------------------------------------------------------------------------------
+static int upload_tables11n(sb200_handle* h) {
+    if (h->tab11n.p) return SB200_OK;
+    HostTables11n* H = new (std::nothrow) HostTables11n();
+    if (!H) return h->fail(SB200_E_NOMEM, "host tables 11n");
+    build_host_tables11n(*H);
+    size_t o = 0; auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t o_sc = take(sizeof H->sincos), o_at = take(sizeof H->atan_lut), o_dm = take(256), o_c8 = take(256), o_pos = take(sizeof H->pos), o_l = take(64), o_ht = take(64);
+    cudaError_t e = h->tab11n.need(o);
+    if (e != cudaSuccess) { delete H; return h->fail(SB200_E_NOMEM, "cudaMalloc tables 11n", e); }
+    char* base = (char*)h->tab11n.p;
+    auto up = [&](size_t off, const void* src, size_t bytes) { return cudaMemcpy(base + off, src, bytes, cudaMemcpyHostToDevice); };
+    e = up(o_sc, H->sincos, sizeof H->sincos);
+    if (e == cudaSuccess) e = up(o_at, H->atan_lut, sizeof H->atan_lut);
+    if (e == cudaSuccess) e = up(o_dm, H->demap, 256);
+    if (e == cudaSuccess) e = up(o_c8, H->crc8, 256);
+    if (e == cudaSuccess) e = up(o_pos, H->pos, sizeof H->pos);
+    if (e == cudaSuccess) e = up(o_l, H->lltf_pos, 64);
+    if (e == cudaSuccess) e = up(o_ht, H->htltf_pos, 64);
+    delete H;
+    if (e != cudaSuccess) { h->tab11n.release(); return h->fail(SB200_E_CUDA, "table upload 11n", e); }
+    DevTables11n& N = h->N;
+    N.sincos = (const uint32_t*)(base + o_sc); N.atan_lut = (const int16_t*)(base + o_at); N.demap = (const uint8_t*)(base + o_dm); N.crc8 = (const uint8_t*)(base + o_c8);
+    N.pos = (const uint8_t*)(base + o_pos); N.lltf_pos = (const uint8_t*)(base + o_l); N.htltf_pos = (const uint8_t*)(base + o_ht);
+    return SB200_OK;
+}
+
+__global__ void k_pack_results11n(const FrameInfo* __restrict__ info, const uint32_t* __restrict__ status, const uint32_t* __restrict__ crc, uint32_t n,
+                                  sb200_frame_result_11n* __restrict__ res) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FrameInfo fi = info[i];
+    sb200_frame_result_11n r;
+    const bool decoded = fi.status == E_SUCCESS;
+    r.status = decoded ? status[i] : fi.status; r.mcs = fi.rate_kbps; r.length = fi.length; r.crc32 = decoded ? crc[i] : 0u; r.nsym = fi.nsym_total;
+    r.detect_index = fi.detect_vec == 0xFFFFFFFFu ? 0u : fi.detect_vec * 4u;
+    r.cfo_est = (int16_t)fi.cfo_est; r.lsig_length = (uint16_t)fi.peak_index;
+    res[i] = r;
+}
+
+static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                     uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11n* res, cudaStream_t st, Taps11n taps,
+                     uint8_t* soft_host, uint64_t soft_host_stride) {
+    if (!h || !iq0 || !iq1 || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (nframes == 0) return SB200_OK;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_tables11n(h); if (rc != SB200_OK) return rc;
+    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len), iq_dev = is_device_ptr(iq0);
+    if (iq_dev != is_device_ptr(iq1)) return h->fail(SB200_E_INVALID, "both antenna buffers must live on the same side");
+    std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
+    const bool cached = off_dev && len_dev && h->tab_off == frame_off && h->tab_len == frame_len && h->tab_n == nframes && h->tab_total == iq_total;
+    if (!cached) {
+        offh.resize(nframes); lenh.resize(nframes);
+        if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
+        if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
+        if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+        h->tab_max_len = 0;
+        for (uint32_t i = 0; i < nframes; i++) {
+            if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+            if (lenh[i] > h->tab_max_len) h->tab_max_len = lenh[i];
+        }
+        if (off_dev && len_dev) { h->tab_off = frame_off; h->tab_len = frame_len; h->tab_n = nframes; h->tab_total = iq_total; } else h->tab_off = nullptr;
+    }
+    const uint32_t* d_iq0; const uint32_t* d_iq1; const uint64_t* d_off; const uint32_t* d_len;
+    if (iq_dev) { d_iq0 = (const uint32_t*)iq0; d_iq1 = (const uint32_t*)iq1; }
+    else {
+        CK(h->iq.need(iq_total * 4ull)); CK(h->iq1.need(iq_total * 4ull));
+        CK(cudaMemcpyAsync(h->iq.p, iq0, iq_total * 4ull, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->iq1.p, iq1, iq_total * 4ull, cudaMemcpyHostToDevice, st));
+        d_iq0 = (const uint32_t*)h->iq.p; d_iq1 = (const uint32_t*)h->iq1.p;
+    }
+    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
+    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
+    const uint64_t max_sym = (h->tab_max_len / 2u) / 80u + 1u;
+    const uint64_t soft_stride = ((max_sym * 208ull) + 15ull) & ~15ull;
+    const uint64_t row = 1536;                         // >= 1500 (MTU, PHY_11n.hpp:478,505)
+    CK(h->info.need(nframes * sizeof(FrameInfo))); CK(h->soft.need(nframes * soft_stride)); CK(h->out.need(nframes * row));
+    CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result_11n)));
+    FrameInfo* d_info = (FrameInfo*)h->info.p;
+    CK(cudaEventRecord(h->ev0, st)); CK(cudaEventRecord(h->evk[0], st));
+    k_sync11n<<<(nframes + 127) / 128, 128, 0, st>>>(d_iq0, d_iq1, d_off, d_len, nframes, d_info);
+    CK(cudaEventRecord(h->evk[1], st));
+    k_front11n<<<(nframes + SB_FRONT11N_WARPS - 1) / SB_FRONT11N_WARPS, 32 * SB_FRONT11N_WARPS, 0, st>>>(d_iq0, d_iq1, d_off, d_len, nframes, h->T, h->N, h->inv_deint,
+            d_info, (uint8_t*)h->soft.p, soft_stride, taps);
+    CK(cudaEventRecord(h->evk[2], st));
+    VitJob job{}; job.depth = 192; job.lookahead = 36; job.raw = 0;                    // T11aViterbi<5000*8, 312, 192, 36> (fb11ndemod_config.hpp:189)
+    const unsigned g = (nframes + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
+    k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    CK(cudaEventRecord(h->evk[3], st));
+    const bool res_dev = is_device_ptr(res);
+    sb200_frame_result_11n* d_res = res_dev ? res : (sb200_frame_result_11n*)h->res.p;
+    k_pack_results11n<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
+    CK(cudaEventRecord(h->evk[4], st)); CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 4; h->launches += 5;
+    CK(cudaGetLastError());
+    bool host_out = false;
+    if (out_bytes && out_stride) {
+        const size_t w = out_stride < row ? out_stride : row; const bool od = is_device_ptr(out_bytes);
+        CK(cudaMemcpy2DAsync(out_bytes, out_stride, h->out.p, row, w, nframes, od ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        host_out |= !od;
+    }
+    if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nframes * sizeof(sb200_frame_result_11n), cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (host_out) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+extern "C" int sb200_rx11n_batch(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples, const uint64_t* frame_off,
+                                 const uint32_t* frame_len, uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11n* res, void* cuda_stream) {
+    Taps11n taps{};
+    return rx11n_run(h, iq0, iq1, iq_total_samples, frame_off, frame_len, nframes, out_bytes, out_stride, res, (cudaStream_t)cuda_stream, taps, nullptr, 0);
+}
+
+extern "C" int sb200_rx11n_taps(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples, const uint64_t* frame_off,
+                                const uint32_t* frame_len, uint32_t nframes, uint32_t max_sym, sb200_frame_result_11n* res,
+                                int16_t* siso, int16_t* hinv, int16_t* eq, int16_t* theta, uint8_t* sig, uint8_t* soft, uint64_t soft_stride) {
+    if (!h) return SB200_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const size_t b0 = (size_t)nframes * 2 * 64 * 4, b1 = (size_t)nframes * 4 * 64 * 4, b2 = (size_t)nframes * 2 * max_sym * 64 * 4 + 4, b3 = (size_t)nframes * max_sym * 2 + 4, b4 = (size_t)nframes * 16;
+    const size_t sz[5] = {b0, b1, b2, b3, b4};
+    for (int i = 0; i < 5; i++) { CK(h->taps[i].need(sz[i])); CK(cudaMemset(h->taps[i].p, 0, sz[i])); }
+    Taps11n taps{};
+    taps.siso = (uint32_t*)h->taps[0].p; taps.hinv = (uint32_t*)h->taps[1].p; taps.eq = (uint32_t*)h->taps[2].p; taps.theta = (int16_t*)h->taps[3].p; taps.sig = (uint8_t*)h->taps[4].p; taps.max_sym = max_sym;
+    int rc = rx11n_run(h, iq0, iq1, iq_total_samples, frame_off, frame_len, nframes, nullptr, 0, res, 0, taps, soft, soft_stride);
+    if (rc != SB200_OK) return rc;
+    if (siso) CK(cudaMemcpy(siso, h->taps[0].p, b0, cudaMemcpyDeviceToHost));
+    if (hinv) CK(cudaMemcpy(hinv, h->taps[1].p, b1, cudaMemcpyDeviceToHost));
+    if (eq) CK(cudaMemcpy(eq, h->taps[2].p, b2 - 4, cudaMemcpyDeviceToHost));
+    if (theta) CK(cudaMemcpy(theta, h->taps[3].p, b3 - 4, cudaMemcpyDeviceToHost));
+    if (sig) CK(cudaMemcpy(sig, h->taps[4].p, b4, cudaMemcpyDeviceToHost));
     return SB200_OK;
 }
 
