@@ -4,6 +4,7 @@
   --config viterbi   config #5: standalone K=7 soft Viterbi, rates 1/2, 2/3, 3/4, independent blocks of 20 022 information
                      bits (max 11a frame, 2500 B), device-resident soft values; coded bits/s and decoded Mbit/s
   --config 11b       config #3: 802.11b 11 Mbps CCK RX chain, PSDU 1500 B, 44 Msps, one frame per slot
+  --config 11n       config #4: 802.11n HT-MF 2x2 RX chain at MCS 8, 9, 10, PSDU 1500 B, 2 x 40 Msps, fixed 2x2 channel
 
 Each prints one JSON line per measurement (same timing rules as bench.py: >= 3 warm-ups, CUDA events on the launch
 stream, inputs larger than L2).  Results are checked against the CPU oracle on a sample before timing.
@@ -102,11 +103,47 @@ def bench_11b(args):
                       "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msamples/s", "cores": ncpu, "kind": "port", "sample": f"{n} slots"},
                       "parity": "bytes and verdicts identical to the oracle on the %d unique slots" % U}))
 
+def bench_11n(args):
+    import torch, oracle_py
+    from sora_b200 import api, synth
+    eng = api.Engine(0); dev = torch.device("cuda", 0); st = torch.cuda.current_stream()
+    for mcs in (8, 9, 10):
+        U = 32
+        iq0, iq1, ps = synth.make_frames_11n(U, psdu_len=1500, mcs=mcs, snr_db=30, lead=400, trail=200)      # fixed 2x2 channel [[1, 0.3j], [-0.2, 0.9]]
+        F0, slot, _ = iq0.shape
+        F = args.frames
+        d0 = torch.from_numpy(iq0.reshape(U, -1)).to(dev).repeat((F + U - 1) // U, 1)[:F].contiguous()
+        d1 = torch.from_numpy(iq1.reshape(U, -1)).to(dev).repeat((F + U - 1) // U, 1)[:F].contiguous()
+        d_off = torch.arange(F, dtype=torch.int64, device=dev) * slot; d_len = torch.full((F,), slot, dtype=torch.int32, device=dev)
+        d_out = torch.zeros((F, 1536), dtype=torch.uint8, device=dev); d_res = torch.zeros((F, 7), dtype=torch.int32, device=dev)
+        def step(): eng.rx11n_raw(d0.data_ptr(), d1.data_ptr(), F * slot, d_off.data_ptr(), d_len.data_ptr(), F, d_out.data_ptr(), 1536, d_res.data_ptr(), st.cuda_stream)
+        step(); torch.cuda.synchronize()
+        ores, oout = oracle_py.rx11n_batch(iq0.reshape(-1, 2), iq1.reshape(-1, 2), np.arange(U) * slot, np.full(U, slot), out_stride=1536)
+        assert (ores["status"] == 1).all() and (oout[:, :1500] == ps).all()
+        assert (d_res[:, 0].cpu().numpy() == 1).all() and (d_out[:U, :1500].cpu().numpy() == oout[:, :1500]).all()
+        for _ in range(3): step()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(st)
+        for _ in range(args.steps): step()
+        e1.record(st); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        kt = eng.last_kernel_times()
+        ncpu = os.cpu_count() or 1; n = 1024
+        t0 = time.perf_counter(); oracle_py.rx11n_batch(iq0.reshape(-1, 2), iq1.reshape(-1, 2), (np.arange(n) % U) * slot, np.full(n, slot), out_stride=1536, nthreads=ncpu); dt = time.perf_counter() - t0
+        alg = F * (slot * 8.0 + 1516)
+        print(json.dumps({"metric": "802.11n 2x2 RX PHY Msample-pairs/s (2 x IQ in, bits out)", "mcs": mcs, "value": F * slot / (ms * 1e-3) / 1e6, "unit": "Msample-pairs/s", "ms_per_step": ms,
+                          "n_gpus": 1, "config": {"workload": "802.11n HT-MF 2x2, 20 MHz, PSDU 1500 B, 40 Msps per antenna, AWGN 30 dB, channel [[1,0.3j],[-0.2,0.9]] (BASELINE config #4)",
+                                                   "slots_per_step": F, "sample_pairs_per_slot": int(slot), "unique_slots": U},
+                          "kernel_ms": dict(zip(("carrier_sense", "ofdm_front_end", "viterbi_descramble_crc", "pack"), kt)) if kt is not None else None,
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks()},
+                          "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msample-pairs/s", "cores": ncpu, "kind": "port", "sample": f"{n} slots"},
+                          "parity": "bytes and verdicts identical to the oracle on the %d unique slots" % U}))
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["viterbi", "11b"], required=True)
+    ap.add_argument("--config", choices=["viterbi", "11b", "11n"], required=True)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--blocks", type=int, default=32768)
     ap.add_argument("--frames", type=int, default=32768)
     a = ap.parse_args()
-    bench_viterbi(a) if a.config == "viterbi" else bench_11b(a)
+    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n}[a.config](a)
