@@ -42,21 +42,22 @@ __host__ __device__ constexpr unsigned vq_sel(int i0, int i1) { return (unsigned
 
 struct VqLane {
     unsigned swz[6];       // per-phase byte swizzle applying this lane's class contribution
-    unsigned lm[2], lo[2]; // lane-phase role mask of this lane's own registers (even: & EV, odd: (& FF) | ONE)
+    unsigned lo[2];        // lane-phase role of this lane's own registers: the odd role adds the survivor mark
 };
 
 // one trellis step at compile-time phase T.  Cbase byte (cA<<1|cB) = metric of the even candidate for a predecessor of
 // that class; the complement class (3 - index) is the odd candidate's.
 template <int T>
 __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
+    // R comes in with the survivor marks already removed (vq_commit); the odd role is then a plain add of the mark.
     const uint32_t Cb = __byte_perm(Cbase, 0, L.swz[T]);
-    const uint32_t EV = 0xFE00FE00u, FF = 0xFF00FF00u, ONE = 0x01000100u;
+    const uint32_t ONE = 0x01000100u;
     if (T <= 1) {                                       // pair = partner lane (xor 2 at T=0, xor 1 at T=1)
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int c0 = vq_scls(T, r, 0), c1 = vq_scls(T, r, 1);
             uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
-            uint32_t own = (R[r] & L.lm[T]) | L.lo[T];  // marked according to this lane's role; the partner did the same
+            uint32_t own = R[r] + L.lo[T];              // marked according to this lane's role; the partner did the same
             uint32_t Z = __shfl_xor_sync(qmask, own, T == 0 ? 2 : 1);
             R[r] = __vminu2(own + av, Z + bv);
         }
@@ -65,7 +66,7 @@ __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const 
         for (int r = 0; r < 8; r++) {
             const int c = vq_scls(2, r, 0);             // class of p (low half); the high half is p+32: complement
             uint32_t ab = __byte_perm(Cb, 0, vq_sel(c, 3 - c)), ba = __byte_perm(Cb, 0, vq_sel(3 - c, c));
-            uint32_t m = (R[r] & 0xFF00FE00u) | 0x01000000u;              // low half = even role, high half = odd role
+            uint32_t m = R[r] + 0x01000000u;            // low half = even role, high half = odd role
             uint32_t t1 = m + ab, t2 = m + ba;          // t1 = [p+a, p32+b], t2 = [p+b, p32+a]
             R[r] = __vminu2(__byte_perm(t1, t2, 0x5410), __byte_perm(t1, t2, 0x7632));   // [t1.lo, t2.lo] vs [t1.hi, t2.hi]
         }
@@ -76,17 +77,21 @@ __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const 
             if (r & d) continue;
             const int c0 = vq_scls(T, r, 0), c1 = vq_scls(T, r, 1);
             uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
-            uint32_t X = R[r] & EV, Y = (R[r + d] & FF) | ONE;
+            uint32_t X = R[r], Y = R[r + d] + ONE;
             R[r]     = __vminu2(X + av, Y + bv);
             R[r + d] = __vminu2(X + bv, Y + av);
         }
     }
 }
-__device__ __forceinline__ uint32_t vq_decisions(const uint32_t (&R)[8]) {   // survivor bit of (reg r, half h) -> bit 8h + r
+// Take the survivor marks (bit 8 of each half) out of the fresh metrics and return them as the 16 decision bits of this
+// lane: bit 8h + r.  One LOP3 per register; the subtraction and the gather (m << r accumulated) are IMADs on the FMA pipe.
+// The bytes below the metrics ("dead" bytes) collect the wrap carries of the low halves; they never decide a compare
+// (the candidates' marks differ) and are wiped at every normalisation, long before they could overflow.
+__device__ __forceinline__ uint32_t vq_commit_marks(uint32_t (&R)[8]) {
     uint32_t acc = 0;
 #pragma unroll
-    for (int r = 0; r < 8; r++) acc |= (R[r] << r) & (0x01000100u << r);      // left shifts only: IMAD.SHL on the FMA pipe
-    return ((acc >> 8) & 0xFFu) | ((acc >> 16) & 0xFF00u);
+    for (int r = 0; r < 8; r++) { const uint32_t m = R[r] & 0x01000100u; R[r] -= m; acc = m * (1u << r) + acc; }
+    return __byte_perm(acc, 0, 0x4431);                 // [byte 1, byte 3, 0, 0]
 }
 // branch-metric byte vectors (byte index = cA<<1 | cB) from soft values in bytes B0 (A) and B0+1 (B) of the packed word w
 __device__ __forceinline__ int vq_dp4a_us(uint32_t a, int b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
@@ -109,14 +114,14 @@ template <int CODE_RATE>
 __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t* __restrict__ soft, uint64_t soft_stride,
         uint32_t nframes, const FrameInfo* __restrict__ info, VitJob job, DevTables T,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t* __restrict__ status_out, uint32_t* __restrict__ crc_out) {
-    __shared__ unsigned long long s_ring[SB_VQ_RING][SB_VQ_FR];
-    __shared__ uint32_t s_crc[16];                     // CRC-32 (reflected 0xEDB88320, core/inc/CRC32.h:76) four bits at a time
+    __shared__ unsigned long long s_ring[SB_VQ_RING][SB_VQ_FR];    // column c lives in slot (c - 1) mod SB_VQ_RING
+    __shared__ uint32_t s_crc[256];                    // CRC-32 (reflected 0xEDB88320, core/inc/CRC32.h:76)
     __shared__ uint8_t s_scr[128];
     __shared__ uint8_t s_win[SB_VQ_FR][48];
     const int lane = threadIdx.x & 31, q = lane & 3;
     const unsigned QM = 0xFu << (lane & 28);           // the 4 lanes of this code block: quads run as independent sub-warps
     const int fb = (threadIdx.x >> 2);                 // code block within the CTA
-    if (threadIdx.x < 16) { uint32_t c = threadIdx.x; for (int k = 0; k < 4; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; s_crc[threadIdx.x] = c; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = __ldg(T.crc32 + i);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_scr[i] = __ldg(T.scramble + i);
     __syncthreads();
     const uint32_t f = blockIdx.x * SB_VQ_FR + fb;
@@ -141,10 +146,9 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         LC.swz[t] = (unsigned)((0 ^ lc) | ((1 ^ lc) << 4) | ((2 ^ lc) << 8) | ((3 ^ lc) << 12));
     }
     {
-        const uint32_t EV = 0xFE00FE00u, FF = 0xFF00FF00u, ONE = 0x01000100u;
+        const uint32_t ONE = 0x01000100u;
         int b0 = (q >> 1) & 1, b1 = q & 1;              // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
-        LC.lm[0] = b0 ? FF : EV; LC.lo[0] = b0 ? ONE : 0u;
-        LC.lm[1] = b1 ? FF : EV; LC.lo[1] = b1 ? ONE : 0u;
+        LC.lo[0] = b0 ? ONE : 0u; LC.lo[1] = b1 ? ONE : 0u;
     }
     // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address
     uint32_t R[8];
@@ -152,42 +156,41 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
     for (int r = 0; r < 8; r++) R[r] = 0x30003000u;
     if (q == 0) R[0] = 0x30000000u;
     const uint32_t end = L * 8u + 16u + 6u;
-    uint32_t t = 0, ob = 0;
-    uint32_t wcol = 0;                                  // ring slot of column t (t % SB_VQ_RING)
+    uint32_t tb = 0, ob = 0;                            // tb = trellis time at the start of the current 6-step chunk
+    uint32_t wcol = 0;                                  // ring slot of column tb + 1 (multiple of 6)
+    uint32_t next_tb = min(end, depth + look + 6u);     // first time a traceback can fire (viterbi.hpp:182-203)
+    uint32_t lastdec = 0;                               // this lane's 16 survivor marks of the newest column
     uint32_t desc_count = 0, desc_reg = 0, byte_count = 0, crc = 0xFFFFFFFFu, fcs = 0, verdict = E_SUCCESS, nraw = 0;
     bool done = false;
-    uint16_t* ring16 = (uint16_t*)&s_ring[0][0] + fb * 4 + q;      // + col * (4 * SB_VQ_FR)
+    uint16_t* ring16 = (uint16_t*)&s_ring[0][0] + fb * 4 + q;      // + slot * (4 * SB_VQ_FR)
     uint32_t pos_soft = 0;
 
-    // normalisation + traceback triggers, evaluated after every puncture group; tm = t % 6 (compile time in the main loop),
-    // cslot = ring slot of column t
-    auto after_group = [&](const uint32_t tm, const uint32_t cslot) {
-        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465
+    // normalisation + traceback triggers, evaluated after every puncture group at time t (column t sits in ring slot cslot);
+    // tm = t % 6 is a compile-time constant in the main loop
+    auto after_group = [&](const uint32_t t, const uint32_t tm, const uint32_t cslot) {
+        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465 (marks are already out: min & 0xFE unchanged)
             uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
             m = min(m & 0xFFFFu, m >> 16) >> 8;         // smallest metric byte of this lane
             m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            const uint32_t mv = (m & 0xFEu) * 0x01000100u;
+            const uint32_t mv = m * 0x01000100u;
 #pragma unroll
-            for (int r = 0; r < 8; r++) R[r] -= mv;        // every metric byte >= m: no borrow between halves
+            for (int r = 0; r < 8; r++) R[r] = (R[r] - mv) & 0xFF00FF00u;     // every metric byte >= m: no borrow; dead bytes wiped
         }
-        uint32_t nout = 0, la = 0;                      // viterbi.hpp:182-203
+        if (t < next_tb) return;
+        uint32_t nout, la;                              // viterbi.hpp:182-203
         if (t >= end) { nout = end - ob - 6u; la = t - end; }
-        else if (t >= ob + depth + look + 6u) { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
+        else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
         if (nout) {                                     // uniform inside the quad
-            // best state: smallest (metric, state index) over the 64 slots (viterbicore.h:468-520)
-            uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
-            m = min(m & 0xFFFFu, m >> 16) >> 8;
-            m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            uint32_t best = 0xFFFFu;                    // (state index << 8) | address
+            // best state: smallest (metric incl. mark, state index) over the 64 slots (viterbicore.h:468-520)
+            uint32_t best = 0xFFFFFFFFu;                // (metric | mark) << 16 | state index << 8 | address
 #pragma unroll
             for (int r = 0; r < 8; r++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    uint32_t v = h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu);
-                    uint32_t A = ((uint32_t)q << 4) | (h << 3) | r;
-                    uint32_t n = ((A << tm) | (A >> (6u - tm))) & 63u;         // state index of this slot at time t
-                    uint32_t key = (n << 8) | A;
-                    if (v == m && key < best) best = key;
+                    const uint32_t v = (h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu)) | ((lastdec >> (8 * h + r)) & 1u);
+                    const uint32_t A = ((uint32_t)q << 4) | (h << 3) | r;
+                    const uint32_t n = ((A << tm) | (A >> (6u - tm))) & 63u;   // state index of this slot at time t
+                    best = min(best, (v << 16) | (n << 8) | A);
                 }
             }
             best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
@@ -195,24 +198,39 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
             if (q == 0) {
                 // traceback in address space: survivor bit d of slot A at column c = bit A of that column's word;
                 // the predecessor slot is A with bit (6 - c%6)%6 replaced by d; d is also the decoded bit of column c.
-                uint32_t A = best & 63u, col = cslot, cm = tm;
-                auto back = [&]() -> uint32_t {
+                uint32_t A = best & 63u, col = cslot, cm = tm, todo = la + nout;
+                unsigned long long fifo = 0; int cnt = -(int)la;            // the first `la` bits are only looked through
+                uint8_t* win = s_win[fb]; uint32_t wpos = nout >> 3;        // bytes come out last-first; the sink needs them first-first
+                auto emit = [&]() { while (cnt >= 8) { win[--wpos] = (uint8_t)(fifo >> (cnt - 8)); cnt -= 8; } };
+                while (cm != 0 && todo) {               // up to 5 columns until the column phase is 0
                     const unsigned long long w = s_ring[col][fb];
-                    const uint32_t d = (uint32_t)(w >> A) & 1u;
-                    const uint32_t j = cm ? 6u - cm : 0u;
+                    const uint32_t d = (uint32_t)(w >> A) & 1u, j = 6u - cm;
                     A = (A & ~(1u << j)) | (d << j);
-                    col = col ? col - 1 : SB_VQ_RING - 1; cm = cm ? cm - 1 : 5;
-                    return d;
-                };
-                for (uint32_t i = 0; i < la; i++) back();
-                const uint32_t nbytes = nout >> 3;      // <= 35 (final flush)
-                uint8_t* win = s_win[fb];               // bytes come out last-first; the sink needs them first-first
-                for (uint32_t b = 0; b < nbytes; b++) {
-                    uint32_t ch = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) ch = (ch << 1) | back();
-                    win[nbytes - 1 - b] = (uint8_t)ch;
+                    col = col ? col - 1 : SB_VQ_RING - 1; cm--; todo--;
+                    fifo = (fifo << 1) | d; cnt++;
                 }
+                emit();
+                while (todo >= 6) {                     // six columns with phases 0,5,4,3,2,1: bit k of A is replaced at the k-th of them,
+                    const unsigned long long* wp = &s_ring[col][fb];       // and slots col..col-5 never wrap (col % 6 == 5)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const unsigned long long w = wp[-k * SB_VQ_FR];
+                        const uint32_t d = (uint32_t)(w >> A) & 1u;
+                        A = (A & ~(1u << k)) | (d << k);
+                    }
+                    col = col >= 6 ? col - 6 : col + SB_VQ_RING - 6; todo -= 6;
+                    fifo = (fifo << 6) | (__brev(A) >> 26); cnt += 6;       // decoded bits, newest column first
+                    emit();
+                }
+                while (todo) {                          // cm == 0 on entry
+                    const unsigned long long w = s_ring[col][fb];
+                    const uint32_t d = (uint32_t)(w >> A) & 1u, j = cm ? 6u - cm : 0u;
+                    A = (A & ~(1u << j)) | (d << j);
+                    col = col ? col - 1 : SB_VQ_RING - 1; cm = cm ? cm - 1 : 5; todo--;
+                    fifo = (fifo << 1) | d; cnt++;
+                }
+                emit();
+                const uint32_t nbytes = nout >> 3;      // <= 35 (final flush)
                 if (job.raw) {
                     for (uint32_t b = 0; b < nbytes; b++) op[(size_t)nraw + b] = win[b];
                 } else {
@@ -226,7 +244,7 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
                         if (byte_count < (uint32_t)((int)L - 4)) {
                             if (byte_count < out_cap) op[byte_count] = (uint8_t)o;
                             byte_count++;
-                            crc ^= o; crc = (crc >> 4) ^ s_crc[crc & 15]; crc = (crc >> 4) ^ s_crc[crc & 15];
+                            crc = (crc >> 8) ^ s_crc[(crc ^ o) & 0xFFu];
                         } else if (byte_count < L) {
                             if (byte_count < out_cap) op[byte_count] = (uint8_t)o;
                             byte_count++;
@@ -238,16 +256,16 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
                 nraw += nbytes;
             }
             ob += nout;
-            if (ob + 6u >= end && t >= end) done = true;
             __syncwarp(QM);
         }
+        if (ob + 6u >= end && t >= end) done = true;
+        next_tb = min(end, ob + depth + look + 6u);
+        if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
     };
-    // store the survivor bits of the new column; k = position inside the 6-step chunk (0 in the tail); returns its slot
-    auto commit = [&](const uint32_t k) -> uint32_t {
-        t++;
-        uint32_t slot = wcol + k + 1; if (slot >= SB_VQ_RING) slot -= SB_VQ_RING;
-        ring16[slot * (4 * SB_VQ_FR)] = (uint16_t)vq_decisions(R);
-        return slot;
+    // store the survivor bits of column tb + k + 1 (slot wcol + k); marks leave the metrics here
+    auto commit = [&](const uint32_t k) {
+        lastdec = vq_commit_marks(R);
+        ring16[(wcol + k) * (4 * SB_VQ_FR)] = (uint16_t)lastdec;
     };
 
     // main loop: 6 trellis steps (one phase cycle) per iteration; the next chunk's soft values are prefetched
@@ -267,41 +285,40 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
     while (!done && pos_soft + CHUNK_BYTES <= nsoft) {
         uint32_t n0, n1, n2; fetch(pos_soft + CHUNK_BYTES, n0, n1, n2);
         pos_soft += CHUNK_BYTES;
-        uint32_t sl;
         if (CODE_RATE == CR_12) {
-            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); sl = commit(0); after_group(1, sl);
-            vq_step<1>(R, vq_bm_ab<2>(w0), LC, QM); sl = commit(1); after_group(2, sl);
-            vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); sl = commit(2); after_group(3, sl);
-            vq_step<3>(R, vq_bm_ab<2>(w1), LC, QM); sl = commit(3); after_group(4, sl);
-            vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); sl = commit(4); after_group(5, sl);
-            vq_step<5>(R, vq_bm_ab<2>(w2), LC, QM); sl = commit(5); after_group(0, sl);
+            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0); after_group(tb + 1, 1, wcol);
+            vq_step<1>(R, vq_bm_ab<2>(w0), LC, QM); commit(1); after_group(tb + 2, 2, wcol + 1);
+            vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); commit(2); after_group(tb + 3, 3, wcol + 2);
+            vq_step<3>(R, vq_bm_ab<2>(w1), LC, QM); commit(3); after_group(tb + 4, 4, wcol + 3);
+            vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); commit(4); after_group(tb + 5, 5, wcol + 4);
+            vq_step<5>(R, vq_bm_ab<2>(w2), LC, QM); commit(5); after_group(tb + 6, 0, wcol + 5);
         } else if (CODE_RATE == CR_34) {
             vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
             vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  commit(1);
-            vq_step<2>(R, vq_bm_b<3>(w0), LC, QM);  sl = commit(2); after_group(3, sl);
+            vq_step<2>(R, vq_bm_b<3>(w0), LC, QM);  commit(2); after_group(tb + 3, 3, wcol + 2);
             vq_step<3>(R, vq_bm_ab<0>(w1), LC, QM); commit(3);
             vq_step<4>(R, vq_bm_a<2>(w1), LC, QM);  commit(4);
-            vq_step<5>(R, vq_bm_b<3>(w1), LC, QM);  sl = commit(5); after_group(0, sl);
+            vq_step<5>(R, vq_bm_b<3>(w1), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
         } else {
             vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
-            vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  sl = commit(1); after_group(2, sl);
+            vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  commit(1); after_group(tb + 2, 2, wcol + 1);
             vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); commit(2);
-            vq_step<3>(R, vq_bm_a<2>(w1), LC, QM);  sl = commit(3); after_group(4, sl);
+            vq_step<3>(R, vq_bm_a<2>(w1), LC, QM);  commit(3); after_group(tb + 4, 4, wcol + 3);
             vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); commit(4);
-            vq_step<5>(R, vq_bm_a<2>(w2), LC, QM);  sl = commit(5); after_group(0, sl);
+            vq_step<5>(R, vq_bm_a<2>(w2), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
         }
-        wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING;
+        tb += 6; wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING;
         w0 = n0; w1 = n1; w2 = n2;
     }
     // tail: whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft).
     // Rare and short, so phases are dispatched at run time.
     {
-        uint32_t tm = 0, sl = wcol;                     // t % 6 (the main loop always leaves it at 0)
+        uint32_t tm = 0, k = 0;                         // t % 6 (the main loop always leaves it at 0), steps into the chunk at tb
         auto step_rt = [&](uint32_t Cbase) {
             switch (tm) { case 0: vq_step<0>(R, Cbase, LC, QM); break; case 1: vq_step<1>(R, Cbase, LC, QM); break;
                           case 2: vq_step<2>(R, Cbase, LC, QM); break; case 3: vq_step<3>(R, Cbase, LC, QM); break;
                           case 4: vq_step<4>(R, Cbase, LC, QM); break; default: vq_step<5>(R, Cbase, LC, QM); }
-            sl = commit(0); wcol = sl;
+            commit(k); k++;
             tm = tm == 5 ? 0 : tm + 1;
         };
         while (!done && pos_soft + GROUP <= nsoft) {
@@ -312,7 +329,8 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
             step_rt(vq_bm_ab<0>(w));
             if (GSTEPS >= 2) step_rt(vq_bm_a<2>(w));
             if (GSTEPS >= 3) step_rt(vq_bm_b<3>(w));
-            after_group(tm, sl);
+            after_group(tb + k, tm, wcol + k - 1);
+            if (k == 6) { k = 0; tb += 6; wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING; }
         }
     }
     if (q == 0) {
