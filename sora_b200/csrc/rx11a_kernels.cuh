@@ -41,8 +41,7 @@ __device__ __forceinline__ int d_uatan2(const DevTables& T, int y, int x) {     
     return (int)__ldg(&T.atan2_lut[((unsigned)y & 0xFF) * 256 + ((unsigned)x & 0xFF)]);
 }
 __device__ __forceinline__ cs16 d_rot(const DevTables& T, int th) {               // (ucos(th), -usin(th))
-    unsigned i = (unsigned)th & 0xFFFF;
-    return mk((int)__ldg(&T.cos_lut[i]), -(int)__ldg(&T.sin_lut[i]));
+    return unpack(__ldg(T.rot + ((unsigned)th & 0xFFFFu)));
 }
 
 // ------------------------------------------------------------------------------------------------

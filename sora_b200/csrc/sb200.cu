@@ -88,14 +88,17 @@ static int upload_tables(sb200_handle* h) {
     for (int m = 0; m < 4; m++) for (int k = 0; k < n[m]; k++) inv[offs[m] + H->deint[offs[m] + k]] = (uint16_t)k;
     // one arena, 256-byte aligned slices
     size_t o = 0; auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-    size_t o_sin = take(131072), o_cos = take(131072), o_at = take(131072), o_tw64 = take(sizeof H->tw64), o_tw16 = take(sizeof H->tw16),
+    std::vector<uint32_t> rot(65536);
+    for (int i = 0; i < 65536; i++) rot[i] = pack(mk((int)H->cos_lut[i], -(int)H->sin_lut[i]));
+    size_t o_rot = take(262144), o_sin = take(131072), o_cos = take(131072), o_at = take(131072), o_tw64 = take(sizeof H->tw64), o_tw16 = take(sizeof H->tw16),
            o_sts = take(sizeof H->sts), o_deint = take(sizeof H->deint), o_inv = take(sizeof inv), o_demap = take(sizeof H->demap),
            o_pil = take(128), o_lts = take(64), o_scr = take(128), o_crc = take(1024);
     cudaError_t e = h->tab.need(o);
     if (e != cudaSuccess) { delete H; return h->fail(SB200_E_NOMEM, "cudaMalloc tables", e); }
     char* base = (char*)h->tab.p;
     auto up = [&](size_t off, const void* src, size_t bytes) { return cudaMemcpy(base + off, src, bytes, cudaMemcpyHostToDevice); };
-    e = up(o_sin, H->sin_lut.data(), 131072);
+    e = up(o_rot, rot.data(), 262144);
+    if (e == cudaSuccess) e = up(o_sin, H->sin_lut.data(), 131072);
     if (e == cudaSuccess) e = up(o_cos, H->cos_lut.data(), 131072);
     if (e == cudaSuccess) e = up(o_at, H->atan2_lut.data(), 131072);
     if (e == cudaSuccess) e = up(o_tw64, H->tw64, sizeof H->tw64);
@@ -111,7 +114,7 @@ static int upload_tables(sb200_handle* h) {
     delete H;
     if (e != cudaSuccess) return h->fail(SB200_E_CUDA, "table upload", e);
     DevTables& T = h->T;
-    T.sin_lut = (const int16_t*)(base + o_sin); T.cos_lut = (const int16_t*)(base + o_cos); T.atan2_lut = (const int16_t*)(base + o_at);
+    T.sin_lut = (const int16_t*)(base + o_sin); T.cos_lut = (const int16_t*)(base + o_cos); T.atan2_lut = (const int16_t*)(base + o_at); T.rot = (const uint32_t*)(base + o_rot);
     T.tw64 = (const uint32_t*)(base + o_tw64); T.tw16 = (const uint32_t*)(base + o_tw16); T.sts = (const uint32_t*)(base + o_sts);
     T.deint = (const uint16_t*)(base + o_deint); T.demap = (const uint8_t*)(base + o_demap); T.pilot_neg = (const uint8_t*)(base + o_pil);
     T.lts_pos = (const uint8_t*)(base + o_lts); T.scramble = (const uint8_t*)(base + o_scr); T.crc32 = (const uint32_t*)(base + o_crc);

@@ -21,6 +21,7 @@ struct DevTables {
     const int16_t* sin_lut;      // [65536]
     const int16_t* cos_lut;      // [65536]
     const int16_t* atan2_lut;    // [256*256]
+    const uint32_t* rot;         // [65536] packed (ucos(th), -usin(th)): one load per rotation instead of two
     const uint32_t* tw64;        // [3][16] packed c16
     const uint32_t* tw16;        // [3][4]
     const uint32_t* sts;         // [16][16] packed c16
