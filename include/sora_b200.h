@@ -152,6 +152,12 @@ int sb200_rx11n_taps(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
                      const uint32_t* frame_len, uint32_t nframes, uint32_t max_sym, sb200_frame_result_11n* res,
                      int16_t* siso, int16_t* hinv, int16_t* eq, int16_t* theta, uint8_t* sig, uint8_t* soft, uint64_t soft_stride);
 
+/* RX_BLOCK ingest: `blocks` = nblocks x 128 bytes (16-byte descriptor + 28 COMPLEX16, kernel/core/inc/_rx_manager.h:79-113) as stored
+ * in *.dmp files and the RX DMA ring; iq_out receives 28*nblocks samples (host or device, 16-byte aligned).  Replaces
+ * LoadSoraDumpFile (kernel/brick/inc/brickutil.h:21-59) with a device-side gather; left_shift = 2 applies the legacy 14-bit fix
+ * (RX_COMPLEX16_INVALID_BITS, kernel/core/inc/const.h:73; dot11a/dot11/arx_fd.c:530), 0 leaves samples untouched. */
+int sb200_rxblocks_unpack(sb200_handle* h, const void* blocks, uint64_t nblocks, uint32_t left_shift, int16_t* iq_out, void* cuda_stream);
+
 /* Standalone K=7 Viterbi over `nblocks` independent blocks of `nsoft` soft values (uint8 0..7, one per coded bit after
  * puncturing; block b starts at soft + b*soft_stride).  frame_len_bytes L sets the flush point 8L+16+6 exactly like
  * CF_11aRxVector::frame_length; each block yields L+2 bytes (SERVICE + PSDU, not descrambled) at out + b*out_stride.

@@ -1,0 +1,72 @@
+/* sora_b200_legacy.h — the reference's legacy C baseband interface for 802.11a receive, served by the GPU engine.
+ *
+ * SURVEY.md §8(f) rank 4.  Same entry-point names, argument order, HRESULT values and result fields as
+ *   kernel/inc/bb/bba.h:15-24 (BB11A_* codes), :61-70 (ri_* result fields), :191-262 (BB11ARx* prototypes) and
+ *   kernel/core/inc/_rx_stream.h:22-50 (SORA_RADIO_RX_STREAM, SoraGenRadioRxStreamOffline),
+ * so that a caller written against them (kernel/bb/demod11/demod11a.cpp:53-200 CsFrameDemod, UMXDot11/dot11arx.c) links against
+ * libsora_b200.so after swapping the include.  The context is this library's own struct: only the documented public fields keep
+ * their names; the reference's private working state (`__` fields, FIFOs, Viterbi thread state) has no counterpart because the
+ * decode runs on the device.  The demodulator behind it is the brick receive chain of include/sora_b200.h (the reference's newer
+ * implementation of the same PHY), not a restatement of dot11a/dot11/arx_*.c: verdicts and payloads agree wherever both decode.
+ * BB11ARxViterbiWorker is a no-op that returns FALSE (there is no separate Viterbi thread to pump).
+ */
+#ifndef SORA_B200_LEGACY_H
+#define SORA_B200_LEGACY_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t HRESULT;
+typedef uint32_t ULONG;
+typedef unsigned char BOOLEAN, UCHAR, *PUCHAR;
+typedef volatile uint32_t FLAG, *PFLAG;
+#ifndef FAILED
+#define FAILED(hr) (((HRESULT)(hr)) < 0)
+#define SUCCEEDED(hr) (((HRESULT)(hr)) >= 0)
+#endif
+
+#define BB11A_CHANNEL_CLEAN      ((HRESULT)0x00000200L)
+#define BB11A_OK_POWER_DETECTED  ((HRESULT)0x00000201L)
+#define BB11A_OK_FRAME           ((HRESULT)0x00000202L)
+#define BB11A_E_PD_LAG           ((HRESULT)0x80006000L)
+#define BB11A_E_SYNC_FAIL        ((HRESULT)0x80006001L)
+#define BB11A_E_INVALID_SIG      ((HRESULT)0x80006002L)
+#define BB11A_E_FRAME_SIZE       ((HRESULT)0x80006003L)
+#define BB11A_E_CRC32            ((HRESULT)0x80006004L)
+#define BB11A_E_FORCE_STOP       ((HRESULT)0x80006005L)
+
+#define SORA_RX_BLOCK_SIZE 128u                 /* 16-byte descriptor + 7 x 16 bytes of samples (_rx_manager.h:79-113) */
+
+typedef struct __SORA_RADIO_RX_STREAM {         /* _rx_stream.h:22-30 */
+    PUCHAR __pStartPt; ULONG __nRxBufSize; PUCHAR __pEndPt; PUCHAR __pScanPt; ULONG __VStreamMask;
+} SORA_RADIO_RX_STREAM, *PSORA_RADIO_RX_STREAM;
+void SoraGenRadioRxStreamOffline(PSORA_RADIO_RX_STREAM pRxStream, PUCHAR pInput, ULONG Size);
+
+typedef struct _BB11A_RX_CONTEXT {
+    /* carrier sense configuration (bba.h:43-47) */
+    unsigned int SampleRate; ULONG uiCSCorrThreshold; unsigned int uiCSMaxFetchRxBlock, uiCSMinFetchRxBlock;
+    /* results (bba.h:61-70) */
+    volatile FLAG* ri_pbWorkIndicator;
+    char* ri_pbFrame; unsigned int ri_uiFrameMaxSize;
+    unsigned int ri_uiFrameSize;                /* LENGTH of the PSDU incl. FCS (arx_fd.c:265) */
+    unsigned int ri_uiDataRate;                 /* kbps */
+    unsigned int ri_uiFrameType;
+    /* engine state */
+    void* b200_engine; void* b200_events; unsigned int b200_shift;
+} BB11A_RX_CONTEXT, *PBB11A_RX_CONTEXT;
+
+void    BB11ARxContextInit(PBB11A_RX_CONTEXT pRxContextA, unsigned int SampleRate, ULONG rxThreshold, ULONG rxMaxBlockCount, ULONG rxMinBlockCount, volatile FLAG* WorkIndicator);
+void    BB11APrepareRx(PBB11A_RX_CONTEXT pRxContextA, char* pcFrame, unsigned int unFrameMaxSize);
+BOOLEAN BB11ARxViterbiWorker(void* pContext);
+void    BB11ARxReset(PBB11A_RX_CONTEXT pRxContextA);
+void    BB11ARxContextCleanup(PBB11A_RX_CONTEXT pRxContextA);
+HRESULT BB11ARxCarrierSense(PBB11A_RX_CONTEXT pRxContextA, PSORA_RADIO_RX_STREAM pRxStream);
+HRESULT BB11ARxFrameDemod(PBB11A_RX_CONTEXT pRxContextA, PSORA_RADIO_RX_STREAM pRxStream);
+/* not in the reference: selects the legacy 14-bit sample fix (left shift by 2) for old captures such as kernel/test-data/fsample-6.dmp */
+void    BB11ARxSetSampleShift(PBB11A_RX_CONTEXT pRxContextA, unsigned int left_shift);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -132,6 +132,13 @@ class Engine:
 
     def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         self._check(self._lib.sb200_rx11b_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11b_batch")
+
+    def rxblocks_unpack(self, raw, left_shift=0):
+        """raw: uint8 array of whole 128-byte RX_BLOCKs (a *.dmp file) -> int16 [28*nblocks, 2] via the device gather."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8); nblk = len(raw) // 128
+        out = np.zeros((nblk * 28, 2), np.int16)
+        self._check(self._lib.sb200_rxblocks_unpack(self._h, C.c_void_p(_ptr(raw)), C.c_uint64(nblk), C.c_uint32(left_shift), C.c_void_p(_ptr(out)), C.c_void_p(0)), "sb200_rxblocks_unpack")
+        return out
 
     def rx11n_raw(self, iq0_ptr, iq1_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         self._check(self._lib.sb200_rx11n_batch(self._h, C.c_void_p(iq0_ptr), C.c_void_p(iq1_ptr), C.c_uint64(iq_total), C.c_void_p(off_ptr), C.c_void_p(len_ptr),

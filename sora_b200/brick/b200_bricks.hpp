@@ -12,6 +12,14 @@
 //     how the CPU bricks write them: after a frame event error_code() becomes E_ERROR_FRAME_OK / E_ERROR_CRC32_FAIL /
 //     E_ERROR_PLCP_HEADER_FAIL and the driver loop (fb11a_demod.cpp:29-81) does its Flush()/Reset() as before.
 //
+//   TB200Dot11bRx<T_CTX, T_NEXT>   replaces everything behind the source of the 802.11b graph
+//       (kernel/bb/demod11/fb11bdemod_config.hpp:123-190: TDCRemove, TEnergyDetect, TSymTiming, TBarkerSync, TBB11bDespread,
+//        TSFDSync, TBB11bPlcpParser, TDBPSKDemap/TDQPSKDemap, TCCK5P5Decoder/TCCK11Decoder, TDesc741, TBB11bFrameSink)
+//     iport COMPLEX16 x 28 at 44 Msps, oport uchar x 1; facades CF_Error, CF_11bRxVector, CF_RxFrameBuffer.
+//   TB200Dot11nRx<T_CTX, T_NEXT>   replaces ds2 .. fsink of CreateDemodGraph11n (kernel/bb/demod11/fb11ndemod_config.hpp:167-262)
+//     iport COMPLEX16 x 28 x 2 streams (what TMemSamples2 emits, memsource.hpp:189-244), oport uchar x 1;
+//     facades CF_Error, CF_11aRxVector, CF_HTRxVector, CF_RxFrameBuffer, CF_CFOffset.
+//
 // Batching: the GPU decodes whole capture slots.  The brick buffers incoming 28-sample blocks and submits a slot when
 // `slot_samples` samples have arrived or on Flush(); one graph instance therefore trades latency for throughput.  A
 // throughput-oriented caller uses sb200_rx11a_batch directly with thousands of slots per call.
@@ -88,5 +96,118 @@ private:
         }
         error_code = r.status;                                     // the driver polls this after Process() (fb11a_demod.cpp:35)
         return false;                                              // frame complete: stop pumping (PHY_11a.hpp:694)
+    }
+};
+
+
+DEFINE_LOCAL_CONTEXT(TB200Dot11bRx, CF_Error, CF_11bRxVector, CF_RxFrameBuffer);
+template <TFILTER_ARGS>
+class TB200Dot11bRx : public TFilter<TFILTER_PARAMS> {
+    CTX_VAR_RW(ulong, error_code)
+    CTX_VAR_RW(ushort, frame_length) CTX_VAR_RW(ulong, data_rate_kbps) CTX_VAR_RW(ulong, frame_crc32)
+    CTX_VAR_RO(uchar*, rx_frame_buf) CTX_VAR_RO(uint, rx_frame_buf_size)
+    sb200_handle* h_; std::vector<COMPLEX16> slot_; std::vector<uchar> bytes_; size_t slot_samples_;
+public:
+    DEFINE_IPORT(COMPLEX16, 28);
+    DEFINE_OPORT(uchar, 1);
+    REFERENCE_LOCAL_CONTEXT(TB200Dot11bRx);
+    STD_TFILTER_CONSTRUCTOR(TB200Dot11bRx)
+        BIND_CONTEXT(CF_Error::error_code, error_code)
+        BIND_CONTEXT(CF_11bRxVector::frame_length, frame_length) BIND_CONTEXT(CF_11bRxVector::data_rate_kbps, data_rate_kbps) BIND_CONTEXT(CF_11bRxVector::crc32, frame_crc32)
+        BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
+        , h_(nullptr), slot_samples_(0)
+    {
+        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+        bytes_.resize(4096);
+    }
+    ~TB200Dot11bRx() { sb200_destroy(h_); }
+    void SetSlotSamples(size_t n) { slot_samples_ = n; }
+    STD_TFILTER_RESET() { slot_.clear(); }
+    STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) Submit(); }
+    BOOL_FUNC_PROCESS(ipin) {
+        while (ipin.check_read()) {
+            const COMPLEX16* p = ipin.peek(); slot_.insert(slot_.end(), p, p + 28); ipin.pop();
+            if (slot_samples_ && slot_.size() >= slot_samples_) { if (!Submit()) return false; }
+        }
+        return true;
+    }
+private:
+    bool Submit() {
+        if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        if (slot_.empty()) return true;
+        uint64_t off = 0; uint32_t len = (uint32_t)slot_.size(); sb200_frame_result_11b r;
+        int rc = sb200_rx11b_batch(h_, (const int16_t*)slot_.data(), slot_.size(), &off, &len, 1, bytes_.data(), (uint32_t)bytes_.size(), &r, nullptr);
+        slot_.clear();
+        if (rc != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
+        if (r.status == SB200_FRAME_NONE) return true;
+        frame_length = (ushort)r.length; data_rate_kbps = r.rate_kbps; frame_crc32 = r.crc32;
+        if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) {
+            const uint n = r.length ? r.length - 1 : 0;            // TBB11bFrameSink decides on the third FCS byte (PHY_11b.hpp:728-739)
+            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, bytes_.data(), n);
+            for (uint i = 0; i < n; i++) { *opin().append() = bytes_[i]; this->Next()->Process(opin()); }
+        }
+        error_code = r.status;
+        return false;
+    }
+};
+
+DEFINE_LOCAL_CONTEXT(TB200Dot11nRx, CF_Error, CF_11aRxVector, CF_HTRxVector, CF_RxFrameBuffer, CF_CFOffset);
+template <TFILTER_ARGS>
+class TB200Dot11nRx : public TFilter<TFILTER_PARAMS> {
+    CTX_VAR_RW(ulong, error_code)
+    CTX_VAR_RW(ushort, frame_length) CTX_VAR_RW(ushort, total_symbols) CTX_VAR_RW(ushort, code_rate) CTX_VAR_RW(ulong, frame_crc32)
+    CTX_VAR_RW(ushort, ht_frame_length) CTX_VAR_RW(ulong, ht_frame_mcs)
+    CTX_VAR_RO(uchar*, rx_frame_buf) CTX_VAR_RO(uint, rx_frame_buf_size)
+    CTX_VAR_RW(short, CFO_est)
+    sb200_handle* h_; std::vector<COMPLEX16> slot_[2]; std::vector<uchar> bytes_; size_t slot_samples_;
+public:
+    static const size_t NSTREAM = 2;
+    DEFINE_IPORT(COMPLEX16, 28, NSTREAM);
+    DEFINE_OPORT(uchar, 1);
+    REFERENCE_LOCAL_CONTEXT(TB200Dot11nRx);
+    STD_TFILTER_CONSTRUCTOR(TB200Dot11nRx)
+        BIND_CONTEXT(CF_Error::error_code, error_code)
+        BIND_CONTEXT(CF_11aRxVector::frame_length, frame_length) BIND_CONTEXT(CF_11aRxVector::total_symbols, total_symbols)
+        BIND_CONTEXT(CF_11aRxVector::code_rate, code_rate) BIND_CONTEXT(CF_11aRxVector::crc32, frame_crc32)
+        BIND_CONTEXT(CF_HTRxVector::ht_frame_length, ht_frame_length) BIND_CONTEXT(CF_HTRxVector::ht_frame_mcs, ht_frame_mcs)
+        BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
+        BIND_CONTEXT(CF_CFOffset::CFO_est, CFO_est)
+        , h_(nullptr), slot_samples_(0)
+    {
+        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+        bytes_.resize(2048);
+    }
+    ~TB200Dot11nRx() { sb200_destroy(h_); }
+    void SetSlotSamples(size_t n) { slot_samples_ = n; }
+    STD_TFILTER_RESET() { slot_[0].clear(); slot_[1].clear(); }
+    STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) Submit(); }
+    BOOL_FUNC_PROCESS(ipin) {
+        while (ipin.check_read()) {
+            for (size_t s = 0; s < NSTREAM; s++) { const COMPLEX16* p = ipin.peek(s); slot_[s].insert(slot_[s].end(), p, p + 28); }
+            ipin.pop();
+            if (slot_samples_ && slot_[0].size() >= slot_samples_) { if (!Submit()) return false; }
+        }
+        return true;
+    }
+private:
+    bool Submit() {
+        if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        if (slot_[0].empty()) return true;
+        uint64_t off = 0; uint32_t len = (uint32_t)slot_[0].size(); sb200_frame_result_11n r;
+        int rc = sb200_rx11n_batch(h_, (const int16_t*)slot_[0].data(), (const int16_t*)slot_[1].data(), slot_[0].size(), &off, &len, 1,
+                                   bytes_.data(), (uint32_t)bytes_.size(), &r, nullptr);
+        slot_[0].clear(); slot_[1].clear();
+        if (rc != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
+        if (r.status == SB200_FRAME_NONE) return true;
+        frame_length = (ushort)r.length; total_symbols = (ushort)r.nsym; frame_crc32 = r.crc32; CFO_est = r.cfo_est;
+        ht_frame_mcs = r.mcs; ht_frame_length = (ushort)(r.nsym ? r.length : 0);
+        code_rate = (ushort)(r.mcs == 10 ? CR_34 : CR_12);
+        if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) {
+            const uint n = r.length;
+            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, bytes_.data(), n);
+            for (uint i = 0; i < n; i++) { *opin().append() = bytes_[i]; this->Next()->Process(opin()); }
+        }
+        error_code = r.status;
+        return false;
     }
 };

@@ -4,6 +4,8 @@
 //   CF_11aRxVector               kernel/bb/Brick11/src/ieee80211facade.hpp:213-238
 //   CF_11CCA                     kernel/bb/Brick11/src/ieee80211facade.hpp:21-45
 //   CF_CFOffset                  kernel/bb/Brick11/src/ieee80211facade.hpp:168-175
+//   CF_11bRxVector               kernel/bb/Brick11/src/ieee80211facade.hpp:72-76
+//   CF_HTRxVector                kernel/bb/Brick11/src/ieee80211facade.hpp:269-272
 // plus the E_ERROR_* codes (stdfacade.h:10-12, ieee80211facade.hpp:10-19).
 #pragma once
 #include "brick.hpp"
@@ -53,3 +55,5 @@ public:
     void OnPowerDetected() {}
 };
 class CF_CFOffset { FACADE_FIELD(short, CFO_est) public: void Reset() { CFO_est() = 0; } };
+class CF_11bRxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(ulong, data_rate_kbps) FACADE_FIELD(ulong, crc32) };
+class CF_HTRxVector { FACADE_FIELD(ushort, ht_frame_length) FACADE_FIELD(ulong, ht_frame_mcs) };

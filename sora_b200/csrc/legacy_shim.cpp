@@ -1,0 +1,93 @@
+// Legacy C baseband interface (include/sora_b200_legacy.h) over the C ABI of include/sora_b200.h.  Host code only.
+//
+// The legacy driver loop alternates BB11ARxCarrierSense / BB11ARxFrameDemod over an RX stream of RX_BLOCKs (demod11a.cpp:81-200).
+// Here the blocks between the scan pointer and the end of the stream are unpacked and decoded once on the device in
+// continuous-capture mode (sb200_rxblocks_unpack + sb200_rx11a_stream); the two entry points then walk the resulting event list
+// and move the stream's scan pointer exactly as far as the samples they consumed.
+#include "../../include/sora_b200_legacy.h"
+#include "../../include/sora_b200.h"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+struct Event { sb200_frame_result r; uint32_t end_sample; uint32_t start_sample; std::vector<uint8_t> bytes; };
+struct Events { const unsigned char* base = nullptr; size_t nblocks = 0; std::vector<Event> ev; size_t next = 0; bool pending = false; };
+const uint32_t MAX_EVENTS = 256;
+
+bool decode_from(PBB11A_RX_CONTEXT c, PSORA_RADIO_RX_STREAM s) {
+    Events* E = (Events*)c->b200_events; sb200_handle* h = (sb200_handle*)c->b200_engine;
+    const size_t nblocks = (size_t)(s->__pEndPt - s->__pScanPt) / SORA_RX_BLOCK_SIZE;
+    E->base = s->__pScanPt; E->nblocks = nblocks; E->ev.clear(); E->next = 0; E->pending = false;
+    if (!h || nblocks == 0) return false;
+    std::vector<int16_t> iq(nblocks * 56);
+    if (sb200_rxblocks_unpack(h, s->__pScanPt, nblocks, c->b200_shift, iq.data(), nullptr) != SB200_OK) return false;
+    std::vector<sb200_frame_result> res(MAX_EVENTS); std::vector<uint32_t> sidx(MAX_EVENTS); std::vector<uint8_t> out((size_t)MAX_EVENTS * 2560);
+    uint32_t n = 0;
+    if (sb200_rx11a_stream(h, iq.data(), nblocks * 28, MAX_EVENTS, out.data(), 2560, res.data(), sidx.data(), &n, nullptr) != SB200_OK) return false;
+    uint32_t prev = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        Event e; e.r = res[i]; e.end_sample = sidx[i]; e.start_sample = prev + 2u * res[i].detect_index;
+        e.bytes.assign(out.begin() + (size_t)i * 2560, out.begin() + (size_t)i * 2560 + (res[i].length < 2560 ? res[i].length : 2560));
+        E->ev.push_back(std::move(e)); prev = sidx[i];
+    }
+    return true;
+}
+}
+
+extern "C" void SoraGenRadioRxStreamOffline(PSORA_RADIO_RX_STREAM s, PUCHAR in, ULONG size) {
+    s->__pStartPt = in; s->__nRxBufSize = size / SORA_RX_BLOCK_SIZE * SORA_RX_BLOCK_SIZE; s->__pEndPt = in + s->__nRxBufSize; s->__pScanPt = in; s->__VStreamMask = 1;
+}
+extern "C" void BB11ARxContextInit(PBB11A_RX_CONTEXT c, unsigned int SampleRate, ULONG thr, ULONG maxBlk, ULONG minBlk, volatile FLAG* work) {
+    memset(c, 0, sizeof *c);
+    c->SampleRate = SampleRate; c->uiCSCorrThreshold = thr; c->uiCSMaxFetchRxBlock = maxBlk; c->uiCSMinFetchRxBlock = minBlk; c->ri_pbWorkIndicator = work;
+    const char* d = getenv("SB200_DEVICE"); sb200_handle* h = nullptr;
+    if (sb200_create(d ? atoi(d) : 0, nullptr, &h) == SB200_OK) c->b200_engine = h;      // no CPU fallback: every later call fails without it
+    c->b200_events = new Events();
+}
+extern "C" void BB11APrepareRx(PBB11A_RX_CONTEXT c, char* frame, unsigned int max) { c->ri_pbFrame = frame; c->ri_uiFrameMaxSize = max; }
+extern "C" BOOLEAN BB11ARxViterbiWorker(void*) { return 0; }
+extern "C" void BB11ARxReset(PBB11A_RX_CONTEXT c) { if (c->b200_events) { Events* E = (Events*)c->b200_events; E->base = nullptr; E->ev.clear(); E->next = 0; E->pending = false; } }
+extern "C" void BB11ARxContextCleanup(PBB11A_RX_CONTEXT c) {
+    sb200_destroy((sb200_handle*)c->b200_engine); delete (Events*)c->b200_events; c->b200_engine = nullptr; c->b200_events = nullptr;
+}
+extern "C" void BB11ARxSetSampleShift(PBB11A_RX_CONTEXT c, unsigned int s) { c->b200_shift = s; BB11ARxReset(c); }
+
+extern "C" HRESULT BB11ARxCarrierSense(PBB11A_RX_CONTEXT c, PSORA_RADIO_RX_STREAM s) {
+    if (!c->b200_engine || !c->b200_events) return BB11A_E_FORCE_STOP;
+    if (c->ri_pbWorkIndicator && !*c->ri_pbWorkIndicator) return BB11A_E_FORCE_STOP;
+    Events* E = (Events*)c->b200_events;
+    const bool inside = E->base && s->__pScanPt >= E->base && s->__pScanPt <= E->base + E->nblocks * SORA_RX_BLOCK_SIZE;
+    if (!inside && !decode_from(c, s)) return BB11A_E_FORCE_STOP;
+    const size_t pos_blk = (size_t)(s->__pScanPt - E->base) / SORA_RX_BLOCK_SIZE;
+    const size_t max_blk = c->uiCSMaxFetchRxBlock ? c->uiCSMaxFetchRxBlock : 150;
+    while (E->next < E->ev.size() && E->ev[E->next].end_sample / 28u <= pos_blk) E->next++;       // events the caller skipped over
+    if (E->next < E->ev.size()) {
+        const size_t det_blk = E->ev[E->next].start_sample / 28u;
+        if (det_blk < pos_blk + max_blk) {
+            s->__pScanPt = (PUCHAR)E->base + (det_blk > pos_blk ? det_blk : pos_blk) * SORA_RX_BLOCK_SIZE;
+            E->pending = true;
+            return BB11A_OK_POWER_DETECTED;
+        }
+    }
+    size_t nb = pos_blk + max_blk; if (nb > E->nblocks) nb = E->nblocks;
+    s->__pScanPt = (PUCHAR)E->base + nb * SORA_RX_BLOCK_SIZE;
+    if (s->__pScanPt >= s->__pEndPt) { s->__pScanPt = s->__pStartPt; E->base = nullptr; }      // ring wrap: decode again from the start
+    return BB11A_CHANNEL_CLEAN;
+}
+
+extern "C" HRESULT BB11ARxFrameDemod(PBB11A_RX_CONTEXT c, PSORA_RADIO_RX_STREAM s) {
+    if (!c->b200_engine || !c->b200_events) return BB11A_E_FORCE_STOP;
+    Events* E = (Events*)c->b200_events;
+    if (!E->pending || E->next >= E->ev.size()) return BB11A_E_SYNC_FAIL;
+    const Event& e = E->ev[E->next++]; E->pending = false;
+    size_t end_blk = (e.end_sample + 27u) / 28u; if (end_blk > E->nblocks) end_blk = E->nblocks;
+    s->__pScanPt = (PUCHAR)E->base + end_blk * SORA_RX_BLOCK_SIZE;
+    if (s->__pScanPt >= s->__pEndPt) { s->__pScanPt = s->__pStartPt; E->base = nullptr; }
+    c->ri_uiFrameSize = e.r.length; c->ri_uiDataRate = e.r.rate_kbps;
+    if (e.r.status == SB200_FRAME_PLCP_FAIL) return BB11A_E_INVALID_SIG;
+    if (e.r.status != SB200_FRAME_OK && e.r.status != SB200_FRAME_CRC32_FAIL) return BB11A_E_SYNC_FAIL;
+    if (!c->ri_pbFrame || e.r.length > c->ri_uiFrameMaxSize) return BB11A_E_FRAME_SIZE;
+    memcpy(c->ri_pbFrame, e.bytes.data(), e.bytes.size());
+    return e.r.status == SB200_FRAME_OK ? BB11A_OK_FRAME : BB11A_E_CRC32;
+}

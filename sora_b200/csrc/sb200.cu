@@ -557,6 +557,40 @@ extern "C" int sb200_rx11n_taps(sb200_handle* h, const int16_t* iq0, const int16
     return SB200_OK;
 }
 
+// ---- RX_BLOCK ingest -------------------------------------------------------------------------------
+// A Sora capture (dump file, RX DMA ring) is a sequence of 128-byte RX_BLOCKs: a 16-byte descriptor followed by seven
+// 16-byte sample units = 28 COMPLEX16 (kernel/core/inc/_rx_manager.h:79-113); LoadSoraDumpFile (kernel/brick/inc/brickutil.h:21-59)
+// strips the descriptors on the CPU.  Here it is a device gather: one thread per 16-byte unit, 128-bit loads and stores, with the
+// optional left shift that drops the invalid low bits of legacy 14-bit captures (RX_COMPLEX16_INVALID_BITS, core/inc/const.h:73).
+__global__ void __launch_bounds__(256) k_rxblocks_unpack(const uint4* __restrict__ blocks, uint64_t nunits, uint32_t shift, uint4* __restrict__ out) {
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nunits; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = u / 7u, j = u - 7u * b;
+        uint4 v = __ldg(blocks + b * 8u + 1u + j);
+        if (shift) {
+            auto sh = [&](uint32_t w) { return (((w & 0xFFFFu) << shift) & 0xFFFFu) | ((w >> 16 << shift) << 16); };
+            v.x = sh(v.x); v.y = sh(v.y); v.z = sh(v.z); v.w = sh(v.w);
+        }
+        out[u] = v;
+    }
+}
+extern "C" int sb200_rxblocks_unpack(sb200_handle* h, const void* blocks, uint64_t nblocks, uint32_t left_shift, int16_t* iq_out, void* cuda_stream) {
+    if (!h || !blocks || !iq_out || left_shift > 15) return h ? h->fail(SB200_E_INVALID, "bad argument") : SB200_E_INVALID;
+    if (nblocks == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    const bool in_dev = is_device_ptr(blocks), out_dev = is_device_ptr(iq_out);
+    const uint4* d_in = (const uint4*)blocks; uint4* d_out = (uint4*)iq_out;
+    if (!in_dev) { CK(h->stage[0].need(nblocks * 128ull)); CK(cudaMemcpyAsync(h->stage[0].p, blocks, nblocks * 128ull, cudaMemcpyHostToDevice, st)); d_in = (const uint4*)h->stage[0].p; }
+    if (!out_dev) { CK(h->stage[1].need(nblocks * 112ull)); d_out = (uint4*)h->stage[1].p; }
+    const uint64_t nunits = nblocks * 7ull;
+    const unsigned grid = (unsigned)((nunits + 255) / 256 < 148ull * 16 ? (nunits + 255) / 256 : 148ull * 16);
+    k_rxblocks_unpack<<<grid, 256, 0, st>>>(d_in, nunits, left_shift, d_out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (!out_dev) { CK(cudaMemcpyAsync(iq_out, d_out, nblocks * 112ull, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    return SB200_OK;
+}
+
 extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t value) {
     if (!h || !name) return SB200_E_INVALID;
     if (!strcmp(name, "chunk_frames")) { h->chunk_frames = (uint32_t)value; return SB200_OK; }

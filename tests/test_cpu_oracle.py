@@ -128,6 +128,11 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(api.EXPORTS) == declared
+    leg = open(os.path.join(ROOT, "include", "sora_b200_legacy.h")).read()
+    legacy = sorted(set(re.findall(r"\b(BB11A[A-Z][a-z][A-Za-z0-9]+|SoraGenRadioRxStreamOffline)\s*\(", leg)))
+    assert len(legacy) >= 8
+    for name in legacy:
+        assert hasattr(lib, name), name
 
 def test_product_never_touches_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sora_b200")):

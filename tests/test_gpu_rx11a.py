@@ -194,3 +194,52 @@ def test_stream_mode_matches_rxthread(eng):
     noise = np.random.default_rng(1).normal(0, 4000, (20000, 2)).astype(np.int16)      # spurious detections, no frames
     ores, _ = oracle_py.rx11a_run(noise, max_frames=32); res, _, sidx = eng.rx11a_stream(noise, max_frames=32)
     assert len(res) == len(ores) and (res["status"] == ores["status"]).all() and (sidx == ores["sample_index"]).all()
+
+def test_rxblock_ingest_on_device(eng):
+    """*.dmp bytes -> device gather (+ legacy 14-bit shift) -> continuous-capture decode: the golden frame comes out."""
+    raw = np.fromfile(os.path.join(GOLD, "fsample-6.dmp"), dtype=np.uint8)
+    iq = eng.rxblocks_unpack(raw, left_shift=2)
+    ref = (load_dump(os.path.join(GOLD, "fsample-6.dmp")).astype(np.int32) << 2).astype(np.int16)
+    assert iq.shape == ref.shape and (iq == ref).all()
+    assert (eng.rxblocks_unpack(raw, 0) == load_dump(os.path.join(GOLD, "fsample-6.dmp"))).all()
+    res, out, sidx = eng.rx11a_stream(iq, max_frames=4)
+    assert len(res) == 1 and res["status"][0] == 1 and res["rate_kbps"][0] == 6000 and res["length"][0] == 1392 and res["crc32"][0] == 0x80EF9B11
+    assert (out[0, :1392] == np.fromfile(os.path.join(GOLD, "fsample-6.psdu.bin"), dtype=np.uint8)).all()
+
+def test_legacy_c_api_shim():
+    """CsFrameDemod's loop (kernel/bb/demod11/demod11a.cpp:81-200) written against include/sora_b200_legacy.h via ctypes."""
+    import ctypes as C
+    lib = api.load_library()
+    class Stream(C.Structure): _fields_ = [("start", C.c_void_p), ("size", C.c_uint32), ("end", C.c_void_p), ("scan", C.c_void_p), ("mask", C.c_uint32)]
+    class Ctx(C.Structure):
+        _fields_ = [("SampleRate", C.c_uint), ("thr", C.c_uint32), ("maxblk", C.c_uint), ("minblk", C.c_uint), ("work", C.c_void_p), ("frame", C.c_void_p),
+                    ("framemax", C.c_uint), ("framesize", C.c_uint), ("datarate", C.c_uint), ("frametype", C.c_uint), ("engine", C.c_void_p), ("events", C.c_void_p), ("shift", C.c_uint)]
+    for f in ("BB11ARxCarrierSense", "BB11ARxFrameDemod"): getattr(lib, f).restype = C.c_int32
+    # a capture with three frames (one of them damaged), stored as RX_BLOCKs
+    parts = []
+    for i, (rate, L) in enumerate(((24000, 300), (54000, 1000), (12000, 80))):
+        iq, _ = synth.make_frames(1, psdu_len=L, rate_kbps=rate, seed0=0x99000000 + i, snr_db=30, lead=300, trail=300, gain=0.5)
+        parts.append(iq[0])
+    parts[1] = parts[1].copy(); parts[1][3000:3200] = 0
+    cap = np.concatenate(parts); cap = cap[: len(cap) // 28 * 28]
+    blocks = np.zeros((len(cap) // 28, 128), np.uint8); blocks[:, 0] = 1; blocks[:, 16:] = cap.reshape(-1, 28 * 2).view(np.uint8)
+    ores, oout = oracle_py.rx11a_run(cap, max_frames=8, out_stride=2560)
+    work = C.c_uint32(1); frame = np.zeros(4096, np.uint8)
+    st = Stream(); ctx = Ctx()
+    lib.SoraGenRadioRxStreamOffline(C.byref(st), C.c_void_p(blocks.ctypes.data), C.c_uint32(blocks.size))
+    lib.BB11ARxContextInit(C.byref(ctx), 40, 250000, 150, 112, C.byref(work))
+    got = []
+    for _ in range(10000):
+        hr = lib.BB11ARxCarrierSense(C.byref(ctx), C.byref(st))
+        if hr == 0x201:                                   # BB11A_OK_POWER_DETECTED
+            lib.BB11APrepareRx(C.byref(ctx), C.c_void_p(frame.ctypes.data), 4096)
+            hr = lib.BB11ARxFrameDemod(C.byref(ctx), C.byref(st)) & 0xFFFFFFFF
+            got.append((hr, ctx.framesize, ctx.datarate, frame[:ctx.framesize].copy()))
+        if st.scan == st.start and got: break             # wrapped: the offline loop ends here
+    lib.BB11ARxContextCleanup(C.byref(ctx))
+    assert len(got) == len(ores) == 3
+    codes = {1: 0x202, oracle_py.E_CRC32_FAIL: 0x80006004, oracle_py.E_PLCP_FAIL: 0x80006002}
+    for (hr, n, rate, by), o, ob in zip(got, ores, oout):
+        assert hr == codes[int(o["status"])] and n == o["length"] and rate == o["rate_kbps"]
+        if o["status"] in (1, oracle_py.E_CRC32_FAIL): assert (by == ob[:n]).all()
+    assert got[0][0] == 0x202 and got[1][0] == 0x80006004 and got[2][0] == 0x202
