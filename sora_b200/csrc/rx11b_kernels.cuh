@@ -27,6 +27,7 @@ struct S16 { short re, im; };
 __device__ __forceinline__ S16 s_sub(S16 a, S16 b) { S16 r; r.re = (short)(a.re - b.re); r.im = (short)(a.im - b.im); return r; }
 __device__ __forceinline__ S16 s_add(S16 a, S16 b) { S16 r; r.re = (short)(a.re + b.re); r.im = (short)(a.im + b.im); return r; }
 __device__ __forceinline__ S16 s_sra(S16 a, int n) { S16 r; r.re = (short)(a.re >> n); r.im = (short)(a.im >> n); return r; }
+__device__ __forceinline__ S16 s_w(uint32_t w) { S16 r; r.re = (short)(w & 0xFFFF); r.im = (short)(w >> 16); return r; }
 __device__ __forceinline__ S16 s_ld(const uint32_t* p) { uint32_t w = __ldg(p); S16 r; r.re = (short)(w & 0xFFFF); r.im = (short)(w >> 16); return r; }
 __device__ __forceinline__ int imul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 
@@ -90,6 +91,11 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const uint32_t* x = iq + off[f];
+    const bool al16 = (((uintptr_t)x) & 15u) == 0;     // block starts are multiples of 4 samples from the slot start
+    auto ld4 = [&](const uint32_t* p, uint32_t (&w)[4]) {
+        if (al16) { const uint4 v = __ldg((const uint4*)p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+        else { w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2); w[3] = __ldg(p + 3); }
+    };
     const uint32_t nblk = len[f] / 28u;
     uint8_t* op = out + (size_t)f * out_stride;
     const uint32_t out_cap = (uint32_t)(out_stride < 0xFFFFFFFFull ? out_stride : 0xFFFFFFFFull);
@@ -272,7 +278,9 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
                 if (s.error_code != E_CS_TIMEOUT) {     // TEnergyDetect stops consuming after the timeout (`ipin.clear(); return 0`)
                     S16 xv[4]; uint32_t pw = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { xv[k] = s_sub(s_ld(x + p0 + k), s.DC); pw += (uint32_t)((xv[k].re * xv[k].re + xv[k].im * xv[k].im) >> 5); }
+                    uint32_t w4[4]; ld4(x + p0, w4);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { xv[k] = s_sub(s_w(w4[k]), s.DC); pw += (uint32_t)((xv[k].re * xv[k].re + xv[k].im * xv[k].im) >> 5); }
                     s.avg_energy = s.avg_energy - s.win[s.win_idx] + pw; s.win[s.win_idx] = pw; s.win_idx = (s.win_idx + 1) & 7;
                     s.ed_count++;
                     if (s.ed_count >= 32) {
@@ -291,16 +299,26 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
             } else {
                 s.st_n += 4;
                 if (s.st_n == 28) {                     // TSymTiming on the 28 samples x[st_base .. st_base+28) minus DC
+                    uint32_t wv[7][4];                  // the whole 28-sample block: seven 128-bit loads when the slot is 16-byte aligned
+#pragma unroll
+                    for (int j = 0; j < 7; j++) ld4(x + st_base + 4u * j, wv[j]);
                     int idx = s.m_index;
-                    while (idx < 28) {
-                        S16 o;
-                        if (idx < 0) { o = s_sub(s_ld(x + st_base), s.DC); s.m_index += 4; } else o = s_sub(s_ld(x + st_base + idx), s.DC);
-                        idx += 4;
+                    if (idx < 0) {                      // symtiming.hpp: a negative phase re-reads the first sample of the block
+                        const S16 o = s_sub(s_w(wv[0][0]), s.DC); s.m_index += 4; idx += 4;
                         if (s.error_code == E_SUCCESS) barker_sync(o);
+                    }
+                    {   // the picked samples are idx, idx+4, ...: always the same component of consecutive vectors
+                        const int c = idx & 3, j0 = idx >> 2;
+                        uint32_t pk[7];
+#pragma unroll
+                        for (int j = 0; j < 7; j++) pk[j] = c == 0 ? wv[j][0] : c == 1 ? wv[j][1] : c == 2 ? wv[j][2] : wv[j][3];
+#pragma unroll 1
+                        for (int j = j0; j < 7; j++) { const S16 o = s_sub(s_w(pk[j]), s.DC); if (s.error_code == E_SUCCESS) barker_sync(o); }
                     }
                     if (s.m_index >= 4) s.m_index = 0;
                     int sum[4] = {0, 0, 0, 0};
-                    for (int i = 0; i < 28; i++) { S16 vv = s_sra(s_sub(s_ld(x + st_base + i), s.DC), 3); sum[i & 3] += vv.re * vv.re + vv.im * vv.im; }
+#pragma unroll
+                    for (int i = 0; i < 28; i++) { S16 vv = s_sra(s_sub(s_w(wv[i >> 2][i & 3]), s.DC), 3); sum[i & 3] += vv.re * vv.re + vv.im * vv.im; }
                     const int mi = s.m_index, early = mi == 0 ? 3 : mi - 1, late = mi == 3 ? 0 : mi + 1;
                     const int se = sum[early], sl = sum[late], sm = sum[mi];
                     if (se < sl) { if (sm < se) { s.m_index++; s.m_frag = 0; } else if (sm < sl) s.m_frag++; }
