@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--unique", type=int, default=2048, help="distinct synthetic frames generated on the host, tiled to --frames in HBM")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chunk", type=int, default=8192, help="slots per pipeline chunk inside the library (0 = no chunking)")
+    ap.add_argument("--chunk-device", type=int, default=0, help="slots per pipeline chunk for device-resident IQ (0 = one pass; >0 overlaps the front end of chunk k+1 with the Viterbi of chunk k)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -140,6 +141,7 @@ def main():
     iq_u, ps_u, U = make_input(F, args.unique)
     eng = api.Engine(local)
     eng.set_option("chunk_frames", args.chunk)
+    eng.set_option("chunk_frames_device", args.chunk_device)
     stream = torch.cuda.current_stream()
     # ---- HBM-resident input: U unique slots tiled to F (distinct addresses: 2.6 GB at F=65536 >> 126 MB L2) ----
     iq_unique_dev = torch.from_numpy(iq_u.reshape(U, -1)).to(dev)
@@ -174,12 +176,12 @@ def main():
     launches = eng.launches - l0
     # per-kernel times of the dominant kernel, measured live with CUDA events on the launch stream (extra pass, same inputs)
     nk = max(3, min(args.steps, 5))
-    eng.set_option("chunk_frames", 0)                    # un-pipelined pass: kernels back to back on one stream
+    eng.set_option("chunk_frames", 0); eng.set_option("chunk_frames_device", 0)   # un-pipelined pass: kernels back to back on one stream
     step_dev()
     for _ in range(nk):
         step_dev(); ktimes += np.array(eng.last_kernel_times())
     ktimes /= nk
-    eng.set_option("chunk_frames", args.chunk)
+    eng.set_option("chunk_frames", args.chunk); eng.set_option("chunk_frames_device", args.chunk_device)
     clk = clocks.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
