@@ -1,6 +1,6 @@
 """CPU suite (pytest -m "not gpu"): the oracle against the reference's golden fixtures and closed-form tables, the host
 logic, the ABI surface.  No CUDA compute is called here."""
-import os, re, sys, subprocess, ctypes
+import zlib, os, re, sys, subprocess, ctypes
 import numpy as np, pytest
 import oracle_py
 from sora_b200 import synth
@@ -26,6 +26,18 @@ def test_fsample6_golden_frame():
     assert (psdu == gold).all()
     if os.path.exists(os.path.join(REF, "kernel/test-data/fsample-6.dmp")):
         assert open(os.path.join(REF, "kernel/test-data/fsample-6.dmp"), "rb").read() == open(os.path.join(GOLD, "fsample-6.dmp"), "rb").read()
+
+def _ofdm_bin():
+    raw = np.fromfile(os.path.join(GOLD, "ofdm.bin"), dtype=np.int8).reshape(-1, 2)
+    iq = raw.astype(np.int16) << 8                       # ConvertModFile2DumpFile_8b (demod11/modulate11a.cpp:178-179)
+    return np.concatenate([np.zeros((400, 2), np.int16), iq, np.zeros((400, 2), np.int16)])
+
+def test_ofdm_bin_golden_frame():
+    """The reference's own modulator output (usr/HwVeri/data/ofdm.bin): 24 Mbps, LENGTH 204, 200 x 0x31 + FCS."""
+    res, out = oracle_py.rx11a_run(_ofdm_bin())
+    assert len(res) == 1 and res[0]["status"] == 1 and res[0]["rate_kbps"] == 24000 and res[0]["length"] == 204
+    assert (out[0, :200] == 0x31).all() and bytes(out[0, 200:204]) == bytes.fromhex("388d4983")
+    assert zlib.crc32(bytes(out[0, :200])) == int.from_bytes(bytes(out[0, 200:204]), "little")
 
 def test_dump_roundtrip(tmp_path):
     iq = _fs6()[:28 * 40]

@@ -243,3 +243,11 @@ def test_legacy_c_api_shim():
         assert hr == codes[int(o["status"])] and n == o["length"] and rate == o["rate_kbps"]
         if o["status"] in (1, oracle_py.E_CRC32_FAIL): assert (by == ob[:n]).all()
     assert got[0][0] == 0x202 and got[1][0] == 0x80006004 and got[2][0] == 0x202
+
+def test_ofdm_bin_golden(eng):
+    """The reference's own 24 Mbps modulator output decodes to 200 x 0x31 + FCS on the GPU as well."""
+    raw = np.fromfile(os.path.join(GOLD, "ofdm.bin"), dtype=np.int8).reshape(-1, 2)
+    iq = np.concatenate([np.zeros((400, 2), np.int16), raw.astype(np.int16) << 8, np.zeros((400, 2), np.int16)])
+    res, out = _compare(eng, iq, [0], [len(iq)])
+    assert res["status"][0] == 1 and res["rate_kbps"][0] == 24000 and res["length"][0] == 204
+    assert (out[0, :200] == 0x31).all() and bytes(out[0, 200:204]) == bytes.fromhex("388d4983")
