@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see ops.h).  C entry points for tests/ (ctypes) and bench.py's cpu_baseline.
 #include "rx11b.h"
 #include "rx11n.h"
+#include "tx11a.h"
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -177,6 +178,13 @@ void sbo_tables11n(int16_t* sincos, int16_t* atan_lut, uint8_t* demap, uint8_t* 
     memcpy(sincos, T.sincos, sizeof T.sincos); memcpy(atan_lut, T.atan_lut, sizeof T.atan_lut); memcpy(demap, T.demap, 256); memcpy(crc8, T.crc8, 256);
     memcpy(deint, T.deint, sizeof T.deint); memcpy(lltf_sign, T.lltf_sign, 64); memcpy(htltf_sign, T.htltf_sign, 64);
 }
+
+// ---- 802.11a transmit ---------------------------------------------------------------------------------------------------
+uint64_t sbo_tx11a_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_kbps, uint8_t seed, int8_t* out, uint64_t cap_samples, uint32_t tail_zeros) {
+    return tx11a_modulate(payload, len, rate_kbps, seed, out, (size_t)cap_samples, tail_zeros);
+}
+uint32_t sbo_tx11a_nsym(uint32_t len, uint32_t rate_kbps) { return tx11a_nsym(len, rate_kbps); }
+void sbo_ifft128(const int16_t* in, int16_t* out) { alignas(16) c16 t[128]; memcpy(t, in, 512); alignas(16) c16 o[128]; ifft128((v128*)t, (v128*)o); memcpy(out, o, 512); }
 
 uint32_t sbo_crc32(const uint8_t* p, uint64_t n) { uint32_t c = 0xFFFFFFFFu; for (uint64_t i = 0; i < n; i++) c = (c >> 8) ^ tables().crc32_lut[p[i] ^ (c & 0xFF)]; return ~c; }
 

@@ -38,6 +38,9 @@ Tables::Tables() {
             tw16[m - 1][j].re = (int16_t)trunc(32767.0 * cos(2 * M_PI * j * m / 16));
             tw16[m - 1][j].im = (int16_t)trunc(-32767.0 * sin(2 * M_PI * j * m / 16));
         }
+        for (int j = 0; j < 32; j++) { tw128[m - 1][j].re = (int16_t)trunc(32767.0 * cos(2 * M_PI * j * m / 128)); tw128[m - 1][j].im = (int16_t)trunc(-32767.0 * sin(2 * M_PI * j * m / 128)); }
+        for (int j = 0; j < 8; j++) { tw32[m - 1][j].re = (int16_t)trunc(32767.0 * cos(2 * M_PI * j * m / 32)); tw32[m - 1][j].im = (int16_t)trunc(-32767.0 * sin(2 * M_PI * j * m / 32));
+        }
     }
     // Viterbi branch metrics (viterbilut.h:51-185): new state n = 16*(g>>1)+lane,
     // predecessor p = (n>>1) + 32*(g&1), expected coded bits from g0=133o, g1=171o.
@@ -63,6 +66,7 @@ Tables::Tables() {
         uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
         crc32_lut[i] = c;
     }
+    tw8[0] = c16{32767, 0}; tw8[1] = c16{23169, -23169}; tw8[2] = c16{32767, 0}; tw8[3] = c16{-23169, -23169};   // trunc(32767 e^{-j pi k/4}), k = 0,1,0,3
     // STS correlation patterns: IFFT<64> of the frequency-domain STS, 16 cyclic shifts
     // (brick/inc/sequence.h:5-33, cca.hpp:266-276).  tw tables above must be ready first.
 }
@@ -141,6 +145,37 @@ static void xform64(v128* p, v128* out) {
         int r = ((i & 1) << 5) | ((i & 2) << 3) | ((i & 4) << 1) | ((i & 8) >> 1) | ((i & 16) >> 3) | ((i & 32) >> 5);
         dst[i] = src[r];                                   // fft_lut_bitreversal.h:76 FFT64LUTMap
     }
+}
+// IFFTSSEEx<8> (ifft_r4dif.h:90-139): two vectors = eight points, input shift 3, one twiddle vector [1, W8, 1, W8^3]
+static inline void ifft8(v128* p) {
+    const Tables& T = tables();
+    const v128 HI64 = _mm_set_epi32(-1, -1, 0, 0), TOP16 = _mm_set_epi32((int)0xFFFF0000, 0, 0, 0), ODD32 = _mm_set_epi32(-1, 0, -1, 0);
+    const v128 HI_IM = _mm_set_epi32((int)0xFFFF0000, (int)0xFFFF0000, 0, 0);
+    v128 a = _mm_srai_epi16(p[0], 3), b = _mm_srai_epi16(p[1], 3);
+    v128 d = _mm_subs_epi16(a, b); a = _mm_adds_epi16(a, b);
+    d = _mm_xor_si128(d, HI_IM); d = _mm_shufflehi_epi16(d, 0xb1);           // upper two elements times j (approximate negation)
+    v128 e = _mm_shuffle_epi32(d, 0x4e);
+    d = _mm_adds_epi16(_mm_xor_si128(d, HI64), e);
+    v128 lo = cmul_conj_shift(d, ld(T.tw8), 15);
+    v128 f = _mm_shuffle_epi32(lo, 0xb1);
+    lo = _mm_adds_epi16(_mm_xor_si128(lo, ODD32), f);
+    e = _mm_shuffle_epi32(a, 0x4e);
+    a = _mm_adds_epi16(_mm_xor_si128(a, HI64), e);
+    a = _mm_xor_si128(a, TOP16); a = _mm_shufflehi_epi16(a, 0xb4);
+    f = _mm_shuffle_epi32(a, 0xb1);
+    a = _mm_adds_epi16(_mm_xor_si128(a, ODD32), f);
+    p[0] = a; p[1] = lo;
+}
+void ifft128(v128* p, v128* out) {
+    const Tables& T = tables();
+    r4_stage<true>(p, 8, T.tw128[0], T.tw128[1], T.tw128[2]);
+    for (int s = 0; s < 4; s++) {
+        v128* q = p + 8 * s;
+        r4_stage<true>(q, 2, T.tw32[0], T.tw32[1], T.tw32[2]);
+        for (int k = 0; k < 4; k++) ifft8(q + 2 * k);
+    }
+    const uint32_t* src = (const uint32_t*)p; uint32_t* dst = (uint32_t*)out;
+    for (int i = 0; i < 128; i++) { int r = 0; for (int b = 0; b < 7; b++) r |= ((i >> b) & 1) << (6 - b); dst[i] = src[r]; }   // FFT128LUTMap
 }
 void fft64(v128* inout, v128* out) { xform64<false>(inout, out); }
 void ifft64(v128* inout, v128* out) { xform64<true>(inout, out); }

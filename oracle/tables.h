@@ -17,6 +17,7 @@ struct Tables {
     int16_t atan2_lut[256 * 256];
     alignas(16) c16 tw64[3][16];        // [M-1][j]
     alignas(16) c16 tw16[3][4];
+    alignas(16) c16 tw128[3][32], tw32[3][8], tw8[4];   // transmit side: IFFT<128> (fft_lut_twiddle.h wFFTLUT128_*, wFFTLUT32_*, wFFTLUT8)
     alignas(16) uint8_t vit_ma[64][16]; // [soft*8 + g][lane]
     alignas(16) uint8_t vit_mb[64][16];
     uint16_t deint48[48], deint96[96], deint192[192], deint288[288];
@@ -34,5 +35,6 @@ int16_t uatan2(int y, int x);           // kernel/core/inc/intalg.h:96-108
 
 void fft64(v128* inout /*16 vectors, destroyed*/, v128* out);   // fft_r4dif.h:134-141 FFT<64>
 void ifft64(v128* inout, v128* out);                             // ifft_r4dif.h IFFT<64>
+void ifft128(v128* inout /*32 vectors, destroyed*/, v128* out);  // ifft_r4dif.h:12-160 IFFT<128> = IFFTSSE<128>, 4 x (IFFTSSE<32>, 4 x IFFTSSEEx<8>), 7-bit reversal
 
 } // namespace sbo

@@ -137,3 +137,17 @@ def tables11n():
     di = np.zeros((2, 2, 104), np.uint8); ls = np.zeros(64, np.uint8); hs = np.zeros(64, np.uint8)
     lib().sbo_tables11n(_p(sc), _p(at), _p(dm), _p(c8), _p(di), _p(ls), _p(hs))
     return dict(sincos=sc, atan=at, demap=dm, crc8=c8, deint=di, lltf_sign=ls, htltf_sign=hs)
+
+
+# ---- 802.11a transmit (brick modulator restatement) ---------------------------------------------------------------------
+def tx11a_modulate(payload, rate_kbps, seed=0xFF, tail_zeros=32):
+    """payload: MPDU bytes without FCS.  Returns int8 [n, 2] complex samples at 40 Msps (what `demod11 -m` writes)."""
+    payload = np.ascontiguousarray(payload, dtype=np.uint8); L = lib(); L.sbo_tx11a_modulate.restype = C.c_uint64
+    nsym = L.sbo_tx11a_nsym(C.c_uint32(len(payload)), C.c_uint32(rate_kbps)); cap = 640 + 160 * (1 + nsym) + tail_zeros
+    out = np.zeros((cap, 2), np.int8)
+    n = L.sbo_tx11a_modulate(_p(payload), C.c_uint32(len(payload)), C.c_uint32(rate_kbps), C.c_uint8(seed), _p(out), C.c_uint64(cap), C.c_uint32(tail_zeros))
+    assert n == cap, (n, cap)
+    return out
+
+def ifft128(x):
+    x = np.ascontiguousarray(x, dtype=np.int16); o = np.zeros((128, 2), np.int16); lib().sbo_ifft128(_p(x), _p(o)); return o
