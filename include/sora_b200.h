@@ -158,6 +158,18 @@ int sb200_rx11n_taps(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
  * (RX_COMPLEX16_INVALID_BITS, kernel/core/inc/const.h:73; dot11a/dot11/arx_fd.c:530), 0 leaves samples untouched. */
 int sb200_rxblocks_unpack(sb200_handle* h, const void* blocks, uint64_t nblocks, uint32_t left_shift, int16_t* iq_out, void* cuda_stream);
 
+/* 802.11a transmit: the brick modulator graphs CreateModGraph11a_40M + CreatePreamble11a_40M (kernel/bb/demod11/fb11amod_config.hpp:75-118,
+ * 150-158) driven like Test11A_FB_Mod (kernel/bb/demod11/fb11a_mod.cpp:27-107), one warp per OFDM symbol.  Frame i = payload[pay_off[i] ..
+ * +pay_len[i]) is the MPDU WITHOUT FCS (the modulator appends CRC-32, as CF_11aTxVector::crc32 does); seeds[i] = CF_ScramblerSeed::sc_seed
+ * (NULL: 0xFF as fb11amod_config.hpp:50).  Slot i of `out` (out_stride_samples complex samples) receives lead_samples zeros, the 640-sample
+ * preamble, 160 samples per symbol (SIGNAL + the reference's symbol count, TBB11aSrc::GetPadingByte) and zeros to the end of the slot;
+ * nsamples[i] = lead + 640 + 160 * symbols.  sample_bits 8: COMPLEX8 as `demod11 -m` writes; 16: COMPLEX16 = COMPLEX8 << 8 as
+ * ConvertModFile2DumpFile_8b (demod11/modulate11a.cpp:178-179) feeds the receiver — such a slot goes straight into sb200_rx11a_batch.
+ * All pointers host or device. */
+int sb200_tx11a_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_total, const uint64_t* pay_off, const uint32_t* pay_len,
+                      const uint8_t* seeds, uint32_t nframes, uint32_t rate_kbps, uint32_t lead_samples, uint32_t sample_bits,
+                      void* out, uint64_t out_stride_samples, uint32_t* nsamples, void* cuda_stream);
+
 /* Standalone K=7 Viterbi over `nblocks` independent blocks of `nsoft` soft values (uint8 0..7, one per coded bit after
  * puncturing; block b starts at soft + b*soft_stride).  frame_len_bytes L sets the flush point 8L+16+6 exactly like
  * CF_11aRxVector::frame_length; each block yields L+2 bytes (SERVICE + PSDU, not descrambled) at out + b*out_stride.

@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -132,6 +132,24 @@ class Engine:
 
     def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         self._check(self._lib.sb200_rx11b_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11b_batch")
+
+    def tx11a_raw(self, pay_ptr, pay_total, off_ptr, len_ptr, seed_ptr, nframes, rate_kbps, lead, bits, out_ptr, out_stride, ns_ptr, stream=0):
+        self._check(self._lib.sb200_tx11a_batch(self._h, C.c_void_p(pay_ptr), C.c_uint64(pay_total), C.c_void_p(off_ptr), C.c_void_p(len_ptr), C.c_void_p(seed_ptr),
+                                                C.c_uint32(nframes), C.c_uint32(rate_kbps), C.c_uint32(lead), C.c_uint32(bits), C.c_void_p(out_ptr), C.c_uint64(out_stride),
+                                                C.c_void_p(ns_ptr), C.c_void_p(stream)), "sb200_tx11a_batch")
+
+    def tx11a_batch(self, payloads, rate_kbps, seeds=None, lead=0, sample_bits=8, out_stride=None):
+        """payloads: list of uint8 arrays (MPDUs without FCS) -> (samples [F, out_stride, 2] int8 or int16, nsamples [F])."""
+        lens = np.array([len(p) for p in payloads], np.uint32); offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(p, np.uint8) for p in payloads]) if lens.sum() else np.zeros(1, np.uint8))
+        from math import ceil
+        if out_stride is None:
+            nd = {6000: 24, 9000: 36, 12000: 48, 18000: 72, 24000: 96, 36000: 144, 48000: 192, 54000: 216}[rate_kbps]
+            out_stride = lead + 640 + 160 * (2 + ceil((int(lens.max()) + 7) * 8 / nd) + 1) + 32
+        out = np.zeros((len(lens), out_stride, 2), np.int8 if sample_bits == 8 else np.int16); ns = np.zeros(len(lens), np.uint32)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint8)
+        self.tx11a_raw(_ptr(flat), max(int(lens.sum()), 1), _ptr(offs), _ptr(lens), 0 if sd is None else _ptr(sd), len(lens), rate_kbps, lead, sample_bits, _ptr(out), out_stride, _ptr(ns))
+        return out, ns
 
     def rxblocks_unpack(self, raw, left_shift=0):
         """raw: uint8 array of whole 128-byte RX_BLOCKs (a *.dmp file) -> int16 [28*nblocks, 2] via the device gather."""

@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
             if (s.cca_state == 0) {
                 if (s.error_code != E_CS_TIMEOUT) {     // TEnergyDetect stops consuming after the timeout (`ipin.clear(); return 0`)
                     S16 xv[4]; uint32_t pw = 0;
-#pragma unroll
                     uint32_t w4[4]; ld4(x + p0, w4);
 #pragma unroll
                     for (int k = 0; k < 4; k++) { xv[k] = s_sub(s_w(w4[k]), s.DC); pw += (uint32_t)((xv[k].re * xv[k].re + xv[k].im * xv[k].im) >> 5); }

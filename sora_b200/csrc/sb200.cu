@@ -4,6 +4,7 @@
 #include "viterbi_k7_quad.cuh"
 #include "rx11b_kernels.cuh"
 #include "rx11n_kernels.cuh"
+#include "tx11a_kernels.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -66,6 +67,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
+    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns;   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
@@ -150,7 +152,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -588,6 +590,96 @@ extern "C" int sb200_rxblocks_unpack(sb200_handle* h, const void* blocks, uint64
     h->launches += 1;
     CK(cudaGetLastError());
     if (!out_dev) { CK(cudaMemcpyAsync(iq_out, d_out, nblocks * 112ull, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    return SB200_OK;
+}
+
+// ---- 802.11a transmit -------------------------------------------------------------------------------
+static int upload_tables_tx(sb200_handle* h) {
+    if (h->tabtx.p) return SB200_OK;
+    uint32_t tw128[3][32], tw32[3][8]; uint8_t seq[127], phase[128];
+    for (int m = 1; m <= 3; m++) {
+        for (int j = 0; j < 32; j++) tw128[m - 1][j] = pack(mk((int)trunc(32767.0 * cos(2 * M_PI * j * m / 128)), (int)trunc(-32767.0 * sin(2 * M_PI * j * m / 128))));
+        for (int j = 0; j < 8; j++) tw32[m - 1][j] = pack(mk((int)trunc(32767.0 * cos(2 * M_PI * j * m / 32)), (int)trunc(-32767.0 * sin(2 * M_PI * j * m / 32))));
+    }
+    {   // scrambler x^7 + x^4 + 1 as a 127-periodic sequence: c[t] = c[t-7] ^ c[t-4] from the all-ones state; phase[s] = t such that
+        // the seven outputs before t equal state s (bit 0 = oldest), which is how T11aSc's byte register reads (scramble.hpp:186-203)
+        int hist[7] = {1, 1, 1, 1, 1, 1, 1}; uint8_t c[127 + 7];
+        for (int t = 0; t < 127; t++) { int o = hist[0] ^ hist[3]; c[t] = (uint8_t)o; for (int q = 0; q < 6; q++) hist[q] = hist[q + 1]; hist[6] = o; }
+        memcpy(seq, c, 127);
+        for (int s7 = 0; s7 < 128; s7++) {
+            phase[s7] = 255;
+            for (int t = 0; t < 127; t++) { bool ok = true; for (int q = 0; q < 7 && ok; q++) ok = c[(t + 127 - 7 + q) % 127] == ((s7 >> q) & 1); if (ok) { phase[s7] = (uint8_t)t; break; } }
+        }
+    }
+    size_t o = 0; auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t o_a = take(sizeof tw128), o_b = take(sizeof tw32), o_s = take(127), o_p = take(128), o_pre = take(640 * 4);
+    cudaError_t e = h->tabtx.need(o);
+    if (e != cudaSuccess) return h->fail(SB200_E_NOMEM, "cudaMalloc tx tables", e);
+    char* base = (char*)h->tabtx.p;
+    e = cudaMemcpy(base + o_a, tw128, sizeof tw128, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + o_b, tw32, sizeof tw32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + o_s, seq, 127, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + o_p, phase, 128, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->tabtx.release(); return h->fail(SB200_E_CUDA, "tx table upload", e); }
+    DevTablesTx& X = h->X;
+    X.tw128 = (const uint32_t*)(base + o_a); X.tw32 = (const uint32_t*)(base + o_b); X.scr_seq = (const uint8_t*)(base + o_s); X.scr_phase = (const uint8_t*)(base + o_p);
+    X.preamble = (uint32_t*)(base + o_pre);
+    k_tx11a_preamble<<<1, 32>>>(X);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { h->tabtx.release(); return h->fail(SB200_E_CUDA, "k_tx11a_preamble", e); }
+    h->launches += 1;
+    return SB200_OK;
+}
+
+extern "C" int sb200_tx11a_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_total, const uint64_t* pay_off, const uint32_t* pay_len, const uint8_t* seeds,
+                                 uint32_t nframes, uint32_t rate_kbps, uint32_t lead_samples, uint32_t sample_bits, void* out, uint64_t out_stride_samples,
+                                 uint32_t* nsamples, void* cuda_stream) {
+    if (!h || !payload || !pay_off || !pay_len || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (sample_bits != 8 && sample_bits != 16) return h->fail(SB200_E_INVALID, "sample_bits must be 8 (COMPLEX8) or 16 (COMPLEX16 = COMPLEX8 << 8)");
+    if (nframes == 0) return SB200_OK;
+    static const struct { uint32_t kbps, code, nbpsc, cr, ndbps; } R[8] = {{6000, 0xB, 1, CR_12, 24}, {9000, 0xF, 1, CR_34, 36}, {12000, 0xA, 2, CR_12, 48}, {18000, 0xE, 2, CR_34, 72},
+        {24000, 0x9, 4, CR_12, 96}, {36000, 0xD, 4, CR_34, 144}, {48000, 0x8, 6, CR_23, 192}, {54000, 0xC, 6, CR_34, 216}};          // ieee80211a_cmn.h:66-157
+    int ri = -1; for (int i = 0; i < 8; i++) if (R[i].kbps == rate_kbps) ri = i;
+    if (ri < 0) return h->fail(SB200_E_INVALID, "rate_kbps is not an 802.11a rate");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_tables_tx(h); if (rc != SB200_OK) return rc;
+    // frame table on the host (sizes the grid and checks the slots)
+    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    const bool off_dev = is_device_ptr(pay_off), len_dev = is_device_ptr(pay_len), pay_dev = is_device_ptr(payload), out_dev = is_device_ptr(out);
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), pay_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), pay_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), pay_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), pay_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    TxJob job{}; job.rate_code = R[ri].code; job.nbpsc = R[ri].nbpsc; job.code_rate = R[ri].cr; job.ndbps = R[ri].ndbps; job.ndbps_pad = rate_kbps == 9000 ? 72 : R[ri].ndbps;
+    job.lead = lead_samples; job.fmt16 = sample_bits == 16;
+    uint32_t max_nsym = 0;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if (lenh[i] + 4u > 4095u || offh[i] + lenh[i] > payload_total) return h->fail(SB200_E_INVALID, "payload slot out of range (LENGTH is 12 bits incl. FCS)");
+        const uint32_t ns = tx11a_nsym(lenh[i], job.ndbps, job.ndbps_pad);
+        if ((uint64_t)lead_samples + 640u + 160ull * (1u + ns) > out_stride_samples) return h->fail(SB200_E_INVALID, "out_stride_samples too small for the frame");
+        if (ns > max_nsym) max_nsym = ns;
+    }
+    job.max_sym = 1u + max_nsym;
+    const uint8_t* d_pay; const uint64_t* d_off; const uint32_t* d_len; const uint8_t* d_seed = nullptr;
+    if (pay_dev) d_pay = payload; else { CK(h->txpay.need(payload_total)); CK(cudaMemcpyAsync(h->txpay.p, payload, payload_total, cudaMemcpyHostToDevice, st)); d_pay = (const uint8_t*)h->txpay.p; }
+    if (off_dev) d_off = pay_off; else { CK(h->txoff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->txoff.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->txoff.p; }
+    if (len_dev) d_len = pay_len; else { CK(h->txlen.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->txlen.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->txlen.p; }
+    if (seeds) { if (is_device_ptr(seeds)) d_seed = seeds; else { CK(h->txseed.need(nframes)); CK(cudaMemcpyAsync(h->txseed.p, seeds, nframes, cudaMemcpyHostToDevice, st)); d_seed = (const uint8_t*)h->txseed.p; } }
+    const size_t bps = sample_bits == 16 ? 4 : 2, out_bytes = (size_t)nframes * out_stride_samples * bps;
+    void* d_out = out; if (!out_dev) { CK(h->txout.need(out_bytes)); d_out = h->txout.p; }
+    uint32_t* d_ns = nullptr; const bool ns_dev = nsamples && is_device_ptr(nsamples);
+    if (nsamples) { if (ns_dev) d_ns = nsamples; else { CK(h->txns.need(nframes * 4ull)); d_ns = (uint32_t*)h->txns.p; } }
+    const unsigned helpers = 8;                          // warps per frame for the preamble and the zero fill
+    dim3 grid((job.max_sym + helpers + SB_TX_WARPS - 1) / SB_TX_WARPS, nframes);
+    CK(cudaEventRecord(h->ev0, st));
+    k_tx11a<<<grid, 32 * SB_TX_WARPS, 0, st>>>(d_pay, d_off, d_len, d_seed, nframes, job, h->T, h->X, h->inv_deint, d_out, out_stride_samples, d_ns);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 0; h->launches += 1;
+    CK(cudaGetLastError());
+    bool sync = false;
+    if (!out_dev) { CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (nsamples && !ns_dev) { CK(cudaMemcpyAsync(nsamples, d_ns, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (sync) CK(cudaStreamSynchronize(st));
     return SB200_OK;
 }
 
