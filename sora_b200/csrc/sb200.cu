@@ -670,7 +670,7 @@ extern "C" int sb200_tx11a_batch(sb200_handle* h, const uint8_t* payload, uint64
     uint32_t* d_ns = nullptr; const bool ns_dev = nsamples && is_device_ptr(nsamples);
     if (nsamples) { if (ns_dev) d_ns = nsamples; else { CK(h->txns.need(nframes * 4ull)); d_ns = (uint32_t*)h->txns.p; } }
     const unsigned helpers = 8;                          // warps per frame for the preamble and the zero fill
-    dim3 grid((job.max_sym + helpers + SB_TX_WARPS - 1) / SB_TX_WARPS, nframes);
+    dim3 grid(nframes, (job.max_sym + helpers + SB_TX_WARPS - 1) / SB_TX_WARPS);
     CK(cudaEventRecord(h->ev0, st));
     k_tx11a<<<grid, 32 * SB_TX_WARPS, 0, st>>>(d_pay, d_off, d_len, d_seed, nframes, job, h->T, h->X, h->inv_deint, d_out, out_stride_samples, d_ns);
     CK(cudaEventRecord(h->ev1, st));

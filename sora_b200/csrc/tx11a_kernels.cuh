@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(32 * SB_TX_WARPS) k_tx11a(const uint8_t* __res
     __shared__ uint32_t s_x[SB_TX_WARPS][128];
     __shared__ uint8_t s_d[SB_TX_WARPS][232];           // scrambled data bits of the symbol, six bits of history in front
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t f = blockIdx.y;
-    const uint32_t sym = blockIdx.x * SB_TX_WARPS + wib;    // 0 = SIGNAL, 1.. = data; symbols >= job.max_sym do the preamble / zero fill
+    const uint32_t f = blockIdx.x;                         // frames on x (no 65535 limit), symbol groups on y
+    const uint32_t sym = blockIdx.y * SB_TX_WARPS + wib;    // 0 = SIGNAL, 1.. = data; symbols >= job.max_sym do the preamble / zero fill
     if (f >= nframes) return;
     const uint32_t len = pay_len[f];
     const uint32_t nsym = tx11a_nsym(len, job.ndbps, job.ndbps_pad);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(32 * SB_TX_WARPS) k_tx11a(const uint8_t* __res
         else out8[pos] = (uint16_t)((re & 0xFF) | ((im & 0xFF) << 8));
     };
     if (sym >= job.max_sym) {                           // helper warps: lead zeros, preamble, trailing zeros
-        const uint32_t helper = sym - job.max_sym, nhelp = gridDim.x * SB_TX_WARPS - job.max_sym;
+        const uint32_t helper = sym - job.max_sym, nhelp = gridDim.y * SB_TX_WARPS - job.max_sym;
         if (helper == 0 && lane == 0 && nsamples) nsamples[f] = used;
         for (uint64_t p = (uint64_t)helper * 32 + lane; p < out_stride; p += (uint64_t)nhelp * 32) {
             if (p >= job.lead && p < job.lead + 640u) put((uint32_t)p, unpack(X.preamble[p - job.lead]));
