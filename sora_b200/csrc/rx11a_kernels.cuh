@@ -355,9 +355,12 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
         if (!z1) { int re, im; cmul32(re, im, F1, ch1); E1 = mk(sx16(re >> 8), sx16(im >> 8)); }
         cs16 C0 = cmul_q15(E0, comp0), C1 = cmul_q15(E1, comp1);                      // freqoffset.hpp:28-30
         int th = 0;                                                                    // pilot.hpp:168-232
-        if (lane == 11 || lane == 25) th = d_uatan2(T, C1.im, C1.re);      // bins 43 (-21) and 57 (-7)
-        if (lane == 7)  th = d_uatan2(T, C0.im, C0.re);                    // bin 7
-        if (lane == 21) th = d_uatan2(T, -C0.im, -C0.re);                  // bin 21 (pilot sent negated)
+        {   // one table walk for the whole warp: bins 43 (-21) and 57 (-7) sit in C1 of lanes 11 / 25, bins 7 and 21 in C0 of lanes 7 / 21
+            const bool hi = lane == 11 || lane == 25, neg = lane == 21;               // bin 21's pilot is sent negated
+            const int py = hi ? C1.im : (neg ? -C0.im : C0.im), px = hi ? C1.re : (neg ? -C0.re : C0.re);
+            const int a = d_uatan2(T, py, px);
+            if (hi || lane == 7 || lane == 21) th = a;
+        }
         if (s_pilot[symbol_count]) th = sx16(th + 0x8000);
         int th1 = __shfl_sync(FULL, th, 11), th2 = __shfl_sync(FULL, th, 25), th3 = __shfl_sync(FULL, th, 7), th4 = __shfl_sync(FULL, th, 21);
         symbol_count++; if (symbol_count >= 127) symbol_count = 0;
@@ -410,7 +413,10 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
             remain = fi.nsym_total; plcp_data = 1; nbpsc = nb; fi.ncbps = 48 * nb;
             load_positions(nb);
         } else {
-            for (int i = lane * 4; i < ncbps; i += 128) *(uint32_t*)(sout + soft_bytes + i) = *(const uint32_t*)(sb + i);
+            {   uint32_t* dst = (uint32_t*)(sout + soft_bytes); const uint32_t* src = (const uint32_t*)sb; const int nw = ncbps >> 2;   // <= 72 words
+                if (lane < nw) dst[lane] = src[lane];
+                if (lane + 32 < nw) dst[lane + 32] = src[lane + 32];
+                if (lane + 64 < nw) dst[lane + 64] = src[lane + 64]; }
             soft_bytes += ncbps;
         }
         __syncwarp();
