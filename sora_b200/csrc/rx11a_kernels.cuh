@@ -257,11 +257,12 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
         uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps) {
     __shared__ uint32_t s_fft[SB_FRONT_WARPS][2][64];
     __shared__ __align__(16) uint8_t s_soft[SB_FRONT_WARPS][288];
-    __shared__ uint8_t s_demap[1024];
+    __shared__ uint32_t s_demap[256];                  // per input value: [bpsk/qpsk/first bit | 16-QAM second | 64-QAM second | 64-QAM third] soft bits
     __shared__ uint8_t s_pilot[128];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_demap[i] = __ldg(T.demap + i);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_demap[i] = (uint32_t)__ldg(T.demap + i) | ((uint32_t)__ldg(T.demap + 256 + i) << 8) | ((uint32_t)__ldg(T.demap + 512 + i) << 16) | ((uint32_t)__ldg(T.demap + 768 + i) << 24);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_pilot[i] = __ldg(T.pilot_neg + i);
     __syncthreads();
     const uint32_t f = blockIdx.x * SB_FRONT_WARPS + wib;
@@ -384,11 +385,12 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t
         auto demap = [&](cs16 r, int d, const unsigned short (&pos)[6]) {
             if (d < 0) return;
             const unsigned re = (unsigned)min(max(r.re >> 4, -128), 127) & 0xFF, im = (unsigned)min(max(r.im >> 4, -128), 127) & 0xFF;
-            if (nbpsc == 1) { sb[pos[0]] = s_demap[re]; }
-            else if (nbpsc == 2) { sb[pos[0]] = s_demap[re]; sb[pos[1]] = s_demap[im]; }
-            else if (nbpsc == 4) { sb[pos[0]] = s_demap[re]; sb[pos[1]] = s_demap[256 + re]; sb[pos[2]] = s_demap[im]; sb[pos[3]] = s_demap[256 + im]; }
-            else { sb[pos[0]] = s_demap[re]; sb[pos[1]] = s_demap[512 + re]; sb[pos[2]] = s_demap[768 + re];
-                   sb[pos[3]] = s_demap[im]; sb[pos[4]] = s_demap[512 + im]; sb[pos[5]] = s_demap[768 + im]; }
+            const uint32_t wr = s_demap[re], wi = s_demap[im];
+            if (nbpsc == 1) { sb[pos[0]] = (uint8_t)wr; }
+            else if (nbpsc == 2) { sb[pos[0]] = (uint8_t)wr; sb[pos[1]] = (uint8_t)wi; }
+            else if (nbpsc == 4) { sb[pos[0]] = (uint8_t)wr; sb[pos[1]] = (uint8_t)(wr >> 8); sb[pos[2]] = (uint8_t)wi; sb[pos[3]] = (uint8_t)(wi >> 8); }
+            else { sb[pos[0]] = (uint8_t)wr; sb[pos[1]] = (uint8_t)(wr >> 16); sb[pos[2]] = (uint8_t)(wr >> 24);
+                   sb[pos[3]] = (uint8_t)wi; sb[pos[4]] = (uint8_t)(wi >> 16); sb[pos[5]] = (uint8_t)(wi >> 24); }
         };
         demap(R0, d0, pos0); demap(R1, d1, pos1);
         __syncwarp();
