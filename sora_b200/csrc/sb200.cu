@@ -672,9 +672,11 @@ extern "C" int sb200_tx11a_batch(sb200_handle* h, const uint8_t* payload, uint64
     const unsigned helpers = 8;                          // warps per frame for the preamble and the zero fill
     dim3 grid(nframes, (job.max_sym + helpers + SB_TX_WARPS - 1) / SB_TX_WARPS);
     CK(cudaEventRecord(h->ev0, st));
-    k_tx11a<<<grid, 32 * SB_TX_WARPS, 0, st>>>(d_pay, d_off, d_len, d_seed, nframes, job, h->T, h->X, h->inv_deint, d_out, out_stride_samples, d_ns);
+    CK(h->crc.need(nframes * 4ull));
+    k_tx11a_crc<<<(nframes + 127) / 128, 128, 0, st>>>(d_pay, d_off, d_len, nframes, h->T, (uint32_t*)h->crc.p);
+    k_tx11a<<<grid, 32 * SB_TX_WARPS, 0, st>>>(d_pay, d_off, d_len, d_seed, nframes, job, h->T, h->X, h->inv_deint, (const uint32_t*)h->crc.p, d_out, out_stride_samples, d_ns);
     CK(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->nk = 0; h->launches += 1;
+    h->timed = true; h->nk = 0; h->launches += 2;
     CK(cudaGetLastError());
     bool sync = false;
     if (!out_dev) { CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st)); sync = true; }

@@ -115,10 +115,21 @@ __host__ __device__ inline uint32_t tx11a_nsym(uint32_t len, uint32_t ndbps, uin
     return (bits + ((padded - bits + 7u) / 8u) * 8u) / ndbps;
 }
 
+// CRC-32 of every MPDU (what fb11amod_config.hpp:40 stores in CF_11aTxVector::crc32): one thread per frame
+__global__ void __launch_bounds__(128) k_tx11a_crc(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ pay_off, const uint32_t* __restrict__ pay_len,
+                                                   uint32_t nframes, DevTables T, uint32_t* __restrict__ crcs) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const uint8_t* p = payload + pay_off[f]; const uint32_t n = pay_len[f];
+    uint32_t c = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < n; i++) c = (c >> 8) ^ __ldg(T.crc32 + ((c ^ p[i]) & 0xFFu));
+    crcs[f] = ~c;
+}
+
 #define SB_TX_WARPS 4
 __global__ void __launch_bounds__(32 * SB_TX_WARPS) k_tx11a(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ pay_off, const uint32_t* __restrict__ pay_len,
         const uint8_t* __restrict__ seeds, uint32_t nframes, TxJob job, DevTables T, DevTablesTx X, const uint16_t* __restrict__ inv_deint,
-        void* __restrict__ out, uint64_t out_stride /*samples per slot*/, uint32_t* __restrict__ nsamples) {
+        const uint32_t* __restrict__ crcs, void* __restrict__ out, uint64_t out_stride /*samples per slot*/, uint32_t* __restrict__ nsamples) {
     __shared__ uint32_t s_x[SB_TX_WARPS][128];
     __shared__ uint8_t s_d[SB_TX_WARPS][232];           // scrambled data bits of the symbol, six bits of history in front
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -157,13 +168,7 @@ __global__ void __launch_bounds__(32 * SB_TX_WARPS) k_tx11a(const uint8_t* __res
         const uint8_t* pl = payload + pay_off[f];
         const uint32_t seed = seeds ? seeds[f] : 0xFFu, phase = __ldg(X.scr_phase + (seed >> 1));
         const uint32_t crc_at = 2u + len, tail_at = crc_at + 4u;
-        // CRC-32 of the payload: every data-symbol warp needs it only when its bits overlap the FCS; computed by lane 0 then
-        uint32_t crc = 0;
-        const uint32_t b_lo = n0 >= 6u ? (n0 - 6u) >> 3 : 0u, b_hi = (n0 + nd - 1u) >> 3;
-        if (b_hi >= crc_at && b_lo < tail_at) {
-            if (lane == 0) { uint32_t c = 0xFFFFFFFFu; for (uint32_t i = 0; i < len; i++) c = (c >> 8) ^ __ldg(T.crc32 + ((c ^ pl[i]) & 0xFFu)); crc = ~c; }
-            crc = __shfl_sync(0xFFFFFFFFu, crc, 0);
-        }
+        const uint32_t crc = __ldg(crcs + f);          // CF_11aTxVector::crc32, computed by k_tx11a_crc
         for (uint32_t i = lane; i < nd + 6u; i += 32) {
             const int j = (int)n0 - 6 + (int)i;
             uint32_t bit = 0;
