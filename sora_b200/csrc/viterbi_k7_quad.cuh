@@ -88,14 +88,10 @@ __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const 
 // The bytes below the metrics ("dead" bytes) collect the wrap carries of the low halves; they never decide a compare
 // (the candidates' marks differ) and are wiped at every normalisation, long before they could overflow.
 __device__ __forceinline__ uint32_t vq_commit_marks(uint32_t (&R)[8]) {
-    uint32_t acc0 = 0, acc1 = 0;                        // two short chains instead of one long one
+    uint32_t acc = 0;
 #pragma unroll
-    for (int r = 0; r < 8; r += 2) {
-        const uint32_t m0 = R[r] & 0x01000100u, m1 = R[r + 1] & 0x01000100u;
-        R[r] -= m0; R[r + 1] -= m1;
-        acc0 = m0 * (1u << r) + acc0; acc1 = m1 * (2u << r) + acc1;
-    }
-    return __byte_perm(acc0 + acc1, 0, 0x4431);         // [byte 1, byte 3, 0, 0]
+    for (int r = 0; r < 8; r++) { const uint32_t m = R[r] & 0x01000100u; R[r] -= m; acc = m * (1u << r) + acc; }
+    return __byte_perm(acc, 0, 0x4431);                 // [byte 1, byte 3, 0, 0]
 }
 // branch-metric byte vectors (byte index = cA<<1 | cB) from soft values in bytes B0 (A) and B0+1 (B) of the packed word w
 __device__ __forceinline__ int vq_dp4a_us(uint32_t a, int b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
@@ -203,7 +199,7 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
                 // traceback in address space: survivor bit d of slot A at column c = bit A of that column's word;
                 // the predecessor slot is A with bit (6 - c%6)%6 replaced by d; d is also the decoded bit of column c.
                 uint32_t A = best & 63u, col = cslot, cm = tm, todo = la + nout;
-                unsigned long long fifo = 0; int cnt = -(int)la;            // the first `la` bits are only looked through
+                uint32_t fifo = 0; int cnt = -(int)la;                      // the first `la` bits are only looked through; at most 13 bits wait
                 uint8_t* win = s_win[fb]; uint32_t wpos = nout >> 3;        // bytes come out last-first; the sink needs them first-first
                 auto emit = [&]() { while (cnt >= 8) { win[--wpos] = (uint8_t)(fifo >> (cnt - 8)); cnt -= 8; } };
                 while (cm != 0 && todo) {               // up to 5 columns until the column phase is 0
