@@ -102,6 +102,14 @@ int sb200_rx11a_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samp
 int sb200_rx11a_stream(sb200_handle* h, const int16_t* iq, uint64_t nsamples, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride,
                        sb200_frame_result* res, uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream);
 
+/* Many continuous captures in one call: capture s = samples [stream_off[s], stream_off[s] + stream_len[s]); results of capture s sit in
+ * res / out_bytes / sample_index rows s * max_frames .. (+ nframes_out[s]).  Every pass decodes the next frame of all captures that still
+ * have samples, so the device works on a full batch while each capture keeps RxThread's sequential semantics.  Tables and results are
+ * host memory; iq may be host or device. */
+int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples, const uint64_t* stream_off, const uint32_t* stream_len,
+                        uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res,
+                        uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream);
+
 /* Same as sb200_rx11a_batch for captures at `sample_rate_mhz` = 40 or 44.  44 Msps slots first pass the reference's 11:10 linear
  * resampler (TDownSample44_40 / Down44to40, Brick11/src/sampling.hpp:37-65, 44MTo40M.hpp:63-123; graph
  * CreateDemodGraph11a_44M, fb11ademod_config.hpp:244-317), each slot starting the interpolator afresh; detect_index then

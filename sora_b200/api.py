@@ -22,7 +22,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
                             ("detect_index", "<u4"), ("cfo_est", "<i2"), ("lsig_length", "<u2")])
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
-           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
+           "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
            "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch"]
 
 class Sb200Error(RuntimeError):
@@ -129,6 +129,16 @@ class Engine:
         sidx = np.zeros(max_frames, np.uint32); n = C.c_uint32(0)
         self._check(self._lib.sb200_rx11a_stream(self._h, _ptr(iq), iq.shape[0], max_frames, _ptr(out), out_stride, _ptr(res), _ptr(sidx), C.addressof(n), 0), "sb200_rx11a_stream")
         return res[:n.value], out[:n.value], sidx[:n.value]
+
+    def rx11a_streams(self, iq, stream_off, stream_len, max_frames=16, out_stride=2560):
+        """Many continuous captures -> (results [S, max_frames], bytes [S, max_frames, out_stride], sample_index [S, max_frames], counts [S])."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(stream_off, dtype=np.uint64); ln = np.ascontiguousarray(stream_len, dtype=np.uint32); S = len(off)
+        res = np.zeros((S, max_frames), dtype=RESULT_DTYPE); out = np.zeros((S, max_frames, out_stride), dtype=np.uint8)
+        sidx = np.zeros((S, max_frames), np.uint32); cnt = np.zeros(S, np.uint32)
+        self._check(self._lib.sb200_rx11a_streams(self._h, C.c_void_p(_ptr(iq)), C.c_uint64(iq.shape[0]), C.c_void_p(_ptr(off)), C.c_void_p(_ptr(ln)), C.c_uint32(S), C.c_uint32(max_frames),
+                                                  C.c_void_p(_ptr(out)), C.c_uint32(out_stride), C.c_void_p(_ptr(res)), C.c_void_p(_ptr(sidx)), C.c_void_p(_ptr(cnt)), C.c_void_p(0)), "sb200_rx11a_streams")
+        return res, out, sidx, cnt
 
     def rx11b_raw(self, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream=0):
         self._check(self._lib.sb200_rx11b_batch(self._h, iq_ptr, iq_total, off_ptr, len_ptr, nframes, out_ptr, out_stride, res_ptr, stream), "sb200_rx11b_batch")

@@ -315,44 +315,69 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     return SB200_OK;
 }
 
-// Continuous capture: frames are found one after another exactly like RxThread does (fb11a_demod.cpp:29-81): after every
+// Many continuous captures at once.  Every pass decodes the next frame of every capture that still has samples (one slot per
+// capture, from its cursor to its end, with its own carried DC), so the device sees a full batch per pass and the number of
+// passes is the largest number of frames in any one capture.
+extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* stream_off, const uint32_t* stream_len,
+                                   uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res,
+                                   uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream) {
+    if (!h || !iq || !stream_off || !stream_len || !res || !nframes_out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    if (is_device_ptr(res) || (out_bytes && is_device_ptr(out_bytes)) || is_device_ptr(stream_off) || is_device_ptr(stream_len) || is_device_ptr(nframes_out))
+        return h->fail(SB200_E_INVALID, "stream mode takes its tables and returns its results in host memory");
+    for (uint32_t s = 0; s < nstreams; s++) { nframes_out[s] = 0; if (stream_off[s] + stream_len[s] > iq_total) return h->fail(SB200_E_INVALID, "capture exceeds iq_total_samples"); }
+    if (nstreams == 0 || max_frames == 0) return SB200_OK;
+    const int16_t* d_iq = iq;
+    if (!is_device_ptr(iq)) { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const int16_t*)h->iq.p; }
+    std::vector<uint64_t> pos(nstreams, 0); std::vector<int2> dc(nstreams, make_int2(0, 0));
+    std::vector<uint32_t> active(nstreams); for (uint32_t s = 0; s < nstreams; s++) active[s] = s;
+    std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<int2> dcv; std::vector<sb200_frame_result> r; std::vector<FrameInfo> fi; std::vector<uint8_t> bytes;
+    const uint32_t row = out_bytes ? (out_stride < 2560u ? out_stride : 2560u) : 0u;
+    const uint32_t saved_chunk = h->chunk_frames_device; h->chunk_frames_device = 0;
+    int rc = SB200_OK;
+    while (!active.empty()) {
+        std::vector<uint32_t> live;
+        for (uint32_t s : active) if (nframes_out[s] < max_frames && pos[s] + 28 <= stream_len[s]) live.push_back(s);
+        if (live.empty()) break;
+        const uint32_t n = (uint32_t)live.size();
+        off.resize(n); len.resize(n); dcv.resize(n); r.resize(n); fi.resize(n); if (row) bytes.resize((size_t)n * row);
+        for (uint32_t j = 0; j < n; j++) { const uint32_t s = live[j]; off[j] = stream_off[s] + pos[s]; len[j] = (uint32_t)(stream_len[s] - pos[s]); dcv[j] = dc[s]; }
+        CK(h->dcbuf.need(n * sizeof(int2))); CK(cudaMemcpyAsync(h->dcbuf.p, dcv.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
+        FrontTaps taps{}; h->tab_off = nullptr;
+        rc = rx11a_run(h, d_iq, iq_total, off.data(), len.data(), n, row ? bytes.data() : nullptr, row, r.data(), st, taps, nullptr, 0, (const int2*)h->dcbuf.p);
+        if (rc != SB200_OK) break;
+        CK(cudaMemcpy(fi.data(), h->info.p, n * sizeof(FrameInfo), cudaMemcpyDeviceToHost));
+        active.clear();
+        for (uint32_t j = 0; j < n; j++) {
+            const uint32_t s = live[j];
+            if (r[j].status == SB200_FRAME_NONE) continue;                               // this capture ran out of samples: RxThread returns
+            dc[s] = make_int2(fi[j].dc_re, fi[j].dc_im);
+            const uint32_t consumed = r[j].status == SB200_FRAME_PLCP_FAIL ? 1u : r[j].nsym;     // OFDM symbols that went through the graph
+            const uint64_t e20 = (uint64_t)r[j].detect_index + 144ull + 80ull * consumed;     // 20 Msps samples up to the end of the last symbol
+            const uint64_t v_last = e20 / 4ull - 1ull, blk = (8ull * v_last + 7ull) / 28ull;
+            pos[s] += (blk + 1ull) * 28ull;                                                   // the driver sees the event after that source block
+            const size_t slot = (size_t)s * max_frames + nframes_out[s];
+            res[slot] = r[j];
+            if (sample_index) sample_index[slot] = (uint32_t)pos[s];
+            if (row) memcpy(out_bytes + slot * out_stride, bytes.data() + (size_t)j * row, row);
+            nframes_out[s]++;
+            active.push_back(s);
+        }
+    }
+    h->chunk_frames_device = saved_chunk;
+    return rc;
+}
+
+// One continuous capture: frames are found one after another exactly like RxThread does (fb11a_demod.cpp:29-81): after every
 // event the graph is flushed and reset, the source continues with the next 28-sample block, and only the DC estimate
 // (CF_VecDC) survives.  Each frame is one pass of the batch pipeline over the remaining samples with that DC.
 extern "C" int sb200_rx11a_stream(sb200_handle* h, const int16_t* iq, uint64_t nsamples, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride,
                                   sb200_frame_result* res, uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream) {
-    if (!h || !iq || !res || !nframes_out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
-    *nframes_out = 0;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    CK(cudaSetDevice(h->device));
-    if (is_device_ptr(res) || (out_bytes && is_device_ptr(out_bytes))) return h->fail(SB200_E_INVALID, "stream mode returns results in host memory");
-    const int16_t* d_iq = iq;
-    if (!is_device_ptr(iq)) { CK(h->iq.need(nsamples * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, nsamples * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const int16_t*)h->iq.p; }
-    CK(h->dcbuf.need(sizeof(int2)));
-    uint64_t pos = 0; int2 dc = make_int2(0, 0);
-    const uint32_t saved_chunk = h->chunk_frames_device; h->chunk_frames_device = 0;
-    int rc = SB200_OK;
-    while (*nframes_out < max_frames && pos + 28 <= nsamples) {
-        const uint64_t off = pos; const uint64_t remain = nsamples - pos;
-        const uint32_t len = remain > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)remain;
-        CK(cudaMemcpyAsync(h->dcbuf.p, &dc, sizeof dc, cudaMemcpyHostToDevice, st));
-        sb200_frame_result r; FrontTaps taps{};
-        h->tab_off = nullptr;
-        uint8_t* ob = out_bytes ? out_bytes + (size_t)(*nframes_out) * out_stride : nullptr;
-        rc = rx11a_run(h, d_iq, nsamples, &off, &len, 1, ob, ob ? out_stride : 0, &r, st, taps, nullptr, 0, (const int2*)h->dcbuf.p);
-        if (rc != SB200_OK) break;
-        if (r.status == SB200_FRAME_NONE) break;          // ran out of samples: the reference's RxThread returns
-        FrameInfo fi; CK(cudaMemcpy(&fi, h->info.p, sizeof fi, cudaMemcpyDeviceToHost));
-        dc = make_int2(fi.dc_re, fi.dc_im);
-        const uint32_t consumed = r.status == SB200_FRAME_PLCP_FAIL ? 1u : r.nsym;      // OFDM symbols that went through the graph
-        const uint64_t e20 = (uint64_t)r.detect_index + 144ull + 80ull * consumed;      // 20 Msps samples up to the end of the last symbol
-        const uint64_t v_last = e20 / 4ull - 1ull, blk = (8ull * v_last + 7ull) / 28ull;
-        pos += (blk + 1ull) * 28ull;                        // the driver sees the event after that source block
-        res[*nframes_out] = r;
-        if (sample_index) sample_index[*nframes_out] = (uint32_t)pos;
-        (*nframes_out)++;
-    }
-    h->chunk_frames_device = saved_chunk;
-    return rc;
+    if (!h || !nframes_out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (nsamples > 0xFFFFFF00ull) return h->fail(SB200_E_INVALID, "capture longer than 2^32 samples: split it");
+    const uint64_t off = 0; const uint32_t len = (uint32_t)nsamples;
+    return sb200_rx11a_streams(h, iq, nsamples, &off, &len, 1, max_frames, out_bytes, out_stride, res, sample_index, nframes_out, cuda_stream);
 }
 
 extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,

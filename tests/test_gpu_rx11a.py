@@ -251,3 +251,20 @@ def test_ofdm_bin_golden(eng):
     res, out = _compare(eng, iq, [0], [len(iq)])
     assert res["status"][0] == 1 and res["rate_kbps"][0] == 24000 and res["length"][0] == 204
     assert (out[0, :200] == 0x31).all() and bytes(out[0, 200:204]) == bytes.fromhex("388d4983")
+
+def test_many_streams_at_once(eng):
+    """sb200_rx11a_streams: a batch of continuous captures, each decoded with RxThread's sequential semantics."""
+    caps = [_mixed_stream(s, dc=(40 * s - 200, 17 * s)) for s in range(7, 19)]
+    caps.append(np.zeros((3000, 2), np.int16)); caps.append(caps[0][:5000].copy()); caps.append(np.zeros((10, 2), np.int16))
+    off = np.concatenate([[0], np.cumsum([len(c) for c in caps])[:-1]]); ln = np.array([len(c) for c in caps])
+    res, out, sidx, cnt = eng.rx11a_streams(np.concatenate(caps), off, ln, max_frames=6)
+    for s, c in enumerate(caps):
+        ores, oout = oracle_py.rx11a_run(c, max_frames=6, out_stride=2560)
+        assert cnt[s] == len(ores), (s, cnt[s], len(ores))
+        for k in ("status", "rate_kbps", "length", "crc32", "nsym", "cfo_est"):
+            assert (res[s, :cnt[s]][k] == ores[k]).all(), (s, k)
+        assert (sidx[s, :cnt[s]] == ores["sample_index"]).all()
+        for i in range(cnt[s]):
+            if ores["status"][i] in (1, oracle_py.E_CRC32_FAIL):
+                L = int(ores["length"][i]); assert (out[s, i, :L] == oout[i, :L]).all()
+    assert cnt.max() == 6 and cnt[-1] == 0 and cnt[-3] == 0
