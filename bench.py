@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chunk", type=int, default=8192, help="slots per pipeline chunk inside the library (0 = no chunking)")
     ap.add_argument("--chunk-device", type=int, default=0, help="slots per pipeline chunk for device-resident IQ (0 = one pass; >0 overlaps the front end of chunk k+1 with the Viterbi of chunk k)")
+    ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -142,6 +143,7 @@ def main():
     eng = api.Engine(local)
     eng.set_option("chunk_frames", args.chunk)
     eng.set_option("chunk_frames_device", args.chunk_device)
+    if args.vq_pad_smem: eng.set_option("vq_pad_smem", args.vq_pad_smem)
     stream = torch.cuda.current_stream()
     # ---- HBM-resident input: U unique slots tiled to F (distinct addresses: 2.6 GB at F=65536 >> 126 MB L2) ----
     iq_unique_dev = torch.from_numpy(iq_u.reshape(U, -1)).to(dev)

@@ -71,6 +71,7 @@ struct sb200_handle {
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
+    uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
     std::string err;
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -201,7 +202,7 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
         h->launches += 3;
     } else {                                           // one launch per code rate; quads of other rates exit at once
         const unsigned g = (n + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
-        k_viterbi_quad<CR_34><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
+        k_viterbi_quad<CR_34><<<g, b, h->vq_pad_smem, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         k_viterbi_quad<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         k_viterbi_quad<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         h->launches += 5;
@@ -714,6 +715,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!h || !name) return SB200_E_INVALID;
     if (!strcmp(name, "chunk_frames")) { h->chunk_frames = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "chunk_frames_device")) { h->chunk_frames_device = (uint32_t)value; return SB200_OK; }
+    if (!strcmp(name, "vq_pad_smem")) { h->vq_pad_smem = (uint32_t)value; return SB200_OK; }
     return h->fail(SB200_E_INVALID, "unknown option");
 }
 
