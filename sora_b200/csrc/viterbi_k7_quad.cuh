@@ -20,7 +20,9 @@
 //   * Survivor bits: the LSB of every new metric, 16 per lane per step -> one 16-bit word in a [column][block] shared
 //     memory ring; bit index == physical address, so the traceback never leaves address space: the predecessor of slot A
 //     at column c is A with bit (6 - c%6)%6 replaced by the survivor bit.
-//   * One lane of the quad runs the windowed traceback, the x^7+x^4+1 descrambler and the CRC-32 / verdict.
+//   * One lane of the quad runs the windowed traceback (six columns per iteration with compile-time bit positions: after six
+//     columns the address register is the six decoded bits), the x^7+x^4+1 descrambler and the CRC-32 / verdict.
+//   * Two renderings of the mark handling (vq_step_a / vq_step_b below), chosen per code rate by measurement.
 #pragma once
 #include "viterbi_k7.cuh"
 
@@ -35,27 +37,37 @@ __host__ __device__ constexpr int vq_cls(int p) {            // (cA << 1) | cB o
     return ((((p >> 1) ^ (p >> 2) ^ (p >> 4)) & 1) << 1) | ((p ^ (p >> 1) ^ (p >> 2)) & 1);
 }
 // static class of (reg r, half h) at phase T, lane part excluded (GF(2)-linear, so the lane part is XORed in later)
-__host__ __device__ constexpr int vq_scls(int T, int r, int h) { return vq_cls(vq_rol6((h << 3) | r, T) & 31); }
+// low four address bits of (register r, half h): reg bit 0 | half | reg bit 2 | reg bit 1 — the order in which the PRMT gather of the
+// survivor marks (vq_commit_marks) lays the 16 decisions of a lane down, so that ring bit index == address
+// (style B); style A keeps half | reg.
+template <int S> __host__ __device__ constexpr int vq_low4(int r, int h) { return S ? ((r & 1) << 3) | (h << 2) | (r >> 1) : (h << 3) | r; }
+template <int S> __host__ __device__ constexpr int vq_scls(int T, int r, int h) { return vq_cls(vq_rol6(vq_low4<S>(r, h), T) & 31); }
 __host__ __device__ constexpr int vq_lcls(int T, int q) { return vq_cls(vq_rol6(q << 4, T) & 31); }
 // PRMT selector building [0, byte i0, 0, byte i1] from (Cb, 0): the branch metric lands in the high byte of each half
 __host__ __device__ constexpr unsigned vq_sel(int i0, int i1) { return (unsigned)(4 | (i0 << 4) | (4 << 8) | (i1 << 12)); }
 
 struct VqLane {
     unsigned swz[6];       // per-phase byte swizzle applying this lane's class contribution
-    unsigned lo[2];        // lane-phase role of this lane's own registers: the odd role adds the survivor mark
+    unsigned lm[2], lo[2]; // lane-phase role mask of this lane's own registers (even: & EV, odd: (& FF) | ONE)
 };
 
 // one trellis step at compile-time phase T.  Cbase byte (cA<<1|cB) = metric of the even candidate for a predecessor of
 // that class; the complement class (3 - index) is the odd candidate's.
+// Two renderings of the same arithmetic; which one is faster depends on how often the per-group bookkeeping runs, i.e. on the
+// code rate (measured, profiles/README.md): style A keeps the ALU pipe lighter (R = 1/2), style B issues fewer instructions (R = 2/3, 3/4).
+//   style A: the survivor marks are taken out of the fresh metrics once per step (LOP3 + IMAD-side subtract / shifted accumulate), the
+//            even / odd roles of the next step are plain adds; address = lane | half | reg.
+//   style B: the role masks of the next step replace the stale marks (one LOP3 per input register), the 16 marks of a lane are gathered
+//            with four PRMTs; address = lane | reg bit 0 | half | reg bits 2,1 so that the gathered word is already in address order.
 template <int T>
-__device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
+__device__ __forceinline__ void vq_step_a(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
     // R comes in with the survivor marks already removed (vq_commit); the odd role is then a plain add of the mark.
     const uint32_t Cb = __byte_perm(Cbase, 0, L.swz[T]);
     const uint32_t ONE = 0x01000100u;
     if (T <= 1) {                                       // pair = partner lane (xor 2 at T=0, xor 1 at T=1)
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            const int c0 = vq_scls(T, r, 0), c1 = vq_scls(T, r, 1);
+            const int c0 = vq_scls<0>(T, r, 0), c1 = vq_scls<0>(T, r, 1);
             uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
             uint32_t own = R[r] + L.lo[T];              // marked according to this lane's role; the partner did the same
             uint32_t Z = __shfl_xor_sync(qmask, own, T == 0 ? 2 : 1);
@@ -64,7 +76,7 @@ __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const 
     } else if (T == 2) {                                // pair = the two halves of each register
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            const int c = vq_scls(2, r, 0);             // class of p (low half); the high half is p+32: complement
+            const int c = vq_scls<0>(2, r, 0);             // class of p (low half); the high half is p+32: complement
             uint32_t ab = __byte_perm(Cb, 0, vq_sel(c, 3 - c)), ba = __byte_perm(Cb, 0, vq_sel(3 - c, c));
             uint32_t m = R[r] + 0x01000000u;            // low half = even role, high half = odd role
             uint32_t t1 = m + ab, t2 = m + ba;          // t1 = [p+a, p32+b], t2 = [p+b, p32+a]
@@ -75,7 +87,7 @@ __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const 
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             if (r & d) continue;
-            const int c0 = vq_scls(T, r, 0), c1 = vq_scls(T, r, 1);
+            const int c0 = vq_scls<0>(T, r, 0), c1 = vq_scls<0>(T, r, 1);
             uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
             uint32_t X = R[r], Y = R[r + d] + ONE;
             R[r]     = __vminu2(X + av, Y + bv);
@@ -87,11 +99,65 @@ __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const 
 // lane: bit 8h + r.  One LOP3 per register; the subtraction and the gather (m << r accumulated) are IMADs on the FMA pipe.
 // The bytes below the metrics ("dead" bytes) collect the wrap carries of the low halves; they never decide a compare
 // (the candidates' marks differ) and are wiped at every normalisation, long before they could overflow.
-__device__ __forceinline__ uint32_t vq_commit_marks(uint32_t (&R)[8]) {
+__device__ __forceinline__ uint32_t vq_commit_marks_a(uint32_t (&R)[8]) {
     uint32_t acc = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) { const uint32_t m = R[r] & 0x01000100u; R[r] -= m; acc = m * (1u << r) + acc; }
     return __byte_perm(acc, 0, 0x4431);                 // [byte 1, byte 3, 0, 0]
+}
+template <int T>
+__device__ __forceinline__ void vq_step_b(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
+    // Metrics carry the survivor mark of the previous step in bit 8 of each half; the role masks below replace it (and wipe the
+    // byte under the metric, where the uint8 wrap carries land) in the same LOP3.
+    const uint32_t Cb = __byte_perm(Cbase, 0, L.swz[T]);
+    const uint32_t EV = 0xFE00FE00u, FF = 0xFF00FF00u, ONE = 0x01000100u;
+    if (T <= 1) {                                       // pair = partner lane (xor 2 at T=0, xor 1 at T=1)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int c0 = vq_scls<1>(T, r, 0), c1 = vq_scls<1>(T, r, 1);
+            uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
+            uint32_t own = (R[r] & L.lm[T]) | L.lo[T];  // marked according to this lane's role; the partner did the same
+            uint32_t Z = __shfl_xor_sync(qmask, own, T == 0 ? 2 : 1);
+            R[r] = __vminu2(own + av, Z + bv);
+        }
+    } else if (T == 3) {                                // pair = the two halves of each register (address bit 2)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int c = vq_scls<1>(3, r, 0);             // class of p (low half); the high half is p+32: complement
+            uint32_t aa = __byte_perm(Cb, 0, vq_sel(c, c)), bb = __byte_perm(Cb, 0, vq_sel(3 - c, 3 - c));
+            uint32_t m = (R[r] & 0xFF00FE00u) | 0x01000000u;              // [p even role, p32 odd role]
+            uint32_t y = __byte_perm(m, 0, 0x1032);     // [p32, p]
+            R[r] = __vminu2(m + aa, y + bb);            // [min(p+a, p32+b), min(p32+a, p+b)] = new states 2p, 2p+1
+        }
+    } else {                                            // pair = register r ^ d inside the lane (address bits 3, 1, 0)
+        const int d = T == 2 ? 1 : T == 4 ? 4 : 2;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (r & d) continue;
+            const int c0 = vq_scls<1>(T, r, 0), c1 = vq_scls<1>(T, r, 1);
+            uint32_t av = __byte_perm(Cb, 0, vq_sel(c0, c1)), bv = __byte_perm(Cb, 0, vq_sel(3 - c0, 3 - c1));
+            uint32_t X = R[r] & EV, Y = (R[r + d] & FF) | ONE;
+            R[r]     = __vminu2(X + av, Y + bv);
+            R[r + d] = __vminu2(X + bv, Y + av);
+        }
+    }
+}
+// The 16 survivor marks of this lane (bit 8 of each half of the fresh metrics) as one word, bit index = vq_low4(r, h).
+// Four PRMTs line the eight metric bytes of two registers up ([R.b1, R.b3, R'.b1, R'.b3]); bit 0 of every byte is a mark, pair p
+// goes to bit p of its byte by three shift + bit-select steps, and the four nibbles are squeezed into 16 bits.
+__device__ __forceinline__ uint32_t vq_commit_marks_b(const uint32_t (&R)[8]) {
+    const uint32_t p0 = __byte_perm(R[0], R[1], 0x7531), p1 = __byte_perm(R[2], R[3], 0x7531);
+    const uint32_t p2 = __byte_perm(R[4], R[5], 0x7531), p3 = __byte_perm(R[6], R[7], 0x7531);
+    uint32_t t = (p0 & 0x01010101u) | ((p1 << 1) & ~0x01010101u);
+    t = (t & 0x03030303u) | ((p2 << 2) & ~0x03030303u);
+    t = (t & 0x07070707u) | ((p3 << 3) & ~0x07070707u);
+    t &= 0x0F0F0F0Fu;
+    t |= t >> 4;                                        // bytes 0 and 2 now hold two nibbles each
+    return __byte_perm(t, 0, 0x4420);                   // [byte 0, byte 2, 0, 0]
+}
+template <int T, int S>
+__device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
+    if (S) vq_step_b<T>(R, Cbase, L, qmask); else vq_step_a<T>(R, Cbase, L, qmask);
 }
 // branch-metric byte vectors (byte index = cA<<1 | cB) from soft values in bytes B0 (A) and B0+1 (B) of the packed word w
 __device__ __forceinline__ int vq_dp4a_us(uint32_t a, int b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
@@ -133,6 +199,7 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         L = fi.length; nsoft = fi.soft_bytes;
     } else if (active) active = job.code_rate == (uint32_t)CODE_RATE;
     if (!active) return;                                // whole quad leaves together (no block-wide sync below)
+    constexpr int S = CODE_RATE == CR_12 ? 0 : 1;       // arithmetic style (see vq_step)
     constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
     constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
     const uint32_t depth = job.depth, look = job.lookahead;
@@ -146,9 +213,10 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         LC.swz[t] = (unsigned)((0 ^ lc) | ((1 ^ lc) << 4) | ((2 ^ lc) << 8) | ((3 ^ lc) << 12));
     }
     {
-        const uint32_t ONE = 0x01000100u;
+        const uint32_t EV = 0xFE00FE00u, FF = 0xFF00FF00u, ONE = 0x01000100u;
         int b0 = (q >> 1) & 1, b1 = q & 1;              // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
-        LC.lo[0] = b0 ? ONE : 0u; LC.lo[1] = b1 ? ONE : 0u;
+        LC.lm[0] = b0 ? FF : EV; LC.lo[0] = b0 ? ONE : 0u;
+        LC.lm[1] = b1 ? FF : EV; LC.lo[1] = b1 ? ONE : 0u;
     }
     // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address
     uint32_t R[8];
@@ -159,8 +227,8 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
     uint32_t tb = 0, ob = 0;                            // tb = trellis time at the start of the current 6-step chunk
     uint32_t wcol = 0;                                  // ring slot of column tb + 1 (multiple of 6)
     uint32_t next_tb = min(end, depth + look + 6u);     // first time a traceback can fire (viterbi.hpp:182-203)
-    uint32_t lastdec = 0;                               // this lane's 16 survivor marks of the newest column
     uint32_t desc_count = 0, desc_reg = 0, byte_count = 0, crc = 0xFFFFFFFFu, fcs = 0, verdict = E_SUCCESS, nraw = 0;
+    uint32_t lastdec = 0;                               // style A: this lane's 16 survivor marks of the newest column
     bool done = false;
     uint16_t* ring16 = (uint16_t*)&s_ring[0][0] + fb * 4 + q;      // + slot * (4 * SB_VQ_FR)
     uint32_t pos_soft = 0;
@@ -168,13 +236,13 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
     // normalisation + traceback triggers, evaluated after every puncture group at time t (column t sits in ring slot cslot);
     // tm = t % 6 is a compile-time constant in the main loop
     auto after_group = [&](const uint32_t t, const uint32_t tm, const uint32_t cslot) {
-        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465 (marks are already out: min & 0xFE unchanged)
+        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465
             uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
             m = min(m & 0xFFFFu, m >> 16) >> 8;         // smallest metric byte of this lane
             m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            const uint32_t mv = m * 0x01000100u;
+            const uint32_t mv = (m & 0xFEu) * 0x01000100u;
 #pragma unroll
-            for (int r = 0; r < 8; r++) R[r] = (R[r] - mv) & 0xFF00FF00u;     // every metric byte >= m: no borrow; dead bytes wiped
+            for (int r = 0; r < 8; r++) R[r] = S ? R[r] - mv : (R[r] - mv) & 0xFF00FF00u;   // every metric byte >= m: no borrow; style A wipes its carry bytes here
         }
         if (t < next_tb) return;
         uint32_t nout, la;                              // viterbi.hpp:182-203
@@ -187,8 +255,9 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
             for (int r = 0; r < 8; r++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const uint32_t v = (h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu)) | ((lastdec >> (8 * h + r)) & 1u);
-                    const uint32_t A = ((uint32_t)q << 4) | (h << 3) | r;
+                    uint32_t v = h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu);            // metric byte, survivor mark included ...
+                    if (!S) v |= (lastdec >> (8 * h + r)) & 1u;                       // ... which style A keeps in the decision word
+                    const uint32_t A = ((uint32_t)q << 4) | (uint32_t)vq_low4<S>(r, h);
                     const uint32_t n = ((A << tm) | (A >> (6u - tm))) & 63u;   // state index of this slot at time t
                     best = min(best, (v << 16) | (n << 8) | A);
                 }
@@ -262,9 +331,9 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         next_tb = min(end, ob + depth + look + 6u);
         if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
     };
-    // store the survivor bits of column tb + k + 1 (slot wcol + k); marks leave the metrics here
+    // store the survivor bits of column tb + k + 1 (slot wcol + k)
     auto commit = [&](const uint32_t k) {
-        lastdec = vq_commit_marks(R);
+        if (S) lastdec = vq_commit_marks_b(R); else lastdec = vq_commit_marks_a(R);
         ring16[(wcol + k) * (4 * SB_VQ_FR)] = (uint16_t)lastdec;
     };
 
@@ -286,26 +355,26 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
         uint32_t n0, n1, n2; fetch(pos_soft + CHUNK_BYTES, n0, n1, n2);
         pos_soft += CHUNK_BYTES;
         if (CODE_RATE == CR_12) {
-            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0); after_group(tb + 1, 1, wcol);
-            vq_step<1>(R, vq_bm_ab<2>(w0), LC, QM); commit(1); after_group(tb + 2, 2, wcol + 1);
-            vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); commit(2); after_group(tb + 3, 3, wcol + 2);
-            vq_step<3>(R, vq_bm_ab<2>(w1), LC, QM); commit(3); after_group(tb + 4, 4, wcol + 3);
-            vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); commit(4); after_group(tb + 5, 5, wcol + 4);
-            vq_step<5>(R, vq_bm_ab<2>(w2), LC, QM); commit(5); after_group(tb + 6, 0, wcol + 5);
+            vq_step<0, S>(R, vq_bm_ab<0>(w0), LC, QM); commit(0); after_group(tb + 1, 1, wcol);
+            vq_step<1, S>(R, vq_bm_ab<2>(w0), LC, QM); commit(1); after_group(tb + 2, 2, wcol + 1);
+            vq_step<2, S>(R, vq_bm_ab<0>(w1), LC, QM); commit(2); after_group(tb + 3, 3, wcol + 2);
+            vq_step<3, S>(R, vq_bm_ab<2>(w1), LC, QM); commit(3); after_group(tb + 4, 4, wcol + 3);
+            vq_step<4, S>(R, vq_bm_ab<0>(w2), LC, QM); commit(4); after_group(tb + 5, 5, wcol + 4);
+            vq_step<5, S>(R, vq_bm_ab<2>(w2), LC, QM); commit(5); after_group(tb + 6, 0, wcol + 5);
         } else if (CODE_RATE == CR_34) {
-            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
-            vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  commit(1);
-            vq_step<2>(R, vq_bm_b<3>(w0), LC, QM);  commit(2); after_group(tb + 3, 3, wcol + 2);
-            vq_step<3>(R, vq_bm_ab<0>(w1), LC, QM); commit(3);
-            vq_step<4>(R, vq_bm_a<2>(w1), LC, QM);  commit(4);
-            vq_step<5>(R, vq_bm_b<3>(w1), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
+            vq_step<0, S>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
+            vq_step<1, S>(R, vq_bm_a<2>(w0), LC, QM);  commit(1);
+            vq_step<2, S>(R, vq_bm_b<3>(w0), LC, QM);  commit(2); after_group(tb + 3, 3, wcol + 2);
+            vq_step<3, S>(R, vq_bm_ab<0>(w1), LC, QM); commit(3);
+            vq_step<4, S>(R, vq_bm_a<2>(w1), LC, QM);  commit(4);
+            vq_step<5, S>(R, vq_bm_b<3>(w1), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
         } else {
-            vq_step<0>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
-            vq_step<1>(R, vq_bm_a<2>(w0), LC, QM);  commit(1); after_group(tb + 2, 2, wcol + 1);
-            vq_step<2>(R, vq_bm_ab<0>(w1), LC, QM); commit(2);
-            vq_step<3>(R, vq_bm_a<2>(w1), LC, QM);  commit(3); after_group(tb + 4, 4, wcol + 3);
-            vq_step<4>(R, vq_bm_ab<0>(w2), LC, QM); commit(4);
-            vq_step<5>(R, vq_bm_a<2>(w2), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
+            vq_step<0, S>(R, vq_bm_ab<0>(w0), LC, QM); commit(0);
+            vq_step<1, S>(R, vq_bm_a<2>(w0), LC, QM);  commit(1); after_group(tb + 2, 2, wcol + 1);
+            vq_step<2, S>(R, vq_bm_ab<0>(w1), LC, QM); commit(2);
+            vq_step<3, S>(R, vq_bm_a<2>(w1), LC, QM);  commit(3); after_group(tb + 4, 4, wcol + 3);
+            vq_step<4, S>(R, vq_bm_ab<0>(w2), LC, QM); commit(4);
+            vq_step<5, S>(R, vq_bm_a<2>(w2), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
         }
         tb += 6; wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING;
         w0 = n0; w1 = n1; w2 = n2;
@@ -315,9 +384,9 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
     {
         uint32_t tm = 0, k = 0;                         // t % 6 (the main loop always leaves it at 0), steps into the chunk at tb
         auto step_rt = [&](uint32_t Cbase) {
-            switch (tm) { case 0: vq_step<0>(R, Cbase, LC, QM); break; case 1: vq_step<1>(R, Cbase, LC, QM); break;
-                          case 2: vq_step<2>(R, Cbase, LC, QM); break; case 3: vq_step<3>(R, Cbase, LC, QM); break;
-                          case 4: vq_step<4>(R, Cbase, LC, QM); break; default: vq_step<5>(R, Cbase, LC, QM); }
+            switch (tm) { case 0: vq_step<0, S>(R, Cbase, LC, QM); break; case 1: vq_step<1, S>(R, Cbase, LC, QM); break;
+                          case 2: vq_step<2, S>(R, Cbase, LC, QM); break; case 3: vq_step<3, S>(R, Cbase, LC, QM); break;
+                          case 4: vq_step<4, S>(R, Cbase, LC, QM); break; default: vq_step<5, S>(R, Cbase, LC, QM); }
             commit(k); k++;
             tm = tm == 5 ? 0 : tm + 1;
         };
