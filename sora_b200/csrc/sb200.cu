@@ -753,7 +753,7 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
                                 int code_rate, uint32_t frame_len_bytes, uint32_t depth, uint32_t lookahead,
                                 uint8_t* out, uint64_t out_stride, void* cuda_stream) {
     if (!h || !soft || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
-    if (code_rate < 0 || code_rate > 2 || depth == 0 || (depth & 7) || depth + lookahead + 8 > SB_VQ_RING || depth > 256)
+    if (code_rate < 0 || code_rate > 2 || depth == 0 || (depth & 7) || depth + lookahead + 8 > 288 || depth > 256)
         return h->fail(SB200_E_INVALID, "unsupported code_rate/depth/lookahead");
     if (soft_stride < nsoft || out_stride < frame_len_bytes + 2ull) return h->fail(SB200_E_INVALID, "stride too small");
     if (nblocks == 0) return SB200_OK;

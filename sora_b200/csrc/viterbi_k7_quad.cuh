@@ -30,7 +30,8 @@ namespace sb {
 
 #define SB_VQ_WARPS 1                      // warps per CTA
 #define SB_VQ_FR (8 * SB_VQ_WARPS)         // code blocks per CTA
-#define SB_VQ_RING 288                     // columns kept per code block: needs depth + lookahead + 4 (283 for 256/24); multiple of 6
+#define SB_VQ_RING_MAX 294                     // columns kept per code block: depth + lookahead + 7 (287 for 256/24) + up to 5 written before a
+                                           // recorded traceback is served; multiple of 6
 
 __host__ __device__ constexpr int vq_rol6(int a, int t) { return ((a << t) | (a >> (6 - t))) & 63; }
 __host__ __device__ constexpr int vq_cls(int p) {            // (cA << 1) | cB of predecessor index p (bit 5 ignored)
@@ -180,6 +181,7 @@ template <int CODE_RATE>
 __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t* __restrict__ soft, uint64_t soft_stride,
         uint32_t nframes, const FrameInfo* __restrict__ info, VitJob job, DevTables T,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t* __restrict__ status_out, uint32_t* __restrict__ crc_out) {
+    constexpr uint32_t SB_VQ_RING = CODE_RATE == CR_12 ? 294u : 288u;   // 6 columns of slack only where tracebacks are deferred (see DEFER)
     __shared__ unsigned long long s_ring[SB_VQ_RING][SB_VQ_FR];    // column c lives in slot (c - 1) mod SB_VQ_RING
     __shared__ uint32_t s_crc[256];                    // CRC-32 (reflected 0xEDB88320, core/inc/CRC32.h:76)
     __shared__ uint8_t s_scr[128];
@@ -235,39 +237,18 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
 
     // normalisation + traceback triggers, evaluated after every puncture group at time t (column t sits in ring slot cslot);
     // tm = t % 6 is a compile-time constant in the main loop
-    auto after_group = [&](const uint32_t t, const uint32_t tm, const uint32_t cslot) {
-        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465
-            uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
-            m = min(m & 0xFFFFu, m >> 16) >> 8;         // smallest metric byte of this lane
-            m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            const uint32_t mv = (m & 0xFEu) * 0x01000100u;
-#pragma unroll
-            for (int r = 0; r < 8; r++) R[r] = S ? R[r] - mv : (R[r] - mv) & 0xFF00FF00u;   // every metric byte >= m: no borrow; style A wipes its carry bytes here
-        }
-        if (t < next_tb) return;
-        uint32_t nout, la;                              // viterbi.hpp:182-203
-        if (t >= end) { nout = end - ob - 6u; la = t - end; }
-        else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
-        if (nout) {                                     // uniform inside the quad
-            // best state: smallest (metric incl. mark, state index) over the 64 slots (viterbicore.h:468-520)
-            uint32_t best = 0xFFFFFFFFu;                // (metric | mark) << 16 | state index << 8 | address
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t v = h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu);            // metric byte, survivor mark included ...
-                    if (!S) v |= (lastdec >> (8 * h + r)) & 1u;                       // ... which style A keeps in the decision word
-                    const uint32_t A = ((uint32_t)q << 4) | (uint32_t)vq_low4<S>(r, h);
-                    const uint32_t n = ((A << tm) | (A >> (6u - tm))) & 63u;   // state index of this slot at time t
-                    best = min(best, (v << 16) | (n << 8) | A);
-                }
-            }
-            best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
-            __syncwarp(QM);
+    // With DEFER, traceback requests are only recorded when they fire (best state, column, window) and carried out once per 6-step chunk: the
+    // pointer chase + descrambler + CRC code then exists once instead of once per group position, which keeps the loop inside the
+    // instruction cache.  The ring has 6 columns of slack for the steps that run before the request is served.
+    constexpr bool DEFER = CODE_RATE == CR_12;          // measured: pays at R = 1/2 (a group after every step), not at 2/3 and 3/4
+    uint32_t pA[2], pcol[2], pcm[2], pla[2], pnout[2], npend = 0;
+    // windowed traceback from slot A0 of the column in ring slot col0 (column phase cm0), then descrambler / CRC-32 / verdict
+    auto do_traceback = [&](const uint32_t A0, const uint32_t col0, const uint32_t cm0, const uint32_t la, const uint32_t nout) {
+        __syncwarp(QM);
             if (q == 0) {
                 // traceback in address space: survivor bit d of slot A at column c = bit A of that column's word;
                 // the predecessor slot is A with bit (6 - c%6)%6 replaced by d; d is also the decoded bit of column c.
-                uint32_t A = best & 63u, col = cslot, cm = tm, todo = la + nout;
+                uint32_t A = A0, col = col0, cm = cm0, todo = la + nout;
                 uint32_t fifo = 0; int cnt = -(int)la;                      // the first `la` bits are only looked through; at most 13 bits wait
                 uint8_t* win = s_win[fb]; uint32_t wpos = nout >> 3;        // bytes come out last-first; the sink needs them first-first
                 auto emit = [&]() { while (cnt >= 8) { win[--wpos] = (uint8_t)(fifo >> (cnt - 8)); cnt -= 8; } };
@@ -324,12 +305,72 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
                 }
                 nraw += nbytes;
             }
+        __syncwarp(QM);
+    };
+    auto after_group = [&](const uint32_t t, const uint32_t tm, const uint32_t cslot) {
+        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465
+            uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
+            m = min(m & 0xFFFFu, m >> 16) >> 8;         // smallest metric byte of this lane
+            m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
+            const uint32_t mv = (m & 0xFEu) * 0x01000100u;
+#pragma unroll
+            for (int r = 0; r < 8; r++) R[r] = S ? R[r] - mv : (R[r] - mv) & 0xFF00FF00u;   // every metric byte >= m: no borrow; style A wipes its carry bytes here
+        }
+        if (t < next_tb) return;
+        uint32_t nout, la;                              // viterbi.hpp:182-203
+        if (t >= end) { nout = end - ob - 6u; la = t - end; }
+        else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
+        if (nout) {                                     // uniform inside the quad
+            // best state: smallest (metric incl. mark, state index) over the 64 slots (viterbicore.h:468-520).  Each half becomes the
+            // 16-bit key (metric | mark) << 8 | state index (the part of the index that comes from reg / half is a constant at this
+            // phase); a SIMD min tree, then the lane part of the index, then the quad.
+            uint32_t n;
+            if constexpr (DEFER) {
+                uint32_t k2 = 0xFFFFFFFFu;
+    #pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    constexpr uint32_t dummy = 0; (void)dummy;
+                    const uint32_t n0 = (uint32_t)(((vq_low4<S>(r, 0) << tm) | (vq_low4<S>(r, 0) >> (6u - tm))) & 63u);
+                    const uint32_t n1 = (uint32_t)(((vq_low4<S>(r, 1) << tm) | (vq_low4<S>(r, 1) >> (6u - tm))) & 63u);
+                    uint32_t key = (R[r] & 0xFF00FF00u) | (n1 << 16) | n0;
+                    if (!S) key |= (((lastdec >> r) & 1u) << 8) | (((lastdec >> (8 + r)) & 1u) << 24);   // style A keeps the marks in the decision word
+                    k2 = __vminu2(k2, key);
+                }
+                uint32_t best = min(k2 & 0xFFFFu, k2 >> 16);
+                const uint32_t nl = (((uint32_t)q << 4 << tm) | ((uint32_t)q << 4 >> (6u - tm))) & 63u;
+                best |= nl;
+                best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
+                n = best & 63u;
+            } else {
+                uint32_t best = 0xFFFFFFFFu;            // (metric | mark) << 16 | state index << 8 | address
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t v = h ? (R[r] >> 24) : ((R[r] >> 8) & 0xFFu);      // metric byte, survivor mark included (style B)
+                        const uint32_t A = ((uint32_t)q << 4) | (uint32_t)vq_low4<S>(r, h);
+                        const uint32_t ns = ((A << tm) | (A >> (6u - tm))) & 63u;         // state index of this slot at time t
+                        best = min(best, (v << 16) | (ns << 8) | A);
+                    }
+                }
+                best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
+                n = (best >> 8) & 63u;
+            }
+            const uint32_t A0 = ((n >> tm) | (n << (6u - tm))) & 63u;
+            if (DEFER) { if (npend < 2u) { pA[npend] = A0; pcol[npend] = cslot; pcm[npend] = tm; pla[npend] = la; pnout[npend] = nout; } npend++; }
+            else do_traceback(A0, cslot, tm, la, nout);
             ob += nout;
-            __syncwarp(QM);
         }
         if (ob + 6u >= end && t >= end) done = true;
         next_tb = min(end, ob + depth + look + 6u);
         if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
+    };
+    auto serve_tracebacks = [&]() {
+        if constexpr (DEFER) {
+            if (npend == 0) return;                     // uniform inside the quad
+            for (uint32_t pi = 0; pi < npend && pi < 2u; pi++) do_traceback(pA[pi], pcol[pi], pcm[pi], pla[pi], pnout[pi]);
+            npend = 0;
+        }
     };
     // store the survivor bits of column tb + k + 1 (slot wcol + k)
     auto commit = [&](const uint32_t k) {
@@ -376,6 +417,7 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
             vq_step<4, S>(R, vq_bm_ab<0>(w2), LC, QM); commit(4);
             vq_step<5, S>(R, vq_bm_a<2>(w2), LC, QM);  commit(5); after_group(tb + 6, 0, wcol + 5);
         }
+        serve_tracebacks();
         tb += 6; wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING;
         w0 = n0; w1 = n1; w2 = n2;
     }
@@ -399,6 +441,7 @@ __global__ void __launch_bounds__(32 * SB_VQ_WARPS) k_viterbi_quad(const uint8_t
             if (GSTEPS >= 2) step_rt(vq_bm_a<2>(w));
             if (GSTEPS >= 3) step_rt(vq_bm_b<3>(w));
             after_group(tb + k, tm, wcol + k - 1);
+            serve_tracebacks();
             if (k == 6) { k = 0; tb += 6; wcol += 6; if (wcol >= SB_VQ_RING) wcol -= SB_VQ_RING; }
         }
     }
