@@ -257,6 +257,8 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     const uint32_t want = iq_dev ? h->chunk_frames_device : h->chunk_frames;
     const uint32_t chunk = (want == 0 || tapping || nframes <= want) ? nframes : want;
     const bool pipelined = chunk < nframes;
+    const bool res_dev_all = is_device_ptr(res), out_dev_all = out_bytes && is_device_ptr(out_bytes);
+    sb200_frame_result* d_res_all = res_dev_all ? res : (sb200_frame_result*)h->res.p;
     CK(cudaEventRecord(h->ev0, st));
     if (!pipelined) {
         const uint32_t* d_iq;
@@ -293,17 +295,35 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
             }
             int rc = launch_chunk(h, base, d_off, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false);
             if (rc != SB200_OK) return rc;
+            // results of this chunk go back while the next chunks are still coming in (PCIe is full duplex): only the last chunk's
+            // device-to-host copy is left exposed at the end of the call
+            const uint32_t n = f1 - f0;
+            k_pack_results<<<(n + 255) / 256, 256, 0, st>>>((const FrameInfo*)h->info.p + f0, (const uint32_t*)h->status.p + f0, (const uint32_t*)h->crc.p + f0, n, d_res_all + f0);
+            h->launches += 1;
+            if (out_bytes && out_stride && !out_dev_all) {
+                const size_t w = out_stride < row ? out_stride : row;
+                CK(cudaMemcpy2DAsync(out_bytes + (size_t)f0 * out_stride, out_stride, (const uint8_t*)h->out.p + (size_t)f0 * row, row, w, n, cudaMemcpyDeviceToHost, st));
+            }
+            if (!res_dev_all) CK(cudaMemcpyAsync(res + f0, d_res_all + f0, n * sizeof(sb200_frame_result), cudaMemcpyDeviceToHost, st));
         }
         h->nk = 0;
     }
-    const bool res_dev = is_device_ptr(res);
-    sb200_frame_result* d_res = res_dev ? res : (sb200_frame_result*)h->res.p;
-    k_pack_results<<<(nframes + 255) / 256, 256, 0, st>>>((const FrameInfo*)h->info.p, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
-    if (!pipelined) CK(cudaEventRecord(h->evk[4], st));
+    const bool res_dev = res_dev_all;
+    sb200_frame_result* d_res = d_res_all;
+    if (!pipelined) {
+        k_pack_results<<<(nframes + 255) / 256, 256, 0, st>>>((const FrameInfo*)h->info.p, (const uint32_t*)h->status.p, (const uint32_t*)h->crc.p, nframes, d_res);
+        h->launches += 1;
+        CK(cudaEventRecord(h->evk[4], st));
+    }
     CK(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->launches += 1;
+    h->timed = true;
     CK(cudaGetLastError());
     bool host_out = false;
+    if (pipelined) {                                    // everything that goes to the host was already queued per chunk
+        if (out_bytes && out_stride && out_dev_all) { const size_t w = out_stride < row ? out_stride : row; CK(cudaMemcpy2DAsync(out_bytes, out_stride, h->out.p, row, w, nframes, cudaMemcpyDeviceToDevice, st)); }
+        if ((out_bytes && out_stride && !out_dev_all) || !res_dev_all) CK(cudaStreamSynchronize(st));
+        return SB200_OK;
+    }
     if (out_bytes && out_stride) {
         const size_t w = out_stride < row ? out_stride : row;
         const bool od = is_device_ptr(out_bytes);
