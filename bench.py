@@ -117,7 +117,7 @@ def main():
     ap.add_argument("--frames", type=int, default=65536, help="capture slots per step per GPU (BASELINE config #2: 65536)")
     ap.add_argument("--unique", type=int, default=2048, help="distinct synthetic frames generated on the host, tiled to --frames in HBM")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--chunk", type=int, default=8192, help="slots per pipeline chunk inside the library (0 = no chunking)")
+    ap.add_argument("--chunk", type=int, default=4096, help="slots per pipeline chunk inside the library (0 = no chunking)")
     ap.add_argument("--chunk-device", type=int, default=0, help="slots per pipeline chunk for device-resident IQ (0 = one pass; >0 overlaps the front end of chunk k+1 with the Viterbi of chunk k)")
     ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
     ap.add_argument("--no-e2e", action="store_true")

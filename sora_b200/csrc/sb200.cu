@@ -63,7 +63,7 @@ struct sb200_handle {
     bool timed = false;
     uint64_t launches = 0;
     uint32_t chunk_frames_device = 0;
-    uint32_t chunk_frames = 8192;                      // slots per pipeline chunk (0 = one chunk, everything on the caller's stream)
+    uint32_t chunk_frames = 4096;                      // slots per pipeline chunk (0 = one chunk, everything on the caller's stream)
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
