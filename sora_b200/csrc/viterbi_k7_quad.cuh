@@ -10,11 +10,10 @@
 //     survivor mark costs one LOP3 per *input* register (even role: & 0xFE00FE00, odd role: (& 0xFF00FF00) | 0x01000100).
 //     The dead bytes are cleared by those masks every step and cannot decide a compare: the candidates' marks differ.
 //   * The trellis is processed IN PLACE: butterfly (p, p+32) -> (2p, 2p+1) writes its results into the slots it read.
-//     A slot's physical address is A = lane[2] | half[1] | reg[3]; its state index at time t is rol6(A, t mod 6), so the
-//     pairing dimension walks through the address bits with period 6:
-//         t%6 = 0,1 -> partner lane (one SHFL.BFLY per register: the path-metric exchange)
-//         t%6 = 2   -> the two halves of one register
-//         t%6 = 3,4,5 -> another register of the same lane (pure SIMD, no data movement).
+//     A slot's physical address is A = lane[2] | four bits made of half[1] and reg[3] (their order depends on the style, see
+//     vq_low4); its state index at time t is rol6(A, t mod 6), so the pairing dimension walks through the address bits with
+//     period 6: two steps pair with a partner lane (one SHFL.BFLY per register: the path-metric exchange), one step pairs the
+//     two halves of each register, three steps pair two registers of the same lane (pure SIMD, no data movement).
 //   * Branch metrics: the 4 possible values of a step are bytes of one register (two IDP4A + two IMAD straight from the
 //     packed soft bytes); each 2-state operand is one PRMT with a compile-time selector.
 //   * Survivor bits: the LSB of every new metric, 16 per lane per step -> one 16-bit word in a [column][block] shared
