@@ -20,6 +20,11 @@
 //     iport COMPLEX16 x 28 x 2 streams (what TMemSamples2 emits, memsource.hpp:189-244), oport uchar x 1;
 //     facades CF_Error, CF_11aRxVector, CF_HTRxVector, CF_RxFrameBuffer, CF_CFOffset.
 //
+//   TB200Dot11aTx<T_CTX, T_NEXT>   source brick replacing both transmit graphs of kernel/bb/demod11/fb11amod_config.hpp:75-158
+//       (TTS11aSrc | TBB11aSrc, T11aSc, TBB11aMRSelect, TConvEncode_*, T11aInterleave*, TMap11a*, T11aAddPilot, TIFFTx, TPackSample16to8):
+//     one Process() modulates the MPDU in CF_TxFrameBuffer at CF_11aTxVector::data_rate_kbps with CF_ScramblerSeed::sc_seed and pushes
+//     the whole PPDU (preamble + SIGNAL + DATA) downstream as COMPLEX8 x 8 bursts, what TPackSample16to8 hands to TModSink.
+//
 // Batching: the GPU decodes whole capture slots.  The brick buffers incoming 28-sample blocks and submits a slot when
 // `slot_samples` samples have arrived or on Flush(); one graph instance therefore trades latency for throughput.  A
 // throughput-oriented caller uses sb200_rx11a_batch directly with thousands of slots per call.
@@ -209,5 +214,44 @@ private:
         }
         error_code = r.status;
         return false;
+    }
+};
+
+
+DEFINE_LOCAL_CONTEXT(TB200Dot11aTx, CF_Error, CF_11aTxVector, CF_TxFrameBuffer, CF_ScramblerSeed);
+template <TSOURCE_ARGS>
+class TB200Dot11aTx : public TSource<TSOURCE_PARAMS> {
+    CTX_VAR_RW(ulong, error_code)
+    CTX_VAR_RO(ushort, frame_length) CTX_VAR_RO(ulong, data_rate_kbps)
+    CTX_VAR_RO(uchar*, mpdu_buf0) CTX_VAR_RO(ushort, mpdu_buf_size0) CTX_VAR_RO(uchar*, mpdu_buf1) CTX_VAR_RO(ushort, mpdu_buf_size1)
+    CTX_VAR_RO(uchar, sc_seed)
+    sb200_handle* h_; std::vector<uchar> mpdu_; std::vector<int8_t> td_;
+public:
+    DEFINE_OPORT(COMPLEX8, 8);
+    REFERENCE_LOCAL_CONTEXT(TB200Dot11aTx);
+    STD_TSOURCE_CONSTRUCTOR(TB200Dot11aTx)
+        BIND_CONTEXT(CF_Error::error_code, error_code)
+        BIND_CONTEXT(CF_11aTxVector::frame_length, frame_length) BIND_CONTEXT(CF_11aTxVector::data_rate_kbps, data_rate_kbps)
+        BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf0, mpdu_buf0) BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf_size0, mpdu_buf_size0)
+        BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf1, mpdu_buf1) BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf_size1, mpdu_buf_size1)
+        BIND_CONTEXT(CF_ScramblerSeed::sc_seed, sc_seed)
+        , h_(nullptr)
+    {
+        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+    }
+    ~TB200Dot11aTx() { sb200_destroy(h_); }
+    STD_TSOURCE_RESET() { }
+    STD_TSOURCE_FLUSH() { }
+    bool Process() override {
+        if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        if (!mpdu_buf0 || (mpdu_buf_size1 > 0 && !mpdu_buf1) || (uint)mpdu_buf_size0 + mpdu_buf_size1 != frame_length) { error_code = E_ERROR_PARAMETER; return false; }   // TBB11aSrc::Preprocess
+        mpdu_.assign(mpdu_buf0, mpdu_buf0 + mpdu_buf_size0); if (mpdu_buf_size1) mpdu_.insert(mpdu_.end(), mpdu_buf1, mpdu_buf1 + mpdu_buf_size1);
+        const uint64_t off = 0; const uint32_t len = frame_length; uint32_t ns = 0; const uchar seed = sc_seed;
+        const size_t cap = 640 + 160 * (size_t)(3 + (len + 7) * 8 / 24) + 64;              // enough for the slowest rate
+        td_.assign(2 * cap, 0);
+        if (sb200_tx11a_batch(h_, mpdu_.empty() ? (const uint8_t*)"" : mpdu_.data(), mpdu_.size() ? mpdu_.size() : 1, &off, &len, &seed, 1, (uint32_t)data_rate_kbps, 0, 8,
+                              td_.data(), cap, &ns, nullptr) != SB200_OK) { error_code = E_ERROR_PARAMETER; return false; }
+        for (uint32_t i = 0; i + 8 <= ns; i += 8) { memcpy(opin().append(), td_.data() + 2 * i, 16); this->Next()->Process(opin()); }
+        return false;                                              // one PPDU per Process(), like TBB11aSrc / TTS11aSrc
     }
 };

@@ -34,6 +34,7 @@ typedef unsigned int uint;
 #include <sys/types.h>                // glibc's `ulong` (64-bit on LP64; the reference's is 32-bit on Windows LLP64 — the
                                       // facade fields only ever hold 32-bit codes, so the wider type is harmless)
 struct COMPLEX16 { short re, im; };   // kernel/core/inc/complex.h
+struct COMPLEX8 { signed char re, im; };
 
 class CF_VOID {};
 

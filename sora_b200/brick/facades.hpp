@@ -6,6 +6,7 @@
 //   CF_CFOffset                  kernel/bb/Brick11/src/ieee80211facade.hpp:168-175
 //   CF_11bRxVector               kernel/bb/Brick11/src/ieee80211facade.hpp:72-76
 //   CF_HTRxVector                kernel/bb/Brick11/src/ieee80211facade.hpp:269-272
+//   CF_11aTxVector, CF_TxFrameBuffer, CF_ScramblerSeed   ieee80211facade.hpp:140-146, 87-92, 116-119
 // plus the E_ERROR_* codes (stdfacade.h:10-12, ieee80211facade.hpp:10-19).
 #pragma once
 #include "brick.hpp"
@@ -57,3 +58,6 @@ public:
 class CF_CFOffset { FACADE_FIELD(short, CFO_est) public: void Reset() { CFO_est() = 0; } };
 class CF_11bRxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(ulong, data_rate_kbps) FACADE_FIELD(ulong, crc32) };
 class CF_HTRxVector { FACADE_FIELD(ushort, ht_frame_length) FACADE_FIELD(ulong, ht_frame_mcs) };
+class CF_11aTxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(ulong, data_rate_kbps) FACADE_FIELD(ulong, crc32) FACADE_FIELD(ushort, coding_rate) };
+class CF_TxFrameBuffer { FACADE_FIELD(uchar*, mpdu_buf0) FACADE_FIELD(ushort, mpdu_buf_size0) FACADE_FIELD(uchar*, mpdu_buf1) FACADE_FIELD(ushort, mpdu_buf_size1) };
+class CF_ScramblerSeed { FACADE_FIELD(uchar, sc_seed) };
