@@ -146,6 +146,13 @@ def test_abi_exports_every_declared_symbol():
     for name in legacy:
         assert hasattr(lib, name), name
 
+def test_brick_adaptors_compile(tmp_path):
+    """The header-only adaptors (11a/b/n receive, 11a transmit) instantiate against the BRICK contract with plain g++."""
+    obj = str(tmp_path / "tu.o")
+    subprocess.check_call(["g++", "-std=c++17", "-O0", "-Wall", "-I", os.path.join(ROOT, "sora_b200", "brick"), "-c",
+                           os.path.join(ROOT, "tests", "cpp", "brick_adaptors_tu.cpp"), "-o", obj])
+    assert os.path.getsize(obj) > 0
+
 def test_product_never_touches_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sora_b200")):
         for f in files:
