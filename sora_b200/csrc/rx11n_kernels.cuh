@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(128) k_sync11n(const uint32_t* __restrict__ iq
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const uint32_t* x[2] = {iq0 + off[f], iq1 + off[f]};
+    const bool al16 = ((((uintptr_t)x[0]) | ((uintptr_t)x[1])) & 15u) == 0;   // a vector = 8 words = two aligned 128-bit loads then
     const uint32_t nvec = (len[f] / 28u) * 28u / 8u;
     int Rre[2] = {0, 0}, Rim[2] = {0, 0}, es[2] = {0, 0}, es64[2] = {0, 0};
     unsigned sense = 0; bool peak_found = false; int peak_count = 0;
@@ -101,15 +102,25 @@ __global__ void __launch_bounds__(128) k_sync11n(const uint32_t* __restrict__ iq
             if (timeout) { sense = 0; peak_found = false; peak_count = 0; timeout = false; }
             cur_blk = blk;
         }
+        // the four samples of this vector and of the vectors 32, 64 and 96 samples back, both antennas: sixteen 128-bit loads issued together
+        uint32_t w[2][4][4];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int tp = 0; tp < 4; tp++) {
+                if (4u * v >= 32u * tp) {
+                    const uint32_t* p = x[a] + 2u * (4u * v - 32u * tp);
+                    if (al16) { const uint4 lo = __ldg((const uint4*)p), hi = __ldg((const uint4*)p + 1); w[a][tp][0] = lo.x; w[a][tp][1] = lo.z; w[a][tp][2] = hi.x; w[a][tp][3] = hi.z; }
+                    else { w[a][tp][0] = __ldg(p); w[a][tp][1] = __ldg(p + 2); w[a][tp][2] = __ldg(p + 4); w[a][tp][3] = __ldg(p + 6); }
+                } else w[a][tp][0] = w[a][tp][1] = w[a][tp][2] = w[a][tp][3] = 0;
+            }
+#pragma unroll
         for (uint32_t k = 0; k < 4; k++) {
+            if (detect != 0xFFFFFFFFu) break;
             const uint32_t n = 4u * v + k;
 #pragma unroll
             for (int a = 0; a < 2; a++) {
-                const cs16 z = mk(0, 0);
-                const cs16 c0 = unpack(__ldg(x[a] + 2u * n));
-                const cs16 c1 = n >= 32 ? unpack(__ldg(x[a] + 2u * (n - 32))) : z;
-                const cs16 c2 = n >= 64 ? unpack(__ldg(x[a] + 2u * (n - 64))) : z;
-                const cs16 c3 = n >= 96 ? unpack(__ldg(x[a] + 2u * (n - 96))) : z;
+                const cs16 c0 = unpack(w[a][0][k]), c1 = unpack(w[a][1][k]), c2 = unpack(w[a][2][k]), c3 = unpack(w[a][3][k]);
                 int pr, pi, qr, qi; cmul_conj32(pr, pi, c0, c1); cmul_conj32(qr, qi, c1, c2);      // autocorr.hpp:110-131 (vShift = 5)
                 Rre[a] = wadd(Rre[a], wadd(pr >> 5, -(qr >> 5))); Rim[a] = wadd(Rim[a], wadd(pi >> 5, -(qi >> 5)));
                 const int e0 = wadd(c0.re * c0.re, c0.im * c0.im) >> 5, e1 = wadd(c1.re * c1.re, c1.im * c1.im) >> 5;
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(128) k_sync11n(const uint32_t* __restrict__ iq
                 sense++;
                 if (step && acorr > (energy >> 1)) { sense = 0; peak_count++; peak_found = true; } else peak_count = 0;
             } else if (acorr < (energy >> 3)) {
-                if (peak_count > 96 && peak_count < 160) { detect = v + 1; break; }
+                if (peak_count > 96 && peak_count < 160) { detect = v + 1; continue; }
                 peak_found = false; peak_count = 0;
             } else { peak_count++; if (peak_count > 160) { peak_found = false; peak_count = 0; } }
         }
