@@ -248,11 +248,14 @@ __device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 
 }
 
 #define SB_FRONT_WARPS 4
+#ifndef SB_FRONT_MINB
+#define SB_FRONT_MINB 6           // resident CTAs per SM the register allocation aims at
+#endif
 // Two OFDM symbols are transformed at once: lanes 0-15 run the three radix stages of symbol A, lanes 16-31 those of
 // symbol B (16 butterflies per stage = 16 lanes, so every lane is busy); the first stage consumes the freq-compensated
 // time samples straight from registers.  Only the part behind the FFT (phase compensation from the pilot recurrence)
 // is serial across symbols, and there every lane owns two subcarriers.
-__global__ void __launch_bounds__(32 * SB_FRONT_WARPS) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
+__global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
         const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, FrameInfo* __restrict__ info,
         uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps) {
     __shared__ uint32_t s_fft[SB_FRONT_WARPS][2][64];

@@ -211,7 +211,10 @@ __device__ __forceinline__ cfl cmulf(cfl a, cfl b) {        // vector128.h:1106-
 }
 
 #define SB_FRONT11N_WARPS 4
-__global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS) k_front11n(const uint32_t* __restrict__ iq0, const uint32_t* __restrict__ iq1,
+#ifndef SB_FRONT11N_MINB
+#define SB_FRONT11N_MINB 6         // resident CTAs per SM the register allocation aims at (profiles/README.md, front-end sweep)
+#endif
+__global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS, SB_FRONT11N_MINB) k_front11n(const uint32_t* __restrict__ iq0, const uint32_t* __restrict__ iq1,
         const uint64_t* __restrict__ off, const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, DevTables11n N, const uint16_t* __restrict__ inv_deint48,
         FrameInfo* __restrict__ info, uint8_t* __restrict__ soft_out, uint64_t soft_stride, Taps11n taps) {
     __shared__ uint32_t s_fft[SB_FRONT11N_WARPS][2][64];
