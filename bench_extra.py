@@ -5,6 +5,7 @@
                      bits (max 11a frame, 2500 B), device-resident soft values; coded bits/s and decoded Mbit/s
   --config 11b       config #3: 802.11b 11 Mbps CCK RX chain, PSDU 1500 B, 44 Msps, one frame per slot
   --config tx11a     SURVEY.md §8(f) rank 2: the 802.11a modulator on the device, 54 Mbps / 1500 B frames into config #2's slots
+  --config tx11b     SURVEY.md §8(f) rank 2: the 802.11b modulator on the device, 11 Mbps CCK / 1500 B frames at 44 Msps
   --config 11n       config #4: 802.11n HT-MF 2x2 RX chain at MCS 8, 9, 10, PSDU 1500 B, 2 x 40 Msps, fixed 2x2 channel
 
 Each prints one JSON line per measurement (same timing rules as bench.py: >= 3 warm-ups, CUDA events on the launch
@@ -179,11 +180,52 @@ def bench_tx11a(args):
                       "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msamples/s", "cores": ncpu, "kind": "port", "sample": f"{n} frames (python threads around the C oracle)"},
                       "parity": "bit-exact vs the transmit oracle on 4 frames; every slot decodes FRAME_OK through the receive path"}))
 
+def bench_tx11b(args):
+    import torch, oracle_py
+    from sora_b200 import api
+    eng = api.Engine(0); dev = torch.device("cuda", 0); st = torch.cuda.current_stream()
+    F, L, rate = args.frames, 1496, 11000                    # PSDU 1500 B incl. FCS at 11 Mbps CCK, as BASELINE config #3's frames
+    rng = np.random.default_rng(11)
+    pay = rng.integers(0, 256, (256, L)).astype(np.uint8)
+    d_pay = torch.from_numpy(pay).to(dev).repeat((F + 255) // 256, 1)[:F].contiguous()
+    d_off = torch.arange(F, dtype=torch.int64, device=dev) * L; d_len = torch.full((F,), L, dtype=torch.int32, device=dev)
+    lead = 392; ns = ((24 * 88 + (L + 4) * 8 + 5) * 4 + 7) // 8 * 8
+    slot = (lead + ns + 200 + 55) // 56 * 56                 # whole 28-sample blocks, multiple of 8
+    d_iq = torch.zeros((F, slot, 2), dtype=torch.int16, device=dev)
+    def step(): eng.tx11b_raw(d_pay.data_ptr(), F * L, d_off.data_ptr(), d_len.data_ptr(), F, rate, 0, lead, 16, d_iq.data_ptr(), slot, 0, st.cuda_stream)
+    step(); torch.cuda.synchronize()
+    got = d_iq[:4, lead:lead + ns].cpu().numpy()
+    for i in range(4):
+        assert (got[i] == oracle_py.tx11b_modulate(pay[i], rate).astype(np.int16) << 8).all(), "GPU modulator differs from the oracle"
+    # the receive path decodes what the transmit path made
+    s_off = torch.arange(F, dtype=torch.int64, device=dev) * slot; s_len = torch.full((F,), slot, dtype=torch.int32, device=dev)
+    d_out = torch.zeros((F, 1504), dtype=torch.uint8, device=dev); d_res = torch.zeros((F, 6), dtype=torch.int32, device=dev)
+    eng.rx11b_raw(d_iq.data_ptr(), F * slot, s_off.data_ptr(), s_len.data_ptr(), F, d_out.data_ptr(), 1504, d_res.data_ptr(), st.cuda_stream); torch.cuda.synchronize()
+    ok = float((d_res[:, 0] == 1).float().mean())
+    assert ok == 1.0 and (d_out[:256, :L].cpu().numpy() == pay).all(), ok
+    for _ in range(3): step()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record(st)
+    for _ in range(args.steps): step()
+    e1.record(st); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    ncpu = os.cpu_count() or 1; n = 512
+    import concurrent.futures as cf
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(ncpu) as ex: list(ex.map(lambda i: oracle_py.tx11b_modulate(pay[i % 256], rate), range(n)))
+    dt = time.perf_counter() - t0
+    alg = F * (L + slot * 4.0)
+    print(json.dumps({"metric": "802.11b TX PHY Msamples/s (bytes in, IQ out)", "value": F * slot / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "n_gpus": 1,
+                      "config": {"workload": "802.11b 11 Mbps CCK modulator, long preamble, PSDU 1500 B, COMPLEX16 slots of %d samples at 44 Msps (the input of BASELINE config #3 made on the device)" % slot, "frames_per_step": F},
+                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks()},
+                      "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msamples/s", "cores": ncpu, "kind": "port", "sample": f"{n} frames (python threads around the C oracle)"},
+                      "parity": "bit-exact vs the transmit oracle on 4 frames; every slot decodes FRAME_OK through the 802.11b receive path"}))
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a"], required=True)
+    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b"], required=True)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--blocks", type=int, default=32768)
     ap.add_argument("--frames", type=int, default=32768)
     a = ap.parse_args()
-    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a}[a.config](a)
+    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b}[a.config](a)

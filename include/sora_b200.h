@@ -178,6 +178,19 @@ int sb200_tx11a_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_
                       const uint8_t* seeds, uint32_t nframes, uint32_t rate_kbps, uint32_t lead_samples, uint32_t sample_bits,
                       void* out, uint64_t out_stride_samples, uint32_t* nsamples, void* cuda_stream);
 
+/* 802.11b transmit: the brick modulator graph CreateModGraph (kernel/bb/demod11/fb11bmod_config.hpp:19-45: TBB11bSrc, TSc741, TBB11bMRSelect,
+ * Barker/CCK spreaders, TQuickPulseShaper, TPackSample16to8, TModSink) driven like Test11B_FB_Mod (kernel/bb/demod11/fb11b_mod.cpp:28-32).
+ * Long preamble only (PHY_11b.hpp:96-100 rejects the short one).  Frame i = payload[pay_off[i] .. +pay_len[i]) is the MPDU WITHOUT FCS
+ * (CF_11bTxVector::crc32 is appended); rate_kbps 1000 / 2000 / 5500 / 11000; init_phase = CF_DifferentialMap::last_phase in front of the
+ * first byte (0 on a fresh context).  Slot i of `out` (out_stride_samples complex samples at 44 Msps, a multiple of 8; out 16-byte
+ * aligned) receives lead_samples zeros, 4 samples per chip, the shaper's 5 flush vectors, and zeros to the end of the slot;
+ * nsamples[i] = lead + what CF_TxSampleBuffer::tx_sample_cnt ends at.  sample_bits 8: COMPLEX8 as `demod11 -m` writes; 16: COMPLEX16 =
+ * COMPLEX8 << 8, which goes straight into sb200_rx11b_batch.  final_phase[i] (may be NULL) = last_phase as frame i leaves it, i.e. the
+ * init_phase of the next frame modulated on the same context (the reference never resets it).  All pointers host or device. */
+int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_total, const uint64_t* pay_off, const uint32_t* pay_len,
+                      uint32_t nframes, uint32_t rate_kbps, uint32_t init_phase, uint32_t lead_samples, uint32_t sample_bits,
+                      void* out, uint64_t out_stride_samples, uint32_t* nsamples, uint32_t* final_phase, void* cuda_stream);
+
 /* Standalone K=7 Viterbi over `nblocks` independent blocks of `nsoft` soft values (uint8 0..7, one per coded bit after
  * puncturing; block b starts at soft + b*soft_stride).  frame_len_bytes L sets the flush point 8L+16+6 exactly like
  * CF_11aRxVector::frame_length; each block yields L+2 bytes (SERVICE + PSDU, not descrambled) at out + b*out_stride.

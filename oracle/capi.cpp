@@ -2,6 +2,7 @@
 #include "rx11b.h"
 #include "rx11n.h"
 #include "tx11a.h"
+#include "tx11b.h"
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -185,6 +186,13 @@ uint64_t sbo_tx11a_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_
 }
 uint32_t sbo_tx11a_nsym(uint32_t len, uint32_t rate_kbps) { return tx11a_nsym(len, rate_kbps); }
 void sbo_ifft128(const int16_t* in, int16_t* out) { alignas(16) c16 t[128]; memcpy(t, in, 512); alignas(16) c16 o[128]; ifft128((v128*)t, (v128*)o); memcpy(out, o, 512); }
+
+// ---- 802.11b transmit ---------------------------------------------------------------------------------------------------
+uint64_t sbo_tx11b_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_kbps, uint32_t init_phase, int8_t* out, uint64_t cap_samples, uint32_t* final_phase) {
+    return tx11b_modulate(payload, len, rate_kbps, init_phase, out, (size_t)cap_samples, final_phase);
+}
+uint32_t sbo_tx11b_nsamples(uint32_t len, uint32_t rate_kbps) { return tx11b_nsamples(len, rate_kbps); }
+void sbo_tx11b_taps(int16_t* out20) { tx11b_taps(out20); }
 
 uint32_t sbo_crc32(const uint8_t* p, uint64_t n) { uint32_t c = 0xFFFFFFFFu; for (uint64_t i = 0; i < n; i++) c = (c >> 8) ^ tables().crc32_lut[p[i] ^ (c & 0xFF)]; return ~c; }
 

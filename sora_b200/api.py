@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -160,6 +160,23 @@ class Engine:
         sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint8)
         self.tx11a_raw(_ptr(flat), max(int(lens.sum()), 1), _ptr(offs), _ptr(lens), 0 if sd is None else _ptr(sd), len(lens), rate_kbps, lead, sample_bits, _ptr(out), out_stride, _ptr(ns))
         return out, ns
+
+    def tx11b_raw(self, pay_ptr, pay_total, off_ptr, len_ptr, nframes, rate_kbps, init_phase, lead, bits, out_ptr, out_stride, ns_ptr, stream=0, fp_ptr=0):
+        self._check(self._lib.sb200_tx11b_batch(self._h, C.c_void_p(pay_ptr), C.c_uint64(pay_total), C.c_void_p(off_ptr), C.c_void_p(len_ptr), C.c_uint32(nframes),
+                                                C.c_uint32(rate_kbps), C.c_uint32(init_phase), C.c_uint32(lead), C.c_uint32(bits), C.c_void_p(out_ptr),
+                                                C.c_uint64(out_stride), C.c_void_p(ns_ptr), C.c_void_p(fp_ptr), C.c_void_p(stream)), "sb200_tx11b_batch")
+
+    def tx11b_batch(self, payloads, rate_kbps, init_phase=0, lead=0, sample_bits=8, out_stride=None, return_phase=False):
+        """payloads: list of uint8 arrays (MPDUs without FCS) -> (samples [F, out_stride, 2] int8 or int16 at 44 Msps, nsamples [F])."""
+        lens = np.array([len(p) for p in payloads], np.uint32); offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(p, np.uint8) for p in payloads]) if lens.sum() else np.zeros(1, np.uint8))
+        if out_stride is None:
+            cpb = {1000: 88, 2000: 44, 5500: 16, 11000: 8}.get(rate_kbps, 8)      # an unknown rate is the library's error to report
+            out_stride = (lead + (24 * 88 + (int(lens.max()) + 4) * cpb + 5) * 4 + 15) // 8 * 8
+        out = np.zeros((len(lens), out_stride, 2), np.int8 if sample_bits == 8 else np.int16); ns = np.zeros(len(lens), np.uint32)
+        fp = np.zeros(len(lens), np.uint32)
+        self.tx11b_raw(_ptr(flat), max(int(lens.sum()), 1), _ptr(offs), _ptr(lens), len(lens), rate_kbps, init_phase, lead, sample_bits, _ptr(out), out_stride, _ptr(ns), 0, _ptr(fp))
+        return (out, ns, fp) if return_phase else (out, ns)
 
     def rxblocks_unpack(self, raw, left_shift=0):
         """raw: uint8 array of whole 128-byte RX_BLOCKs (a *.dmp file) -> int16 [28*nblocks, 2] via the device gather."""

@@ -21,6 +21,7 @@
 //     facades CF_Error, CF_11aRxVector, CF_HTRxVector, CF_RxFrameBuffer, CF_CFOffset.
 //
 //   TB200Dot11aTx<T_CTX, T_NEXT>   source brick replacing both transmit graphs of kernel/bb/demod11/fb11amod_config.hpp:75-158
+//   TB200Dot11bTx<T_CTX, T_NEXT>   source brick replacing the transmit graph of kernel/bb/demod11/fb11bmod_config.hpp:19-45
 //       (TTS11aSrc | TBB11aSrc, T11aSc, TBB11aMRSelect, TConvEncode_*, T11aInterleave*, TMap11a*, T11aAddPilot, TIFFTx, TPackSample16to8):
 //     one Process() modulates the MPDU in CF_TxFrameBuffer at CF_11aTxVector::data_rate_kbps with CF_ScramblerSeed::sc_seed and pushes
 //     the whole PPDU (preamble + SIGNAL + DATA) downstream as COMPLEX8 x 8 bursts, what TPackSample16to8 hands to TModSink.
@@ -253,5 +254,53 @@ public:
                               td_.data(), cap, &ns, nullptr) != SB200_OK) { error_code = E_ERROR_PARAMETER; return false; }
         for (uint32_t i = 0; i + 8 <= ns; i += 8) { memcpy(opin().append(), td_.data() + 2 * i, 16); this->Next()->Process(opin()); }
         return false;                                              // one PPDU per Process(), like TBB11aSrc / TTS11aSrc
+    }
+};
+
+
+// 802.11b transmit: everything between TBB11bSrc and TModSink of fb11bmod_config.hpp:25-44 as one source brick.  Same context as the
+// graph it replaces (CF_11bTxVector, CF_TxFrameBuffer, CF_DifferentialMap, CF_Error); emits COMPLEX8 bursts of 8 like TPackSample16to8.
+DEFINE_LOCAL_CONTEXT(TB200Dot11bTx, CF_Error, CF_11bTxVector, CF_TxFrameBuffer, CF_DifferentialMap);
+template <TSOURCE_ARGS>
+class TB200Dot11bTx : public TSource<TSOURCE_PARAMS> {
+    CTX_VAR_RW(ulong, error_code)
+    CTX_VAR_RO(ushort, frame_length) CTX_VAR_RO(uchar, preamble_type) CTX_VAR_RO(ulong, data_rate_kbps)
+    CTX_VAR_RO(uchar*, mpdu_buf0) CTX_VAR_RO(ushort, mpdu_buf_size0) CTX_VAR_RO(uchar*, mpdu_buf1) CTX_VAR_RO(ushort, mpdu_buf_size1)
+    CTX_VAR_RW(uint, last_phase)
+    sb200_handle* h_; std::vector<uchar> mpdu_; std::vector<int8_t> td_;
+public:
+    DEFINE_OPORT(COMPLEX8, 8);
+    REFERENCE_LOCAL_CONTEXT(TB200Dot11bTx);
+    STD_TSOURCE_CONSTRUCTOR(TB200Dot11bTx)
+        BIND_CONTEXT(CF_Error::error_code, error_code)
+        BIND_CONTEXT(CF_11bTxVector::frame_length, frame_length) BIND_CONTEXT(CF_11bTxVector::preamble_type, preamble_type)
+        BIND_CONTEXT(CF_11bTxVector::data_rate_kbps, data_rate_kbps)
+        BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf0, mpdu_buf0) BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf_size0, mpdu_buf_size0)
+        BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf1, mpdu_buf1) BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf_size1, mpdu_buf_size1)
+        BIND_CONTEXT(CF_DifferentialMap::last_phase, last_phase)
+        , h_(nullptr)
+    {
+        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+    }
+    ~TB200Dot11bTx() { sb200_destroy(h_); }
+    STD_TSOURCE_RESET() { }
+    STD_TSOURCE_FLUSH() { }
+    bool Process() override {
+        if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        error_code = E_ERROR_SUCCESS;
+        if (!mpdu_buf0 || (mpdu_buf_size1 > 0 && !mpdu_buf1) || (uint)mpdu_buf_size0 + mpdu_buf_size1 != frame_length) { error_code = E_ERROR_PARAMETER; return false; }   // TBB11bSrc::Preprocess
+        const ulong rate = data_rate_kbps;
+        if (rate != 1000 && rate != 2000 && rate != 5500 && rate != 11000) { error_code = E_ERROR_DATARATE; return false; }     // PHY_11b.hpp:89-94
+        if (preamble_type == 1) { error_code = E_ERROR_NOT_SUPPORTED; return false; }                                             // PHY_11b.hpp:96-100
+        mpdu_.assign(mpdu_buf0, mpdu_buf0 + mpdu_buf_size0); if (mpdu_buf_size1) mpdu_.insert(mpdu_.end(), mpdu_buf1, mpdu_buf1 + mpdu_buf_size1);
+        const uint64_t off = 0; const uint32_t len = frame_length; uint32_t ns = 0, fin = 0;
+        const size_t cap = ((24 * 88 + ((size_t)len + 4) * 88 + 5) * 4 + 15) / 8 * 8;          // enough for 1 Mbps
+        td_.assign(2 * cap + 16, 0);
+        int8_t* td = td_.data() + ((16 - ((uintptr_t)td_.data() & 15)) & 15);                  // the entry point wants 16-byte alignment
+        if (sb200_tx11b_batch(h_, mpdu_.empty() ? (const uint8_t*)"" : mpdu_.data(), mpdu_.size() ? mpdu_.size() : 1, &off, &len, 1, (uint32_t)rate, last_phase & 3u, 0, 8,
+                              td, cap, &ns, &fin, nullptr) != SB200_OK) { error_code = E_ERROR_PARAMETER; return false; }
+        for (uint32_t i = 0; i + 8 <= ns; i += 8) { memcpy(opin().append(), td + 2 * i, 16); this->Next()->Process(opin()); }
+        last_phase = fin;                                          // the reference never resets it between frames (barkerspread.hpp:99-100, cck.hpp:864)
+        return false;
     }
 };

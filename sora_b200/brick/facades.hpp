@@ -7,6 +7,7 @@
 //   CF_11bRxVector               kernel/bb/Brick11/src/ieee80211facade.hpp:72-76
 //   CF_HTRxVector                kernel/bb/Brick11/src/ieee80211facade.hpp:269-272
 //   CF_11aTxVector, CF_TxFrameBuffer, CF_ScramblerSeed   ieee80211facade.hpp:140-146, 87-92, 116-119
+//   CF_11bTxVector, CF_DifferentialMap                   ieee80211facade.hpp:78-85, 94-98
 // plus the E_ERROR_* codes (stdfacade.h:10-12, ieee80211facade.hpp:10-19).
 #pragma once
 #include "brick.hpp"
@@ -17,6 +18,8 @@
 #define E_ERROR_PLCP_HEADER_FAIL 0x80000005
 #define E_ERROR_CRC32_FAIL       0x80000006
 #define E_ERROR_CS_TIMEOUT       0x80000007
+#define E_ERROR_NOT_SUPPORTED    0x80000003
+#define E_ERROR_DATARATE         0x80000002
 #define E_ERROR_FAILED           0x8000FFFF
 #define BK_ERROR_FAILED          0x8000FFFF
 #define CR_12 0
@@ -61,3 +64,5 @@ class CF_HTRxVector { FACADE_FIELD(ushort, ht_frame_length) FACADE_FIELD(ulong, 
 class CF_11aTxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(ulong, data_rate_kbps) FACADE_FIELD(ulong, crc32) FACADE_FIELD(ushort, coding_rate) };
 class CF_TxFrameBuffer { FACADE_FIELD(uchar*, mpdu_buf0) FACADE_FIELD(ushort, mpdu_buf_size0) FACADE_FIELD(uchar*, mpdu_buf1) FACADE_FIELD(ushort, mpdu_buf_size1) };
 class CF_ScramblerSeed { FACADE_FIELD(uchar, sc_seed) };
+class CF_11bTxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(uchar, preamble_type) FACADE_FIELD(uchar, mod_select) FACADE_FIELD(ulong, data_rate_kbps) FACADE_FIELD(ulong, crc32) };
+class CF_DifferentialMap { FACADE_FIELD(uint, last_phase) };

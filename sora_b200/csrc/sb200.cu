@@ -5,6 +5,7 @@
 #include "rx11b_kernels.cuh"
 #include "rx11n_kernels.cuh"
 #include "tx11a_kernels.cuh"
+#include "tx11b_kernels.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -67,7 +68,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
-    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns;   // 802.11a transmit tables (built on first use) and staging
+    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc;   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
@@ -153,7 +154,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -727,6 +728,68 @@ extern "C" int sb200_tx11a_batch(sb200_handle* h, const uint8_t* payload, uint64
     bool sync = false;
     if (!out_dev) { CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (nsamples && !ns_dev) { CK(cudaMemcpyAsync(nsamples, d_ns, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (sync) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+// 802.11b transmit (tx11b_kernels.cuh)
+extern "C" int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_total, const uint64_t* pay_off, const uint32_t* pay_len,
+                                 uint32_t nframes, uint32_t rate_kbps, uint32_t init_phase, uint32_t lead_samples, uint32_t sample_bits, void* out,
+                                 uint64_t out_stride_samples, uint32_t* nsamples, uint32_t* final_phase, void* cuda_stream) {
+    if (!h || !payload || !pay_off || !pay_len || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (sample_bits != 8 && sample_bits != 16) return h->fail(SB200_E_INVALID, "sample_bits must be 8 (COMPLEX8) or 16 (COMPLEX16 = COMPLEX8 << 8)");
+    if (out_stride_samples % 8u || ((uintptr_t)out & 15u)) return h->fail(SB200_E_INVALID, "out must be 16-byte aligned and out_stride_samples a multiple of 8");
+    if (nframes == 0) return SB200_OK;
+    Tx11bJob job{};
+    job.rate_kbps = rate_kbps; job.lead = lead_samples; job.fmt16 = sample_bits == 16; job.init_phase = init_phase & 3u;
+    switch (rate_kbps) {                                                                // bb/bbb.h:47-50, DataRate.h:40-43
+        case 1000: job.rate_code = 0x0A; job.chips_per_byte = 88; break;  case 2000: job.rate_code = 0x14; job.chips_per_byte = 44; break;
+        case 5500: job.rate_code = 0x37; job.chips_per_byte = 16; break;  case 11000: job.rate_code = 0x6E; job.chips_per_byte = 8; break;
+        default: return h->fail(SB200_E_INVALID, "rate_kbps is not an 802.11b rate");
+    }
+    for (int k = 0; k < 20; k++) {                                                      // pulse.hpp:292-300, with that file's own PI
+        const int i = 8 - k; const double PI_ = 3.141593;
+        const double x = (i == 1 || i == -1) ? 1.0 : 4 * cos(PI_ * i / 2) / PI_ / (1 - i * i);
+        job.taps[k] = (short)(x * 80 + .5);
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    const bool off_dev = is_device_ptr(pay_off), len_dev = is_device_ptr(pay_len), pay_dev = is_device_ptr(payload), out_dev = is_device_ptr(out);
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), pay_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), pay_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), pay_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), pay_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if (lenh[i] + 4u > 4095u || offh[i] + lenh[i] > payload_total) return h->fail(SB200_E_INVALID, "payload slot out of range (frame_length 1..4095 incl. FCS)");
+        if ((uint64_t)lead_samples + tx11b_nsamples(tx11b_nchips(lenh[i], job.chips_per_byte)) > out_stride_samples) return h->fail(SB200_E_INVALID, "out_stride_samples too small for the frame");
+        if (lenh[i] > max_len) max_len = lenh[i];
+    }
+    job.desc_stride = (24u + max_len + 4u + 7u) & ~7u;
+    const uint8_t* d_pay; const uint64_t* d_off; const uint32_t* d_len;
+    if (pay_dev) d_pay = payload; else { CK(h->txpay.need(payload_total)); CK(cudaMemcpyAsync(h->txpay.p, payload, payload_total, cudaMemcpyHostToDevice, st)); d_pay = (const uint8_t*)h->txpay.p; }
+    if (off_dev) d_off = pay_off; else { CK(h->txoff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->txoff.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->txoff.p; }
+    if (len_dev) d_len = pay_len; else { CK(h->txlen.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->txlen.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->txlen.p; }
+    const size_t bps = sample_bits == 16 ? 4 : 2, out_bytes = (size_t)nframes * out_stride_samples * bps;
+    void* d_out = out; if (!out_dev) { CK(h->txout.need(out_bytes)); d_out = h->txout.p; }
+    uint32_t* d_ns = nullptr; const bool ns_dev = nsamples && is_device_ptr(nsamples);
+    if (nsamples) { if (ns_dev) d_ns = nsamples; else { CK(h->txns.need(nframes * 4ull)); d_ns = (uint32_t*)h->txns.p; } }
+    uint32_t* d_fp = nullptr; const bool fp_dev = final_phase && is_device_ptr(final_phase);
+    if (final_phase) { if (fp_dev) d_fp = final_phase; else { CK(h->txseed.need(nframes * 4ull)); d_fp = (uint32_t*)h->txseed.p; } }
+    CK(h->crc.need(nframes * 4ull)); CK(h->txdesc.need((size_t)nframes * job.desc_stride * 2ull));
+    const uint64_t per_cta = (uint64_t)SB_TX11B_THREADS * SB_TX11B_SPT, ny = (out_stride_samples + per_cta - 1) / per_cta;
+    if (ny > 65535u) return h->fail(SB200_E_INVALID, "out_stride_samples too large");
+    CK(cudaEventRecord(h->ev0, st));
+    k_tx11a_crc<<<(nframes + 127) / 128, 128, 0, st>>>(d_pay, d_off, d_len, nframes, h->T, (uint32_t*)h->crc.p);
+    k_tx11b_code<<<(nframes + 127) / 128, 128, 0, st>>>(d_pay, d_off, d_len, nframes, job, (const uint32_t*)h->crc.p, (uint16_t*)h->txdesc.p, d_fp);
+    k_tx11b_shape<<<dim3(nframes, (unsigned)ny), SB_TX11B_THREADS, 0, st>>>(d_len, job, (const uint16_t*)h->txdesc.p, d_out, out_stride_samples, d_ns);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 0; h->launches += 3;
+    CK(cudaGetLastError());
+    bool sync = false;
+    if (!out_dev) { CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (nsamples && !ns_dev) { CK(cudaMemcpyAsync(nsamples, d_ns, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (final_phase && !fp_dev) { CK(cudaMemcpyAsync(final_phase, d_fp, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (sync) CK(cudaStreamSynchronize(st));
     return SB200_OK;
 }

@@ -151,3 +151,18 @@ def tx11a_modulate(payload, rate_kbps, seed=0xFF, tail_zeros=32):
 
 def ifft128(x):
     x = np.ascontiguousarray(x, dtype=np.int16); o = np.zeros((128, 2), np.int16); lib().sbo_ifft128(_p(x), _p(o)); return o
+
+
+# ---- 802.11b transmit (brick modulator restatement) ---------------------------------------------------------------------
+def tx11b_modulate(payload, rate_kbps, init_phase=0, return_phase=False):
+    """payload: MPDU bytes without FCS.  Returns int8 [n, 2] complex samples at 44 Msps (the COMPLEX8 buffer TModSink fills)."""
+    payload = np.ascontiguousarray(payload, dtype=np.uint8); L = lib(); L.sbo_tx11b_modulate.restype = C.c_uint64
+    cap = L.sbo_tx11b_nsamples(C.c_uint32(len(payload)), C.c_uint32(rate_kbps)); assert cap, "not an 802.11b rate"
+    out = np.zeros((cap, 2), np.int8)
+    fin = C.c_uint32(0)
+    n = L.sbo_tx11b_modulate(_p(payload), C.c_uint32(len(payload)), C.c_uint32(rate_kbps), C.c_uint32(init_phase), _p(out), C.c_uint64(cap), C.byref(fin))
+    assert n == cap, (n, cap)
+    return (out, fin.value) if return_phase else out
+
+def tx11b_taps():
+    o = np.zeros(20, np.int16); lib().sbo_tx11b_taps(_p(o)); return o
