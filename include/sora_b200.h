@@ -133,6 +133,16 @@ int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samp
                       const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
                       uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, void* cuda_stream);
 
+/* 802.11b continuous captures (SURVEY.md §8(f) rank 1 for the DSSS/CCK chain): capture s = samples [stream_off[s], +stream_len[s]) at 44 Msps;
+ * events are reported in the order MAC11b_Receive meets them (kernel/bb/demod11/fb11b_demod.cpp:26-75): after FRAME_OK / CRC32_FAIL the
+ * source seeks past the last FCS byte (352 / 176 / 64 / 32 samples), every event ends with Flush, ctx.reset and Reset, and the DC
+ * estimate, descrambler register and differential reference carry over.  res and out_bytes hold nstreams x max_frames entries (row
+ * s * max_frames + k = event k of capture s; entries past nframes_out[s] are zero); sample_index = CF_MemSamples::mem_sample_index
+ * when the event was seen, detect_vec counts vectors since the start of the capture.  All pointers host or device. */
+int sb200_rx11b_streams(sb200_handle* h, const int16_t* iq, uint64_t iq_total_samples, const uint64_t* stream_off, const uint32_t* stream_len,
+                        uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res,
+                        uint32_t* nframes_out, void* cuda_stream);
+
 /* 802.11n 2x2 receive path (HT mixed format, 20 MHz, two spatial streams; the reference accepts MCS 8, 9 and 10 only,
  * PHY_11n.hpp:496-501).  Replaces the graph of kernel/bb/demod11/fb11ndemod_config.hpp:167-262 (CreateDemodGraph11n) driven like
  * kernel/bb/demod11/fb11n_demod.cpp:29-81: TMemSamples2 -> TDownSample2 -> TCCA11n | TFreqEstimator_11n ... TSisoChannelEst |
@@ -153,6 +163,16 @@ typedef struct sb200_frame_result_11n {
 int sb200_rx11n_batch(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples,
                       const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes,
                       uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11n* res, void* cuda_stream);
+/* 802.11n continuous captures (SURVEY.md §8(f) rank 1 for the HT chain): capture s = the same range [stream_off[s], +stream_len[s]) of
+ * both antenna buffers; events in the order RxThread meets them (kernel/bb/demod11/fb11n_demod.cpp:29-81).  After each event the graph is
+ * flushed and reset and the source continues with the next 28-sample block, while TCCA11n and MimoAutoCorr keep their history
+ * (cca_11n.hpp:146-163, autocorr.hpp:9-42) — carried per capture on the device.  res / out_bytes / sample_index are HOST arrays of
+ * nstreams x max_frames entries (row s * max_frames + k); sample_index = CF_MemSamples::mem_sample_index when event k was seen; the
+ * sample_index and detect_index fields inside res are relative to the restart. */
+int sb200_rx11n_streams(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples, const uint64_t* stream_off,
+                        const uint32_t* stream_len, uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride,
+                        sb200_frame_result_11n* res, uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream);
+
 /* Stage taps for parity tests (host outputs, any may be NULL): siso [n][2][64][2] legacy channel per antenna, hinv [n][4][64][2]
  * inverse 2x2 channel (11,12,21,22), eq [n][2][max_sym][64][2] per-stream equalised data symbols, theta [n][max_sym] NCO phase
  * after each data symbol, sig [n][16] the nine L-SIG/HT-SIG bytes, soft [n][soft_stride] stream-parsed soft values. */

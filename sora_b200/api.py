@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -217,6 +217,26 @@ class Engine:
         res = np.zeros(nf, dtype=RESULT11B_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
         self.rx11b_raw(_ptr(iq), iq.shape[0], _ptr(off), _ptr(ln), nf, _ptr(out), out_stride, _ptr(res))
         return res, out
+
+    def rx11n_streams(self, iq0, iq1, stream_off, stream_len, max_frames=8, out_stride=1536):
+        """802.11n continuous captures -> (results RESULT11N_DTYPE [S, max_frames], bytes [S, max_frames, out_stride], sample_index [S, max_frames], counts [S])."""
+        iq0 = np.ascontiguousarray(iq0, dtype=np.int16).reshape(-1, 2); iq1 = np.ascontiguousarray(iq1, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(stream_off, dtype=np.uint64); ln = np.ascontiguousarray(stream_len, dtype=np.uint32); S = len(off)
+        res = np.zeros((S, max_frames), dtype=RESULT11N_DTYPE); out = np.zeros((S, max_frames, out_stride), dtype=np.uint8)
+        sidx = np.zeros((S, max_frames), np.uint32); cnt = np.zeros(S, np.uint32)
+        self._check(self._lib.sb200_rx11n_streams(self._h, C.c_void_p(_ptr(iq0)), C.c_void_p(_ptr(iq1)), C.c_uint64(iq0.shape[0]), C.c_void_p(_ptr(off)), C.c_void_p(_ptr(ln)), C.c_uint32(S),
+                                                  C.c_uint32(max_frames), C.c_void_p(_ptr(out)), C.c_uint32(out_stride), C.c_void_p(_ptr(res)), C.c_void_p(_ptr(sidx)), C.c_void_p(_ptr(cnt)),
+                                                  C.c_void_p(0)), "sb200_rx11n_streams")
+        return res, out, sidx, cnt
+
+    def rx11b_streams(self, iq, stream_off, stream_len, max_frames=8, out_stride=4096):
+        """802.11b continuous captures -> (results RESULT11B_DTYPE [S, max_frames], bytes [S, max_frames, out_stride], counts [S])."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        off = np.ascontiguousarray(stream_off, dtype=np.uint64); ln = np.ascontiguousarray(stream_len, dtype=np.uint32); S = len(off)
+        res = np.zeros((S, max_frames), dtype=RESULT11B_DTYPE); out = np.zeros((S, max_frames, out_stride), dtype=np.uint8); cnt = np.zeros(S, np.uint32)
+        self._check(self._lib.sb200_rx11b_streams(self._h, C.c_void_p(_ptr(iq)), C.c_uint64(iq.shape[0]), C.c_void_p(_ptr(off)), C.c_void_p(_ptr(ln)), C.c_uint32(S), C.c_uint32(max_frames),
+                                                  C.c_void_p(_ptr(out)), C.c_uint32(out_stride), C.c_void_p(_ptr(res)), C.c_void_p(_ptr(cnt)), C.c_void_p(0)), "sb200_rx11b_streams")
+        return res, out, cnt
 
     def rx11a_taps(self, iq, frame_off, frame_len, max_sym):
         iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)

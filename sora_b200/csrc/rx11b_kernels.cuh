@@ -80,7 +80,7 @@ struct Rx11bState {
 
 __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
                                               uint32_t nframes, uint32_t cca_thr, uint8_t* __restrict__ out, uint64_t out_stride,
-                                              Result11b* __restrict__ res) {
+                                              Result11b* __restrict__ res, uint32_t max_frames, uint32_t* __restrict__ counts) {
     __shared__ uint32_t s_crc[16];
     __shared__ unsigned short s_crc16[16];
     if (threadIdx.x < 16) {
@@ -90,14 +90,14 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
     __syncthreads();
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
-    const uint32_t* x = iq + off[f];
+    const uint32_t* x = iq + off[f];                   // start of the part of the slot not consumed yet (continuous-capture mode moves it)
     const bool al16 = (((uintptr_t)x) & 15u) == 0;     // block starts are multiples of 4 samples from the slot start
     auto ld4 = [&](const uint32_t* p, uint32_t (&w)[4]) {
         if (al16) { const uint4 v = __ldg((const uint4*)p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
         else { w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2); w[3] = __ldg(p + 3); }
     };
-    const uint32_t nblk = len[f] / 28u;
-    uint8_t* op = out + (size_t)f * out_stride;
+    const uint32_t slot_len = len[f]; uint32_t nblk = slot_len / 28u, consumed = 0, found = 0;
+    uint8_t* op = out + (size_t)f * max_frames * out_stride;
     const uint32_t out_cap = (uint32_t)(out_stride < 0xFFFFFFFFull ? out_stride : 0xFFFFFFFFull);
     Rx11bState s;
     auto bricks_reset = [&]() {
@@ -269,9 +269,14 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
         } else s.bs_state = 4;
     };
 
+    // One pass of this loop = one event of the reference's driver (fb11b_demod.cpp:26-75).  max_frames == 1 is the slot-per-frame mode;
+    // larger values walk a continuous capture: after FRAME_OK / CRC32_FAIL the source seeks past the last FCS byte, every event ends with
+    // Flush(); ctx.reset(); Reset() and the DC estimate, the descrambler register and the differential reference carry over.
+    for (;;) {
     Result11b r; r.status = E_NO_FRAME; r.rate_kbps = 0; r.length = 0; r.crc32 = 0; r.sample_index = 0; r.detect_vec = 0;
-    uint32_t st_base = 0;                               // sample index (in the slot) of the first sample of the symbol-timing block being filled
-    for (uint32_t blk = 0; blk < nblk; blk++) {
+    uint32_t st_base = 0;                               // sample index (from x) of the first sample of the symbol-timing block being filled
+    uint32_t blk = 0; bool event = false;
+    for (; blk < nblk; blk++) {
         for (int v = 0; v < 7; v++) {
             const uint32_t p0 = blk * 28u + 4u * v;
             if (s.cca_state == 0) {
@@ -332,12 +337,23 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
         if (err == E_SUCCESS) continue;
         if (err != E_CS_TIMEOUT) {
             r.status = err; r.rate_kbps = s.data_rate_kbps; r.length = s.frame_length; r.crc32 = s.frame_crc32 & 0x00FFFFFFu;
-            r.sample_index = (blk + 1u) * 28u; r.detect_vec = s.detect_vec;
-            break;
+            r.sample_index = consumed + (blk + 1u) * 28u; r.detect_vec = s.detect_vec;
+            event = true; break;
         }
         ctx_reset(); bricks_reset();
     }
-    res[f] = r;
+    if (!event) { if (max_frames == 1u) res[f] = r; break; }
+    res[(size_t)f * max_frames + found] = r; found++;
+    if (found == max_frames) break;
+    uint32_t adv = (blk + 1u) * 28u;
+    if (r.status == E_FRAME_OK || r.status == E_CRC32_FAIL)      // "jump advance of the last CRC byte" (fb11b_demod.cpp:43-61)
+        adv += s.data_rate_kbps == 1000 ? 352u : s.data_rate_kbps == 2000 ? 176u : s.data_rate_kbps == 5500 ? 64u : 32u;
+    consumed += adv;
+    if (consumed + 28u > slot_len) break;
+    x += adv; nblk = (slot_len - consumed) / 28u; op += out_stride;
+    ctx_reset(); bricks_reset();
+    }
+    if (counts) counts[f] = found;
 }
 
 } // namespace sb

@@ -150,6 +150,77 @@ __global__ void __launch_bounds__(128) k_sync11n(const uint32_t* __restrict__ iq
     info[f] = fi;
 }
 
+// Continuous-capture carrier sense (SURVEY.md §8(f) rank 1 for 802.11n).  TCCA11n and MimoAutoCorr are never reset between frames
+// (cca_11n.hpp:146-163, autocorr.hpp:9-42) and do not see the samples the demodulator consumed, so across a frame their history is
+// the stretch of samples in front of the previous detection — and the energy ring lags the sample history by the lanes dropped in the
+// detection vector.  Rather than re-derive that from the input, this variant keeps the bricks' own state per capture in device memory
+// (1.6 KB) and runs the reference's recurrences on it; one thread per capture, resumed pass after pass.
+struct Cca11nState {
+    uint32_t his_sample[2][32];                        // autocorr.hpp:14-18: 8 vectors of 4 samples per antenna
+    int his_corr_re[2][32], his_corr_im[2][32], his_energy[2][32];
+    int corr_re[2], corr_im[2], energy_sum[2];
+    uint32_t his_idx;                                  // vector slot 0..7 the next input replaces
+    uint32_t his_index, ring_written;                  // cca_11n.hpp:150-156: 64 moving energies; entries are valid once written (saturates at 64)
+    long long ring[64];
+};
+__global__ void __launch_bounds__(64) k_sync11n_stream(const uint32_t* __restrict__ iq0, const uint32_t* __restrict__ iq1, const uint64_t* __restrict__ off,
+                                                       const uint32_t* __restrict__ len, uint32_t nframes, const uint32_t* __restrict__ state_idx,
+                                                       Cca11nState* __restrict__ states, FrameInfo* __restrict__ info) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const uint32_t* x[2] = {iq0 + off[f], iq1 + off[f]};
+    Cca11nState& S = states[state_idx[f]];
+    const uint32_t nvec = (len[f] / 28u) * 28u / 8u;
+    int Rre[2] = {S.corr_re[0], S.corr_re[1]}, Rim[2] = {S.corr_im[0], S.corr_im[1]}, es[2] = {S.energy_sum[0], S.energy_sum[1]};
+    uint32_t hidx = S.his_idx, rindex = S.his_index, written = S.ring_written;
+    unsigned sense = 0; bool peak_found = false; int peak_count = 0;                   // BB11nDemodContext::ResetCarrierSense ran at the last event
+    bool timeout = false; uint32_t cur_blk = 0, detect = 0xFFFFFFFFu;
+    for (uint32_t v = 0; v < nvec && detect == 0xFFFFFFFFu; v++) {
+        const uint32_t blk = (8u * v + 7u) / 28u;
+        if (blk != cur_blk) {                          // the driver polls error_code once per 28-sample block (fb11n_demod.cpp:35-58)
+            if (timeout) { sense = 0; peak_found = false; peak_count = 0; timeout = false; }
+            cur_blk = blk;
+        }
+        int R_re[2][4], R_im[2][4], ve[2][4];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                                               // autocorr.hpp:110-146
+                const uint32_t w = __ldg(x[a] + 2u * (4u * v + k)); const cs16 c0 = unpack(w), c1 = unpack(S.his_sample[a][4u * hidx + k]);
+                int pr, pi; cmul_conj32(pr, pi, c0, c1); pr >>= 5; pi >>= 5;
+                Rre[a] = wadd(Rre[a], wadd(pr, -S.his_corr_re[a][4u * hidx + k])); Rim[a] = wadd(Rim[a], wadd(pi, -S.his_corr_im[a][4u * hidx + k]));
+                S.his_corr_re[a][4u * hidx + k] = pr; S.his_corr_im[a][4u * hidx + k] = pi; R_re[a][k] = Rre[a]; R_im[a][k] = Rim[a];
+                const int e = wadd(c0.re * c0.re, c0.im * c0.im) >> 5;
+                es[a] = wadd(es[a], wadd(e, -S.his_energy[a][4u * hidx + k])); S.his_energy[a][4u * hidx + k] = e; ve[a][k] = es[a];
+                S.his_sample[a][4u * hidx + k] = w;
+            }
+        }
+        hidx = (hidx + 1u) & 7u;
+        for (int k = 0; k < 4; k++) {                                                   // cca_11n.hpp:62-118
+            const long long cr = wadd(R_re[0][k] >> 1, R_re[1][k] >> 1), ci = wadd(R_im[0][k] >> 1, R_im[1][k] >> 1);
+            const long long acorr = cr * cr + ci * ci;
+            const long long e = wadd(ve[0][k] >> 1, ve[1][k] >> 1), energy = e * e;
+            const bool step = written >= 64u && energy / 6 >= S.ring[rindex] + 1;       // eb = energy / (his + 1) > 5; the ring starts at LLONG_MAX (eb = 0)
+            if (!peak_found) {
+                sense++;
+                if (step && acorr > (energy >> 1)) { sense = 0; peak_count++; peak_found = true; } else peak_count = 0;
+            } else if (acorr < (energy >> 3)) {
+                if (peak_count > 96 && peak_count < 160) { detect = v + 1; break; }     // the rest of the vector never reaches the ring (ipin.clear())
+                peak_found = false; peak_count = 0;
+            } else { peak_count++; if (peak_count > 160) { peak_found = false; peak_count = 0; } }
+            S.ring[rindex] = energy; rindex = (rindex + 1u) & 63u; if (written < 64u) written++;
+        }
+        if (sense >= 84 && detect == 0xFFFFFFFFu) timeout = true;                       // cca_11n.hpp:120-124
+    }
+    S.corr_re[0] = Rre[0]; S.corr_re[1] = Rre[1]; S.corr_im[0] = Rim[0]; S.corr_im[1] = Rim[1]; S.energy_sum[0] = es[0]; S.energy_sum[1] = es[1];
+    S.his_idx = hidx; S.his_index = rindex; S.ring_written = written;
+    FrameInfo fi;
+    fi.status = detect == 0xFFFFFFFFu ? (uint32_t)E_NO_FRAME : (uint32_t)E_SUCCESS;
+    fi.detect_vec = detect; fi.rate_kbps = 0; fi.length = 0; fi.nsym_total = 0; fi.code_rate = CR_12; fi.ncbps = 104;
+    fi.soft_bytes = 0; fi.cfo_est = 0; fi.peak_index = 0; fi.dc_re = 0; fi.dc_im = 0;
+    info[f] = fi;
+}
+
 // ------------------------------------------------------------------------------------------------
 // L-SIG / HT-SIG Viterbi: N trellis steps from the zero state, full traceback (Viterbi_sig11(..., output_bit))
 // ------------------------------------------------------------------------------------------------

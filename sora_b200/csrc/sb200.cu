@@ -68,7 +68,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
-    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc;   // 802.11a transmit tables (built on first use) and staging
+    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx;   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
@@ -154,7 +154,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -438,10 +438,11 @@ extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t
                              out_bytes, out_stride, res, cuda_stream);
 }
 
-extern "C" int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
-                                 uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, void* cuda_stream) {
+static int rx11b_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                     uint32_t nframes, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, uint32_t* counts, void* cuda_stream) {
     static_assert(sizeof(sb200_frame_result_11b) == sizeof(Result11b), "result layout");
     if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (max_frames == 0) return h->fail(SB200_E_INVALID, "max_frames must be at least 1");
     if (nframes == 0) return SB200_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CK(cudaSetDevice(h->device));
@@ -453,24 +454,39 @@ extern "C" int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq
     if (iq_dev) d_iq = (const uint32_t*)iq; else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
     if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, frame_off, nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
     if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, frame_len, nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
-    const uint64_t row = 4096;
-    CK(h->out.need(nframes * row)); CK(h->res.need(nframes * sizeof(Result11b)));
+    const uint64_t row = 4096; const size_t nres = (size_t)nframes * max_frames;
+    CK(h->out.need(nres * row)); CK(h->res.need(nres * sizeof(Result11b)));
     const bool res_dev = is_device_ptr(res);
     Result11b* d_res = res_dev ? (Result11b*)res : (Result11b*)h->res.p;
+    uint32_t* d_cnt = nullptr; const bool cnt_dev = counts && is_device_ptr(counts);
+    if (counts) { if (cnt_dev) d_cnt = counts; else { CK(h->txns.need(nframes * 4ull)); d_cnt = (uint32_t*)h->txns.p; } }
+    if (max_frames > 1) CK(cudaMemsetAsync(d_res, 0, nres * sizeof(Result11b), st));          // entries past the count read "no event"
     CK(cudaEventRecord(h->ev0, st));
-    k_rx11b<<<(nframes + 63) / 64, 64, 0, st>>>(d_iq, d_off, d_len, nframes, h->cca_thr, (uint8_t*)h->out.p, row, d_res);
+    k_rx11b<<<(nframes + 63) / 64, 64, 0, st>>>(d_iq, d_off, d_len, nframes, h->cca_thr, (uint8_t*)h->out.p, row, d_res, max_frames, d_cnt);
     CK(cudaEventRecord(h->ev1, st));
     h->timed = true; h->nk = 0; h->launches += 1;
     CK(cudaGetLastError());
     bool host_out = false;
     if (out_bytes && out_stride) {
         const size_t w = out_stride < row ? out_stride : row; const bool od = is_device_ptr(out_bytes);
-        CK(cudaMemcpy2DAsync(out_bytes, out_stride, h->out.p, row, w, nframes, od ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpy2DAsync(out_bytes, out_stride, h->out.p, row, w, nres, od ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         host_out |= !od;
     }
-    if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nframes * sizeof(Result11b), cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (!res_dev) { CK(cudaMemcpyAsync(res, d_res, nres * sizeof(Result11b), cudaMemcpyDeviceToHost, st)); host_out = true; }
+    if (counts && !cnt_dev) { CK(cudaMemcpyAsync(counts, d_cnt, nframes * 4ull, cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
     return SB200_OK;
+}
+
+extern "C" int sb200_rx11b_batch(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                                 uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res, void* cuda_stream) {
+    return rx11b_run(h, iq, iq_total, frame_off, frame_len, nframes, 1, out_bytes, out_stride, res, nullptr, cuda_stream);
+}
+
+extern "C" int sb200_rx11b_streams(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* stream_off, const uint32_t* stream_len,
+                                   uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11b* res,
+                                   uint32_t* nframes_out, void* cuda_stream) {
+    return rx11b_run(h, iq, iq_total, stream_off, stream_len, nstreams, max_frames, out_bytes, out_stride, res, nframes_out, cuda_stream);
 }
 
 // ---- 802.11n 2x2 ----------------------------------------------------------------------------------------------------------
@@ -515,7 +531,7 @@ __global__ void k_pack_results11n(const FrameInfo* __restrict__ info, const uint
 
 static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
                      uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11n* res, cudaStream_t st, Taps11n taps,
-                     uint8_t* soft_host, uint64_t soft_host_stride) {
+                     uint8_t* soft_host, uint64_t soft_host_stride, const uint32_t* state_idx = nullptr /* host: carrier-sense state slot per capture (stream mode) */) {
     if (!h || !iq0 || !iq1 || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
     if (nframes == 0) return SB200_OK;
     CK(cudaSetDevice(h->device));
@@ -552,6 +568,10 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
     CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result_11n)));
     FrameInfo* d_info = (FrameInfo*)h->info.p;
     CK(cudaEventRecord(h->ev0, st)); CK(cudaEventRecord(h->evk[0], st));
+    if (state_idx) {
+        CK(h->ccaidx.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->ccaidx.p, state_idx, nframes * 4ull, cudaMemcpyHostToDevice, st));
+        k_sync11n_stream<<<(nframes + 63) / 64, 64, 0, st>>>(d_iq0, d_iq1, d_off, d_len, nframes, (const uint32_t*)h->ccaidx.p, (Cca11nState*)h->cca11n.p, d_info);
+    } else
     k_sync11n<<<(nframes + 127) / 128, 128, 0, st>>>(d_iq0, d_iq1, d_off, d_len, nframes, d_info);
     CK(cudaEventRecord(h->evk[1], st));
     k_front11n<<<(nframes + SB_FRONT11N_WARPS - 1) / SB_FRONT11N_WARPS, 32 * SB_FRONT11N_WARPS, 0, st>>>(d_iq0, d_iq1, d_off, d_len, nframes, h->T, h->N, h->inv_deint,
@@ -578,6 +598,62 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
     if (soft_host) { CK(cudaMemcpy2DAsync(soft_host, soft_host_stride, h->soft.p, soft_stride, soft_host_stride < soft_stride ? soft_host_stride : soft_stride, nframes, cudaMemcpyDeviceToHost, st)); host_out = true; }
     if (host_out) CK(cudaStreamSynchronize(st));
     return SB200_OK;
+}
+
+// Continuous two-antenna captures: every pass decodes the next frame of all captures that still have samples (the batch pipeline over the
+// rest of each capture), with TCCA11n / MimoAutoCorr's never-reset state kept per capture on the device (k_sync11n_stream).
+extern "C" int sb200_rx11n_streams(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total, const uint64_t* stream_off, const uint32_t* stream_len,
+                                   uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result_11n* res,
+                                   uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream) {
+    if (!h || !iq0 || !iq1 || !stream_off || !stream_len || !res || !nframes_out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    if (is_device_ptr(res) || (out_bytes && is_device_ptr(out_bytes)) || is_device_ptr(stream_off) || is_device_ptr(stream_len) || is_device_ptr(nframes_out))
+        return h->fail(SB200_E_INVALID, "stream mode takes its tables and returns its results in host memory");
+    if (is_device_ptr(iq0) != is_device_ptr(iq1)) return h->fail(SB200_E_INVALID, "both antenna buffers must live on the same side");
+    for (uint32_t s = 0; s < nstreams; s++) { nframes_out[s] = 0; if (stream_off[s] + stream_len[s] > iq_total) return h->fail(SB200_E_INVALID, "capture exceeds iq_total_samples"); }
+    if (nstreams == 0 || max_frames == 0) return SB200_OK;
+    const int16_t* d_iq0 = iq0; const int16_t* d_iq1 = iq1;
+    if (!is_device_ptr(iq0)) {
+        CK(h->iq.need(iq_total * 4ull)); CK(h->iq1.need(iq_total * 4ull));
+        CK(cudaMemcpyAsync(h->iq.p, iq0, iq_total * 4ull, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->iq1.p, iq1, iq_total * 4ull, cudaMemcpyHostToDevice, st));
+        d_iq0 = (const int16_t*)h->iq.p; d_iq1 = (const int16_t*)h->iq1.p;
+    }
+    CK(h->cca11n.need((size_t)nstreams * sizeof(Cca11nState))); CK(cudaMemsetAsync(h->cca11n.p, 0, (size_t)nstreams * sizeof(Cca11nState), st));   // TCCA11n / MimoAutoCorr constructors
+    std::vector<uint64_t> pos(nstreams, 0);
+    std::vector<uint32_t> active(nstreams); for (uint32_t s = 0; s < nstreams; s++) active[s] = s;
+    std::vector<uint64_t> off; std::vector<uint32_t> len, idx; std::vector<sb200_frame_result_11n> r; std::vector<uint8_t> bytes;
+    const uint32_t row = out_bytes ? (out_stride < 1536u ? out_stride : 1536u) : 0u;
+    int rc = SB200_OK;
+    while (!active.empty()) {
+        std::vector<uint32_t> live;
+        for (uint32_t s : active) if (nframes_out[s] < max_frames && pos[s] + 28 <= stream_len[s]) live.push_back(s);
+        if (live.empty()) break;
+        const uint32_t n = (uint32_t)live.size();
+        off.resize(n); len.resize(n); idx.resize(n); r.resize(n); if (row) bytes.resize((size_t)n * row);
+        for (uint32_t j = 0; j < n; j++) { const uint32_t s = live[j]; off[j] = stream_off[s] + pos[s]; len[j] = (uint32_t)(stream_len[s] - pos[s]); idx[j] = s; }
+        Taps11n taps{}; h->tab_off = nullptr;
+        rc = rx11n_run(h, d_iq0, d_iq1, iq_total, off.data(), len.data(), n, row ? bytes.data() : nullptr, row, r.data(), st, taps, nullptr, 0, idx.data());
+        if (rc != SB200_OK) break;
+        active.clear();
+        for (uint32_t j = 0; j < n; j++) {
+            const uint32_t s = live[j];
+            if (r[j].status == SB200_FRAME_NONE) continue;                               // this capture ran out of samples: RxThread returns
+            // symbols that went through the graph behind the 128-sample L-LTF: the three SIG symbols when the header is refused (T11nSigParser
+            // runs in the third), else SIG x 3 + HT-STF + HT-LTF x 2 + data = total_symbols + 2 (PHY_11n.hpp:508 counts data + 4)
+            const bool whole = r[j].status == SB200_FRAME_OK || r[j].status == SB200_FRAME_CRC32_FAIL || r[j].status == SB200_FRAME_FAILED;
+            const uint64_t e20 = (uint64_t)r[j].detect_index + 128ull + 80ull * (whole ? r[j].nsym + 2ull : 3ull);
+            const uint64_t v_last = e20 / 4ull - 1ull, blk = (8ull * v_last + 7ull) / 28ull;
+            pos[s] += (blk + 1ull) * 28ull;                                                   // the driver sees the event after that source block
+            const size_t slot = (size_t)s * max_frames + nframes_out[s];
+            res[slot] = r[j];
+            if (sample_index) sample_index[slot] = (uint32_t)pos[s];
+            if (row) memcpy(out_bytes + slot * out_stride, bytes.data() + (size_t)j * row, row);
+            nframes_out[s]++;
+            active.push_back(s);
+        }
+    }
+    return rc;
 }
 
 extern "C" int sb200_rx11n_batch(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, uint64_t iq_total_samples, const uint64_t* frame_off,
@@ -752,6 +828,8 @@ extern "C" int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64
         const double x = (i == 1 || i == -1) ? 1.0 : 4 * cos(PI_ * i / 2) / PI_ / (1 - i * i);
         job.taps[k] = (short)(x * 80 + .5);
     }
+    {   const int H[20] = SB_TX11B_TAPS;                                                    // the aligned kernel's compile-time copy
+        for (int k = 0; k < 20; k++) if (job.taps[k] != H[k]) return h->fail(SB200_E_INVALID, "shaper taps differ from the compiled constants"); }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CK(cudaSetDevice(h->device));
     std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
@@ -778,11 +856,16 @@ extern "C" int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64
     if (final_phase) { if (fp_dev) d_fp = final_phase; else { CK(h->txseed.need(nframes * 4ull)); d_fp = (uint32_t*)h->txseed.p; } }
     CK(h->crc.need(nframes * 4ull)); CK(h->txdesc.need((size_t)nframes * job.desc_stride * 2ull));
     const uint64_t per_cta = (uint64_t)SB_TX11B_THREADS * SB_TX11B_SPT, ny = (out_stride_samples + per_cta - 1) / per_cta;
-    if (ny > 65535u) return h->fail(SB200_E_INVALID, "out_stride_samples too large");
+    if (ny > 65535u || (uint64_t)lead_samples + out_stride_samples >= (1ull << 27)) return h->fail(SB200_E_INVALID, "out_stride_samples too large");
     CK(cudaEventRecord(h->ev0, st));
     k_tx11a_crc<<<(nframes + 127) / 128, 128, 0, st>>>(d_pay, d_off, d_len, nframes, h->T, (uint32_t*)h->crc.p);
     k_tx11b_code<<<(nframes + 127) / 128, 128, 0, st>>>(d_pay, d_off, d_len, nframes, job, (const uint32_t*)h->crc.p, (uint16_t*)h->txdesc.p, d_fp);
-    k_tx11b_shape<<<dim3(nframes, (unsigned)ny), SB_TX11B_THREADS, 0, st>>>(d_len, job, (const uint16_t*)h->txdesc.p, d_out, out_stride_samples, d_ns);
+    {   const dim3 grid(nframes, (unsigned)ny); const uint16_t* dd = (const uint16_t*)h->txdesc.p; const bool al = lead_samples % 4u == 0;
+#define SB_TX11B_LAUNCH(R) do { if (al) k_tx11b_shape<true, R><<<grid, SB_TX11B_THREADS, 0, st>>>(d_len, job, dd, d_out, out_stride_samples, d_ns); \
+                                else k_tx11b_shape<false, R><<<grid, SB_TX11B_THREADS, 0, st>>>(d_len, job, dd, d_out, out_stride_samples, d_ns); } while (0)
+        switch (rate_kbps) { case 1000: SB_TX11B_LAUNCH(1000); break; case 2000: SB_TX11B_LAUNCH(2000); break; case 5500: SB_TX11B_LAUNCH(5500); break; default: SB_TX11B_LAUNCH(11000); break; }
+#undef SB_TX11B_LAUNCH
+    }
     CK(cudaEventRecord(h->ev1, st));
     h->timed = true; h->nk = 0; h->launches += 3;
     CK(cudaGetLastError());

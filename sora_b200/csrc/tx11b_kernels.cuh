@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(128) k_tx11b_code(const uint8_t* __restrict__ 
     if (final_phase) final_phase[f] = ref;                                              // what CF_DifferentialMap::last_phase is left at
 }
 
-// chip n of a frame from its descriptor row: (re, im) in {-1, 0, 1}, packed re | im << 8 as two signed bytes
-__device__ __forceinline__ unsigned tx11b_chip(const uint16_t* __restrict__ d, uint32_t n, uint32_t rate_kbps) {
+// chip n of a frame from its descriptor row: one of 1, j, -1, -j as the integer re + 65536 * im, so that one 32-bit multiply-add
+// per tap filters both components (the low half borrows from the high half when re < 0; tx11b_unborrow undoes it at the end)
+template <uint32_t rate_kbps>
+__device__ __forceinline__ int tx11b_chip(const uint16_t* __restrict__ d, uint32_t n) {
     const unsigned BARKER_NEG = 0x712u;                                                 // bit k set where Barker11[k] = -1 (barkerspread.hpp:7)
     unsigned q; bool flip = false;
     if (n < 2112u || rate_kbps == 1000) {
@@ -125,59 +127,95 @@ __device__ __forceinline__ unsigned tx11b_chip(const uint16_t* __restrict__ d, u
     }
     if (flip) q += 2u;
     q &= 3u;                                                                            // 0: 1, 1: +j, 2: -1, 3: -j
-    const int re = q == 0u ? 1 : q == 2u ? -1 : 0, im = q == 1u ? 1 : q == 3u ? -1 : 0;
-    return (unsigned)(re & 0xFF) | ((unsigned)(im & 0xFF) << 8);
+    return q == 0u ? 1 : q == 2u ? -1 : q == 1u ? 65536 : -65536;
 }
 
 #define SB_TX11B_THREADS 256
 #define SB_TX11B_SPT 8                 // samples per thread
+// pulse.hpp:279-305 evaluated once: h(8) .. h(-11).  The host recomputes them from the reference's formula on every call and refuses
+// to launch if they ever differ (sb200_tx11b_batch); compile-time values let the aligned path drop the eight zero taps.
+#define SB_TX11B_TAPS {-1, 0, 3, 0, -6, 0, 34, 80, 102, 80, 34, 0, -6, 0, 3, 0, -1, 0, 1, 0}
+__host__ __device__ constexpr int tx11b_branch_max(int k) {                              // largest |output| of polyphase branch k for chips in {-1, 0, 1}
+    constexpr int H[20] = SB_TX11B_TAPS; int a = 0;
+    for (int j = 0; j < 5; j++) a += H[4 * j + k] < 0 ? -H[4 * j + k] : H[4 * j + k];
+    return a;
+}
+static_assert(tx11b_branch_max(0) <= 127 && tx11b_branch_max(1) <= 127 && tx11b_branch_max(2) <= 127 && tx11b_branch_max(3) <= 127,
+              "TPackSample16to8 (packsswb) never saturates on this shaper, so the pack is a plain byte extraction");
+__device__ __forceinline__ uint32_t tx11b_unborrow(int t) { return (uint32_t)t + (((uint32_t)t & 0x8000u) << 1); }   // high half := im exactly
+
+// ALIGNED: lead is a multiple of 4, so a thread's 8 samples are the two whole shaper vectors of chips n and n + 1
+template <bool ALIGNED, uint32_t RATE>
 __global__ void __launch_bounds__(SB_TX11B_THREADS) k_tx11b_shape(const uint32_t* __restrict__ pay_len, Tx11bJob job, const uint16_t* __restrict__ desc,
         void* __restrict__ out, uint64_t out_stride /*samples per slot, multiple of 8*/, uint32_t* __restrict__ nsamples) {
-    __shared__ short s_chip[SB_TX11B_THREADS * SB_TX11B_SPT / 4 + 8];
+    __shared__ int s_chip[SB_TX11B_THREADS * SB_TX11B_SPT / 4 + 8];
     const uint32_t f = blockIdx.x;                                                      // frames on x: the y extent stops at 65535
     const uint32_t len = pay_len[f], nc = tx11b_nchips(len, job.chips_per_byte), ns = tx11b_nsamples(nc);
-    const uint64_t s_blk = (uint64_t)blockIdx.y * (SB_TX11B_THREADS * SB_TX11B_SPT);    // first slot sample of this CTA
+    const uint32_t s_blk = blockIdx.y * (SB_TX11B_THREADS * SB_TX11B_SPT);              // first slot sample of this CTA (the host keeps slots below 2^27 samples)
     if (s_blk >= out_stride) return;
     if (blockIdx.y == 0 && threadIdx.x == 0 && nsamples) nsamples[f] = job.lead + ns;
     // chips the CTA's samples lean on: n_lo .. n_lo + count - 1 (four chips of history in front)
-    const long long m_lo = (long long)s_blk - (long long)job.lead;                      // frame-relative index of the CTA's first sample
-    const long long n_lo = (m_lo >= 0 ? m_lo >> 2 : -((-m_lo + 3) >> 2)) - 4;
+    const int m_lo = (int)s_blk - (int)job.lead;                                        // frame-relative index of the CTA's first sample
+    const int n_lo = (m_lo >> 2) - 4;                                                   // arithmetic shift = floor
     const int count = SB_TX11B_THREADS * SB_TX11B_SPT / 4 + 6;
-    const uint16_t* d = desc + (size_t)f * job.desc_stride;
-    for (int i = threadIdx.x; i < count; i += SB_TX11B_THREADS) {
-        const long long n = n_lo + i;
-        s_chip[i] = (n >= 0 && n < (long long)nc) ? (short)tx11b_chip(d, (uint32_t)n, job.rate_kbps) : (short)0;
+    const uint32_t s0 = s_blk + threadIdx.x * SB_TX11B_SPT;
+    const int nvec = (int)nc + 5;                                                       // shaper output vectors, flush included
+    const bool inside = m_lo + SB_TX11B_THREADS * SB_TX11B_SPT > 0 && m_lo < nvec * 4;   // does the CTA touch the frame at all?
+    if (inside) {
+        const uint16_t* d = desc + (size_t)f * job.desc_stride;
+        for (int i = threadIdx.x; i < count; i += SB_TX11B_THREADS) {
+            const int n = n_lo + i;
+            s_chip[i] = (n >= 0 && n < (int)nc) ? tx11b_chip<RATE>(d, (uint32_t)n) : 0;
+        }
     }
     __syncthreads();
-    const uint64_t s0 = s_blk + (uint64_t)threadIdx.x * SB_TX11B_SPT;
     if (s0 >= out_stride) return;
-    int v[2 * SB_TX11B_SPT];
+    uint32_t t[SB_TX11B_SPT];                                                           // per sample: re in the low half, im in the high half
 #pragma unroll
-    for (int i = 0; i < SB_TX11B_SPT; i++) {
-        const long long m = (long long)s0 + i - (long long)job.lead;
-        int re = 0, im = 0;
-        if (m >= 0 && m < (long long)(nc + 5u) * 4) {
-            const int n = (int)((m >> 2) - n_lo), k = (int)(m & 3);
+    for (int i = 0; i < SB_TX11B_SPT; i++) t[i] = 0;
+    if (inside) {
+        if (ALIGNED) {
+            constexpr int H[20] = SB_TX11B_TAPS;
+            const int nA = ((int)s0 - (int)job.lead) >> 2;                                  // exact: both are multiples of 4
 #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const unsigned c = (unsigned short)s_chip[n - j]; const int h = job.taps[4 * j + k];
-                re += (int)(signed char)(c & 0xFFu) * h; im += (int)(signed char)(c >> 8) * h;
+            for (int c = 0; c < 2; c++) {
+                const int n = nA + c;
+                if (n < 0 || n >= nvec) continue;
+                const int loc = n - n_lo;
+                int x[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) x[j] = s_chip[loc - j];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int a = 0;
+#pragma unroll
+                    for (int j = 0; j < 5; j++) if (H[4 * j + k] != 0) a += x[j] * H[4 * j + k];
+                    t[4 * c + k] = tx11b_unborrow(a);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SB_TX11B_SPT; i++) {
+                const int m = (int)s0 + i - (int)job.lead;
+                if (m < 0 || m >= nvec * 4) continue;
+                const int n = (m >> 2) - n_lo, k = m & 3;
+                int a = 0;
+#pragma unroll
+                for (int j = 0; j < 5; j++) a += s_chip[n - j] * (int)job.taps[4 * j + k];
+                t[i] = tx11b_unborrow(a);
             }
         }
-        v[2 * i] = pack8s(re); v[2 * i + 1] = pack8s(im);                               // TPackSample16to8: packsswb
     }
+    // TPackSample16to8 keeps the low byte of each component (never saturates, see above); COMPLEX16 output is that byte << 8
     if (job.fmt16) {
         uint4 a, b;
-        a.x = (uint32_t)((v[0] << 8) & 0xFFFF) | ((uint32_t)(v[1] << 8) << 16); a.y = (uint32_t)((v[2] << 8) & 0xFFFF) | ((uint32_t)(v[3] << 8) << 16);
-        a.z = (uint32_t)((v[4] << 8) & 0xFFFF) | ((uint32_t)(v[5] << 8) << 16); a.w = (uint32_t)((v[6] << 8) & 0xFFFF) | ((uint32_t)(v[7] << 8) << 16);
-        b.x = (uint32_t)((v[8] << 8) & 0xFFFF) | ((uint32_t)(v[9] << 8) << 16); b.y = (uint32_t)((v[10] << 8) & 0xFFFF) | ((uint32_t)(v[11] << 8) << 16);
-        b.z = (uint32_t)((v[12] << 8) & 0xFFFF) | ((uint32_t)(v[13] << 8) << 16); b.w = (uint32_t)((v[14] << 8) & 0xFFFF) | ((uint32_t)(v[15] << 8) << 16);
+        a.x = __byte_perm(t[0], 0, 0x2404); a.y = __byte_perm(t[1], 0, 0x2404); a.z = __byte_perm(t[2], 0, 0x2404); a.w = __byte_perm(t[3], 0, 0x2404);
+        b.x = __byte_perm(t[4], 0, 0x2404); b.y = __byte_perm(t[5], 0, 0x2404); b.z = __byte_perm(t[6], 0, 0x2404); b.w = __byte_perm(t[7], 0, 0x2404);
         uint4* o = (uint4*)((uint32_t*)out + (size_t)f * out_stride + s0);
         o[0] = a; o[1] = b;
     } else {
         uint4 a;
-        auto p4 = [&](int i) { return (uint32_t)(v[i] & 0xFF) | ((uint32_t)(v[i + 1] & 0xFF) << 8) | ((uint32_t)(v[i + 2] & 0xFF) << 16) | ((uint32_t)(v[i + 3] & 0xFF) << 24); };
-        a.x = p4(0); a.y = p4(4); a.z = p4(8); a.w = p4(12);
+        a.x = __byte_perm(t[0], t[1], 0x6420); a.y = __byte_perm(t[2], t[3], 0x6420); a.z = __byte_perm(t[4], t[5], 0x6420); a.w = __byte_perm(t[6], t[7], 0x6420);
         *(uint4*)((uint16_t*)out + (size_t)f * out_stride + s0) = a;
     }
 }

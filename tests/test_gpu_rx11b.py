@@ -48,3 +48,47 @@ def test_edges(eng):
     _cmp(eng, iq.reshape(-1, 2), np.arange(F, dtype=np.uint64) * slot, ln)
     z = np.zeros((2, 5600, 2), np.int16)
     _cmp(eng, z.reshape(-1, 2), np.arange(2, dtype=np.uint64) * 5600, np.full(2, 5600, np.uint32))
+
+
+def _capture_11b(seed, specs, noise=0.0):
+    """A continuous 44 Msps capture: frames made by the transmit oracle (rate, length, corrupt?) separated by silence."""
+    rng = np.random.default_rng(seed); parts = [np.zeros((rng.integers(300, 900) // 4 * 4, 2), np.int16)]; pays = []
+    for rate, L, corrupt in specs:
+        p = rng.integers(0, 256, L).astype(np.uint8); pays.append(p)
+        td = oracle_py.tx11b_modulate(p, rate).astype(np.int16) << 8
+        if corrupt: k = len(td) * 3 // 4; td[k:k + 400] = -td[k:k + 400]
+        parts.append(td); parts.append(np.zeros((int(rng.integers(700, 3000)), 2), np.int16))
+    iq = np.concatenate(parts)
+    if noise: iq = (iq + rng.normal(0, noise, iq.shape)).clip(-32768, 32767).astype(np.int16)
+    return iq, pays
+
+def test_streams_match_oracle_driver(eng):
+    """Continuous captures through sb200_rx11b_streams == the restated MAC11b_Receive loop (oracle Rx11b::run): same events in the
+    same order, same positions, same bytes — including a CRC failure, the seek past the last FCS byte and the carried-over state."""
+    caps = [_capture_11b(1, [(11000, 300, False), (2000, 60, False), (5500, 200, True), (11000, 1000, False), (1000, 40, False)], noise=60.0),
+            _capture_11b(2, [(5500, 500, False), (11000, 77, False)]),
+            _capture_11b(3, [(2000, 100, True), (1000, 30, False), (11000, 1496, False)], noise=120.0),
+            (np.zeros((5000, 2), np.int16), [])]
+    off = np.cumsum([0] + [(len(c[0]) + 3) // 4 * 4 for c in caps[:-1]]).astype(np.uint64)
+    total = int(off[-1]) + len(caps[-1][0]); iq = np.zeros((total, 2), np.int16)
+    for o, c in zip(off, caps): iq[int(o):int(o) + len(c[0])] = c[0]
+    ln = np.array([len(c[0]) for c in caps], np.uint32)
+    res, out, cnt = eng.rx11b_streams(iq, off, ln, max_frames=8, out_stride=2048)
+    nok = 0
+    for s, c in enumerate(caps):
+        ores, oout = oracle_py.rx11b_run(c[0], max_frames=8, out_stride=2048)
+        assert cnt[s] == len(ores), (s, cnt[s], len(ores), res[s, :cnt[s]], ores)
+        for k in range(len(ores)):
+            for fld in ("status", "rate_kbps", "length", "sample_index", "detect_vec"):
+                assert res[s, k][fld] == ores[k][fld], (s, k, fld, res[s, k], ores[k])
+            assert (res[s, k]["crc32"] & 0xFFFFFF) == (ores[k]["crc32"] & 0xFFFFFF)
+            if ores[k]["status"] in (1, 0x80000006):
+                n = int(ores[k]["length"]) - 1                       # the sink stops one byte short of the FCS end (PHY_11b.hpp:728-739)
+                assert (out[s, k, :n] == oout[k, :n]).all(), (s, k)
+            nok += int(ores[k]["status"] == 1)
+        assert (res[s, cnt[s]:]["status"] == 0).all()
+    assert nok >= 7 and cnt[3] == 0
+    # max_frames smaller than the number of events: the first ones, in order
+    res2, _, cnt2 = eng.rx11b_streams(iq, off, ln, max_frames=2, out_stride=64)
+    for s in range(len(caps)):
+        assert cnt2[s] == min(2, cnt[s]) and (res2[s, :cnt2[s]] == res[s, :cnt2[s]]).all()

@@ -77,3 +77,47 @@ def test_11n_device_resident_and_many_slots(eng):
     st = d_res[:, 0].cpu().numpy().astype(np.uint32).reshape(rep, F)
     assert (st == ores["status"][None, :]).all() and (ores["status"] == 1).all()
     assert (d_out.cpu().numpy().reshape(rep, F, 1536)[:, :, :700] == oout[None, :, :700]).all()
+
+
+def _capture_11n(seed, specs):
+    """A continuous two-antenna capture: HT-MF frames (mcs, psdu_len, snr, lead, trail, damage) back to back; damage = None,
+    'data' (a stretch of a data symbol negated: CRC failure) or 'sig' (HT-SIG flattened: header refused)."""
+    a, b = [], []
+    for i, (mcs, L, snr, lead, trail, damage) in enumerate(specs):
+        i0, i1, _ = synth.make_frames_11n(1, psdu_len=L, mcs=mcs, seed0=seed * 1000 + i, snr_db=snr, lead=lead, trail=trail)
+        i0, i1 = i0[0].copy(), i1[0].copy()
+        if damage == "data": i0[lead + 1700:lead + 1800] = -i0[lead + 1700:lead + 1800]; i1[lead + 1700:lead + 1800] = -i1[lead + 1700:lead + 1800]
+        if damage == "sig": i0[lead + 840:lead + 1100] //= 16; i1[lead + 840:lead + 1100] //= 16
+        a.append(i0); b.append(i1)
+    return np.concatenate(a), np.concatenate(b)
+
+def test_streams_match_oracle_driver(eng):
+    """Continuous captures through sb200_rx11n_streams == the restated RxThread loop (oracle Rx11n::run): same events, same order, same
+    positions, same bytes, with TCCA11n / MimoAutoCorr's history carried across frames exactly as the never-reset bricks keep it."""
+    caps = [_capture_11n(1, [(8, 200, 30, 400, 300, None), (9, 500, 28, 250, 420, None), (10, 120, 30, 333, 200, None), (8, 60, 30, 401, 500, None)]),
+            _capture_11n(2, [(9, 300, 26, 500, 180, "data"), (8, 100, 30, 180, 300, None), (10, 700, 30, 222, 100, "sig"), (9, 90, 30, 300, 300, None)]),
+            _capture_11n(3, [(10, 1500, 24, 777, 64, None), (10, 40, 30, 140, 900, None)]),
+            (np.zeros((3000, 2), np.int16), np.zeros((3000, 2), np.int16))]
+    off = np.cumsum([0] + [(len(c[0]) + 3) // 4 * 4 for c in caps[:-1]]).astype(np.uint64)
+    total = int(off[-1]) + len(caps[-1][0]); iq0 = np.zeros((total, 2), np.int16); iq1 = np.zeros((total, 2), np.int16)
+    for o, c in zip(off, caps): iq0[int(o):int(o) + len(c[0])] = c[0]; iq1[int(o):int(o) + len(c[1])] = c[1]
+    ln = np.array([len(c[0]) for c in caps], np.uint32)
+    res, out, sidx, cnt = eng.rx11n_streams(iq0, iq1, off, ln, max_frames=8)
+    nok = 0
+    for s, c in enumerate(caps):
+        ores, oout = oracle_py.rx11n_run(c[0], c[1], max_frames=8, out_stride=1536)
+        assert cnt[s] == len(ores), (s, cnt[s], res[s, :cnt[s]], ores)
+        vec_base = 0; prev = 0
+        for k in range(len(ores)):
+            for fld in ("status", "mcs", "length", "nsym", "cfo_est", "lsig_length"):
+                assert res[s, k][fld] == ores[k][fld], (s, k, fld, res[s, k], ores[k])
+            assert sidx[s, k] == ores[k]["sample_index"], (s, k, sidx[s, k], ores[k]["sample_index"])
+            assert vec_base + res[s, k]["detect_index"] == ores[k]["detect_index"], (s, k)          # the oracle counts 20 Msps vectors since the capture began
+            vec_base += 4 * ((int(sidx[s, k]) - prev) // 8); prev = int(sidx[s, k])
+            if ores[k]["status"] in (1, oracle_py.E_CRC32_FAIL):
+                L = int(ores[k]["length"]); assert res[s, k]["crc32"] == ores[k]["crc32"] and (out[s, k, :L] == oout[k, :L]).all(), (s, k)
+            nok += int(ores[k]["status"] == 1)
+    assert nok >= 8 and cnt[3] == 0
+    # single-capture form of the same call and a max_frames cut-off
+    r1, _, s1, c1 = eng.rx11n_streams(caps[1][0], caps[1][1], [0], [len(caps[1][0])], max_frames=2)
+    assert c1[0] == 2 and (r1[0, :2] == res[1, :2]).all() and (s1[0, :2] == sidx[1, :2]).all()
