@@ -32,30 +32,37 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms (B200_PROFILING.md recipe).  The process is started before the warm-up
+    (nvidia-smi needs up to a second before its first line) and every line is stamped on arrival; stop() keeps the lines that arrived
+    between mark() and stop(), i.e. under the load of the timed steps."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     def __init__(self, index):
-        self.rows = []; self.p = None; self.index = index
+        self.rows = []; self.p = None; self.index = index; self.t0 = None
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.p = None
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+    def mark(self):
+        self.t0 = time.perf_counter()
+    def seen(self):
+        return sum(1 for t, _ in self.rows if self.t0 is not None and t >= self.t0)
     def stop(self):
         if self.p:
             self.p.terminate()
             try: self.p.wait(timeout=2)
             except Exception: pass
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t0 is None or t >= self.t0]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 7:
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"): reasons.add(n)
@@ -162,10 +169,11 @@ def main():
     assert (st == 1).all(), f"rank {rank}: {(st != 1).sum()} slots not FRAME_OK"
     got = out_dev[:U].cpu().numpy()
     assert (got == ps_u).all(), "decoded PSDU bytes differ from the transmitted ones"
+    clocks = ClockSampler(local); clocks.start()
     for _ in range(args.warmup): step_dev()
     torch.cuda.synchronize()
     if dist: dist.barrier()
-    clocks = ClockSampler(local); clocks.start()
+    clocks.mark()
     l0 = eng.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     ktimes = np.zeros(4)
@@ -184,6 +192,9 @@ def main():
         step_dev(); ktimes += np.array(eng.last_kernel_times())
     ktimes /= nk
     eng.set_option("chunk_frames", args.chunk); eng.set_option("chunk_frames_device", args.chunk_device)
+    t_wait = time.perf_counter()                           # a short run can end between two nvidia-smi lines: keep the same load on, untimed, until two have landed
+    while clocks.p and clocks.seen() < 2 and time.perf_counter() - t_wait < 2.0:
+        step_dev(); torch.cuda.synchronize()
     clk = clocks.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
