@@ -1,4 +1,4 @@
-/* sora_b200_legacy.h — the reference's legacy C baseband interface for 802.11a receive, served by the GPU engine.
+/* sora_b200_legacy.h — the reference's legacy C baseband interfaces for 802.11a and 802.11b receive, served by the GPU engine.
  *
  * SURVEY.md §8(f) rank 4.  Same entry-point names, argument order, HRESULT values and result fields as
  *   kernel/inc/bb/bba.h:15-24 (BB11A_* codes), :61-70 (ri_* result fields), :191-262 (BB11ARx* prototypes) and
@@ -65,6 +65,52 @@ HRESULT BB11ARxCarrierSense(PBB11A_RX_CONTEXT pRxContextA, PSORA_RADIO_RX_STREAM
 HRESULT BB11ARxFrameDemod(PBB11A_RX_CONTEXT pRxContextA, PSORA_RADIO_RX_STREAM pRxStream);
 /* not in the reference: selects the legacy 14-bit sample fix (left shift by 2) for old captures such as kernel/test-data/fsample-6.dmp */
 void    BB11ARxSetSampleShift(PBB11A_RX_CONTEXT pRxContextA, unsigned int left_shift);
+
+/* ---- 802.11b: kernel/inc/bb/bbb.h:8-36 (BB11B_* codes), :134-197 (contexts), :199-262 (prototypes); driver loop kernel/bb/demod11/demod11b.cpp:73-174.
+ * Only the fields a caller reads or writes keep their names: thresholds, block counts, reset flags, DC offset, work indicator, and the
+ * BB11bCommon results (b_length = PSDU length incl. FCS, b_dataRate = PLCP SIGNAL code, counters).  Power detection and demodulation are
+ * the brick receive graph of fb11bdemod_config.hpp on the device (energy detector instead of the legacy LH/HL gain logic): BB11BSpd stops
+ * at the block in which that graph's carrier sense fires, BB11BRx returns the frame that follows. */
+#define BB11B_E_ENERGY           ((HRESULT)0x80050100L)
+#define BB11B_E_DOWNSAMPLE       ((HRESULT)0x80050101L)
+#define BB11B_E_BARKER           ((HRESULT)0x80050102L)
+#define BB11B_E_SFD              ((HRESULT)0x80050103L)
+#define BB11B_E_DATA             ((HRESULT)0x80050105L)
+#define BB11B_E_PD_LAG           ((HRESULT)0x80050106L)
+#define BB11B_E_FORCE_STOP       ((HRESULT)0x80050107L)
+#define BB11B_E_PLCP_HEADER_CRC  ((HRESULT)0x80050210L)
+#define BB11B_E_PLCP_HEADER_SIG  ((HRESULT)0x80050211L)
+#define BB11B_OK_FRAME           ((HRESULT)0x0000007FL)
+#define BB11B_OK_POWER_DETECTED  ((HRESULT)0x00000101L)
+#define BB11B_CHANNEL_CLEAN      ((HRESULT)0x00000102L)
+
+typedef struct _SORA_COMPLEX16 { int16_t re, im; } SORA_COMPLEX16;
+typedef struct _BB11B_COMMON {                  /* bbb.h:84-127, result part */
+    unsigned int b_length;                      /* PSDU length incl. CRC-32 */
+    unsigned char b_dataRate;                   /* PLCP SIGNAL: 0x0A, 0x14, 0x37, 0x6E */
+    char b_isLongPreamble;
+    unsigned long b_crc32;
+    unsigned int b_errEnergyLoss, b_errFrame, b_errPLCPHeader, b_goodFrameCounter;
+    PUCHAR b_outputPt; ULONG b_maxOutputSize;
+} BB11B_COMMON, *PBB11B_COMMON;
+typedef struct __BB11B_RX_CONTEXT {             /* bbb.h:134-158 */
+    unsigned int b_maxDescCount; int b_resetFlag; short b_energyLeast; volatile FLAG* b_workIndicator; int b_shiftRight;
+    SORA_COMPLEX16 b_dcOffset;
+    BB11B_COMMON BB11bCommon;
+    void* b200_engine; void* b200_events;
+} BB11B_RX_CONTEXT, *PBB11B_RX_CONTEXT;
+typedef struct _BB11B_SPD_CONTEXT {             /* bbb.h:161-186 */
+    unsigned int b_minDescCount, b_maxDescCount, b_threshold, b_thresholdLH, b_thresholdHL, b_gainLevel, b_gainLevelNext;
+    int b_resetFlag; volatile FLAG* b_workIndicator; SORA_COMPLEX16 b_dcOffset; char b_reestimateOffset; ULONG b_evalEnergy;
+    void* b200_rx;                              /* the receive context initialised together with this one */
+} BB11B_SPD_CONTEXT, *PBB11B_SPD_CONTEXT;
+
+void    BB11BRxSpdContextInit(PBB11B_RX_CONTEXT pRxContext, PBB11B_SPD_CONTEXT pSpdContext, PFLAG pfCanWork, ULONG nRxMaxBlockCount, ULONG nSPDMaxBlockCount,
+                              ULONG nSPDMinBlockCount, ULONG nSPDThreashold, ULONG nSPDThreasholdLow, ULONG nSPDThreasholdHigh, ULONG nShiftRight);
+void    BB11BRxSpdContextCleanUp(PBB11B_RX_CONTEXT pRxContext);
+void    BB11BPrepareRx(PBB11B_RX_CONTEXT pRxContext, void* pOutputBuf, ULONG OutputBufSize);
+HRESULT BB11BSpd(PBB11B_SPD_CONTEXT pSpdContext, PSORA_RADIO_RX_STREAM pRxStream);
+HRESULT BB11BRx(PBB11B_RX_CONTEXT pRxContext, PSORA_RADIO_RX_STREAM pRxStream);
 
 #ifdef __cplusplus
 }

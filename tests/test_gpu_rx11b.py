@@ -92,3 +92,51 @@ def test_streams_match_oracle_driver(eng):
     res2, _, cnt2 = eng.rx11b_streams(iq, off, ln, max_frames=2, out_stride=64)
     for s in range(len(caps)):
         assert cnt2[s] == min(2, cnt[s]) and (res2[s, :cnt2[s]] == res[s, :cnt2[s]]).all()
+
+
+def test_legacy_c_api_shim_11b():
+    """The driver loop of kernel/bb/demod11/demod11b.cpp:73-174 (BB11BSpd until power is detected, BB11BRx until the frame is settled)
+    written against include/sora_b200_legacy.h via ctypes, over RX_BLOCKs holding frames from the transmit oracle."""
+    import ctypes as C
+    lib = api.load_library()
+    class Stream(C.Structure): _fields_ = [("start", C.c_void_p), ("size", C.c_uint32), ("end", C.c_void_p), ("scan", C.c_void_p), ("mask", C.c_uint32)]
+    class C16(C.Structure): _fields_ = [("re", C.c_int16), ("im", C.c_int16)]
+    class Common(C.Structure):
+        _fields_ = [("b_length", C.c_uint), ("b_dataRate", C.c_ubyte), ("b_isLongPreamble", C.c_char), ("b_crc32", C.c_ulong), ("b_errEnergyLoss", C.c_uint), ("b_errFrame", C.c_uint),
+                    ("b_errPLCPHeader", C.c_uint), ("b_goodFrameCounter", C.c_uint), ("b_outputPt", C.c_void_p), ("b_maxOutputSize", C.c_uint32)]
+    class Rx(C.Structure):
+        _fields_ = [("b_maxDescCount", C.c_uint), ("b_resetFlag", C.c_int), ("b_energyLeast", C.c_short), ("b_workIndicator", C.c_void_p), ("b_shiftRight", C.c_int), ("b_dcOffset", C16),
+                    ("BB11bCommon", Common), ("engine", C.c_void_p), ("events", C.c_void_p)]
+    class Spd(C.Structure):
+        _fields_ = [("b_minDescCount", C.c_uint), ("b_maxDescCount", C.c_uint), ("b_threshold", C.c_uint), ("b_thresholdLH", C.c_uint), ("b_thresholdHL", C.c_uint), ("b_gainLevel", C.c_uint),
+                    ("b_gainLevelNext", C.c_uint), ("b_resetFlag", C.c_int), ("b_workIndicator", C.c_void_p), ("b_dcOffset", C16), ("b_reestimateOffset", C.c_char), ("b_evalEnergy", C.c_ulong),
+                    ("rx", C.c_void_p)]
+    for f in ("BB11BSpd", "BB11BRx"): getattr(lib, f).restype = C.c_int32
+    cap, pays = _capture_11b(5, [(11000, 400, False), (2000, 90, False), (5500, 150, True), (1000, 33, False)], noise=40.0)
+    cap = cap[: len(cap) // 28 * 28]
+    blocks = np.zeros((len(cap) // 28, 128), np.uint8); blocks[:, 0] = 1; blocks[:, 16:] = np.ascontiguousarray(cap).reshape(-1, 28 * 2).view(np.uint8)
+    ores, oout = oracle_py.rx11b_run(cap, max_frames=16, out_stride=4096)
+    frames = [(int(o["status"]), int(o["length"]), int(o["rate_kbps"]), ob) for o, ob in zip(ores, oout) if o["status"] in (1, oracle_py.E_CRC32_FAIL)]
+    work = C.c_uint32(1); outbuf = np.zeros(4096, np.uint8)
+    st = Stream(); rx = Rx(); spd = Spd()
+    lib.SoraGenRadioRxStreamOffline(C.byref(st), C.c_void_p(blocks.ctypes.data), C.c_uint32(blocks.size))
+    lib.BB11BRxSpdContextInit(C.byref(rx), C.byref(spd), C.byref(work), 0xFFFFFFF, blocks.shape[0], 15, 4000, 4000, 4000, 0)
+    lib.BB11BPrepareRx(C.byref(rx), C.c_void_p(outbuf.ctypes.data), 4096)
+    got = []; done = False
+    for _ in range(1000):
+        spd.b_resetFlag = 1
+        hr = lib.BB11BSpd(C.byref(spd), C.byref(st))
+        if hr != 0x101: break                              # BB11B_CHANNEL_CLEAN: the offline loop ends (demod11b.cpp:102-103)
+        rx.b_resetFlag = 1
+        for _ in range(8):
+            hr = lib.BB11BRx(C.byref(rx), C.byref(st)) & 0xFFFFFFFF
+            if hr in (0x7F, 0x80050105): got.append((hr, rx.BB11bCommon.b_length, rx.BB11bCommon.b_dataRate, outbuf[:rx.BB11bCommon.b_length].copy()))
+            if hr in (0x7F, 0x80050105, 0x80050100, 0x80050103): break     # demod11b.cpp:172-173
+            rx.b_resetFlag = 0
+    good = rx.BB11bCommon.b_goodFrameCounter; bad = rx.BB11bCommon.b_errFrame
+    lib.BB11BRxSpdContextCleanUp(C.byref(rx))
+    assert len(got) == len(frames) == 4, (len(got), len(frames), [hex(g[0]) for g in got])
+    code = {1000: 0x0A, 2000: 0x14, 5500: 0x37, 11000: 0x6E}
+    for (hr, n, rc, by), (stt, L, rate, ob) in zip(got, frames):
+        assert hr == (0x7F if stt == 1 else 0x80050105) and n == L and rc == code[rate] and (by[:L - 1] == ob[:L - 1]).all()
+    assert good == 3 and bad == 1
