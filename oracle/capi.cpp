@@ -3,6 +3,7 @@
 #include "rx11n.h"
 #include "tx11a.h"
 #include "tx11b.h"
+#include "tx11n.h"
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -193,6 +194,13 @@ uint64_t sbo_tx11b_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_
 }
 uint32_t sbo_tx11b_nsamples(uint32_t len, uint32_t rate_kbps) { return tx11b_nsamples(len, rate_kbps); }
 void sbo_tx11b_taps(int16_t* out20) { tx11b_taps(out20); }
+
+// ---- 802.11n transmit ---------------------------------------------------------------------------------------------------
+uint64_t sbo_tx11n_modulate(const uint8_t* payload, uint32_t len, uint32_t mcs, uint8_t seed, int16_t* out0, int16_t* out1, uint64_t cap_samples) {
+    return tx11n_modulate(payload, len, mcs, seed, (c16*)out0, (c16*)out1, (size_t)cap_samples);
+}
+uint32_t sbo_tx11n_nsym(uint32_t len, uint32_t mcs, uint32_t* signalled) { return tx11n_nsym(len, mcs, signalled); }
+void sbo_tx11n_preamble_tables(int16_t* lstf, int16_t* lltf, int16_t* htstf, int16_t* htltf) { tx11n_preamble_tables((c16*)lstf, (c16*)lltf, (c16*)htstf, (c16*)htltf); }
 
 uint32_t sbo_crc32(const uint8_t* p, uint64_t n) { uint32_t c = 0xFFFFFFFFu; for (uint64_t i = 0; i < n; i++) c = (c >> 8) ^ tables().crc32_lut[p[i] ^ (c & 0xFF)]; return ~c; }
 

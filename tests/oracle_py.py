@@ -166,3 +166,19 @@ def tx11b_modulate(payload, rate_kbps, init_phase=0, return_phase=False):
 
 def tx11b_taps():
     o = np.zeros(20, np.int16); lib().sbo_tx11b_taps(_p(o)); return o
+
+
+# ---- 802.11n transmit (brick modulator restatement) ---------------------------------------------------------------------
+def tx11n_modulate(payload, mcs, seed=0xAB):
+    """payload: MPDU bytes without FCS.  Returns two int16 [n, 2] streams at 40 Msps (what `demod11` writes to *_0.dmp / *_1.dmp)."""
+    payload = np.ascontiguousarray(payload, dtype=np.uint8); L = lib(); L.sbo_tx11n_modulate.restype = C.c_uint64
+    sig = C.c_uint32(0); nsym = L.sbo_tx11n_nsym(C.c_uint32(len(payload)), C.c_uint32(mcs), C.byref(sig)); assert nsym, "mcs must be 8, 9 or 10"
+    cap = 640 + 480 + 480 + 160 * nsym
+    o0 = np.zeros((cap, 2), np.int16); o1 = np.zeros((cap, 2), np.int16)
+    n = L.sbo_tx11n_modulate(_p(payload), C.c_uint32(len(payload)), C.c_uint32(mcs), C.c_uint8(seed), _p(o0), _p(o1), C.c_uint64(cap))
+    assert n == cap, (n, cap)
+    return o0, o1
+
+def tx11n_preamble_tables():
+    a = np.zeros((320, 2), np.int16); b = np.zeros((320, 2), np.int16); c = np.zeros((160, 2), np.int16); d = np.zeros((160, 2), np.int16)
+    lib().sbo_tx11n_preamble_tables(_p(a), _p(b), _p(c), _p(d)); return a, b, c, d
