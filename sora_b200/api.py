@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -160,6 +160,23 @@ class Engine:
         sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint8)
         self.tx11a_raw(_ptr(flat), max(int(lens.sum()), 1), _ptr(offs), _ptr(lens), 0 if sd is None else _ptr(sd), len(lens), rate_kbps, lead, sample_bits, _ptr(out), out_stride, _ptr(ns))
         return out, ns
+
+    def tx11n_raw(self, pay_ptr, pay_total, off_ptr, len_ptr, seed_ptr, nframes, mcs, lead, out0_ptr, out1_ptr, out_stride, ns_ptr, stream=0):
+        self._check(self._lib.sb200_tx11n_batch(self._h, C.c_void_p(pay_ptr), C.c_uint64(pay_total), C.c_void_p(off_ptr), C.c_void_p(len_ptr), C.c_void_p(seed_ptr), C.c_uint32(nframes),
+                                                C.c_uint32(mcs), C.c_uint32(lead), C.c_void_p(out0_ptr), C.c_void_p(out1_ptr), C.c_uint64(out_stride), C.c_void_p(ns_ptr),
+                                                C.c_void_p(stream)), "sb200_tx11n_batch")
+
+    def tx11n_batch(self, payloads, mcs, seeds=None, lead=0, out_stride=None):
+        """payloads: list of uint8 arrays (MPDUs without FCS) -> (stream 0 [F, out_stride, 2] int16, stream 1, nsamples [F]) at 40 Msps."""
+        lens = np.array([len(p) for p in payloads], np.uint32); offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.uint64)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(p, np.uint8) for p in payloads]) if lens.sum() else np.zeros(1, np.uint8))
+        if out_stride is None:
+            nd = {8: 52, 9: 104, 10: 156}.get(mcs, 52)
+            out_stride = lead + 1600 + 160 * (-(-((int(lens.max()) + 4) * 8 + 22) // nd) + 1)
+        o0 = np.zeros((len(lens), out_stride, 2), np.int16); o1 = np.zeros_like(o0); ns = np.zeros(len(lens), np.uint32)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint8)
+        self.tx11n_raw(_ptr(flat), max(int(lens.sum()), 1), _ptr(offs), _ptr(lens), 0 if sd is None else _ptr(sd), len(lens), mcs, lead, _ptr(o0), _ptr(o1), out_stride, _ptr(ns))
+        return o0, o1, ns
 
     def tx11b_raw(self, pay_ptr, pay_total, off_ptr, len_ptr, nframes, rate_kbps, init_phase, lead, bits, out_ptr, out_stride, ns_ptr, stream=0, fp_ptr=0):
         self._check(self._lib.sb200_tx11b_batch(self._h, C.c_void_p(pay_ptr), C.c_uint64(pay_total), C.c_void_p(off_ptr), C.c_void_p(len_ptr), C.c_uint32(nframes),

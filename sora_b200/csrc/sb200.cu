@@ -6,6 +6,7 @@
 #include "rx11n_kernels.cuh"
 #include "tx11a_kernels.cuh"
 #include "tx11b_kernels.cuh"
+#include "tx11n_kernels.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -68,7 +69,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
-    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx;   // 802.11a transmit tables (built on first use) and staging
+    DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx, tabtx11n, txout1; DevTablesTx11n XN{};   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
@@ -154,7 +155,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -873,6 +874,116 @@ extern "C" int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64
     if (!out_dev) { CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (nsamples && !ns_dev) { CK(cudaMemcpyAsync(nsamples, d_ns, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (final_phase && !fp_dev) { CK(cudaMemcpyAsync(final_phase, d_fp, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (sync) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+// 802.11n transmit (tx11n_kernels.cuh)
+static int upload_tables_tx11n(sb200_handle* h) {
+    if (h->tabtx11n.p) return SB200_OK;
+    // the four preamble tables (Brick11/src/_b_lstf.h, _b_lltf.h, _b_htstf.h, _b_htltf.h) from their defining formula: 128-point inverse DFTs of
+    // the L-STF / L-LTF / HT-LTF tone sets, equal power, one common amplitude (fitted: the literal tables fix it to 362.0592 +- 0.0001)
+    const double A = 362.0592, PI_ = 3.14159265358979323846;
+    static const int8_t L[53] = {1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,0,
+                                 1,-1,-1,1,1,-1,1,-1,1,-1,-1,-1,-1,-1,1,1,-1,-1,1,-1,1,-1,1,1,1,1};
+    std::vector<double> Sre(3 * 128, 0.0), Sim(3 * 128, 0.0);
+    static const int stf_k[12] = {-24, -20, -16, -12, -8, -4, 4, 8, 12, 16, 20, 24}; static const int stf_s[12] = {1, -1, 1, -1, -1, 1, -1, -1, 1, 1, 1, 1};
+    for (int i = 0; i < 12; i++) { Sre[(stf_k[i] + 128) % 128] = stf_s[i]; Sim[(stf_k[i] + 128) % 128] = stf_s[i]; }
+    for (int k = -26; k <= 26; k++) Sre[128 + (k + 128) % 128] = L[k + 26];
+    for (int k = -28; k <= 28; k++) Sre[256 + (k + 128) % 128] = k == -28 || k == -27 ? 1 : k == 27 || k == 28 ? -1 : L[k + 26];
+    auto gen = [&](int set, double scale, int n0, int count, uint32_t* out) {
+        for (int i = 0; i < count; i++) {
+            const int n = n0 + i; double re = 0, im = 0;
+            for (int k = 0; k < 128; k++) {
+                const double sr = Sre[set * 128 + k], si = Sim[set * 128 + k];
+                if (sr == 0 && si == 0) continue;
+                const double ph = 2 * PI_ * (double)((((long long)k * n) % 128 + 128) % 128) / 128, c = cos(ph), sn = sin(ph);
+                re += sr * c - si * sn; im += sr * sn + si * c;
+            }
+            out[i] = pack(mk((int)lround(re * scale), (int)lround(im * scale)));
+        }
+    };
+    std::vector<uint32_t> lstf(320), lltf(320), htstf(160), htltf(160), pre(2 * 1120);
+    gen(0, A, 0, 320, lstf.data()); gen(1, A * sqrt(24.0 / 52.0), -64, 320, lltf.data()); gen(0, A, -32, 160, htstf.data()); gen(2, A * sqrt(24.0 / 56.0), -32, 160, htltf.data());
+    auto negw = [](uint32_t w) { const cs16 c = unpack(w); return pack(mk(-c.re, -c.im)); };
+    // stream 1 (preamble11n.hpp:22-37,56-76): tables as they are, second HT-LTF negated; stream 2: 200 ns / 400 ns cyclic delays
+    for (int i = 0; i < 320; i++) { pre[i] = lstf[i]; pre[320 + i] = lltf[i]; pre[1120 + (i + 8) % 320] = lstf[i]; }
+    for (int i = 0; i < 256; i++) pre[1120 + 320 + 64 + i] = lltf[64 + i - 8];
+    for (int i = 0; i < 64; i++) pre[1120 + 320 + i] = pre[1120 + 320 + 256 + i];
+    for (int i = 0; i < 160; i++) { pre[640 + i] = htstf[i]; pre[800 + i] = htltf[i]; pre[960 + i] = negw(htltf[i]); pre[1120 + 640 + (i + 16) % 160] = htstf[i]; }
+    for (int r = 0; r < 2; r++) { uint32_t* o = pre.data() + 1120 + 800 + 160 * r; for (int i = 0; i < 128; i++) o[32 + i] = htltf[32 + i - 16]; for (int i = 0; i < 32; i++) o[i] = o[128 + i]; }
+    // inverse of T11Interleave<52 N_BPSC, N_BPSC, 13, 11, I_SS> (interleave.hpp:33-60): air position -> stream bit
+    std::vector<uint8_t> inv(4 * 104, 0);
+    for (int bi = 0; bi < 2; bi++) for (int iss = 1; iss <= 2; iss++) {
+        const int nbpsc = bi + 1, ncbps = 52 * nbpsc, ncol = 13, nrot = 11, ns = 1;
+        for (int k = 0; k < ncbps; k++) {
+            const int i = ncbps / ncol * (k % ncol) + k / ncol, j = ns * (i / ns) + (i + ncbps - ncol * i / ncbps) % ns;
+            const int r = (ncbps + j - (((iss - 1) * 2) % 3 + 3 * ((iss - 1) / 3)) * nrot * nbpsc) % ncbps;
+            inv[(bi * 2 + iss - 1) * 104 + r] = (uint8_t)k;
+        }
+    }
+    cudaError_t e = h->tabtx11n.need(pre.size() * 4 + 512);
+    if (e != cudaSuccess) return h->fail(SB200_E_NOMEM, "cudaMalloc tx11n tables", e);
+    char* base = (char*)h->tabtx11n.p;
+    e = cudaMemcpy(base, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + pre.size() * 4, inv.data(), inv.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { h->tabtx11n.release(); return h->fail(SB200_E_CUDA, "tx11n table upload", e); }
+    h->XN.pre = (const uint32_t*)base; h->XN.inv = (const uint8_t*)(base + pre.size() * 4);
+    return SB200_OK;
+}
+
+extern "C" int sb200_tx11n_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_total, const uint64_t* pay_off, const uint32_t* pay_len, const uint8_t* seeds,
+                                 uint32_t nframes, uint32_t mcs, uint32_t lead_samples, int16_t* out0, int16_t* out1, uint64_t out_stride_samples,
+                                 uint32_t* nsamples, void* cuda_stream) {
+    if (!h || !payload || !pay_off || !pay_len || !out0 || !out1) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (nframes == 0) return SB200_OK;
+    Tx11nJob job{}; job.mcs = mcs; job.lead = lead_samples;
+    switch (mcs) {                                      // ieee80211const.h:35-55; the range the receiver accepts (PHY_11n.hpp:496-501)
+        case 8:  job.nbpsc = 1; job.code_rate = CR_12; job.ndbps = 52;  job.enc_in = 1; job.parse_in = 13; break;
+        case 9:  job.nbpsc = 2; job.code_rate = CR_12; job.ndbps = 104; job.enc_in = 1; job.parse_in = 26; break;
+        case 10: job.nbpsc = 2; job.code_rate = CR_34; job.ndbps = 156; job.enc_in = 3; job.parse_in = 26; break;
+        default: return h->fail(SB200_E_INVALID, "mcs must be 8, 9 or 10");
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_tables_tx(h); if (rc != SB200_OK) return rc;
+    rc = upload_tables_tx11n(h); if (rc != SB200_OK) return rc;
+    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    const bool off_dev = is_device_ptr(pay_off), len_dev = is_device_ptr(pay_len), pay_dev = is_device_ptr(payload), out_dev = is_device_ptr(out0);
+    if (out_dev != is_device_ptr(out1)) return h->fail(SB200_E_INVALID, "both output buffers must live on the same side");
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), pay_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), pay_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), pay_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), pay_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    uint32_t max_nsym = 0;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if (lenh[i] + 4u > 4095u || offh[i] + lenh[i] > payload_total) return h->fail(SB200_E_INVALID, "payload slot out of range");
+        const uint32_t ns = tx11n_nsym_emitted(lenh[i], job, nullptr, nullptr);
+        if ((uint64_t)lead_samples + 1600u + 160ull * ns > out_stride_samples) return h->fail(SB200_E_INVALID, "out_stride_samples too small for the frame");
+        if (ns > max_nsym) max_nsym = ns;
+    }
+    job.max_sym = 3u + max_nsym;
+    const uint8_t* d_pay; const uint64_t* d_off; const uint32_t* d_len; const uint8_t* d_seed = nullptr;
+    if (pay_dev) d_pay = payload; else { CK(h->txpay.need(payload_total)); CK(cudaMemcpyAsync(h->txpay.p, payload, payload_total, cudaMemcpyHostToDevice, st)); d_pay = (const uint8_t*)h->txpay.p; }
+    if (off_dev) d_off = pay_off; else { CK(h->txoff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->txoff.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->txoff.p; }
+    if (len_dev) d_len = pay_len; else { CK(h->txlen.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->txlen.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->txlen.p; }
+    if (seeds) { if (is_device_ptr(seeds)) d_seed = seeds; else { CK(h->txseed.need(nframes)); CK(cudaMemcpyAsync(h->txseed.p, seeds, nframes, cudaMemcpyHostToDevice, st)); d_seed = (const uint8_t*)h->txseed.p; } }
+    const size_t out_bytes = (size_t)nframes * out_stride_samples * 4;
+    uint32_t* d_o0 = (uint32_t*)out0; uint32_t* d_o1 = (uint32_t*)out1;
+    if (!out_dev) { CK(h->txout.need(out_bytes)); CK(h->txout1.need(out_bytes)); d_o0 = (uint32_t*)h->txout.p; d_o1 = (uint32_t*)h->txout1.p; }
+    uint32_t* d_ns = nullptr; const bool ns_dev = nsamples && is_device_ptr(nsamples);
+    if (nsamples) { if (ns_dev) d_ns = nsamples; else { CK(h->txns.need(nframes * 4ull)); d_ns = (uint32_t*)h->txns.p; } }
+    const unsigned helpers = 8;
+    dim3 grid(nframes, (2u * job.max_sym + helpers + SB_TX11N_WARPS - 1) / SB_TX11N_WARPS);
+    CK(cudaEventRecord(h->ev0, st));
+    CK(h->crc.need(nframes * 4ull));
+    k_tx11a_crc<<<(nframes + 127) / 128, 128, 0, st>>>(d_pay, d_off, d_len, nframes, h->T, (uint32_t*)h->crc.p);
+    k_tx11n<<<grid, 32 * SB_TX11N_WARPS, 0, st>>>(d_pay, d_off, d_len, d_seed, nframes, job, h->T, h->X, h->XN, h->inv_deint, (const uint32_t*)h->crc.p, d_o0, d_o1, out_stride_samples, d_ns);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 0; h->launches += 2;
+    CK(cudaGetLastError());
+    bool sync = false;
+    if (!out_dev) { CK(cudaMemcpyAsync(out0, d_o0, out_bytes, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(out1, d_o1, out_bytes, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (nsamples && !ns_dev) { CK(cudaMemcpyAsync(nsamples, d_ns, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (sync) CK(cudaStreamSynchronize(st));
     return SB200_OK;
 }
