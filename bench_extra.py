@@ -6,6 +6,7 @@
   --config 11b       config #3: 802.11b 11 Mbps CCK RX chain, PSDU 1500 B, 44 Msps, one frame per slot
   --config tx11a     SURVEY.md §8(f) rank 2: the 802.11a modulator on the device, 54 Mbps / 1500 B frames into config #2's slots
   --config tx11b     SURVEY.md §8(f) rank 2: the 802.11b modulator on the device, 11 Mbps CCK / 1500 B frames at 44 Msps
+  --config tx11n     the 802.11n two-stream modulator on the device, MCS 8 / 9 / 10, 1500 B frames: the input of config #4 made on the device
   --config 11n       config #4: 802.11n HT-MF 2x2 RX chain at MCS 8, 9, 10, PSDU 1500 B, 2 x 40 Msps, fixed 2x2 channel
 
 Each prints one JSON line per measurement (same timing rules as bench.py: >= 3 warm-ups, CUDA events on the launch
@@ -221,11 +222,46 @@ def bench_tx11b(args):
                       "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msamples/s", "cores": ncpu, "kind": "port", "sample": f"{n} frames (python threads around the C oracle)"},
                       "parity": "bit-exact vs the transmit oracle on 4 frames; every slot decodes FRAME_OK through the 802.11b receive path"}))
 
+def bench_tx11n(args):
+    import torch, oracle_py
+    from sora_b200 import api
+    eng = api.Engine(0); dev = torch.device("cuda", 0); st = torch.cuda.current_stream()
+    F, L = args.frames, 1496
+    rng = np.random.default_rng(12)
+    pay = rng.integers(0, 256, (256, L)).astype(np.uint8)
+    d_pay = torch.from_numpy(pay).to(dev).repeat((F + 255) // 256, 1)[:F].contiguous()
+    d_off = torch.arange(F, dtype=torch.int64, device=dev) * L; d_len = torch.full((F,), L, dtype=torch.int32, device=dev)
+    for mcs in (8, 9, 10):
+        nd = {8: 52, 9: 104, 10: 156}[mcs]; nsym = -(-((L + 4) * 8 + 22) // nd) + 1
+        lead = 400; slot = (lead + 1600 + 160 * nsym + 200 + 27) // 28 * 28
+        d0 = torch.zeros((F, slot, 2), dtype=torch.int16, device=dev); d1 = torch.zeros_like(d0)
+        def step(): eng.tx11n_raw(d_pay.data_ptr(), F * L, d_off.data_ptr(), d_len.data_ptr(), 0, F, mcs, lead, d0.data_ptr(), d1.data_ptr(), slot, 0, st.cuda_stream)
+        step(); torch.cuda.synchronize()
+        for i in range(3):
+            w0, w1 = oracle_py.tx11n_modulate(pay[i], mcs)
+            assert (d0[i, lead:lead + len(w0)].cpu().numpy() == w0).all() and (d1[i, lead:lead + len(w1)].cpu().numpy() == w1).all(), "GPU modulator differs from the oracle"
+        s_off = torch.arange(F, dtype=torch.int64, device=dev) * slot; s_len = torch.full((F,), slot, dtype=torch.int32, device=dev)
+        d_out = torch.zeros((F, 1536), dtype=torch.uint8, device=dev); d_res = torch.zeros((F, 7), dtype=torch.int32, device=dev)
+        eng.rx11n_raw(d0.data_ptr(), d1.data_ptr(), F * slot, s_off.data_ptr(), s_len.data_ptr(), F, d_out.data_ptr(), 1536, d_res.data_ptr(), st.cuda_stream); torch.cuda.synchronize()
+        assert bool((d_res[:, 0] == 1).all()) and (d_out[:256, :L].cpu().numpy() == pay).all()
+        for _ in range(3): step()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(st)
+        for _ in range(args.steps): step()
+        e1.record(st); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        alg = F * (L + 2 * slot * 4.0)
+        print(json.dumps({"metric": "802.11n 2-stream TX PHY Msample-pairs/s (bytes in, 2 x IQ out)", "mcs": mcs, "value": F * slot / (ms * 1e-3) / 1e6, "unit": "Msample-pairs/s", "ms_per_step": ms, "n_gpus": 1,
+                          "config": {"workload": "802.11n HT-MF two-stream modulator, PSDU 1500 B, two COMPLEX16 slots of %d samples at 40 Msps per frame" % slot, "frames_per_step": F},
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks()},
+                          "parity": "bit-exact vs the transmit oracle on 3 frames; every slot pair decodes FRAME_OK through the 802.11n receive path"}))
+        del d0, d1
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b"], required=True)
+    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b", "tx11n"], required=True)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--blocks", type=int, default=32768)
     ap.add_argument("--frames", type=int, default=32768)
     a = ap.parse_args()
-    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b}[a.config](a)
+    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b, "tx11n": bench_tx11n}[a.config](a)

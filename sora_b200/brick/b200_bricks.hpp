@@ -22,6 +22,7 @@
 //
 //   TB200Dot11aTx<T_CTX, T_NEXT>   source brick replacing both transmit graphs of kernel/bb/demod11/fb11amod_config.hpp:75-158
 //   TB200Dot11bTx<T_CTX, T_NEXT>   source brick replacing the transmit graph of kernel/bb/demod11/fb11bmod_config.hpp:19-45
+//   TB200Dot11nTx<T_CTX, T_NEXT>   source brick replacing the four transmit graphs of kernel/bb/demod11/fb11nmod_config.hpp:74-171
 //       (TTS11aSrc | TBB11aSrc, T11aSc, TBB11aMRSelect, TConvEncode_*, T11aInterleave*, TMap11a*, T11aAddPilot, TIFFTx, TPackSample16to8):
 //     one Process() modulates the MPDU in CF_TxFrameBuffer at CF_11aTxVector::data_rate_kbps with CF_ScramblerSeed::sc_seed and pushes
 //     the whole PPDU (preamble + SIGNAL + DATA) downstream as COMPLEX8 x 8 bursts, what TPackSample16to8 hands to TModSink.
@@ -302,5 +303,52 @@ public:
         for (uint32_t i = 0; i + 8 <= ns; i += 8) { memcpy(opin().append(), td + 2 * i, 16); this->Next()->Process(opin()); }
         last_phase = fin;                                          // the reference never resets it between frames (barkerspread.hpp:99-100, cck.hpp:864)
         return false;
+    }
+};
+
+
+// 802.11n two-stream transmit: the preamble, SIG and DATA graphs of fb11nmod_config.hpp as one source brick with a two-stream output port
+// (vectors of 4 COMPLEX16 per stream, what the two TModSink1 sinks of the reference take).  Context: CF_11nTxVector, CF_TxFrameBuffer,
+// CF_ScramblerSeed, CF_Error — the fields BB11nModCtx::init fills (fb11nmod_config.hpp:31-53).
+DEFINE_LOCAL_CONTEXT(TB200Dot11nTx, CF_Error, CF_11nTxVector, CF_TxFrameBuffer, CF_ScramblerSeed);
+template <TSOURCE_ARGS>
+class TB200Dot11nTx : public TSource<TSOURCE_PARAMS> {
+    CTX_VAR_RW(ulong, error_code)
+    CTX_VAR_RO(ushort, frame_length) CTX_VAR_RO(ushort, mcs_index)
+    CTX_VAR_RO(uchar*, mpdu_buf0) CTX_VAR_RO(ushort, mpdu_buf_size0) CTX_VAR_RO(uchar*, mpdu_buf1) CTX_VAR_RO(ushort, mpdu_buf_size1)
+    CTX_VAR_RO(uchar, sc_seed)
+    sb200_handle* h_; std::vector<uchar> mpdu_; std::vector<int16_t> td_[2];
+public:
+    static const size_t NSTREAM = 2;
+    DEFINE_OPORT(COMPLEX16, 4, NSTREAM);
+    REFERENCE_LOCAL_CONTEXT(TB200Dot11nTx);
+    STD_TSOURCE_CONSTRUCTOR(TB200Dot11nTx)
+        BIND_CONTEXT(CF_Error::error_code, error_code)
+        BIND_CONTEXT(CF_11nTxVector::frame_length, frame_length) BIND_CONTEXT(CF_11nTxVector::mcs_index, mcs_index)
+        BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf0, mpdu_buf0) BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf_size0, mpdu_buf_size0)
+        BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf1, mpdu_buf1) BIND_CONTEXT(CF_TxFrameBuffer::mpdu_buf_size1, mpdu_buf_size1)
+        BIND_CONTEXT(CF_ScramblerSeed::sc_seed, sc_seed)
+        , h_(nullptr)
+    {
+        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+    }
+    ~TB200Dot11nTx() { sb200_destroy(h_); }
+    STD_TSOURCE_RESET() { }
+    STD_TSOURCE_FLUSH() { }
+    bool Process() override {
+        if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        error_code = E_ERROR_SUCCESS;
+        if (!mpdu_buf0 || (mpdu_buf_size1 > 0 && !mpdu_buf1) || (uint)mpdu_buf_size0 + mpdu_buf_size1 != frame_length) { error_code = E_ERROR_PARAMETER; return false; }   // TBB11nSrc::Preprocess
+        mpdu_.assign(mpdu_buf0, mpdu_buf0 + mpdu_buf_size0); if (mpdu_buf_size1) mpdu_.insert(mpdu_.end(), mpdu_buf1, mpdu_buf1 + mpdu_buf_size1);
+        const uint64_t off = 0; const uint32_t len = frame_length; uint32_t ns = 0; const uchar seed = sc_seed;
+        const size_t cap = 1600 + 160 * (size_t)(2 + ((len + 4) * 8 + 22) / 52);            // enough for MCS 8
+        td_[0].assign(2 * cap, 0); td_[1].assign(2 * cap, 0);
+        if (sb200_tx11n_batch(h_, mpdu_.empty() ? (const uint8_t*)"" : mpdu_.data(), mpdu_.size() ? mpdu_.size() : 1, &off, &len, &seed, 1, (uint32_t)mcs_index, 0,
+                              td_[0].data(), td_[1].data(), cap, &ns, nullptr) != SB200_OK) { error_code = E_ERROR_PARAMETER; return false; }
+        for (uint32_t i = 0; i + 4 <= ns; i += 4) {
+            for (size_t s = 0; s < NSTREAM; s++) memcpy(opin().write(s), td_[s].data() + 2 * i, 16);
+            opin().append(); this->Next()->Process(opin());
+        }
+        return false;                                              // one PPDU per Process(), like the four graphs run back to back (fb11n_mod.cpp:44-70)
     }
 };

@@ -8,6 +8,7 @@
 //   CF_HTRxVector                kernel/bb/Brick11/src/ieee80211facade.hpp:269-272
 //   CF_11aTxVector, CF_TxFrameBuffer, CF_ScramblerSeed   ieee80211facade.hpp:140-146, 87-92, 116-119
 //   CF_11bTxVector, CF_DifferentialMap                   ieee80211facade.hpp:78-85, 94-98
+//   CF_11nTxVector                                       ieee80211facade.hpp:262-267
 // plus the E_ERROR_* codes (stdfacade.h:10-12, ieee80211facade.hpp:10-19).
 #pragma once
 #include "brick.hpp"
@@ -66,3 +67,4 @@ class CF_TxFrameBuffer { FACADE_FIELD(uchar*, mpdu_buf0) FACADE_FIELD(ushort, mp
 class CF_ScramblerSeed { FACADE_FIELD(uchar, sc_seed) };
 class CF_11bTxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(uchar, preamble_type) FACADE_FIELD(uchar, mod_select) FACADE_FIELD(ulong, data_rate_kbps) FACADE_FIELD(ulong, crc32) };
 class CF_DifferentialMap { FACADE_FIELD(uint, last_phase) };
+class CF_11nTxVector { FACADE_FIELD(ushort, frame_length) FACADE_FIELD(ulong, crc32) FACADE_FIELD(ushort, coding_rate) FACADE_FIELD(ushort, mcs_index) };
