@@ -185,6 +185,9 @@ int sb200_rx11n_taps(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
  * LoadSoraDumpFile (kernel/brick/inc/brickutil.h:21-59) with a device-side gather; left_shift = 2 applies the legacy 14-bit fix
  * (RX_COMPLEX16_INVALID_BITS, kernel/core/inc/const.h:73; dot11a/dot11/arx_fd.c:530), 0 leaves samples untouched. */
 int sb200_rxblocks_unpack(sb200_handle* h, const void* blocks, uint64_t nblocks, uint32_t left_shift, int16_t* iq_out, void* cuda_stream);
+/* The descriptor words the unpack drops: per RX_BLOCK the VStreamBits word (which virtual streams the block is valid for) and the radio's
+ * TimeStamp (___RX_DESC, kernel/core/inc/_rx_manager.h:97-107); either output may be NULL, host or device. */
+int sb200_rxblocks_desc(sb200_handle* h, const void* blocks, uint64_t nblocks, uint32_t* vstream_bits, uint32_t* timestamps, void* cuda_stream);
 
 /* 802.11a transmit: the brick modulator graphs CreateModGraph11a_40M + CreatePreamble11a_40M (kernel/bb/demod11/fb11amod_config.hpp:75-118,
  * 150-158) driven like Test11A_FB_Mod (kernel/bb/demod11/fb11a_mod.cpp:27-107), one warp per OFDM symbol.  Frame i = payload[pay_off[i] ..

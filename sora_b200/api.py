@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -194,6 +194,13 @@ class Engine:
         fp = np.zeros(len(lens), np.uint32)
         self.tx11b_raw(_ptr(flat), max(int(lens.sum()), 1), _ptr(offs), _ptr(lens), len(lens), rate_kbps, init_phase, lead, sample_bits, _ptr(out), out_stride, _ptr(ns), 0, _ptr(fp))
         return (out, ns, fp) if return_phase else (out, ns)
+
+    def rxblocks_desc(self, raw):
+        """raw: uint8 array of whole 128-byte RX_BLOCKs -> (VStreamBits uint32 [nblocks], TimeStamp uint32 [nblocks])."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8); nblk = len(raw) // 128
+        vb = np.zeros(nblk, np.uint32); ts = np.zeros(nblk, np.uint32)
+        self._check(self._lib.sb200_rxblocks_desc(self._h, C.c_void_p(_ptr(raw)), C.c_uint64(nblk), C.c_void_p(_ptr(vb)), C.c_void_p(_ptr(ts)), C.c_void_p(0)), "sb200_rxblocks_desc")
+        return vb, ts
 
     def rxblocks_unpack(self, raw, left_shift=0):
         """raw: uint8 array of whole 128-byte RX_BLOCKs (a *.dmp file) -> int16 [28*nblocks, 2] via the device gather."""

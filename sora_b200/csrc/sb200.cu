@@ -717,6 +717,36 @@ extern "C" int sb200_rxblocks_unpack(sb200_handle* h, const void* blocks, uint64
     return SB200_OK;
 }
 
+// descriptor words of every RX_BLOCK (___RX_DESC, _rx_manager.h:97-107): VStreamBits at byte 0, TimeStamp at byte 12
+__global__ void __launch_bounds__(256) k_rxblocks_desc(const uint4* __restrict__ blocks, uint64_t nblocks, uint32_t* __restrict__ vbits, uint32_t* __restrict__ stamps) {
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 d = __ldg(blocks + b * 8u);
+        if (vbits) vbits[b] = d.x;
+        if (stamps) stamps[b] = d.w;
+    }
+}
+extern "C" int sb200_rxblocks_desc(sb200_handle* h, const void* blocks, uint64_t nblocks, uint32_t* vstream_bits, uint32_t* timestamps, void* cuda_stream) {
+    if (!h || !blocks || (!vstream_bits && !timestamps)) return h ? h->fail(SB200_E_INVALID, "bad argument") : SB200_E_INVALID;
+    if (nblocks == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    const bool in_dev = is_device_ptr(blocks);
+    const bool v_dev = vstream_bits && is_device_ptr(vstream_bits), t_dev = timestamps && is_device_ptr(timestamps);
+    const uint4* d_in = (const uint4*)blocks;
+    if (!in_dev) { CK(h->stage[0].need(nblocks * 128ull)); CK(cudaMemcpyAsync(h->stage[0].p, blocks, nblocks * 128ull, cudaMemcpyHostToDevice, st)); d_in = (const uint4*)h->stage[0].p; }
+    uint32_t* d_v = vstream_bits; uint32_t* d_t = timestamps;
+    if ((vstream_bits && !v_dev) || (timestamps && !t_dev)) { CK(h->stage[1].need(nblocks * 8ull)); if (vstream_bits && !v_dev) d_v = (uint32_t*)h->stage[1].p; if (timestamps && !t_dev) d_t = (uint32_t*)h->stage[1].p + nblocks; }
+    const unsigned grid = (unsigned)((nblocks + 255) / 256 < 148ull * 8 ? (nblocks + 255) / 256 : 148ull * 8);
+    k_rxblocks_desc<<<grid, 256, 0, st>>>(d_in, nblocks, d_v, d_t);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    bool sync = false;
+    if (vstream_bits && !v_dev) { CK(cudaMemcpyAsync(vstream_bits, d_v, nblocks * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (timestamps && !t_dev) { CK(cudaMemcpyAsync(timestamps, d_t, nblocks * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (sync) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
 // ---- 802.11a transmit -------------------------------------------------------------------------------
 static int upload_tables_tx(sb200_handle* h) {
     if (h->tabtx.p) return SB200_OK;

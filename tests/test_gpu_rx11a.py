@@ -206,6 +206,16 @@ def test_rxblock_ingest_on_device(eng):
     assert len(res) == 1 and res["status"][0] == 1 and res["rate_kbps"][0] == 6000 and res["length"][0] == 1392 and res["crc32"][0] == 0x80EF9B11
     assert (out[0, :1392] == np.fromfile(os.path.join(GOLD, "fsample-6.psdu.bin"), dtype=np.uint8)).all()
 
+def test_rxblock_descriptors(eng):
+    """VStreamBits and TimeStamp of every RX_BLOCK (___RX_DESC) come back as the file holds them."""
+    raw = np.fromfile(os.path.join(GOLD, "fsample-6.dmp"), dtype=np.uint8)
+    vb, ts = eng.rxblocks_desc(raw)
+    blk = raw[: len(raw) // 128 * 128].reshape(-1, 128)
+    assert (vb == blk[:, 0:4].copy().view("<u4")[:, 0]).all() and (ts == blk[:, 12:16].copy().view("<u4")[:, 0]).all()
+    rng = np.random.default_rng(2); syn = rng.integers(0, 256, (1000, 128)).astype(np.uint8)
+    vb, ts = eng.rxblocks_desc(syn.reshape(-1))
+    assert (vb == syn[:, 0:4].copy().view("<u4")[:, 0]).all() and (ts == syn[:, 12:16].copy().view("<u4")[:, 0]).all()
+
 def test_legacy_c_api_shim():
     """CsFrameDemod's loop (kernel/bb/demod11/demod11a.cpp:81-200) written against include/sora_b200_legacy.h via ctypes."""
     import ctypes as C
