@@ -7,9 +7,10 @@ import oracle_py
 
 REF = "/root/reference"
 
-def _rx(o0, o1, chan=((1, 0), (0, 1)), noise=0.0, seed=0, lead=400, trail=300):
+def _rx(o0, o1, chan=((1, 0), (0, 1)), noise=0.0, seed=0, lead=400, trail=300, cfo_hz=0.0):
     a = o0.astype(np.float64); b = o1.astype(np.float64)
-    ca = a[:, 0] + 1j * a[:, 1]; cb = b[:, 0] + 1j * b[:, 1]
+    rot = np.exp(2j * np.pi * cfo_hz * np.arange(len(a)) / 40e6)
+    ca = (a[:, 0] + 1j * a[:, 1]) * rot; cb = (b[:, 0] + 1j * b[:, 1]) * rot
     r0 = chan[0][0] * ca + chan[0][1] * cb; r1 = chan[1][0] * ca + chan[1][1] * cb
     rng = np.random.default_rng(seed)
     def pack(r):
@@ -29,6 +30,17 @@ def test_tx_oracle_to_rx_oracle_roundtrip(mcs):
             res, out = _rx(o0, o1, chan, noise, seed=L)
             assert len(res) == 1 and res[0]["status"] == 1 and res[0]["mcs"] == mcs and res[0]["length"] == L + 4, (mcs, L, chan, res)
             assert (out[0, :L] == p).all() and int.from_bytes(bytes(out[0, L:L + 4]), "little") == zlib.crc32(p.tobytes())
+
+def test_roundtrip_with_carrier_offset():
+    """+-40 kHz between the two restated halves: joint CFO estimate, NCO and pilot tracking of the receive side against the transmit side's
+    preambles and pilots (the pilot polarity index of the modulator is one ahead of the standard's; the receiver's tracking is polarity-blind)."""
+    p = np.arange(400, dtype=np.uint8)
+    for mcs in (8, 9, 10):
+        for cfo in (-40e3, 13e3, 40e3):
+            res, out = _rx(*oracle_py.tx11n_modulate(p, mcs), chan=((1.0, 0.3j), (-0.2, 0.9)), noise=25.0, seed=7, cfo_hz=cfo)
+            assert len(res) == 1 and res[0]["status"] == 1 and (out[0, :400] == p).all(), (mcs, cfo, res)
+            est_hz = res[0]["cfo_est"] / 65536.0 * 20e6                                      # 2^16 / 2 pi radians per 20 Msps sample
+            assert abs(est_hz + cfo) < 3e3, (mcs, cfo, est_hz)                               # CFO_est is the correction, i.e. minus the offset
 
 def test_symbol_counts_and_flush_padding():
     """HT-SIG announces ceil((8 (L + 4) + 22) / N_DBPS) symbols; the graph emits one more when the padded byte stream does not end on a
