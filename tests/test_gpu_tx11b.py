@@ -27,7 +27,7 @@ def test_tx_matches_oracle_bit_exact(eng, rate):
 
 def test_tx_formats_and_lead(eng):
     p = [np.full(200, 0x31, np.uint8), np.arange(90, dtype=np.uint8)]
-    for lead in (0, 3, 8, 101):
+    for lead in (0, 3, 4, 8, 12, 101):
         o8, ns = eng.tx11b_batch(p, 11000, lead=lead, sample_bits=8)
         o16, ns16 = eng.tx11b_batch(p, 11000, lead=lead, sample_bits=16)
         for i in range(2):
