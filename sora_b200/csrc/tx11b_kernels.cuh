@@ -4,8 +4,8 @@
 // split where the data dependence allows it:
 //   k_tx11b_code   one thread per frame: everything that is a recurrence over the byte stream — PLCP header (CRC-16), the
 //                  self-synchronising 7-4-1 scrambler and the differential phase reference — leaving one 16-bit descriptor
-//                  per byte: [7:0] the DBPSK/DQPSK phase code or the scrambled CCK byte, [9:8] the phase reference in front
-//                  of the byte, [10] the odd-symbol flag of 11 Mbps.  ~20 integer instructions per byte.
+//                  per byte: [7:0] the DBPSK/DQPSK phase code or the scrambled CCK 5.5 byte with [9:8] the phase reference in front of it;
+//                  at 11 Mbps the symbol's four phase terms as quarter turns (m0 m1 + odd-symbol pi, m2, m3, m4).  ~20 integer instructions per byte.
 //                  Reference: PHY_11b.hpp:82-151,216-293; scramble.hpp:9-91; barkerspread.hpp:25-41,129-156; cck.hpp:854-866,945-953.
 //   k_tx11b_shape  every output sample independently: a CTA stages the chips its 2048 samples depend on in shared memory
 //                  (chip = pure function of a descriptor and the chip number), then each thread runs the 5-input polyphase
@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(128) k_tx11b_code(const uint8_t* __restrict__ 
         } else if (job.rate_kbps == 5500) {                                             // two 4-bit CCK symbols; the second carries the odd-symbol pi
             word = sb | (ref << 8);
             ref = dqpsk_of_q(2u + q_of_dqpsk(ref) + q_of_dqpsk(sb) + q_of_dqpsk(sb >> 4));
-        } else {
-            word = sb | (ref << 8) | (odd << 10);
-            ref = dqpsk_of_q(q_of_dqpsk(ref) + q_of_dqpsk(sb) + 2u * odd); odd ^= 1u;
+        } else {                                                                        // 11 Mbps: the four phase terms of the symbol as quarter turns
+            const unsigned q0 = (q_of_dqpsk(ref) + q_of_dqpsk(sb) + 2u * odd) & 3u;     // m0 m1 and the odd-symbol pi
+            word = q0 | (q_of_cck11(sb >> 2) << 2) | (q_of_cck11(sb >> 4) << 4) | (q_of_cck11(sb >> 6) << 6);
+            ref = dqpsk_of_q(q0); odd ^= 1u;
         }
         d[i] = (uint16_t)word;
     }
@@ -117,17 +118,18 @@ __device__ __forceinline__ int tx11b_chip(const uint16_t* __restrict__ d, uint32
             q = q_of_dqpsk(ref) + q_of_dqpsk(sb) + ((row >> (2u * (i & 7u))) & 3u);
             if (i >= 8u) q += 2u + q_of_dqpsk(sb >> 4);
         } else {
-            const uint32_t byte = m >> 3, i = m & 7u; const unsigned w = __ldg(d + 24u + byte), sb = w & 0xFFu;
-            q = q_of_dqpsk(w >> 8) + q_of_dqpsk(sb) + ((w >> 10) & 1u) * 2u;
-            if (!(i & 1u)) q += q_of_cck11(sb >> 2);                                    // m2 on chips 0, 2, 4, 6
-            if (!(i & 2u)) q += q_of_cck11(sb >> 4);                                    // m3 on chips 0, 1, 4, 5
-            if (!(i & 4u)) q += q_of_cck11(sb >> 6);                                    // m4 on chips 0 .. 3
+            const uint32_t byte = m >> 3, i = m & 7u; const unsigned w = __ldg(d + 24u + byte);
+            q = w;                                                                      // bits above the low two are cut off at the end, so the terms go in unmasked
+            if (!(i & 1u)) q += w >> 2;                                                 // m2 on chips 0, 2, 4, 6
+            if (!(i & 2u)) q += w >> 4;                                                 // m3 on chips 0, 1, 4, 5
+            if (!(i & 4u)) q += w >> 6;                                                 // m4 on chips 0 .. 3
             if (i == 3u || i == 6u) q += 2u;
         }
     }
     if (flip) q += 2u;
     q &= 3u;                                                                            // 0: 1, 1: +j, 2: -1, 3: -j
-    return q == 0u ? 1 : q == 2u ? -1 : q == 1u ? 65536 : -65536;
+    const int v = 1 << ((q & 1u) << 4);                                                 // 1 or j
+    return (q & 2u) ? -v : v;
 }
 
 #define SB_TX11B_THREADS 256
@@ -142,7 +144,9 @@ __host__ __device__ constexpr int tx11b_branch_max(int k) {                     
 }
 static_assert(tx11b_branch_max(0) <= 127 && tx11b_branch_max(1) <= 127 && tx11b_branch_max(2) <= 127 && tx11b_branch_max(3) <= 127,
               "TPackSample16to8 (packsswb) never saturates on this shaper, so the pack is a plain byte extraction");
-__device__ __forceinline__ uint32_t tx11b_unborrow(int t) { return (uint32_t)t + (((uint32_t)t & 0x8000u) << 1); }   // high half := im exactly
+// Both halves are kept non-negative by a bias of 128 (|output| <= 127, see above), so the low half never borrows from the high one; the bias
+// is bit 7 of the byte that goes out and is flipped back after the bytes are gathered.
+#define SB_TX11B_BIAS 0x00800080u
 
 // ALIGNED: lead is a multiple of 4, so a thread's 8 samples are the two whole shaper vectors of chips n and n + 1
 template <bool ALIGNED, uint32_t RATE>
@@ -170,9 +174,9 @@ __global__ void __launch_bounds__(SB_TX11B_THREADS) k_tx11b_shape(const uint32_t
     }
     __syncthreads();
     if (s0 >= out_stride) return;
-    uint32_t t[SB_TX11B_SPT];                                                           // per sample: re in the low half, im in the high half
+    uint32_t t[SB_TX11B_SPT];                                                           // per sample: re + 128 in the low half, im + 128 in the high half
 #pragma unroll
-    for (int i = 0; i < SB_TX11B_SPT; i++) t[i] = 0;
+    for (int i = 0; i < SB_TX11B_SPT; i++) t[i] = SB_TX11B_BIAS;
     if (inside) {
         if (ALIGNED) {
             constexpr int H[20] = SB_TX11B_TAPS;
@@ -187,10 +191,10 @@ __global__ void __launch_bounds__(SB_TX11B_THREADS) k_tx11b_shape(const uint32_t
                 for (int j = 0; j < 5; j++) x[j] = s_chip[loc - j];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    int a = 0;
+                    int a = (int)SB_TX11B_BIAS;
 #pragma unroll
                     for (int j = 0; j < 5; j++) if (H[4 * j + k] != 0) a += x[j] * H[4 * j + k];
-                    t[4 * c + k] = tx11b_unborrow(a);
+                    t[4 * c + k] = (uint32_t)a;
                 }
             }
         } else {
@@ -199,23 +203,23 @@ __global__ void __launch_bounds__(SB_TX11B_THREADS) k_tx11b_shape(const uint32_t
                 const int m = (int)s0 + i - (int)job.lead;
                 if (m < 0 || m >= nvec * 4) continue;
                 const int n = (m >> 2) - n_lo, k = m & 3;
-                int a = 0;
+                int a = (int)SB_TX11B_BIAS;
 #pragma unroll
                 for (int j = 0; j < 5; j++) a += s_chip[n - j] * (int)job.taps[4 * j + k];
-                t[i] = tx11b_unborrow(a);
+                t[i] = (uint32_t)a;
             }
         }
     }
     // TPackSample16to8 keeps the low byte of each component (never saturates, see above); COMPLEX16 output is that byte << 8
     if (job.fmt16) {
-        uint4 a, b;
-        a.x = __byte_perm(t[0], 0, 0x2404); a.y = __byte_perm(t[1], 0, 0x2404); a.z = __byte_perm(t[2], 0, 0x2404); a.w = __byte_perm(t[3], 0, 0x2404);
-        b.x = __byte_perm(t[4], 0, 0x2404); b.y = __byte_perm(t[5], 0, 0x2404); b.z = __byte_perm(t[6], 0, 0x2404); b.w = __byte_perm(t[7], 0, 0x2404);
+        uint4 a, b; const uint32_t F = 0x80008000u;     // the bias, now in the high byte of each 16-bit component
+        a.x = __byte_perm(t[0], 0, 0x2404) ^ F; a.y = __byte_perm(t[1], 0, 0x2404) ^ F; a.z = __byte_perm(t[2], 0, 0x2404) ^ F; a.w = __byte_perm(t[3], 0, 0x2404) ^ F;
+        b.x = __byte_perm(t[4], 0, 0x2404) ^ F; b.y = __byte_perm(t[5], 0, 0x2404) ^ F; b.z = __byte_perm(t[6], 0, 0x2404) ^ F; b.w = __byte_perm(t[7], 0, 0x2404) ^ F;
         uint4* o = (uint4*)((uint32_t*)out + (size_t)f * out_stride + s0);
         o[0] = a; o[1] = b;
     } else {
-        uint4 a;
-        a.x = __byte_perm(t[0], t[1], 0x6420); a.y = __byte_perm(t[2], t[3], 0x6420); a.z = __byte_perm(t[4], t[5], 0x6420); a.w = __byte_perm(t[6], t[7], 0x6420);
+        uint4 a; const uint32_t F = 0x80808080u;
+        a.x = __byte_perm(t[0], t[1], 0x6420) ^ F; a.y = __byte_perm(t[2], t[3], 0x6420) ^ F; a.z = __byte_perm(t[4], t[5], 0x6420) ^ F; a.w = __byte_perm(t[6], t[7], 0x6420) ^ F;
         *(uint4*)((uint16_t*)out + (size_t)f * out_stride + s0) = a;
     }
 }
