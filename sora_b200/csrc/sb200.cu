@@ -1,7 +1,7 @@
 // sora_b200 — host side of the C ABI (include/sora_b200.h): workspaces, table upload, kernel launches.
 // Single translation unit: the kernels live in the .cuh files included below.
 #include "../../include/sora_b200.h"
-#include "viterbi_k7_quad.cuh"
+#include "viterbi_k7_re.cuh"
 #include "rx11b_kernels.cuh"
 #include "rx11n_kernels.cuh"
 #include "tx11a_kernels.cuh"
@@ -75,6 +75,7 @@ struct sb200_handle {
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
+    bool use_v2 = false;                               // SB200_VITERBI=v2 selects the per-step-mark quad kernel (A/B against the history-carrying one)
     std::string err;
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         err = what; if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
@@ -136,7 +137,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v1 = e && e[0] == 'v' && e[1] == '1'; }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v1 = e && e[0] == 'v' && e[1] == '1'; h->use_v2 = e && e[0] == 'v' && e[1] == '2'; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
@@ -202,12 +203,19 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
     if (h->use_v1) {
         k_viterbi_k7<<<(n + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         h->launches += 3;
-    } else {                                           // one launch per code rate; quads of other rates exit at once
+    } else if (h->use_v2) {                            // one launch per code rate; quads of other rates exit at once
         const unsigned g = (n + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         k_viterbi_quad<CR_34><<<g, b, h->vq_pad_smem, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         k_viterbi_quad<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         k_viterbi_quad<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         h->launches += 5;
+    } else {                                           // history-carrying kernel (one launch per code rate) + descrambler / frame sink
+        const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, b = 32 * SB_VR_WARPS;
+        k_viterbi_re<CR_34><<<g, b, h->vq_pad_smem, sv>>>(d_soft, soft_stride, n, d_info, job, d_out, row, 14u, d_status);
+        k_viterbi_re<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, d_out, row, 14u, d_status);
+        k_viterbi_re<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, d_out, row, 14u, d_status);
+        k_sink11a<<<(n + 127) / 128, 128, 0, sv>>>(d_out, row, n, d_info, h->T, d_status, d_crc);
+        h->launches += 6;
     }
     if (timed) CK(cudaEventRecord(h->evk[3], sv));
     return SB200_OK;
@@ -579,9 +587,17 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
             d_info, (uint8_t*)h->soft.p, soft_stride, taps);
     CK(cudaEventRecord(h->evk[2], st));
     VitJob job{}; job.depth = 192; job.lookahead = 36; job.raw = 0;                    // T11aViterbi<5000*8, 312, 192, 36> (fb11ndemod_config.hpp:189)
-    const unsigned g = (nframes + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
-    k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-    k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    if (h->use_v2) {
+        const unsigned g = (nframes + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
+        k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    } else {
+        const unsigned g = (nframes + SB_VR_FR - 1) / SB_VR_FR, b = 32 * SB_VR_WARPS;
+        k_viterbi_re<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        k_viterbi_re<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        k_sink11a<<<(nframes + 127) / 128, 128, 0, st>>>((uint8_t*)h->out.p, row, nframes, d_info, h->T, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        h->launches += 1;
+    }
     CK(cudaEventRecord(h->evk[3], st));
     const bool res_dev = is_device_ptr(res);
     sb200_frame_result_11n* d_res = res_dev ? res : (sb200_frame_result_11n*)h->res.p;
@@ -1084,6 +1100,11 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
     if (h->use_v1) {
         k_viterbi_k7<<<(nblocks + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T,
                 d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+    } else if (!h->use_v2) {
+        const unsigned g = (nblocks + SB_VR_FR - 1) / SB_VR_FR, b = 32 * SB_VR_WARPS;
+        if (code_rate == CR_34) k_viterbi_re<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        else if (code_rate == CR_12) k_viterbi_re<CR_12><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        else k_viterbi_re<CR_23><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
     } else {
         const unsigned g = (nblocks + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         if (code_rate == CR_34) k_viterbi_quad<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);

@@ -39,6 +39,33 @@ def test_ofdm_bin_golden_frame():
     assert (out[0, :200] == 0x31).all() and bytes(out[0, 200:204]) == bytes.fromhex("388d4983")
     assert zlib.crc32(bytes(out[0, :200])) == int.from_bytes(bytes(out[0, 200:204]), "little")
 
+@pytest.mark.parametrize("name", ["dummy_20m", "dummy_16_40m", "dummy_8_20m", "dummy_8_ack_40m"])
+def test_reference_dummy_frames(name):
+    """kernel/sample/mac/Dot11ADummy*.txt: four waveforms of the reference's own (legacy) modulator.  The two long ones carry the very
+    frame of fsample-6.dmp (three independent renderings of one PSDU must decode to the same 1392 bytes); the two short ones are the
+    14-byte ACK that BB11AModulateACK builds, whose bytes are known in full."""
+    import golden_vectors as gv
+    iq, rate, want = gv.dummy_vectors()[name]
+    res, out = oracle_py.rx11a_run(iq)
+    assert len(res) == 1 and res[0]["status"] == oracle_py.E_FRAME_OK and res[0]["rate_kbps"] == rate
+    L = int(res[0]["length"]); psdu = bytes(out[0, :L])
+    assert zlib.crc32(psdu[:-4]) == int.from_bytes(psdu[-4:], "little") == int(res[0]["crc32"])
+    if want is None:
+        assert L == 1392 and psdu == bytes(gv.fsample6_psdu()) and int(res[0]["crc32"]) == 0x80EF9B11
+    else:
+        assert psdu == want
+        # the ACK is a legal control frame: FC 0x00D4, duration 0, RA, FCS (dot11 ACK layout, atx_fe.c:168-180)
+        assert psdu[:2] == b"\xd4\x00" and psdu[2:4] == b"\x00\x00" and L == 14
+
+def test_reference_dummy_frames_gain_invariant():
+    """The decode does not hinge on the gain chosen in golden_vectors: any power of two that clears the energy threshold gives the same bytes."""
+    import golden_vectors as gv
+    v = np.fromfile(os.path.join(GOLD, "dot11a_dummy_16_40m.i16"), np.int16).reshape(-1, 2).astype(np.int32)
+    for sh in (2, 3):
+        iq = np.concatenate([np.zeros((400, 2), np.int16), (v << sh).astype(np.int16), np.zeros((428, 2), np.int16)])
+        res, out = oracle_py.rx11a_run(iq)
+        assert len(res) == 1 and res[0]["status"] == 1 and bytes(out[0, :1392]) == bytes(gv.fsample6_psdu())
+
 def test_dump_roundtrip(tmp_path):
     iq = _fs6()[:28 * 40]
     p = tmp_path / "x.dmp"; write_dump(str(p), iq)

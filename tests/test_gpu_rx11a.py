@@ -104,6 +104,25 @@ def test_viterbi_standalone(eng):
             if flip == 0.0:
                 assert (np.unpackbits(g, axis=1, bitorder="little")[:, :8 * L + 16] == bits[:, :8 * L + 16]).all()
 
+def test_viterbi_wrap_and_ragged_stress(eng):
+    """Soft values that make the uint8 path metrics wrap (uniform garbage, all-ones, alternating extremes) and block lengths that end
+    anywhere in a 6-step phase cycle / 8-step normalisation period: the device decoder must follow the reference's wrap, tie-break and
+    windowing bit for bit at all three code rates and both windows (256/24 of 802.11a, 192/36 of 802.11n)."""
+    rng = np.random.default_rng(11)
+    for cr, per in ((api.CR_12, 2), (api.CR_23, 3), (api.CR_34, 4)):
+        steps_per = {2: 1, 3: 2, 4: 3}[per]
+        for L in (1, 2, 3, 5, 17, 40, 101, 333, 1000):
+            nbits = 8 * L + 16 + 6
+            ngroups = -(-nbits // steps_per) + int(rng.integers(0, 5))          # a few groups past the end as well
+            ns = ngroups * per
+            pats = [rng.integers(0, 8, (6, ns)), np.full((1, ns), 7), np.zeros((1, ns), int), np.tile([0, 7, 7, 0, 7], ns)[None, :ns],
+                    rng.integers(3, 5, (2, ns))]
+            soft = np.concatenate(pats).astype(np.uint8)
+            for depth, look in ((256, 24), (192, 36)):
+                g = eng.viterbi_k7(soft, cr, L, depth, look)
+                o = oracle_py.viterbi_blocks(soft, cr, L, depth, look)
+                assert (g == o).all(), (cr, L, depth, np.argwhere(g != o)[:4])
+
 def test_brick_adaptor_graph(eng):
     """The header-only GPU brick inside a CREATE_BRICK_* graph driven like RxThread (sora_b200/brick/demo_graph.cpp)."""
     import subprocess, json
@@ -261,6 +280,18 @@ def test_ofdm_bin_golden(eng):
     res, out = _compare(eng, iq, [0], [len(iq)])
     assert res["status"][0] == 1 and res["rate_kbps"][0] == 24000 and res["length"][0] == 204
     assert (out[0, :200] == 0x31).all() and bytes(out[0, 200:204]) == bytes.fromhex("388d4983")
+
+def test_reference_dummy_frames(eng):
+    """kernel/sample/mac/Dot11ADummy*.txt (four waveforms of the reference's own modulator) in one batch of ragged slots: the GPU
+    returns what the oracle returns, the two long ones give fsample-6's PSDU, the two short ones the known ACK bytes."""
+    import golden_vectors as gv
+    vec = gv.dummy_vectors(); names = sorted(vec)
+    caps = [vec[n][0] for n in names]
+    off = np.concatenate([[0], np.cumsum([len(c) for c in caps])[:-1]]).astype(np.uint64); ln = np.array([len(c) for c in caps], np.uint32)
+    res, out = _compare(eng, np.concatenate(caps), off, ln, expect_ok=4)
+    for i, n in enumerate(names):
+        want = vec[n][2] if vec[n][2] is not None else bytes(gv.fsample6_psdu())
+        assert res["rate_kbps"][i] == 6000 and res["length"][i] == len(want) and bytes(out[i, :len(want)]) == want, n
 
 def test_many_streams_at_once(eng):
     """sb200_rx11a_streams: a batch of continuous captures, each decoded with RxThread's sequential semantics."""
