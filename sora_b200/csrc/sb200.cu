@@ -57,7 +57,7 @@ struct sb200_handle {
     int device = 0;
     uint32_t cca_thr = 1000 * 1000;
     DevTables T{};
-    DevBuf tab, iq, off, len, info, soft, out, status, crc, res, taps[5];
+    DevBuf tab, iq, off, len, info, soft, out, status, crc, res, taps[5], vlist, vcnt;
     uint16_t* inv_deint = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // boundaries of sync | front | viterbi | pack
@@ -154,7 +154,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
-                     &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4]};
+                     &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4], &h->vlist, &h->vcnt};
     for (DevBuf* b : all) b->release();
     h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -186,7 +186,7 @@ extern "C" int sb200_last_kernel_times(sb200_handle* h, float* ms4) {
 // Launch the decode kernels for frames [f0, f1) of a call.  `iq_base + off[f]` must address slot f.
 // sync + front end go to `sf`, the Viterbi launches to `sv` (sv waits for `front_done` when the streams differ).
 static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t f0, uint32_t f1,
-                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr) {
+                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr, uint32_t chunk_idx = 0) {
     const uint32_t n = f1 - f0;
     FrameInfo* d_info = (FrameInfo*)h->info.p + f0;
     uint8_t* d_soft = (uint8_t*)h->soft.p + (size_t)f0 * soft_stride;
@@ -209,13 +209,16 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
         k_viterbi_quad<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         k_viterbi_quad<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         h->launches += 5;
-    } else {                                           // history-carrying kernel (one launch per code rate) + descrambler / frame sink
-        const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, b = 32 * SB_VR_WARPS;
-        k_viterbi_re<CR_34><<<g, b, h->vq_pad_smem, sv>>>(d_soft, soft_stride, n, d_info, job, d_out, row, 14u, d_status);
-        k_viterbi_re<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, d_out, row, 14u, d_status);
-        k_viterbi_re<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, d_out, row, 14u, d_status);
+    } else {                                           // history-carrying kernel: work lists per code rate, one launch per rate, descrambler / frame sink
+        const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR;
+        uint32_t* d_list = (uint32_t*)h->vlist.p + 3 * (size_t)f0; uint32_t* d_cnt = (uint32_t*)h->vcnt.p + 4 * (size_t)chunk_idx;
+        CK(cudaMemsetAsync(d_cnt, 0, 16, sv));
+        k_vit_lists<<<(n + 255) / 256, 256, 0, sv>>>(d_info, n, d_cnt, d_list);
+        k_viterbi_re<CR_34><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status);
+        k_viterbi_re<CR_12><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status);
+        k_viterbi_re<CR_23><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status);
         k_sink11a<<<(n + 127) / 128, 128, 0, sv>>>(d_out, row, n, d_info, h->T, d_status, d_crc);
-        h->launches += 6;
+        h->launches += 7;
     }
     if (timed) CK(cudaEventRecord(h->evk[3], sv));
     return SB200_OK;
@@ -261,12 +264,14 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     CK(h->soft.need(nframes * soft_stride));
     CK(h->out.need(nframes * row));
     CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result)));
+    CK(h->vlist.need(nframes * 12ull));
     const bool tapping = taps.freq_coeffs || taps.fft_out || soft_host || dc_init;
     // device-resident IQ gains nothing from chunking (a chunk's Viterbi grid no longer fills 148 SMs x 5 CTAs); host IQ does:
     // the PCIe copy of chunk k+1 hides behind the kernels of chunk k.  chunk_frames_device lets a caller force it anyway.
     const uint32_t want = iq_dev ? h->chunk_frames_device : h->chunk_frames;
     const uint32_t chunk = (want == 0 || tapping || nframes <= want) ? nframes : want;
     const bool pipelined = chunk < nframes;
+    CK(h->vcnt.need(16ull * ((nframes + chunk - 1) / chunk)));
     const bool res_dev_all = is_device_ptr(res), out_dev_all = out_bytes && is_device_ptr(out_bytes);
     sb200_frame_result* d_res_all = res_dev_all ? res : (sb200_frame_result*)h->res.p;
     CK(cudaEventRecord(h->ev0, st));
@@ -303,7 +308,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
                 CK(cudaStreamWaitEvent(h->s_front, h->ev_h2d[b], 0));
                 base = (const uint32_t*)h->stage[b].p - lo;
             }
-            int rc = launch_chunk(h, base, d_off, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false);
+            int rc = launch_chunk(h, base, d_off, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false, nullptr, k);
             if (rc != SB200_OK) return rc;
             // results of this chunk go back while the next chunks are still coming in (PCIe is full duplex): only the last chunk's
             // device-to-host copy is left exposed at the end of the call
@@ -592,11 +597,14 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
         k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
         k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
     } else {
-        const unsigned g = (nframes + SB_VR_FR - 1) / SB_VR_FR, b = 32 * SB_VR_WARPS;
-        k_viterbi_re<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
-        k_viterbi_re<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        const unsigned g = (nframes + SB_VR_FR - 1) / SB_VR_FR;
+        CK(h->vlist.need(nframes * 12ull)); CK(h->vcnt.need(16));
+        CK(cudaMemsetAsync(h->vcnt.p, 0, 16, st));
+        k_vit_lists<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, nframes, (uint32_t*)h->vcnt.p, (uint32_t*)h->vlist.p);
+        k_viterbi_re<CR_12><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        k_viterbi_re<CR_34><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
         k_sink11a<<<(nframes + 127) / 128, 128, 0, st>>>((uint8_t*)h->out.p, row, nframes, d_info, h->T, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-        h->launches += 1;
+        h->launches += 2;
     }
     CK(cudaEventRecord(h->evk[3], st));
     const bool res_dev = is_device_ptr(res);
@@ -1101,10 +1109,10 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
         k_viterbi_k7<<<(nblocks + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T,
                 d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
     } else if (!h->use_v2) {
-        const unsigned g = (nblocks + SB_VR_FR - 1) / SB_VR_FR, b = 32 * SB_VR_WARPS;
-        if (code_rate == CR_34) k_viterbi_re<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
-        else if (code_rate == CR_12) k_viterbi_re<CR_12><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
-        else k_viterbi_re<CR_23><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        const unsigned g = (nblocks + SB_VR_FR - 1) / SB_VR_FR;
+        if (code_rate == CR_34) k_viterbi_re<CR_34><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        else if (code_rate == CR_12) k_viterbi_re<CR_12><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        else k_viterbi_re<CR_23><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
     } else {
         const unsigned g = (nblocks + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         if (code_rate == CR_34) k_viterbi_quad<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);

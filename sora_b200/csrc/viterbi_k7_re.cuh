@@ -6,20 +6,23 @@
 //     new = min_u8( (old[p] + bm) & 0xFE , (old[p+32] + bm') | 1 )   ==   m7' = min(a7, b7) mod 128 with ties to the even candidate,
 //     decision d = (b7 < a7).
 //
-// Machine mapping (same quad / in-place trellis as v2, viterbi_k7_quad.cuh, different bookkeeping):
+// Machine mapping (the quad / in-place trellis of v2, viterbi_k7_quad.cuh, with different bookkeeping):
 //   * 4 lanes per code block, 16 metrics per lane, two per register as 16-bit halves; m7 sits in bits 9..15 of its half, so the uint8 wrap is the
 //     half's own carry-out.  Every add is a per-half SIMD add (VIADD.16x2, or the add inside VIADDMNMX.U16x2): nothing crosses halves.
-//   * The low bits of a half carry the survivor HISTORY of the path that ends in that state: trellis step T of a 6-step block (T = t mod 6)
-//     gives the odd candidate bit T (folded into its branch-metric constant) and leaves it clear in the even candidate.  Bits T+1..8 are still
-//     zero in both candidates, so a metric tie is decided by bit T exactly like the reference's LSB mark decides it (even wins), bits below T
-//     are never reached by the compare, and the min moves the winner's history along for free.  One fused VIADDMNMX.U16x2 (DPX add-min) plus
-//     one VIADD.16x2 per register and step is the whole add-compare-select: no role masks, no per-step gathering of decision bits.
-//   * After the 6th step every half holds the six decisions of its survivor over the block (register exchange over one phase cycle).  At a
-//     block boundary state index == slot address, so four PRMTs line the 16 history bytes of a lane up in address order and one 128-bit
-//     store puts them into a shared-memory ring: entry [block][code block][slot] = 64 bytes per 6 columns.
-//   * Traceback jumps a whole block per lookup: the history byte h of slot A gives the six decoded bits (bit T = column 6b+T+1) and the
-//     predecessor slot six columns earlier is bit-reverse6(h) — K=7 replaces all six state bits in six steps.  A window of 256+24..31 columns
-//     costs ~48 byte loads instead of 280 64-bit word look-ups.
+//   * The low byte of a half carries the survivor HISTORY of the path that ends in that state: trellis step t gives the odd candidate bit
+//     j = (t - 1) mod 8 (folded into its branch-metric constant) and leaves it clear in the even candidate.  Bits j+1..8 are still zero in both
+//     candidates, so a metric tie is decided by bit j exactly like the reference's LSB mark decides it (even wins), bits below j are never
+//     reached by the compare, and the min moves the winner's history along for free.  One fused VIADDMNMX.U16x2 (DPX add-min) plus one
+//     VIADD.16x2 per register and step is the whole add-compare-select: no role masks, no per-step gathering of decision bits.
+//   * Every 8 steps each half holds the eight decisions of its survivor over the block (register exchange over 8 columns): four PRMTs line
+//     the 16 history bytes of a lane up in slot-address order and one 128-bit store puts them into a shared-memory ring:
+//     entry [block][code block][slot] = 64 bytes per 8 columns, the same 8 bytes per column a plain decision matrix needs.
+//   * Traceback jumps a whole block per lookup: the history byte h of slot A gives the eight decoded bits, and the slot eight columns earlier
+//     is a fixed bit permutation of h rotated by the phase of the block boundary (K=7 replaces all six state bits in six steps).
+//     A window of 256+24..31 columns costs ~37 byte loads instead of 280 64-bit word look-ups.
+//   * The 8 code blocks of a warp run in lockstep (the caller hands every launch a dense list of the frames of its code rate), so the
+//     path-metric exchange is a plain full-mask SHFL.BFLY; 24 steps (lcm of the 6-step phase cycle and the 8-step history block) without a
+//     traceback trigger run as one branch-free instruction stream, everything else goes through a 6-step path with the event checks.
 //   * The kernel emits the decoded bytes (SERVICE + PSDU, still scrambled).  Descrambler, CRC-32 and the verdict (scramble.hpp:269-355,
 //     PHY_11a.hpp:609-702) run in k_sink11a, one thread per frame, after it.
 // Measured instruction rates that shaped this (tools/microbench/pipes.cu on B200): VIADDMNMX.U16x2 + IMAD/VIADD issue together at ~1.0 per
@@ -29,45 +32,44 @@
 
 namespace sb {
 
-#define SB_VR_WARPS 1                      // warps per CTA
-#define SB_VR_FR (8 * SB_VR_WARPS)         // code blocks per CTA
-#define SB_VR_NB 50                        // ring entries of 6 columns: depth + lookahead + 7 <= 288 columns = 48 entries, + the partial one + 1
+#define SB_VR_FR 8                         // code blocks per CTA (one warp)
+#define SB_VR_NB 38                        // ring entries of 8 columns: depth + lookahead + 7 <= 288 columns = 36 entries, + the running one + 1
 
-// low four address bits of (register r, half h): r << 1 | h — the order in which the PRMT gather of commit lays a lane's 16 history bytes down
+// low four address bits of (register r, half h): r << 1 | h — the order in which the PRMT gather of store_hist lays a lane's 16 history bytes down
 __host__ __device__ constexpr int vr_low4(int r, int h) { return (r << 1) | h; }
 __host__ __device__ constexpr int vr_scls(int T, int r, int h) { return vq_cls(vq_rol6(vr_low4(r, h), T) & 31); }
 __host__ __device__ constexpr int vr_kcls(int T) { return vq_cls(vq_rol6(1, T) & 31); }     // class difference between the two halves of a register
 
 struct VrLane {
     unsigned swz[6];       // per-phase byte swizzle applying this lane's class contribution
-    unsigned mA[2], mB[2]; // lane-pair phases: history mark of this step for my own value / for my partner's (exactly one is non-zero)
+    uint32_t bA[2], bB[2]; // lane-pair phases: 1 if the history mark of the step goes to my own value / to my partner's (exactly one is set)
 };
 
-// one trellis step at compile-time phase T.  Cbase byte (cA<<1|cB) = metric of the even candidate for a predecessor of that class; the
-// complement class (3 - index) is the odd candidate's.  The odd candidate (state p+32) carries bit T of the low byte.
-template <int T>
-__device__ __forceinline__ void vr_step(uint32_t (&R)[8], uint32_t Cbase, const VrLane& L, unsigned qmask) {
+// one trellis step at compile-time phase T (= (t - 1) mod 6 for the step that produces column t).  Cbase byte (cA<<1|cB) = metric of the even
+// candidate for a predecessor of that class; the complement class (3 - index) is the odd candidate's.  The odd candidate (state p+32)
+// carries `mark` = 0x00010001 << ((t - 1) mod 8).  WARP: the whole warp executes the step together (full-mask shuffle).
+template <int T, bool WARP>
+__device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, const VrLane& L, const uint32_t mark, const unsigned qmask) {
     const uint32_t Cb = __byte_perm(Cbase, 0, L.swz[T]);
-    constexpr uint32_t ONE = 0x00010001u << T;
     constexpr int K = vr_kcls(T);
     uint32_t V[4];                                      // [0, Cb[c], 0, Cb[c ^ K]]: branch metrics of class c (low half) and its high-half companion
 #pragma unroll
     for (int c = 0; c < 4; c++) V[c] = __byte_perm(Cb, 0, vq_sel(c, c ^ K));
-    if (T <= 1) {                                       // pair = partner lane (xor 2 at T=0, xor 1 at T=1): the path-metric exchange
+    if constexpr (T <= 1) {                             // pair = partner lane (xor 2 at T=0, xor 1 at T=1): the path-metric exchange
         uint32_t Va[4], Vb[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) { Va[c] = V[c] + L.mA[T]; Vb[c] = V[c] + L.mB[T]; }
+        for (int c = 0; c < 4; c++) { Va[c] = L.bA[T] * mark + V[c]; Vb[c] = L.bB[T] * mark + V[c]; }
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int c0 = vr_scls(T, r, 0);
-            const uint32_t Z = __shfl_xor_sync(qmask, R[r], T == 0 ? 2 : 1);
+            const uint32_t Z = __shfl_xor_sync(WARP ? 0xFFFFFFFFu : qmask, R[r], T == 0 ? 2 : 1);
             R[r] = __viaddmin_u16x2(R[r], Va[c0], __vadd2(Z, Vb[c0 ^ 3]));
         }
-    } else if (T <= 4) {                                // pair = register r ^ d inside the lane
+    } else if constexpr (T <= 4) {                      // pair = register r ^ d inside the lane
         constexpr int d = T == 2 ? 4 : T == 3 ? 2 : 1;
         uint32_t VO[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) VO[c] = V[c] + ONE;
+        for (int c = 0; c < 4; c++) VO[c] = V[c] + mark;
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             if (r & d) continue;
@@ -79,7 +81,7 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], uint32_t Cbase, const 
     } else {                                            // pair = the two halves of each register: low = p, high = p + 32
         uint32_t W1[4], W2[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) { W1[c] = V[c] + (ONE & 0xFFFF0000u); W2[c] = V[c] + (ONE & 0x0000FFFFu); }
+        for (int c = 0; c < 4; c++) { W1[c] = V[c] + (mark & 0xFFFF0000u); W2[c] = V[c] + (mark & 0x0000FFFFu); }
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int c = vr_scls(5, r, 0);
@@ -89,204 +91,282 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], uint32_t Cbase, const 
     }
 }
 
-template <int CODE_RATE>
-__global__ void __launch_bounds__(32 * SB_VR_WARPS) k_viterbi_re(const uint8_t* __restrict__ soft, uint64_t soft_stride,
-        uint32_t nframes, const FrameInfo* __restrict__ info, VitJob job,
-        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out) {
-    __shared__ uint4 s_ring[SB_VR_NB][SB_VR_FR][4];    // entry b: history bytes of the 64 slots of every code block after column 6(b+1)
-    const int lane = threadIdx.x & 31, q = lane & 3;
-    const unsigned QM = 0xFu << (lane & 28);           // the 4 lanes of this code block: quads run as independent sub-warps
-    const int fb = (threadIdx.x >> 2);                 // code block within the CTA
-    const uint32_t f = blockIdx.x * SB_VR_FR + fb;
-    uint32_t L = job.frame_len, nsoft = job.nsoft; bool active = f < nframes;
-    if (active && info) {
-        FrameInfo fi = info[f];
-        active = fi.status == E_SUCCESS && fi.code_rate == (uint32_t)CODE_RATE;
-        L = fi.length; nsoft = fi.soft_bytes;
-    } else if (active) active = job.code_rate == (uint32_t)CODE_RATE;
-    if (!active) return;                                // whole quad leaves together (no block-wide sync below)
-    constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
-    constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
-    const uint32_t depth = job.depth, look = job.lookahead;
-    const uint8_t* sp = soft + (size_t)f * soft_stride;
-    uint8_t* op = out + (size_t)f * out_stride + raw_off;
-    const uint32_t out_cap = (uint32_t)(out_stride - raw_off < 0xFFFFFFFFull ? out_stride - raw_off : 0xFFFFFFFFull);
-    VrLane LC;
-#pragma unroll
-    for (int t = 0; t < 6; t++) {
-        int lc = q == 0 ? vq_lcls(t, 0) : q == 1 ? vq_lcls(t, 1) : q == 2 ? vq_lcls(t, 2) : vq_lcls(t, 3);
-        LC.swz[t] = (unsigned)((0 ^ lc) | ((1 ^ lc) << 4) | ((2 ^ lc) << 8) | ((3 ^ lc) << 12));
-    }
-    {
-        const int b0 = (q >> 1) & 1, b1 = q & 1;        // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
-        LC.mA[0] = b0 ? 0x00010001u : 0u; LC.mB[0] = b0 ? 0u : 0x00010001u;
-        LC.mA[1] = b1 ? 0x00020002u : 0u; LC.mB[1] = b1 ? 0u : 0x00020002u;
-    }
-    // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address; byte value v sits at v << 8
-    uint32_t R[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) R[r] = 0x30003000u;
-    if (q == 0) R[0] = 0x30000000u;
-    const uint32_t end = L * 8u + 16u + 6u;
-    uint32_t tb = 0, ob = 0;                            // tb = trellis time at the start of the current 6-step block
-    uint32_t wslot = 0;                                 // ring entry of the block that starts at tb
-    uint32_t next_tb = min(end, depth + look + 6u);     // first time a traceback can fire (viterbi.hpp:182-203)
-    uint32_t nraw = 0;
-    bool done = false;
-    uint4* ring_q = &s_ring[0][fb][q];                  // + entry * (SB_VR_FR * 4)
-    const uint8_t* ring_b = (const uint8_t*)&s_ring[0][fb][0];   // + entry * (SB_VR_FR * 64) + slot
-    uint32_t pos_soft = 0;
+// branch-metric vector of step s (0..5) of a 6-step chunk held in w[] (vq_bm_*: viterbi_k7_quad.cuh)
+template <int CODE_RATE, int s> __device__ __forceinline__ uint32_t vr_bm(const uint32_t (&w)[3]) {
+    if constexpr (CODE_RATE == CR_12) return (s & 1) ? vq_bm_ab<2>(w[s >> 1]) : vq_bm_ab<0>(w[s >> 1]);
+    else if constexpr (CODE_RATE == CR_34) return s % 3 == 0 ? vq_bm_ab<0>(w[s / 3]) : s % 3 == 1 ? vq_bm_a<2>(w[s / 3]) : vq_bm_b<3>(w[s / 3]);
+    else return (s & 1) ? vq_bm_a<2>(w[s >> 1]) : vq_bm_ab<0>(w[s >> 1]);
+}
 
-    // the 16 history bytes of this lane (low byte of every half), in address order, into ring entry `e`
-    auto store_hist = [&](const uint32_t e) {
+// Windowed traceback (viterbi.hpp:205-237) from slot A0 at time t over la + nout columns; the newest block (kp = t mod 8 columns, 0 = a whole
+// one) is in ring entry e.  The nout decoded bits end at byte wpos (exclusive) of the output row and are written last-first.
+// Kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the step loop.
+__device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t wpos,
+                                          uint32_t e, const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
+    uint32_t A = A0, todo = la + nout;
+    uint32_t fifo = 0; int cnt = -(int)la;                  // the first `la` bits are only looked through; at most 15 bits wait
+    uint32_t tt = t;                                         // time of the newest column not yet walked
+    const uint32_t kp = t & 7u;
+    auto emit = [&]() { while (cnt >= 8) { --wpos; if (wpos < out_cap) op[wpos] = (uint8_t)(fifo >> (cnt - 8)); cnt -= 8; } };
+    if (kp) {                                                // running block: kp decisions in bits 0..kp-1, one slot-address bit changes per column
+        const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
+        const uint32_t take = min(kp, todo);
+        for (uint32_t j = 0; j < take; j++) {                // column tt - j was produced at phase (tt - j - 1) mod 6: bit 5 - phase is replaced
+            const uint32_t b = 5u - (tt - j - 1u) % 6u, d = (h >> (kp - 1u - j)) & 1u;
+            A = (A & ~(1u << b)) | (d << b);
+        }
+        fifo = (h & ((1u << kp) - 1u)) >> (kp - take); cnt += (int)take;
+        emit();
+        todo -= take; tt -= kp; e = e ? e - 1u : SB_VR_NB - 1u;
+    }
+    uint32_t ph = tt % 6u;                                   // phase of the block boundary the walk stands on
+    while (todo >= 8u) {
+        const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
+        const uint32_t r = __brev(h) >> 24;                  // r bit i = h bit 7 - i = decision of column tt - i
+        const uint32_t G = (r & 0x3Cu) | (r >> 6);           // slot-address bit (i - ph) mod 6 <- column tt - i, the two oldest overriding i = 0, 1
+        A = ((G >> ph) | (G << (6u - ph))) & 63u;
+        fifo = (fifo << 8) | h; cnt += 8;
+        emit();
+        todo -= 8u; e = e ? e - 1u : SB_VR_NB - 1u; ph = ph >= 2u ? ph - 2u : ph + 4u;   // (tt - 8) mod 6
+    }
+    if (todo) {                                              // oldest block of the window: only its newest `todo` columns
+        const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
+        fifo = (fifo << todo) | (h >> (8u - todo)); cnt += (int)todo;
+        emit();
+    }
+}
+// best state at time t (phase tm): smallest (byte = m7 << 1 | newest mark, state index) over the 64 slots of a code block (viterbicore.h:468-520);
+// returns the slot address of that state.  Out of line for the same reason as vr_traceback.
+__device__ __noinline__ uint32_t vr_best_slot(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
+                                              const uint32_t q, const uint32_t tm, const uint32_t tn, const unsigned QM) {
+    const uint32_t R[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t v = h ? (R[r] >> 16) : (R[r] & 0xFFFFu);
+            const uint32_t A = (q << 4) | (uint32_t)vr_low4(r, h);
+            const uint32_t ns = ((A << tm) | (A >> (6u - tm))) & 63u;         // state index of this slot at time t
+            best = min(best, ((((v >> 9) << 1) | ((v >> tn) & 1u)) << 8) | ns);
+        }
+    }
+    best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
+    const uint32_t n = best & 63u;
+    return ((n >> tm) | (n << (6u - tm))) & 63u;
+}
+
+template <int CODE_RATE>
+struct VrDecoder {
+    static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
+    static constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
+    static constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;                                // 12 (R=1/2), 9 (2/3), 8 (3/4) soft bytes per 6 steps
+    uint32_t R[8];
+    VrLane LC;
+    unsigned QM; int q;
+    uint4* ring_q; const uint8_t* ring_b;
+    const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
+    uint32_t depth, look, end, ob, next_tb, nraw, wslot;
+    bool done;
+
+    __device__ __forceinline__ void fetch(const uint32_t pos, uint32_t (&a)[3]) const {
+        if (pos + CHUNK_BYTES > nsoft) { a[0] = a[1] = a[2] = 0; return; }
+        if constexpr (CODE_RATE == CR_34) { const uint2 v = __ldg((const uint2*)(sp + pos)); a[0] = v.x; a[1] = v.y; a[2] = 0; }
+        else if constexpr (CODE_RATE == CR_12) { a[0] = __ldg((const uint32_t*)(sp + pos)); a[1] = __ldg((const uint32_t*)(sp + pos + 4)); a[2] = __ldg((const uint32_t*)(sp + pos + 8)); }
+        else { uint32_t b[9];
+#pragma unroll
+               for (int i = 0; i < 9; i++) b[i] = __ldg(sp + pos + i);
+               // keep every puncture group inside one word: w0 = b0 b1 b2 -, w1 = b3 b4 b5 -, w2 = b6 b7 b8 -
+               a[0] = b[0] | (b[1] << 8) | (b[2] << 16); a[1] = b[3] | (b[4] << 8) | (b[5] << 16); a[2] = b[6] | (b[7] << 8) | (b[8] << 16); }
+    }
+    // the 16 history bytes of this lane (low byte of every half), in slot-address order, into ring entry `e`
+    __device__ __forceinline__ void store_hist(const uint32_t e) {
         uint4 w;
         w.x = __byte_perm(R[0], R[1], 0x6420); w.y = __byte_perm(R[2], R[3], 0x6420);
         w.z = __byte_perm(R[4], R[5], 0x6420); w.w = __byte_perm(R[6], R[7], 0x6420);
         ring_q[e * (SB_VR_FR * 4)] = w;
-    };
-    // windowed traceback from slot A0 at time t = tb + k (k = columns into the current block; its histories are in entry wslot), viterbi.hpp:205-237
-    auto do_traceback = [&](const uint32_t A0, const uint32_t k, const uint32_t la, const uint32_t nout) {
+    }
+    __device__ __forceinline__ void clear_hist() {
+#pragma unroll
+        for (int r = 0; r < 8; r++) R[r] &= 0xFE00FE00u;
+    }
+    __device__ __forceinline__ void next_slot() { wslot = wslot == SB_VR_NB - 1u ? 0u : wslot + 1u; }
+    // viterbi.hpp:177-180 -> viterbicore.h:445-465: subtract (smallest byte & 0xFE) = the smallest m7; `mask` names the lanes that take part
+    __device__ __forceinline__ void normalize(const unsigned mask) {
+        uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
+        m = min(m & 0xFFFFu, m >> 16) >> 9;             // smallest m7 of this lane
+        m = min(m, __shfl_xor_sync(mask, m, 1)); m = min(m, __shfl_xor_sync(mask, m, 2));
+        const uint32_t mv = m * 0x02000200u;
+#pragma unroll
+        for (int r = 0; r < 8; r++) R[r] -= mv;         // every half >= m << 9: no borrow between halves, histories untouched
+    }
+    // windowed traceback from slot A0 at time t (viterbi.hpp:205-237): one lane of the quad walks the ring (vr_traceback)
+    __device__ __forceinline__ void traceback(const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
         __syncwarp(QM);
-        if (q == 0) {
-            uint32_t A = A0, todo = la + nout, e = wslot;
-            uint32_t fifo = 0; int cnt = -(int)la;                  // the first `la` bits are only looked through; at most 13 bits wait
-            uint32_t wpos = nraw + (nout >> 3);                      // bytes come out last-first
-            auto push = [&](uint32_t bits, uint32_t n) {
-                fifo = (fifo << n) | bits; cnt += (int)n;
-                while (cnt >= 8) { --wpos; if (wpos < out_cap) op[wpos] = (uint8_t)(fifo >> (cnt - 8)); cnt -= 8; }
-            };
-            if (k < 6u) {                                            // partial newest block: k decisions in bits 0..k-1, the top k address bits change
-                const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
-                const uint32_t take = min(k, todo), am = (0x3Fu << (6u - k)) & 0x3Fu;
-                A = (A & ~am) | ((__brev(h) >> 26) & am);
-                push((h & ((1u << k) - 1u)) >> (k - take), take);
-                todo -= take; e = e ? e - 1u : SB_VR_NB - 1u;
-            }
-            while (todo >= 6u) {
-                const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A] & 0x3Fu;
-                A = __brev(h) >> 26;                                 // predecessor slot six columns earlier
-                push(h, 6u);
-                todo -= 6u; e = e ? e - 1u : SB_VR_NB - 1u;
-            }
-            if (todo) {                                              // oldest block of the window: only its newest `todo` columns
-                const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A] & 0x3Fu;
-                push(h >> (6u - todo), todo);
-            }
-        }
+        if (q == 0) vr_traceback(ring_b, op, out_cap, nraw + (nout >> 3), wslot, A0, t, la, nout);
         nraw += nout >> 3;
         __syncwarp(QM);
-    };
-    // normalisation + traceback triggers, evaluated after every puncture group at time t = tb + k, phase tm = t % 6 (compile-time in the main loop)
-    auto after_group = [&](const uint32_t t, const uint32_t tm, const uint32_t k) {
-        if ((t & 7u) == 0) {                            // viterbi.hpp:177-180 -> viterbicore.h:445-465: subtract (smallest byte & 0xFE) = smallest m7
-            uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
-            m = min(m & 0xFFFFu, m >> 16) >> 9;         // smallest m7 of this lane
-            m = min(m, __shfl_xor_sync(QM, m, 1)); m = min(m, __shfl_xor_sync(QM, m, 2));
-            const uint32_t mv = m * 0x02000200u;
-#pragma unroll
-            for (int r = 0; r < 8; r++) R[r] -= mv;     // every half >= m << 9: no borrow between halves, histories untouched
-        }
+    }
+    // traceback trigger at time t (a puncture-group boundary), viterbi.hpp:182-203; tm = t mod 6
+    __device__ __forceinline__ void trigger(const uint32_t t, const uint32_t tm) {
         if (t < next_tb) return;
-        uint32_t nout, la;                              // viterbi.hpp:182-203
+        uint32_t nout, la;
         if (t >= end) { nout = end - ob - 6u; la = t - end; }
         else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
         if (nout) {                                     // uniform inside the quad
-            // best state: smallest (byte = m7 << 1 | newest mark, state index) over the 64 slots (viterbicore.h:468-520)
-            const uint32_t tn = tm ? tm - 1u : 5u;      // bit of the newest decision
-            uint32_t best = 0xFFFFFFFFu;
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t v = h ? (R[r] >> 16) : (R[r] & 0xFFFFu);
-                    const uint32_t A = ((uint32_t)q << 4) | (uint32_t)vr_low4(r, h);
-                    const uint32_t ns = ((A << tm) | (A >> (6u - tm))) & 63u;         // state index of this slot at time t
-                    best = min(best, ((((v >> 9) << 1) | ((v >> tn) & 1u)) << 8) | ns);
-                }
-            }
-            best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
-            const uint32_t n = best & 63u;
-            const uint32_t A0 = ((n >> tm) | (n << (6u - tm))) & 63u;
-            if (k < 6u) store_hist(wslot);              // mid-block: the partial histories of the running block (a block end has just stored its own)
-            do_traceback(A0, k, la, nout);
+            const uint32_t A0 = vr_best_slot(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], (uint32_t)q, tm, (t - 1u) & 7u, QM);
+            if (t & 7u) store_hist(wslot);              // mid-block: the partial histories of the running block (a block end has just stored its own)
+            traceback(A0, t, la, nout);
             ob += nout;
         }
         if (ob + 6u >= end && t >= end) done = true;
         next_tb = min(end, ob + depth + look + 6u);
         if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
-    };
-    auto clear_hist = [&]() {
-#pragma unroll
-        for (int r = 0; r < 8; r++) R[r] &= 0xFE00FE00u;
-    };
+    }
+    // steps S .. 23 of a 24-step stretch that starts at a multiple of 24 and holds no traceback trigger: no branches at all
+    template <int S> __device__ __forceinline__ void fast(const uint32_t (&w)[4][3]) {
+        if constexpr (S < 24) {
+            vr_step<S % 6, true>(R, vr_bm<CODE_RATE, S % 6>(w[S / 6]), LC, 0x00010001u << (S % 8), 0xFFFFFFFFu);
+            if constexpr ((S + 1) % 8 == 0) {
+                store_hist(wslot); next_slot();
+                if constexpr ((S + 1) % GSTEPS == 0) normalize(0xFFFFFFFFu);
+                clear_hist();
+            }
+            fast<S + 1>(w);
+        }
+    }
+    // steps s .. 5 of a 6-step chunk that starts at time tb (a multiple of 6), with every event check; quads that are not `live` only keep step
+    template <int s> __device__ __forceinline__ void slow(const uint32_t (&w)[3], const uint32_t tb, const bool live) {
+        if constexpr (s < 6) {
+            const uint32_t t = tb + s + 1u;
+            vr_step<s, true>(R, vr_bm<CODE_RATE, s>(w), LC, 0x00010001u << ((t - 1u) & 7u), 0xFFFFFFFFu);
+            const bool blk = (t & 7u) == 0u;            // uniform over the warp
+            if (blk) store_hist(wslot);
+            if constexpr ((s + 1) % GSTEPS == 0) {
+                if (blk) normalize(0xFFFFFFFFu);
+                if (live && !done) trigger(t, (s + 1) % 6);
+            }
+            if (blk) { clear_hist(); next_slot(); }
+            slow<s + 1>(w, tb, live);
+        }
+    }
+};
 
-    // main loop: 6 trellis steps (one phase cycle = one history block) per iteration; the next chunk's soft values are prefetched
-    constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;        // 12 (R=1/2), 9 (2/3), 8 (3/4)
-    uint32_t w0 = 0, w1 = 0, w2 = 0;                    // current chunk, little-endian bytes
-    auto fetch = [&](uint32_t pos, uint32_t& a0, uint32_t& a1, uint32_t& a2) {
-        if (pos + CHUNK_BYTES > nsoft) { a0 = a1 = a2 = 0; return; }
-        if (CODE_RATE == CR_34) { uint2 v = __ldg((const uint2*)(sp + pos)); a0 = v.x; a1 = v.y; a2 = 0; }
-        else if (CODE_RATE == CR_12) { a0 = __ldg((const uint32_t*)(sp + pos)); a1 = __ldg((const uint32_t*)(sp + pos + 4)); a2 = __ldg((const uint32_t*)(sp + pos + 8)); }
-        else { uint32_t b[9];
+// Work lists: the frames of every code rate, densely, so that each rate's launch runs warps of eight live code blocks.
+// cnt[3] must be zero on entry; list holds 3 x nframes entries.
+__global__ void k_vit_lists(const FrameInfo* __restrict__ info, uint32_t nframes, uint32_t* __restrict__ cnt, uint32_t* __restrict__ list) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t rate = 3u;
+    if (f < nframes) { const FrameInfo fi = info[f]; if (fi.status == E_SUCCESS && fi.code_rate < 3u) rate = fi.code_rate; }
 #pragma unroll
-               for (int i = 0; i < 9; i++) b[i] = __ldg(sp + pos + i);
-               // keep every puncture group inside one word: w0 = b0 b1 b2 -, w1 = b3 b4 b5 -, w2 = b6 b7 b8 -
-               a0 = b[0] | (b[1] << 8) | (b[2] << 16); a1 = b[3] | (b[4] << 8) | (b[5] << 16); a2 = b[6] | (b[7] << 8) | (b[8] << 16); }
-    };
-    fetch(0, w0, w1, w2);
-    while (!done && pos_soft + CHUNK_BYTES <= nsoft) {
-        uint32_t n0, n1, n2; fetch(pos_soft + CHUNK_BYTES, n0, n1, n2);
-        pos_soft += CHUNK_BYTES;
-        if (CODE_RATE == CR_12) {
-            vr_step<0>(R, vq_bm_ab<0>(w0), LC, QM); after_group(tb + 1, 1, 1);
-            vr_step<1>(R, vq_bm_ab<2>(w0), LC, QM); after_group(tb + 2, 2, 2);
-            vr_step<2>(R, vq_bm_ab<0>(w1), LC, QM); after_group(tb + 3, 3, 3);
-            vr_step<3>(R, vq_bm_ab<2>(w1), LC, QM); after_group(tb + 4, 4, 4);
-            vr_step<4>(R, vq_bm_ab<0>(w2), LC, QM); after_group(tb + 5, 5, 5);
-            vr_step<5>(R, vq_bm_ab<2>(w2), LC, QM); store_hist(wslot); after_group(tb + 6, 0, 6);
-        } else if (CODE_RATE == CR_34) {
-            vr_step<0>(R, vq_bm_ab<0>(w0), LC, QM);
-            vr_step<1>(R, vq_bm_a<2>(w0), LC, QM);
-            vr_step<2>(R, vq_bm_b<3>(w0), LC, QM);  after_group(tb + 3, 3, 3);
-            vr_step<3>(R, vq_bm_ab<0>(w1), LC, QM);
-            vr_step<4>(R, vq_bm_a<2>(w1), LC, QM);
-            vr_step<5>(R, vq_bm_b<3>(w1), LC, QM);  store_hist(wslot); after_group(tb + 6, 0, 6);
-        } else {
-            vr_step<0>(R, vq_bm_ab<0>(w0), LC, QM);
-            vr_step<1>(R, vq_bm_a<2>(w0), LC, QM);  after_group(tb + 2, 2, 2);
-            vr_step<2>(R, vq_bm_ab<0>(w1), LC, QM);
-            vr_step<3>(R, vq_bm_a<2>(w1), LC, QM);  after_group(tb + 4, 4, 4);
-            vr_step<4>(R, vq_bm_ab<0>(w2), LC, QM);
-            vr_step<5>(R, vq_bm_a<2>(w2), LC, QM);  store_hist(wslot); after_group(tb + 6, 0, 6);
-        }
-        clear_hist();
-        tb += 6; wslot = wslot == SB_VR_NB - 1u ? 0u : wslot + 1u;
-        w0 = n0; w1 = n1; w2 = n2;
+    for (uint32_t r = 0; r < 3u; r++) {                 // one atomic per warp and rate
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, rate == r);
+        if (m == 0u) continue;
+        const int leader = __ffs(m) - 1; uint32_t base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(cnt + r, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (rate == r) list[(size_t)r * nframes + base + (uint32_t)__popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = f;
     }
-    // tail: whole puncture groups that do not fill a 6-step block (standalone API with arbitrary nsoft).
-    // Rare and short, so phases are dispatched at run time.
-    {
-        uint32_t k = 0;                                 // steps into the block at tb (the main loop always leaves it at 0)
-        auto step_rt = [&](uint32_t Cbase) {
-            switch (k) { case 0: vr_step<0>(R, Cbase, LC, QM); break; case 1: vr_step<1>(R, Cbase, LC, QM); break;
-                         case 2: vr_step<2>(R, Cbase, LC, QM); break; case 3: vr_step<3>(R, Cbase, LC, QM); break;
-                         case 4: vr_step<4>(R, Cbase, LC, QM); break; default: vr_step<5>(R, Cbase, LC, QM); }
+}
+
+// list / cnt: work list of this code rate (k_vit_lists) or null = frames 0 .. nframes-1 with the uniform parameters of `job`.
+template <int CODE_RATE>
+__global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
+        const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
+        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out) {
+    __shared__ uint4 s_ring[SB_VR_NB][SB_VR_FR][4];    // entry: history bytes of the 64 slots of every code block over 8 columns
+    using D = VrDecoder<CODE_RATE>;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
+    if (blockIdx.x * SB_VR_FR >= nvalid) return;        // whole CTA
+    const int lane = threadIdx.x & 31, q = lane & 3, fb = lane >> 2;
+    const uint32_t idx = blockIdx.x * SB_VR_FR + fb;
+    const bool valid = idx < nvalid;
+    const uint32_t f = !valid ? 0u : list ? __ldg(list + (size_t)CODE_RATE * nframes + idx) : idx;
+    uint32_t L = job.frame_len;
+    D d;
+    d.nsoft = job.nsoft;
+    if (valid && info) { const FrameInfo fi = info[f]; L = fi.length; d.nsoft = fi.soft_bytes; }
+    if (!valid) d.nsoft = 0;
+    d.q = q; d.QM = 0xFu << (lane & 28);
+    d.depth = job.depth; d.look = job.lookahead;
+    d.sp = soft + (size_t)f * soft_stride;
+    d.op = out + (size_t)f * out_stride + raw_off;
+    d.out_cap = (uint32_t)(out_stride - raw_off < 0xFFFFFFFFull ? out_stride - raw_off : 0xFFFFFFFFull);
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        int lc = q == 0 ? vq_lcls(t, 0) : q == 1 ? vq_lcls(t, 1) : q == 2 ? vq_lcls(t, 2) : vq_lcls(t, 3);
+        d.LC.swz[t] = (unsigned)((0 ^ lc) | ((1 ^ lc) << 4) | ((2 ^ lc) << 8) | ((3 ^ lc) << 12));
+    }
+    d.LC.bA[0] = (q >> 1) & 1; d.LC.bB[0] = 1u - d.LC.bA[0];       // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
+    d.LC.bA[1] = q & 1;        d.LC.bB[1] = 1u - d.LC.bA[1];
+    // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address; byte value v sits at v << 8
+#pragma unroll
+    for (int r = 0; r < 8; r++) d.R[r] = 0x30003000u;
+    if (q == 0) d.R[0] = 0x30000000u;
+    d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
+    d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
+    d.ring_q = &s_ring[0][fb][q];                       // + entry * (SB_VR_FR * 4)
+    d.ring_b = (const uint8_t*)&s_ring[0][fb][0];       // + entry * (SB_VR_FR * 64) + slot
+
+    // lockstep part: all eight code blocks of the warp advance together, 24 or 6 steps at a time; the soft values of the next four chunks
+    // are always in registers
+    uint32_t tb = 0, pos = 0, phase24 = 0;              // time and soft position at the start of the next chunk (uniform); (tb / 6) mod 4
+    uint32_t w[4][3];
+#pragma unroll
+    for (int c = 0; c < 4; c++) d.fetch(pos + c * D::CHUNK_BYTES, w[c]);
+    bool stale = false;                                 // out of input while others kept stepping (cannot happen with whole-symbol inputs)
+    for (;;) {
+        const bool more = !d.done && pos + D::CHUNK_BYTES <= d.nsoft;
+        if (!__any_sync(FULL, more)) break;
+        if (!more && !d.done) stale = true;
+        const bool fast_ok = d.done || (tb + 24u < d.next_tb && pos + 4u * D::CHUNK_BYTES <= d.nsoft);
+        if (phase24 == 0u && __all_sync(FULL, fast_ok)) {
+            uint32_t n[4][3];
+#pragma unroll
+            for (int c = 0; c < 4; c++) d.fetch(pos + (4 + c) * D::CHUNK_BYTES, n[c]);
+            d.template fast<0>(w);
+#pragma unroll
+            for (int c = 0; c < 4; c++) { w[c][0] = n[c][0]; w[c][1] = n[c][1]; w[c][2] = n[c][2]; }
+            tb += 24u; pos += 4u * D::CHUNK_BYTES;
+            continue;
+        }
+        uint32_t n[3];
+        d.fetch(pos + 4u * D::CHUNK_BYTES, n);
+        d.template slow<0>(w[0], tb, more);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { w[c][0] = w[c + 1][0]; w[c][1] = w[c + 1][1]; w[c][2] = w[c + 1][2]; }
+        w[3][0] = n[0]; w[3][1] = n[1]; w[3][2] = n[2];
+        tb += 6u; pos += D::CHUNK_BYTES; phase24 = (phase24 + 1u) & 3u;
+    }
+    // tail: whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft): per code block, phases at run time
+    if (!d.done && !stale) {
+        uint32_t k = 0;                                 // steps into the chunk at tb
+        auto step_rt = [&](const uint32_t Cbase) {
+            const uint32_t mark = 0x00010001u << ((tb + k) & 7u);
+            switch (k) { case 0: vr_step<0, false>(d.R, Cbase, d.LC, mark, d.QM); break; case 1: vr_step<1, false>(d.R, Cbase, d.LC, mark, d.QM); break;
+                         case 2: vr_step<2, false>(d.R, Cbase, d.LC, mark, d.QM); break; case 3: vr_step<3, false>(d.R, Cbase, d.LC, mark, d.QM); break;
+                         case 4: vr_step<4, false>(d.R, Cbase, d.LC, mark, d.QM); break; default: vr_step<5, false>(d.R, Cbase, d.LC, mark, d.QM); }
             k++;
-            if (k == 6) store_hist(wslot);
+            if (((tb + k) & 7u) == 0u) d.store_hist(d.wslot);
         };
-        while (!done && pos_soft + GROUP <= nsoft) {
-            uint32_t w = __ldg(sp + pos_soft) | ((uint32_t)__ldg(sp + pos_soft + 1) << 8);
-            if (GROUP > 2) w |= (uint32_t)__ldg(sp + pos_soft + 2) << 16;
-            if (GROUP > 3) w |= (uint32_t)__ldg(sp + pos_soft + 3) << 24;
-            pos_soft += GROUP;
-            step_rt(vq_bm_ab<0>(w));
-            if (GSTEPS >= 2) step_rt(vq_bm_a<2>(w));
-            if (GSTEPS >= 3) step_rt(vq_bm_b<3>(w));
-            after_group(tb + k, k == 6 ? 0u : k, k);
-            if (k == 6) { clear_hist(); k = 0; tb += 6; wslot = wslot == SB_VR_NB - 1u ? 0u : wslot + 1u; }
+        auto block_end = [&]() { if (((tb + k) & 7u) == 0u) { d.clear_hist(); d.next_slot(); } };
+        while (!d.done && pos + D::GROUP <= d.nsoft) {
+            uint32_t g = __ldg(d.sp + pos) | ((uint32_t)__ldg(d.sp + pos + 1) << 8);
+            if (D::GROUP > 2) g |= (uint32_t)__ldg(d.sp + pos + 2) << 16;
+            if (D::GROUP > 3) g |= (uint32_t)__ldg(d.sp + pos + 3) << 24;
+            pos += D::GROUP;
+            step_rt(vq_bm_ab<0>(g));
+            if (D::GSTEPS >= 2) { block_end(); step_rt(vq_bm_a<2>(g)); }
+            if (D::GSTEPS >= 3) { block_end(); step_rt(vq_bm_b<3>(g)); }
+            const uint32_t t = tb + k;
+            if ((t & 7u) == 0u) d.normalize(d.QM);
+            d.trigger(t, k == 6 ? 0u : k);
+            block_end();
+            if (k == 6) { k = 0; tb += 6; }
         }
     }
-    if (q == 0) nraw_out[f] = nraw;
+    if (valid && q == 0) nraw_out[f] = d.nraw;
 }
 
 // Descrambler + frame sink after the Viterbi kernel, one thread per frame (T11aDesc, scramble.hpp:269-355; TBB11aFrameSink, PHY_11a.hpp:609-702):
