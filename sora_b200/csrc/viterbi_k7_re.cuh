@@ -29,6 +29,7 @@
 // cycle per sub-partition; VIMNMX + two adds (the v2 ACS) at 0.75; LOP3 and PRMT at 0.5.
 #pragma once
 #include "viterbi_k7_quad.cuh"
+#include <type_traits>
 
 namespace sb {
 
@@ -40,25 +41,31 @@ __host__ __device__ constexpr int vr_low4(int r, int h) { return (r << 1) | h; }
 __host__ __device__ constexpr int vr_scls(int T, int r, int h) { return vq_cls(vq_rol6(vr_low4(r, h), T) & 31); }
 __host__ __device__ constexpr int vr_kcls(int T) { return vq_cls(vq_rol6(1, T) & 31); }     // class difference between the two halves of a register
 
+// adds that must run on the FMA pipe (IMAD), not the ALU pipe the add-min and the PRMTs already fill: ptxas picks the pipe of a plain `+` itself
+__device__ __forceinline__ uint32_t vr_fadd(uint32_t a, uint32_t b) { uint32_t d; asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t vr_frsub(uint32_t v, uint32_t k) { uint32_t d; asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, %2;" : "=r"(d) : "r"(v), "r"(k)); return d; }   // k - v
+
 struct VrLane {
-    unsigned swz[6];       // per-phase byte swizzle applying this lane's class contribution
+    unsigned sel[6][2];    // per phase: PRMT selectors building [0, Cb[c], 0, Cb[c ^ K]] for c = 0, 1 straight from the class-indexed branch-metric
+                           // bytes, this lane's class contribution folded in (Cb[i] = Cbase[i ^ lane class])
     uint32_t bA[2], bB[2]; // lane-pair phases: 1 if the history mark of the step goes to my own value / to my partner's (exactly one is set)
 };
 
 // one trellis step at compile-time phase T (= (t - 1) mod 6 for the step that produces column t).  Cbase byte (cA<<1|cB) = metric of the even
-// candidate for a predecessor of that class; the complement class (3 - index) is the odd candidate's.  The odd candidate (state p+32)
-// carries `mark` = 0x00010001 << ((t - 1) mod 8).  WARP: the whole warp executes the step together (full-mask shuffle).
+// candidate for a predecessor of that class; the complement class (3 - index) is the odd candidate's and equals KC - it per half (KC = 28 << 8 per half
+// when both coded bits are present, 14 << 8 when one is punctured; a register like the marks).  The odd candidate (state p+32) carries the history mark of the step, 0x00010001 << ((t-1) mod 8):
+//   T <= 1 : mA = mark if this lane holds the odd role else 0, mB = mark - mA;   T = 2..4 : mA = mark;   T = 5 : mA = mark << 16 part, mB = low part.
+// The marks come in as registers so that every constant add is an IMAD.IADD (FMA pipe), not an immediate VIADD (ALU pipe, the busy one).
+// WARP: the whole warp executes the step together (full-mask shuffle).
 template <int T, bool WARP>
-__device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, const VrLane& L, const uint32_t mark, const unsigned qmask) {
-    const uint32_t Cb = __byte_perm(Cbase, 0, L.swz[T]);
-    constexpr int K = vr_kcls(T);
+__device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, const VrLane& L, const uint32_t KC, const uint32_t mA, const uint32_t mB, const unsigned qmask) {
     uint32_t V[4];                                      // [0, Cb[c], 0, Cb[c ^ K]]: branch metrics of class c (low half) and its high-half companion
-#pragma unroll
-    for (int c = 0; c < 4; c++) V[c] = __byte_perm(Cb, 0, vq_sel(c, c ^ K));
+    V[0] = __byte_perm(Cbase, 0, L.sel[T][0]); V[1] = __byte_perm(Cbase, 0, L.sel[T][1]);
+    V[3] = vr_frsub(V[0], KC); V[2] = vr_frsub(V[1], KC);                 // complement classes; no borrow: every half of V is <= its half of KC
     if constexpr (T <= 1) {                             // pair = partner lane (xor 2 at T=0, xor 1 at T=1): the path-metric exchange
         uint32_t Va[4], Vb[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) { Va[c] = L.bA[T] * mark + V[c]; Vb[c] = L.bB[T] * mark + V[c]; }
+        for (int c = 0; c < 4; c++) { Va[c] = vr_fadd(V[c], mA); Vb[c] = vr_fadd(V[c], mB); }
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int c0 = vr_scls(T, r, 0);
@@ -69,7 +76,7 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, 
         constexpr int d = T == 2 ? 4 : T == 3 ? 2 : 1;
         uint32_t VO[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) VO[c] = V[c] + mark;
+        for (int c = 0; c < 4; c++) VO[c] = vr_fadd(V[c], mA);
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             if (r & d) continue;
@@ -81,7 +88,7 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, 
     } else {                                            // pair = the two halves of each register: low = p, high = p + 32
         uint32_t W1[4], W2[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) { W1[c] = V[c] + (mark & 0xFFFF0000u); W2[c] = V[c] + (mark & 0x0000FFFFu); }
+        for (int c = 0; c < 4; c++) { W1[c] = vr_fadd(V[c], mA); W2[c] = vr_fadd(V[c], mB); }
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int c = vr_scls(5, r, 0);
@@ -89,6 +96,13 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, 
             R[r] = __viaddmin_u16x2(R[r], W1[c], __vadd2(y, W2[c ^ 3]));   // [min(p + a, p32 + b), min(p32 + a, p + b)] = new states 2p, 2p + 1
         }
     }
+}
+// the same with the mark of the step given as a plain value (6-step path and tail: the time is only known at run time)
+template <int T, bool WARP>
+__device__ __forceinline__ void vr_step_rt(uint32_t (&R)[8], const uint32_t Cbase, const VrLane& L, const uint32_t KC, const uint32_t mark, const unsigned qmask) {
+    if constexpr (T <= 1) vr_step<T, WARP>(R, Cbase, L, KC, L.bA[T] * mark, L.bB[T] * mark, qmask);
+    else if constexpr (T <= 4) vr_step<T, WARP>(R, Cbase, L, KC, mark, 0u, qmask);
+    else vr_step<T, WARP>(R, Cbase, L, KC, mark & 0xFFFF0000u, mark & 0x0000FFFFu, qmask);
 }
 
 // branch-metric vector of step s (0..5) of a 6-step chunk held in w[] (vq_bm_*: viterbi_k7_quad.cuh)
@@ -156,6 +170,11 @@ __device__ __noinline__ uint32_t vr_best_slot(uint32_t r0, uint32_t r1, uint32_t
     return ((n >> tm) | (n << (6u - tm))) & 63u;
 }
 
+// sum of the two complementary branch metrics of step s: 28 with both coded bits, 14 with one
+template <int CODE_RATE, int s> __host__ __device__ constexpr uint32_t vr_ksum() {
+    return CODE_RATE == CR_12 ? 28u : CODE_RATE == CR_34 ? (s % 3 == 0 ? 28u : 14u) : ((s & 1) ? 14u : 28u);
+}
+
 template <int CODE_RATE>
 struct VrDecoder {
     static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
@@ -163,6 +182,8 @@ struct VrDecoder {
     static constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;                                // 12 (R=1/2), 9 (2/3), 8 (3/4) soft bytes per 6 steps
     uint32_t R[8];
     VrLane LC;
+    uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves, as registers
+    uint32_t mk[8], mkA[2][4], mkB[2][4], mkH[4], mkL[4];   // history marks 0x00010001 << j as registers; per lane-pair phase and chunk; T = 5 halves
     unsigned QM; int q;
     uint4* ring_q; const uint8_t* ring_b;
     const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
@@ -226,7 +247,12 @@ struct VrDecoder {
     // steps S .. 23 of a 24-step stretch that starts at a multiple of 24 and holds no traceback trigger: no branches at all
     template <int S> __device__ __forceinline__ void fast(const uint32_t (&w)[4][3]) {
         if constexpr (S < 24) {
-            vr_step<S % 6, true>(R, vr_bm<CODE_RATE, S % 6>(w[S / 6]), LC, 0x00010001u << (S % 8), 0xFFFFFFFFu);
+            constexpr int T = S % 6, J = S % 8, I = S / 6;
+            const uint32_t cb = vr_bm<CODE_RATE, T>(w[I]);
+            const uint32_t KC = kc[vr_ksum<CODE_RATE, T>() == 28u ? 0 : 1];
+            if constexpr (T <= 1) vr_step<T, true>(R, cb, LC, KC, mkA[T][I], mkB[T][I], 0xFFFFFFFFu);
+            else if constexpr (T <= 4) vr_step<T, true>(R, cb, LC, KC, mk[J], 0u, 0xFFFFFFFFu);
+            else vr_step<T, true>(R, cb, LC, KC, mkH[I], mkL[I], 0xFFFFFFFFu);
             if constexpr ((S + 1) % 8 == 0) {
                 store_hist(wslot); next_slot();
                 if constexpr ((S + 1) % GSTEPS == 0) normalize(0xFFFFFFFFu);
@@ -239,7 +265,7 @@ struct VrDecoder {
     template <int s> __device__ __forceinline__ void slow(const uint32_t (&w)[3], const uint32_t tb, const bool live) {
         if constexpr (s < 6) {
             const uint32_t t = tb + s + 1u;
-            vr_step<s, true>(R, vr_bm<CODE_RATE, s>(w), LC, 0x00010001u << ((t - 1u) & 7u), 0xFFFFFFFFu);
+            vr_step_rt<s, true>(R, vr_bm<CODE_RATE, s>(w), LC, kc[vr_ksum<CODE_RATE, s>() == 28u ? 0 : 1], 0x00010001u << ((t - 1u) & 7u), 0xFFFFFFFFu);
             const bool blk = (t & 7u) == 0u;            // uniform over the warp
             if (blk) store_hist(wslot);
             if constexpr ((s + 1) % GSTEPS == 0) {
@@ -295,11 +321,24 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     d.out_cap = (uint32_t)(out_stride - raw_off < 0xFFFFFFFFull ? out_stride - raw_off : 0xFFFFFFFFull);
 #pragma unroll
     for (int t = 0; t < 6; t++) {
-        int lc = q == 0 ? vq_lcls(t, 0) : q == 1 ? vq_lcls(t, 1) : q == 2 ? vq_lcls(t, 2) : vq_lcls(t, 3);
-        d.LC.swz[t] = (unsigned)((0 ^ lc) | ((1 ^ lc) << 4) | ((2 ^ lc) << 8) | ((3 ^ lc) << 12));
+        const int lc = q == 0 ? vq_lcls(t, 0) : q == 1 ? vq_lcls(t, 1) : q == 2 ? vq_lcls(t, 2) : vq_lcls(t, 3);
+        const int K = vr_kcls(t);
+        d.LC.sel[t][0] = vq_sel(0 ^ lc, 0 ^ K ^ lc); d.LC.sel[t][1] = vq_sel(1 ^ lc, 1 ^ K ^ lc);
     }
     d.LC.bA[0] = (q >> 1) & 1; d.LC.bB[0] = 1u - d.LC.bA[0];       // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
     d.LC.bA[1] = q & 1;        d.LC.bB[1] = 1u - d.LC.bA[1];
+    {   // history marks as run-time values (z is always 0, which the compiler cannot know): they must stay register operands
+        const uint32_t z = (uint32_t)(soft_stride >> 63);
+        d.kc[0] = 0x1C001C00u + z; d.kc[1] = 0x0E000E00u + z;
+#pragma unroll
+        for (int j = 0; j < 8; j++) d.mk[j] = (0x00010001u << j) + z;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {                   // chunk i of a 24-step stretch: its steps 0, 1, 5 are steps 6i, 6i+1, 6i+5
+            d.mkA[0][i] = d.LC.bA[0] * d.mk[(6 * i) % 8];     d.mkB[0][i] = d.LC.bB[0] * d.mk[(6 * i) % 8];
+            d.mkA[1][i] = d.LC.bA[1] * d.mk[(6 * i + 1) % 8]; d.mkB[1][i] = d.LC.bB[1] * d.mk[(6 * i + 1) % 8];
+            d.mkH[i] = d.mk[(6 * i + 5) % 8] & 0xFFFF0000u;   d.mkL[i] = d.mk[(6 * i + 5) % 8] & 0x0000FFFFu;
+        }
+    }
     // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address; byte value v sits at v << 8
 #pragma unroll
     for (int r = 0; r < 8; r++) d.R[r] = 0x30003000u;
@@ -342,11 +381,11 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     // tail: whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft): per code block, phases at run time
     if (!d.done && !stale) {
         uint32_t k = 0;                                 // steps into the chunk at tb
-        auto step_rt = [&](const uint32_t Cbase) {
+        auto step_rt = [&](const uint32_t Cbase, const uint32_t KC) {
             const uint32_t mark = 0x00010001u << ((tb + k) & 7u);
-            switch (k) { case 0: vr_step<0, false>(d.R, Cbase, d.LC, mark, d.QM); break; case 1: vr_step<1, false>(d.R, Cbase, d.LC, mark, d.QM); break;
-                         case 2: vr_step<2, false>(d.R, Cbase, d.LC, mark, d.QM); break; case 3: vr_step<3, false>(d.R, Cbase, d.LC, mark, d.QM); break;
-                         case 4: vr_step<4, false>(d.R, Cbase, d.LC, mark, d.QM); break; default: vr_step<5, false>(d.R, Cbase, d.LC, mark, d.QM); }
+            switch (k) { case 0: vr_step_rt<0, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break; case 1: vr_step_rt<1, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break;
+                         case 2: vr_step_rt<2, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break; case 3: vr_step_rt<3, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break;
+                         case 4: vr_step_rt<4, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break; default: vr_step_rt<5, false>(d.R, Cbase, d.LC, KC, mark, d.QM); }
             k++;
             if (((tb + k) & 7u) == 0u) d.store_hist(d.wslot);
         };
@@ -356,9 +395,9 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
             if (D::GROUP > 2) g |= (uint32_t)__ldg(d.sp + pos + 2) << 16;
             if (D::GROUP > 3) g |= (uint32_t)__ldg(d.sp + pos + 3) << 24;
             pos += D::GROUP;
-            step_rt(vq_bm_ab<0>(g));
-            if (D::GSTEPS >= 2) { block_end(); step_rt(vq_bm_a<2>(g)); }
-            if (D::GSTEPS >= 3) { block_end(); step_rt(vq_bm_b<3>(g)); }
+            step_rt(vq_bm_ab<0>(g), d.kc[0]);
+            if (D::GSTEPS >= 2) { block_end(); step_rt(vq_bm_a<2>(g), d.kc[1]); }
+            if (D::GSTEPS >= 3) { block_end(); step_rt(vq_bm_b<3>(g), d.kc[1]); }
             const uint32_t t = tb + k;
             if ((t & 7u) == 0u) d.normalize(d.QM);
             d.trigger(t, k == 6 ? 0u : k);
