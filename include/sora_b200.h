@@ -81,10 +81,15 @@ float sb200_last_kernel_ms(sb200_handle* h);
 /* per-kernel device times (ms) of the most recent sb200_rx11a_batch: [0] carrier sense, [1] OFDM front end,
  * [2] Viterbi+descramble+CRC, [3] result pack */
 int sb200_last_kernel_times(sb200_handle* h, float* ms4);
-/* Tunables.  "chunk_frames" (default 8192): when the IQ buffer is HOST memory, calls with more slots are cut into chunks whose
+/* Tunables.  "chunk_frames" (default 4096): when the IQ buffer is HOST memory, calls with more slots are cut into chunks whose
  * host->device copy, OFDM front end and Viterbi overlap on three streams; 0 = one pass on the caller's stream.
- * "chunk_frames_device" (default 0 = off): the same for device-resident IQ.  sb200_last_kernel_times needs an un-chunked call.  A device-resident slot table (frame_off/frame_len) is
- * read back once and assumed unchanged while the same pointers are passed again. */
+ * "chunk_frames_device" (default 0 = off): the same for device-resident IQ.  sb200_last_kernel_times needs an un-chunked call.
+ * "host_decimate" (default 0 = off): number of host threads (the caller's included) that gather the even samples of every slot of a chunk
+ * into pinned staging memory before the copy — TDownSample2 (Brick11/src/samples.hpp:27-49) keeps samples 0 and 2 of every 4, so the
+ * 802.11a chain never reads the odd ones and only half of a host-resident 40 Msps capture has to cross PCIe.  Results are identical.
+ * Slot tables (frame_off/frame_len) are bounds-checked against iq_total_samples on EVERY call, host- or device-resident (a device table costs one
+ * small reduction kernel and an 8-byte read-back).  "slot_table_immutable" (default 0): set to 1 to promise that a device-resident table is not
+ * rewritten while the same pointers, count and total are passed again; only then is the check (and the host copy the chunked path needs) cached. */
 int sb200_set_option(sb200_handle* h, const char* name, uint64_t value);
 
 /* Decode `nframes` independent capture slots.  Slot i is iq[2*frame_off[i] .. 2*(frame_off[i]+frame_len[i])) int16

@@ -10,7 +10,10 @@
 
 using namespace sbo;
 
+static uint32_t g_cca_thr = 1000 * 1000;   // CF_11CCA::cca_pwr_threshold used by the 802.11a entry points below (fb11ademod_config.hpp:107 default)
+
 extern "C" {
+void sbo_set_cca_threshold(uint32_t thr) { g_cca_thr = thr ? thr : 1000 * 1000; }
 
 struct sbo_frame_result {           // mirrors sbo::FrameResult; keep in sync with tests/oracle_py.py
     uint32_t status, rate_kbps, length, crc32, nsym, sample_index, detect_index;
@@ -19,7 +22,7 @@ struct sbo_frame_result {           // mirrors sbo::FrameResult; keep in sync wi
 
 int sbo_rx11a_run(const int16_t* iq, uint64_t nsamples, int max_frames, sbo_frame_result* res,
                   uint8_t* out, uint64_t out_stride) {
-    Rx11a rx;
+    Rx11a rx; rx.cca_pwr_threshold = g_cca_thr;
     return rx.run((const c16*)iq, (size_t)nsamples, (FrameResult*)res, out, (size_t)out_stride, max_frames);
 }
 
@@ -29,7 +32,7 @@ void sbo_rx11a_batch(const int16_t* iq, const uint64_t* off, const uint32_t* len
                      sbo_frame_result* res, uint8_t* out, uint64_t out_stride, int nthreads) {
     std::atomic<uint32_t> next(0);
     auto work = [&]() {
-        Rx11a rx;
+        Rx11a rx; rx.cca_pwr_threshold = g_cca_thr;
         for (;;) {
             uint32_t i = next.fetch_add(1); if (i >= nframes) break;
             FrameResult r; memset(&r, 0, sizeof r);
@@ -43,12 +46,69 @@ void sbo_rx11a_batch(const int16_t* iq, const uint64_t* off, const uint32_t* len
     for (auto& t : th) t.join();
 }
 
+// The same batch through the reference's two-thread topology: every pipeline = one front-end thread (carrier sense .. de-interleaver) and one
+// Viterbi thread (T11aViterbi .. frame sink) joined by a single-producer / single-consumer ring, like TThreadSeparator<> (stdbrick.hpp:91-248).
+// npipes pipelines share the slots through an atomic counter.  Results are identical to sbo_rx11a_batch (tests/test_cpu_oracle.py).
+namespace {
+struct SplitRing : Rx11a::SoftSplit {
+    struct Rec { uint32_t kind, slot; int code_rate; uint16_t frame_length; int ncbps; uint8_t soft[288]; };   // kind 0 begin, 1 symbol, 2 frame complete, 3 stop, 4 slot ended without a complete frame
+    static const uint32_t N = 512;
+    std::vector<Rec> ring; std::atomic<uint32_t> head{0}, tail{0}; uint32_t cur_slot = 0;
+    SplitRing() : ring(N) {}
+    Rec& claim() { uint32_t h = head.load(std::memory_order_relaxed); while (h - tail.load(std::memory_order_acquire) >= N) std::this_thread::yield(); return ring[h % N]; }
+    void publish() { head.store(head.load(std::memory_order_relaxed) + 1, std::memory_order_release); }
+    void begin(int code_rate, uint16_t frame_length) override { Rec& r = claim(); r.kind = 0; r.slot = cur_slot; r.code_rate = code_rate; r.frame_length = frame_length; publish(); }
+    void symbol(const uint8_t* dsoft, int ncbps) override { Rec& r = claim(); r.kind = 1; r.slot = cur_slot; r.ncbps = ncbps; memcpy(r.soft, dsoft, (size_t)ncbps); publish(); }
+    void mark(uint32_t kind, uint32_t slot) { Rec& r = claim(); r.kind = kind; r.slot = slot; publish(); }
+    const Rec* peek() { uint32_t t = tail.load(std::memory_order_relaxed); while (head.load(std::memory_order_acquire) == t) std::this_thread::yield(); return &ring[t % N]; }
+    void pop() { tail.store(tail.load(std::memory_order_relaxed) + 1, std::memory_order_release); }
+};
+}
+void sbo_rx11a_batch_2t(const int16_t* iq, const uint64_t* off, const uint32_t* len, uint32_t nframes,
+                        sbo_frame_result* res, uint8_t* out, uint64_t out_stride, int npipes) {
+    std::atomic<uint32_t> next(0);
+    auto pipeline = [&]() {
+        SplitRing q;
+        std::thread back([&]() {                        // Viterbi thread
+            Rx11a vb; bool open = false;
+            for (;;) {
+                const SplitRing::Rec* r = q.peek(); const uint32_t kind = r->kind, slot = r->slot;
+                if (kind == 3) { q.pop(); break; }
+                if (kind == 0) { vb.back_begin(r->code_rate, r->frame_length); open = true; }
+                else if (kind == 1) vb.back_symbol(r->soft, r->ncbps);
+                else if (kind == 2 && open) {           // the slot's frame is complete: verdict, FCS and bytes come from this side
+                    uint32_t st = vb.back_status(); if (st == E_SUCCESS) st = E_FAILED;
+                    res[slot].status = st; res[slot].crc32 = vb.back_crc32();
+                    if (out) { size_t nb = res[slot].length < out_stride ? res[slot].length : out_stride; memcpy(out + (size_t)slot * out_stride, vb.frame_bytes(), nb); }
+                    open = false;
+                } else if (kind == 4) open = false;     // the capture ended inside the frame: nothing to report from this side
+                q.pop();
+            }
+        });
+        Rx11a rx; rx.cca_pwr_threshold = g_cca_thr; rx.split = &q;
+        for (;;) {
+            uint32_t i = next.fetch_add(1); if (i >= nframes) break;
+            q.cur_slot = i;
+            FrameResult r; memset(&r, 0, sizeof r);
+            int n = rx.run((const c16*)iq + off[i], len[i], &r, nullptr, 0, 1);
+            if (n == 0) { memset(&r, 0, sizeof r); r.status = E_NO_FRAME; }
+            memcpy(&res[i], &r, sizeof r);              // front-end fields; a decoded frame's status / crc32 / bytes are overwritten by the Viterbi thread
+            q.mark(n > 0 && r.status == E_FAILED ? 2u : 4u, i);   // E_FAILED = all symbols went through, the verdict is the Viterbi thread's
+        }
+        q.mark(3, 0);
+        back.join();
+    };
+    if (npipes <= 1) { pipeline(); return; }
+    std::vector<std::thread> th; for (int t = 0; t < npipes; t++) th.emplace_back(pipeline);
+    for (auto& t : th) t.join();
+}
+
 // Stage taps of the first frame in a buffer.  Buffers sized by the caller: coeffs 64 c16 each;
 // per-symbol arrays max_sym*64 c16; soft max_sym*288 bytes.  Returns number of symbols captured (incl. SIGNAL).
 int sbo_rx11a_taps(const int16_t* iq, uint64_t nsamples, sbo_frame_result* res,
                    int16_t* freq_coeffs, int16_t* chan_coeffs, int16_t* fft_out, int16_t* equalized, int16_t* tracked,
                    uint8_t* soft, uint32_t* soft_off, int max_sym) {
-    Rx11a rx; rx.taps.enable = true;
+    Rx11a rx; rx.cca_pwr_threshold = g_cca_thr; rx.taps.enable = true;
     FrameResult r; memset(&r, 0, sizeof r);
     int n = rx.run((const c16*)iq, (size_t)nsamples, &r, nullptr, 0, 1);
     if (n == 0) r.status = E_NO_FRAME;

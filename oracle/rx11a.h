@@ -46,6 +46,15 @@ public:
 
     uint32_t cca_pwr_threshold = 1000 * 1000;
     Taps taps;
+    // Two-thread topology of the reference (TThreadSeparator between the de-interleaver and T11aViterbi, fb11ademod_config.hpp:169-242;
+    // stdbrick.hpp:91-248): with `split` set, the front end hands every de-interleaved DATA symbol to it instead of decoding it, and a second
+    // Rx11a object on the consumer thread runs back_begin / back_symbol / back_result.
+    struct SoftSplit { virtual void begin(int code_rate, uint16_t frame_length) = 0; virtual void symbol(const uint8_t* dsoft, int ncbps) = 0; virtual ~SoftSplit() {} };
+    SoftSplit* split = nullptr;
+    void back_begin(int code_rate_, uint16_t frame_length_);
+    void back_symbol(const uint8_t* dsoft, int ncbps);
+    uint32_t back_status() const { return error_code; }
+    uint32_t back_crc32() const { return frame_crc32; }
     const uint8_t* frame_bytes() const { return frame_buf; }
 
 private:

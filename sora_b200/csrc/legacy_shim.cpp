@@ -31,6 +31,9 @@ bool decode_from(PBB11A_RX_CONTEXT c, PSORA_RADIO_RX_STREAM s) {
         e.bytes.assign(out.begin() + (size_t)i * 2560, out.begin() + (size_t)i * 2560 + (res[i].length < 2560 ? res[i].length : 2560));
         E->ev.push_back(std::move(e)); prev = sidx[i];
     }
+    // a full event list means the capture may hold more: the decoded span ends with the block of the last event, and the next carrier sense
+    // behind it decodes again from there (RxThread never stops after a fixed number of frames, fb11a_demod.cpp:29-81)
+    if (n == MAX_EVENTS) { const size_t nb = ((size_t)sidx[n - 1] + 27u) / 28u; if (nb < E->nblocks) E->nblocks = nb; }
     return true;
 }
 }
@@ -42,7 +45,10 @@ extern "C" void BB11ARxContextInit(PBB11A_RX_CONTEXT c, unsigned int SampleRate,
     memset(c, 0, sizeof *c);
     c->SampleRate = SampleRate; c->uiCSCorrThreshold = thr; c->uiCSMaxFetchRxBlock = maxBlk; c->uiCSMinFetchRxBlock = minBlk; c->ri_pbWorkIndicator = work;
     const char* d = getenv("SB200_DEVICE"); sb200_handle* h = nullptr;
-    if (sb200_create(d ? atoi(d) : 0, nullptr, &h) == SB200_OK) c->b200_engine = h;      // no CPU fallback: every later call fails without it
+    // rxThreshold gates the carrier sense.  The legacy detector asks autocorrelation > threshold (arx_cs.c:60-61), the brick detector this engine
+    // runs asks energy > threshold with autocorrelation >= 7/8 energy (cca.hpp:342): same scale (16 samples of x >> 2), so it is handed through.
+    sb200_cfg cfg; memset(&cfg, 0, sizeof cfg); cfg.cca_pwr_threshold = (uint32_t)thr;
+    if (sb200_create(d ? atoi(d) : 0, &cfg, &h) == SB200_OK) c->b200_engine = h;          // no CPU fallback: every later call fails without it
     c->b200_events = new Events();
 }
 extern "C" void BB11APrepareRx(PBB11A_RX_CONTEXT c, char* frame, unsigned int max) { c->ri_pbFrame = frame; c->ri_uiFrameMaxSize = max; }
@@ -57,7 +63,7 @@ extern "C" HRESULT BB11ARxCarrierSense(PBB11A_RX_CONTEXT c, PSORA_RADIO_RX_STREA
     if (!c->b200_engine || !c->b200_events) return BB11A_E_FORCE_STOP;
     if (c->ri_pbWorkIndicator && !*c->ri_pbWorkIndicator) return BB11A_E_FORCE_STOP;
     Events* E = (Events*)c->b200_events;
-    const bool inside = E->base && s->__pScanPt >= E->base && s->__pScanPt <= E->base + E->nblocks * SORA_RX_BLOCK_SIZE;
+    const bool inside = E->base && s->__pScanPt >= E->base && s->__pScanPt < E->base + E->nblocks * SORA_RX_BLOCK_SIZE;   // end exclusive: behind the decoded span, decode again
     if (!inside && !decode_from(c, s)) return BB11A_E_FORCE_STOP;
     const size_t pos_blk = (size_t)(s->__pScanPt - E->base) / SORA_RX_BLOCK_SIZE;
     const size_t max_blk = c->uiCSMaxFetchRxBlock ? c->uiCSMaxFetchRxBlock : 150;
@@ -119,6 +125,7 @@ bool decode11b_from(PBB11B_RX_CONTEXT c, PSORA_RADIO_RX_STREAM s) {
             skipped += res[i].rate_kbps == 1000 ? 352u : res[i].rate_kbps == 2000 ? 176u : res[i].rate_kbps == 5500 ? 64u : 32u;
         E->ev.push_back(std::move(e));
     }
+    if (n == MAX_EVENTS) { const size_t nb = ((size_t)res[n - 1].sample_index + 27u) / 28u; if (nb < E->nblocks) E->nblocks = nb; }   // as for 802.11a above
     return true;
 }
 }
@@ -129,6 +136,8 @@ extern "C" void BB11BRxSpdContextInit(PBB11B_RX_CONTEXT rx, PBB11B_SPD_CONTEXT s
     spd->b_minDescCount = nSpdMin; spd->b_maxDescCount = nSpdMax; spd->b_threshold = thr; spd->b_thresholdLH = thrLow; spd->b_thresholdHL = thrHigh;
     spd->b_workIndicator = work; spd->b200_rx = rx;
     const char* d = getenv("SB200_DEVICE"); sb200_handle* h = nullptr;
+    // nSPDThreshold is stored but not handed to the engine: the legacy software power detector compares it with a per-block energy in another
+    // scale (bbb_spd.c:204, demod11's default 4000) than TEnergyDetect's 8-vector average (cca.hpp:79, default 1000*1000), which is what runs here.
     if (sb200_create(d ? atoi(d) : 0, nullptr, &h) == SB200_OK) rx->b200_engine = h;    // no CPU fallback: every later call fails without it
     rx->b200_events = new Events11b();
 }
@@ -142,7 +151,7 @@ extern "C" HRESULT BB11BSpd(PBB11B_SPD_CONTEXT spd, PSORA_RADIO_RX_STREAM s) {
     if (!c || !c->b200_engine || !c->b200_events) return BB11B_E_FORCE_STOP;
     if (spd->b_workIndicator && !*spd->b_workIndicator) return BB11B_E_FORCE_STOP;
     Events11b* E = (Events11b*)c->b200_events;
-    const bool inside = E->base && s->__pScanPt >= E->base && s->__pScanPt <= E->base + E->nblocks * SORA_RX_BLOCK_SIZE;
+    const bool inside = E->base && s->__pScanPt >= E->base && s->__pScanPt < E->base + E->nblocks * SORA_RX_BLOCK_SIZE;
     if (!inside && !decode11b_from(c, s)) return BB11B_E_FORCE_STOP;
     const size_t pos_blk = (size_t)(s->__pScanPt - E->base) / SORA_RX_BLOCK_SIZE;
     const size_t max_blk = spd->b_maxDescCount ? spd->b_maxDescCount : 150;

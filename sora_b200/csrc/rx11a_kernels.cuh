@@ -77,7 +77,9 @@ __device__ __forceinline__ int cca_xcorr(const CcaState& s, const uint32_t* __re
 
 __global__ void __launch_bounds__(128) k_sync11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
                                                   const uint32_t* __restrict__ len, uint32_t nframes, uint32_t cca_thr,
-                                                  DevTables T, FrameInfo* __restrict__ info, const int2* __restrict__ dc_init) {
+                                                  DevTables T, FrameInfo* __restrict__ info, const int2* __restrict__ dc_init, uint32_t sh) {
+    // sh = 1: `iq` is the 40 Msps capture and TDownSample2 (samples.hpp:27-49) is the stride-2 gather below; sh = 0: the caller's samples were
+    // decimated on the way in (host-side gather of the even samples, sb200.cu), off[] then addresses that packed copy; len[] stays in 40 Msps samples
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const uint32_t* x = iq + off[f];
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(128) k_sync11a(const uint32_t* __restrict__ iq
         }
         cs16 p[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) p[k] = subw(unpack(__ldg(x + 8u * v + 2u * k)), mk(dc_re, dc_im));   // dc.hpp:48-85
+        for (int k = 0; k < 4; k++) p[k] = subw(unpack(__ldg(x + ((4u * v + (uint32_t)k) << sh))), mk(dc_re, dc_im));   // dc.hpp:48-85
         if (s.sync_state == 0) {                       // cca.hpp:326-398
             int sr = 0, si = 0, se = 0; uint32_t pk[4];
             const int oldest = s.his_idx;
@@ -257,7 +259,7 @@ __device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 
 // is serial across symbols, and there every lane owns two subcarriers.
 __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
         const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, FrameInfo* __restrict__ info,
-        uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps) {
+        uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps, uint32_t sh) {
     __shared__ uint32_t s_fft[SB_FRONT_WARPS][2][64];
     __shared__ __align__(16) uint8_t s_soft[SB_FRONT_WARPS][288];
     __shared__ uint32_t s_demap[256];                  // per input value: [bpsk/qpsk/first bit | 16-QAM second | 64-QAM second | 64-QAM third] soft bits
@@ -300,8 +302,8 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a
     };
     // ---- T11aLTS (channel_11a.hpp:34-230) -----------------------------------------------------------
     {   // FreqOffsetEstimate<16> (dspalg.hpp:227-243): sum over the 64 samples of (LTS2 * conj(LTS1 >> 1)) >> 5
-        cs16 l0 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b0))), 1), l1 = sra(unpack(__ldg(x + 2u * (s0 + 8u + b1))), 1);
-        cs16 h0 = unpack(__ldg(x + 2u * (s0 + 72u + b0))), h1 = unpack(__ldg(x + 2u * (s0 + 72u + b1)));
+        cs16 l0 = sra(unpack(__ldg(x + ((s0 + 8u + b0) << sh))), 1), l1 = sra(unpack(__ldg(x + ((s0 + 8u + b1) << sh))), 1);
+        cs16 h0 = unpack(__ldg(x + ((s0 + 72u + b0) << sh))), h1 = unpack(__ldg(x + ((s0 + 72u + b1) << sh)));
         int re0, im0, re1, im1; cmul_conj32(re0, im0, h0, l0); cmul_conj32(re1, im1, h1, l1);
         int sr = wadd(re0 >> 5, re1 >> 5), si = wadd(im0 >> 5, im1 >> 5);
         for (int o = 16; o; o >>= 1) { sr = wadd(sr, __shfl_xor_sync(FULL, sr, o)); si = wadd(si, __shfl_xor_sync(FULL, si, o)); }
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a
     for (int j = 0; j < 4; j++) fcv[j] = d_rot(T, fi.cfo_est * (hl + 16 * j));
     auto load4 = [&](uint32_t first, cs16 (&v)[4]) {    // (x >> 1) * FreqCoeffs for samples first + hl + 16 j
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = cmul_q15(sra(unpack(__ldg(x + 2u * (first + hl + 16u * j))), 1), fcv[j]);
+        for (int j = 0; j < 4; j++) v[j] = cmul_q15(sra(unpack(__ldg(x + ((first + hl + 16u * j) << sh))), 1), fcv[j]);
     };
     {   cs16 v[4]; load4(s0 + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]); }     // both halves transform LTS1 (same data)
     cs16 ch0, ch1;
@@ -465,13 +467,13 @@ __host__ __device__ inline uint32_t resampled_len_40(uint32_t len44) {      // w
 __global__ void __launch_bounds__(256) k_resample_44_40(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
                                                         uint32_t nframes, uint32_t* __restrict__ out, uint64_t out_stride /*samples per slot*/,
                                                         uint64_t* __restrict__ off40, uint32_t* __restrict__ len40) {
-    const uint32_t f = blockIdx.y;
+    const uint32_t f = blockIdx.x;                      // slots on x (2^31 - 1 blocks), sample tiles on y
     if (f >= nframes) return;
     const uint32_t n40 = resampled_len_40(len[f]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { off40[f] = (uint64_t)f * out_stride; len40[f] = n40; }
+    if (blockIdx.y == 0 && threadIdx.x == 0) { off40[f] = (uint64_t)f * out_stride; len40[f] = n40; }
     const uint32_t* x = iq + off[f];
     uint32_t* y = out + (size_t)f * out_stride;
-    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n40; m += gridDim.x * blockDim.x) {
+    for (uint32_t m = blockIdx.y * blockDim.x + threadIdx.x; m < n40; m += gridDim.y * blockDim.x) {
         const uint32_t k = m / 10u, r = m - 10u * k;
         if (r == 0) { y[m] = __ldg(x + 11u * k); continue; }
         const int R = r == 1 ? 115 : r == 2 ? 102 : r == 3 ? 90 : r == 4 ? 77 : r == 5 ? 64 : r == 6 ? 51 : r == 7 ? 38 : r == 8 ? 26 : 13;

@@ -13,6 +13,11 @@
 #include <string.h>
 #include <new>
 #include <stdio.h>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
+#include <emmintrin.h>
 
 using namespace sb;
 
@@ -45,6 +50,15 @@ __global__ void k_pack_results(const FrameInfo* __restrict__ info, const uint32_
     res[i] = r;
 }
 
+// max(len) and an out-of-bounds flag over a device-resident slot table: res[0] = max frame_len, res[1] != 0 if any slot leaves [0, iq_total)
+__global__ void k_slot_check(const uint64_t* __restrict__ off, const uint32_t* __restrict__ len, uint32_t n, uint64_t iq_total, uint32_t* __restrict__ res) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t l = 0, bad = 0;
+    if (i < n) { l = len[i]; const uint64_t o = off[i]; bad = (l > iq_total || o > iq_total - l) ? 1u : 0u; }
+    l = __reduce_max_sync(0xFFFFFFFFu, l); bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+    if ((threadIdx.x & 31) == 0) { if (l) atomicMax(res, l); if (bad) atomicOr(res + 1, 1u); }
+}
+
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -52,6 +66,55 @@ bool is_device_ptr(const void* p) {
 }
 
 } // namespace
+
+// ---- host-side TDownSample2 for host-resident captures ---------------------------------------------------------------------------------
+// The 802.11a graph keeps samples 0 and 2 of every 4 (samples.hpp:27-49): half of a 40 Msps capture is dropped on arrival.  With the option
+// "host_decimate" = T > 0 the chunked host-IQ path gathers the even samples of every slot of a chunk into pinned staging memory with T host
+// threads and sends only those over PCIe (half the bytes); the kernels then read the packed copy with stride 1 (sh = 0).  Results are
+// identical: the same samples reach the same arithmetic.
+static void decimate_slot(const uint32_t* __restrict__ src, uint32_t n2, uint32_t* __restrict__ dst) {     // dst[j] = src[2 j], j < n2
+    uint32_t j = 0;
+    for (; j + 4 <= n2; j += 4) {
+        const __m128 a = _mm_loadu_ps((const float*)(src + 2 * j)), b = _mm_loadu_ps((const float*)(src + 2 * j + 4));
+        _mm_storeu_ps((float*)(dst + j), _mm_shuffle_ps(a, b, 0x88));
+    }
+    for (; j < n2; j++) dst[j] = src[2 * j];
+}
+struct DecimPool {
+    struct Job { const uint32_t* iq; const uint64_t* off; const uint32_t* len; const uint64_t* doff; uint32_t f0, f1; uint32_t* dst; };
+    std::vector<std::thread> th; std::mutex m; std::condition_variable cv, cv_done;
+    Job job{}; uint64_t gen = 0; int pending = 0; bool stop = false; int n = 0;
+    static void part(const Job& j, int w, int n) {
+        const uint64_t cnt = j.f1 - j.f0; const uint32_t a = j.f0 + (uint32_t)(cnt * w / n), b = j.f0 + (uint32_t)(cnt * (w + 1) / n);
+        for (uint32_t f = a; f < b; f++) decimate_slot(j.iq + j.off[f], (j.len[f] + 1u) / 2u, j.dst + (j.doff[f] - j.doff[j.f0]));
+    }
+    void start(int nthreads) {                          // nthreads includes the calling thread
+        shutdown(); n = nthreads < 1 ? 1 : nthreads; stop = false;
+        for (int w = 1; w < n; w++) th.emplace_back([this, w]() {
+            uint64_t seen = 0;
+            for (;;) {
+                Job j;
+                { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; j = job; }
+                part(j, w, n);
+                { std::lock_guard<std::mutex> l(m); if (--pending == 0) cv_done.notify_one(); }
+            }
+        });
+    }
+    void run(const Job& j) {
+        if (n <= 1) { part(j, 0, 1); return; }
+        { std::lock_guard<std::mutex> l(m); job = j; gen++; pending = n - 1; }
+        cv.notify_all();
+        part(j, 0, n);
+        std::unique_lock<std::mutex> l(m); cv_done.wait(l, [&] { return pending == 0; });
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear(); n = 0;
+    }
+    ~DecimPool() { shutdown(); }
+};
 
 struct sb200_handle {
     int device = 0;
@@ -72,7 +135,12 @@ struct sb200_handle {
     DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx, tabtx11n, txout1; DevTablesTx11n XN{};   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
-    const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0;
+    const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0; bool tab_host = false;
+    uint32_t host_decimate = 0;                        // option: host threads gathering the even samples of host-resident 40 Msps captures (0 = off)
+    DecimPool* pool = nullptr; void* hstage[3] = {nullptr, nullptr, nullptr}; size_t hstage_cap = 0; cudaEvent_t ev_hfree[3] = {nullptr, nullptr, nullptr};
+    DevBuf doff; std::vector<uint64_t> doffh;
+    bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
+    DevBuf slotchk;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
     bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
     bool use_v2 = false;                               // SB200_VITERBI=v2 selects the per-step-mark quad kernel (A/B against the history-carrying one)
@@ -154,7 +222,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
-                     &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4], &h->vlist, &h->vcnt};
+                     &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4], &h->vlist, &h->vcnt, &h->slotchk, &h->doff};
     for (DevBuf* b : all) b->release();
     h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -162,6 +230,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     for (int i = 0; i < 2; i++) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); h->stage[i].release(); }
+    delete h->pool; for (int i = 0; i < 3; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); if (h->ev_hfree[i]) cudaEventDestroy(h->ev_hfree[i]); }
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_front) cudaStreamDestroy(h->s_front);
     delete h;
@@ -183,20 +252,67 @@ extern "C" int sb200_last_kernel_times(sb200_handle* h, float* ms4) {
     return SB200_OK;
 }
 
+// Slot table of a call: bounds-checks every slot against iq_total and returns the largest slot length (workspaces are sized from it).
+//   host tables   : checked on the host, copied to the device.
+//   device tables : checked on the device (k_slot_check, one 8-byte read-back) on EVERY call; with `need_host_copy` the table is also copied back
+//                   (the chunked host-IQ path stages sample ranges per chunk).  Only after set_option("slot_table_immutable", 1) — the caller's
+//                   promise not to rewrite a device-resident table between calls — is the result cached by (pointers, count, total).
+static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t* frame_len, uint32_t nframes, uint64_t iq_total, bool need_host_copy,
+                      cudaStream_t st, const uint64_t** d_off, const uint32_t** d_len, uint32_t* max_len, bool* host_valid) {
+    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len);
+    std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
+    *host_valid = false;
+    if (off_dev && len_dev) {
+        const bool cached = h->tab_immutable && h->tab_off == frame_off && h->tab_len == frame_len && h->tab_n == nframes && h->tab_total == iq_total && (!need_host_copy || h->tab_host);
+        if (!cached) {
+            CK(h->slotchk.need(8));
+            CK(cudaMemsetAsync(h->slotchk.p, 0, 8, st));
+            k_slot_check<<<(nframes + 255) / 256, 256, 0, st>>>(frame_off, frame_len, nframes, iq_total, (uint32_t*)h->slotchk.p);
+            uint32_t r[2] = {0, 0};
+            CK(cudaMemcpyAsync(r, h->slotchk.p, 8, cudaMemcpyDeviceToHost, st));
+            if (need_host_copy) {
+                offh.resize(nframes); lenh.resize(nframes);
+                CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaStreamSynchronize(st));
+            h->tab_off = nullptr;
+            if (r[1]) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+            h->tab_max_len = r[0]; h->tab_host = need_host_copy;
+            if (h->tab_immutable) { h->tab_off = frame_off; h->tab_len = frame_len; h->tab_n = nframes; h->tab_total = iq_total; }
+        }
+        *d_off = frame_off; *d_len = frame_len; *max_len = h->tab_max_len; *host_valid = h->tab_host && (cached || need_host_copy);
+        return SB200_OK;
+    }
+    h->tab_off = nullptr;
+    offh.resize(nframes); lenh.resize(nframes);
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if (lenh[i] > iq_total || offh[i] > iq_total - lenh[i]) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+        if (lenh[i] > mx) mx = lenh[i];
+    }
+    if (off_dev) *d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); *d_off = (const uint64_t*)h->off.p; }
+    if (len_dev) *d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); *d_len = (const uint32_t*)h->len.p; }
+    *max_len = mx; *host_valid = true;
+    return SB200_OK;
+}
+
 // Launch the decode kernels for frames [f0, f1) of a call.  `iq_base + off[f]` must address slot f.
 // sync + front end go to `sf`, the Viterbi launches to `sv` (sv waits for `front_done` when the streams differ).
 static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t f0, uint32_t f1,
-                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr, uint32_t chunk_idx = 0) {
+                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr, uint32_t chunk_idx = 0, uint32_t sh = 1) {
     const uint32_t n = f1 - f0;
     FrameInfo* d_info = (FrameInfo*)h->info.p + f0;
     uint8_t* d_soft = (uint8_t*)h->soft.p + (size_t)f0 * soft_stride;
     uint8_t* d_out = (uint8_t*)h->out.p + (size_t)f0 * row;
     uint32_t* d_status = (uint32_t*)h->status.p + f0; uint32_t* d_crc = (uint32_t*)h->crc.p + f0;
     if (timed) CK(cudaEventRecord(h->evk[0], sf));
-    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info, dc_init ? dc_init + f0 : nullptr);
+    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info, dc_init ? dc_init + f0 : nullptr, sh);
     if (timed) CK(cudaEventRecord(h->evk[1], sf));
     k_front11a<<<(n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info,
-            d_soft, soft_stride, h->inv_deint, taps);
+            d_soft, soft_stride, h->inv_deint, taps, sh);
     if (timed) CK(cudaEventRecord(h->evk[2], sf));
     if (sv != sf) { CK(cudaEventRecord(front_done, sf)); CK(cudaStreamWaitEvent(sv, front_done, 0)); }
     VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
@@ -230,32 +346,19 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
 // The front end is latency bound and the Viterbi integer-issue bound, so they overlap well on the same SMs.
 static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
                      uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, cudaStream_t st,
-                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride, const int2* dc_init = nullptr) {
+                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride, const int2* dc_init = nullptr, bool no_chunk = false) {
     if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
     if (nframes == 0) return SB200_OK;
     CK(cudaSetDevice(h->device));
-    // slot table (host copy needed for sizing; a device-resident table is copied back once per distinct table)
-    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len);
-    std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
-    const bool cached = off_dev && len_dev && h->tab_off == frame_off && h->tab_len == frame_len && h->tab_n == nframes && h->tab_total == iq_total;
-    if (!cached) {
-        offh.resize(nframes); lenh.resize(nframes);
-        if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
-        if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
-        if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
-        h->tab_max_len = 0;
-        for (uint32_t i = 0; i < nframes; i++) {
-            if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
-            if (lenh[i] > h->tab_max_len) h->tab_max_len = lenh[i];
-        }
-        // a device-resident slot table is assumed immutable between calls that pass the same pointers (documented in the header)
-        if (off_dev && len_dev) { h->tab_off = frame_off; h->tab_len = frame_len; h->tab_n = nframes; h->tab_total = iq_total; } else h->tab_off = nullptr;
-    }
-    const uint32_t max_len = h->tab_max_len;
+    // slot table: checked on every call (slot_table above); the chunked host-IQ path also needs it on the host
     const bool iq_dev = is_device_ptr(iq);
-    const uint64_t* d_off; const uint32_t* d_len;
-    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
-    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
+    std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
+    const uint64_t* d_off; const uint32_t* d_len; uint32_t max_len = 0; bool tab_on_host = false;
+    {
+        const bool may_chunk = !no_chunk && !iq_dev && h->chunk_frames != 0 && nframes > h->chunk_frames;
+        int rc = slot_table(h, frame_off, frame_len, nframes, iq_total, may_chunk, st, &d_off, &d_len, &max_len, &tab_on_host);
+        if (rc != SB200_OK) return rc;
+    }
     // workspaces
     const uint64_t max_sym = (max_len / 2u) / 80u + 1u;
     const uint64_t soft_stride = ((max_sym * 288ull) + 15ull) & ~15ull;
@@ -268,8 +371,8 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     const bool tapping = taps.freq_coeffs || taps.fft_out || soft_host || dc_init;
     // device-resident IQ gains nothing from chunking (a chunk's Viterbi grid no longer fills 148 SMs x 5 CTAs); host IQ does:
     // the PCIe copy of chunk k+1 hides behind the kernels of chunk k.  chunk_frames_device lets a caller force it anyway.
-    const uint32_t want = iq_dev ? h->chunk_frames_device : h->chunk_frames;
-    const uint32_t chunk = (want == 0 || tapping || nframes <= want) ? nframes : want;
+    const uint32_t want = no_chunk ? 0u : iq_dev ? h->chunk_frames_device : h->chunk_frames;
+    const uint32_t chunk = (want == 0 || tapping || nframes <= want || (!iq_dev && !tab_on_host)) ? nframes : want;
     const bool pipelined = chunk < nframes;
     CK(h->vcnt.need(16ull * ((nframes + chunk - 1) / chunk)));
     const bool res_dev_all = is_device_ptr(res), out_dev_all = out_bytes && is_device_ptr(out_bytes);
@@ -283,15 +386,36 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         if (rc != SB200_OK) return rc;
         h->nk = 4;
     } else {
-        // host IQ: per-chunk sample range [lo, hi) staged through two device buffers
+        // host IQ: per-chunk sample range [lo, hi) staged through two device buffers; with host_decimate only the even samples of every slot
+        // travel, gathered by the host threads into one of three pinned buffers while earlier chunks are on the wire / in the kernels
+        const bool dec = !iq_dev && h->host_decimate > 0;
+        const uint64_t* d_off_k = d_off; std::vector<uint64_t>& doffh = h->doffh;
         uint64_t stage_samples = 0;
         if (!iq_dev) {
+            if (dec) {
+                doffh.resize((size_t)nframes + 1); doffh[0] = 0;
+                for (uint32_t i = 0; i < nframes; i++) doffh[i + 1] = doffh[i] + (lenh[i] + 1u) / 2u;
+            }
             for (uint32_t f0 = 0; f0 < nframes; f0 += chunk) {
                 uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; uint64_t lo = ~0ull, hi = 0;
-                for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
+                if (dec) { lo = doffh[f0]; hi = doffh[f1]; }
+                else for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
                 if (hi - lo > stage_samples) stage_samples = hi - lo;
             }
             CK(h->stage[0].need(stage_samples * 4ull + 16)); CK(h->stage[1].need(stage_samples * 4ull + 16));
+            if (dec) {
+                if (!h->pool || h->pool->n != (int)h->host_decimate) { delete h->pool; h->pool = new (std::nothrow) DecimPool(); if (!h->pool) return h->fail(SB200_E_NOMEM, "host thread pool"); h->pool->start((int)h->host_decimate); }
+                if (h->hstage_cap < stage_samples * 4ull) {
+                    for (int i = 0; i < 3; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); h->hstage[i] = nullptr; }
+                    h->hstage_cap = 0;
+                    const size_t want_b = stage_samples * 4ull + stage_samples / 2 + 256;
+                    for (int i = 0; i < 3; i++) CK(cudaHostAlloc(&h->hstage[i], want_b, cudaHostAllocDefault));
+                    h->hstage_cap = want_b;
+                }
+                for (int i = 0; i < 3; i++) if (!h->ev_hfree[i]) CK(cudaEventCreateWithFlags(&h->ev_hfree[i], cudaEventDisableTiming));
+                CK(h->doff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->doff.p, doffh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st));
+                d_off_k = (const uint64_t*)h->doff.p;
+            }
         }
         CK(cudaEventRecord(h->ev_start, st));
         CK(cudaStreamWaitEvent(h->s_copy, h->ev_start, 0)); CK(cudaStreamWaitEvent(h->s_front, h->ev_start, 0));
@@ -299,7 +423,18 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         for (uint32_t f0 = 0; f0 < nframes; f0 += chunk, k++) {
             const uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; const int b = k & 1;
             const uint32_t* base = (const uint32_t*)iq;
-            if (!iq_dev) {
+            if (dec) {
+                const int hb = (int)(k % 3u);
+                if (k >= 3) CK(cudaEventSynchronize(h->ev_hfree[hb]));                      // pinned buffer hb is free once chunk k-3 has crossed the link
+                DecimPool::Job j{(const uint32_t*)iq, offh.data(), lenh.data(), doffh.data(), f0, f1, (uint32_t*)h->hstage[hb]};
+                h->pool->run(j);
+                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));
+                CK(cudaMemcpyAsync(h->stage[b].p, h->hstage[hb], (doffh[f1] - doffh[f0]) * 4ull, cudaMemcpyHostToDevice, h->s_copy));
+                CK(cudaEventRecord(h->ev_hfree[hb], h->s_copy));
+                CK(cudaEventRecord(h->ev_h2d[b], h->s_copy));
+                CK(cudaStreamWaitEvent(h->s_front, h->ev_h2d[b], 0));
+                base = (const uint32_t*)h->stage[b].p - doffh[f0];
+            } else if (!iq_dev) {
                 uint64_t lo = ~0ull, hi = 0;
                 for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
                 if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));        // buffer b free once chunk k-2's front end has read it
@@ -308,7 +443,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
                 CK(cudaStreamWaitEvent(h->s_front, h->ev_h2d[b], 0));
                 base = (const uint32_t*)h->stage[b].p - lo;
             }
-            int rc = launch_chunk(h, base, d_off, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false, nullptr, k);
+            int rc = launch_chunk(h, base, d_off_k, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false, nullptr, k, dec ? 0u : 1u);
             if (rc != SB200_OK) return rc;
             // results of this chunk go back while the next chunks are still coming in (PCIe is full duplex): only the last chunk's
             // device-to-host copy is left exposed at the end of the call
@@ -370,7 +505,6 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
     std::vector<uint32_t> active(nstreams); for (uint32_t s = 0; s < nstreams; s++) active[s] = s;
     std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<int2> dcv; std::vector<sb200_frame_result> r; std::vector<FrameInfo> fi; std::vector<uint8_t> bytes;
     const uint32_t row = out_bytes ? (out_stride < 2560u ? out_stride : 2560u) : 0u;
-    const uint32_t saved_chunk = h->chunk_frames_device; h->chunk_frames_device = 0;
     int rc = SB200_OK;
     while (!active.empty()) {
         std::vector<uint32_t> live;
@@ -380,8 +514,8 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
         off.resize(n); len.resize(n); dcv.resize(n); r.resize(n); fi.resize(n); if (row) bytes.resize((size_t)n * row);
         for (uint32_t j = 0; j < n; j++) { const uint32_t s = live[j]; off[j] = stream_off[s] + pos[s]; len[j] = (uint32_t)(stream_len[s] - pos[s]); dcv[j] = dc[s]; }
         CK(h->dcbuf.need(n * sizeof(int2))); CK(cudaMemcpyAsync(h->dcbuf.p, dcv.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
-        FrontTaps taps{}; h->tab_off = nullptr;
-        rc = rx11a_run(h, d_iq, iq_total, off.data(), len.data(), n, row ? bytes.data() : nullptr, row, r.data(), st, taps, nullptr, 0, (const int2*)h->dcbuf.p);
+        FrontTaps taps{};
+        rc = rx11a_run(h, d_iq, iq_total, off.data(), len.data(), n, row ? bytes.data() : nullptr, row, r.data(), st, taps, nullptr, 0, (const int2*)h->dcbuf.p, true);
         if (rc != SB200_OK) break;
         CK(cudaMemcpy(fi.data(), h->info.p, n * sizeof(FrameInfo), cudaMemcpyDeviceToHost));
         active.clear();
@@ -401,7 +535,6 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
             active.push_back(s);
         }
     }
-    h->chunk_frames_device = saved_chunk;
     return rc;
 }
 
@@ -434,7 +567,7 @@ extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t
     if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
     uint32_t max40 = 28;
     for (uint32_t i = 0; i < nframes; i++) {
-        if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
+        if (lenh[i] > iq_total || offh[i] > iq_total - lenh[i]) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
         const uint32_t n40 = resampled_len_40(lenh[i]); if (n40 > max40) max40 = n40;
     }
     const uint64_t stride40 = ((uint64_t)max40 + 3ull) & ~3ull;
@@ -443,11 +576,10 @@ extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t
     if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
     if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
     CK(h->iq40.need(nframes * stride40 * 4ull)); CK(h->off40.need(nframes * 8ull)); CK(h->len40.need(nframes * 4ull));
-    dim3 grid((unsigned)((max40 + 255) / 256 > 64 ? 64 : (max40 + 255) / 256), nframes);
+    dim3 grid(nframes, (unsigned)((max40 + 255) / 256 > 64 ? 64 : (max40 + 255) / 256));   // slots on x: the y extent stops at 65535
     k_resample_44_40<<<grid, 256, 0, st>>>(d_iq, d_off, d_len, nframes, (uint32_t*)h->iq40.p, stride40, (uint64_t*)h->off40.p, (uint32_t*)h->len40.p);
     h->launches += 1;
     CK(cudaGetLastError());
-    h->tab_off = nullptr;                                  // the resampled slot table changes with every call: no caching
     return sb200_rx11a_batch(h, (const int16_t*)h->iq40.p, nframes * stride40, (const uint64_t*)h->off40.p, (const uint32_t*)h->len40.p, nframes,
                              out_bytes, out_stride, res, cuda_stream);
 }
@@ -460,14 +592,10 @@ static int rx11b_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     if (nframes == 0) return SB200_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CK(cudaSetDevice(h->device));
-    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len), iq_dev = is_device_ptr(iq);
-    if (!off_dev || !len_dev || !iq_dev) {              // bounds are checked on the host copy of the slot table when there is one
-        if (!off_dev && !len_dev) for (uint32_t i = 0; i < nframes; i++) if (frame_off[i] + frame_len[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
-    }
-    const uint32_t* d_iq; const uint64_t* d_off; const uint32_t* d_len;
+    const bool iq_dev = is_device_ptr(iq);
+    const uint32_t* d_iq; const uint64_t* d_off; const uint32_t* d_len; uint32_t max_len = 0; bool tab_on_host = false;
+    { int rc = slot_table(h, frame_off, frame_len, nframes, iq_total, false, st, &d_off, &d_len, &max_len, &tab_on_host); if (rc != SB200_OK) return rc; }
     if (iq_dev) d_iq = (const uint32_t*)iq; else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
-    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, frame_off, nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
-    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, frame_len, nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
     const uint64_t row = 4096; const size_t nres = (size_t)nframes * max_frames;
     CK(h->out.need(nres * row)); CK(h->res.need(nres * sizeof(Result11b)));
     const bool res_dev = is_device_ptr(res);
@@ -550,32 +678,18 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
     if (nframes == 0) return SB200_OK;
     CK(cudaSetDevice(h->device));
     int rc = upload_tables11n(h); if (rc != SB200_OK) return rc;
-    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len), iq_dev = is_device_ptr(iq0);
+    const bool iq_dev = is_device_ptr(iq0);
     if (iq_dev != is_device_ptr(iq1)) return h->fail(SB200_E_INVALID, "both antenna buffers must live on the same side");
-    std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
-    const bool cached = off_dev && len_dev && h->tab_off == frame_off && h->tab_len == frame_len && h->tab_n == nframes && h->tab_total == iq_total;
-    if (!cached) {
-        offh.resize(nframes); lenh.resize(nframes);
-        if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
-        if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
-        if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
-        h->tab_max_len = 0;
-        for (uint32_t i = 0; i < nframes; i++) {
-            if (offh[i] + lenh[i] > iq_total) return h->fail(SB200_E_INVALID, "slot exceeds iq_total_samples");
-            if (lenh[i] > h->tab_max_len) h->tab_max_len = lenh[i];
-        }
-        if (off_dev && len_dev) { h->tab_off = frame_off; h->tab_len = frame_len; h->tab_n = nframes; h->tab_total = iq_total; } else h->tab_off = nullptr;
-    }
-    const uint32_t* d_iq0; const uint32_t* d_iq1; const uint64_t* d_off; const uint32_t* d_len;
+    const uint64_t* d_off; const uint32_t* d_len; uint32_t max_len = 0; bool tab_on_host = false;
+    { int rc = slot_table(h, frame_off, frame_len, nframes, iq_total, false, st, &d_off, &d_len, &max_len, &tab_on_host); if (rc != SB200_OK) return rc; }
+    const uint32_t* d_iq0; const uint32_t* d_iq1;
     if (iq_dev) { d_iq0 = (const uint32_t*)iq0; d_iq1 = (const uint32_t*)iq1; }
     else {
         CK(h->iq.need(iq_total * 4ull)); CK(h->iq1.need(iq_total * 4ull));
         CK(cudaMemcpyAsync(h->iq.p, iq0, iq_total * 4ull, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->iq1.p, iq1, iq_total * 4ull, cudaMemcpyHostToDevice, st));
         d_iq0 = (const uint32_t*)h->iq.p; d_iq1 = (const uint32_t*)h->iq1.p;
     }
-    if (off_dev) d_off = frame_off; else { CK(h->off.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->off.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->off.p; }
-    if (len_dev) d_len = frame_len; else { CK(h->len.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->len.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->len.p; }
-    const uint64_t max_sym = (h->tab_max_len / 2u) / 80u + 1u;
+    const uint64_t max_sym = (max_len / 2u) / 80u + 1u;
     const uint64_t soft_stride = ((max_sym * 208ull) + 15ull) & ~15ull;
     const uint64_t row = 1536;                         // >= 1500 (MTU, PHY_11n.hpp:478,505)
     CK(h->info.need(nframes * sizeof(FrameInfo))); CK(h->soft.need(nframes * soft_stride)); CK(h->out.need(nframes * row));
@@ -1047,6 +1161,8 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "chunk_frames")) { h->chunk_frames = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "chunk_frames_device")) { h->chunk_frames_device = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "vq_pad_smem")) { h->vq_pad_smem = (uint32_t)value; return SB200_OK; }
+    if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
+    if (!strcmp(name, "slot_table_immutable")) { h->tab_immutable = value != 0; h->tab_off = nullptr; return SB200_OK; }
     return h->fail(SB200_E_INVALID, "unknown option");
 }
 

@@ -48,6 +48,15 @@ def rx11a_batch(iq, off, length, out_stride=2048, nthreads=1):
     lib().sbo_rx11a_batch(_p(iq), _p(off), _p(length), C.c_uint32(nf), _p(res), _p(out), C.c_uint64(out_stride), C.c_int(nthreads))
     return res, out
 
+def rx11a_batch_2t(iq, off, length, out_stride=2048, npipes=1):
+    """The same batch through the reference's two-thread topology (front end | Viterbi thread per pipeline), npipes pipelines."""
+    iq = np.ascontiguousarray(iq, dtype=np.int16)
+    off = np.ascontiguousarray(off, dtype=np.uint64); length = np.ascontiguousarray(length, dtype=np.uint32)
+    nf = len(off)
+    res = np.zeros(nf, dtype=RES_DTYPE); out = np.zeros((nf, out_stride), dtype=np.uint8)
+    lib().sbo_rx11a_batch_2t(_p(iq), _p(off), _p(length), C.c_uint32(nf), _p(res), _p(out), C.c_uint64(out_stride), C.c_int(npipes))
+    return res, out
+
 def rx11a_taps(iq, max_sym=600):
     iq = np.ascontiguousarray(iq, dtype=np.int16)
     res = np.zeros(1, dtype=RES_DTYPE)

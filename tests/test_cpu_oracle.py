@@ -79,6 +79,22 @@ def test_roundtrip_all_rates(rate):
     assert (res["status"] == 1).all() and (res["rate_kbps"] == rate).all() and (res["length"] == 211).all()
     assert (out[:, :211] == ps).all()
 
+def test_two_thread_topology_gives_the_same_results():
+    """The CPU baseline's variant (ii) — front end and Viterbi on two threads joined by a ring like TThreadSeparator — is the same decoder."""
+    parts = []
+    for rate in (6000, 36000, 54000):
+        iq, _ = synth.make_frames(3, psdu_len=300, rate_kbps=rate, snr_db=12 if rate == 36000 else 28, seed0=rate + 9)
+        parts.append(iq)
+    slot = max(p.shape[1] for p in parts); F = 9
+    iq = np.zeros((F, slot, 2), np.int16)
+    for i, p in enumerate(parts): iq[3 * i: 3 * i + 3, :p.shape[1]] = p
+    flat = iq.reshape(-1, 2).copy(); flat[5 * slot + 700: 5 * slot + 760] = 0          # damage one SIGNAL/early symbol region
+    off = np.arange(F) * slot; ln = np.full(F, slot); ln[7] = 2000                      # and truncate one slot
+    r1, o1 = oracle_py.rx11a_batch(flat, off, ln)
+    for npipes in (1, 3):
+        r2, o2 = oracle_py.rx11a_batch_2t(flat, off, ln, npipes=npipes)
+        assert (r1 == r2).all() and (o1 == o2).all()
+
 def test_stream_mode_multiple_frames():
     """RxThread semantics: several frames in one capture are found one after another (fb11a_demod.cpp:29-81)."""
     iq, ps = synth.make_frames(4, psdu_len=150, rate_kbps=24000, snr_db=30, lead=400, trail=300)

@@ -145,16 +145,26 @@ def test_chunked_pipeline_host_and_device(eng):
     try:
         res, out = eng.rx11a_batch(flat, off, ln)                      # host IQ: staged through the double buffer
         assert (res == ref).all() and (out == refo).all()
+        for nthreads in (1, 3):                                        # host-side TDownSample2: only the even samples cross PCIe
+            eng.set_option("host_decimate", nthreads)
+            res, out = eng.rx11a_batch(flat, off, ln)
+            assert (res == ref).all() and (out == refo).all()
+            lo = ln.copy(); lo[::2] -= 29; lo[1] = 27; lo[3] = 700     # ragged (odd) slot lengths, a slot shorter than one block, a truncated one
+            r1, o1 = eng.rx11a_batch(flat, off, lo)
+            eng.set_option("host_decimate", 0); r0, o0 = eng.rx11a_batch(flat, off, lo); eng.set_option("host_decimate", nthreads)
+            assert (r1 == r0).all() and (o1 == o0).all()
+        eng.set_option("host_decimate", 0)
         dev = torch.device("cuda", 0)
         t_iq = torch.from_numpy(flat).to(dev); t_off = torch.from_numpy(off.astype(np.int64)).to(dev); t_len = torch.from_numpy(ln.astype(np.int32)).to(dev)
         t_out = torch.zeros((11, 256), dtype=torch.uint8, device=dev); t_res = torch.zeros((11, 7), dtype=torch.int32, device=dev)
+        eng.set_option("slot_table_immutable", 1)
         for _ in range(2):                                             # second call hits the cached slot table
             eng.rx11a_raw(t_iq.data_ptr(), flat.shape[0], t_off.data_ptr(), t_len.data_ptr(), 11, t_out.data_ptr(), 256, t_res.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert (t_res.cpu().numpy().view(api.RESULT_DTYPE).reshape(-1) == ref).all()
         assert (t_out.cpu().numpy()[:, :180] == ps).all()
     finally:
-        eng.set_option("chunk_frames", 8192); eng.set_option("chunk_frames_device", 0)
+        eng.set_option("chunk_frames", 4096); eng.set_option("chunk_frames_device", 0); eng.set_option("slot_table_immutable", 0); eng.set_option("host_decimate", 0)
 
 def test_44msps_capture(eng):
     """sb200_rx11a_batch_ex(sample_rate_mhz=44): on-device 11:10 resampler + the 40 Msps chain == oracle doing the same."""
@@ -252,7 +262,9 @@ def test_legacy_c_api_shim():
     parts[1] = parts[1].copy(); parts[1][3000:3200] = 0
     cap = np.concatenate(parts); cap = cap[: len(cap) // 28 * 28]
     blocks = np.zeros((len(cap) // 28, 128), np.uint8); blocks[:, 0] = 1; blocks[:, 16:] = cap.reshape(-1, 28 * 2).view(np.uint8)
-    ores, oout = oracle_py.rx11a_run(cap, max_frames=8, out_stride=2560)
+    oracle_py.lib().sbo_set_cca_threshold(C.c_uint32(250000))             # rxThreshold reaches the carrier sense of the engine: same value in the oracle
+    try: ores, oout = oracle_py.rx11a_run(cap, max_frames=8, out_stride=2560)
+    finally: oracle_py.lib().sbo_set_cca_threshold(C.c_uint32(0))
     work = C.c_uint32(1); frame = np.zeros(4096, np.uint8)
     st = Stream(); ctx = Ctx()
     lib.SoraGenRadioRxStreamOffline(C.byref(st), C.c_void_p(blocks.ctypes.data), C.c_uint32(blocks.size))
@@ -272,6 +284,66 @@ def test_legacy_c_api_shim():
         assert hr == codes[int(o["status"])] and n == o["length"] and rate == o["rate_kbps"]
         if o["status"] in (1, oracle_py.E_CRC32_FAIL): assert (by == ob[:n]).all()
     assert got[0][0] == 0x202 and got[1][0] == 0x80006004 and got[2][0] == 0x202
+
+def test_device_slot_table_is_checked_every_call(eng):
+    """A device-resident slot table rewritten in place between two calls (same pointers): the second call sees the new table — a slot that
+    now leaves the buffer is refused, a longer valid slot gets workspaces of its own size (no stale cached max length)."""
+    import torch
+    iq, ps = synth.make_frames(3, psdu_len=90, rate_kbps=12000, snr_db=30, seed0=0xD0)
+    big, psb = synth.make_frames(1, psdu_len=1400, rate_kbps=12000, snr_db=30, seed0=0xD1)
+    flat = np.concatenate([iq.reshape(-1, 2), big.reshape(-1, 2)]); slot = iq.shape[1]
+    dev = torch.device("cuda", 0); st = torch.cuda.current_stream().cuda_stream
+    t_iq = torch.from_numpy(flat).to(dev)
+    t_off = torch.tensor([0, slot, 2 * slot], dtype=torch.int64, device=dev); t_len = torch.full((3,), slot, dtype=torch.int32, device=dev)
+    t_out = torch.zeros((3, 1500), dtype=torch.uint8, device=dev); t_res = torch.zeros((3, 7), dtype=torch.int32, device=dev)
+    call = lambda: eng.rx11a_raw(t_iq.data_ptr(), flat.shape[0], t_off.data_ptr(), t_len.data_ptr(), 3, t_out.data_ptr(), 1500, t_res.data_ptr(), st)
+    call(); torch.cuda.synchronize()
+    assert (t_res.cpu().numpy()[:, 0] == 1).all() and (t_out.cpu().numpy()[:, :90] == ps).all()
+    t_off[2] = 3 * slot; t_len[2] = big.shape[1]                       # same pointers, a much longer (valid) third slot
+    call(); torch.cuda.synchronize()
+    r = t_res.cpu().numpy(); assert (r[:, 0] == 1).all() and r[2, 2] == 1400 and (t_out.cpu().numpy()[2, :1400] == psb[0]).all()
+    t_len[1] = flat.shape[0]                                            # slot 1 now runs past the end of the buffer
+    with pytest.raises(api.Sb200Error): call()
+    t_len[1] = slot; t_off[0] = 2 ** 63                                 # offset + length would wrap a 64-bit sum
+    with pytest.raises(api.Sb200Error): call()
+
+def test_44msps_more_than_65535_slots(eng):
+    """sb200_rx11a_batch_ex at 44 Msps with more slots than a grid's y extent allows (65535): empty slots, one real capture among them."""
+    from test_cpu_oracle import _capture_44
+    cap, ps = _capture_44(24000, 120, 91, snr_db=30)
+    n = 66000; ln = np.full(n, 56, np.uint32); off = np.arange(n, dtype=np.uint64) * 56
+    flat = np.zeros((n * 56 + len(cap), 2), np.int16); flat[n * 56:] = cap
+    off[65999] = n * 56; ln[65999] = len(cap)
+    res, out = eng.rx11a_batch(flat, off, ln, sample_rate_mhz=44)
+    assert res["status"][65999] == 1 and res["length"][65999] == 120 and (out[65999, :120] == ps).all()
+    assert (res["status"][:65999] == api.FRAME_NONE).all()
+
+def test_legacy_shim_more_events_than_one_pass_holds():
+    """300 short frames in one RX stream: the legacy entry points keep finding them after the shim's 256-event pass (RxThread has no such limit)."""
+    import ctypes as C
+    lib = api.load_library()
+    class Stream(C.Structure): _fields_ = [("start", C.c_void_p), ("size", C.c_uint32), ("end", C.c_void_p), ("scan", C.c_void_p), ("mask", C.c_uint32)]
+    class Ctx(C.Structure):
+        _fields_ = [("SampleRate", C.c_uint), ("thr", C.c_uint32), ("maxblk", C.c_uint), ("minblk", C.c_uint), ("work", C.c_void_p), ("frame", C.c_void_p),
+                    ("framemax", C.c_uint), ("framesize", C.c_uint), ("datarate", C.c_uint), ("frametype", C.c_uint), ("engine", C.c_void_p), ("events", C.c_void_p), ("shift", C.c_uint)]
+    for f in ("BB11ARxCarrierSense", "BB11ARxFrameDemod"): getattr(lib, f).restype = C.c_int32
+    iq, ps = synth.make_frames(300, psdu_len=30, rate_kbps=24000, snr_db=30, seed0=0xE000, lead=200, trail=220)
+    cap = iq.reshape(-1, 2); cap = cap[: len(cap) // 28 * 28]
+    blocks = np.zeros((len(cap) // 28, 128), np.uint8); blocks[:, 0] = 1; blocks[:, 16:] = cap.reshape(-1, 28 * 2).view(np.uint8)
+    work = C.c_uint32(1); frame = np.zeros(4096, np.uint8); st = Stream(); ctx = Ctx()
+    lib.SoraGenRadioRxStreamOffline(C.byref(st), C.c_void_p(blocks.ctypes.data), C.c_uint32(blocks.size))
+    lib.BB11ARxContextInit(C.byref(ctx), 40, 0, 150, 112, C.byref(work))
+    got = []
+    for _ in range(100000):
+        hr = lib.BB11ARxCarrierSense(C.byref(ctx), C.byref(st))
+        if hr == 0x201:
+            lib.BB11APrepareRx(C.byref(ctx), C.c_void_p(frame.ctypes.data), 4096)
+            hr = lib.BB11ARxFrameDemod(C.byref(ctx), C.byref(st)) & 0xFFFFFFFF
+            got.append((hr, frame[:ctx.framesize].copy()))
+        if st.scan == st.start and got: break
+    lib.BB11ARxContextCleanup(C.byref(ctx))
+    assert len(got) == 300 and all(hr == 0x202 for hr, _ in got)
+    for (hr, by), p in zip(got, ps): assert (by == p).all()
 
 def test_ofdm_bin_golden(eng):
     """The reference's own 24 Mbps modulator output decodes to 200 x 0x31 + FCS on the GPU as well."""
