@@ -325,7 +325,7 @@ def main():
         def step_e2e():
             eng.rx11a_raw(iq_host.data_ptr(), F * SLOT, off_h.ctypes.data, len_h.ctypes.data, F, out_host.data_ptr(), PSDU, res_host.data_ptr(), stream.cuda_stream)
         ne = max(3, min(args.steps, 5))
-        nth = args.host_threads if args.host_threads >= 0 else int(max(1, min(12, cores_rank - 2)))
+        nth = args.host_threads if args.host_threads >= 0 else int(max(1, min(16, cores_rank - 2)))
         modes = {}
         eng.set_option("host_decimate", 0)
         ms_full = timed_max(step_e2e, ne)
@@ -351,8 +351,8 @@ def main():
     if dist and not args.no_mgpu:
         P = 4                                              # pieces per slab: the scatter of piece p+1 overlaps the decode of piece p
         Fp = F // P; assert Fp * P == F
-        slab = torch.empty((F, SLOT * 2), dtype=torch.int16, device=dev)
-        root = iq_unique_dev.repeat((world * F + U - 1) // U, 1)[: world * F].contiguous().view(world, P, Fp, SLOT * 2) if rank == 0 else None
+        slab = torch.empty((F, SLOT * 2), dtype=torch.int16, device=dev); slab32 = slab.view(torch.int32)   # NCCL has no 16-bit integer type: one COMPLEX16 = one int32
+        root = iq_unique_dev.repeat((world * F + U - 1) // U, 1)[: world * F].contiguous().view(torch.int32).view(world, P, Fp, SLOT) if rank == 0 else None
         out_all = torch.empty((world, F, PSDU), dtype=torch.uint8, device=dev) if rank == 0 else None
         res_all = torch.empty((world, F, 7), dtype=torch.int32, device=dev) if rank == 0 else None
         offp = (torch.arange(Fp, dtype=torch.int64, device=dev) * SLOT); lenp = torch.full((Fp,), SLOT, dtype=torch.int32, device=dev)
@@ -360,7 +360,7 @@ def main():
             works = []
             for p in range(P):
                 lst = [root[r, p] for r in range(world)] if rank == 0 else None
-                works.append(dist.scatter(slab[p * Fp:(p + 1) * Fp], lst, src=0, async_op=True))
+                works.append(dist.scatter(slab32[p * Fp:(p + 1) * Fp], lst, src=0, async_op=True))
             for p in range(P):
                 works[p].wait()
                 eng.rx11a_raw(slab[p * Fp:(p + 1) * Fp].data_ptr(), Fp * SLOT, offp.data_ptr(), lenp.data_ptr(), Fp,
@@ -375,7 +375,7 @@ def main():
             mgpu = {"value": world * F * SLOT / (ms_m * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_m, "collective": "NCCL scatter (IQ slabs, root -> ranks) + gather (bytes, verdicts -> root)",
                     "nccl_ranks": world, "scatter_bytes_per_step": int((world - 1) * F * SLOT * 4), "gather_bytes_per_step": int((world - 1) * F * (PSDU + 28)),
                     "pieces_per_slab": P, "note": "all N*F slots resident on rank 0's GPU at the start of the step; bound by rank 0's NVLink egress"}
-        del slab, root, out_all, res_all
+        del slab, slab32, root, out_all, res_all
     del iq_unique_dev
     if rank != 0:
         if dist: dist.destroy_process_group()

@@ -22,10 +22,49 @@ def peaks():
     try: return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception: return 6650.0
 
+class Ctx:
+    """One process per GPU (torchrun) or a single process: device, engine, and a timing helper that follows bench.py's rules
+    (>= 3 warm-ups, barrier + synchronize on both sides, CUDA events on the launch stream, max over ranks)."""
+    def __init__(self):
+        import torch
+        from sora_b200 import api
+        from bench import numa_bind, effective_cpus
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1")); self.rank = int(os.environ.get("RANK", "0")); self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.aff0 = os.sched_getaffinity(0); self.numa = numa_bind(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local)); self.dist = dist
+        self.dev = torch.device("cuda", self.local); self.st = torch.cuda.current_stream()
+        self.eng = api.Engine(self.local); self.eng.set_option("slot_table_immutable", 1)
+        self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+    def cpus(self):
+        from bench import effective_cpus
+        os.sched_setaffinity(0, self.aff0)
+        return effective_cpus()[0]
+    def timed(self, fn, n, warm=3):
+        torch = self.torch
+        for _ in range(warm): fn()
+        torch.cuda.synchronize()
+        if self.dist: self.dist.barrier()
+        self.e0.record(self.st)
+        for _ in range(n): fn()
+        self.e1.record(self.st); torch.cuda.synchronize()
+        if self.dist: self.dist.barrier()
+        t = torch.tensor([self.e0.elapsed_time(self.e1)], dtype=torch.float64, device=self.dev)
+        if self.dist: self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()) / n
+    def emit(self, line):
+        if self.rank == 0: print(json.dumps(line), flush=True)
+    def close(self):
+        if self.dist: self.dist.destroy_process_group()
+
 def bench_viterbi(args):
-    import torch, oracle_py
+    import oracle_py
     from sora_b200 import api, synth
-    eng = api.Engine(0); dev = torch.device("cuda", 0); st = torch.cuda.current_stream()
+    c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st
     L = 2500
     for cr, rate, name in ((api.CR_12, (1, 2), "1/2"), (api.CR_23, (2, 3), "2/3"), (api.CR_34, (3, 4), "3/4")):
         nbits = 8 * L + 16 + 6; nbits += (-nbits) % 48
@@ -37,7 +76,9 @@ def bench_viterbi(args):
         flip = rng.random(coded.shape) < 0.03
         soft = np.where(flip, rng.integers(0, 8, coded.shape), soft).astype(np.uint8)
         nsoft = soft.shape[1]; stride = (nsoft + 15) // 16 * 16
-        NB = args.blocks
+        # BASELINE config #5: 1e9 coded bits in total ("strong": the same total at every GPU count), or --blocks per GPU ("weak")
+        total = args.blocks * c.world if args.blocks else -(-10**9 // nsoft)
+        NB = -(-total // c.world)
         sp = np.zeros((U, stride), np.uint8); sp[:, :nsoft] = soft
         d_soft = torch.from_numpy(sp).to(dev).repeat((NB + U - 1) // U, 1)[:NB].contiguous()
         d_out = torch.zeros((NB, L + 2 + 14), dtype=torch.uint8, device=dev)
@@ -46,28 +87,26 @@ def bench_viterbi(args):
         ref = oracle_py.viterbi_blocks(soft, cr, L)
         got = d_out[:U, :L + 2].cpu().numpy()
         assert (got == ref).all(), "GPU Viterbi differs from the oracle"
-        for _ in range(3): step()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record(st)
-        for _ in range(args.steps): step()
-        e1.record(st); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        coded_bits = NB * nsoft
-        t0 = time.perf_counter(); ncpu = os.cpu_count() or 1
-        rep = np.tile(soft, (max(1, 4096 // U), 1))
-        oracle_py.viterbi_blocks(rep, cr, L, nthreads=ncpu); dt = time.perf_counter() - t0
-        alg = coded_bits * (1.0 + (rate[0] / rate[1]) / 8.0)
-        print(json.dumps({"metric": "standalone K=7 soft Viterbi throughput", "code_rate": name, "value": coded_bits / (ms * 1e-3) / 1e9, "unit": "G coded bits/s",
-                          "decoded_mbit_s": NB * (8 * L + 16) / (ms * 1e-3) / 1e6, "ms_per_step": ms, "blocks": NB, "info_bits_per_block": 8 * L + 22,
-                          "coded_bits_per_step": coded_bits, "n_gpus": 1, "dtype": "uint8 path metrics",
-                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks()},
-                          "cpu_baseline": {"value": rep.shape[0] * nsoft / dt / 1e9, "unit": "G coded bits/s", "cores": ncpu, "kind": "port", "sample": f"{rep.shape[0]} blocks"},
-                          "parity": "bit-exact vs oracle on %d blocks" % U}))
+        ms = c.timed(step, args.steps)
+        coded_bits = NB * c.world * nsoft
+        line = {"metric": "standalone K=7 soft Viterbi throughput", "code_rate": name, "value": coded_bits / (ms * 1e-3) / 1e9, "unit": "G coded bits/s",
+                "decoded_mbit_s": NB * c.world * (8 * L + 16) / (ms * 1e-3) / 1e6, "ms_per_step": ms, "blocks_per_gpu": NB, "info_bits_per_block": 8 * L + 22,
+                "coded_bits_per_step": coded_bits, "n_gpus": c.world, "scaling": "weak" if args.blocks else "strong (1e9 coded bits in total, BASELINE config #5)", "dtype": "uint8 path metrics",
+                "parity": "bit-exact vs oracle on %d blocks" % U}
+        alg = coded_bits / c.world * (1.0 + (rate[0] / rate[1]) / 8.0)
+        line["roofline"] = {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks(), "note": "per GPU"}
+        if c.rank == 0 and c.world == 1:
+            ncpu = c.cpus(); rep = np.tile(soft, (max(1, 4096 // U), 1))
+            t0 = time.perf_counter(); oracle_py.viterbi_blocks(rep, cr, L, nthreads=ncpu); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": rep.shape[0] * nsoft / dt / 1e9, "unit": "G coded bits/s", "cores": ncpu, "kind": "port", "sample": f"{rep.shape[0]} blocks"}
+        c.emit(line)
+        del d_soft, d_out
+    c.close()
 
 def bench_11b(args):
-    import torch, oracle_py
+    import oracle_py
     from sora_b200 import api, synth
-    eng = api.Engine(0); dev = torch.device("cuda", 0); st = torch.cuda.current_stream()
+    c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st
     # The reference's CCK decoder is a pruned search (cck.hpp:262-769) and drops isolated symbols on some band-limited
     # waveforms even without noise; the timed set is made of slots the CPU oracle decodes FRAME_OK, so that the whole
     # chain (all 1500 bytes + CRC) is exercised.  GPU == oracle is asserted on all of them either way.
@@ -90,26 +129,22 @@ def bench_11b(args):
     assert (d_res[:U, 0].cpu().numpy().astype(np.uint32) == ores["status"]).all() and (ores["status"] == 1).all()
     assert (d_out[:U, :1499].cpu().numpy() == oout[:, :1499]).all() and (oout[:, :1499] == ps[:, :1499]).all()
     assert (d_res[:, 0].cpu().numpy() == 1).all()
-    for _ in range(3): step()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record(st)
-    for _ in range(args.steps): step()
-    e1.record(st); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    ncpu = os.cpu_count() or 1
-    n = 2048
-    t0 = time.perf_counter(); oracle_py.rx11b_batch(iq.reshape(-1, 2), (np.arange(n) % U) * slot, np.full(n, slot), out_stride=1504, nthreads=ncpu); dt = time.perf_counter() - t0
+    ms = c.timed(step, args.steps)
     alg = F * (slot * 4.0 + 1516)
-    print(json.dumps({"metric": "802.11b 11 Mbps CCK RX PHY Msamples/s (IQ in, bits out)", "value": F * slot / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
-                      "n_gpus": 1, "config": {"workload": "802.11b 11 Mbps CCK long preamble, PSDU 1500 B, 44 Msps (BASELINE config #3)", "slots_per_step": F, "samples_per_slot": int(slot), "unique_slots": U},
-                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks()},
-                      "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msamples/s", "cores": ncpu, "kind": "port", "sample": f"{n} slots"},
-                      "parity": "bytes and verdicts identical to the oracle on the %d unique slots" % U}))
+    line = {"metric": "802.11b 11 Mbps CCK RX PHY Msamples/s (IQ in, bits out)", "value": c.world * F * slot / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+            "n_gpus": c.world, "scaling": "weak", "config": {"workload": "802.11b 11 Mbps CCK long preamble, PSDU 1500 B, 44 Msps (BASELINE config #3)", "slots_per_step_per_gpu": F, "samples_per_slot": int(slot), "unique_slots": U},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks(), "note": "per GPU"},
+            "parity": "bytes and verdicts identical to the oracle on the %d unique slots" % U}
+    if c.rank == 0 and c.world == 1:
+        ncpu = c.cpus(); n = 2048
+        t0 = time.perf_counter(); oracle_py.rx11b_batch(iq.reshape(-1, 2), (np.arange(n) % U) * slot, np.full(n, slot), out_stride=1504, nthreads=ncpu); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n * slot / dt / 1e6, "unit": "Msamples/s", "cores": ncpu, "kind": "port", "sample": f"{n} slots"}
+    c.emit(line); c.close()
 
 def bench_11n(args):
-    import torch, oracle_py
+    import oracle_py
     from sora_b200 import api, synth
-    eng = api.Engine(0); dev = torch.device("cuda", 0); st = torch.cuda.current_stream()
+    c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st; dist = c.dist
     for mcs in (8, 9, 10):
         U = 32
         iq0, iq1, ps = synth.make_frames_11n(U, psdu_len=1500, mcs=mcs, snr_db=30, lead=400, trail=200)      # fixed 2x2 channel [[1, 0.3j], [-0.2, 0.9]]
@@ -124,23 +159,50 @@ def bench_11n(args):
         ores, oout = oracle_py.rx11n_batch(iq0.reshape(-1, 2), iq1.reshape(-1, 2), np.arange(U) * slot, np.full(U, slot), out_stride=1536)
         assert (ores["status"] == 1).all() and (oout[:, :1500] == ps).all()
         assert (d_res[:, 0].cpu().numpy() == 1).all() and (d_out[:U, :1500].cpu().numpy() == oout[:, :1500]).all()
-        for _ in range(3): step()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record(st)
-        for _ in range(args.steps): step()
-        e1.record(st); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        ms = c.timed(step, args.steps)
         kt = eng.last_kernel_times()
-        ncpu = os.cpu_count() or 1; n = 1024
-        t0 = time.perf_counter(); oracle_py.rx11n_batch(iq0.reshape(-1, 2), iq1.reshape(-1, 2), (np.arange(n) % U) * slot, np.full(n, slot), out_stride=1536, nthreads=ncpu); dt = time.perf_counter() - t0
         alg = F * (slot * 8.0 + 1516)
-        print(json.dumps({"metric": "802.11n 2x2 RX PHY Msample-pairs/s (2 x IQ in, bits out)", "mcs": mcs, "value": F * slot / (ms * 1e-3) / 1e6, "unit": "Msample-pairs/s", "ms_per_step": ms,
-                          "n_gpus": 1, "config": {"workload": "802.11n HT-MF 2x2, 20 MHz, PSDU 1500 B, 40 Msps per antenna, AWGN 30 dB, channel [[1,0.3j],[-0.2,0.9]] (BASELINE config #4)",
-                                                   "slots_per_step": F, "sample_pairs_per_slot": int(slot), "unique_slots": U},
-                          "kernel_ms": dict(zip(("carrier_sense", "ofdm_front_end", "viterbi_descramble_crc", "pack"), kt)) if kt is not None else None,
-                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks()},
-                          "cpu_baseline": {"value": n * slot / dt / 1e6, "unit": "Msample-pairs/s", "cores": ncpu, "kind": "port", "sample": f"{n} slots"},
-                          "parity": "bytes and verdicts identical to the oracle on the %d unique slots" % U}))
+        line = {"metric": "802.11n 2x2 RX PHY Msample-pairs/s (2 x IQ in, bits out)", "mcs": mcs, "value": c.world * F * slot / (ms * 1e-3) / 1e6, "unit": "Msample-pairs/s", "ms_per_step": ms,
+                "n_gpus": c.world, "scaling": "weak", "config": {"workload": "802.11n HT-MF 2x2, 20 MHz, PSDU 1500 B, 40 Msps per antenna, AWGN 30 dB, channel [[1,0.3j],[-0.2,0.9]] (BASELINE config #4)",
+                                                   "slots_per_step_per_gpu": F, "sample_pairs_per_slot": int(slot), "unique_slots": U, "numa": c.numa},
+                "kernel_ms": dict(zip(("carrier_sense", "ofdm_front_end", "viterbi_descramble_crc", "pack"), kt)) if kt is not None else None,
+                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks(), "note": "per GPU"},
+                "parity": "bytes and verdicts identical to the oracle on the %d unique slots" % U}
+        if dist:
+            # "frames sharded across 2/4/8 B200" (BASELINE config #4): both antenna captures of all world*F slots sit on rank 0; NCCL scatters the two
+            # slabs per rank, every rank decodes its share, NCCL gathers bytes + verdicts on rank 0; everything inside the timed region
+            P = 4; Fp = F // P; assert Fp * P == F
+            s0 = torch.empty_like(d0); s1 = torch.empty_like(d1); v0 = s0.view(torch.int32); v1 = s1.view(torch.int32)   # NCCL has no 16-bit integer type
+            r0 = d0[:U].repeat((c.world * F + U - 1) // U, 1)[: c.world * F].contiguous().view(torch.int32).view(c.world, P, Fp, -1) if c.rank == 0 else None
+            r1 = d1[:U].repeat((c.world * F + U - 1) // U, 1)[: c.world * F].contiguous().view(torch.int32).view(c.world, P, Fp, -1) if c.rank == 0 else None
+            oa = torch.empty((c.world, F, 1536), dtype=torch.uint8, device=dev) if c.rank == 0 else None
+            ra = torch.empty((c.world, F, 7), dtype=torch.int32, device=dev) if c.rank == 0 else None
+            offp = torch.arange(Fp, dtype=torch.int64, device=dev) * slot; lenp = torch.full((Fp,), slot, dtype=torch.int32, device=dev)
+            def step_m():
+                w = []
+                for p in range(P):
+                    w.append((dist.scatter(v0[p * Fp:(p + 1) * Fp], [r0[r, p] for r in range(c.world)] if c.rank == 0 else None, src=0, async_op=True),
+                              dist.scatter(v1[p * Fp:(p + 1) * Fp], [r1[r, p] for r in range(c.world)] if c.rank == 0 else None, src=0, async_op=True)))
+                for p in range(P):
+                    w[p][0].wait(); w[p][1].wait()
+                    eng.rx11n_raw(s0[p * Fp:(p + 1) * Fp].data_ptr(), s1[p * Fp:(p + 1) * Fp].data_ptr(), Fp * slot, offp.data_ptr(), lenp.data_ptr(), Fp,
+                                  d_out[p * Fp:(p + 1) * Fp].data_ptr(), 1536, d_res[p * Fp:(p + 1) * Fp].data_ptr(), st.cuda_stream)
+                dist.gather(d_out, [oa[r] for r in range(c.world)] if c.rank == 0 else None, dst=0)
+                dist.gather(d_res, [ra[r] for r in range(c.world)] if c.rank == 0 else None, dst=0)
+            msm = c.timed(step_m, max(3, min(args.steps, 5)), warm=2)
+            if c.rank == 0:
+                assert bool((ra[:, :, 0] == 1).all()) and (oa[c.world - 1, :U, :1500].cpu().numpy() == oout[:, :1500]).all()
+                line["mgpu"] = {"value": c.world * F * slot / (msm * 1e-3) / 1e6, "unit": "Msample-pairs/s", "ms_per_step": msm, "nccl_ranks": c.world,
+                                "collective": "NCCL scatter of both antenna slabs (root -> ranks) + gather of bytes and verdicts",
+                                "scatter_bytes_per_step": int((c.world - 1) * F * slot * 8), "gather_bytes_per_step": int((c.world - 1) * F * (1536 + 28))}
+            del s0, s1, v0, v1, r0, r1, oa, ra
+        if c.rank == 0 and c.world == 1:
+            ncpu = c.cpus(); n = 1024
+            t0 = time.perf_counter(); oracle_py.rx11n_batch(iq0.reshape(-1, 2), iq1.reshape(-1, 2), (np.arange(n) % U) * slot, np.full(n, slot), out_stride=1536, nthreads=ncpu); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n * slot / dt / 1e6, "unit": "Msample-pairs/s", "cores": ncpu, "kind": "port", "sample": f"{n} slots"}
+        c.emit(line)
+        del d0, d1, d_out, d_res
+    c.close()
 
 def bench_tx11a(args):
     import torch, oracle_py
@@ -261,7 +323,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b", "tx11n"], required=True)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--blocks", type=int, default=32768)
+    ap.add_argument("--blocks", type=int, default=0, help="Viterbi code blocks per GPU (0 = BASELINE config #5: 1e9 coded bits in total over all GPUs)")
     ap.add_argument("--frames", type=int, default=32768)
     a = ap.parse_args()
     {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b, "tx11n": bench_tx11n}[a.config](a)

@@ -74,9 +74,15 @@ bool is_device_ptr(const void* p) {
 // identical: the same samples reach the same arithmetic.
 static void decimate_slot(const uint32_t* __restrict__ src, uint32_t n2, uint32_t* __restrict__ dst) {     // dst[j] = src[2 j], j < n2
     uint32_t j = 0;
-    for (; j + 4 <= n2; j += 4) {
+    // the packed copy is written once and read by the DMA engine only: streaming stores keep it from costing a read-for-ownership and from
+    // pushing the capture out of the cache.  Head up to a 16-byte boundary of dst, then 4 samples per store.
+    for (; j < n2 && ((uintptr_t)(dst + j) & 15u); j++) dst[j] = src[2 * j];
+    for (; j + 8 <= n2; j += 8) {
         const __m128 a = _mm_loadu_ps((const float*)(src + 2 * j)), b = _mm_loadu_ps((const float*)(src + 2 * j + 4));
-        _mm_storeu_ps((float*)(dst + j), _mm_shuffle_ps(a, b, 0x88));
+        const __m128 c = _mm_loadu_ps((const float*)(src + 2 * j + 8)), d = _mm_loadu_ps((const float*)(src + 2 * j + 12));
+        _mm_prefetch((const char*)(src + 2 * j + 256), _MM_HINT_NTA);
+        _mm_stream_ps((float*)(dst + j), _mm_shuffle_ps(a, b, 0x88));
+        _mm_stream_ps((float*)(dst + j + 4), _mm_shuffle_ps(c, d, 0x88));
     }
     for (; j < n2; j++) dst[j] = src[2 * j];
 }
@@ -87,6 +93,7 @@ struct DecimPool {
     static void part(const Job& j, int w, int n) {
         const uint64_t cnt = j.f1 - j.f0; const uint32_t a = j.f0 + (uint32_t)(cnt * w / n), b = j.f0 + (uint32_t)(cnt * (w + 1) / n);
         for (uint32_t f = a; f < b; f++) decimate_slot(j.iq + j.off[f], (j.len[f] + 1u) / 2u, j.dst + (j.doff[f] - j.doff[j.f0]));
+        _mm_sfence();                                   // streaming stores visible before the copy is queued
     }
     void start(int nthreads) {                          // nthreads includes the calling thread
         shutdown(); n = nthreads < 1 ? 1 : nthreads; stop = false;

@@ -304,7 +304,7 @@ def test_device_slot_table_is_checked_every_call(eng):
     r = t_res.cpu().numpy(); assert (r[:, 0] == 1).all() and r[2, 2] == 1400 and (t_out.cpu().numpy()[2, :1400] == psb[0]).all()
     t_len[1] = flat.shape[0]                                            # slot 1 now runs past the end of the buffer
     with pytest.raises(api.Sb200Error): call()
-    t_len[1] = slot; t_off[0] = 2 ** 63                                 # offset + length would wrap a 64-bit sum
+    t_len[1] = slot; t_off[0] = -2 ** 63                                # read as uint64 2^63: offset + length would wrap a 64-bit sum
     with pytest.raises(api.Sb200Error): call()
 
 def test_44msps_more_than_65535_slots(eng):
