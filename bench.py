@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=4096, help="slots per pipeline chunk inside the library (0 = no chunking)")
     ap.add_argument("--chunk-device", type=int, default=0, help="slots per pipeline chunk for device-resident IQ (0 = one pass; >0 overlaps the front end of chunk k+1 with the Viterbi of chunk k)")
     ap.add_argument("--host-threads", type=int, default=-1, help="host threads of the decimating e2e path (option host_decimate); -1 = from the CPUs this rank may use")
+    ap.add_argument("--front-stage", type=int, default=-1, help="experiment: sample staging of the OFDM front end (0 direct, 1 register double buffer, 2 bulk async copy); -1 = library default")
     ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -249,6 +250,7 @@ def main():
     eng.set_option("chunk_frames_device", args.chunk_device)
     eng.set_option("slot_table_immutable", 1)             # the slot tables below are written once and never touched again
     if args.vq_pad_smem: eng.set_option("vq_pad_smem", args.vq_pad_smem)
+    if args.front_stage >= 0: eng.set_option("front_stage", args.front_stage)
     stream = torch.cuda.current_stream()
     # ---- HBM-resident input: U unique slots tiled to F (distinct addresses: 2.6 GB at F=65536 >> 126 MB L2) ----
     iq_unique_dev = torch.from_numpy(iq_u.reshape(U, -1)).to(dev)

@@ -257,6 +257,12 @@ __device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 
 // symbol B (16 butterflies per stage = 16 lanes, so every lane is busy); the first stage consumes the freq-compensated
 // time samples straight from registers.  Only the part behind the FFT (phase compensation from the pilot recurrence)
 // is serial across symbols, and there every lane owns two subcarriers.
+// STAGE: how the time samples of the DATA symbols reach the FFT (A/B of the staging experiment, profiles/README.md):
+//   0  loaded straight into registers right before the transform (round 1);
+//   1  the next symbol pair's samples are loaded into registers while the current pair is processed (register double buffer);
+//   2  one lane starts a 1-D bulk asynchronous copy (cp.async.bulk, the TMA unit; SASS UBLKCP) of the next pair's span into a shared-memory
+//      double buffer, completion on an mbarrier; the lanes then read their samples from shared memory.
+template <int STAGE>
 __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
         const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, FrameInfo* __restrict__ info,
         uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps, uint32_t sh) {
@@ -264,8 +270,15 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a
     __shared__ __align__(16) uint8_t s_soft[SB_FRONT_WARPS][288];
     __shared__ uint32_t s_demap[256];                  // per input value: [bpsk/qpsk/first bit | 16-QAM second | 64-QAM second | 64-QAM third] soft bits
     __shared__ uint8_t s_pilot[128];
+    __shared__ __align__(16) uint32_t s_stage[STAGE == 2 ? SB_FRONT_WARPS : 1][2][STAGE == 2 ? 328 : 4];   // 2 x (320 words of a symbol pair + alignment slack)
+    __shared__ __align__(8) unsigned long long s_mbar[STAGE == 2 ? SB_FRONT_WARPS : 1][2];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (STAGE == 2 && lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_mbar[wib][0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_mbar[wib][1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         s_demap[i] = (uint32_t)__ldg(T.demap + i) | ((uint32_t)__ldg(T.demap + 256 + i) << 8) | ((uint32_t)__ldg(T.demap + 512 + i) << 16) | ((uint32_t)__ldg(T.demap + 768 + i) << 24);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_pilot[i] = __ldg(T.pilot_neg + i);
@@ -438,17 +451,77 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a
         cs16 v[4]; load4(s0 + 144u + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]);
         more = post_fft(0, 0);
     }
+    // ---- staging of the DATA symbols (see STAGE above) ----
+    const uint32_t nsamp20 = nvec * 4u;                                   // 20 Msps samples of the slot that may be read
+    uint32_t raw[4] = {0, 0, 0, 0}; uint32_t raw_first = 0xFFFFFFFFu;     // STAGE 1: samples first + hl + 16 j of the prefetched symbol
+    auto prefetch_regs = [&](uint32_t first) {                            // whole symbol inside the slot, else nothing
+        raw_first = 0xFFFFFFFFu;
+        if (first + 72u <= nsamp20) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) raw[j] = __ldg(x + ((first + hl + 16u * j) << sh));
+            raw_first = first;
+        }
+    };
+    uint32_t st_par[2] = {0, 0}; uint32_t st_base[2] = {0, 0}, st_cnt[2] = {0, 0}; uint32_t st_i = 0;   // STAGE 2: parity / first 20 Msps sample / samples per buffer
+    auto stage_issue = [&](int b, uint32_t first20, uint32_t n20) {       // samples [first20, first20 + n20) of the slot -> buffer b (word index << sh)
+        st_base[b] = first20; st_cnt[b] = 0;
+        if (first20 >= nsamp20) return;
+        if (first20 + n20 > nsamp20) n20 = nsamp20 - first20;
+        st_cnt[b] = n20;
+        if (lane == 0) {
+            const uint32_t* src = x + (first20 << sh);
+            const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15, a1 = ((uintptr_t)(src + (n20 << sh)) + 15) & ~(uintptr_t)15;
+            const uint32_t bytes = (uint32_t)(a1 - a0);
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar[wib][b]), dst = (uint32_t)__cvta_generic_to_shared(&s_stage[wib][b][0]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(a0), "r"(bytes), "r"(mb) : "memory");
+        }
+    };
+    auto stage_wait = [&](int b) {
+        if (st_cnt[b] == 0) return;
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar[wib][b]); uint32_t ok = 0;
+        while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mb), "r"(st_par[b]) : "memory");
+        st_par[b] ^= 1u;
+    };
+    auto stage_load4 = [&](int b, uint32_t first, cs16 (&v)[4]) {        // (x >> 1) * FreqCoeffs from buffer b; the buffer starts at the 16-byte line of its first sample
+        const uint32_t skew = (uint32_t)(((uintptr_t)(x + (st_base[b] << sh)) & 15u) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = cmul_q15(sra(unpack(s_stage[wib][b][skew + ((first - st_base[b] + hl + 16u * j) << sh)]), 1), fcv[j]);
+    };
+    if (STAGE == 2 && more) stage_issue(0, s0 + 144u + 80u, 160u);        // symbols 1 and 2
+    if (STAGE == 1 && more) prefetch_regs(s0 + 144u + 80u * (1u + (uint32_t)half) + 8u);
     for (uint32_t sym = 1; more; sym += 2) {
         const bool haveA = sym_ready(sym), haveB = remain >= 2 && sym_ready(sym + 1);
         if (!haveA) { status = E_NO_FRAME; break; }
         {   cs16 v[4];
             const uint32_t mine = (half && haveB) ? sym + 1 : sym;          // without a second symbol both halves transform A
-            load4(s0 + 144u + 80u * mine + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]); }
+            const uint32_t first = s0 + 144u + 80u * mine + 8u;
+            if (STAGE == 2) {
+                const int b = (int)(st_i & 1u);
+                const bool staged = st_base[b] == s0 + 144u + 80u * sym && st_cnt[b] >= (mine - sym + 1u) * 80u;
+                stage_wait(b);
+                if (staged) stage_load4(b, first, v); else load4(first, v);
+                __syncwarp();                                               // every lane has its samples: the other buffer's previous contents are no longer needed either
+                st_i++; stage_issue((int)(st_i & 1u), s0 + 144u + 80u * (sym + 2u), 160u);
+            } else if (STAGE == 1) {
+                if (raw_first == first) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = cmul_q15(sra(unpack(raw[j]), 1), fcv[j]);
+                } else load4(first, v);
+                prefetch_regs(s0 + 144u + 80u * (sym + 2u + (uint32_t)half) + 8u);
+            } else load4(first, v);
+            fft_from_regs(v[0], v[1], v[2], v[3]); }
         more = post_fft(0, sym);
         if (!more) break;
-        if (!haveB) { if (remain >= 1 && !sym_ready(sym + 1)) { status = E_NO_FRAME; break; } sym -= 1; continue; }
+        if (!haveB) {
+            if (remain >= 1 && !sym_ready(sym + 1)) { status = E_NO_FRAME; break; }
+            sym -= 1;                                                       // the next pair starts one symbol later than staged: restage
+            if (STAGE == 2) { stage_wait((int)(st_i & 1u)); __syncwarp(); stage_issue((int)(st_i & 1u), s0 + 144u + 80u * (sym + 2u), 160u); }
+            continue;
+        }
         more = post_fft(1, sym + 1);
     }
+    if (STAGE == 2) { stage_wait((int)(st_i & 1u)); __syncwarp(); }        // no copy may be in flight when the CTA's shared memory is released
     if (lane == 0) { fi.status = status; fi.soft_bytes = soft_bytes; info[f] = fi; }
 }
 

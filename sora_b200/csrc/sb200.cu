@@ -143,6 +143,7 @@ struct sb200_handle {
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0; bool tab_host = false;
+    uint32_t front_stage = 0;                          // option: sample staging of k_front11a (0 direct loads, 1 register double buffer, 2 bulk async copy to shared memory)
     uint32_t host_decimate = 0;                        // option: host threads gathering the even samples of host-resident 40 Msps captures (0 = off)
     DecimPool* pool = nullptr; void* hstage[3] = {nullptr, nullptr, nullptr}; size_t hstage_cap = 0; cudaEvent_t ev_hfree[3] = {nullptr, nullptr, nullptr};
     DevBuf doff; std::vector<uint64_t> doffh;
@@ -318,8 +319,10 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
     if (timed) CK(cudaEventRecord(h->evk[0], sf));
     k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info, dc_init ? dc_init + f0 : nullptr, sh);
     if (timed) CK(cudaEventRecord(h->evk[1], sf));
-    k_front11a<<<(n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info,
-            d_soft, soft_stride, h->inv_deint, taps, sh);
+    {   const dim3 g((n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS), b(32 * SB_FRONT_WARPS);
+        if (h->front_stage == 2) k_front11a<2><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh);
+        else if (h->front_stage == 1) k_front11a<1><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh);
+        else k_front11a<0><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh); }
     if (timed) CK(cudaEventRecord(h->evk[2], sf));
     if (sv != sf) { CK(cudaEventRecord(front_done, sf)); CK(cudaStreamWaitEvent(sv, front_done, 0)); }
     VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
@@ -1168,6 +1171,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "chunk_frames")) { h->chunk_frames = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "chunk_frames_device")) { h->chunk_frames_device = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "vq_pad_smem")) { h->vq_pad_smem = (uint32_t)value; return SB200_OK; }
+    if (!strcmp(name, "front_stage")) { if (value > 2) return h->fail(SB200_E_INVALID, "front_stage is 0, 1 or 2"); h->front_stage = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
     if (!strcmp(name, "slot_table_immutable")) { h->tab_immutable = value != 0; h->tab_off = nullptr; return SB200_OK; }
     return h->fail(SB200_E_INVALID, "unknown option");

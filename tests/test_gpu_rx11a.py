@@ -39,6 +39,27 @@ def test_all_rates_clean_and_noisy(eng, rate):
             for i in range(6):
                 assert (out[i, :257] == ps[i]).all()
 
+@pytest.mark.parametrize("stage", [1, 2])
+def test_front_end_staging_variants(eng, stage):
+    """Option front_stage: register double buffer (1) and bulk asynchronous copy into shared memory (2) feed the same samples to the same
+    arithmetic as the direct loads (0): identical results on all rates, odd symbol counts, truncated and misaligned slots."""
+    caps = []
+    for i, rate in enumerate(sorted(synth.RATES)):
+        iq, _ = synth.make_frames(2, psdu_len=61 + 97 * i, rate_kbps=rate, snr_db=25, seed0=0x5000 + rate, lead=37 + 3 * i, trail=50 + i)
+        caps += [iq[0], iq[1][: len(iq[1]) - 400 * (i % 3)]]
+    off = np.concatenate([[0], np.cumsum([len(c) + 1 for c in caps])[:-1]]).astype(np.uint64)     # + 1: slot starts at every alignment mod 4 words
+    flat = np.zeros((int(off[-1]) + len(caps[-1]) + 8, 2), np.int16)
+    for o, c in zip(off, caps): flat[int(o): int(o) + len(c)] = c
+    ln = np.array([len(c) for c in caps], np.uint32)
+    ref, refo = eng.rx11a_batch(flat, off, ln)
+    eng.set_option("front_stage", stage)
+    try:
+        res, out = eng.rx11a_batch(flat, off, ln)
+        assert (res == ref).all() and (out == refo).all()
+        assert (ref["status"] == 1).sum() >= 8
+    finally:
+        eng.set_option("front_stage", 0)
+
 def test_fsample6_golden(eng):
     iq = load_dump(os.path.join(GOLD, "fsample-6.dmp"))
     iq = (iq.astype(np.int32) << 2).astype(np.int16)     # 14-bit sample sign adjust (arx_fd.c:530 xmmAdjustSignBit)
