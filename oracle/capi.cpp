@@ -246,6 +246,10 @@ uint64_t sbo_tx11a_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_
     return tx11a_modulate(payload, len, rate_kbps, seed, out, (size_t)cap_samples, tail_zeros);
 }
 uint32_t sbo_tx11a_nsym(uint32_t len, uint32_t rate_kbps) { return tx11a_nsym(len, rate_kbps); }
+uint64_t sbo_tx11a_legacy_modulate(const uint8_t* mpdu, uint32_t len, int append_crc, uint32_t rate_kbps, const int16_t* preamble640, int8_t* out, uint64_t cap_samples) {
+    return tx11a_legacy_modulate(mpdu, len, append_crc, rate_kbps, (const c16*)preamble640, out, (size_t)cap_samples);
+}
+uint32_t sbo_tx11a_legacy_nsym(uint32_t psdu_len, uint32_t rate_kbps) { return tx11a_legacy_nsym(psdu_len, rate_kbps); }
 void sbo_ifft128(const int16_t* in, int16_t* out) { alignas(16) c16 t[128]; memcpy(t, in, 512); alignas(16) c16 o[128]; ifft128((v128*)t, (v128*)o); memcpy(out, o, 512); }
 
 // ---- 802.11b transmit ---------------------------------------------------------------------------------------------------

@@ -6,6 +6,8 @@
 
 namespace sbo {
 
+void tx11a_encode_bits(const std::vector<uint8_t>& bytes, int cr, std::vector<uint8_t>& coded);
+
 static const int16_t BPSK_MOD = 10720;                                  // mapper11a.hpp:8-11
 static inline int16_t kmod_of(int nbpsc) { return nbpsc == 1 ? BPSK_MOD : nbpsc == 2 ? (int16_t)(BPSK_MOD / 1.414) : nbpsc == 4 ? (int16_t)(BPSK_MOD / 3.162) : (int16_t)(BPSK_MOD / 6.481); }
 
@@ -87,7 +89,7 @@ static void symbol_out(const uint8_t* coded /*ncbps bits, one per byte*/, int nb
 }
 
 // rate-1/2 mother code, bits LSB first, then puncturing (conv_enc.hpp:5-280): returns coded bits, one per byte
-static void encode(const std::vector<uint8_t>& bytes, int cr, std::vector<uint8_t>& coded) {
+void tx11a_encode_bits(const std::vector<uint8_t>& bytes, int cr, std::vector<uint8_t>& coded) {
     unsigned s = 0; coded.clear();
     size_t n = bytes.size() * 8;
     for (size_t i = 0; i < n; i++) {
@@ -117,7 +119,7 @@ size_t tx11a_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_kbps, 
         uint32_t sig = ri->code | ((len + 4u) << 5);
         uint32_t p = sig ^ (sig >> 16); p ^= p >> 8; p ^= p >> 4; p ^= p >> 2; p ^= p >> 1; sig |= (p & 1u) << 17;
         std::vector<uint8_t> b = {(uint8_t)sig, (uint8_t)(sig >> 8), (uint8_t)(sig >> 16)}, coded;
-        encode(b, CR_12, coded);
+        tx11a_encode_bits(b, CR_12, coded);
         symbol_out(coded.data(), 1, pilot_index, out + 2 * 640);
     }
     // DATA: SERVICE, MPDU, CRC-32, tail byte, pad (TBB11aSrc::Process, PHY_11a.hpp:125-190) through T11aSc (scramble.hpp:169-262)
@@ -132,7 +134,7 @@ size_t tx11a_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_kbps, 
         data[i] = (uint8_t)(data[i] ^ reg);
         if (i == tail_at) data[i] &= 0xC0;
     }
-    std::vector<uint8_t> coded; encode(data, ri->cr, coded);
+    std::vector<uint8_t> coded; tx11a_encode_bits(data, ri->cr, coded);
     const int ncbps = 48 * ri->nbpsc;
     for (uint32_t s = 0; s < nsym; s++) symbol_out(coded.data() + (size_t)s * ncbps, ri->nbpsc, pilot_index, out + 2 * (640 + 160 * (size_t)(1 + s)));
     memset(out + 2 * (640 + 160 * (size_t)(1 + nsym)), 0, 2 * (size_t)tail_zeros);

@@ -18,4 +18,7 @@ size_t tx11a_modulate(const uint8_t* payload, uint32_t len, uint32_t rate_kbps, 
 // symbol count the reference transmits (TBB11aSrc::GetPadingByte, PHY_11a.hpp:107-123): the tail is counted as a whole byte and
 // 9 Mbps pads to a pair of symbols, so this can exceed the standard's N_SYM by one
 uint32_t tx11a_nsym(uint32_t len, uint32_t rate_kbps);
+// the LEGACY transmitter (tx11a_legacy.cpp): BB11ATxFrameMod / BB11ATxBufferMod6M; pinned by usr/HwVeri/data/ofdm.bin
+size_t tx11a_legacy_modulate(const uint8_t* mpdu, uint32_t len, int append_crc, uint32_t rate_kbps, const c16* preamble640, int8_t* out, size_t cap_samples);
+uint32_t tx11a_legacy_nsym(uint32_t psdu_len, uint32_t rate_kbps);
 }

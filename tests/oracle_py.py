@@ -158,6 +158,17 @@ def tx11a_modulate(payload, rate_kbps, seed=0xFF, tail_zeros=32):
     assert n == cap, (n, cap)
     return out
 
+def tx11a_legacy_modulate(body, rate_kbps, append_crc=True):
+    """The reference's LEGACY transmitter (BB11ATxFrameMod; oracle/tx11a_legacy.cpp).  Returns int8 [n, 2]: 640 + 160 (1 + nsym) + 8 samples at 40 Msps."""
+    body = np.ascontiguousarray(body, dtype=np.uint8); L = lib(); L.sbo_tx11a_legacy_modulate.restype = C.c_uint64
+    pre = np.fromfile(os.path.join(ROOT, "tests", "golden", "preamble40_11a.i16"), np.int16)
+    nsym = L.sbo_tx11a_legacy_nsym(C.c_uint32(len(body) + (4 if append_crc else 0)), C.c_uint32(rate_kbps)); assert nsym, "not an 802.11a rate"
+    cap = 640 + 160 * (1 + nsym) + 8
+    out = np.zeros((cap, 2), np.int8)
+    n = L.sbo_tx11a_legacy_modulate(_p(body), C.c_uint32(len(body)), C.c_int(1 if append_crc else 0), C.c_uint32(rate_kbps), _p(pre), _p(out), C.c_uint64(cap))
+    assert n == cap, (n, cap)
+    return out
+
 def ifft128(x):
     x = np.ascontiguousarray(x, dtype=np.int16); o = np.zeros((128, 2), np.int16); lib().sbo_ifft128(_p(x), _p(o)); return o
 

@@ -54,3 +54,52 @@ def test_tx_tables_vs_reference():
     assert (rc.ref_bitrev(128) == np.array([int(format(i, "07b")[::-1], 2) for i in range(128)])).all()
     t8 = np.array(rc.parse_array(rc._read("kernel/core/inc/fft_lut_twiddle.h"), "wFFTLUT8")).reshape(-1, 2)
     assert (t8 == np.array([[32767, 0], [23169, -23169], [32767, 0], [-23169, -23169]])).all()
+
+
+# ---- the reference's LEGACY transmitter (BB11ATxFrameMod): pinned by its own output file and by vectors made from its own tables ------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LEGACY_RATES = (6000, 9000, 12000, 18000, 24000, 36000, 48000, 54000)
+
+def test_legacy_tx_reproduces_ofdm_bin():
+    """usr/HwVeri/data/ofdm.bin is the output of the reference's legacy modulator for 200 x 0x31 at 24 Mbps: the restatement
+    (oracle/tx11a_legacy.cpp) gives the same 3680 signal samples, sample for sample (the file then holds zeros where
+    UpsampleTailAndCopyNT would put the 8-sample window tail, and zero padding up to a 64-byte multiple)."""
+    ref = np.fromfile(os.path.join(GOLD, "ofdm.bin"), np.int8).reshape(-1, 2)
+    got = oracle_py.tx11a_legacy_modulate(np.full(200, 0x31, np.uint8), 24000)
+    assert len(got) == 3688 and len(ref) == 3712
+    assert (got[:3680] == ref[:3680]).all()
+    assert not ref[3680:].any()
+
+@pytest.mark.parametrize("kbps", LEGACY_RATES)
+def test_legacy_tx_vectors_from_reference_tables(kbps):
+    """tests/golden/legacy_tx/: one frame per rate made by driving the reference's own LUTs (scrambler, encoder, interleaver, mapper, pilots,
+    preamble) the way its C code drives them (tests/golden/make_legacy_tx_vectors.py).  The function-driven restatement must reproduce every
+    sample, and the receive oracle must decode the waveform to the frame body: a table-derived known answer at every rate, 54 Mbps included."""
+    body = np.fromfile(os.path.join(GOLD, "legacy_tx", f"legacy_tx_{kbps}.bin"), np.uint8)
+    ref = np.fromfile(os.path.join(GOLD, "legacy_tx", f"legacy_tx_{kbps}.i8"), np.int8).reshape(-1, 2)
+    got = oracle_py.tx11a_legacy_modulate(body, kbps)
+    assert got.shape == ref.shape and (got == ref).all()
+    iq = np.concatenate([np.zeros((400, 2), np.int16), ref.astype(np.int16) << 8, np.zeros((428, 2), np.int16)])      # ConvertModFile2DumpFile_8b
+    res, out = oracle_py.rx11a_run(iq)
+    assert len(res) == 1 and res[0]["status"] == 1 and res[0]["rate_kbps"] == kbps and res[0]["length"] == len(body) + 4
+    assert bytes(out[0, :len(body)]) == bytes(body)
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_legacy_tx_vectors_regenerate_from_the_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(GOLD, "make_legacy_tx_vectors.py")); mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    frame = mk.build()
+    for kbps in (9000, 54000):
+        body = np.fromfile(os.path.join(GOLD, "legacy_tx", f"legacy_tx_{kbps}.bin"), np.uint8)
+        assert (frame(body, kbps) == np.fromfile(os.path.join(GOLD, "legacy_tx", f"legacy_tx_{kbps}.i8"), np.int8).reshape(-1, 2)).all()
+    pre = np.fromfile(os.path.join(GOLD, "preamble40_11a.i16"), np.int16)
+    assert (pre == mk.table("preamble40_11a.c")).all()
+
+def test_legacy_tx_ack_frame_round_trip():
+    """BB11AModulateACK's path (BB11ATxBufferMod6M: the buffer already ends in its FCS): the 14-byte ACK of the Dot11ADummy fixtures."""
+    import golden_vectors as gv
+    w = oracle_py.tx11a_legacy_modulate(np.frombuffer(gv.ACK_PSDU, np.uint8), 6000, append_crc=False)
+    assert len(w) == 640 + 160 * 7 + 8
+    iq = np.concatenate([np.zeros((400, 2), np.int16), w.astype(np.int16) << 8, np.zeros((428, 2), np.int16)])
+    res, out = oracle_py.rx11a_run(iq)
+    assert len(res) == 1 and res[0]["status"] == 1 and bytes(out[0, :14]) == gv.ACK_PSDU

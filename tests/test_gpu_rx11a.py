@@ -386,6 +386,20 @@ def test_reference_dummy_frames(eng):
         want = vec[n][2] if vec[n][2] is not None else bytes(gv.fsample6_psdu())
         assert res["rate_kbps"][i] == 6000 and res["length"][i] == len(want) and bytes(out[i, :len(want)]) == want, n
 
+def test_legacy_tx_vectors_decode_on_the_device(eng):
+    """tests/golden/legacy_tx/: frames made from the reference's own transmit tables at all eight rates (54 Mbps / 64-QAM / R = 3/4 included),
+    one ragged batch: the device returns the oracle's results and every frame body."""
+    rates = (6000, 9000, 12000, 18000, 24000, 36000, 48000, 54000)
+    caps, bodies = [], []
+    for kbps in rates:
+        w = np.fromfile(os.path.join(GOLD, "legacy_tx", f"legacy_tx_{kbps}.i8"), np.int8).reshape(-1, 2)
+        caps.append(np.concatenate([np.zeros((400, 2), np.int16), w.astype(np.int16) << 8, np.zeros((428, 2), np.int16)]))
+        bodies.append(np.fromfile(os.path.join(GOLD, "legacy_tx", f"legacy_tx_{kbps}.bin"), np.uint8))
+    off = np.concatenate([[0], np.cumsum([len(c) for c in caps])[:-1]]).astype(np.uint64); ln = np.array([len(c) for c in caps], np.uint32)
+    res, out = _compare(eng, np.concatenate(caps), off, ln, expect_ok=8)
+    for i, kbps in enumerate(rates):
+        assert res["rate_kbps"][i] == kbps and res["length"][i] == len(bodies[i]) + 4 and (out[i, :len(bodies[i])] == bodies[i]).all()
+
 def test_many_streams_at_once(eng):
     """sb200_rx11a_streams: a batch of continuous captures, each decoded with RxThread's sequential semantics."""
     caps = [_mixed_stream(s, dc=(40 * s - 200, 17 * s)) for s in range(7, 19)]
