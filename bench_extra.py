@@ -319,11 +319,32 @@ def bench_tx11n(args):
                           "parity": "bit-exact vs the transmit oracle on 3 frames; every slot pair decodes FRAME_OK through the 802.11n receive path"}))
         del d0, d1
 
+def bench_fir(args):
+    """The anti-alias FIR decimator on a device-resident capture: the one streaming (HBM-bound) stage of the path; 6 B per input sample."""
+    c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st
+    n = args.frames * 9824 * 2                                           # twice config #2's per-step sample count
+    x = torch.randint(-20000, 20000, (n, 2), dtype=torch.int16, device=dev); y = torch.empty(((n + 1) // 2, 2), dtype=torch.int16, device=dev)
+    def step(): eng.fir_decimate2_raw(x.data_ptr(), n, 0, 0, y.data_ptr(), st.cuda_stream)
+    step(); torch.cuda.synchronize()
+    import numpy as np
+    xs = x[:50000].cpu().numpy().astype(np.int64); taps = np.array([-121, 0, 209, 0, -381, 0, 644, 0, -1056, 0, 1759, 0, -3278, 0, 10391, 16434, 10391, 0, -3278, 0, 1759, 0, -1056, 0, 644, 0, -381, 0, 209, 0, -121], np.int64)
+    xp = np.zeros((50000 + 32, 2), np.int64); xp[15:15 + 50000] = xs; ref = np.zeros((24000, 2), np.int64)
+    for k, t in enumerate(taps):
+        if t: ref += t * xp[k: k + 48000: 2]
+    assert (np.clip((ref + (1 << 14)) >> 15, -32768, 32767) == y[:24000].cpu().numpy()).all(), "FIR output differs from the stated arithmetic"
+    ms = c.timed(step, args.steps)
+    alg = n * 6.0
+    c.emit({"metric": "anti-alias FIR decimator 2:1 Msamples/s (COMPLEX16 in)", "value": c.world * n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "n_gpus": c.world,
+            "config": {"workload": "31-tap half-band low-pass, 40 -> 20 Msps, device-resident COMPLEX16", "samples_per_step_per_gpu": n},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks(), "note": "6 B per input sample: 4 read + 4 written per two"},
+            "parity": "equal to the arithmetic of include/sora_b200.h (numpy, 64-bit) on the first 24000 outputs"})
+    c.close()
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b", "tx11n"], required=True)
+    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b", "tx11n", "fir"], required=True)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--blocks", type=int, default=0, help="Viterbi code blocks per GPU (0 = BASELINE config #5: 1e9 coded bits in total over all GPUs)")
     ap.add_argument("--frames", type=int, default=32768)
     a = ap.parse_args()
-    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b, "tx11n": bench_tx11n}[a.config](a)
+    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b, "tx11n": bench_tx11n, "fir": bench_fir}[a.config](a)

@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc", "sb200_fir_decimate2"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -201,6 +201,17 @@ class Engine:
         vb = np.zeros(nblk, np.uint32); ts = np.zeros(nblk, np.uint32)
         self._check(self._lib.sb200_rxblocks_desc(self._h, C.c_void_p(_ptr(raw)), C.c_uint64(nblk), C.c_void_p(_ptr(vb)), C.c_void_p(_ptr(ts)), C.c_void_p(0)), "sb200_rxblocks_desc")
         return vb, ts
+
+    def fir_decimate2_raw(self, in_ptr, n_in, taps_ptr, ntaps, out_ptr, stream=0):
+        self._check(self._lib.sb200_fir_decimate2(self._h, C.c_void_p(in_ptr), C.c_uint64(n_in), C.c_void_p(taps_ptr), C.c_uint32(ntaps), C.c_void_p(out_ptr), C.c_void_p(stream)), "sb200_fir_decimate2")
+
+    def fir_decimate2(self, iq, taps=None):
+        """2:1 anti-alias FIR decimator: int16 [n,2] -> int16 [(n+1)//2, 2]; taps int16 Q15 (odd count <= 63) or None for the built-in half-band."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        out = np.zeros(((len(iq) + 1) // 2, 2), np.int16)
+        t = None if taps is None else np.ascontiguousarray(taps, dtype=np.int16)
+        self.fir_decimate2_raw(_ptr(iq), len(iq), _ptr(t) if t is not None else 0, 0 if t is None else len(t), _ptr(out))
+        return out
 
     def rxblocks_unpack(self, raw, left_shift=0):
         """raw: uint8 array of whole 128-byte RX_BLOCKs (a *.dmp file) -> int16 [28*nblocks, 2] via the device gather."""

@@ -77,13 +77,13 @@ __device__ __forceinline__ int cca_xcorr(const CcaState& s, const uint32_t* __re
 
 __global__ void __launch_bounds__(128) k_sync11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
                                                   const uint32_t* __restrict__ len, uint32_t nframes, uint32_t cca_thr,
-                                                  DevTables T, FrameInfo* __restrict__ info, const int2* __restrict__ dc_init, uint32_t sh) {
+                                                  DevTables T, FrameInfo* __restrict__ info, const int2* __restrict__ dc_init, uint32_t sh, uint32_t lsh) {
     // sh = 1: `iq` is the 40 Msps capture and TDownSample2 (samples.hpp:27-49) is the stride-2 gather below; sh = 0: the caller's samples were
     // decimated on the way in (host-side gather of the even samples, sb200.cu), off[] then addresses that packed copy; len[] stays in 40 Msps samples
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const uint32_t* x = iq + off[f];
-    const uint32_t nblk = len[f] / 28u;               // memsource.hpp:87: whole 28-sample source blocks only
+    const uint32_t nblk = (len[f] << lsh) / 28u;      // memsource.hpp:87: whole 28-sample source blocks only (lsh = 1: len[] counts 20 Msps samples)
     const uint32_t nvec = nblk * 28u / 8u;
     CcaState s; s.reset();
     int dc_re = dc_init ? dc_init[f].x : 0, dc_im = dc_init ? dc_init[f].y : 0;   // CF_VecDC: zero at Init, carried along a stream
@@ -265,7 +265,7 @@ __device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 
 template <int STAGE>
 __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a(const uint32_t* __restrict__ iq, const uint64_t* __restrict__ off,
         const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, FrameInfo* __restrict__ info,
-        uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps, uint32_t sh) {
+        uint8_t* __restrict__ soft_out, uint64_t soft_stride, const uint16_t* __restrict__ inv_deint, FrontTaps taps, uint32_t sh, uint32_t lsh) {
     __shared__ uint32_t s_fft[SB_FRONT_WARPS][2][64];
     __shared__ __align__(16) uint8_t s_soft[SB_FRONT_WARPS][288];
     __shared__ uint32_t s_demap[256];                  // per input value: [bpsk/qpsk/first bit | 16-QAM second | 64-QAM second | 64-QAM third] soft bits
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a
     if (fi.status != E_SUCCESS) return;
     uint8_t* sb = s_soft[wib];
     const uint32_t* x = iq + off[f];
-    const uint32_t nvec = (len[f] / 28u) * 28u / 8u;
+    const uint32_t nvec = ((len[f] << lsh) / 28u) * 28u / 8u;
     const uint32_t s0 = fi.detect_vec * 4u;            // first 20 Msps sample of the 144-sample LTS block
     if (fi.detect_vec + 36u > nvec) { if (lane == 0) info[f].status = E_NO_FRAME; return; }
     const int half = lane >> 4, hl = lane & 15;        // FFT role: which of the two symbols, which butterfly

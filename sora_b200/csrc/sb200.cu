@@ -7,6 +7,7 @@
 #include "tx11a_kernels.cuh"
 #include "tx11b_kernels.cuh"
 #include "tx11n_kernels.cuh"
+#include "fir_kernels.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -310,19 +311,19 @@ static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t
 // Launch the decode kernels for frames [f0, f1) of a call.  `iq_base + off[f]` must address slot f.
 // sync + front end go to `sf`, the Viterbi launches to `sv` (sv waits for `front_done` when the streams differ).
 static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t f0, uint32_t f1,
-                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr, uint32_t chunk_idx = 0, uint32_t sh = 1) {
+                        uint64_t soft_stride, uint64_t row, cudaStream_t sf, cudaStream_t sv, cudaEvent_t front_done, FrontTaps taps, bool timed, const int2* dc_init = nullptr, uint32_t chunk_idx = 0, uint32_t sh = 1, uint32_t lsh = 0) {
     const uint32_t n = f1 - f0;
     FrameInfo* d_info = (FrameInfo*)h->info.p + f0;
     uint8_t* d_soft = (uint8_t*)h->soft.p + (size_t)f0 * soft_stride;
     uint8_t* d_out = (uint8_t*)h->out.p + (size_t)f0 * row;
     uint32_t* d_status = (uint32_t*)h->status.p + f0; uint32_t* d_crc = (uint32_t*)h->crc.p + f0;
     if (timed) CK(cudaEventRecord(h->evk[0], sf));
-    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info, dc_init ? dc_init + f0 : nullptr, sh);
+    k_sync11a<<<(n + 127) / 128, 128, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->cca_thr, h->T, d_info, dc_init ? dc_init + f0 : nullptr, sh, lsh);
     if (timed) CK(cudaEventRecord(h->evk[1], sf));
     {   const dim3 g((n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS), b(32 * SB_FRONT_WARPS);
-        if (h->front_stage == 2) k_front11a<2><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh);
-        else if (h->front_stage == 1) k_front11a<1><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh);
-        else k_front11a<0><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh); }
+        if (h->front_stage == 2) k_front11a<2><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh, lsh);
+        else if (h->front_stage == 1) k_front11a<1><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh, lsh);
+        else k_front11a<0><<<g, b, 0, sf>>>(iq_base, d_off + f0, d_len + f0, n, h->T, d_info, d_soft, soft_stride, h->inv_deint, taps, sh, lsh); }
     if (timed) CK(cudaEventRecord(h->evk[2], sf));
     if (sv != sf) { CK(cudaEventRecord(front_done, sf)); CK(cudaStreamWaitEvent(sv, front_done, 0)); }
     VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
@@ -356,7 +357,7 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
 // The front end is latency bound and the Viterbi integer-issue bound, so they overlap well on the same SMs.
 static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
                      uint32_t nframes, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res, cudaStream_t st,
-                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride, const int2* dc_init = nullptr, bool no_chunk = false) {
+                     FrontTaps taps, uint8_t* soft_host, uint64_t soft_host_stride, const int2* dc_init = nullptr, bool no_chunk = false, bool rate20 = false) {
     if (!h || !iq || !frame_off || !frame_len || !res) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
     if (nframes == 0) return SB200_OK;
     CK(cudaSetDevice(h->device));
@@ -365,9 +366,10 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     std::vector<uint64_t>& offh = h->offh; std::vector<uint32_t>& lenh = h->lenh;
     const uint64_t* d_off; const uint32_t* d_len; uint32_t max_len = 0; bool tab_on_host = false;
     {
-        const bool may_chunk = !no_chunk && !iq_dev && h->chunk_frames != 0 && nframes > h->chunk_frames;
+        const bool may_chunk = !no_chunk && !rate20 && !iq_dev && h->chunk_frames != 0 && nframes > h->chunk_frames;
         int rc = slot_table(h, frame_off, frame_len, nframes, iq_total, may_chunk, st, &d_off, &d_len, &max_len, &tab_on_host);
         if (rc != SB200_OK) return rc;
+        if (rate20) { if (max_len > 0x7FFFFFFFu) return h->fail(SB200_E_INVALID, "slot too long"); max_len <<= 1; }   // slots counted in 20 Msps samples
     }
     // workspaces
     const uint64_t max_sym = (max_len / 2u) / 80u + 1u;
@@ -381,7 +383,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     const bool tapping = taps.freq_coeffs || taps.fft_out || soft_host || dc_init;
     // device-resident IQ gains nothing from chunking (a chunk's Viterbi grid no longer fills 148 SMs x 5 CTAs); host IQ does:
     // the PCIe copy of chunk k+1 hides behind the kernels of chunk k.  chunk_frames_device lets a caller force it anyway.
-    const uint32_t want = no_chunk ? 0u : iq_dev ? h->chunk_frames_device : h->chunk_frames;
+    const uint32_t want = (no_chunk || rate20) ? 0u : iq_dev ? h->chunk_frames_device : h->chunk_frames;
     const uint32_t chunk = (want == 0 || tapping || nframes <= want || (!iq_dev && !tab_on_host)) ? nframes : want;
     const bool pipelined = chunk < nframes;
     CK(h->vcnt.need(16ull * ((nframes + chunk - 1) / chunk)));
@@ -392,7 +394,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         const uint32_t* d_iq;
         if (iq_dev) d_iq = (const uint32_t*)iq;
         else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
-        int rc = launch_chunk(h, d_iq, d_off, d_len, 0, nframes, soft_stride, row, st, st, nullptr, taps, true, dc_init);
+        int rc = launch_chunk(h, d_iq, d_off, d_len, 0, nframes, soft_stride, row, st, st, nullptr, taps, true, dc_init, 0, rate20 ? 0u : 1u, rate20 ? 1u : 0u);
         if (rc != SB200_OK) return rc;
         h->nk = 4;
     } else {
@@ -559,12 +561,42 @@ extern "C" int sb200_rx11a_stream(sb200_handle* h, const int16_t* iq, uint64_t n
     return sb200_rx11a_streams(h, iq, nsamples, &off, &len, 1, max_frames, out_bytes, out_stride, res, sample_index, nframes_out, cuda_stream);
 }
 
+// 2:1 anti-alias FIR decimator (fir_kernels.cuh): out[m] = sat16((sum_k taps[k] x[2m + k - (ntaps-1)/2] + 2^14) >> 15), zero outside the buffer.
+// taps == NULL selects the built-in 31-tap half-band low-pass (equiripple: +-0.05 dB to 8.3 MHz of a 40 Msps capture, 50 dB down beyond 11.7 MHz).
+static const int16_t kHalfBand31[31] = {-121, 0, 209, 0, -381, 0, 644, 0, -1056, 0, 1759, 0, -3278, 0, 10391, 16434, 10391, 0, -3278, 0, 1759, 0, -1056, 0, 644, 0, -381, 0, 209, 0, -121};   // sum 32768 (unit DC gain)
+extern "C" int sb200_fir_decimate2(sb200_handle* h, const int16_t* iq, uint64_t n_in, const int16_t* taps, uint32_t ntaps, int16_t* out, void* cuda_stream) {
+    if (!h || !iq || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (!taps) { taps = kHalfBand31; ntaps = 31; }
+    if ((ntaps & 1u) == 0 || ntaps > SB_FIR_MAXTAPS) return h->fail(SB200_E_INVALID, "ntaps must be odd and at most 63");
+    if (n_in == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    const uint64_t n_out = (n_in + 1) / 2;
+    const bool in_dev = is_device_ptr(iq), out_dev = is_device_ptr(out);
+    const uint32_t* d_in; uint32_t* d_out;
+    if (in_dev) { if ((uintptr_t)iq & 15u) return h->fail(SB200_E_INVALID, "device input must be 16-byte aligned"); d_in = (const uint32_t*)iq; }
+    else { CK(h->iq.need(n_in * 4ull + 16)); CK(cudaMemcpyAsync(h->iq.p, iq, n_in * 4ull, cudaMemcpyHostToDevice, st)); d_in = (const uint32_t*)h->iq.p; }
+    if (out_dev) d_out = (uint32_t*)out; else { CK(h->iq40.need(n_out * 4ull + 16)); d_out = (uint32_t*)h->iq40.p; }
+    FirTaps T; memset(&T, 0, sizeof T); T.n = ntaps; for (uint32_t i = 0; i < ntaps; i++) T.t[i] = taps[i];
+    CK(cudaEventRecord(h->ev0, st));
+    k_fir_decimate2<<<(unsigned)((n_in + SB_FIR_TILE - 1) / SB_FIR_TILE), SB_FIR_THREADS, 0, st>>>(d_in, n_in, T, d_out, n_out);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 0; h->launches += 1;
+    CK(cudaGetLastError());
+    if (!out_dev) { CK(cudaMemcpyAsync(out, d_out, n_out * 4ull, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    return SB200_OK;
+}
+
 extern "C" int sb200_rx11a_batch_ex(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* frame_off, const uint32_t* frame_len,
                                     uint32_t nframes, uint32_t sample_rate_mhz, uint8_t* out_bytes, uint32_t out_stride,
                                     sb200_frame_result* res, void* cuda_stream) {
     if (!h) return SB200_E_INVALID;
     if (sample_rate_mhz == 40) return sb200_rx11a_batch(h, iq, iq_total, frame_off, frame_len, nframes, out_bytes, out_stride, res, cuda_stream);
-    if (sample_rate_mhz != 44) return h->fail(SB200_E_INVALID, "sample_rate_mhz must be 40 or 44");
+    if (sample_rate_mhz == 20) {                        // already decimated (sb200_fir_decimate2, or a 20 Msps front end): what TDownSample2 would hand on
+        FrontTaps taps{};
+        return rx11a_run(h, iq, iq_total, frame_off, frame_len, nframes, out_bytes, out_stride, res, (cudaStream_t)cuda_stream, taps, nullptr, 0, nullptr, true, true);
+    }
+    if (sample_rate_mhz != 44) return h->fail(SB200_E_INVALID, "sample_rate_mhz must be 20, 40 or 44");
     if (!iq || !frame_off || !frame_len || !res) return h->fail(SB200_E_INVALID, "null argument");
     if (nframes == 0) return SB200_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
