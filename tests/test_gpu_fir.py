@@ -30,7 +30,7 @@ def test_fir_decimate2_matches_the_stated_arithmetic(eng, n):
         assert (eng.fir_decimate2(iq, taps) == fir_model(iq, taps)).all(), (n, nt)
 
 def test_fir_then_20msps_chain_decodes_and_rejects_an_adjacent_channel(eng):
-    """A frame with a strong interferer 15 MHz off the carrier: dropping every other sample (the reference's TDownSample2) folds it onto the
+    """A frame under a strong interferer 11.5 .. 18.5 MHz off the carrier: dropping every other sample (the reference's TDownSample2) folds it onto the
     channel, the FIR decimator removes it first.  Also: the even samples handed to the 20 Msps entry give what the 40 Msps chain gives."""
     iq, ps = synth.make_frames(4, psdu_len=300, rate_kbps=36000, snr_db=30, seed0=0xF1, lead=120, trail=136)
     F, slot, _ = iq.shape
@@ -41,10 +41,11 @@ def test_fir_then_20msps_chain_decodes_and_rejects_an_adjacent_channel(eng):
     r20, o20 = eng.rx11a_batch(pick, off // 2, ln // 2, sample_rate_mhz=20)
     for k in ("status", "rate_kbps", "length", "crc32", "nsym", "detect_index", "cfo_est"): assert (r20[k] == ref[k]).all(), k
     assert (o20 == refo).all() and (ref["status"] == 1).all()
-    t = np.arange(len(flat)); tone = 9000 * np.exp(2j * np.pi * 15e6 / 40e6 * t)
-    jam = flat.astype(np.int32) + np.stack([tone.real, tone.imag], 1).astype(np.int32)
-    jam = np.clip(jam, -32768, 32767).astype(np.int16)
-    rj, _ = eng.rx11a_batch(jam, off, ln)                                      # plain decimation: the tone lands at -5 MHz inside the channel
+    rng = np.random.default_rng(5); N = len(flat)                              # band-limited interferer 11.5 .. 18.5 MHz off the carrier, stronger than the frame
+    S = (rng.normal(size=N) + 1j * rng.normal(size=N)); fr = np.fft.fftfreq(N, 1 / 40e6); S[(fr < 11.5e6) | (fr > 18.5e6)] = 0
+    w = np.fft.ifft(S); w *= 6000 / np.sqrt((np.abs(w) ** 2).mean() / 2)
+    jam = np.clip(flat.astype(np.int32) + np.stack([w.real, w.imag], 1).round().astype(np.int32), -32768, 32767).astype(np.int16)
+    rj, _ = eng.rx11a_batch(jam, off, ln)                                      # plain decimation folds the interferer onto the channel
     y = eng.fir_decimate2(jam)
     rf, of = eng.rx11a_batch(y, off // 2, ln // 2, sample_rate_mhz=20)
     assert (rf["status"] == 1).all() and (of[:, :300] == ps).all()
