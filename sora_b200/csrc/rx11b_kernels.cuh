@@ -67,14 +67,15 @@ struct Rx11bState {
     uint32_t error_code; int cca_state, rate_state, plcp_state;
     S16 DC, last_symbol; unsigned byte_reg, frame_length, data_rate_kbps, frame_crc32, detect_vec, vec_count;
     // bricks
-    uint32_t avg_energy, win[8], win_idx, ed_count;
+    uint32_t avg_energy, win0, win1, win2, win3, win4, win5, win6, win7, ed_count;   // TEnergyDetect's 8-vector window as a shift register (newest in win0)
     uint32_t dc_cnt; S16 dc_sum;
     int m_index, m_frag, st_n;
     int bs_state, bs_last_peak, bs_max, bs_search; S16 bs_partial[10];
-    S16 q[16]; int q_n, cck_even;                 // despread (11) / CCK (8|16) chip queue: only one is live at a time
-    S16 sym_q[8]; int sym_n;
+    int q_n, cck_even;                            // chips of the running symbol: Barker despread accumulates (q_sr, q_si), CCK chips wait in shared memory
+    int q_sr, q_si;
+    unsigned sym_bits; int sym_n;                 // DBPSK / DQPSK bits of the running byte
     bool sfd_one; unsigned sfd_word; int sfd_err; unsigned sfd_cnt;
-    unsigned char hdr[6]; int hdr_n;
+    unsigned hdr_lo, hdr_hi; int hdr_n;           // PLCP header bytes 0..3 / 4..5
     uint32_t byte_count, crc;
 };
 
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
                                               Result11b* __restrict__ res, uint32_t max_frames, uint32_t* __restrict__ counts) {
     __shared__ uint32_t s_crc[16];
     __shared__ unsigned short s_crc16[16];
+    __shared__ uint32_t s_q[64][17];                   // CCK chip queue of every thread (16 chips; 17 words per row: no bank conflicts between threads)
     if (threadIdx.x < 16) {
         uint32_t c = threadIdx.x; for (int k = 0; k < 4; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; s_crc[threadIdx.x] = c;
         uint32_t d = threadIdx.x; for (int k = 0; k < 4; k++) d = (d & 1) ? 0x8408u ^ (d >> 1) : d >> 1; s_crc16[threadIdx.x] = (unsigned short)d;
@@ -101,12 +103,12 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
     const uint32_t out_cap = (uint32_t)(out_stride < 0xFFFFFFFFull ? out_stride : 0xFFFFFFFFull);
     Rx11bState s;
     auto bricks_reset = [&]() {
-        s.avg_energy = 0; for (int i = 0; i < 8; i++) s.win[i] = 0; s.win_idx = 0; s.ed_count = 0;
+        s.avg_energy = 0; s.win0 = s.win1 = s.win2 = s.win3 = s.win4 = s.win5 = s.win6 = s.win7 = 0; s.ed_count = 0;
         s.dc_cnt = 8; s.dc_sum.re = s.dc_sum.im = 0;
         s.m_index = 2; s.m_frag = 0; s.st_n = 0;
         s.bs_state = 0; s.bs_last_peak = -1; s.bs_max = 0; s.bs_search = 0; for (int i = 0; i < 10; i++) { s.bs_partial[i].re = 0; s.bs_partial[i].im = 0; }
-        s.q_n = 0; s.sym_n = 0; s.cck_even = 0;
-        s.sfd_one = false; s.sfd_word = 0; s.sfd_err = 0; s.sfd_cnt = 0; s.hdr_n = 0;
+        s.q_n = 0; s.q_sr = s.q_si = 0; s.sym_n = 0; s.sym_bits = 0; s.cck_even = 0;
+        s.sfd_one = false; s.sfd_word = 0; s.sfd_err = 0; s.sfd_cnt = 0; s.hdr_n = 0; s.hdr_lo = s.hdr_hi = 0;
         s.byte_count = 0; s.crc = 0xFFFFFFFFu;
     };
     auto ctx_reset = [&]() { s.error_code = E_SUCCESS; s.cca_state = 0; s.rate_state = 0; s.plcp_state = 0; };
@@ -121,15 +123,18 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
         for (int k = 0; k < 8; k++) { unsigned o1 = (xx ^ sr ^ (sr >> 3)) & 1u; sr = ((sr >> 1) | ((xx & 1u) << 6)) & 0xFFu; o = (o >> 1) | (o1 << 7); xx >>= 1; }
         s.byte_reg = b >> 1;
         if (s.plcp_state == 0) {
-            s.hdr[s.hdr_n++] = (unsigned char)o;
+            if (s.hdr_n < 4) s.hdr_lo |= (o & 0xFFu) << (8 * s.hdr_n); else s.hdr_hi |= (o & 0xFFu) << (8 * (s.hdr_n - 4));
+            s.hdr_n++;
             if (s.hdr_n < 6) return;
             s.hdr_n = 0;
             unsigned c = 0xFFFFu;
-            for (int i = 0; i < 4; i++) { c ^= s.hdr[i]; c = (c >> 4) ^ s_crc16[c & 15]; c = (c >> 4) ^ s_crc16[c & 15]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { c ^= (s.hdr_lo >> (8 * i)) & 0xFFu; c = (c >> 4) ^ s_crc16[c & 15]; c = (c >> 4) ^ s_crc16[c & 15]; }
             c = (~c) & 0xFFFFu;
-            const unsigned got = s.hdr[4] | (s.hdr[5] << 8);
+            const unsigned got = s.hdr_hi & 0xFFFFu;
+            const unsigned hl = s.hdr_lo; s.hdr_lo = s.hdr_hi = 0;
             if (c != got) { s.error_code = E_PLCP_HEADER_FAIL; return; }
-            const unsigned signal = s.hdr[0], service = s.hdr[1], l = s.hdr[2] | (s.hdr[3] << 8);
+            const unsigned signal = hl & 0xFFu, service = (hl >> 8) & 0xFFu, l = hl >> 16;
             if (signal == 0x0A) { s.data_rate_kbps = 1000; s.frame_length = (l >> 3) & 0xFFFFu; s.rate_state = 1; }
             else if (signal == 0x14) { s.data_rate_kbps = 2000; s.frame_length = (l >> 2) & 0xFFFFu; s.rate_state = 2; }
             else if (signal == 0x37) { s.data_rate_kbps = 5500; s.frame_length = (((l * 11u) >> 4) - (service >> 7) - ((service >> 3) & 1u)) & 0xFFFFu; s.rate_state = 3; }
@@ -154,20 +159,17 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
     // ---- chip path behind TBB11bRxRateSel ----
     auto on_chip = [&](S16 c) {
         if (s.error_code != E_SUCCESS && s.error_code != E_CS_TIMEOUT) return;
-        s.q[s.q_n++] = c;
         if (s.rate_state <= 2) {
-            if (s.q_n < 11) return;
-            s.q_n = 0;
-            int sr = 0, si = 0;
-#pragma unroll
-            for (int i = 0; i < 11; i++) {                                  // QuickBarkerDespread (barkerspread.hpp:276-304)
-                short re, im;
-                if (i == 1 || i == 4) { re = (short)((short)(-s.q[i].re) >> 4); im = (short)((short)(-s.q[i].im) >> 4); }
-                else if (i >= 8) { re = (short)(-(s.q[i].re >> 4)); im = (short)(-(s.q[i].im >> 4)); }
-                else { re = (short)(s.q[i].re >> 4); im = (short)(s.q[i].im >> 4); }
-                sr += re; si += im;
+            {   // QuickBarkerDespread (barkerspread.hpp:276-304), one chip at a time: chips 1 and 4 are negated before the shift, chips 8..10 after it
+                const int i = s.q_n; short re, im;
+                if (i == 1 || i == 4) { re = (short)((short)(-c.re) >> 4); im = (short)((short)(-c.im) >> 4); }
+                else if (i >= 8) { re = (short)(-(c.re >> 4)); im = (short)(-(c.im >> 4)); }
+                else { re = (short)(c.re >> 4); im = (short)(c.im >> 4); }
+                s.q_sr += re; s.q_si += im;
             }
-            S16 sym; sym.re = (short)sr; sym.im = (short)si;
+            if (++s.q_n < 11) return;
+            S16 sym; sym.re = (short)s.q_sr; sym.im = (short)s.q_si;
+            s.q_n = 0; s.q_sr = s.q_si = 0;
             if (s.rate_state == 0) {                                        // TSFDSync
                 const unsigned bit = (unsigned)(s.last_symbol.re * sym.re + s.last_symbol.im * sym.im) >> 31;
                 s.last_symbol = sym;
@@ -184,26 +186,26 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
                 if (s.sfd_cnt > 144u) s.error_code = E_SFD_TIMEOUT;
                 return;
             }
-            s.sym_q[s.sym_n++] = sym;
-            if (s.rate_state == 1 && s.sym_n == 8) {                        // TDBPSKDemap
-                unsigned r = 0; S16 ref = s.last_symbol;
-#pragma unroll
-                for (int i = 0; i < 8; i++) { r |= ((unsigned)(ref.re * s.sym_q[i].re + ref.im * s.sym_q[i].im) >> 31) << i; ref = s.sym_q[i]; }
-                s.last_symbol = s.sym_q[7]; s.sym_n = 0; on_byte(r);
-            } else if (s.rate_state == 2 && s.sym_n == 4) {                 // TDQPSKDemap
-                unsigned r = 0; S16 ref = s.last_symbol;
-#pragma unroll
-                for (int i = 0; i < 4; i++) { r |= dqpsk_bits(ref, s.sym_q[i]) << (2 * i); ref = s.sym_q[i]; }
-                s.last_symbol = s.sym_q[3]; s.sym_n = 0; on_byte(r);
+            if (s.rate_state == 1) {                                        // TDBPSKDemap: 8 symbols -> one byte, each against its predecessor
+                s.sym_bits |= ((unsigned)(s.last_symbol.re * sym.re + s.last_symbol.im * sym.im) >> 31) << s.sym_n;
+                s.last_symbol = sym;
+                if (++s.sym_n == 8) { const unsigned r = s.sym_bits; s.sym_n = 0; s.sym_bits = 0; on_byte(r); }
+            } else {                                                        // TDQPSKDemap: 4 symbols -> one byte
+                s.sym_bits |= dqpsk_bits(s.last_symbol, sym) << (2 * s.sym_n);
+                s.last_symbol = sym;
+                if (++s.sym_n == 4) { const unsigned r = s.sym_bits; s.sym_n = 0; s.sym_bits = 0; on_byte(r); }
             }
             return;
         }
+        uint32_t* qrow = s_q[threadIdx.x];
+        qrow[s.q_n++] = ((uint32_t)(unsigned short)c.re) | ((uint32_t)(unsigned short)c.im << 16);
         if (s.rate_state == 4) {
             if (s.q_n < 8) return;
             s.q_n = 0;
             int R[8], I[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { R[i] = s.q[i].re; I[i] = s.q[i].im; }
+            for (int i = 0; i < 8; i++) { const S16 ch = s_w(qrow[i]); R[i] = ch.re; I[i] = ch.im; }
+            const S16 q7 = s_w(qrow[7]);
             CckPick m1 = cck11_module(R[0] + R[1], I[0] + I[1], R[2] - R[3], I[2] - I[3], R[4] + R[5], I[4] + I[5], R[7] - R[6], I[7] - I[6]);
             CckPick m2 = cck11_module(I[0] + R[1], I[1] - R[0], I[2] - R[3], -(R[2] + I[3]), I[4] + R[5], I[5] - R[4], R[7] - I[6], R[6] + I[7]);
             m2.val |= 0x08u;
@@ -215,9 +217,9 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
                 CckPick m3 = cck11_module(R[1] - R[0], I[1] - I[0], -(R[2] + R[3]), -(I[2] + I[3]), R[5] - R[4], I[5] - I[4], R[6] + R[7], I[6] + I[7]);
                 m3.val |= 0x04u; o = m2.mx > m3.mx ? m2.val : m3.val;
             }
-            o |= dqpsk_bits(s.last_symbol, s.q[7]);
+            o |= dqpsk_bits(s.last_symbol, q7);
             o ^= (unsigned)((s.cck_even << 1) | s.cck_even);
-            s.cck_even ^= 1; s.last_symbol = s.q[7];
+            s.cck_even ^= 1; s.last_symbol = q7;
             on_byte(o & 0xFFu);
             return;
         }
@@ -228,7 +230,8 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
         for (int hb = 0; hb < 2; hb++) {
             int R[8], I[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { R[i] = s.q[8 * hb + i].re; I[i] = s.q[8 * hb + i].im; }
+            for (int i = 0; i < 8; i++) { const S16 ch = s_w(qrow[8 * hb + i]); R[i] = ch.re; I[i] = ch.im; }
+            const S16 q7 = s_w(qrow[8 * hb + 7]);
             auto corr = [&](int a00r, int a00i, int a01r, int a01i, int a10r, int a10i, int a11r, int a11i) -> int {
                 int b0r = a00r + a01r, b0i = -(a00i + a01i), b1r = a10r + a11r, b1i = a10i + a11i;
                 b0r >>= 2; b0i >>= 2; b1r >>= 2; b1i >>= 2;
@@ -241,9 +244,9 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
             if (l1 > 0) { max1 = l1; v1 = 0; } else { max1 = -l1; v1 = b3; }
             if (l2 > 0) { max2 = l2; v2 = b2; } else { max2 = -l2; v2 = b2 | b3; }
             b |= max1 > max2 ? v1 : v2;
-            b |= dqpsk_bits(s.last_symbol, s.q[8 * hb + 7]) << (4 * hb);
+            b |= dqpsk_bits(s.last_symbol, q7) << (4 * hb);
             if (hb) b ^= 0x30u;
-            s.last_symbol = s.q[8 * hb + 7];
+            s.last_symbol = q7;
         }
         on_byte(b & 0xFFu);
     };
@@ -285,7 +288,8 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
                     uint32_t w4[4]; ld4(x + p0, w4);
 #pragma unroll
                     for (int k = 0; k < 4; k++) { xv[k] = s_sub(s_w(w4[k]), s.DC); pw += (uint32_t)((xv[k].re * xv[k].re + xv[k].im * xv[k].im) >> 5); }
-                    s.avg_energy = s.avg_energy - s.win[s.win_idx] + pw; s.win[s.win_idx] = pw; s.win_idx = (s.win_idx + 1) & 7;
+                    s.avg_energy = s.avg_energy - s.win7 + pw;
+                    s.win7 = s.win6; s.win6 = s.win5; s.win5 = s.win4; s.win4 = s.win3; s.win3 = s.win2; s.win2 = s.win1; s.win1 = s.win0; s.win0 = pw;
                     s.ed_count++;
                     if (s.ed_count >= 32) {
                         if (s.ed_count >= 100) s.error_code = E_CS_TIMEOUT;
@@ -317,14 +321,18 @@ __global__ void __launch_bounds__(64) k_rx11b(const uint32_t* __restrict__ iq, c
 #pragma unroll
                         for (int j = 0; j < 7; j++) pk[j] = c == 0 ? wv[j][0] : c == 1 ? wv[j][1] : c == 2 ? wv[j][2] : wv[j][3];
 #pragma unroll 1
-                        for (int j = j0; j < 7; j++) { const S16 o = s_sub(s_w(pk[j]), s.DC); if (s.error_code == E_SUCCESS) barker_sync(o); }
+                        for (int j = j0; j < 7; j++) {
+                            const uint32_t w = j == 0 ? pk[0] : j == 1 ? pk[1] : j == 2 ? pk[2] : j == 3 ? pk[3] : j == 4 ? pk[4] : j == 5 ? pk[5] : pk[6];   // register select, no local array
+                            const S16 o = s_sub(s_w(w), s.DC); if (s.error_code == E_SUCCESS) barker_sync(o);
+                        }
                     }
                     if (s.m_index >= 4) s.m_index = 0;
                     int sum[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int i = 0; i < 28; i++) { S16 vv = s_sra(s_sub(s_w(wv[i >> 2][i & 3]), s.DC), 3); sum[i & 3] += vv.re * vv.re + vv.im * vv.im; }
                     const int mi = s.m_index, early = mi == 0 ? 3 : mi - 1, late = mi == 3 ? 0 : mi + 1;
-                    const int se = sum[early], sl = sum[late], sm = sum[mi];
+                    auto pick4 = [&](int i) { return i == 0 ? sum[0] : i == 1 ? sum[1] : i == 2 ? sum[2] : sum[3]; };
+                    const int se = pick4(early), sl = pick4(late), sm = pick4(mi);
                     if (se < sl) { if (sm < se) { s.m_index++; s.m_frag = 0; } else if (sm < sl) s.m_frag++; }
                     else { if (sm < sl) { s.m_index--; s.m_frag = 0; } else if (sm < se) s.m_frag--; }
                     if (s.m_frag >= 4) { s.m_index++; s.m_frag = -3; } else if (s.m_frag <= -4) { s.m_index--; s.m_frag = 3; }
