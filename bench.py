@@ -188,6 +188,22 @@ def run_reference_arm(args):
             "frames_ok_fraction": okc / float(per_step * args.steps)}
     print(json.dumps(line))
 
+def brick_leg(iq_u, nframes=256, instances=16):
+    """The BRICK path end to end: sora_b200/brick/demo_graph (TMemSamples -> TB200Dot11aRx -> sink, driven like RxThread) over a dump file of
+    `nframes` frames, `instances` graph instances in as many threads (K radios); host samples in, events out, engine shared, windows batched."""
+    import tempfile
+    from sora_b200.dumpfile import write_dump
+    exe = os.path.join(ROOT, "sora_b200", "brick", "demo_graph")
+    if not os.path.exists(exe): subprocess.check_call(["make", "-C", os.path.dirname(exe)], stdout=subprocess.DEVNULL)
+    cap = iq_u[:nframes].reshape(-1, 2); cap = cap[: len(cap) // 28 * 28]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "bench.dmp"); write_dump(p, cap)
+        out = subprocess.run([exe, p, "--threads", str(instances), "--repeat", "2"], capture_output=True, text=True, timeout=600).stdout
+    s = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert s["frames_ok"] == 2 * instances * nframes, s
+    return {"value": s["msamples_per_s"], "unit": "Msamples/s", "frames_per_s": s["frames_per_s"], "graph_instances": instances, "frames_per_capture": nframes,
+            "note": "brick graphs driven like RxThread (fb11a_demod.cpp:29-81); continuous-capture semantics: one frame of every capture per device pass"}
+
 def oracle_gate(eng, torch, iq_u, ps_u, U, res_dev, out_dev, ncores, rank):
     """Every result field and every byte of the U unique slots against the CPU oracle on the same IQ (the remaining slots are copies of these)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -406,6 +422,9 @@ def main():
                          "note": "achieved = 4.154 B/sample x samples per launch / Viterbi kernel time; the chain is integer-ALU/issue bound, not HBM bound (DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e}
     if mgpu: line["mgpu"] = mgpu
+    if world == 1 and not args.no_e2e:
+        try: line["e2e_brick"] = brick_leg(iq_u)
+        except Exception as e: line["e2e_brick"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if not args.no_cpu and world == 1:
         os.sched_setaffinity(0, aff0); ncores, cores_how = effective_cpus()
         variants, best = cpu_baseline(iq_u, ncores)

@@ -27,16 +27,84 @@
 //     one Process() modulates the MPDU in CF_TxFrameBuffer at CF_11aTxVector::data_rate_kbps with CF_ScramblerSeed::sc_seed and pushes
 //     the whole PPDU (preamble + SIGNAL + DATA) downstream as COMPLEX8 x 8 bursts, what TPackSample16to8 hands to TModSink.
 //
-// Batching: the GPU decodes whole capture slots.  The brick buffers incoming 28-sample blocks and submits a slot when
-// `slot_samples` samples have arrived or on Flush(); one graph instance therefore trades latency for throughput.  A
-// throughput-oriented caller uses sb200_rx11a_batch directly with thousands of slots per call.
+// Batching: the GPU decodes windows of samples.  The 802.11a receive brick buffers incoming 28-sample blocks and decodes a window in
+// continuous-capture mode when `SetSlotSamples(n)` new samples have arrived or on Flush(); every frame of the window becomes one event, handed
+// to the driver one per poll, and the samples behind the last event stay for the next window.  All bricks of a process share one engine
+// (B200Engine); B200StreamBatcher decodes the windows of several graph instances (threads) in one device call.  A throughput-oriented caller
+// that owns the capture uses sb200_rx11a_batch / sb200_rx11a_streams directly with thousands of slots per call.
 #pragma once
 #include "facades.hpp"
 #include "../../include/sora_b200.h"
 #include <vector>
+#include <mutex>
+#include <condition_variable>
+#include <chrono>
+#include <cstring>
 #ifndef SB200_BRICK_DEVICE
 #define SB200_BRICK_DEVICE 0      /* CUDA device ordinal the bricks of this translation unit bind to */
 #endif
+
+// ---- one engine per process and device; windows of many graph instances decoded together --------------------------------------------------
+// sb200 handles are thread-compatible, not thread-safe: the shared handle is used under its mutex.  B200StreamBatcher::Decode is what the
+// 802.11a receive brick calls with a window of samples: when `participants` graph instances (threads) are configured, the calls of one round are
+// collected and go to the device as ONE sb200_rx11a_streams call (every pass of it decodes the next frame of all windows at once), so K radios
+// cost K frames per kernel pass instead of one.  A lone caller, or a round that stays incomplete for `wait_us`, is decoded on its own.
+struct B200Engine {
+    sb200_handle* h = nullptr; std::mutex m;
+    static B200Engine& Get(uint32_t cca_pwr_threshold = 0) {
+        static B200Engine e;
+        std::lock_guard<std::mutex> l(e.m);
+        if (!e.h) { sb200_cfg cfg; memset(&cfg, 0, sizeof cfg); cfg.cca_pwr_threshold = cca_pwr_threshold; if (sb200_create(SB200_BRICK_DEVICE, &cfg, &e.h) != SB200_OK) e.h = nullptr; }
+        return e;
+    }
+    ~B200Engine() { sb200_destroy(h); }
+};
+struct B200Event { sb200_frame_result r; uint32_t end_sample; std::vector<uchar> bytes; };
+class B200StreamBatcher {
+    struct Req { const COMPLEX16* p; size_t n; uint32_t max_events; std::vector<B200Event>* out; int rc; bool done, taken; };
+    std::mutex m_; std::condition_variable cv_; std::vector<Req*> pend_; unsigned participants_ = 1; unsigned wait_us_ = 2000; bool running_ = false;
+    std::vector<int16_t> iq_; std::vector<uint64_t> off_; std::vector<uint32_t> len_, sidx_, cnt_; std::vector<sb200_frame_result> res_; std::vector<uchar> bytes_;
+    void Run(std::vector<Req*>& batch) {                  // called without the lock by the thread that closes the round
+        B200Engine& E = B200Engine::Get(); std::lock_guard<std::mutex> le(E.m);
+        uint32_t K = 1; size_t tot = 0;
+        for (Req* q : batch) { if (q->max_events > K) K = q->max_events; tot += q->n; }
+        const uint32_t S = (uint32_t)batch.size(); const uint32_t row = 2560;
+        iq_.resize(2 * tot + 8); off_.resize(S); len_.resize(S); cnt_.assign(S, 0); sidx_.assign((size_t)S * K, 0); res_.resize((size_t)S * K); bytes_.resize((size_t)S * K * row);
+        size_t o = 0;
+        for (uint32_t i = 0; i < S; i++) { memcpy(iq_.data() + 2 * o, batch[i]->p, batch[i]->n * sizeof(COMPLEX16)); off_[i] = o; len_[i] = (uint32_t)batch[i]->n; o += batch[i]->n; }
+        int rc = E.h ? sb200_rx11a_streams(E.h, iq_.data(), tot, off_.data(), len_.data(), S, K, bytes_.data(), row, res_.data(), sidx_.data(), cnt_.data(), nullptr) : SB200_E_NODEVICE;
+        for (uint32_t i = 0; i < S; i++) {
+            Req* q = batch[i]; q->rc = rc; q->out->clear();
+            if (rc == SB200_OK) for (uint32_t k = 0; k < cnt_[i] && k < q->max_events; k++) {
+                B200Event e; e.r = res_[(size_t)i * K + k]; e.end_sample = sidx_[(size_t)i * K + k];
+                const uchar* b = bytes_.data() + ((size_t)i * K + k) * row; e.bytes.assign(b, b + (e.r.length < row ? e.r.length : row));
+                q->out->push_back(std::move(e));
+            }
+        }
+    }
+public:
+    static B200StreamBatcher& Get() { static B200StreamBatcher b; return b; }
+    void Configure(unsigned participants, unsigned wait_us = 2000) { std::lock_guard<std::mutex> l(m_); participants_ = participants ? participants : 1; wait_us_ = wait_us; }
+    int Decode(const COMPLEX16* p, size_t n, uint32_t max_events, std::vector<B200Event>& out) {
+        Req q{p, n, max_events, &out, SB200_OK, false, false};
+        std::unique_lock<std::mutex> l(m_);
+        pend_.push_back(&q);
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(wait_us_);
+        while (!q.done) {
+            const bool late = std::chrono::steady_clock::now() >= deadline;
+            if (!running_ && !q.taken && (pend_.size() >= participants_ || late)) {   // this thread closes the round (complete, or waited long enough) and runs it
+                std::vector<Req*> batch; batch.swap(pend_);
+                for (Req* r : batch) r->taken = true;
+                running_ = true;
+                l.unlock(); Run(batch); l.lock();
+                for (Req* r : batch) r->done = true;
+                running_ = false; cv_.notify_all();
+            } else if (late || q.taken) cv_.wait(l);
+            else cv_.wait_until(l, deadline);
+        }
+        return q.rc;
+    }
+};
 
 DEFINE_LOCAL_CONTEXT(TB200Dot11aRx, CF_Error, CF_11aRxVector, CF_RxFrameBuffer, CF_11CCA, CF_CFOffset);
 template <TFILTER_ARGS>
@@ -46,10 +114,10 @@ class TB200Dot11aRx : public TFilter<TFILTER_PARAMS> {
     CTX_VAR_RO(uchar*, rx_frame_buf) CTX_VAR_RO(uint, rx_frame_buf_size)
     CTX_VAR_RO(uint, cca_pwr_threshold) CTX_VAR_RW(uint, cca_peak_index) CTX_VAR_RW(CF_11CCA::CCAState, cca_state)
     CTX_VAR_RW(short, CFO_est)
-    sb200_handle* h_;
-    std::vector<COMPLEX16> slot_;
-    std::vector<uchar> bytes_;
-    size_t slot_samples_;
+    bool ok_;
+    std::vector<COMPLEX16> buf_;                          // samples received and not yet behind a delivered event
+    std::vector<B200Event> ev_; size_t ev_next_;          // events of the last decoded window, delivered one per Process() / Flush()
+    size_t window_, decoded_upto_; uint32_t max_events_;
 public:
     DEFINE_IPORT(COMPLEX16, 28);
     DEFINE_OPORT(uchar, 1);
@@ -62,47 +130,63 @@ public:
         BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
         BIND_CONTEXT(CF_11CCA::cca_pwr_threshold, cca_pwr_threshold) BIND_CONTEXT(CF_11CCA::cca_peak_index, cca_peak_index)
         BIND_CONTEXT(CF_11CCA::cca_state, cca_state) BIND_CONTEXT(CF_CFOffset::CFO_est, CFO_est)
-        , h_(nullptr), slot_samples_(0)
+        , ok_(false), ev_next_(0), window_(0), decoded_upto_(0), max_events_(64)
     {
-        sb200_cfg cfg; memset(&cfg, 0, sizeof cfg); cfg.cca_pwr_threshold = cca_pwr_threshold;
-        if (sb200_create(SB200_BRICK_DEVICE, &cfg, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }   // no CPU fallback
-        bytes_.resize(4096);
+        ok_ = B200Engine::Get(cca_pwr_threshold).h != nullptr;                                   // no CPU fallback
+        if (!ok_) error_code = E_ERROR_FAILED;
     }
-    ~TB200Dot11aRx() { sb200_destroy(h_); }
-    // capture-slot size in 40 Msps samples; 0 = submit only on Flush() (whole dump file = one slot, like demod11 -d)
-    void SetSlotSamples(size_t n) { slot_samples_ = n; }
+    // decode whenever this many new 40 Msps samples have arrived (0 = only on Flush(): a whole dump file is one window, like demod11 -d);
+    // every window goes through continuous-capture mode, so all of its frames come out, one event per driver poll
+    void SetSlotSamples(size_t n) { window_ = n; }
+    void SetMaxEventsPerWindow(uint32_t k) { max_events_ = k ? k : 1; }
 
-    STD_TFILTER_RESET() { slot_.clear(); }
-    STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) Submit(); }
+    // The driver's Flush(); ctx.Reset(); Reset() after an event (fb11a_demod.cpp:64-72) must not lose what the source already pumped in:
+    // samples behind the delivered event and the events still queued stay.
+    STD_TFILTER_RESET() { }
+    STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) { if (!Deliver() ) return; if (buf_.size() > decoded_upto_ || ev_next_ < ev_.size()) { DecodeWindow(); Deliver(); } } }
 
     BOOL_FUNC_PROCESS(ipin) {
         while (ipin.check_read()) {
             const COMPLEX16* p = ipin.peek();
-            slot_.insert(slot_.end(), p, p + 28);
+            buf_.insert(buf_.end(), p, p + 28);
             ipin.pop();
-            if (slot_samples_ && slot_.size() >= slot_samples_) { if (!Submit()) return false; }
+            if (ev_next_ < ev_.size()) { if (!Deliver()) return false; }
+            else if (window_ && buf_.size() - decoded_upto_ >= window_) { if (!DecodeWindow()) return false; if (!Deliver()) return false; }
         }
         return true;
     }
+    bool EventsPending() const { return ev_next_ < ev_.size(); }
 private:
-    bool Submit() {
-        if (!h_) { error_code = E_ERROR_FAILED; return false; }
-        if (slot_.empty()) return true;
-        uint64_t off = 0; uint32_t len = (uint32_t)slot_.size(); sb200_frame_result r;
-        int rc = sb200_rx11a_batch(h_, (const int16_t*)slot_.data(), slot_.size(), &off, &len, 1, bytes_.data(), (uint32_t)bytes_.size(), &r, nullptr);
-        slot_.clear();
-        if (rc != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
-        if (r.status == SB200_FRAME_NONE) return true;             // nothing detected in this slot: keep sensing
+    bool DecodeWindow() {                                  // all events of buf_ (a frame cut by its end is not an event: it waits for more samples)
+        if (!ok_) { error_code = E_ERROR_FAILED; return false; }
+        ev_.clear(); ev_next_ = 0; decoded_upto_ = buf_.size();
+        if (buf_.size() < 28) return true;
+        if (B200StreamBatcher::Get().Decode(buf_.data(), buf_.size(), max_events_, ev_) != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
+        const size_t keep = 5880 * 28;                     // longer than the longest PPDU (2500 B at 6 Mbps = 3.4 ms = 136 000 samples at 40 Msps)
+        if (ev_.empty() && buf_.size() > keep) {           // nothing in this window: a frame still arriving can only be inside its last `keep` samples
+            const size_t cut = (buf_.size() - keep) / 28 * 28;
+            buf_.erase(buf_.begin(), buf_.begin() + cut); decoded_upto_ -= cut;
+        }
+        return true;
+    }
+    bool Deliver() {                                       // next queued event -> context + output port; false = an event was delivered (stop pumping, PHY_11a.hpp:694)
+        if (ev_next_ >= ev_.size()) return true;
+        const B200Event& e = ev_[ev_next_++]; const sb200_frame_result& r = e.r;
         frame_length = (ushort)r.length; total_symbols = (ushort)r.nsym; data_rate_kbps = r.rate_kbps; frame_crc32 = r.crc32;
         code_rate = (ushort)(r.rate_kbps == 48000 ? CR_23 : (r.rate_kbps == 9000 || r.rate_kbps == 18000 || r.rate_kbps == 36000 || r.rate_kbps == 54000) ? CR_34 : CR_12);
         cca_peak_index = r.peak_index; cca_state = CF_11CCA::power_detected; CFO_est = r.cfo_est;
         if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) {
-            uint n = r.length;
-            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, bytes_.data(), n);
-            for (uint i = 0; i < n; i++) { *opin().append() = bytes_[i]; this->Next()->Process(opin()); }
+            const uint n = (uint)e.bytes.size();
+            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, e.bytes.data(), n);
+            for (uint i = 0; i < n; i++) { *opin().append() = e.bytes[i]; this->Next()->Process(opin()); }
         }
-        error_code = r.status;                                     // the driver polls this after Process() (fb11a_demod.cpp:35)
-        return false;                                              // frame complete: stop pumping (PHY_11a.hpp:694)
+        if (ev_next_ == ev_.size()) {                      // window exhausted: drop the samples up to the end of its last event
+            const size_t cut = e.end_sample < buf_.size() ? e.end_sample : buf_.size();
+            buf_.erase(buf_.begin(), buf_.begin() + cut); decoded_upto_ = decoded_upto_ > cut ? decoded_upto_ - cut : 0;
+            ev_.clear(); ev_next_ = 0;
+        }
+        error_code = r.status;                             // the driver polls this after Process() (fb11a_demod.cpp:35)
+        return false;
     }
 };
 
@@ -114,6 +198,7 @@ class TB200Dot11bRx : public TFilter<TFILTER_PARAMS> {
     CTX_VAR_RW(ushort, frame_length) CTX_VAR_RW(ulong, data_rate_kbps) CTX_VAR_RW(ulong, frame_crc32)
     CTX_VAR_RO(uchar*, rx_frame_buf) CTX_VAR_RO(uint, rx_frame_buf_size)
     sb200_handle* h_; std::vector<COMPLEX16> slot_; std::vector<uchar> bytes_; size_t slot_samples_;
+    std::vector<sb200_frame_result_11b> ev_; size_t ev_next_ = 0;   // events of the last decoded window (continuous-capture mode), one per driver poll
 public:
     DEFINE_IPORT(COMPLEX16, 28);
     DEFINE_OPORT(uchar, 1);
@@ -124,34 +209,47 @@ public:
         BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
         , h_(nullptr), slot_samples_(0)
     {
-        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
-        bytes_.resize(4096);
+        h_ = B200Engine::Get().h; if (!h_) error_code = E_ERROR_FAILED;                 // one engine per process (no CPU fallback)
+        bytes_.resize(16 * 4096);
     }
-    ~TB200Dot11bRx() { sb200_destroy(h_); }
     void SetSlotSamples(size_t n) { slot_samples_ = n; }
-    STD_TFILTER_RESET() { slot_.clear(); }
+    STD_TFILTER_RESET() { }                               // samples behind a delivered event and queued events survive the driver's Reset()
     STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) Submit(); }
+    bool EventsPending() const { return ev_next_ < ev_.size(); }
     BOOL_FUNC_PROCESS(ipin) {
         while (ipin.check_read()) {
             const COMPLEX16* p = ipin.peek(); slot_.insert(slot_.end(), p, p + 28); ipin.pop();
-            if (slot_samples_ && slot_.size() >= slot_samples_) { if (!Submit()) return false; }
+            if (ev_next_ < ev_.size() || (slot_samples_ && slot_.size() >= slot_samples_)) { if (!Submit()) return false; }
         }
         return true;
     }
 private:
     bool Submit() {
         if (!h_) { error_code = E_ERROR_FAILED; return false; }
-        if (slot_.empty()) return true;
-        uint64_t off = 0; uint32_t len = (uint32_t)slot_.size(); sb200_frame_result_11b r;
-        int rc = sb200_rx11b_batch(h_, (const int16_t*)slot_.data(), slot_.size(), &off, &len, 1, bytes_.data(), (uint32_t)bytes_.size(), &r, nullptr);
-        slot_.clear();
-        if (rc != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
-        if (r.status == SB200_FRAME_NONE) return true;
+        if (ev_next_ >= ev_.size()) {                      // decode the window: every event MAC11b_Receive would meet in it (fb11b_demod.cpp:26-75)
+            if (slot_.empty()) return true;
+            const uint32_t K = 16; uint64_t off = 0; uint32_t len = (uint32_t)slot_.size(), n = 0;
+            ev_.assign(K, sb200_frame_result_11b()); ev_next_ = 0;
+            int rc;
+            { std::lock_guard<std::mutex> engine_lock(B200Engine::Get().m);
+              rc = sb200_rx11b_streams(h_, (const int16_t*)slot_.data(), slot_.size(), &off, &len, 1, K, bytes_.data(), 4096, ev_.data(), &n, nullptr); }
+            if (rc != SB200_OK) { ev_.clear(); error_code = E_ERROR_FAILED; return false; }
+            ev_.resize(n);
+            if (n == 0) { slot_.clear(); return true; }            // nothing detected in this window: keep sensing
+        }
+        const size_t k = ev_next_++; const sb200_frame_result_11b r = ev_[k];
         frame_length = (ushort)r.length; data_rate_kbps = r.rate_kbps; frame_crc32 = r.crc32;
         if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) {
             const uint n = r.length ? r.length - 1 : 0;            // TBB11bFrameSink decides on the third FCS byte (PHY_11b.hpp:728-739)
-            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, bytes_.data(), n);
-            for (uint i = 0; i < n; i++) { *opin().append() = bytes_[i]; this->Next()->Process(opin()); }
+            const uchar* b = bytes_.data() + k * 4096;
+            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, b, n);
+            for (uint i = 0; i < n; i++) { *opin().append() = b[i]; this->Next()->Process(opin()); }
+        }
+        if (ev_next_ == ev_.size()) {                      // window exhausted: what lies behind its last event waits for the next one
+            size_t cut = r.sample_index;                   // + the driver's seek past the last FCS byte after a frame (fb11b_demod.cpp:43-61)
+            if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) cut += r.rate_kbps == 1000 ? 352u : r.rate_kbps == 2000 ? 176u : r.rate_kbps == 5500 ? 64u : 32u;
+            if (cut > slot_.size()) cut = slot_.size();
+            slot_.erase(slot_.begin(), slot_.begin() + cut); ev_.clear(); ev_next_ = 0;
         }
         error_code = r.status;
         return false;
@@ -167,6 +265,7 @@ class TB200Dot11nRx : public TFilter<TFILTER_PARAMS> {
     CTX_VAR_RO(uchar*, rx_frame_buf) CTX_VAR_RO(uint, rx_frame_buf_size)
     CTX_VAR_RW(short, CFO_est)
     sb200_handle* h_; std::vector<COMPLEX16> slot_[2]; std::vector<uchar> bytes_; size_t slot_samples_;
+    std::vector<sb200_frame_result_11n> ev_; std::vector<uint32_t> ev_end_; size_t ev_next_ = 0;   // events of the last decoded window, one per driver poll
 public:
     static const size_t NSTREAM = 2;
     DEFINE_IPORT(COMPLEX16, 28, NSTREAM);
@@ -181,38 +280,48 @@ public:
         BIND_CONTEXT(CF_CFOffset::CFO_est, CFO_est)
         , h_(nullptr), slot_samples_(0)
     {
-        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
-        bytes_.resize(2048);
+        h_ = B200Engine::Get().h; if (!h_) error_code = E_ERROR_FAILED;                 // one engine per process (no CPU fallback)
+        bytes_.resize(16 * 2048);
     }
-    ~TB200Dot11nRx() { sb200_destroy(h_); }
     void SetSlotSamples(size_t n) { slot_samples_ = n; }
-    STD_TFILTER_RESET() { slot_[0].clear(); slot_[1].clear(); }
+    STD_TFILTER_RESET() { }                               // samples behind a delivered event and queued events survive the driver's Reset()
     STD_TFILTER_FLUSH() { if (error_code == E_ERROR_SUCCESS) Submit(); }
+    bool EventsPending() const { return ev_next_ < ev_.size(); }
     BOOL_FUNC_PROCESS(ipin) {
         while (ipin.check_read()) {
             for (size_t s = 0; s < NSTREAM; s++) { const COMPLEX16* p = ipin.peek(s); slot_[s].insert(slot_[s].end(), p, p + 28); }
             ipin.pop();
-            if (slot_samples_ && slot_[0].size() >= slot_samples_) { if (!Submit()) return false; }
+            if (ev_next_ < ev_.size() || (slot_samples_ && slot_[0].size() >= slot_samples_)) { if (!Submit()) return false; }
         }
         return true;
     }
 private:
     bool Submit() {
         if (!h_) { error_code = E_ERROR_FAILED; return false; }
-        if (slot_[0].empty()) return true;
-        uint64_t off = 0; uint32_t len = (uint32_t)slot_[0].size(); sb200_frame_result_11n r;
-        int rc = sb200_rx11n_batch(h_, (const int16_t*)slot_[0].data(), (const int16_t*)slot_[1].data(), slot_[0].size(), &off, &len, 1,
-                                   bytes_.data(), (uint32_t)bytes_.size(), &r, nullptr);
-        slot_[0].clear(); slot_[1].clear();
-        if (rc != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
-        if (r.status == SB200_FRAME_NONE) return true;
+        if (ev_next_ >= ev_.size()) {                      // decode the window in continuous-capture mode (fb11n_demod.cpp:29-81)
+            if (slot_[0].empty()) return true;
+            const uint32_t K = 16; uint64_t off = 0; uint32_t len = (uint32_t)slot_[0].size(), n = 0;
+            ev_.assign(K, sb200_frame_result_11n()); ev_end_.assign(K, 0); ev_next_ = 0;
+            int rc;
+            { std::lock_guard<std::mutex> engine_lock(B200Engine::Get().m);
+              rc = sb200_rx11n_streams(h_, (const int16_t*)slot_[0].data(), (const int16_t*)slot_[1].data(), slot_[0].size(), &off, &len, 1, K,
+                                       bytes_.data(), 2048, ev_.data(), ev_end_.data(), &n, nullptr); }
+            if (rc != SB200_OK) { ev_.clear(); error_code = E_ERROR_FAILED; return false; }
+            ev_.resize(n);
+            if (n == 0) { slot_[0].clear(); slot_[1].clear(); return true; }
+        }
+        const size_t k = ev_next_++; const sb200_frame_result_11n r = ev_[k];
         frame_length = (ushort)r.length; total_symbols = (ushort)r.nsym; frame_crc32 = r.crc32; CFO_est = r.cfo_est;
         ht_frame_mcs = r.mcs; ht_frame_length = (ushort)(r.nsym ? r.length : 0);
         code_rate = (ushort)(r.mcs == 10 ? CR_34 : CR_12);
         if (r.status == SB200_FRAME_OK || r.status == SB200_FRAME_CRC32_FAIL) {
-            const uint n = r.length;
-            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, bytes_.data(), n);
-            for (uint i = 0; i < n; i++) { *opin().append() = bytes_[i]; this->Next()->Process(opin()); }
+            const uint n = r.length; const uchar* b = bytes_.data() + k * 2048;
+            if (rx_frame_buf && n <= rx_frame_buf_size) memcpy(rx_frame_buf, b, n);
+            for (uint i = 0; i < n; i++) { *opin().append() = b[i]; this->Next()->Process(opin()); }
+        }
+        if (ev_next_ == ev_.size()) {
+            const size_t cut = ev_end_[k] < slot_[0].size() ? ev_end_[k] : slot_[0].size();
+            slot_[0].erase(slot_[0].begin(), slot_[0].begin() + cut); slot_[1].erase(slot_[1].begin(), slot_[1].begin() + cut); ev_.clear(); ev_next_ = 0;
         }
         error_code = r.status;
         return false;
@@ -239,13 +348,13 @@ public:
         BIND_CONTEXT(CF_ScramblerSeed::sc_seed, sc_seed)
         , h_(nullptr)
     {
-        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+        h_ = B200Engine::Get().h; if (!h_) error_code = E_ERROR_FAILED;                 // one engine per process (no CPU fallback)
     }
-    ~TB200Dot11aTx() { sb200_destroy(h_); }
     STD_TSOURCE_RESET() { }
     STD_TSOURCE_FLUSH() { }
     bool Process() override {
         if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        std::lock_guard<std::mutex> engine_lock(B200Engine::Get().m);
         if (!mpdu_buf0 || (mpdu_buf_size1 > 0 && !mpdu_buf1) || (uint)mpdu_buf_size0 + mpdu_buf_size1 != frame_length) { error_code = E_ERROR_PARAMETER; return false; }   // TBB11aSrc::Preprocess
         mpdu_.assign(mpdu_buf0, mpdu_buf0 + mpdu_buf_size0); if (mpdu_buf_size1) mpdu_.insert(mpdu_.end(), mpdu_buf1, mpdu_buf1 + mpdu_buf_size1);
         const uint64_t off = 0; const uint32_t len = frame_length; uint32_t ns = 0; const uchar seed = sc_seed;
@@ -281,13 +390,13 @@ public:
         BIND_CONTEXT(CF_DifferentialMap::last_phase, last_phase)
         , h_(nullptr)
     {
-        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+        h_ = B200Engine::Get().h; if (!h_) error_code = E_ERROR_FAILED;                 // one engine per process (no CPU fallback)
     }
-    ~TB200Dot11bTx() { sb200_destroy(h_); }
     STD_TSOURCE_RESET() { }
     STD_TSOURCE_FLUSH() { }
     bool Process() override {
         if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        std::lock_guard<std::mutex> engine_lock(B200Engine::Get().m);
         error_code = E_ERROR_SUCCESS;
         if (!mpdu_buf0 || (mpdu_buf_size1 > 0 && !mpdu_buf1) || (uint)mpdu_buf_size0 + mpdu_buf_size1 != frame_length) { error_code = E_ERROR_PARAMETER; return false; }   // TBB11bSrc::Preprocess
         const ulong rate = data_rate_kbps;
@@ -330,13 +439,13 @@ public:
         BIND_CONTEXT(CF_ScramblerSeed::sc_seed, sc_seed)
         , h_(nullptr)
     {
-        if (sb200_create(SB200_BRICK_DEVICE, nullptr, &h_) != SB200_OK) { h_ = nullptr; error_code = E_ERROR_FAILED; }
+        h_ = B200Engine::Get().h; if (!h_) error_code = E_ERROR_FAILED;                 // one engine per process (no CPU fallback)
     }
-    ~TB200Dot11nTx() { sb200_destroy(h_); }
     STD_TSOURCE_RESET() { }
     STD_TSOURCE_FLUSH() { }
     bool Process() override {
         if (!h_) { error_code = E_ERROR_FAILED; return false; }
+        std::lock_guard<std::mutex> engine_lock(B200Engine::Get().m);
         error_code = E_ERROR_SUCCESS;
         if (!mpdu_buf0 || (mpdu_buf_size1 > 0 && !mpdu_buf1) || (uint)mpdu_buf_size0 + mpdu_buf_size1 != frame_length) { error_code = E_ERROR_PARAMETER; return false; }   // TBB11nSrc::Preprocess
         mpdu_.assign(mpdu_buf0, mpdu_buf0 + mpdu_buf_size0); if (mpdu_buf_size1) mpdu_.insert(mpdu_.end(), mpdu_buf1, mpdu_buf1 + mpdu_buf_size1);

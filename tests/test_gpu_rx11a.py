@@ -156,6 +156,33 @@ def test_brick_adaptor_graph(eng):
     assert ev and ev[0]["error_code"] == "0x00000001" and ev[0]["rate_kbps"] == 6000 and ev[0]["length"] == 1392
     assert ev[0]["crc32"] == "0x80EF9B11" and ev[0]["bytes_out"] == 1392
 
+def test_brick_adaptor_finds_every_frame_of_a_capture(tmp_path):
+    """A dump file with several frames (one damaged, one with a broken SIGNAL) through the brick graph of demo_graph.cpp driven like RxThread:
+    the adaptor decodes the window in continuous-capture mode and hands the driver one event per poll — the same events, in the same order,
+    with the same fields as the CPU oracle's RxThread run.  Then 6 graph instances in 6 threads: their windows are decoded together."""
+    import subprocess, json
+    from sora_b200.dumpfile import write_dump
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sora_b200", "brick", "demo_graph")
+    if not os.path.exists(exe): subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    cap = _mixed_stream(21)
+    cap = cap[: len(cap) // 28 * 28]
+    p = tmp_path / "multi.dmp"; write_dump(str(p), cap)
+    ores, _ = oracle_py.rx11a_run(cap, max_frames=32, out_stride=2560)
+    for extra in ([], ["--window", "20000"]):
+        out = subprocess.run([exe, str(p)] + extra, capture_output=True, text=True, timeout=120).stdout
+        ev = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+        if not extra:                                   # one window = the whole file: exactly RxThread's event list
+            assert len(ev) == len(ores) >= 6
+            for e, o in zip(ev, ores):
+                assert int(e["error_code"], 16) == int(o["status"]) and e["rate_kbps"] == o["rate_kbps"] and e["length"] == o["length"]
+        else:                                           # windowed: the carrier sense restarts at window cuts, every good frame is still found
+            good = [o for o in ores if o["status"] == 1]
+            assert [e["length"] for e in ev if int(e["error_code"], 16) == 1] == [int(o["length"]) for o in good]
+    out = subprocess.run([exe, str(p), "--threads", "6"], capture_output=True, text=True, timeout=180).stdout
+    summ = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert summ["graph_instances"] == 6 and summ["events"] == 6 * len(ores) and summ["frames_ok"] == 6 * int((ores["status"] == 1).sum())
+
 def test_chunked_pipeline_host_and_device(eng):
     """Large calls are cut into chunks pipelined over three streams (copy | front end | Viterbi): same results."""
     import torch
