@@ -117,7 +117,7 @@ class TB200Dot11aRx : public TFilter<TFILTER_PARAMS> {
     bool ok_;
     std::vector<COMPLEX16> buf_;                          // samples received and not yet behind a delivered event
     std::vector<B200Event> ev_; size_t ev_next_;          // events of the last decoded window, delivered one per Process() / Flush()
-    size_t window_, decoded_upto_; uint32_t max_events_;
+    size_t window_, decoded_upto_; uint32_t max_events_; bool truncated_;   // truncated_: the last window filled its event list, more may follow
 public:
     DEFINE_IPORT(COMPLEX16, 28);
     DEFINE_OPORT(uchar, 1);
@@ -130,7 +130,7 @@ public:
         BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
         BIND_CONTEXT(CF_11CCA::cca_pwr_threshold, cca_pwr_threshold) BIND_CONTEXT(CF_11CCA::cca_peak_index, cca_peak_index)
         BIND_CONTEXT(CF_11CCA::cca_state, cca_state) BIND_CONTEXT(CF_CFOffset::CFO_est, CFO_est)
-        , ok_(false), ev_next_(0), window_(0), decoded_upto_(0), max_events_(64)
+        , ok_(false), ev_next_(0), window_(0), decoded_upto_(0), max_events_(64), truncated_(false)
     {
         ok_ = B200Engine::Get(cca_pwr_threshold).h != nullptr;                                   // no CPU fallback
         if (!ok_) error_code = E_ERROR_FAILED;
@@ -151,7 +151,7 @@ public:
             buf_.insert(buf_.end(), p, p + 28);
             ipin.pop();
             if (ev_next_ < ev_.size()) { if (!Deliver()) return false; }
-            else if (window_ && buf_.size() - decoded_upto_ >= window_) { if (!DecodeWindow()) return false; if (!Deliver()) return false; }
+            else if ((window_ && buf_.size() - decoded_upto_ >= window_) || (truncated_ && decoded_upto_ == 0 && buf_.size() >= 28)) { if (!DecodeWindow()) return false; if (!Deliver()) return false; }
         }
         return true;
     }
@@ -162,6 +162,7 @@ private:
         ev_.clear(); ev_next_ = 0; decoded_upto_ = buf_.size();
         if (buf_.size() < 28) return true;
         if (B200StreamBatcher::Get().Decode(buf_.data(), buf_.size(), max_events_, ev_) != SB200_OK) { error_code = E_ERROR_FAILED; return false; }
+        truncated_ = ev_.size() >= max_events_;
         const size_t keep = 5880 * 28;                     // longer than the longest PPDU (2500 B at 6 Mbps = 3.4 ms = 136 000 samples at 40 Msps)
         if (ev_.empty() && buf_.size() > keep) {           // nothing in this window: a frame still arriving can only be inside its last `keep` samples
             const size_t cut = (buf_.size() - keep) / 28 * 28;
@@ -182,7 +183,7 @@ private:
         }
         if (ev_next_ == ev_.size()) {                      // window exhausted: drop the samples up to the end of its last event
             const size_t cut = e.end_sample < buf_.size() ? e.end_sample : buf_.size();
-            buf_.erase(buf_.begin(), buf_.begin() + cut); decoded_upto_ = decoded_upto_ > cut ? decoded_upto_ - cut : 0;
+            buf_.erase(buf_.begin(), buf_.begin() + cut); decoded_upto_ = truncated_ ? 0 : (decoded_upto_ > cut ? decoded_upto_ - cut : 0);   // a full event list: the rest is not scanned yet
             ev_.clear(); ev_next_ = 0;
         }
         error_code = r.status;                             // the driver polls this after Process() (fb11a_demod.cpp:35)
