@@ -14,8 +14,9 @@ static inline c16 csra(c16 a, int n) { return c16{w16(a.re >> n), w16(a.im >> n)
 static inline int cnorm2(c16 a) { return a.re * a.re + a.im * a.im; }
 
 static uint16_t g_crc16_lut[256];
-static void build_crc16() {                 // CCITT CRC-16 reflected (0x8408), core/inc/CRC16.h:37-48
+static bool build_crc16() {                 // CCITT CRC-16 reflected (0x8408), core/inc/CRC16.h:37-48
     for (unsigned i = 0; i < 256; i++) { unsigned c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0x8408u ^ (c >> 1) : c >> 1; g_crc16_lut[i] = (uint16_t)c; }
+    return true;
 }
 static uint16_t crc16(const uint8_t* p, unsigned n) {
     uint16_t c = 0xFFFF;
@@ -23,7 +24,7 @@ static uint16_t crc16(const uint8_t* p, unsigned n) {
     return (uint16_t)~c;
 }
 
-Rx11b::Rx11b() { tables(); if (!g_crc16_lut[1]) build_crc16(); init(); }
+Rx11b::Rx11b() { tables(); static const bool crc_ready = build_crc16(); (void)crc_ready; init(); }
 
 void Rx11b::bricks_reset() {               // every brick's Reset(): queues cleared, local state re-initialised
     // TEnergyDetect (cca.hpp:35-40)

@@ -71,10 +71,11 @@ Tables::Tables() {
     // (brick/inc/sequence.h:5-33, cca.hpp:266-276).  tw tables above must be ready first.
 }
 
-static Tables* g_tables = nullptr;
 static void build_sts(Tables& t);
-const Tables& tables() {
-    if (!g_tables) { Tables* t = new Tables(); g_tables = t; build_sts(*t); }
+static thread_local const Tables* tl_building = nullptr;   // build_sts() runs the IFFT, which asks for the (twiddle) tables: only the building thread sees them early
+const Tables& tables() {   // a function-local static: built once, and complete before any other batch thread can see it
+    if (tl_building) return *tl_building;
+    static const Tables* g_tables = [] { Tables* t = new Tables(); tl_building = t; build_sts(*t); tl_building = nullptr; return t; }();
     return *g_tables;
 }
 

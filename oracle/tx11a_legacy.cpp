@@ -129,9 +129,9 @@ size_t tx11a_legacy_modulate(const uint8_t* mpdu, uint32_t len, int append_crc, 
     const int ncbps = 48 * ri->nbpsc;
     coded.resize((size_t)nsym * ncbps + 8, 0);
     const Tables& TT = tables(); (void)TT;
-    static uint8_t pneg[127]; static bool have = false;
-    if (!have) { unsigned st = 0x7F; uint8_t seq[127]; for (int i = 0; i < 127; i++) { unsigned o = ((st >> 6) ^ (st >> 3)) & 1; st = ((st << 1) | o) & 0x7F; seq[i] = (uint8_t)o; }
-                 for (int i = 0; i < 127; i++) pneg[i] = seq[(i + 1) % 127]; have = true; }      // lutst/pilotsgn.c: entry i = p_{i+1}
+    static uint8_t pneg[127];
+    static const bool have = [] { unsigned st = 0x7F; uint8_t seq[127]; for (int i = 0; i < 127; i++) { unsigned o = ((st >> 6) ^ (st >> 3)) & 1; st = ((st << 1) | o) & 0x7F; seq[i] = (uint8_t)o; }
+                 for (int i = 0; i < 127; i++) pneg[i] = seq[(i + 1) % 127]; return true; }(); (void)have;      // lutst/pilotsgn.c: entry i = p_{i+1}
     unsigned pi = 0;
     for (uint32_t s = 0; s < nsym; s++) {
         tx.symbol(coded.data() + (size_t)s * ncbps, ri->nbpsc, pneg[pi] != 0, out + 2 * (640 + 160 * (size_t)(1 + s)));

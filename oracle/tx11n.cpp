@@ -35,10 +35,10 @@ int ht_interleave_pos(int k, int ncbps, int nbpsc, int iss /*1, 2*/) {
     return (ncbps + j - (((iss - 1) * 2) % 3 + 3 * ((iss - 1) / 3)) * nrot * nbpsc) % ncbps;
 }
 const uint8_t* pilot_neg() {                                            // _b_dot11_pilot.h:40-46 == pilot.hpp:10-28: entry i is p(i+1) of the 127-periodic polarity sequence
-    static uint8_t t[128]; static bool done = false;
-    if (!done) { unsigned st = 0x7F; uint8_t seq[127]; for (int i = 0; i < 127; i++) { unsigned o = ((st >> 6) ^ (st >> 3)) & 1; st = ((st << 1) | o) & 0x7F; seq[i] = (uint8_t)o; }
-                 for (int i = 0; i < 127; i++) t[i] = seq[(i + 1) % 127]; t[127] = 0; done = true; }
-    return t;
+    static uint8_t t[128];
+    static const bool done = [] { unsigned st = 0x7F; uint8_t seq[127]; for (int i = 0; i < 127; i++) { unsigned o = ((st >> 6) ^ (st >> 3)) & 1; st = ((st << 1) | o) & 0x7F; seq[i] = (uint8_t)o; }
+                 for (int i = 0; i < 127; i++) t[i] = seq[(i + 1) % 127]; t[127] = 0; return true; }();
+    (void)done; return t;
 }
 // TIFFTxOnly (fft.hpp:62-101): zero-stuffed IFFT<128>, no scaling; TAddGI (gi.hpp:32-41): last 32 samples in front.  csd_vec = TCSD<n>
 void ifft_gi(const c16* f64, int csd_vec, c16* out160) {

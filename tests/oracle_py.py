@@ -19,8 +19,14 @@ def lib():
     if _LIB is None:
         so = os.path.join(ROOT, "oracle", "libsora_oracle.so")
         srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle")) if f.endswith((".cpp", ".h", ".inc"))]
-        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        stale = lambda: not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+        if stale():                                     # several ranks / test workers may get here at once: one builds, the others wait for it
+            import fcntl
+            with open(os.path.join(ROOT, "oracle", ".build.lock"), "w") as lk:
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                try:
+                    if stale(): subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                finally: fcntl.flock(lk, fcntl.LOCK_UN)
         _LIB = C.CDLL(so)
         _LIB.sbo_viterbi_block.restype = C.c_uint64
         _LIB.sbo_uatan2.restype = C.c_int16; _LIB.sbo_usin.restype = C.c_int16; _LIB.sbo_ucos.restype = C.c_int16
