@@ -202,7 +202,7 @@ def brick_leg(iq_u, nframes=256, instances=16):
     s = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     assert s["frames_ok"] == 2 * instances * nframes, s
     return {"value": s["msamples_per_s"], "unit": "Msamples/s", "frames_per_s": s["frames_per_s"], "graph_instances": instances, "frames_per_capture": nframes,
-            "note": "brick graphs driven like RxThread (fb11a_demod.cpp:29-81); continuous-capture semantics: one frame of every capture per device pass"}
+            "note": "brick graphs driven like RxThread (fb11a_demod.cpp:29-81); continuous-capture semantics (every frame search starts where the previous event ended): a header-only scout pass per event, then all frames of all graphs in one batch"}
 
 def oracle_gate(eng, torch, iq_u, ps_u, U, res_dev, out_dev, ncores, rank):
     """Every result field and every byte of the U unique slots against the CPU oracle on the same IQ (the remaining slots are copies of these)."""

@@ -241,6 +241,7 @@ __device__ __forceinline__ uint32_t warp_viterbi_signal(const uint8_t* soft, int
 // ------------------------------------------------------------------------------------------------
 struct FrontTaps {            // optional stage taps (device pointers, nullptr = off); per slot, per symbol, 64 packed c16
     uint32_t* freq_coeffs; uint32_t* chan_coeffs; uint32_t* fft_out; uint32_t* equalized; uint32_t* tracked; uint32_t max_sym;
+    uint32_t hdr_only;        // stop after SIGNAL: status = E_SUCCESS (all symbols of the frame lie in the slot) / E_NO_FRAME (they do not) / E_PLCP_HEADER_FAIL
 };
 
 __device__ __forceinline__ int data_index(int bin) {   // demapper11a.hpp:22-36 subcarrier order; -1 for non-data bins
@@ -450,6 +451,10 @@ __global__ void __launch_bounds__(32 * SB_FRONT_WARPS, SB_FRONT_MINB) k_front11a
     if (more) {
         cs16 v[4]; load4(s0 + 144u + 8u, v); fft_from_regs(v[0], v[1], v[2], v[3]);
         more = post_fft(0, 0);
+    }
+    if (taps.hdr_only && more) {                                          // continuous-capture scout pass: where the frame ends is all the caller wants
+        if (!sym_ready(fi.nsym_total - 1u)) status = E_NO_FRAME;
+        more = false;
     }
     // ---- staging of the DATA symbols (see STAGE above) ----
     const uint32_t nsamp20 = nvec * 4u;                                   // 20 Msps samples of the slot that may be read

@@ -51,6 +51,35 @@ __global__ void k_pack_results(const FrameInfo* __restrict__ info, const uint32_
     res[i] = r;
 }
 
+// Continuous-capture scout (sb200_rx11a_streams): after a header-only pass, move every live capture past the event it just found the way
+// RxThread does (fb11a_demod.cpp:29-81: the driver sees the event after the source block that completed the last symbol, flushes, resets, and
+// the source continues with the next 28-sample block; only CF_VecDC survives), and note the event as a slot for the batched decode that follows.
+struct StreamEvent { uint64_t off; uint32_t len; uint32_t pos_after; int2 dc; };
+__global__ void k_stream_advance(const FrameInfo* __restrict__ info, uint32_t n, uint64_t* __restrict__ off_cur, uint32_t* __restrict__ len_cur,
+                                 int2* __restrict__ dc_cur, uint32_t* __restrict__ pos_cur, uint32_t* __restrict__ nev, uint32_t max_frames,
+                                 StreamEvent* __restrict__ ev, uint32_t* __restrict__ live) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t rem = len_cur[s];
+    if (rem < 28u) return;                                   // finished earlier
+    const FrameInfo fi = info[s];
+    if (fi.status != E_SUCCESS && fi.status != E_PLCP_HEADER_FAIL) { len_cur[s] = 0; return; }     // ran out of samples: RxThread returns
+    const uint32_t consumed = fi.status == E_PLCP_HEADER_FAIL ? 1u : fi.nsym_total;                 // OFDM symbols that went through the graph
+    const uint64_t e20 = (uint64_t)fi.detect_vec * 4ull + 144ull + 80ull * consumed;               // 20 Msps samples up to the end of the last symbol
+    const uint64_t v_last = e20 / 4ull - 1ull, blk = (8ull * v_last + 7ull) / 28ull;
+    uint64_t adv = (blk + 1ull) * 28ull; if (adv > rem) adv = rem;
+    const uint32_t j = nev[s];
+    StreamEvent e; e.off = off_cur[s]; e.len = (uint32_t)adv; e.pos_after = pos_cur[s] + (uint32_t)adv; e.dc = dc_cur[s];
+    ev[(size_t)s * max_frames + j] = e;
+    nev[s] = j + 1u;
+    dc_cur[s] = make_int2(fi.dc_re, fi.dc_im);
+    off_cur[s] += adv; pos_cur[s] += (uint32_t)adv;
+    const uint32_t left = rem - (uint32_t)adv;
+    const bool go_on = j + 1u < max_frames && left >= 28u;
+    len_cur[s] = go_on ? left : 0u;
+    if (go_on) atomicAdd(live, 1u);
+}
+
 // max(len) and an out-of-bounds flag over a device-resident slot table: res[0] = max frame_len, res[1] != 0 if any slot leaves [0, iq_total)
 __global__ void k_slot_check(const uint64_t* __restrict__ off, const uint32_t* __restrict__ len, uint32_t n, uint64_t iq_total, uint32_t* __restrict__ res) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +169,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
+    DevBuf soff, slen, spos, snev, sev;                // continuous-capture scout: current slot of every capture, position, event count, event list
     DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx, tabtx11n, txout1; DevTablesTx11n XN{};   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
     std::vector<uint64_t> offh; std::vector<uint32_t> lenh;   // host copy of the slot table (cached for device-resident tables)
@@ -233,7 +263,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4], &h->vlist, &h->vcnt, &h->slotchk, &h->doff};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->soff.release(); h->slen.release(); h->spos.release(); h->snev.release(); h->sev.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -513,40 +543,60 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
     if (nstreams == 0 || max_frames == 0) return SB200_OK;
     const int16_t* d_iq = iq;
     if (!is_device_ptr(iq)) { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const int16_t*)h->iq.p; }
-    std::vector<uint64_t> pos(nstreams, 0); std::vector<int2> dc(nstreams, make_int2(0, 0));
-    std::vector<uint32_t> active(nstreams); for (uint32_t s = 0; s < nstreams; s++) active[s] = s;
-    std::vector<uint64_t> off; std::vector<uint32_t> len; std::vector<int2> dcv; std::vector<sb200_frame_result> r; std::vector<FrameInfo> fi; std::vector<uint8_t> bytes;
-    const uint32_t row = out_bytes ? (out_stride < 2560u ? out_stride : 2560u) : 0u;
-    int rc = SB200_OK;
-    while (!active.empty()) {
-        std::vector<uint32_t> live;
-        for (uint32_t s : active) if (nframes_out[s] < max_frames && pos[s] + 28 <= stream_len[s]) live.push_back(s);
-        if (live.empty()) break;
-        const uint32_t n = (uint32_t)live.size();
-        off.resize(n); len.resize(n); dcv.resize(n); r.resize(n); fi.resize(n); if (row) bytes.resize((size_t)n * row);
-        for (uint32_t j = 0; j < n; j++) { const uint32_t s = live[j]; off[j] = stream_off[s] + pos[s]; len[j] = (uint32_t)(stream_len[s] - pos[s]); dcv[j] = dc[s]; }
-        CK(h->dcbuf.need(n * sizeof(int2))); CK(cudaMemcpyAsync(h->dcbuf.p, dcv.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
-        FrontTaps taps{};
-        rc = rx11a_run(h, d_iq, iq_total, off.data(), len.data(), n, row ? bytes.data() : nullptr, row, r.data(), st, taps, nullptr, 0, (const int2*)h->dcbuf.p, true);
-        if (rc != SB200_OK) break;
-        CK(cudaMemcpy(fi.data(), h->info.p, n * sizeof(FrameInfo), cudaMemcpyDeviceToHost));
-        active.clear();
-        for (uint32_t j = 0; j < n; j++) {
-            const uint32_t s = live[j];
-            if (r[j].status == SB200_FRAME_NONE) continue;                               // this capture ran out of samples: RxThread returns
-            dc[s] = make_int2(fi[j].dc_re, fi[j].dc_im);
-            const uint32_t consumed = r[j].status == SB200_FRAME_PLCP_FAIL ? 1u : r[j].nsym;     // OFDM symbols that went through the graph
-            const uint64_t e20 = (uint64_t)r[j].detect_index + 144ull + 80ull * consumed;     // 20 Msps samples up to the end of the last symbol
-            const uint64_t v_last = e20 / 4ull - 1ull, blk = (8ull * v_last + 7ull) / 28ull;
-            pos[s] += (blk + 1ull) * 28ull;                                                   // the driver sees the event after that source block
-            const size_t slot = (size_t)s * max_frames + nframes_out[s];
-            res[slot] = r[j];
-            if (sample_index) sample_index[slot] = (uint32_t)pos[s];
-            if (row) memcpy(out_bytes + slot * out_stride, bytes.data() + (size_t)j * row, row);
-            nframes_out[s]++;
-            active.push_back(s);
+    // Phase 1, scout: carrier sense + SIGNAL only, one pass per event of the busiest capture; positions, DC estimates and the event list stay on
+    // the device, the host only reads a "captures still live" counter every few passes.  Where a frame ends depends on its header alone, so the
+    // expensive part (data symbols, Viterbi) need not sit inside this serial chain.
+    const uint32_t n = nstreams;
+    std::vector<uint64_t> off0(n); std::vector<uint32_t> len0(n);
+    for (uint32_t s = 0; s < n; s++) { off0[s] = stream_off[s]; len0[s] = stream_len[s] >= 28u ? stream_len[s] : 0u; }
+    CK(h->soff.need(n * 8ull)); CK(h->slen.need(n * 4ull)); CK(h->dcbuf.need(n * sizeof(int2))); CK(h->spos.need(n * 4ull)); CK(h->snev.need(n * 4ull + 64));
+    CK(h->sev.need((size_t)n * max_frames * sizeof(StreamEvent))); CK(h->info.need(n * sizeof(FrameInfo)));
+    CK(cudaMemcpyAsync(h->soff.p, off0.data(), n * 8ull, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->slen.p, len0.data(), n * 4ull, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->dcbuf.p, 0, n * sizeof(int2), st)); CK(cudaMemsetAsync(h->spos.p, 0, n * 4ull, st)); CK(cudaMemsetAsync(h->snev.p, 0, n * 4ull + 64, st));
+    uint32_t* d_live = (uint32_t*)h->snev.p + n;                      // one counter per pass of a round (<= 16)
+    FrontTaps hdr{}; hdr.hdr_only = 1;
+    const uint32_t ROUND = 8;
+    for (uint32_t done_passes = 0; done_passes < max_frames;) {
+        CK(cudaMemsetAsync(d_live, 0, ROUND * 4ull, st));
+        uint32_t k = 0;
+        for (; k < ROUND && done_passes + k < max_frames; k++) {
+            k_sync11a<<<(n + 127) / 128, 128, 0, st>>>((const uint32_t*)d_iq, (const uint64_t*)h->soff.p, (const uint32_t*)h->slen.p, n, h->cca_thr, h->T, (FrameInfo*)h->info.p, (const int2*)h->dcbuf.p, 1u, 0u);
+            k_front11a<0><<<(n + SB_FRONT_WARPS - 1) / SB_FRONT_WARPS, 32 * SB_FRONT_WARPS, 0, st>>>((const uint32_t*)d_iq, (const uint64_t*)h->soff.p, (const uint32_t*)h->slen.p, n, h->T, (FrameInfo*)h->info.p, nullptr, 0, h->inv_deint, hdr, 1u, 0u);
+            k_stream_advance<<<(n + 127) / 128, 128, 0, st>>>((const FrameInfo*)h->info.p, n, (uint64_t*)h->soff.p, (uint32_t*)h->slen.p, (int2*)h->dcbuf.p, (uint32_t*)h->spos.p, (uint32_t*)h->snev.p, max_frames, (StreamEvent*)h->sev.p, d_live + k);
+            h->launches += 3;
         }
+        CK(cudaGetLastError());
+        uint32_t live[16]; CK(cudaMemcpyAsync(live, d_live, ROUND * 4ull, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        done_passes += k;
+        if (live[k - 1] == 0) break;
     }
+    // Phase 2: every event is an independent slot (start of the search, length up to the block after its last symbol, the DC estimate the search
+    // started with): one batch through the ordinary pipeline.
+    std::vector<uint32_t> nev(n); CK(cudaMemcpy(nev.data(), h->snev.p, n * 4ull, cudaMemcpyDeviceToHost));
+    size_t E = 0; for (uint32_t s = 0; s < n; s++) E += nev[s];
+    if (E == 0) return SB200_OK;
+    std::vector<StreamEvent> ev((size_t)n * max_frames);
+    CK(cudaMemcpy(ev.data(), h->sev.p, ev.size() * sizeof(StreamEvent), cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> off(E); std::vector<uint32_t> len(E); std::vector<int2> dcv(E); std::vector<sb200_frame_result> r(E);
+    const uint32_t row = out_bytes ? (out_stride < 2560u ? out_stride : 2560u) : 0u;
+    std::vector<uint8_t> bytes((size_t)E * row);
+    {   size_t e = 0;
+        for (uint32_t s = 0; s < n; s++) for (uint32_t j = 0; j < nev[s]; j++, e++) { const StreamEvent& v = ev[(size_t)s * max_frames + j]; off[e] = v.off; len[e] = v.len; dcv[e] = v.dc; } }
+    CK(h->dcbuf.need(E * sizeof(int2))); CK(cudaMemcpyAsync(h->dcbuf.p, dcv.data(), E * sizeof(int2), cudaMemcpyHostToDevice, st));
+    FrontTaps taps{};
+    int rc = rx11a_run(h, d_iq, iq_total, off.data(), len.data(), (uint32_t)E, row ? bytes.data() : nullptr, row, r.data(), st, taps, nullptr, 0, (const int2*)h->dcbuf.p, true);
+    if (rc != SB200_OK) return rc;
+    {   size_t e = 0;
+        for (uint32_t s = 0; s < n; s++) {
+            for (uint32_t j = 0; j < nev[s]; j++, e++) {
+                const size_t slot = (size_t)s * max_frames + j;
+                if (r[e].status == SB200_FRAME_NONE) return h->fail(SB200_E_CUDA, "internal: stream scout and batch decode disagree about a frame");
+                res[slot] = r[e];
+                if (sample_index) sample_index[slot] = ev[slot].pos_after;
+                if (row) memcpy(out_bytes + slot * out_stride, bytes.data() + e * row, row);
+            }
+            nframes_out[s] = nev[s];
+        } }
     return rc;
 }
 
