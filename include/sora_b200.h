@@ -226,6 +226,18 @@ int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_
                       uint32_t nframes, uint32_t rate_kbps, uint32_t init_phase, uint32_t lead_samples, uint32_t sample_bits,
                       void* out, uint64_t out_stride_samples, uint32_t* nsamples, uint32_t* final_phase, void* cuda_stream);
 
+/* Legacy 802.11b transmit filter: BB11BPMDSpreadFIR4SSE (variant 0) and BB11BPMDSpreadFIR4ASM (variant 1) of kernel/inc/bb/bbb.h:188-200
+ * (bodies: kernel/bb/dot11b/bbb_fir.c:92-110 + :413-566, and :113-135 + :137-386) — the 37-tap pulse shaper BB11BPMDPacketGenSignal
+ * (bbb_tx.c:116-150) runs over the 4x zero-stuffed chip stream of a frame — for a batch of frames.  Frame i = chips[frame_off[i] ..
+ * +frame_len[i]) COMPLEX8 samples (int8 re, im), frame_off and frame_len multiples of 8 (the reference returns E_FAIL on uiInputSize & 7
+ * and wants 16-byte aligned buffers); out receives frame_len[i] filtered COMPLEX8 samples at the same offsets.  As in the reference the
+ * filter starts at the frame's SECOND 16-byte block (output n answers input n + 8; the first eight inputs never enter) and samples past the
+ * end of the frame read as zero (the reference's caller zeroes 64 bytes of tail).  variant 0 reproduces the compiled x64 body bit for bit,
+ * including what its outer +-1 taps really do (the tests check it against the reference's own compiled filter body).
+ * All pointers host or device; device buffers 16-byte aligned. */
+int sb200_tx11b_fir37(sb200_handle* h, const int8_t* chips, uint64_t chips_total_samples, const uint64_t* frame_off, const uint32_t* frame_len,
+                      uint32_t nframes, uint32_t variant, int8_t* out, void* cuda_stream);
+
 /* 802.11n transmit, two spatial streams, HT-mixed format: the modulator graphs CreatePreambleGraph11n + CreateSigGraph11n + CreateModGraph11n
  * (kernel/bb/demod11/fb11nmod_config.hpp:74-171) driven like Test11N_FB_Mod (kernel/bb/demod11/fb11n_mod.cpp:44-70).  Frame i =
  * payload[pay_off[i] .. +pay_len[i]) is the MPDU WITHOUT FCS (CF_11nTxVector::crc32 is appended); mcs 8, 9 or 10 (what the receiver

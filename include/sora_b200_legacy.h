@@ -112,6 +112,17 @@ void    BB11BPrepareRx(PBB11B_RX_CONTEXT pRxContext, void* pOutputBuf, ULONG Out
 HRESULT BB11BSpd(PBB11B_SPD_CONTEXT pSpdContext, PSORA_RADIO_RX_STREAM pRxStream);
 HRESULT BB11BRx(PBB11B_RX_CONTEXT pRxContext, PSORA_RADIO_RX_STREAM pRxStream);
 
+/* ---- 802.11b transmit filter: kernel/inc/bb/bbb.h:188-200.  The 37-tap pulse shaper over the 4x zero-stuffed chip stream (COMPLEX8), the
+ * last stage of BB11BPMDPacketGenSignal (kernel/bb/dot11b/bbb_tx.c:116-150).  uiInputSize in samples, a multiple of 8 (else E_FAIL, as in
+ * the reference); *puiOutputSize = uiInputSize.  Runs on a process-wide engine created on first use (device SB200_DEVICE, default 0); E_FAIL
+ * without a GPU.  The SSE entry reproduces the reference's compiled intrinsic body bit for bit, the ASM entry its 32-bit assembly body
+ * (they differ in the outermost +-1 taps, see sb200_tx11b_fir37 in sora_b200.h). */
+#define SORA_S_OK    ((HRESULT)0)
+#define SORA_E_FAIL  ((HRESULT)0x80004005L)
+typedef struct _SORA_COMPLEX8 { int8_t re, im; } SORA_COMPLEX8, *PCOMPLEX8;
+HRESULT BB11BPMDSpreadFIR4SSE(const SORA_COMPLEX8* pcSrc, uint32_t uiInputSize, SORA_COMPLEX8* pcDest, ULONG* puiOutputSize);
+HRESULT BB11BPMDSpreadFIR4ASM(const SORA_COMPLEX8* pcSrc, uint32_t uiInputSize, SORA_COMPLEX8* pcDest, ULONG* puiOutputSize);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,10 @@
 //   * outputs are >> 8 (arithmetic) and packed to int8 with signed saturation;
 //   * variant 0 = the intrinsic body FIR37SSE_INTRINSIC (bbb_fir.c:413-566, what BB11BPMDSpreadFIR4SSE calls): rows 37 and 38 of the fresh
 //     partial sums are formed from the ALREADY MULTIPLIED row-36 product of the low half-block (bbb_fir.c:485-491, :553-559), so row 37 is
-//     always zero and row 38 carries -x[2] of the low group instead of +x[2] of the current one;
+//     always zero and row 38 carries -x[2] of the low group instead of +x[2] of the current one; and the helper macro that forms outputs
+//     1..3 of the LOW half-block names its coefficient argument `pTags` but reads `pTaps` (bbb_fir.c:390-395), so those three outputs take
+//     x[0] * 1 (row 0) where rows 1..3 were meant.  All of it sits in the +-1 outer taps; oracle/_ref (the compiled reference body,
+//     oracle/build_ref.sh) is what this restatement is checked against, sample for sample;
 //     variant 1 = the inline-assembly body FIR37SSE_INLINE (bbb_fir.c:137-386, BB11BPMDSpreadFIR4ASM, 32-bit builds), which multiplies the
 //     input itself in all four rows.
 // Pin status: unpinned by a reference output.  The reference's 802.11b sample files (kernel/HWTest/exe/tx samples/*.mf.bin) were shaped by a
@@ -41,7 +44,8 @@ void fir37_legacy(const int8_t* src, uint32_t n_in, int variant, int8_t* dst) {
         // four finished outputs
         for (int r = 0; r < 4; r++) for (int c = 0; c < 2; c++) {
             int l[4];
-            for (int i = 0; i < 4; i++) l[i] = sat16(mul16(v[i][c], coef(r, i)) + T[r][i][c]);
+            const int row = (variant == 0 && (p & 1u) == 0) ? 0 : r;          // variant 0, low half-block: rows 1..3 are multiplied by row 0 (see header)
+            for (int i = 0; i < 4; i++) l[i] = sat16(mul16(v[i][c], coef(row, i)) + T[r][i][c]);
             const int y = sat16(sat16(l[0] + l[2]) + sat16(l[1] + l[3])) >> 8;
             dst[2 * (4ull * p + r) + c] = (int8_t)std::min(127, std::max(-128, y));
         }

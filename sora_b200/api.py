@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc", "sb200_fir_decimate2"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc", "sb200_fir_decimate2", "sb200_tx11b_fir37"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -212,6 +212,20 @@ class Engine:
         t = None if taps is None else np.ascontiguousarray(taps, dtype=np.int16)
         self.fir_decimate2_raw(_ptr(iq), len(iq), _ptr(t) if t is not None else 0, 0 if t is None else len(t), _ptr(out))
         return out
+
+    def tx11b_fir37_raw(self, in_ptr, total, off_ptr, len_ptr, nframes, variant, out_ptr, stream=0):
+        self._check(self._lib.sb200_tx11b_fir37(self._h, C.c_void_p(in_ptr), C.c_uint64(total), C.c_void_p(off_ptr), C.c_void_p(len_ptr), C.c_uint32(nframes),
+                                                C.c_uint32(variant), C.c_void_p(out_ptr), C.c_void_p(stream)), "sb200_tx11b_fir37")
+
+    def tx11b_fir37(self, chips, variant=0, frame_len=None):
+        """Legacy 37-tap transmit filter.  chips int8 [n, 2] (one frame) or [F, L, 2] (F frames of L samples, L % 8 == 0) -> same shape."""
+        x = np.ascontiguousarray(chips, dtype=np.int8)
+        fr = x.reshape(1, -1, 2) if x.ndim == 2 else x
+        F, L, _ = fr.shape
+        off = (np.arange(F, dtype=np.uint64) * L); ln = np.full(F, L if frame_len is None else frame_len, np.uint32)
+        out = np.zeros_like(fr)
+        self.tx11b_fir37_raw(_ptr(fr), F * L, _ptr(off), _ptr(ln), F, variant, _ptr(out))
+        return out.reshape(x.shape)
 
     def rxblocks_unpack(self, raw, left_shift=0):
         """raw: uint8 array of whole 128-byte RX_BLOCKs (a *.dmp file) -> int16 [28*nblocks, 2] via the device gather."""

@@ -195,3 +195,23 @@ extern "C" HRESULT BB11BRx(PBB11B_RX_CONTEXT c, PSORA_RADIO_RX_STREAM s) {
         default: B.b_errEnergyLoss++; return BB11B_E_ENERGY;
     }
 }
+
+
+// ---- BB11BPMDSpreadFIR4SSE / BB11BPMDSpreadFIR4ASM (bbb.h:188-200): context-free in the reference, so the engine is process-wide here ----
+#include <mutex>
+static std::mutex g_fir_mu; static sb200_handle* g_fir_engine = nullptr;
+static HRESULT spread_fir(const SORA_COMPLEX8* src, uint32_t n, SORA_COMPLEX8* dst, ULONG* out_n, uint32_t variant) {
+    if (!src || !dst || (n & 7u)) return SORA_E_FAIL;
+    std::lock_guard<std::mutex> lk(g_fir_mu);
+    if (!g_fir_engine) {
+        const char* d = getenv("SB200_DEVICE"); sb200_handle* h = nullptr;
+        if (sb200_create(d ? atoi(d) : 0, nullptr, &h) != SB200_OK) return SORA_E_FAIL;            // no CPU fallback
+        g_fir_engine = h;
+    }
+    const uint64_t off = 0; const uint32_t len = n;
+    if (n && sb200_tx11b_fir37(g_fir_engine, (const int8_t*)src, n, &off, &len, 1, variant, (int8_t*)dst, nullptr) != SB200_OK) return SORA_E_FAIL;
+    if (out_n) *out_n = n;
+    return SORA_S_OK;
+}
+extern "C" HRESULT BB11BPMDSpreadFIR4SSE(const SORA_COMPLEX8* s, uint32_t n, SORA_COMPLEX8* d, ULONG* on) { return spread_fir(s, n, d, on, 0); }
+extern "C" HRESULT BB11BPMDSpreadFIR4ASM(const SORA_COMPLEX8* s, uint32_t n, SORA_COMPLEX8* d, ULONG* on) { return spread_fir(s, n, d, on, 1); }

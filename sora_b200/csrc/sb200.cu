@@ -6,6 +6,7 @@
 #include "rx11n_kernels.cuh"
 #include "tx11a_kernels.cuh"
 #include "tx11b_kernels.cuh"
+#include "tx11b_legacy_kernels.cuh"
 #include "tx11n_kernels.cuh"
 #include "fir_kernels.cuh"
 #include <stdlib.h>
@@ -1135,6 +1136,46 @@ extern "C" int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64
     if (nsamples && !ns_dev) { CK(cudaMemcpyAsync(nsamples, d_ns, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (final_phase && !fp_dev) { CK(cudaMemcpyAsync(final_phase, d_fp, nframes * 4ull, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (sync) CK(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+// Legacy 802.11b transmit filter (tx11b_legacy_kernels.cuh): BB11BPMDSpreadFIR4SSE (variant 0) / BB11BPMDSpreadFIR4ASM (variant 1), batched.
+extern "C" int sb200_tx11b_fir37(sb200_handle* h, const int8_t* chips, uint64_t chips_total, const uint64_t* frame_off, const uint32_t* frame_len,
+                                 uint32_t nframes, uint32_t variant, int8_t* out, void* cuda_stream) {
+    if (!h || !chips || !frame_off || !frame_len || !out) return h ? h->fail(SB200_E_INVALID, "null argument") : SB200_E_INVALID;
+    if (variant > 1) return h->fail(SB200_E_INVALID, "variant must be 0 (BB11BPMDSpreadFIR4SSE) or 1 (BB11BPMDSpreadFIR4ASM)");
+    if (nframes == 0) return SB200_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaSetDevice(h->device));
+    std::vector<uint64_t> offh(nframes); std::vector<uint32_t> lenh(nframes);
+    const bool off_dev = is_device_ptr(frame_off), len_dev = is_device_ptr(frame_len), in_dev = is_device_ptr(chips), out_dev = is_device_ptr(out);
+    if (off_dev) CK(cudaMemcpyAsync(offh.data(), frame_off, nframes * 8ull, cudaMemcpyDeviceToHost, st)); else memcpy(offh.data(), frame_off, nframes * 8ull);
+    if (len_dev) CK(cudaMemcpyAsync(lenh.data(), frame_len, nframes * 4ull, cudaMemcpyDeviceToHost, st)); else memcpy(lenh.data(), frame_len, nframes * 4ull);
+    if (off_dev || len_dev) CK(cudaStreamSynchronize(st));
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < nframes; i++) {
+        if ((lenh[i] & 7u) || (offh[i] & 7u)) return h->fail(SB200_E_INVALID, "frame_off and frame_len must be multiples of 8 samples (the reference fails on uiInputSize & 7 and needs 16-byte aligned buffers)");
+        if (lenh[i] > chips_total || offh[i] > chips_total - lenh[i]) return h->fail(SB200_E_INVALID, "frame exceeds chips_total");
+        if (lenh[i] > max_len) max_len = lenh[i];
+    }
+    if ((in_dev && ((uintptr_t)chips & 15u)) || (out_dev && ((uintptr_t)out & 15u))) return h->fail(SB200_E_INVALID, "device buffers must be 16-byte aligned");
+    const int8_t* d_in; int8_t* d_out; const uint64_t* d_off; const uint32_t* d_len;
+    if (in_dev) d_in = chips; else { CK(h->txpay.need(chips_total * 2ull + 16)); CK(cudaMemcpyAsync(h->txpay.p, chips, chips_total * 2ull, cudaMemcpyHostToDevice, st)); d_in = (const int8_t*)h->txpay.p; }
+    if (out_dev) d_out = out; else { CK(h->txout.need(chips_total * 2ull + 16)); d_out = (int8_t*)h->txout.p; }
+    if (off_dev) d_off = frame_off; else { CK(h->txoff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->txoff.p, offh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st)); d_off = (const uint64_t*)h->txoff.p; }
+    if (len_dev) d_len = frame_len; else { CK(h->txlen.need(nframes * 4ull)); CK(cudaMemcpyAsync(h->txlen.p, lenh.data(), nframes * 4ull, cudaMemcpyHostToDevice, st)); d_len = (const uint32_t*)h->txlen.p; }
+    const uint64_t groups = (uint64_t)(max_len >> 3) * 2u; uint64_t ny = (groups + SB_FIR37_THREADS - 1) / SB_FIR37_THREADS; if (ny > 4096) ny = 4096; if (ny == 0) ny = 1;
+    CK(cudaEventRecord(h->ev0, st));
+    const dim3 grid(nframes, (unsigned)ny);
+    if (variant == 0) k_fir37_legacy<0><<<grid, SB_FIR37_THREADS, 0, st>>>(d_in, d_off, d_len, nframes, d_out);
+    else k_fir37_legacy<1><<<grid, SB_FIR37_THREADS, 0, st>>>(d_in, d_off, d_len, nframes, d_out);
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->nk = 0; h->launches += 1;
+    CK(cudaGetLastError());
+    if (!out_dev) {                                     // only the frames' own ranges are defined; copy them back one by one (they may be sparse in the buffer)
+        for (uint32_t i = 0; i < nframes; i++) if (lenh[i]) CK(cudaMemcpyAsync(out + 2ull * offh[i], d_out + 2ull * offh[i], 2ull * lenh[i], cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return SB200_OK;
 }
 

@@ -208,3 +208,21 @@ def tx11n_modulate(payload, mcs, seed=0xAB):
 def tx11n_preamble_tables():
     a = np.zeros((320, 2), np.int16); b = np.zeros((320, 2), np.int16); c = np.zeros((160, 2), np.int16); d = np.zeros((160, 2), np.int16)
     lib().sbo_tx11n_preamble_tables(_p(a), _p(b), _p(c), _p(d)); return a, b, c, d
+
+
+def fir37_legacy(chips, variant=0):
+    """oracle/tx11b_legacy.cpp: BB11BPMDSpreadFIR4SSE (variant 0) / BB11BPMDSpreadFIR4ASM (variant 1) restated.  int8 [n,2] -> int8 [n,2] (n % 8 == 0)."""
+    x = np.ascontiguousarray(chips, dtype=np.int8).reshape(-1, 2); out = np.zeros_like(x)
+    lib().sbo_fir37_legacy(C.c_void_p(x.ctypes.data), C.c_uint32(len(x)), C.c_int(variant), C.c_void_p(out.ctypes.data))
+    return out
+
+_REF_FIR = None
+def ref_fir37_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfir37_ref.so"))
+def ref_fir37(chips):
+    """oracle/_ref/libfir37_ref.so: the reference's own FIR37SSE_INTRINSIC body + coefficient table, compiled by oracle/build_ref.sh."""
+    global _REF_FIR
+    if _REF_FIR is None: _REF_FIR = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfir37_ref.so"))
+    x = np.ascontiguousarray(chips, dtype=np.int8).reshape(-1, 2); out = np.zeros_like(x)
+    _REF_FIR.ref_fir37(C.c_void_p(x.ctypes.data), C.c_uint(len(x)), C.c_void_p(out.ctypes.data))
+    return out
