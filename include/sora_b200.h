@@ -84,6 +84,10 @@ int sb200_last_kernel_times(sb200_handle* h, float* ms4);
 /* Tunables.  "chunk_frames" (default 4096): when the IQ buffer is HOST memory, calls with more slots are cut into chunks whose
  * host->device copy, OFDM front end and Viterbi overlap on three streams; 0 = one pass on the caller's stream.
  * "chunk_frames_device" (default 0 = off): the same for device-resident IQ.  sb200_last_kernel_times needs an un-chunked call.
+ * "ht_mcs_limit" (default 11): the first 802.11n MCS index the HT-SIG parser refuses.  11 is the reference as it ships (PHY_11n.hpp:496-501:
+ *   MCS 8..10 decode, anything else ends with E_ERROR_PLCP_HEADER_FAIL); 15 sends MCS 11..14 through the 16-QAM / 64-QAM branches the
+ *   reference's receive graph already carries (fb11ndemod_config.hpp:196-236, demapper11n.hpp:199-309, deinterleaver_11n.hpp) — rate 1/2,
+ *   3/4 and 2/3 Viterbi, stream parser blocks of 2 / 3 bits.  Values 9 .. 15.
  * "host_decimate" (default 0 = off): number of host threads (the caller's included) that gather the even samples of every slot of a chunk
  * into pinned staging memory before the copy — TDownSample2 (Brick11/src/samples.hpp:27-49) keeps samples 0 and 2 of every 4, so the
  * 802.11a chain never reads the odd ones and only half of a host-resident 40 Msps capture has to cross PCIe.  Results are identical.
@@ -240,8 +244,8 @@ int sb200_tx11b_fir37(sb200_handle* h, const int8_t* chips, uint64_t chips_total
 
 /* 802.11n transmit, two spatial streams, HT-mixed format: the modulator graphs CreatePreambleGraph11n + CreateSigGraph11n + CreateModGraph11n
  * (kernel/bb/demod11/fb11nmod_config.hpp:74-171) driven like Test11N_FB_Mod (kernel/bb/demod11/fb11n_mod.cpp:44-70).  Frame i =
- * payload[pay_off[i] .. +pay_len[i]) is the MPDU WITHOUT FCS (CF_11nTxVector::crc32 is appended); mcs 8, 9 or 10 (what the receiver
- * accepts, PHY_11n.hpp:496-501); seeds[i] = CF_ScramblerSeed::sc_seed (NULL: 0xAB as fb11nmod_config.hpp:52).  Slot i of out0 / out1
+ * payload[pay_off[i] .. +pay_len[i]) is the MPDU WITHOUT FCS (CF_11nTxVector::crc32 is appended); mcs 8 .. 14 (the modulator graph's own
+ * range, fb11nmod_config.hpp:146-155; the reference's receiver admits 8 .. 10 only, PHY_11n.hpp:496-501 — see option "ht_mcs_limit"); seeds[i] = CF_ScramblerSeed::sc_seed (NULL: 0xAB as fb11nmod_config.hpp:52).  Slot i of out0 / out1
  * (out_stride_samples COMPLEX16 samples at 40 Msps each, the two transmit chains) receives lead_samples zeros, L-STF + L-LTF (640), L-SIG
  * + HT-SIG (480), HT-STF + 2 HT-LTF (480), 160 samples per DATA symbol — one more symbol than HT-SIG announces when the graph's Flush
  * padding spills over a symbol boundary — and zeros to the end of the slot; nsamples[i] = lead + samples written.  The two slots go

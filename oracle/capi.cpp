@@ -235,7 +235,10 @@ int sbo_rx11n_taps(const int16_t* iq0, const int16_t* iq1, uint64_t nsamples, vo
     return (int)nd;
 }
 int16_t sbo_dsp_atan(int x, int y) { return dsp_atan(x, y); }
-void sbo_tables11n(int16_t* sincos, int16_t* atan_lut, uint8_t* demap, uint8_t* crc8, uint8_t* deint, uint8_t* lltf_sign, uint8_t* htltf_sign) {
+void sbo_set_ht_mcs_limit(uint32_t first_refused) { set_ht_mcs_limit(first_refused); }
+uint32_t sbo_ht_mcs_limit() { return ht_mcs_limit(); }
+void sbo_tables11n_qam(uint8_t* demap16, uint8_t* demap64) { const Tables11n& T = tables11n(); memcpy(demap16, T.demap16, sizeof T.demap16); memcpy(demap64, T.demap64, sizeof T.demap64); }
+void sbo_tables11n(int16_t* sincos, int16_t* atan_lut, uint8_t* demap, uint8_t* crc8, uint16_t* deint, uint8_t* lltf_sign, uint8_t* htltf_sign) {
     const Tables11n& T = tables11n();
     memcpy(sincos, T.sincos, sizeof T.sincos); memcpy(atan_lut, T.atan_lut, sizeof T.atan_lut); memcpy(demap, T.demap, 256); memcpy(crc8, T.crc8, 256);
     memcpy(deint, T.deint, sizeof T.deint); memcpy(lltf_sign, T.lltf_sign, 64); memcpy(htltf_sign, T.htltf_sign, 64);

@@ -37,13 +37,24 @@ Tables11n::Tables11n() {
     static const uint8_t rle[8][2] = {{4, 11}, {5, 10}, {6, 10}, {7, 97}, {0, 97}, {1, 10}, {2, 10}, {3, 11}};
     int p = 0; for (auto& r : rle) for (int k = 0; k < r[1]; k++) demap[p++] = r[0];
     for (int b = 0; b < 256; b++) { uint8_t c = (uint8_t)b; for (int k = 0; k < 8; k++) c = (c & 1) ? (uint8_t)((c >> 1) ^ 0xE0) : (uint8_t)(c >> 1); crc8[b] = c; }
-    for (int q = 0; q < 2; q++) for (int ss = 0; ss < 2; ss++) {   // IEEE 802.11n-2009 20.3.11.7.3 (== deinterleaver_11n.hpp tables)
-        const int nbpsc = q + 1, ncbpss = 52 * nbpsc, nrow = 4 * nbpsc, ncol = 13, s = 1;
+    {   // 16-QAM / 64-QAM soft-bit tables (dsp_demap.h, hand-tuned data carried as run lengths; diffed against the header by the tests)
+        static const uint8_t r161[][2] = {{4, 5}, {5, 4}, {6, 7}, {7, 112}, {0, 113}, {1, 7}, {2, 4}, {3, 4}};
+        static const uint8_t r162[][2] = {{7, 56}, {6, 3}, {5, 3}, {4, 2}, {3, 2}, {2, 2}, {1, 3}, {0, 115}, {1, 3}, {2, 2}, {3, 2}, {4, 2}, {5, 3}, {6, 3}, {7, 55}};
+        static const uint8_t r641[][2] = {{0, 138}, {1, 3}, {2, 2}, {3, 1}, {4, 2}, {5, 2}, {6, 3}, {7, 137}};
+        static const uint8_t r642[][2] = {{0, 68}, {1, 3}, {2, 2}, {3, 2}, {4, 1}, {5, 2}, {6, 3}, {7, 127}, {6, 3}, {5, 2}, {4, 1}, {3, 2}, {2, 2}, {1, 3}, {0, 67}};
+        static const uint8_t r643[][2] = {{0, 34}, {1, 2}, {2, 2}, {3, 2}, {4, 2}, {5, 1}, {6, 3}, {7, 57}, {6, 3}, {5, 2}, {4, 2}, {3, 1}, {2, 2}, {1, 3}, {0, 57},
+                                          {1, 3}, {2, 2}, {3, 1}, {4, 2}, {5, 2}, {6, 3}, {7, 57}, {6, 3}, {5, 1}, {4, 2}, {3, 2}, {2, 2}, {1, 2}, {0, 33}};
+        auto fill = [](uint8_t* dst, const uint8_t (*r)[2], size_t n) { int p = 0; for (size_t i = 0; i < n; i++) for (int k = 0; k < r[i][1]; k++) dst[p++] = r[i][0]; };
+        fill(demap16[0], r161, sizeof r161 / 2); fill(demap16[1], r162, sizeof r162 / 2);
+        fill(demap64[0], r641, sizeof r641 / 2); fill(demap64[1], r642, sizeof r642 / 2); fill(demap64[2], r643, sizeof r643 / 2);
+    }
+    for (int q = 0; q < 4; q++) for (int ss = 0; ss < 2; ss++) {   // IEEE 802.11n-2009 20.3.11.7.3 (== deinterleaver_11n.hpp tables)
+        const int nbpsc = q == 3 ? 6 : q == 2 ? 4 : q + 1, ncbpss = 52 * nbpsc, nrow = 4 * nbpsc, ncol = 13, s = nbpsc / 2 > 1 ? nbpsc / 2 : 1;
         for (int k = 0; k < ncbpss; k++) {
             int i = nrow * (k % ncol) + k / ncol;
             int j = s * (i / s) + (i + ncbpss - (ncol * i) / ncbpss) % s;
             int r = ((j - ((ss * 2) % 3 + 3 * (ss / 3)) * 11 * nbpsc) % ncbpss + ncbpss) % ncbpss;
-            deint[q][ss][k] = (uint8_t)r;
+            deint[q][ss][k] = (uint16_t)r;
         }
     }
     for (int i = 0; i < 64; i++) {
@@ -53,6 +64,15 @@ Tables11n::Tables11n() {
     }
 }
 const Tables11n& tables11n() { static Tables11n t; return t; }
+
+static uint32_t g_ht_mcs_limit = 11;                    // PHY_11n.hpp:497: `ht_frame_mcs >= 11` is refused
+void set_ht_mcs_limit(uint32_t first_refused) { g_ht_mcs_limit = first_refused < 9 ? 9 : first_refused > 15 ? 15 : first_refused; }
+uint32_t ht_mcs_limit() { return g_ht_mcs_limit; }
+bool ht_mcs_params(uint32_t mcs, HtMcs& m) {
+    static const HtMcs P[7] = {{1, CR_12, 52, 0}, {2, CR_12, 104, 1}, {2, CR_34, 156, 1}, {4, CR_12, 208, 2}, {4, CR_34, 312, 2}, {6, CR_23, 416, 3}, {6, CR_34, 468, 3}};
+    if (mcs < 8 || mcs > 14) return false;
+    m = P[mcs - 8]; return true;
+}
 
 int16_t dsp_atan(int x, int y) {                        // dsp_math.h:166-212 (the short overload :90-164 agrees on its range)
     const int sign = (x ^ y) >> 31;                     // 0 or -1
@@ -256,14 +276,14 @@ void Rx11n::on_sig3() {                                // T11nSigDemap, T11aDein
         if (c != (uint8_t)((ip[4] >> 2) | (ip[5] << 6))) { ht_frame_mcs = 0; ht_frame_length = 0; ok = false; }
         else {
             ht_frame_mcs = ip[0] & 0x7F;
-            if (ht_frame_mcs < 8 || ht_frame_mcs >= 11) ok = false;
+            if (ht_frame_mcs < 8 || ht_frame_mcs >= ht_mcs_limit()) ok = false;
             else {
                 ht_frame_length = (uint16_t)(ip[1] | (ip[2] << 8));
                 if (ht_frame_length > 1500) ok = false;
                 else {
-                    code_rate = (ht_frame_mcs % 8 == 2) ? CR_34 : CR_12;                  // ieee80211n_cmn.h:7-26
-                    const int ndbps = ht_frame_mcs == 8 ? 52 : ht_frame_mcs == 9 ? 104 : 156;
-                    total_symbols = (uint16_t)((ht_frame_length * 8 + 16 + 6 + ndbps - 1) / ndbps + 4); remain_symbols = total_symbols;
+                    HtMcs m; ht_mcs_params(ht_frame_mcs, m);
+                    code_rate = (uint16_t)m.cr;                                            // ieee80211n_cmn.h:7-26
+                    total_symbols = (uint16_t)((ht_frame_length * 8 + 16 + 6 + m.ndbps - 1) / m.ndbps + 4); remain_symbols = total_symbols;
                 }
             }
         }
@@ -321,21 +341,30 @@ void Rx11n::on_data(const c16 Y[2][64]) {
     }
     vfo_theta = w16(vfo_theta + w16((th[0] + th[1]) >> 1));
     if (taps.enable) taps.theta.push_back(vfo_theta);
-    const int q = ht_frame_mcs == 8 ? 0 : 1, nss = 52 * (q + 1);
-    uint8_t soft[2][104], dso[2][104];
+    HtMcs m; ht_mcs_params(ht_frame_mcs, m);
+    const int q = m.q, nss = 52 * m.nbpsc;
+    uint8_t soft[2][312], dso[2][312];
     for (int s = 0; s < 2; s++) {
         int j = 0;
         for (int pass = 0; pass < 2; pass++)
             for (int i = pass ? 1 : 36; i <= (pass ? 28 : 63); i++) {
                 if (i == 43 || i == 57 || i == 7 || i == 21) continue;
                 int16_t re = X[s][i].re, im = X[s][i].im;
-                re = re < -128 ? -128 : re > 127 ? 127 : re; im = im < -128 ? -128 : im > 127 ? 127 : im;
-                soft[s][j++] = T.demap[(uint8_t)re]; if (q) soft[s][j++] = T.demap[(uint8_t)im];
+                re = re < -128 ? -128 : re > 127 ? 127 : re; im = im < -128 ? -128 : im > 127 ? 127 : im;     // demap_limit with DemapMin / DemapMax, all four demappers
+                if (q <= 1) { soft[s][j++] = T.demap[(uint8_t)re]; if (q) soft[s][j++] = T.demap[(uint8_t)im]; }
+                else if (q == 2) {                                                                             // dsp_demap.h demap_16qam
+                    soft[s][j++] = T.demap16[0][(uint8_t)re]; soft[s][j++] = T.demap16[1][(uint8_t)re];
+                    soft[s][j++] = T.demap16[0][(uint8_t)im]; soft[s][j++] = T.demap16[1][(uint8_t)im];
+                } else {                                                                                       // demap_64qam: tables based at entry 144
+                    for (int t = 0; t < 3; t++) soft[s][j++] = T.demap64[t][144 + re];
+                    for (int t = 0; t < 3; t++) soft[s][j++] = T.demap64[t][144 + im];
+                }
             }
         for (int k = 0; k < nss; k++) dso[s][k] = soft[s][T.deint[q][s][k]];
     }
+    const int S = m.nbpsc / 2 > 1 ? m.nbpsc / 2 : 1;                                                            // TStreamJoin<2, N> + TStreamConcat<2, S>: S values of stream 0, S of stream 1, ...
     const size_t base = vit_in.size(); vit_in.resize(base + 2 * nss);
-    for (int k = 0; k < nss; k++) { vit_in[base + 2 * k] = dso[0][k]; vit_in[base + 2 * k + 1] = dso[1][k]; }   // TStreamJoin + TStreamConcat<2,1>
+    for (int k = 0; k < nss; k++) { vit_in[base + (2 * (k / S)) * S + k % S] = dso[0][k]; vit_in[base + (2 * (k / S) + 1) * S + k % S] = dso[1][k]; }
     if (taps.enable) taps.soft.insert(taps.soft.end(), vit_in.begin() + base, vit_in.end());
     viterbi_feed(false);
 }

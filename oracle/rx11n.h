@@ -1,5 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see ops.h).
-// CPU restatement of the reference's 802.11n 2x2 (HT mixed format, 20 MHz, 2 spatial streams, MCS 8..10) receive graph
+// CPU restatement of the reference's 802.11n 2x2 (HT mixed format, 20 MHz, 2 spatial streams) receive graph: MCS 8..10 as the reference's HT-SIG parser
+// admits them (PHY_11n.hpp:496-501), and MCS 11..14 through the 16-QAM / 64-QAM branches the graph already carries (fb11ndemod_config.hpp:206-236,
+// demapper11n.hpp:199-309, deinterleaver_11n.hpp) when the parser's gate is opened (ht_mcs_limit)
 //   kernel/bb/demod11/fb11ndemod_config.hpp:167-262 (CreateDemodGraph11n)
 //   driven like kernel/bb/demod11/fb11n_demod.cpp:29-81 (RxThread).
 // Written as scalar integer code with the SSE lane semantics (wrapping / saturating / arithmetic shifts) spelled out;
@@ -18,7 +20,9 @@ struct Tables11n {
     int16_t  atan_lut[4097];       // dsp_math.h:233-247
     uint8_t  demap[256];           // dsp_demap.h:97-137 lookup_table_bpsk == lookup_table_qpsk (data, run-length coded)
     uint8_t  crc8[256];            // core/inc/CRC8.h:16-26
-    uint8_t  deint[2][2][104];     // [qpsk][stream][k] : out[k] = in[map]   deinterleaver_11n.hpp:6-620
+    uint8_t  demap16[2][256];      // dsp_demap.h lookup_table_16qam1 / 16qam2 (data, run-length coded), indexed by the uint8 of the limited value
+    uint8_t  demap64[3][288];      // dsp_demap.h lookup_table_64qam1..3, indexed by value + 144
+    uint16_t deint[4][2][312];     // [bpsk, qpsk, 16-qam, 64-qam][stream][k] : out[k] = in[map]   deinterleaver_11n.hpp:6-1618
     uint8_t  lltf_sign[64];        // 1 where L-LTF carrier is +1      channel_11n.hpp:7-32  (_80211_LLTFMask)
     uint8_t  htltf_sign[64];       // 1 where HT-LTF carrier is +1     channel_11n.hpp:300-325 (_80211n_HTLTFMask)
     Tables11n();
@@ -27,6 +31,11 @@ const Tables11n& tables11n();
 
 int16_t dsp_atan(int x, int y);                                   // dsp_math.h:166-212 atan(int,int)
 uint8_t crc8_htsig(const uint8_t* p, unsigned nbytes, unsigned tail_bits);   // CRC8.h:29-50 CalcCRC8
+// first MCS index the HT-SIG parser refuses: 11 as the reference ships it (PHY_11n.hpp:497), 15 with the 16-/64-QAM branches enabled
+void set_ht_mcs_limit(uint32_t first_refused);
+uint32_t ht_mcs_limit();
+struct HtMcs { int nbpsc, cr, ndbps, q; };                         // q = table index 0..3 for N_BPSC 1, 2, 4, 6
+bool ht_mcs_params(uint32_t mcs, HtMcs& m);                       // MCS 8..14 (ieee80211n_cmn.h:7-26, ieee80211const.h:35-55)
 
 struct FrameResult11n {
     uint32_t status, mcs, length, crc32, nsym;

@@ -8,10 +8,16 @@
 
 namespace sbo {
 namespace {
-const int16_t MOD_BPSK = 30339, MOD_QPSK = 21453;                       // fb11nmod_config.hpp:129-132 (TMap11aBPSK<30339>, TMap11aQPSK<21453>)
+const int16_t MOD_BPSK = 30339, MOD_QPSK = 21453, MOD_QAM16 = 9594, MOD_QAM64 = 4681;   // fb11nmod_config.hpp:129-136 (TMap11aBPSK<30339>, TMap11aQPSK<21453>, TMap11aQAM16<9594>, TMap11aQAM64<4681>)
 struct McsInfo { int nbpsc, cr, ndbps, enc_in, parse_in; };             // ieee80211const.h:35-55, conv_enc.hpp:66-67,152-153,245-246, streamparser.hpp:13,50
 bool mcs_info(uint32_t mcs, McsInfo& m) {
-    if (mcs == 8) m = {1, CR_12, 52, 1, 13}; else if (mcs == 9) m = {2, CR_12, 104, 1, 26}; else if (mcs == 10) m = {2, CR_34, 156, 3, 26}; else return false;
+    // the modulator graph carries MCS 8..14 (fb11nmod_config.hpp:146-155: encoders 1/2, 3/4, 2/3 behind TBB11nMRSelect; parsers streamparser.hpp:13,46,80,114)
+    switch (mcs) {
+        case 8: m = {1, CR_12, 52, 1, 13}; break;    case 9: m = {2, CR_12, 104, 1, 26}; break;   case 10: m = {2, CR_34, 156, 3, 26}; break;
+        case 11: m = {4, CR_12, 208, 1, 52}; break;  case 12: m = {4, CR_34, 312, 3, 52}; break;
+        case 13: m = {6, CR_23, 416, 2, 78}; break;  case 14: m = {6, CR_34, 468, 3, 78}; break;
+        default: return false;
+    }
     return true;
 }
 // K = 7 (133, 171) mother code on a bit string, LSB first, with the three puncture patterns (conv_enc.hpp:20-280)
@@ -82,7 +88,7 @@ uint32_t tx11n_nsym(uint32_t len, uint32_t mcs, uint32_t* signalled) {
     if (signalled) *signalled = ns;
     uint32_t total_bytes = (ns * m.ndbps + 7u) / 8u;                                                   // TBB11nSrc: service + frame + FCS + tail + pad (PHY_11n.hpp:88-134)
     total_bytes = (total_bytes + m.enc_in - 1) / m.enc_in * m.enc_in;                                   // MRSelect's FlushPort pads the encoder's input burst
-    const uint32_t coded_bytes = m.cr == CR_12 ? 2u * total_bytes : total_bytes / 3u * 4u;
+    const uint32_t coded_bytes = m.cr == CR_12 ? 2u * total_bytes : m.cr == CR_34 ? total_bytes / 3u * 4u : total_bytes / 2u * 3u;
     return (coded_bytes + m.parse_in - 1) / m.parse_in;                                                // the encoder's FlushPort pads the stream parser's burst
 }
 
@@ -151,14 +157,22 @@ size_t tx11n_modulate(const uint8_t* payload, uint32_t len, uint32_t mcs, uint8_
     for (uint32_t s = 0; s < nsym; s++) {
         const uint8_t* cb = coded.data() + (size_t)s * per_sym;
         for (int iss = 0; iss < 2; iss++) {
-            uint8_t air[104];
-            for (int k = 0; k < ncbpss; k++) air[ht_interleave_pos(k, ncbpss, m.nbpsc, iss + 1)] = cb[2 * k + iss];      // _b_stream_parser.h:36-49: even bits to stream 1, odd to stream 2
+            uint8_t air[312];
+            const int S = m.nbpsc / 2 > 1 ? m.nbpsc / 2 : 1;                                           // _b_stream_parser.h:36-49,140-198,200-275: S bits to stream 1, S to stream 2, round robin
+            for (int k = 0; k < ncbpss; k++) air[ht_interleave_pos(k, ncbpss, m.nbpsc, iss + 1)] = cb[(2 * (k / S) + iss) * S + k % S];
+            auto level = [&](const uint8_t* b, int mbits, int16_t mod) -> int16_t {                    // mapper11a.hpp:16-41 InitQamMapLut: bit-reverse, Gray -> binary, (2b - (2^M - 1)) * MOD
+                unsigned g = 0; for (int t = 0; t < mbits; t++) g = (g << 1) | b[t];                   // first bit on air = LSB of the LUT index = MSB after BitReverseN
+                unsigned bin = g; for (unsigned sh = g >> 1; sh; sh >>= 1) bin ^= sh;
+                return (int16_t)(((int)bin * 2 - ((1 << mbits) - 1)) * mod);
+            };
             alignas(16) c16 f[64]; memset(f, 0, sizeof f); int d = 0;
             for (int pass = 0; pass < 2; pass++)                                                       // pilot_11n.hpp:54-66: -28..-1 then 1..28 without +-7, +-21
                 for (int i = pass ? 1 : 36; i <= (pass ? 28 : 63); i++) {
                     if (i == 43 || i == 57 || i == 7 || i == 21) continue;
                     if (m.nbpsc == 1) f[i].re = air[d] ? MOD_BPSK : (int16_t)-MOD_BPSK;
-                    else { f[i].re = air[2 * d] ? MOD_QPSK : (int16_t)-MOD_QPSK; f[i].im = air[2 * d + 1] ? MOD_QPSK : (int16_t)-MOD_QPSK; }
+                    else if (m.nbpsc == 2) { f[i].re = air[2 * d] ? MOD_QPSK : (int16_t)-MOD_QPSK; f[i].im = air[2 * d + 1] ? MOD_QPSK : (int16_t)-MOD_QPSK; }
+                    else if (m.nbpsc == 4) { f[i].re = level(air + 4 * d, 2, MOD_QAM16); f[i].im = level(air + 4 * d + 2, 2, MOD_QAM16); }
+                    else { f[i].re = level(air + 6 * d, 3, MOD_QAM64); f[i].im = level(air + 6 * d + 3, 3, MOD_QAM64); }
                     d++;
                 }
             const int sg = neg[(s + 3) % 127] ? -1 : 1; const int8_t* pp = PIL[s & 3][iss];           // _b_dot11_pilot.h:7-17

@@ -252,7 +252,7 @@ class Engine:
         off = np.ascontiguousarray(frame_off, dtype=np.uint64); ln = np.ascontiguousarray(frame_len, dtype=np.uint32); nf = len(off)
         res = np.zeros(nf, dtype=RESULT11N_DTYPE)
         siso = np.zeros((nf, 2, 64, 2), np.int16); hinv = np.zeros((nf, 4, 64, 2), np.int16); eq = np.zeros((nf, 2, max_sym, 64, 2), np.int16)
-        theta = np.zeros((nf, max_sym), np.int16); sig = np.zeros((nf, 16), np.uint8); sstride = max_sym * 208; soft = np.zeros((nf, sstride), np.uint8)
+        theta = np.zeros((nf, max_sym), np.int16); sig = np.zeros((nf, 16), np.uint8); sstride = max_sym * 624; soft = np.zeros((nf, sstride), np.uint8)
         self._check(self._lib.sb200_rx11n_taps(self._h, C.c_void_p(_ptr(iq0)), C.c_void_p(_ptr(iq1)), C.c_uint64(iq0.shape[0]), C.c_void_p(_ptr(off)), C.c_void_p(_ptr(ln)),
                                                C.c_uint32(nf), C.c_uint32(max_sym), C.c_void_p(_ptr(res)), C.c_void_p(_ptr(siso)), C.c_void_p(_ptr(hinv)), C.c_void_p(_ptr(eq)),
                                                C.c_void_p(_ptr(theta)), C.c_void_p(_ptr(sig)), C.c_void_p(_ptr(soft)), C.c_uint64(sstride)), "sb200_rx11n_taps")

@@ -31,9 +31,14 @@ struct DevTables11n {
     const uint8_t*  pos;        // [2 qpsk][2 stream][104] position, in the stream-parsed symbol, of demap output j of stream s
     const uint8_t*  lltf_pos;   // [64] 1 where the L-LTF carrier is +1  channel_11n.hpp:7-32
     const uint8_t*  htltf_pos;  // [64] 1 where the HT-LTF carrier is +1 channel_11n.hpp:300-325
+    const uint16_t* pos16;      // [2: 16-QAM, 64-QAM][2 stream][312] the same position map for the 16-QAM / 64-QAM branches (stream parser blocks of 2 / 3)
+    const uint8_t*  demap16;    // [2][256] dsp_demap.h lookup_table_16qam1 / 16qam2 (data)
+    const uint8_t*  demap64;    // [3][288] dsp_demap.h lookup_table_64qam1..3, entry 144 = value 0 (data)
+    uint32_t mcs_limit;         // first MCS index the HT-SIG parser refuses: 11 as the reference ships it (PHY_11n.hpp:497), 15 with the QAM branches enabled
 };
 struct HostTables11n {
     uint32_t sincos[65536]; int16_t atan_lut[4097]; uint8_t demap[256], crc8[256], pos[2][2][104], lltf_pos[64], htltf_pos[64];
+    uint16_t pos16[2][2][312]; uint8_t demap16[2][256], demap64[3][288];
 };
 static inline void build_host_tables11n(HostTables11n& H) {
     for (unsigned i = 0; i < 65536; i++) {
@@ -52,6 +57,23 @@ static inline void build_host_tables11n(HostTables11n& H) {
             H.pos[q][ss][r] = (uint8_t)(2 * k + ss);                                             // TStreamJoin + TStreamConcat<2,1>
         }
     }
+    for (int q = 0; q < 2; q++) for (int ss = 0; ss < 2; ss++) {        // 16-QAM (s = 2) and 64-QAM (s = 3): deinterleaver_11n.hpp T11nDeinterleaveQAM16/64_S0/S1
+        const int nbpsc = q ? 6 : 4, n = 52 * nbpsc, sb = nbpsc / 2;
+        for (int k = 0; k < n; k++) {
+            const int i = 4 * nbpsc * (k % 13) + k / 13;
+            const int j = sb * (i / sb) + (i + n - (13 * i) / n) % sb;
+            const int r = ((j - ((ss * 2) % 3 + 3 * (ss / 3)) * 11 * nbpsc) % n + n) % n;        // out[k] = in[r]
+            H.pos16[q][ss][r] = (uint16_t)((2 * (k / sb) + ss) * sb + k % sb);                   // TStreamJoin + TStreamConcat<2, 2 | 3> (fb11ndemod_config.hpp:196-213)
+        }
+    }
+    {   static const unsigned char r161[8][2] = {{4, 5}, {5, 4}, {6, 7}, {7, 112}, {0, 113}, {1, 7}, {2, 4}, {3, 4}};
+        static const unsigned char r162[15][2] = {{7, 56}, {6, 3}, {5, 3}, {4, 2}, {3, 2}, {2, 2}, {1, 3}, {0, 115}, {1, 3}, {2, 2}, {3, 2}, {4, 2}, {5, 3}, {6, 3}, {7, 55}};
+        static const unsigned char r641[8][2] = {{0, 138}, {1, 3}, {2, 2}, {3, 1}, {4, 2}, {5, 2}, {6, 3}, {7, 137}};
+        static const unsigned char r642[15][2] = {{0, 68}, {1, 3}, {2, 2}, {3, 2}, {4, 1}, {5, 2}, {6, 3}, {7, 127}, {6, 3}, {5, 2}, {4, 1}, {3, 2}, {2, 2}, {1, 3}, {0, 67}};
+        static const unsigned char r643[29][2] = {{0, 34}, {1, 2}, {2, 2}, {3, 2}, {4, 2}, {5, 1}, {6, 3}, {7, 57}, {6, 3}, {5, 2}, {4, 2}, {3, 1}, {2, 2}, {1, 3}, {0, 57},
+                                                  {1, 3}, {2, 2}, {3, 1}, {4, 2}, {5, 2}, {6, 3}, {7, 57}, {6, 3}, {5, 1}, {4, 2}, {3, 2}, {2, 2}, {1, 2}, {0, 33}};
+        rle_expand(r161, 8, H.demap16[0]); rle_expand(r162, 15, H.demap16[1]);
+        rle_expand(r641, 8, H.demap64[0]); rle_expand(r642, 15, H.demap64[1]); rle_expand(r643, 29, H.demap64[2]); }
     static const int8_t L[53] = {1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,1,1,-1,-1,1,1,-1,1,-1,1,1,1,1,0,
                                  1,-1,-1,1,1,-1,1,-1,1,-1,-1,-1,-1,-1,1,1,-1,-1,1,-1,1,-1,1,1,1,1};
     for (int i = 0; i < 64; i++) {
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS, SB_FRONT11N_MINB) k_fr
         const uint64_t* __restrict__ off, const uint32_t* __restrict__ len, uint32_t nframes, DevTables T, DevTables11n N, const uint16_t* __restrict__ inv_deint48,
         FrameInfo* __restrict__ info, uint8_t* __restrict__ soft_out, uint64_t soft_stride, Taps11n taps) {
     __shared__ uint32_t s_fft[SB_FRONT11N_WARPS][2][64];
-    __shared__ __align__(16) uint8_t s_soft[SB_FRONT11N_WARPS][208];
+    __shared__ __align__(16) uint8_t s_soft[SB_FRONT11N_WARPS][624];       // one stream-parsed symbol: 2 x 52 x N_BPSC soft values (SIG phase: 3 x 48)
     __shared__ uint32_t s_dec[SB_FRONT11N_WARPS][96];
     __shared__ uint8_t s_demap[256];
     const unsigned FULL = 0xFFFFFFFFu;
@@ -429,13 +451,14 @@ __global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS, SB_FRONT11N_MINB) k_fr
             if (c != (uint8_t)((sg[7] >> 2) | (sg[8] << 6))) { mcs = 0; ok = false; }
             else {
                 mcs = sg[3] & 0x7F;
-                if (mcs < 8 || mcs >= 11) ok = false;
+                if (mcs < 8 || mcs >= N.mcs_limit) ok = false;
                 else {
                     const uint32_t hl16 = (uint32_t)sg[4] | ((uint32_t)sg[5] << 8);
                     if (hl16 > 1500u) ok = false;
                     else {
-                        code_rate = (mcs == 10) ? CR_34 : CR_12;
-                        const uint32_t ndbps = mcs == 8 ? 52u : mcs == 9 ? 104u : 156u;
+                        const uint32_t m8 = mcs & 7u;                                     // ieee80211n_cmn.h:7-26, ieee80211const.h:46-54
+                        code_rate = m8 == 5u ? CR_23 : (m8 == 2u || m8 == 4u || m8 == 6u) ? CR_34 : CR_12;
+                        const uint32_t ndbps = mcs == 8 ? 52u : mcs == 9 ? 104u : mcs == 10 ? 156u : mcs == 11 ? 208u : mcs == 12 ? 312u : mcs == 13 ? 416u : 468u;
                         total_symbols = (hl16 * 8u + 16u + 6u + ndbps - 1u) / ndbps + 4u;
                         frame_length = hl16;
                     }
@@ -486,7 +509,8 @@ __global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS, SB_FRONT11N_MINB) k_fr
             }
         }
         // ---- data symbols ----
-        const int q = mcs == 8 ? 0 : 1, nss = 52 * (q + 1);
+        const int nbpsc = mcs == 8 ? 1 : mcs <= 10 ? 2 : mcs <= 12 ? 4 : 6;
+        const int q = mcs == 8 ? 0 : 1, nss = 52 * nbpsc;           // q: BPSK / QPSK position map (the 16-/64-QAM branches look theirs up per symbol)
         const int dh0 = ht_data_index(b0), dh1 = ht_data_index(b1);
         uint8_t pz[2][2][2];                            // [b0 | b1][stream][re | im] position in the stream-parsed symbol
 #pragma unroll
@@ -528,19 +552,38 @@ __global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS, SB_FRONT11N_MINB) k_fr
                 vfo_theta = sx16(vfo_theta + sx16((th0 + th1) >> 1));
                 if (taps.theta && n < taps.max_sym && lane == 0) taps.theta[(size_t)f * taps.max_sym + n] = (int16_t)vfo_theta;
             }
+            if (nbpsc <= 2) {
 #pragma unroll
-            for (int w = 0; w < 2; w++) {
-                if ((w ? dh1 : dh0) < 0) continue;
+                for (int w = 0; w < 2; w++) {
+                    if ((w ? dh1 : dh0) < 0) continue;
 #pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    sb[pz[w][s][0]] = s_demap[(unsigned)min(max(X[s][w].re, -128), 127) & 0xFF];
-                    if (q) sb[pz[w][s][1]] = s_demap[(unsigned)min(max(X[s][w].im, -128), 127) & 0xFF];
+                    for (int s = 0; s < 2; s++) {
+                        sb[pz[w][s][0]] = s_demap[(unsigned)min(max(X[s][w].re, -128), 127) & 0xFF];
+                        if (q) sb[pz[w][s][1]] = s_demap[(unsigned)min(max(X[s][w].im, -128), 127) & 0xFF];
+                    }
+                }
+            } else {                                    // T11nDemapQAM16 / QAM64 (demapper11n.hpp:199-309): limit to [-128, 127], per-bit tables, then the position map
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    const int d = w ? dh1 : dh0;
+                    if (d < 0) continue;
+#pragma unroll
+                    for (int s = 0; s < 2; s++) {
+                        const int re = min(max(X[s][w].re, -128), 127), im = min(max(X[s][w].im, -128), 127);
+                        const uint16_t* pp = N.pos16 + (((nbpsc == 6 ? 2 : 0) + s) * 312 + d * nbpsc);
+                        if (nbpsc == 4) {
+                            sb[__ldg(pp + 0)] = __ldg(N.demap16 + (re & 0xFF)); sb[__ldg(pp + 1)] = __ldg(N.demap16 + 256 + (re & 0xFF));
+                            sb[__ldg(pp + 2)] = __ldg(N.demap16 + (im & 0xFF)); sb[__ldg(pp + 3)] = __ldg(N.demap16 + 256 + (im & 0xFF));
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 3; t++) { sb[__ldg(pp + t)] = __ldg(N.demap64 + 288 * t + 144 + re); sb[__ldg(pp + 3 + t)] = __ldg(N.demap64 + 288 * t + 144 + im); }
+                        }
+                    }
                 }
             }
             __syncwarp();
-            {   uint32_t* dst = (uint32_t*)(sout + soft_bytes); const uint32_t* src = (const uint32_t*)sb; const int nw = nss >> 1;   // 26 or 52 words
-                if (lane < nw) dst[lane] = src[lane];
-                if (lane + 32 < nw) dst[lane + 32] = src[lane + 32]; }
+            {   uint32_t* dst = (uint32_t*)(sout + soft_bytes); const uint32_t* src = (const uint32_t*)sb; const int nw = nss >> 1;   // 26 x N_BPSC words
+                for (int i = lane; i < nw; i += 32) dst[i] = src[i]; }
             soft_bytes += 2 * nss;
             __syncwarp();
         }

@@ -170,6 +170,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
+    uint32_t ht_mcs_limit = 11;                        // first MCS the 802.11n HT-SIG parser refuses (PHY_11n.hpp:497); option "ht_mcs_limit"
     DevBuf soff, slen, spos, snev, sev;                // continuous-capture scout: current slot of every capture, position, event count, event list
     DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx, tabtx11n, txout1; DevTablesTx11n XN{};   // 802.11a transmit tables (built on first use) and staging
     DevTables11n N{}; DevBuf tab11n, iq1;              // 802.11n tables (uploaded on first use) and the second antenna's samples
@@ -731,7 +732,7 @@ static int upload_tables11n(sb200_handle* h) {
     if (!H) return h->fail(SB200_E_NOMEM, "host tables 11n");
     build_host_tables11n(*H);
     size_t o = 0; auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-    const size_t o_sc = take(sizeof H->sincos), o_at = take(sizeof H->atan_lut), o_dm = take(256), o_c8 = take(256), o_pos = take(sizeof H->pos), o_l = take(64), o_ht = take(64);
+    const size_t o_sc = take(sizeof H->sincos), o_at = take(sizeof H->atan_lut), o_dm = take(256), o_c8 = take(256), o_pos = take(sizeof H->pos), o_l = take(64), o_ht = take(64), o_p16 = take(sizeof H->pos16), o_d16 = take(sizeof H->demap16), o_d64 = take(sizeof H->demap64);
     cudaError_t e = h->tab11n.need(o);
     if (e != cudaSuccess) { delete H; return h->fail(SB200_E_NOMEM, "cudaMalloc tables 11n", e); }
     char* base = (char*)h->tab11n.p;
@@ -743,11 +744,15 @@ static int upload_tables11n(sb200_handle* h) {
     if (e == cudaSuccess) e = up(o_pos, H->pos, sizeof H->pos);
     if (e == cudaSuccess) e = up(o_l, H->lltf_pos, 64);
     if (e == cudaSuccess) e = up(o_ht, H->htltf_pos, 64);
+    if (e == cudaSuccess) e = up(o_p16, H->pos16, sizeof H->pos16);
+    if (e == cudaSuccess) e = up(o_d16, H->demap16, sizeof H->demap16);
+    if (e == cudaSuccess) e = up(o_d64, H->demap64, sizeof H->demap64);
     delete H;
     if (e != cudaSuccess) { h->tab11n.release(); return h->fail(SB200_E_CUDA, "table upload 11n", e); }
     DevTables11n& N = h->N;
     N.sincos = (const uint32_t*)(base + o_sc); N.atan_lut = (const int16_t*)(base + o_at); N.demap = (const uint8_t*)(base + o_dm); N.crc8 = (const uint8_t*)(base + o_c8);
     N.pos = (const uint8_t*)(base + o_pos); N.lltf_pos = (const uint8_t*)(base + o_l); N.htltf_pos = (const uint8_t*)(base + o_ht);
+    N.pos16 = (const uint16_t*)(base + o_p16); N.demap16 = (const uint8_t*)(base + o_d16); N.demap64 = (const uint8_t*)(base + o_d64);
     return SB200_OK;
 }
 
@@ -783,7 +788,8 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
         d_iq0 = (const uint32_t*)h->iq.p; d_iq1 = (const uint32_t*)h->iq1.p;
     }
     const uint64_t max_sym = (max_len / 2u) / 80u + 1u;
-    const uint64_t soft_stride = ((max_sym * 208ull) + 15ull) & ~15ull;
+    h->N.mcs_limit = h->ht_mcs_limit;
+    const uint64_t soft_stride = ((max_sym * (h->ht_mcs_limit > 11u ? 624ull : 208ull)) + 15ull) & ~15ull;   // 2 x 52 x N_BPSC soft values per symbol
     const uint64_t row = 1536;                         // >= 1500 (MTU, PHY_11n.hpp:478,505)
     CK(h->info.need(nframes * sizeof(FrameInfo))); CK(h->soft.need(nframes * soft_stride)); CK(h->out.need(nframes * row));
     CK(h->status.need(nframes * 4ull)); CK(h->crc.need(nframes * 4ull)); CK(h->res.need(nframes * sizeof(sb200_frame_result_11n)));
@@ -803,6 +809,7 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
         const unsigned g = (nframes + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         k_viterbi_quad<CR_12><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
         k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
+        if (h->ht_mcs_limit > 13u) k_viterbi_quad<CR_23><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
     } else {
         const unsigned g = (nframes + SB_VR_FR - 1) / SB_VR_FR;
         CK(h->vlist.need(nframes * 12ull)); CK(h->vcnt.need(16));
@@ -810,6 +817,7 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
         k_vit_lists<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, nframes, (uint32_t*)h->vcnt.p, (uint32_t*)h->vlist.p);
         k_viterbi_re<CR_12><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
         k_viterbi_re<CR_34><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        if (h->ht_mcs_limit > 13u) { k_viterbi_re<CR_23><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); h->launches += 1; }
         k_sink11a<<<(nframes + 127) / 128, 128, 0, st>>>((uint8_t*)h->out.p, row, nframes, d_info, h->T, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
         h->launches += 2;
     }
@@ -1223,12 +1231,23 @@ static int upload_tables_tx11n(sb200_handle* h) {
             inv[(bi * 2 + iss - 1) * 104 + r] = (uint8_t)k;
         }
     }
-    cudaError_t e = h->tabtx11n.need(pre.size() * 4 + 512);
+    std::vector<uint16_t> inv16(4 * 312, 0);                                                  // the same for 16-QAM (s = 2) and 64-QAM (s = 3): T11nInterleaveQAM16/64_S1/_S2
+    for (int bi = 0; bi < 2; bi++) for (int iss = 1; iss <= 2; iss++) {
+        const int nbpsc = bi ? 6 : 4, ncbps = 52 * nbpsc, ncol = 13, nrot = 11, ns = nbpsc / 2;
+        for (int k = 0; k < ncbps; k++) {
+            const int i = ncbps / ncol * (k % ncol) + k / ncol, j = ns * (i / ns) + (i + ncbps - ncol * i / ncbps) % ns;
+            const int r = (ncbps + j - (((iss - 1) * 2) % 3 + 3 * ((iss - 1) / 3)) * nrot * nbpsc) % ncbps;
+            inv16[(bi * 2 + iss - 1) * 312 + r] = (uint16_t)k;
+        }
+    }
+    cudaError_t e = h->tabtx11n.need(pre.size() * 4 + 512 + inv16.size() * 2);
     if (e != cudaSuccess) return h->fail(SB200_E_NOMEM, "cudaMalloc tx11n tables", e);
     char* base = (char*)h->tabtx11n.p;
     e = cudaMemcpy(base, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(base + pre.size() * 4, inv.data(), inv.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(base + pre.size() * 4 + 512, inv16.data(), inv16.size() * 2, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { h->tabtx11n.release(); return h->fail(SB200_E_CUDA, "tx11n table upload", e); }
+    h->XN.inv16 = (const uint16_t*)(base + pre.size() * 4 + 512);
     h->XN.pre = (const uint32_t*)base; h->XN.inv = (const uint8_t*)(base + pre.size() * 4);
     return SB200_OK;
 }
@@ -1243,7 +1262,11 @@ extern "C" int sb200_tx11n_batch(sb200_handle* h, const uint8_t* payload, uint64
         case 8:  job.nbpsc = 1; job.code_rate = CR_12; job.ndbps = 52;  job.enc_in = 1; job.parse_in = 13; break;
         case 9:  job.nbpsc = 2; job.code_rate = CR_12; job.ndbps = 104; job.enc_in = 1; job.parse_in = 26; break;
         case 10: job.nbpsc = 2; job.code_rate = CR_34; job.ndbps = 156; job.enc_in = 3; job.parse_in = 26; break;
-        default: return h->fail(SB200_E_INVALID, "mcs must be 8, 9 or 10");
+        case 11: job.nbpsc = 4; job.code_rate = CR_12; job.ndbps = 208; job.enc_in = 1; job.parse_in = 52; break;      // the 16-QAM / 64-QAM branches of the modulator graph
+        case 12: job.nbpsc = 4; job.code_rate = CR_34; job.ndbps = 312; job.enc_in = 3; job.parse_in = 52; break;      // (fb11nmod_config.hpp:133-155: enc11 .. enc14)
+        case 13: job.nbpsc = 6; job.code_rate = CR_23; job.ndbps = 416; job.enc_in = 2; job.parse_in = 78; break;
+        case 14: job.nbpsc = 6; job.code_rate = CR_34; job.ndbps = 468; job.enc_in = 3; job.parse_in = 78; break;
+        default: return h->fail(SB200_E_INVALID, "mcs must be 8 .. 14");
     }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CK(cudaSetDevice(h->device));
@@ -1297,6 +1320,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "front_stage")) { if (value > 2) return h->fail(SB200_E_INVALID, "front_stage is 0, 1 or 2"); h->front_stage = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
     if (!strcmp(name, "slot_table_immutable")) { h->tab_immutable = value != 0; h->tab_off = nullptr; return SB200_OK; }
+    if (!strcmp(name, "ht_mcs_limit")) { if (value < 9 || value > 15) return h->fail(SB200_E_INVALID, "ht_mcs_limit is the first 802.11n MCS index refused: 9 .. 15 (11 = the reference's parser, 15 = MCS 8..14)"); h->ht_mcs_limit = (uint32_t)value; return SB200_OK; }
     return h->fail(SB200_E_INVALID, "unknown option");
 }
 

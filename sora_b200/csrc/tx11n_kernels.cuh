@@ -18,9 +18,10 @@ namespace sb {
 struct DevTablesTx11n {
     const uint32_t* pre;       // [2][1120] packed c16: per stream L-STF + L-LTF (640) then HT-STF + HT-LTF x 2 (480), cyclic shifts applied
     const uint8_t*  inv;       // [2 (BPSK, QPSK)][2 (stream)][104]: air position -> bit index inside the stream's share of the symbol
+    const uint16_t* inv16;     // [2 (16-QAM, 64-QAM)][2 (stream)][312]: the same for the 16-QAM / 64-QAM interleavers
 };
 struct Tx11nJob {
-    uint32_t mcs, nbpsc, code_rate, ndbps;   // 8..10; N_BPSCS; CR_12 / CR_34; N_DBPS over both streams
+    uint32_t mcs, nbpsc, code_rate, ndbps;   // 8..14; N_BPSCS; CR_12 / CR_23 / CR_34; N_DBPS over both streams
     uint32_t enc_in, parse_in;               // input bursts of the encoder and of the stream parser, bytes (conv_enc.hpp, streamparser.hpp)
     uint32_t lead, max_sym;                  // zero samples in front; symbols per frame the grid covers (3 SIG + data)
 };
@@ -29,7 +30,7 @@ __host__ __device__ inline uint32_t tx11n_nsym_signalled(uint32_t len, uint32_t 
 __host__ __device__ inline uint32_t tx11n_nsym_emitted(uint32_t len, const Tx11nJob& j, uint32_t* enc_bits, uint32_t* coded_bits) {
     const uint32_t ns = tx11n_nsym_signalled(len, j.ndbps);
     uint32_t bytes = (ns * j.ndbps + 7u) / 8u; bytes = (bytes + j.enc_in - 1u) / j.enc_in * j.enc_in;
-    const uint32_t cbytes = j.code_rate == CR_12 ? 2u * bytes : bytes / 3u * 4u;
+    const uint32_t cbytes = j.code_rate == CR_12 ? 2u * bytes : j.code_rate == CR_34 ? bytes / 3u * 4u : bytes / 2u * 3u;
     if (enc_bits) *enc_bits = bytes * 8u; if (coded_bits) *coded_bits = cbytes * 8u;
     return (cbytes + j.parse_in - 1u) / j.parse_in;
 }
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(32 * SB_TX11N_WARPS) k_tx11n(const uint8_t* __
         const uint8_t* __restrict__ seeds, uint32_t nframes, Tx11nJob job, DevTables T, DevTablesTx X, DevTablesTx11n N, const uint16_t* __restrict__ inv_deint,
         const uint32_t* __restrict__ crcs, uint32_t* __restrict__ out0, uint32_t* __restrict__ out1, uint64_t out_stride /*samples per slot*/, uint32_t* __restrict__ nsamples) {
     __shared__ uint32_t s_x[SB_TX11N_WARPS][128];
-    __shared__ uint8_t s_d[SB_TX11N_WARPS][168];        // scrambled data bits of the symbol (<= 156), six bits of history in front
+    __shared__ uint8_t s_d[SB_TX11N_WARPS][480];        // scrambled data bits of the symbol (<= 468), six bits of history in front
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x;
     const uint32_t unit = blockIdx.y * SB_TX11N_WARPS + wib;       // (symbol, stream) pairs first, helper warps behind them
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(32 * SB_TX11N_WARPS) k_tx11n(const uint8_t* __
         if (!sig && cbase + k >= coded_bits) return 0u;  // behind the encoder's last burst: the stream parser's pad bytes
         uint32_t n, isb;
         if (cr == CR_12) { n = k >> 1; isb = k & 1u; }
-        else { const uint32_t g = k >> 2, r = k & 3u; n = 3u * g + (r == 3u ? 2u : r >> 1); isb = (r == 1u || r == 3u); }
+        else if (cr == CR_34) { const uint32_t g = k >> 2, r = k & 3u; n = 3u * g + (r == 3u ? 2u : r >> 1); isb = (r == 1u || r == 3u); }
+        else { const uint32_t g = k / 3u, r = k - 3u * g; n = 2u * g + (r == 2u ? 1u : 0u); isb = r == 1u; }          // rate 2/3: A0 B0 A1 (conv_enc.hpp:102-188)
         const uint8_t* d = sd + 6 + n;
         return isb ? (d[0] ^ d[-1] ^ d[-2] ^ d[-3] ^ d[-6]) & 1u : (d[0] ^ d[-2] ^ d[-3] ^ d[-5] ^ d[-6]) & 1u;
     };
@@ -148,7 +150,20 @@ __global__ void __launch_bounds__(32 * SB_TX11N_WARPS) k_tx11n(const uint8_t* __
                 if (dd < 26) { if (bin >= 43) bin++; if (bin >= 57) bin++; } else { if (bin >= 7) bin++; if (bin >= 21) bin++; }
                 cs16 c;
                 if (job.nbpsc == 1) c = mk(coded(2u * __ldg(inv + dd) + iss) ? 30339 : -30339, 0);
-                else c = mk(coded(2u * __ldg(inv + 2 * dd) + iss) ? 21453 : -21453, coded(2u * __ldg(inv + 2 * dd + 1) + iss) ? 21453 : -21453);
+                else if (job.nbpsc == 2) c = mk(coded(2u * __ldg(inv + 2 * dd) + iss) ? 21453 : -21453, coded(2u * __ldg(inv + 2 * dd + 1) + iss) ? 21453 : -21453);
+                else {                                  // TMap11aQAM16<9594> / TMap11aQAM64<4681> (mapper11a.hpp:16-41): Gray level of the M bits, first on air = most significant
+                    const uint32_t M = job.nbpsc >> 1;  // stream parser: M bits to stream 1, M to stream 2, in turn (_b_stream_parser.h:140-275)
+                    const uint16_t* iv = N.inv16 + ((job.nbpsc == 6 ? 2 : 0) + iss) * 312 + dd * job.nbpsc;
+                    int lv[2];
+#pragma unroll
+                    for (int a = 0; a < 2; a++) {
+                        uint32_t g = 0;
+                        for (uint32_t t = 0; t < M; t++) { const uint32_t m = __ldg(iv + a * M + t); g = (g << 1) | coded((2u * (m / M) + iss) * M + m % M); }
+                        uint32_t bin = g; for (uint32_t sh = g >> 1; sh; sh >>= 1) bin ^= sh;
+                        lv[a] = ((int)bin * 2 - ((1 << M) - 1)) * (M == 2 ? 9594 : 4681);
+                    }
+                    c = mk(lv[0], lv[1]);
+                }
                 xs[bin < 32 ? bin : bin + 64] = pack(c);
             }
         }

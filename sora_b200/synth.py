@@ -294,9 +294,11 @@ def make_frames_11b(nframes, psdu_len=1500, rate_kbps=11000, seed0=0xB11B0000, s
 
 # =====================================================================================================================
 # 802.11n HT mixed format, 20 MHz, 2 spatial streams, direct mapping onto 2 transmit chains (IEEE 802.11n-2009 clause 20),
-# MCS 8..10 — the only ones the reference receiver accepts (Brick11/src/PHY_11n.hpp:496-501).  Float modulator, test input only.
+# MCS 8..10 — the ones the reference's HT-SIG parser admits (Brick11/src/PHY_11n.hpp:496-501) — and MCS 11..14 (16-QAM / 64-QAM), which its
+# graphs carry and the engine decodes with option ht_mcs_limit = 15.  Float modulator, test input only.
 # =====================================================================================================================
-HT_MCS = {8: (1, (1, 2), 52), 9: (2, (1, 2), 104), 10: (2, (3, 4), 156)}     # mcs: (N_BPSC per stream, code rate, N_DBPS)
+HT_MCS = {8: (1, (1, 2), 52), 9: (2, (1, 2), 104), 10: (2, (3, 4), 156),       # mcs: (N_BPSC per stream, code rate, N_DBPS)
+          11: (4, (1, 2), 208), 12: (4, (3, 4), 312), 13: (6, (2, 3), 416), 14: (6, (3, 4), 468)}
 
 def _crc8_htsig(b, nbytes=4, tail_bits=2):
     """CRC-8 x^8+x^2+x+1 as the reference computes it (core/inc/CRC8.h:29-50): reflected, init 0xFF, inverted."""
@@ -369,11 +371,16 @@ def modulate_11n(psdus, mcs=8, scramble_seeds=None):
             H = Lf.copy(); H[27] = H[28] = -1; H[64 - 28] = H[64 - 27] = 1
             P = ((1, -1), (1, 1))[ch]
             for n in range(2): parts.append(_ofdm_td(_csd(H, sh_ht) * A0 * P[n]))
-            sb = coded[:, ch::2]                                                                    # stream parser, s = 1
+            sblk = max(nbpsc // 2, 1)                                                               # stream parser: s = max(N_BPSC / 2, 1) bits per stream in turn
+            sb = coded.reshape(nsym, -1, 2, sblk)[:, :, ch, :].reshape(nsym, 52 * nbpsc)
             jm = ht_interleave_map(nbpsc, ch)
             air = np.zeros_like(sb); air[:, jm] = sb
             if nbpsc == 1: pts = 2.0 * air - 1.0 + 0j
-            else: q = air.reshape(nsym, 52, 2); pts = ((2.0 * q[..., 0] - 1) + 1j * (2.0 * q[..., 1] - 1)) / np.sqrt(2.0)
+            elif nbpsc == 2: q = air.reshape(nsym, 52, 2); pts = ((2.0 * q[..., 0] - 1) + 1j * (2.0 * q[..., 1] - 1)) / np.sqrt(2.0)
+            else:                                                                                   # Gray-coded 16-QAM / 64-QAM, unit average power (clause 17.3.5.7 levels)
+                h = nbpsc // 2; q = air.reshape(nsym, 52, nbpsc).astype(np.int64); w = (1 << np.arange(h))
+                ii = (q[..., :h] * w).sum(-1); qq = (q[..., h:] * w).sum(-1)
+                pts = (_GRAY[h][ii] + 1j * _GRAY[h][qq]) / np.sqrt(10.0 if h == 2 else 42.0)
             fr = np.zeros((nsym, 64), np.complex128)
             idx = np.array([k % 64 for k in list(range(-28, 0)) + list(range(1, 29)) if k not in (-21, -7, 7, 21)])
             fr[:, idx] = pts

@@ -142,16 +142,21 @@ def rx11n_taps(iq0, iq1, max_sym=300):
     res = np.zeros(1, dtype=RES11N_DTYPE)
     siso = np.zeros((2, 64, 2), np.int16); hinv = np.zeros((4, 64, 2), np.int16)
     fo = np.zeros((2, max_sym, 64, 2), np.int16); eq = np.zeros((2, max_sym, 64, 2), np.int16)
-    soft = np.zeros(max_sym * 208, np.uint8); nsoft = C.c_uint32(0); theta = np.zeros(max_sym, np.int16); sig = np.zeros(9, np.uint8); nfft = C.c_int(0)
+    soft = np.zeros(max_sym * 624, np.uint8); nsoft = C.c_uint32(0); theta = np.zeros(max_sym, np.int16); sig = np.zeros(9, np.uint8); nfft = C.c_int(0)
     nd = lib().sbo_rx11n_taps(_p(iq0), _p(iq1), C.c_uint64(iq0.reshape(-1, 2).shape[0]), _p(res), _p(siso), _p(hinv), _p(fo), _p(eq), _p(soft),
                               C.byref(nsoft), _p(theta), _p(sig), C.c_int(max_sym), C.byref(nfft))
     return dict(res=res[0], siso=siso, hinv=hinv, fft_out=fo[:, :nfft.value], eq=eq[:, :nd], soft=soft[:nsoft.value], theta=theta[:nd], sig=sig, ndata=nd)
 
 def tables11n():
     sc = np.zeros((65536, 2), np.int16); at = np.zeros(4097, np.int16); dm = np.zeros(256, np.uint8); c8 = np.zeros(256, np.uint8)
-    di = np.zeros((2, 2, 104), np.uint8); ls = np.zeros(64, np.uint8); hs = np.zeros(64, np.uint8)
+    di = np.zeros((4, 2, 312), np.uint16); ls = np.zeros(64, np.uint8); hs = np.zeros(64, np.uint8)
     lib().sbo_tables11n(_p(sc), _p(at), _p(dm), _p(c8), _p(di), _p(ls), _p(hs))
-    return dict(sincos=sc, atan=at, demap=dm, crc8=c8, deint=di, lltf_sign=ls, htltf_sign=hs)
+    d16 = np.zeros((2, 256), np.uint8); d64 = np.zeros((3, 288), np.uint8); lib().sbo_tables11n_qam(_p(d16), _p(d64))
+    return dict(sincos=sc, atan=at, demap=dm, crc8=c8, deint=di, lltf_sign=ls, htltf_sign=hs, demap16=d16, demap64=d64)
+
+def set_ht_mcs_limit(first_refused=11):
+    """11 = the reference's HT-SIG parser as shipped (MCS 8..10); 15 = the 16-/64-QAM branches enabled (MCS 8..14)."""
+    lib().sbo_set_ht_mcs_limit(C.c_uint32(first_refused))
 
 
 # ---- 802.11a transmit (brick modulator restatement) ---------------------------------------------------------------------
@@ -198,7 +203,7 @@ def tx11b_taps():
 def tx11n_modulate(payload, mcs, seed=0xAB):
     """payload: MPDU bytes without FCS.  Returns two int16 [n, 2] streams at 40 Msps (what `demod11` writes to *_0.dmp / *_1.dmp)."""
     payload = np.ascontiguousarray(payload, dtype=np.uint8); L = lib(); L.sbo_tx11n_modulate.restype = C.c_uint64
-    sig = C.c_uint32(0); nsym = L.sbo_tx11n_nsym(C.c_uint32(len(payload)), C.c_uint32(mcs), C.byref(sig)); assert nsym, "mcs must be 8, 9 or 10"
+    sig = C.c_uint32(0); nsym = L.sbo_tx11n_nsym(C.c_uint32(len(payload)), C.c_uint32(mcs), C.byref(sig)); assert nsym, "mcs must be 8 .. 14"
     cap = 640 + 480 + 480 + 160 * nsym
     o0 = np.zeros((cap, 2), np.int16); o1 = np.zeros((cap, 2), np.int16)
     n = L.sbo_tx11n_modulate(_p(payload), C.c_uint32(len(payload)), C.c_uint32(mcs), C.c_uint8(seed), _p(o0), _p(o1), C.c_uint64(cap))
