@@ -304,6 +304,30 @@ __device__ __forceinline__ cfl cmulf(cfl a, cfl b) {        // vector128.h:1106-
 }
 
 #define SB_FRONT11N_WARPS 4
+// T11nDemapQAM16 / QAM64 (demapper11n.hpp:199-309) for the two carriers of a lane, both streams: limit to [-128, 127], per-bit tables, then the
+// position map (HT de-interleaver + stream joiner).  Kept out of line so that the BPSK / QPSK symbol loop keeps its register allocation.
+__device__ __noinline__ void demap_qam11n(uint8_t* sb, const uint16_t* __restrict__ pos16, const uint8_t* __restrict__ demap16, const uint8_t* __restrict__ demap64,
+                                          int nbpsc, int dh0, int dh1, uint32_t x00, uint32_t x01, uint32_t x10, uint32_t x11) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        const int d = w ? dh1 : dh0;
+        if (d < 0) continue;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const cs16 x = unpack(s ? (w ? x11 : x10) : (w ? x01 : x00));
+            const int re = min(max(x.re, -128), 127), im = min(max(x.im, -128), 127);
+            const uint16_t* pp = pos16 + (((nbpsc == 6 ? 2 : 0) + s) * 312 + d * nbpsc);
+            if (nbpsc == 4) {
+                sb[__ldg(pp + 0)] = __ldg(demap16 + (re & 0xFF)); sb[__ldg(pp + 1)] = __ldg(demap16 + 256 + (re & 0xFF));
+                sb[__ldg(pp + 2)] = __ldg(demap16 + (im & 0xFF)); sb[__ldg(pp + 3)] = __ldg(demap16 + 256 + (im & 0xFF));
+            } else {
+#pragma unroll
+                for (int t = 0; t < 3; t++) { sb[__ldg(pp + t)] = __ldg(demap64 + 288 * t + 144 + re); sb[__ldg(pp + 3 + t)] = __ldg(demap64 + 288 * t + 144 + im); }
+            }
+        }
+    }
+}
+
 #ifndef SB_FRONT11N_MINB
 #define SB_FRONT11N_MINB 6         // resident CTAs per SM the register allocation aims at (profiles/README.md, front-end sweep)
 #endif
@@ -562,25 +586,7 @@ __global__ void __launch_bounds__(32 * SB_FRONT11N_WARPS, SB_FRONT11N_MINB) k_fr
                         if (q) sb[pz[w][s][1]] = s_demap[(unsigned)min(max(X[s][w].im, -128), 127) & 0xFF];
                     }
                 }
-            } else {                                    // T11nDemapQAM16 / QAM64 (demapper11n.hpp:199-309): limit to [-128, 127], per-bit tables, then the position map
-#pragma unroll
-                for (int w = 0; w < 2; w++) {
-                    const int d = w ? dh1 : dh0;
-                    if (d < 0) continue;
-#pragma unroll
-                    for (int s = 0; s < 2; s++) {
-                        const int re = min(max(X[s][w].re, -128), 127), im = min(max(X[s][w].im, -128), 127);
-                        const uint16_t* pp = N.pos16 + (((nbpsc == 6 ? 2 : 0) + s) * 312 + d * nbpsc);
-                        if (nbpsc == 4) {
-                            sb[__ldg(pp + 0)] = __ldg(N.demap16 + (re & 0xFF)); sb[__ldg(pp + 1)] = __ldg(N.demap16 + 256 + (re & 0xFF));
-                            sb[__ldg(pp + 2)] = __ldg(N.demap16 + (im & 0xFF)); sb[__ldg(pp + 3)] = __ldg(N.demap16 + 256 + (im & 0xFF));
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 3; t++) { sb[__ldg(pp + t)] = __ldg(N.demap64 + 288 * t + 144 + re); sb[__ldg(pp + 3 + t)] = __ldg(N.demap64 + 288 * t + 144 + im); }
-                        }
-                    }
-                }
-            }
+            } else demap_qam11n(sb, N.pos16, N.demap16, N.demap64, nbpsc, dh0, dh1, pack(X[0][0]), pack(X[0][1]), pack(X[1][0]), pack(X[1][1]));
             __syncwarp();
             {   uint32_t* dst = (uint32_t*)(sout + soft_bytes); const uint32_t* src = (const uint32_t*)sb; const int nw = nss >> 1;   // 26 x N_BPSC words
                 for (int i = lane; i < nw; i += 32) dst[i] = src[i]; }
