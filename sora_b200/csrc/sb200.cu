@@ -103,20 +103,8 @@ bool is_device_ptr(const void* p) {
 // "host_decimate" = T > 0 the chunked host-IQ path gathers the even samples of every slot of a chunk into pinned staging memory with T host
 // threads and sends only those over PCIe (half the bytes); the kernels then read the packed copy with stride 1 (sh = 0).  Results are
 // identical: the same samples reach the same arithmetic.
-static void decimate_slot(const uint32_t* __restrict__ src, uint32_t n2, uint32_t* __restrict__ dst) {     // dst[j] = src[2 j], j < n2
-    uint32_t j = 0;
-    // the packed copy is written once and read by the DMA engine only: streaming stores keep it from costing a read-for-ownership and from
-    // pushing the capture out of the cache.  Head up to a 16-byte boundary of dst, then 4 samples per store.
-    for (; j < n2 && ((uintptr_t)(dst + j) & 15u); j++) dst[j] = src[2 * j];
-    for (; j + 8 <= n2; j += 8) {
-        const __m128 a = _mm_loadu_ps((const float*)(src + 2 * j)), b = _mm_loadu_ps((const float*)(src + 2 * j + 4));
-        const __m128 c = _mm_loadu_ps((const float*)(src + 2 * j + 8)), d = _mm_loadu_ps((const float*)(src + 2 * j + 12));
-        _mm_prefetch((const char*)(src + 2 * j + 256), _MM_HINT_NTA);
-        _mm_stream_ps((float*)(dst + j), _mm_shuffle_ps(a, b, 0x88));
-        _mm_stream_ps((float*)(dst + j + 4), _mm_shuffle_ps(c, d, 0x88));
-    }
-    for (; j < n2; j++) dst[j] = src[2 * j];
-}
+namespace sb { void gather_even(const uint32_t* src, uint32_t n2, uint32_t* dst); }      // host_gather.cpp: dst[j] = src[2 j], streaming stores, SSE2 / AVX-512 chosen at run time
+static inline void decimate_slot(const uint32_t* src, uint32_t n2, uint32_t* dst) { sb::gather_even(src, n2, dst); }
 struct DecimPool {
     struct Job { const uint32_t* iq; const uint64_t* off; const uint32_t* len; const uint64_t* doff; uint32_t f0, f1; uint32_t* dst; };
     std::vector<std::thread> th; std::mutex m; std::condition_variable cv, cv_done;
