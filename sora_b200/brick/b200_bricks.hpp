@@ -130,7 +130,7 @@ public:
         BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf, rx_frame_buf) BIND_CONTEXT(CF_RxFrameBuffer::rx_frame_buf_size, rx_frame_buf_size)
         BIND_CONTEXT(CF_11CCA::cca_pwr_threshold, cca_pwr_threshold) BIND_CONTEXT(CF_11CCA::cca_peak_index, cca_peak_index)
         BIND_CONTEXT(CF_11CCA::cca_state, cca_state) BIND_CONTEXT(CF_CFOffset::CFO_est, CFO_est)
-        , ok_(false), ev_next_(0), window_(0), decoded_upto_(0), max_events_(64), truncated_(false)
+        , ok_(false), ev_next_(0), window_(0), decoded_upto_(0), max_events_(256), truncated_(false)
     {
         ok_ = B200Engine::Get(cca_pwr_threshold).h != nullptr;                                   // no CPU fallback
         if (!ok_) error_code = E_ERROR_FAILED;

@@ -1,6 +1,6 @@
 // Builds a brick graph the way kernel/bb/demod11/fb11ademod_config.hpp does, with the CPU sub-chain ds2..fsink replaced
 // by the GPU brick, and drives it like RxThread (kernel/bb/demod11/fb11a_demod.cpp:29-81) over a Sora dump file.
-//   usage: demo_graph <file.dmp> [legacy14] [--threads K] [--window N] [--repeat R]   (see main)
+//   usage: demo_graph <file.dmp> [legacy14] [--threads K] [--window N] [--repeat R] [--max-events E]   (see main)
 #include "b200_bricks.hpp"
 #include <cstdio>
 #include <string>
@@ -42,6 +42,7 @@ struct DemodCtx : LOCAL_CONTEXT(TB200Dot11aRx), LOCAL_CONTEXT(TMemSamples), LOCA
 };
 
 // one graph instance driven like RxThread over `iq`; returns the number of frame events (and FRAME_OK among them)
+static unsigned g_max_events = 0;                             // --max-events N: events one decoded window may hold (0 = the adaptor's default)
 static int run_graph(std::vector<COMPLEX16>& iq, size_t window, bool print, int* ok_frames) {
     DemodCtx* ctx = new DemodCtx(); static thread_local uchar frame[4096];
     ctx->CF_MemSamples::Init(iq.data(), (uint)(iq.size() * sizeof(COMPLEX16)));
@@ -51,6 +52,7 @@ static int run_graph(std::vector<COMPLEX16>& iq, size_t window, bool print, int*
     CREATE_BRICK_FILTER(gpurx, TB200Dot11aRx, *ctx, fsink);
     CREATE_BRICK_SOURCE(fsrc, TMemSamples, *ctx, gpurx);
     gpurx->SetSlotSamples(window);
+    if (g_max_events) gpurx->SetMaxEventsPerWindow(g_max_events);
     ISource* ssrc = fsrc;
     int nframes = 0, nok = 0;
     for (;;) {                                               // RxThread
@@ -90,6 +92,7 @@ int main(int argc, char** argv) {
         else if (a == "--threads" && i + 1 < argc) K = atoi(argv[++i]);
         else if (a == "--window" && i + 1 < argc) window = (size_t)atoll(argv[++i]);
         else if (a == "--repeat" && i + 1 < argc) R = atoi(argv[++i]);
+        else if (a == "--max-events" && i + 1 < argc) g_max_events = (unsigned)atoi(argv[++i]);
     }
     while (fread(blk, 1, 128, f) == 128) {                  // LoadSoraDumpFile: strip the 16-byte RX_BLOCK descriptor (brickutil.h:21-59)
         const COMPLEX16* s = (const COMPLEX16*)(blk + 16);

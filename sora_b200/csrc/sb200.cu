@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <chrono>
 #include <string.h>
 #include <new>
 #include <stdio.h>
@@ -532,11 +533,16 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
     for (uint32_t s = 0; s < nstreams; s++) { nframes_out[s] = 0; if (stream_off[s] + stream_len[s] > iq_total) return h->fail(SB200_E_INVALID, "capture exceeds iq_total_samples"); }
     if (nstreams == 0 || max_frames == 0) return SB200_OK;
     const int16_t* d_iq = iq;
-    if (!is_device_ptr(iq)) { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const int16_t*)h->iq.p; }
+    if (!is_device_ptr(iq)) {                           // host captures: only the ranges the streams name travel (they may be islands in a large arena)
+        CK(h->iq.need(iq_total * 4ull));
+        for (uint32_t s = 0; s < nstreams; s++) if (stream_len[s]) CK(cudaMemcpyAsync((char*)h->iq.p + stream_off[s] * 4ull, iq + 2ull * stream_off[s], stream_len[s] * 4ull, cudaMemcpyHostToDevice, st));
+        d_iq = (const int16_t*)h->iq.p;
+    }
     // Phase 1, scout: carrier sense + SIGNAL only, one pass per event of the busiest capture; positions, DC estimates and the event list stay on
     // the device, the host only reads a "captures still live" counter every few passes.  Where a frame ends depends on its header alone, so the
     // expensive part (data symbols, Viterbi) need not sit inside this serial chain.
     const uint32_t n = nstreams;
+    const bool trace = getenv("SB200_TRACE") != nullptr; const auto t_begin = std::chrono::steady_clock::now();
     std::vector<uint64_t> off0(n); std::vector<uint32_t> len0(n);
     for (uint32_t s = 0; s < n; s++) { off0[s] = stream_off[s]; len0[s] = stream_len[s] >= 28u ? stream_len[s] : 0u; }
     CK(h->soff.need(n * 8ull)); CK(h->slen.need(n * 4ull)); CK(h->dcbuf.need(n * sizeof(int2))); CK(h->spos.need(n * 4ull)); CK(h->snev.need(n * 4ull + 64));
@@ -560,6 +566,7 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
         done_passes += k;
         if (live[k - 1] == 0) break;
     }
+    const auto t_scout = std::chrono::steady_clock::now();
     // Phase 2: every event is an independent slot (start of the search, length up to the block after its last symbol, the DC estimate the search
     // started with): one batch through the ordinary pipeline.
     std::vector<uint32_t> nev(n); CK(cudaMemcpy(nev.data(), h->snev.p, n * 4ull, cudaMemcpyDeviceToHost));
@@ -587,6 +594,9 @@ extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t 
             }
             nframes_out[s] = nev[s];
         } }
+    if (trace) { const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sb200] rx11a_streams: %u captures, %zu events, %llu samples: scout %.3f ms, batch %.3f ms\n", n, E, (unsigned long long)iq_total,
+                std::chrono::duration<double, std::milli>(t_scout - t_begin).count(), std::chrono::duration<double, std::milli>(t_end - t_scout).count()); }
     return rc;
 }
 

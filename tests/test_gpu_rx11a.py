@@ -182,8 +182,9 @@ def test_brick_adaptor_finds_every_frame_of_a_capture(tmp_path):
     iq, _ = synth.make_frames(70, psdu_len=30, rate_kbps=24000, snr_db=30, seed0=0xB00, lead=200, trail=220)   # more frames than one window's event list holds
     many = iq.reshape(-1, 2); many = many[: len(many) // 28 * 28]
     p2 = tmp_path / "many.dmp"; write_dump(str(p2), many)
-    ev = [json.loads(l) for l in subprocess.run([exe, str(p2)], capture_output=True, text=True, timeout=120).stdout.splitlines() if l.startswith("{")]
-    assert len(ev) == 70 and all(int(e["error_code"], 16) == 1 and e["length"] == 30 for e in ev)
+    for extra in ([], ["--max-events", "16"]):          # the second run fills the event list of a window five times over: the window is re-armed, no frame is lost
+        ev = [json.loads(l) for l in subprocess.run([exe, str(p2)] + extra, capture_output=True, text=True, timeout=120).stdout.splitlines() if l.startswith("{")]
+        assert len(ev) == 70 and all(int(e["error_code"], 16) == 1 and e["length"] == 30 for e in ev)
     out = subprocess.run([exe, str(p), "--threads", "6"], capture_output=True, text=True, timeout=180).stdout
     summ = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     assert summ["graph_instances"] == 6 and summ["events"] == 6 * len(ores) and summ["frames_ok"] == 6 * int((ores["status"] == 1).sum())
