@@ -113,40 +113,49 @@ template <int CODE_RATE, int s> __device__ __forceinline__ uint32_t vr_bm(const 
 }
 
 // Windowed traceback (viterbi.hpp:205-237) from slot A0 at time t over la + nout columns; the newest block (kp = t mod 8 columns, 0 = a whole
-// one) is in ring entry e.  The nout decoded bits end at byte wpos (exclusive) of the output row and are written last-first.
+// one) is in ring entry e.  The walk is a chain of dependent shared-memory look-ups, one per 8 columns, done by one lane of the quad; it only
+// collects the history bytes it passes, newest first, into the quad's scratch row `hb`: byte 0 = the kp decisions of the running block (right
+// aligned; absent when kp = 0), then one byte per block, bit 7 = the newest column of the block.  vr_emit turns the row into output bytes.
 // Kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the step loop.
-__device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t wpos,
-                                          uint32_t e, const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
-    uint32_t A = A0, todo = la + nout;
-    uint32_t fifo = 0; int cnt = -(int)la;                  // the first `la` bits are only looked through; at most 15 bits wait
+#define SB_VR_HB 48                                          // >= (7 + 31 + 256 + 6) / 8 + 2
+__device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ hb, uint32_t e, const uint32_t A0, const uint32_t t, uint32_t todo) {
+    uint32_t A = A0, j = 0;
     uint32_t tt = t;                                         // time of the newest column not yet walked
     const uint32_t kp = t & 7u;
-    auto emit = [&]() { while (cnt >= 8) { --wpos; if (wpos < out_cap) op[wpos] = (uint8_t)(fifo >> (cnt - 8)); cnt -= 8; } };
     if (kp) {                                                // running block: kp decisions in bits 0..kp-1, one slot-address bit changes per column
         const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
         const uint32_t take = min(kp, todo);
-        for (uint32_t j = 0; j < take; j++) {                // column tt - j was produced at phase (tt - j - 1) mod 6: bit 5 - phase is replaced
-            const uint32_t b = 5u - (tt - j - 1u) % 6u, d = (h >> (kp - 1u - j)) & 1u;
+        for (uint32_t c = 0; c < take; c++) {                // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
+            const uint32_t b = 5u - (tt - c - 1u) % 6u, d = (h >> (kp - 1u - c)) & 1u;
             A = (A & ~(1u << b)) | (d << b);
         }
-        fifo = (h & ((1u << kp) - 1u)) >> (kp - take); cnt += (int)take;
-        emit();
+        hb[j++] = (uint8_t)(h & ((1u << kp) - 1u));
         todo -= take; tt -= kp; e = e ? e - 1u : SB_VR_NB - 1u;
     }
     uint32_t ph = tt % 6u;                                   // phase of the block boundary the walk stands on
+    const uint8_t* rp = ring_b + e * (SB_VR_FR * 64);
     while (todo >= 8u) {
-        const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
+        const uint32_t h = rp[A];
+        hb[j++] = (uint8_t)h;
         const uint32_t r = __brev(h) >> 24;                  // r bit i = h bit 7 - i = decision of column tt - i
         const uint32_t G = (r & 0x3Cu) | (r >> 6);           // slot-address bit (i - ph) mod 6 <- column tt - i, the two oldest overriding i = 0, 1
-        A = ((G >> ph) | (G << (6u - ph))) & 63u;
-        fifo = (fifo << 8) | h; cnt += 8;
-        emit();
-        todo -= 8u; e = e ? e - 1u : SB_VR_NB - 1u; ph = ph >= 2u ? ph - 2u : ph + 4u;   // (tt - 8) mod 6
+        A = ((G | (G << 6)) >> ph) & 63u;
+        todo -= 8u; ph = ph >= 2u ? ph - 2u : ph + 4u;       // (tt - 8) mod 6
+        rp = rp == ring_b ? ring_b + (SB_VR_NB - 1u) * (SB_VR_FR * 64) : rp - SB_VR_FR * 64;
     }
-    if (todo) {                                              // oldest block of the window: only its newest `todo` columns
-        const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
-        fifo = (fifo << todo) | (h >> (8u - todo)); cnt += (int)todo;
-        emit();
+    if (todo) hb[j++] = rp[A];                               // oldest block of the window: only its newest `todo` columns count
+    hb[j] = 0; hb[j + 1] = 0;
+}
+// The nout / 8 decoded bytes of a window from the scratch row: bit k of the walk (k = 0 the newest column) sits at row bit (8 - kp) % 8 + k,
+// counted from bit 7 of byte 0; the first la bits are only looked through, byte m of the output (m = 0 the LAST byte of the window) is the
+// eight bits from la + 8 m on, newest in bit 7.  All four lanes of the quad take part; byte m goes to op[first + nbytes - 1 - m].
+__device__ __forceinline__ void vr_emit(const uint8_t* __restrict__ hb, uint8_t* __restrict__ op, const uint32_t out_cap, const uint32_t first, const uint32_t nbytes,
+                                        const uint32_t kp, const uint32_t la, const uint32_t q) {
+    const uint32_t s0 = ((8u - kp) & 7u) + la, sh = s0 & 7u, i0 = s0 >> 3;
+    for (uint32_t m = q; m < nbytes; m += 4u) {
+        const uint32_t v = ((uint32_t)hb[i0 + m] << 8) | hb[i0 + m + 1u];
+        const uint32_t at = first + nbytes - 1u - m;
+        if (at < out_cap) op[at] = (uint8_t)(v >> (8u - sh));
     }
 }
 // best state at time t (phase tm): smallest (byte = m7 << 1 | newest mark, state index) over the 64 slots of a code block (viterbicore.h:468-520);
@@ -185,7 +194,7 @@ struct VrDecoder {
     uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves, as registers
     uint32_t mk[8], mkA[2][4], mkB[2][4], mkH[4], mkL[4];   // history marks 0x00010001 << j as registers; per lane-pair phase and chunk; T = 5 halves
     unsigned QM; int q;
-    uint4* ring_q; const uint8_t* ring_b;
+    uint4* ring_q; const uint8_t* ring_b; uint8_t* hb;   // hb: the quad's traceback scratch row (SB_VR_HB bytes of shared memory)
     const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
     uint32_t depth, look, end, ob, next_tb, nraw, wslot;
     bool done;
@@ -224,7 +233,9 @@ struct VrDecoder {
     // windowed traceback from slot A0 at time t (viterbi.hpp:205-237): one lane of the quad walks the ring (vr_traceback)
     __device__ __forceinline__ void traceback(const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
         __syncwarp(QM);
-        if (q == 0) vr_traceback(ring_b, op, out_cap, nraw + (nout >> 3), wslot, A0, t, la, nout);
+        if (q == 0) vr_traceback(ring_b, hb, wslot, A0, t, la + nout);
+        __syncwarp(QM);
+        vr_emit(hb, op, out_cap, nraw, nout >> 3, t & 7u, la, (uint32_t)q);
         nraw += nout >> 3;
         __syncwarp(QM);
     }
@@ -301,6 +312,7 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out) {
     __shared__ uint4 s_ring[SB_VR_NB][SB_VR_FR][4];    // entry: history bytes of the 64 slots of every code block over 8 columns
+    __shared__ uint8_t s_hb[SB_VR_FR][SB_VR_HB];       // traceback scratch: the history bytes a walk passed, per code block
     using D = VrDecoder<CODE_RATE>;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
@@ -347,6 +359,7 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
     d.ring_q = &s_ring[0][fb][q];                       // + entry * (SB_VR_FR * 4)
     d.ring_b = (const uint8_t*)&s_ring[0][fb][0];       // + entry * (SB_VR_FR * 64) + slot
+    d.hb = s_hb[fb];
 
     // lockstep part: all eight code blocks of the warp advance together, 24 or 6 steps at a time; the soft values of the next four chunks
     // are always in registers
