@@ -7,6 +7,7 @@
   --config tx11a     SURVEY.md §8(f) rank 2: the 802.11a modulator on the device, 54 Mbps / 1500 B frames into config #2's slots
   --config tx11b     SURVEY.md §8(f) rank 2: the 802.11b modulator on the device, 11 Mbps CCK / 1500 B frames at 44 Msps
   --config tx11n     the 802.11n two-stream modulator on the device, MCS 8 / 9 / 10, 1500 B frames: the input of config #4 made on the device
+  --config fir37     the legacy 802.11b transmit filter (BB11BPMDSpreadFIR4SSE) on the device
   --config 11n       config #4: 802.11n HT-MF 2x2 RX chain at MCS 8, 9, 10, PSDU 1500 B, 2 x 40 Msps, fixed 2x2 channel
 
 Each prints one JSON line per measurement (same timing rules as bench.py: >= 3 warm-ups, CUDA events on the launch
@@ -145,9 +146,11 @@ def bench_11n(args):
     import oracle_py
     from sora_b200 import api, synth
     c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st; dist = c.dist
-    for mcs in (8, 9, 10):
+    mcs_list = [int(m) for m in args.mcs.split(",")]
+    if max(mcs_list) > 10: eng.set_option("ht_mcs_limit", 15); oracle_py.set_ht_mcs_limit(15)      # the 16-/64-QAM branches (default: refuse like PHY_11n.hpp:496-501)
+    for mcs in mcs_list:
         U = 32
-        iq0, iq1, ps = synth.make_frames_11n(U, psdu_len=1500, mcs=mcs, snr_db=30, lead=400, trail=200)      # fixed 2x2 channel [[1, 0.3j], [-0.2, 0.9]]
+        iq0, iq1, ps = synth.make_frames_11n(U, psdu_len=1500, mcs=mcs, snr_db=30 if mcs <= 10 else 36, lead=400, trail=200)      # fixed 2x2 channel [[1, 0.3j], [-0.2, 0.9]]
         F0, slot, _ = iq0.shape
         F = args.frames
         d0 = torch.from_numpy(iq0.reshape(U, -1)).to(dev).repeat((F + U - 1) // U, 1)[:F].contiguous()
@@ -319,6 +322,29 @@ def bench_tx11n(args):
                           "parity": "bit-exact vs the transmit oracle on 3 frames; every slot pair decodes FRAME_OK through the 802.11n receive path"}))
         del d0, d1
 
+def bench_fir37(args):
+    """The legacy 802.11b transmit filter (BB11BPMDSpreadFIR4SSE) on device-resident chip streams: one frame = 1500 B at 11 Mbps CCK, 4x zero-stuffed."""
+    import oracle_py
+    c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st
+    F = args.frames; L = ((24 * 88 + 1504 * 8) * 4 + 64 + 7) // 8 * 8                       # chips x 4 of one frame, rounded to the filter's 8-sample blocks
+    rng = np.random.default_rng(7); U = 16
+    host = np.zeros((U, L, 2), np.int8); k = rng.integers(0, 4, (U, L // 4))
+    host[:, ::4, 0] = np.array([127, 0, -128, 0], np.int8)[k]; host[:, ::4, 1] = np.array([0, 127, 0, -128], np.int8)[k]
+    x = torch.from_numpy(host.reshape(U, -1)).to(dev).repeat((F + U - 1) // U, 1)[:F].contiguous(); y = torch.empty_like(x)
+    d_off = torch.arange(F, dtype=torch.int64, device=dev) * L; d_len = torch.full((F,), L, dtype=torch.int32, device=dev)
+    def step(): eng.tx11b_fir37_raw(x.data_ptr(), F * L, d_off.data_ptr(), d_len.data_ptr(), F, 0, y.data_ptr(), st.cuda_stream)
+    step(); torch.cuda.synchronize()
+    got = y[:U].cpu().numpy().reshape(U, L, 2)
+    for i in range(U): assert (got[i] == oracle_py.fir37_legacy(host[i], 0)).all(), "filter output differs from the oracle"
+    if oracle_py.ref_fir37_available(): assert (got[0] == oracle_py.ref_fir37(host[0])).all(), "filter output differs from the reference's compiled body"
+    ms = c.timed(step, args.steps)
+    alg = F * L * 4.0
+    c.emit({"metric": "legacy 802.11b transmit filter Msamples/s (COMPLEX8 in, COMPLEX8 out)", "value": c.world * F * L / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms, "n_gpus": c.world,
+            "config": {"workload": "BB11BPMDSpreadFIR4SSE, 37 taps, 44 Msps chip streams of 1500 B / 11 Mbps frames", "frames_per_step_per_gpu": F, "samples_per_frame": L},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks(), "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks(), "note": "4 B per sample: 2 read + 2 written"},
+            "parity": "equal to the oracle on the %d unique frames%s" % (U, " and to the reference's compiled filter body (oracle/_ref)" if oracle_py.ref_fir37_available() else "")})
+    c.close()
+
 def bench_fir(args):
     """The anti-alias FIR decimator on a device-resident capture: the one streaming (HBM-bound) stage of the path; 6 B per input sample."""
     c = Ctx(); torch = c.torch; eng, dev, st = c.eng, c.dev, c.st
@@ -342,9 +368,10 @@ def bench_fir(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b", "tx11n", "fir"], required=True)
+    ap.add_argument("--config", choices=["viterbi", "11b", "11n", "tx11a", "tx11b", "tx11n", "fir", "fir37"], required=True)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--blocks", type=int, default=0, help="Viterbi code blocks per GPU (0 = BASELINE config #5: 1e9 coded bits in total over all GPUs)")
     ap.add_argument("--frames", type=int, default=32768)
+    ap.add_argument("--mcs", default="8,9,10", help="802.11n MCS list for --config 11n (11..14 enable the engine option ht_mcs_limit = 15)")
     a = ap.parse_args()
-    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b, "tx11n": bench_tx11n, "fir": bench_fir}[a.config](a)
+    {"viterbi": bench_viterbi, "11b": bench_11b, "11n": bench_11n, "tx11a": bench_tx11a, "tx11b": bench_tx11b, "tx11n": bench_tx11n, "fir": bench_fir, "fir37": bench_fir37}[a.config](a)

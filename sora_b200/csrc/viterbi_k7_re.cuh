@@ -57,28 +57,33 @@ struct VrLane {
 //   T <= 1 : mA = mark if this lane holds the odd role else 0, mB = mark - mA;   T = 2..4 : mA = mark;   T = 5 : mA = mark << 16 part, mB = low part.
 // The marks come in as registers so that every constant add is an IMAD.IADD (FMA pipe), not an immediate VIADD (ALU pipe, the busy one).
 // WARP: the whole warp executes the step together (full-mask shuffle).
-template <int T, bool WARP>
-__device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, const VrLane& L, const uint32_t KC, const uint32_t mA, const uint32_t mB, const unsigned qmask) {
+// LB = lane bits of the slot address: 2 = four lanes per code block, 8 registers per lane (slot = lane << 4 | reg << 1 | half);
+//                                      1 = two lanes per code block, 16 registers per lane (slot = lane << 5 | reg << 1 | half).
+// The address bit replaced at phase T is bit 5 - T: a lane bit for T < LB (exchange with lane xor 1 << (LB - 1 - T)), a register bit for
+// LB <= T <= 4 (pair r, r + (1 << (4 - T))), the half for T = 5.
+template <int T, bool WARP, int LB>
+__device__ __forceinline__ void vr_step(uint32_t (&R)[8 << (2 - LB)], const uint32_t Cbase, const VrLane& L, const uint32_t KC, const uint32_t mA, const uint32_t mB, const unsigned qmask) {
+    constexpr int NR = 8 << (2 - LB);
     uint32_t V[4];                                      // [0, Cb[c], 0, Cb[c ^ K]]: branch metrics of class c (low half) and its high-half companion
     V[0] = __byte_perm(Cbase, 0, L.sel[T][0]); V[1] = __byte_perm(Cbase, 0, L.sel[T][1]);
     V[3] = vr_frsub(V[0], KC); V[2] = vr_frsub(V[1], KC);                 // complement classes; no borrow: every half of V is <= its half of KC
-    if constexpr (T <= 1) {                             // pair = partner lane (xor 2 at T=0, xor 1 at T=1): the path-metric exchange
+    if constexpr (T < LB) {                             // pair = partner lane: the path-metric exchange
         uint32_t Va[4], Vb[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) { Va[c] = vr_fadd(V[c], mA); Vb[c] = vr_fadd(V[c], mB); }
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < NR; r++) {
             const int c0 = vr_scls(T, r, 0);
-            const uint32_t Z = __shfl_xor_sync(WARP ? 0xFFFFFFFFu : qmask, R[r], T == 0 ? 2 : 1);
+            const uint32_t Z = __shfl_xor_sync(WARP ? 0xFFFFFFFFu : qmask, R[r], 1 << (LB - 1 - T));
             R[r] = __viaddmin_u16x2(R[r], Va[c0], __vadd2(Z, Vb[c0 ^ 3]));
         }
     } else if constexpr (T <= 4) {                      // pair = register r ^ d inside the lane
-        constexpr int d = T == 2 ? 4 : T == 3 ? 2 : 1;
+        constexpr int d = 1 << (4 - T);
         uint32_t VO[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) VO[c] = vr_fadd(V[c], mA);
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < NR; r++) {
             if (r & d) continue;
             const int c0 = vr_scls(T, r, 0);
             const uint32_t X = R[r], Y = R[r + d];      // X = states p (even role), Y = states p + 32 (odd role)
@@ -90,7 +95,7 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, 
 #pragma unroll
         for (int c = 0; c < 4; c++) { W1[c] = vr_fadd(V[c], mA); W2[c] = vr_fadd(V[c], mB); }
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < NR; r++) {
             const int c = vr_scls(5, r, 0);
             const uint32_t y = __byte_perm(R[r], 0, 0x1032);          // [p + 32, p]
             R[r] = __viaddmin_u16x2(R[r], W1[c], __vadd2(y, W2[c ^ 3]));   // [min(p + a, p32 + b), min(p32 + a, p + b)] = new states 2p, 2p + 1
@@ -98,11 +103,11 @@ __device__ __forceinline__ void vr_step(uint32_t (&R)[8], const uint32_t Cbase, 
     }
 }
 // the same with the mark of the step given as a plain value (6-step path and tail: the time is only known at run time)
-template <int T, bool WARP>
-__device__ __forceinline__ void vr_step_rt(uint32_t (&R)[8], const uint32_t Cbase, const VrLane& L, const uint32_t KC, const uint32_t mark, const unsigned qmask) {
-    if constexpr (T <= 1) vr_step<T, WARP>(R, Cbase, L, KC, L.bA[T] * mark, L.bB[T] * mark, qmask);
-    else if constexpr (T <= 4) vr_step<T, WARP>(R, Cbase, L, KC, mark, 0u, qmask);
-    else vr_step<T, WARP>(R, Cbase, L, KC, mark & 0xFFFF0000u, mark & 0x0000FFFFu, qmask);
+template <int T, bool WARP, int LB>
+__device__ __forceinline__ void vr_step_rt(uint32_t (&R)[8 << (2 - LB)], const uint32_t Cbase, const VrLane& L, const uint32_t KC, const uint32_t mark, const unsigned qmask) {
+    if constexpr (T < LB) vr_step<T, WARP, LB>(R, Cbase, L, KC, L.bA[T] * mark, L.bB[T] * mark, qmask);
+    else if constexpr (T <= 4) vr_step<T, WARP, LB>(R, Cbase, L, KC, mark, 0u, qmask);
+    else vr_step<T, WARP, LB>(R, Cbase, L, KC, mark & 0xFFFF0000u, mark & 0x0000FFFFu, qmask);
 }
 
 // branch-metric vector of step s (0..5) of a 6-step chunk held in w[] (vq_bm_*: viterbi_k7_quad.cuh)
@@ -118,12 +123,13 @@ template <int CODE_RATE, int s> __device__ __forceinline__ uint32_t vr_bm(const 
 // aligned; absent when kp = 0), then one byte per block, bit 7 = the newest column of the block.  vr_emit turns the row into output bytes.
 // Kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the step loop.
 #define SB_VR_HB 48                                          // >= (7 + 31 + 256 + 6) / 8 + 2
+template <int FR>
 __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ hb, uint32_t e, const uint32_t A0, const uint32_t t, uint32_t todo) {
     uint32_t A = A0, j = 0;
     uint32_t tt = t;                                         // time of the newest column not yet walked
     const uint32_t kp = t & 7u;
     if (kp) {                                                // running block: kp decisions in bits 0..kp-1, one slot-address bit changes per column
-        const uint32_t h = ring_b[e * (SB_VR_FR * 64) + A];
+        const uint32_t h = ring_b[e * (FR * 64) + A];
         const uint32_t take = min(kp, todo);
         for (uint32_t c = 0; c < take; c++) {                // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
             const uint32_t b = 5u - (tt - c - 1u) % 6u, d = (h >> (kp - 1u - c)) & 1u;
@@ -133,7 +139,7 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
         todo -= take; tt -= kp; e = e ? e - 1u : SB_VR_NB - 1u;
     }
     uint32_t ph = tt % 6u;                                   // phase of the block boundary the walk stands on
-    const uint8_t* rp = ring_b + e * (SB_VR_FR * 64);
+    const uint8_t* rp = ring_b + e * (FR * 64);
     while (todo >= 8u) {
         const uint32_t h = rp[A];
         hb[j++] = (uint8_t)h;
@@ -141,7 +147,7 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
         const uint32_t G = (r & 0x3Cu) | (r >> 6);           // slot-address bit (i - ph) mod 6 <- column tt - i, the two oldest overriding i = 0, 1
         A = ((G | (G << 6)) >> ph) & 63u;
         todo -= 8u; ph = ph >= 2u ? ph - 2u : ph + 4u;       // (tt - 8) mod 6
-        rp = rp == ring_b ? ring_b + (SB_VR_NB - 1u) * (SB_VR_FR * 64) : rp - SB_VR_FR * 64;
+        rp = rp == ring_b ? ring_b + (SB_VR_NB - 1u) * (FR * 64) : rp - FR * 64;
     }
     if (todo) hb[j++] = rp[A];                               // oldest block of the window: only its newest `todo` columns count
     hb[j] = 0; hb[j + 1] = 0;
@@ -150,9 +156,9 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
 // counted from bit 7 of byte 0; the first la bits are only looked through, byte m of the output (m = 0 the LAST byte of the window) is the
 // eight bits from la + 8 m on, newest in bit 7.  All four lanes of the quad take part; byte m goes to op[first + nbytes - 1 - m].
 __device__ __forceinline__ void vr_emit(const uint8_t* __restrict__ hb, uint8_t* __restrict__ op, const uint32_t out_cap, const uint32_t first, const uint32_t nbytes,
-                                        const uint32_t kp, const uint32_t la, const uint32_t q) {
+                                        const uint32_t kp, const uint32_t la, const uint32_t q, const uint32_t nl) {
     const uint32_t s0 = ((8u - kp) & 7u) + la, sh = s0 & 7u, i0 = s0 >> 3;
-    for (uint32_t m = q; m < nbytes; m += 4u) {
+    for (uint32_t m = q; m < nbytes; m += nl) {
         const uint32_t v = ((uint32_t)hb[i0 + m] << 8) | hb[i0 + m + 1u];
         const uint32_t at = first + nbytes - 1u - m;
         if (at < out_cap) op[at] = (uint8_t)(v >> (8u - sh));
@@ -160,23 +166,34 @@ __device__ __forceinline__ void vr_emit(const uint8_t* __restrict__ hb, uint8_t*
 }
 // best state at time t (phase tm): smallest (byte = m7 << 1 | newest mark, state index) over the 64 slots of a code block (viterbicore.h:468-520);
 // returns the slot address of that state.  Out of line for the same reason as vr_traceback.
-__device__ __noinline__ uint32_t vr_best_slot(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
-                                              const uint32_t q, const uint32_t tm, const uint32_t tn, const unsigned QM) {
-    const uint32_t R[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+template <int LB>
+__device__ __forceinline__ uint32_t vr_best_core(const uint32_t (&R)[8 << (2 - LB)], const uint32_t q, const uint32_t tm, const uint32_t tn, const unsigned QM) {
     uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < (8 << (2 - LB)); r++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t v = h ? (R[r] >> 16) : (R[r] & 0xFFFFu);
-            const uint32_t A = (q << 4) | (uint32_t)vr_low4(r, h);
+            const uint32_t A = (q << (6 - LB)) | (uint32_t)vr_low4(r, h);
             const uint32_t ns = ((A << tm) | (A >> (6u - tm))) & 63u;         // state index of this slot at time t
             best = min(best, ((((v >> 9) << 1) | ((v >> tn) & 1u)) << 8) | ns);
         }
     }
-    best = min(best, __shfl_xor_sync(QM, best, 1)); best = min(best, __shfl_xor_sync(QM, best, 2));
+    best = min(best, __shfl_xor_sync(QM, best, 1));
+    if (LB == 2) best = min(best, __shfl_xor_sync(QM, best, 2));
     const uint32_t n = best & 63u;
     return ((n >> tm) | (n << (6u - tm))) & 63u;
+}
+__device__ __noinline__ uint32_t vr_best_slot(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
+                                              const uint32_t q, const uint32_t tm, const uint32_t tn, const unsigned QM) {
+    const uint32_t R[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    return vr_best_core<2>(R, q, tm, tn, QM);
+}
+__device__ __noinline__ uint32_t vr_best_slot16(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
+                                                uint32_t r8, uint32_t r9, uint32_t r10, uint32_t r11, uint32_t r12, uint32_t r13, uint32_t r14, uint32_t r15,
+                                                const uint32_t q, const uint32_t tm, const uint32_t tn, const unsigned QM) {
+    const uint32_t R[16] = {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15};
+    return vr_best_core<1>(R, q, tm, tn, QM);
 }
 
 // sum of the two complementary branch metrics of step s: 28 with both coded bits, 14 with one
@@ -184,12 +201,13 @@ template <int CODE_RATE, int s> __host__ __device__ constexpr uint32_t vr_ksum()
     return CODE_RATE == CR_12 ? 28u : CODE_RATE == CR_34 ? (s % 3 == 0 ? 28u : 14u) : ((s & 1) ? 14u : 28u);
 }
 
-template <int CODE_RATE>
+template <int CODE_RATE, int LB>
 struct VrDecoder {
+    static constexpr int NR = 8 << (2 - LB), NL = 1 << LB, FR = 32 >> LB;                        // registers per lane, lanes per code block, code blocks per warp
     static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
     static constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
     static constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;                                // 12 (R=1/2), 9 (2/3), 8 (3/4) soft bytes per 6 steps
-    uint32_t R[8];
+    uint32_t R[NR];
     VrLane LC;
     uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves, as registers
     uint32_t mk[8], mkA[2][4], mkB[2][4], mkH[4], mkL[4];   // history marks 0x00010001 << j as registers; per lane-pair phase and chunk; T = 5 halves
@@ -209,33 +227,37 @@ struct VrDecoder {
                // keep every puncture group inside one word: w0 = b0 b1 b2 -, w1 = b3 b4 b5 -, w2 = b6 b7 b8 -
                a[0] = b[0] | (b[1] << 8) | (b[2] << 16); a[1] = b[3] | (b[4] << 8) | (b[5] << 16); a[2] = b[6] | (b[7] << 8) | (b[8] << 16); }
     }
-    // the 16 history bytes of this lane (low byte of every half), in slot-address order, into ring entry `e`
+    // the history bytes of this lane (low byte of every half: 16 or 32), in slot-address order, into ring entry `e`
     __device__ __forceinline__ void store_hist(const uint32_t e) {
-        uint4 w;
-        w.x = __byte_perm(R[0], R[1], 0x6420); w.y = __byte_perm(R[2], R[3], 0x6420);
-        w.z = __byte_perm(R[4], R[5], 0x6420); w.w = __byte_perm(R[6], R[7], 0x6420);
-        ring_q[e * (SB_VR_FR * 4)] = w;
+#pragma unroll
+        for (int i = 0; i < NR / 8; i++) {
+            uint4 w;
+            w.x = __byte_perm(R[8 * i + 0], R[8 * i + 1], 0x6420); w.y = __byte_perm(R[8 * i + 2], R[8 * i + 3], 0x6420);
+            w.z = __byte_perm(R[8 * i + 4], R[8 * i + 5], 0x6420); w.w = __byte_perm(R[8 * i + 6], R[8 * i + 7], 0x6420);
+            ring_q[e * (FR * 4) + i] = w;
+        }
     }
     __device__ __forceinline__ void clear_hist() {
 #pragma unroll
-        for (int r = 0; r < 8; r++) R[r] &= 0xFE00FE00u;
+        for (int r = 0; r < NR; r++) R[r] &= 0xFE00FE00u;
     }
     __device__ __forceinline__ void next_slot() { wslot = wslot == SB_VR_NB - 1u ? 0u : wslot + 1u; }
     // viterbi.hpp:177-180 -> viterbicore.h:445-465: subtract (smallest byte & 0xFE) = the smallest m7; `mask` names the lanes that take part
     __device__ __forceinline__ void normalize(const unsigned mask) {
         uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
+        if constexpr (NR == 16) m = __vminu2(m, __vminu2(__vminu2(__vminu2(R[8], R[9]), __vminu2(R[10], R[11])), __vminu2(__vminu2(R[12], R[13]), __vminu2(R[14], R[15]))));
         m = min(m & 0xFFFFu, m >> 16) >> 9;             // smallest m7 of this lane
-        m = min(m, __shfl_xor_sync(mask, m, 1)); m = min(m, __shfl_xor_sync(mask, m, 2));
+        m = min(m, __shfl_xor_sync(mask, m, 1)); if constexpr (LB == 2) m = min(m, __shfl_xor_sync(mask, m, 2));
         const uint32_t mv = m * 0x02000200u;
 #pragma unroll
-        for (int r = 0; r < 8; r++) R[r] -= mv;         // every half >= m << 9: no borrow between halves, histories untouched
+        for (int r = 0; r < NR; r++) R[r] -= mv;        // every half >= m << 9: no borrow between halves, histories untouched
     }
     // windowed traceback from slot A0 at time t (viterbi.hpp:205-237): one lane of the quad walks the ring (vr_traceback)
     __device__ __forceinline__ void traceback(const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
         __syncwarp(QM);
-        if (q == 0) vr_traceback(ring_b, hb, wslot, A0, t, la + nout);
+        if (q == 0) vr_traceback<FR>(ring_b, hb, wslot, A0, t, la + nout);
         __syncwarp(QM);
-        vr_emit(hb, op, out_cap, nraw, nout >> 3, t & 7u, la, (uint32_t)q);
+        vr_emit(hb, op, out_cap, nraw, nout >> 3, t & 7u, la, (uint32_t)q, (uint32_t)NL);
         nraw += nout >> 3;
         __syncwarp(QM);
     }
@@ -246,7 +268,9 @@ struct VrDecoder {
         if (t >= end) { nout = end - ob - 6u; la = t - end; }
         else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
         if (nout) {                                     // uniform inside the quad
-            const uint32_t A0 = vr_best_slot(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], (uint32_t)q, tm, (t - 1u) & 7u, QM);
+            uint32_t A0;
+            if constexpr (LB == 2) A0 = vr_best_slot(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], (uint32_t)q, tm, (t - 1u) & 7u, QM);
+            else A0 = vr_best_slot16(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8], R[9], R[10], R[11], R[12], R[13], R[14], R[15], (uint32_t)q, tm, (t - 1u) & 7u, QM);
             if (t & 7u) store_hist(wslot);              // mid-block: the partial histories of the running block (a block end has just stored its own)
             traceback(A0, t, la, nout);
             ob += nout;
@@ -261,9 +285,9 @@ struct VrDecoder {
             constexpr int T = S % 6, J = S % 8, I = S / 6;
             const uint32_t cb = vr_bm<CODE_RATE, T>(w[I]);
             const uint32_t KC = kc[vr_ksum<CODE_RATE, T>() == 28u ? 0 : 1];
-            if constexpr (T <= 1) vr_step<T, true>(R, cb, LC, KC, mkA[T][I], mkB[T][I], 0xFFFFFFFFu);
-            else if constexpr (T <= 4) vr_step<T, true>(R, cb, LC, KC, mk[J], 0u, 0xFFFFFFFFu);
-            else vr_step<T, true>(R, cb, LC, KC, mkH[I], mkL[I], 0xFFFFFFFFu);
+            if constexpr (T < LB) vr_step<T, true, LB>(R, cb, LC, KC, mkA[T][I], mkB[T][I], 0xFFFFFFFFu);
+            else if constexpr (T <= 4) vr_step<T, true, LB>(R, cb, LC, KC, mk[J], 0u, 0xFFFFFFFFu);
+            else vr_step<T, true, LB>(R, cb, LC, KC, mkH[I], mkL[I], 0xFFFFFFFFu);
             if constexpr ((S + 1) % 8 == 0) {
                 store_hist(wslot); next_slot();
                 if constexpr ((S + 1) % GSTEPS == 0) normalize(0xFFFFFFFFu);
@@ -276,7 +300,7 @@ struct VrDecoder {
     template <int s> __device__ __forceinline__ void slow(const uint32_t (&w)[3], const uint32_t tb, const bool live) {
         if constexpr (s < 6) {
             const uint32_t t = tb + s + 1u;
-            vr_step_rt<s, true>(R, vr_bm<CODE_RATE, s>(w), LC, kc[vr_ksum<CODE_RATE, s>() == 28u ? 0 : 1], 0x00010001u << ((t - 1u) & 7u), 0xFFFFFFFFu);
+            vr_step_rt<s, true, LB>(R, vr_bm<CODE_RATE, s>(w), LC, kc[vr_ksum<CODE_RATE, s>() == 28u ? 0 : 1], 0x00010001u << ((t - 1u) & 7u), 0xFFFFFFFFu);
             const bool blk = (t & 7u) == 0u;            // uniform over the warp
             if (blk) store_hist(wslot);
             if constexpr ((s + 1) % GSTEPS == 0) {
@@ -307,18 +331,19 @@ __global__ void k_vit_lists(const FrameInfo* __restrict__ info, uint32_t nframes
 }
 
 // list / cnt: work list of this code rate (k_vit_lists) or null = frames 0 .. nframes-1 with the uniform parameters of `job`.
-template <int CODE_RATE>
+template <int CODE_RATE, int LB = 2>
 __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out) {
-    __shared__ uint4 s_ring[SB_VR_NB][SB_VR_FR][4];    // entry: history bytes of the 64 slots of every code block over 8 columns
-    __shared__ uint8_t s_hb[SB_VR_FR][SB_VR_HB];       // traceback scratch: the history bytes a walk passed, per code block
-    using D = VrDecoder<CODE_RATE>;
+    using D = VrDecoder<CODE_RATE, LB>;
+    constexpr int FR = D::FR, NL = D::NL;               // code blocks per warp (8 | 16), lanes per code block (4 | 2)
+    __shared__ uint4 s_ring[SB_VR_NB][FR][4];          // entry: history bytes of the 64 slots of every code block over 8 columns
+    __shared__ uint8_t s_hb[FR][SB_VR_HB];             // traceback scratch: the history bytes a walk passed, per code block
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
-    if (blockIdx.x * SB_VR_FR >= nvalid) return;        // whole CTA
-    const int lane = threadIdx.x & 31, q = lane & 3, fb = lane >> 2;
-    const uint32_t idx = blockIdx.x * SB_VR_FR + fb;
+    if (blockIdx.x * FR >= nvalid) return;              // whole CTA
+    const int lane = threadIdx.x & 31, q = lane & (NL - 1), fb = lane >> LB;
+    const uint32_t idx = blockIdx.x * FR + fb;
     const bool valid = idx < nvalid;
     const uint32_t f = !valid ? 0u : list ? __ldg(list + (size_t)CODE_RATE * nframes + idx) : idx;
     uint32_t L = job.frame_len;
@@ -326,19 +351,19 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     d.nsoft = job.nsoft;
     if (valid && info) { const FrameInfo fi = info[f]; L = fi.length; d.nsoft = fi.soft_bytes; }
     if (!valid) d.nsoft = 0;
-    d.q = q; d.QM = 0xFu << (lane & 28);
+    d.q = q; d.QM = (NL == 4 ? 0xFu : 0x3u) << (lane & ~(NL - 1));
     d.depth = job.depth; d.look = job.lookahead;
     d.sp = soft + (size_t)f * soft_stride;
     d.op = out + (size_t)f * out_stride + raw_off;
     d.out_cap = (uint32_t)(out_stride - raw_off < 0xFFFFFFFFull ? out_stride - raw_off : 0xFFFFFFFFull);
 #pragma unroll
     for (int t = 0; t < 6; t++) {
-        const int lc = q == 0 ? vq_lcls(t, 0) : q == 1 ? vq_lcls(t, 1) : q == 2 ? vq_lcls(t, 2) : vq_lcls(t, 3);
+        const int lc = vq_cls(vq_rol6(q << (6 - LB), t) & 31);     // class contribution of this lane's address bits at phase t
         const int K = vr_kcls(t);
         d.LC.sel[t][0] = vq_sel(0 ^ lc, 0 ^ K ^ lc); d.LC.sel[t][1] = vq_sel(1 ^ lc, 1 ^ K ^ lc);
     }
-    d.LC.bA[0] = (q >> 1) & 1; d.LC.bB[0] = 1u - d.LC.bA[0];       // pair bit at T=0 is address bit 5 (lane bit 1), at T=1 address bit 4
-    d.LC.bA[1] = q & 1;        d.LC.bB[1] = 1u - d.LC.bA[1];
+    d.LC.bA[0] = (q >> (LB - 1)) & 1; d.LC.bB[0] = 1u - d.LC.bA[0];     // pair bit at T = 0 is address bit 5 (the top lane bit), at T = 1 (LB = 2) address bit 4
+    d.LC.bA[1] = q & 1;               d.LC.bB[1] = 1u - d.LC.bA[1];
     {   // history marks as run-time values (z is always 0, which the compiler cannot know): they must stay register operands
         const uint32_t z = (uint32_t)(soft_stride >> 63);
         d.kc[0] = 0x1C001C00u + z; d.kc[1] = 0x0E000E00u + z;
@@ -353,12 +378,12 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     }
     // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t=0 state == address; byte value v sits at v << 8
 #pragma unroll
-    for (int r = 0; r < 8; r++) d.R[r] = 0x30003000u;
+    for (int r = 0; r < D::NR; r++) d.R[r] = 0x30003000u;
     if (q == 0) d.R[0] = 0x30000000u;
     d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
-    d.ring_q = &s_ring[0][fb][q];                       // + entry * (SB_VR_FR * 4)
-    d.ring_b = (const uint8_t*)&s_ring[0][fb][0];       // + entry * (SB_VR_FR * 64) + slot
+    d.ring_q = &s_ring[0][fb][q * (4 / NL)];            // + entry * (FR * 4): this lane's 16 / 32 bytes of the code block's 64
+    d.ring_b = (const uint8_t*)&s_ring[0][fb][0];       // + entry * (FR * 64) + slot
     d.hb = s_hb[fb];
 
     // lockstep part: all eight code blocks of the warp advance together, 24 or 6 steps at a time; the soft values of the next four chunks
@@ -396,9 +421,9 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
         uint32_t k = 0;                                 // steps into the chunk at tb
         auto step_rt = [&](const uint32_t Cbase, const uint32_t KC) {
             const uint32_t mark = 0x00010001u << ((tb + k) & 7u);
-            switch (k) { case 0: vr_step_rt<0, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break; case 1: vr_step_rt<1, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break;
-                         case 2: vr_step_rt<2, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break; case 3: vr_step_rt<3, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break;
-                         case 4: vr_step_rt<4, false>(d.R, Cbase, d.LC, KC, mark, d.QM); break; default: vr_step_rt<5, false>(d.R, Cbase, d.LC, KC, mark, d.QM); }
+            switch (k) { case 0: vr_step_rt<0, false, LB>(d.R, Cbase, d.LC, KC, mark, d.QM); break; case 1: vr_step_rt<1, false, LB>(d.R, Cbase, d.LC, KC, mark, d.QM); break;
+                         case 2: vr_step_rt<2, false, LB>(d.R, Cbase, d.LC, KC, mark, d.QM); break; case 3: vr_step_rt<3, false, LB>(d.R, Cbase, d.LC, KC, mark, d.QM); break;
+                         case 4: vr_step_rt<4, false, LB>(d.R, Cbase, d.LC, KC, mark, d.QM); break; default: vr_step_rt<5, false, LB>(d.R, Cbase, d.LC, KC, mark, d.QM); }
             k++;
             if (((tb + k) & 7u) == 0u) d.store_hist(d.wslot);
         };
