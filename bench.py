@@ -404,6 +404,17 @@ def main():
                     "nccl_ranks": world, "scatter_bytes_per_step": int((world - 1) * F * SLOT * 4), "gather_bytes_per_step": int((world - 1) * F * (PSDU + 28)),
                     "pieces_per_slab": P, "note": "all N*F slots resident on rank 0's GPU at the start of the step; bound by rank 0's NVLink egress"}
         del slab, slab32, root, out_all, res_all
+        # the host-side sharding helper the CPU (gloo) tests cover, on the GPUs: the U unique slots split into contiguous blocks per rank
+        # (sora_b200/shard.py), every rank decodes its block from host IQ, verdicts and bytes gathered on rank 0 over NCCL and compared whole
+        from sora_b200 import shard
+        offu = np.arange(U, dtype=np.uint64) * SLOT; lnu = np.full(U, SLOT, np.uint32)
+        def decode_block(iq, off, ln):
+            r_, o_ = eng.rx11a_batch(iq, off, ln, out_stride=PSDU)
+            return r_, o_
+        res_s, out_s = shard.decode_sharded(decode_block, iq_u.reshape(-1, 2), offu, lnu, dist=dist, device=dev)
+        if rank == 0:
+            assert (res_s["status"] == 1).all() and (res_s["length"] == PSDU).all() and (out_s[:, :PSDU] == ps_u).all(), "sharded decode: gathered results differ"
+            mgpu["sharded_check"] = f"{U} slots decoded in {world} contiguous blocks (shard.decode_sharded), gathered over NCCL, all FRAME_OK with the transmitted bytes"
     del iq_unique_dev
     if rank != 0:
         if dist: dist.destroy_process_group()

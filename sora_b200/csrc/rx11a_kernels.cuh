@@ -12,7 +12,7 @@
 //                PHY_11a.hpp:363-430,520-604.
 // Data layout: IQ is the caller's interleaved int16 (I,Q) stream, one 32-bit word per 40 Msps sample; the
 // 20 Msps stream is "every other word".  Soft bits leave this stage as one byte per coded bit (0..7),
-// N_CBPS per symbol, contiguous per frame, ready for viterbi_k7.cuh.
+// N_CBPS per symbol, contiguous per frame, ready for viterbi_k7_re.cuh.
 #pragma once
 #include "tables.cuh"
 

@@ -172,7 +172,6 @@ struct sb200_handle {
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
-    bool use_v1 = false;                               // SB200_VITERBI=v1 selects the warp-per-block kernel (A/B measurements)
     bool use_pair = false;                             // SB200_VITERBI=v4: two lanes per code block, 16 code blocks per warp (A/B against four lanes)
     bool use_v2 = false;                               // SB200_VITERBI=v2 selects the per-step-mark quad kernel (A/B against the history-carrying one)
     std::string err;
@@ -236,7 +235,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v1 = e && e[0] == 'v' && e[1] == '1'; h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && e[1] == '4'; }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && e[1] == '4'; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
@@ -349,10 +348,7 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
     if (timed) CK(cudaEventRecord(h->evk[2], sf));
     if (sv != sf) { CK(cudaEventRecord(front_done, sf)); CK(cudaStreamWaitEvent(sv, front_done, 0)); }
     VitJob job{}; job.depth = 256; job.lookahead = 24; job.raw = 0;
-    if (h->use_v1) {
-        k_viterbi_k7<<<(n + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
-        h->launches += 3;
-    } else if (h->use_v2) {                            // one launch per code rate; quads of other rates exit at once
+    if (h->use_v2) {                                   // one launch per code rate; quads of other rates exit at once
         const unsigned g = (n + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         k_viterbi_quad<CR_34><<<g, b, h->vq_pad_smem, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         k_viterbi_quad<CR_12><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
@@ -1378,10 +1374,7 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
     CK(h->status.need(nblocks * 4ull)); CK(h->crc.need(nblocks * 4ull));
     VitJob job{}; job.code_rate = (uint32_t)code_rate; job.frame_len = frame_len_bytes; job.nsoft = nsoft; job.depth = depth; job.lookahead = lookahead; job.raw = 1;
     CK(cudaEventRecord(h->ev0, st));
-    if (h->use_v1) {
-        k_viterbi_k7<<<(nblocks + SB_VIT_WARPS - 1) / SB_VIT_WARPS, 32 * SB_VIT_WARPS, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T,
-                d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
-    } else if (!h->use_v2) {
+    if (!h->use_v2) {
         const unsigned g = (nblocks + SB_VR_FR - 1) / SB_VR_FR, gp = (nblocks + 15) / 16;
         if (code_rate == CR_34) do { if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
         else if (code_rate == CR_12) do { if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);

@@ -1,6 +1,6 @@
 // sora_b200 — batched K=7 (133,171) soft Viterbi, v2 "quad" mapping for sm_100a.
 //
-// Same arithmetic contract as viterbi_k7.cuh (bit-exact with kernel/bb/Brick11/src/viterbicore.h:269-556 driven like
+// Arithmetic contract: bit-exact with kernel/bb/Brick11/src/viterbicore.h:269-556 driven like
 // kernel/bb/Brick11/src/viterbi.hpp:104-237), different machine mapping:
 //
 //   * 4 lanes decode one code block; each lane keeps 16 of the 64 path metrics in 8 registers, two per register as
@@ -23,9 +23,14 @@
 //     columns the address register is the six decoded bits), the x^7+x^4+1 descrambler and the CRC-32 / verdict.
 //   * Two renderings of the mark handling (vq_step_a / vq_step_b below), chosen per code rate by measurement.
 #pragma once
-#include "viterbi_k7.cuh"
+#include "rx11a_kernels.cuh"
 
 namespace sb {
+
+struct VitJob {               // uniform-parameter mode (standalone API); per-frame mode reads FrameInfo instead
+    uint32_t code_rate, frame_len, nsoft; uint32_t depth, lookahead; uint32_t raw; // raw=1: emit SERVICE+PSDU bytes undescrambled
+};
+
 
 #define SB_VQ_WARPS 1                      // warps per CTA
 #define SB_VQ_FR (8 * SB_VQ_WARPS)         // code blocks per CTA
