@@ -159,6 +159,7 @@ struct sb200_handle {
     cudaStream_t s_copy = nullptr, s_front = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr};
     DevBuf stage[2], iq40, off40, len40, dcbuf;
+    double gather_ms = 0.0;                            // host_decimate: time the host threads spent gathering during the last call (SB200_TRACE prints it)
     uint32_t ht_mcs_limit = 11;                        // first MCS the 802.11n HT-SIG parser refuses (PHY_11n.hpp:497); option "ht_mcs_limit"
     DevBuf soff, slen, spos, snev, sev;                // continuous-capture scout: current slot of every capture, position, event count, event list
     DevTablesTx X{}; DevBuf tabtx, txpay, txoff, txlen, txseed, txout, txns, txdesc, cca11n, ccaidx, tabtx11n, txout1; DevTablesTx11n XN{};   // 802.11a transmit tables (built on first use) and staging
@@ -455,9 +456,12 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
             const uint32_t* base = (const uint32_t*)iq;
             if (dec) {
                 const int hb = (int)(k % 3u);
+                if (k == 0) h->gather_ms = 0.0;
                 if (k >= 3) CK(cudaEventSynchronize(h->ev_hfree[hb]));                      // pinned buffer hb is free once chunk k-3 has crossed the link
                 DecimPool::Job j{(const uint32_t*)iq, offh.data(), lenh.data(), doffh.data(), f0, f1, (uint32_t*)h->hstage[hb]};
+                const auto tg0 = std::chrono::steady_clock::now();
                 h->pool->run(j);
+                h->gather_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
                 if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));
                 CK(cudaMemcpyAsync(h->stage[b].p, h->hstage[hb], (doffh[f1] - doffh[f0]) * 4ull, cudaMemcpyHostToDevice, h->s_copy));
                 CK(cudaEventRecord(h->ev_hfree[hb], h->s_copy));
@@ -487,6 +491,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
             if (!res_dev_all) CK(cudaMemcpyAsync(res + f0, d_res_all + f0, n * sizeof(sb200_frame_result), cudaMemcpyDeviceToHost, st));
         }
         h->nk = 0;
+        if (dec && getenv("SB200_TRACE")) fprintf(stderr, "[sb200] rx11a host_decimate: %u chunks, host gather %.2f ms in total (%u threads)\n", k, h->gather_ms, h->host_decimate);
     }
     const bool res_dev = res_dev_all;
     sb200_frame_result* d_res = d_res_all;
