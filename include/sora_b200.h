@@ -230,6 +230,12 @@ int sb200_tx11b_batch(sb200_handle* h, const uint8_t* payload, uint64_t payload_
                       uint32_t nframes, uint32_t rate_kbps, uint32_t init_phase, uint32_t lead_samples, uint32_t sample_bits,
                       void* out, uint64_t out_stride_samples, uint32_t* nsamples, uint32_t* final_phase, void* cuda_stream);
 
+/* Page-locked (DMA-able) host memory for capture buffers, as the reference's user-mode extension maps for a radio
+ * (SoraURadioMapRxSampleBuf, kernel/core/inc/_user_mode_ext.h:100).  Host captures handed to any entry point from such a buffer cross
+ * PCIe without an intermediate staging copy.  NULL on failure (or without a device). */
+void* sb200_host_alloc(size_t bytes);
+void  sb200_host_free(void* p);
+
 /* Legacy 802.11b transmit filter: BB11BPMDSpreadFIR4SSE (variant 0) and BB11BPMDSpreadFIR4ASM (variant 1) of kernel/inc/bb/bbb.h:188-200
  * (bodies: kernel/bb/dot11b/bbb_fir.c:92-110 + :413-566, and :113-135 + :137-386) — the 37-tap pulse shaper BB11BPMDPacketGenSignal
  * (bbb_tx.c:116-150) runs over the 4x zero-stuffed chip stream of a frame — for a batch of frames.  Frame i = chips[frame_off[i] ..

@@ -40,6 +40,7 @@
 #include <condition_variable>
 #include <chrono>
 #include <cstring>
+#include <cstdlib>
 #ifndef SB200_BRICK_DEVICE
 #define SB200_BRICK_DEVICE 0      /* CUDA device ordinal the bricks of this translation unit bind to */
 #endif
@@ -61,18 +62,36 @@ struct B200Engine {
 };
 struct B200Event { sb200_frame_result r; uint32_t end_sample; std::vector<uchar> bytes; };
 class B200StreamBatcher {
-    struct Req { const COMPLEX16* p; size_t n; uint32_t max_events; std::vector<B200Event>* out; int rc; bool done, taken; };
+    // Windows are staged in ONE page-locked arena (sb200_host_alloc): every participant copies its own window into a region it reserved under
+    // the lock — K memcpys in K threads, in parallel, while the round is still filling — and the closing thread hands the arena to
+    // sb200_rx11a_streams, which sends only the regions in use across PCIe by DMA.  A request that does not fit (the arena grows only between
+    // rounds) is staged by the closing thread.
+    struct Req { const COMPLEX16* p; size_t n; uint32_t max_events; std::vector<B200Event>* out; int rc; bool done, taken, staged; size_t off; };
     std::mutex m_; std::condition_variable cv_; std::vector<Req*> pend_; unsigned participants_ = 1; unsigned wait_us_ = 2000; bool running_ = false;
-    std::vector<int16_t> iq_; std::vector<uint64_t> off_; std::vector<uint32_t> len_, sidx_, cnt_; std::vector<sb200_frame_result> res_; std::vector<uchar> bytes_;
-    void Run(std::vector<Req*>& batch) {                  // called without the lock by the thread that closes the round
+    int16_t* arena_ = nullptr; size_t cap_ = 0, used_ = 0, want_ = 0; unsigned copying_ = 0; bool pinned_ = false;   // cap_, used_, want_ in samples
+    std::vector<uint64_t> off_; std::vector<uint32_t> len_, sidx_, cnt_; std::vector<sb200_frame_result> res_; std::vector<uchar> bytes_;
+    static size_t Round8(size_t n) { return (n + 7) & ~(size_t)7; }
+    void Grow(size_t samples) {                             // only with no copy in flight and no region in use
+        if (arena_) { if (pinned_) sb200_host_free(arena_); else free(arena_); }
+        arena_ = (int16_t*)sb200_host_alloc(samples * 4 + 64); pinned_ = arena_ != nullptr;
+        if (!arena_) arena_ = (int16_t*)malloc(samples * 4 + 64);                  // no device: the decode call will fail loudly
+        cap_ = arena_ ? samples : 0;
+    }
+    void Run(std::vector<Req*>& batch) {                  // called without the lock by the thread that closes the round (no copy is in flight any more)
         B200Engine& E = B200Engine::Get(); std::lock_guard<std::mutex> le(E.m);
-        uint32_t K = 1; size_t tot = 0;
-        for (Req* q : batch) { if (q->max_events > K) K = q->max_events; tot += q->n; }
+        uint32_t K = 1; size_t tot = 0; bool all_staged = true;
+        for (Req* q : batch) { if (q->max_events > K) K = q->max_events; tot += Round8(q->n); all_staged = all_staged && q->staged; }
         const uint32_t S = (uint32_t)batch.size(); const uint32_t row = 2560;
-        iq_.resize(2 * tot + 8); off_.resize(S); len_.resize(S); cnt_.assign(S, 0); sidx_.assign((size_t)S * K, 0); res_.resize((size_t)S * K); bytes_.resize((size_t)S * K * row);
-        size_t o = 0;
-        for (uint32_t i = 0; i < S; i++) { memcpy(iq_.data() + 2 * o, batch[i]->p, batch[i]->n * sizeof(COMPLEX16)); off_[i] = o; len_[i] = (uint32_t)batch[i]->n; o += batch[i]->n; }
-        int rc = E.h ? sb200_rx11a_streams(E.h, iq_.data(), tot, off_.data(), len_.data(), S, K, bytes_.data(), row, res_.data(), sidx_.data(), cnt_.data(), nullptr) : SB200_E_NODEVICE;
+        if (!all_staged) {                                  // lay everything out again from the callers' own buffers (they are blocked in Decode)
+            if (tot > cap_) Grow(tot + tot / 4);
+            size_t o = 0;
+            for (Req* q : batch) { if (arena_) memcpy(arena_ + 2 * o, q->p, q->n * sizeof(COMPLEX16)); q->off = o; o += Round8(q->n); }
+        }
+        if (tot > want_) want_ = tot;
+        off_.resize(S); len_.resize(S); cnt_.assign(S, 0); sidx_.assign((size_t)S * K, 0); res_.resize((size_t)S * K); bytes_.resize((size_t)S * K * row);
+        size_t span = 0;
+        for (uint32_t i = 0; i < S; i++) { off_[i] = batch[i]->off; len_[i] = (uint32_t)batch[i]->n; if (batch[i]->off + batch[i]->n > span) span = batch[i]->off + batch[i]->n; }
+        int rc = (E.h && arena_) ? sb200_rx11a_streams(E.h, arena_, span, off_.data(), len_.data(), S, K, bytes_.data(), row, res_.data(), sidx_.data(), cnt_.data(), nullptr) : SB200_E_NODEVICE;
         for (uint32_t i = 0; i < S; i++) {
             Req* q = batch[i]; q->rc = rc; q->out->clear();
             if (rc == SB200_OK) for (uint32_t k = 0; k < cnt_[i] && k < q->max_events; k++) {
@@ -84,22 +103,33 @@ class B200StreamBatcher {
     }
 public:
     static B200StreamBatcher& Get() { static B200StreamBatcher b; return b; }
+    ~B200StreamBatcher() { if (arena_) { if (pinned_) sb200_host_free(arena_); else free(arena_); } }
     void Configure(unsigned participants, unsigned wait_us = 2000) { std::lock_guard<std::mutex> l(m_); participants_ = participants ? participants : 1; wait_us_ = wait_us; }
     int Decode(const COMPLEX16* p, size_t n, uint32_t max_events, std::vector<B200Event>& out) {
-        Req q{p, n, max_events, &out, SB200_OK, false, false};
+        Req q{p, n, max_events, &out, SB200_OK, false, false, false, 0};
         std::unique_lock<std::mutex> l(m_);
+        if (!running_ && pend_.empty() && copying_ == 0) {   // a round opens: the arena is free, size it for what the last rounds needed
+            used_ = 0;
+            const size_t need = want_ + want_ / 4;
+            if (need > cap_) Grow(need);
+        }
         pend_.push_back(&q);
+        if (!running_ && arena_ && used_ + Round8(n) <= cap_) {                    // stage my own window while the round fills
+            q.off = used_; used_ += Round8(n); copying_++;
+            l.unlock(); memcpy(arena_ + 2 * q.off, p, n * sizeof(COMPLEX16)); l.lock();
+            q.staged = true; copying_--; cv_.notify_all();
+        }
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(wait_us_);
         while (!q.done) {
             const bool late = std::chrono::steady_clock::now() >= deadline;
-            if (!running_ && !q.taken && (pend_.size() >= participants_ || late)) {   // this thread closes the round (complete, or waited long enough) and runs it
+            if (!running_ && !q.taken && copying_ == 0 && (pend_.size() >= participants_ || late)) {   // this thread closes the round (complete, or waited long enough) and runs it
                 std::vector<Req*> batch; batch.swap(pend_);
                 for (Req* r : batch) r->taken = true;
                 running_ = true;
                 l.unlock(); Run(batch); l.lock();
                 for (Req* r : batch) r->done = true;
                 running_ = false; cv_.notify_all();
-            } else if (late || q.taken) cv_.wait(l);
+            } else if ((late && copying_ == 0) || q.taken) cv_.wait(l);
             else cv_.wait_until(l, deadline);
         }
         return q.rc;

@@ -524,6 +524,11 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
 // Many continuous captures at once.  Every pass decodes the next frame of every capture that still has samples (one slot per
 // capture, from its cursor to its end, with its own carried DC), so the device sees a full batch per pass and the number of
 // passes is the largest number of frames in any one capture.
+// Page-locked host memory for capture buffers: what the reference's user-mode extension maps for a radio (SoraURadioMapRxSampleBuf,
+// kernel/core/inc/_user_mode_ext.h:100) is DMA-able memory too.  Captures handed to the engine from such a buffer cross PCIe without a staging copy.
+extern "C" void* sb200_host_alloc(size_t bytes) { void* p = nullptr; if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+extern "C" void sb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int sb200_rx11a_streams(sb200_handle* h, const int16_t* iq, uint64_t iq_total, const uint64_t* stream_off, const uint32_t* stream_len,
                                    uint32_t nstreams, uint32_t max_frames, uint8_t* out_bytes, uint32_t out_stride, sb200_frame_result* res,
                                    uint32_t* sample_index, uint32_t* nframes_out, void* cuda_stream) {
