@@ -449,3 +449,24 @@ def test_many_streams_at_once(eng):
             if ores["status"][i] in (1, oracle_py.E_CRC32_FAIL):
                 L = int(ores["length"][i]); assert (out[s, i, :L] == oout[i, :L]).all()
     assert cnt.max() == 6 and cnt[-1] == 0 and cnt[-3] == 0
+
+def test_page_locked_capture_buffer(eng):
+    """sb200_host_alloc: a capture buffer the device can DMA from (the role of SoraURadioMapRxSampleBuf's mapping); decoding from it gives the
+    same results as from ordinary host memory, and the brick batcher stages its windows in one."""
+    import ctypes as C
+    lib = api.load_library()
+    lib.sb200_host_alloc.restype = C.c_void_p; lib.sb200_host_alloc.argtypes = [C.c_size_t]; lib.sb200_host_free.argtypes = [C.c_void_p]
+    iq, ps = synth.make_frames(5, psdu_len=333, rate_kbps=36000, snr_db=28, seed0=0xA110C)
+    flat, off, ln = _slots(iq)
+    ref, refo = eng.rx11a_batch(flat, off, ln)
+    nbytes = flat.size * 2
+    p = lib.sb200_host_alloc(nbytes); assert p
+    try:
+        C.memmove(p, flat.ctypes.data, nbytes)
+        res = np.zeros(len(off), dtype=api.RESULT_DTYPE); out = np.zeros((len(off), 2560), np.uint8)
+        eng.rx11a_raw(p, flat.shape[0], off.ctypes.data, ln.ctypes.data, len(off), out.ctypes.data, 2560, res.ctypes.data)
+        for k in ("status", "rate_kbps", "length", "crc32", "nsym", "detect_index", "cfo_est"): assert (res[k] == ref[k]).all(), k
+        assert (out == refo).all() and (res["status"] == 1).all()
+    finally:
+        lib.sb200_host_free(p)
+    assert lib.sb200_host_alloc(0) is None
