@@ -173,6 +173,8 @@ struct sb200_handle {
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
+    bool use_gring = false;                            // SB200_VITERBI=v5 / v6: history ring in global memory (v5: two lanes per code block, v6: four)
+    DevBuf vring;
     bool use_pair = false;                             // SB200_VITERBI=v4: two lanes per code block, 16 code blocks per warp (A/B against four lanes)
     bool use_v2 = false;                               // SB200_VITERBI=v2 selects the per-step-mark quad kernel (A/B against the history-carrying one)
     std::string err;
@@ -236,7 +238,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && e[1] == '4'; }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6'); }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
@@ -255,7 +257,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     DevBuf* all[] = {&h->tab, &h->iq, &h->off, &h->len, &h->info, &h->soft, &h->out, &h->status, &h->crc, &h->res,
                      &h->taps[0], &h->taps[1], &h->taps[2], &h->taps[3], &h->taps[4], &h->vlist, &h->vcnt, &h->slotchk, &h->doff};
     for (DevBuf* b : all) b->release();
-    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->soff.release(); h->slen.release(); h->spos.release(); h->snev.release(); h->sev.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
+    h->iq40.release(); h->off40.release(); h->len40.release(); h->dcbuf.release(); h->vring.release(); h->soff.release(); h->slen.release(); h->spos.release(); h->snev.release(); h->sev.release(); h->tab11n.release(); h->iq1.release(); h->tabtx.release(); h->txpay.release(); h->txoff.release(); h->txlen.release(); h->txseed.release(); h->txout.release(); h->txns.release(); h->txdesc.release(); h->cca11n.release(); h->ccaidx.release(); h->tabtx11n.release(); h->txout1.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
@@ -357,12 +359,13 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
         h->launches += 5;
     } else {                                           // history-carrying kernel: work lists per code rate, one launch per rate, descrambler / frame sink
         const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
+        if (h->use_gring) CK(h->vring.need((size_t)(h->use_pair ? gp : g) * SB_VR_NB * (h->use_pair ? 16 : 8) * 64));
         uint32_t* d_list = (uint32_t*)h->vlist.p + 3 * (size_t)f0; uint32_t* d_cnt = (uint32_t*)h->vcnt.p + 4 * (size_t)chunk_idx;
         CK(cudaMemsetAsync(d_cnt, 0, 16, sv));
         k_vit_lists<<<(n + 255) / 256, 256, 0, sv>>>(d_info, n, d_cnt, d_list);
-        do { if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_34, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
-        do { if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_12, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
-        do { if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_23, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
+        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_34, 1, true><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); else k_viterbi_re<CR_34, 2, true><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_34, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
+        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_12, 1, true><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); else k_viterbi_re<CR_12, 2, true><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_12, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
+        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_23, 1, true><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); else k_viterbi_re<CR_23, 2, true><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_23, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
         k_sink11a<<<(n + 127) / 128, 128, 0, sv>>>(d_out, row, n, d_info, h->T, d_status, d_crc);
         h->launches += 7;
     }
@@ -817,12 +820,13 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
         if (h->ht_mcs_limit > 13u) k_viterbi_quad<CR_23><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
     } else {
         const unsigned g = (nframes + SB_VR_FR - 1) / SB_VR_FR, gp = (nframes + 15) / 16;
+        if (h->use_gring) CK(h->vring.need((size_t)(h->use_pair ? gp : g) * SB_VR_NB * (h->use_pair ? 16 : 8) * 64));
         CK(h->vlist.need(nframes * 12ull)); CK(h->vcnt.need(16));
         CK(cudaMemsetAsync(h->vcnt.p, 0, 16, st));
         k_vit_lists<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, nframes, (uint32_t*)h->vcnt.p, (uint32_t*)h->vlist.p);
-        do { if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0);
-        do { if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0);
-        if (h->ht_mcs_limit > 13u) { do { if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_23, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0); h->launches += 1; }
+        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_12, 1, true><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_12, 2, true><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0);
+        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_34, 1, true><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_34, 2, true><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0);
+        if (h->ht_mcs_limit > 13u) { do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_23, 1, true><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_23, 2, true><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_23, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0); h->launches += 1; }
         k_sink11a<<<(nframes + 127) / 128, 128, 0, st>>>((uint8_t*)h->out.p, row, nframes, d_info, h->T, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
         h->launches += 2;
     }
@@ -1386,9 +1390,10 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
     CK(cudaEventRecord(h->ev0, st));
     if (!h->use_v2) {
         const unsigned g = (nblocks + SB_VR_FR - 1) / SB_VR_FR, gp = (nblocks + 15) / 16;
-        if (code_rate == CR_34) do { if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
-        else if (code_rate == CR_12) do { if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
-        else do { if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_23, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
+        if (h->use_gring) CK(h->vring.need((size_t)(h->use_pair ? gp : g) * SB_VR_NB * (h->use_pair ? 16 : 8) * 64));
+        if (code_rate == CR_34) do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_34, 1, true><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_34, 2, true><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
+        else if (code_rate == CR_12) do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_12, 1, true><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_12, 2, true><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
+        else do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_23, 1, true><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_23, 2, true><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_23, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
     } else {
         const unsigned g = (nblocks + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         if (code_rate == CR_34) k_viterbi_quad<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
