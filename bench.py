@@ -7,9 +7,10 @@ A "step" = one pass of the whole RX hot path (carrier sense -> LTS -> OFDM demod
 -> CRC) over one batch of F synthetic capture slots (BASELINE config #2: 54 Mbps, PSDU 1500 B, 9824 samples per slot at
 40 Msps, AWGN 30 dB).
   value        Msamples/s with the IQ already resident in HBM (device-timed, CUDA events, max over ranks);
-  e2e          the same through the C ABI with pinned HOST buffers: H2D of the IQ and D2H of bytes + verdicts inside the timed region.  Two
-               documented ways to call it are timed — the whole 40 Msps capture copied as it is, and option "host_decimate" (host threads
-               gather the even samples TDownSample2 keeps, half the bytes cross PCIe) — and the better one is reported (`e2e.mode`);
+  e2e          the same through the C ABI with pinned HOST buffers: H2D of the IQ and D2H of bytes + verdicts inside the timed region.  Three
+               documented ways to call it are timed — the whole 40 Msps capture copied as it is; option "host_decimate" (host threads
+               gather the even samples TDownSample2 keeps, half the bytes cross PCIe); and the same with "host_decimate_mix" = 1, where the
+               library decides per chunk between the two so that link and host cores are both busy — the best is reported (`e2e.mode`);
   mgpu         (N > 1) the partitioning BASELINE.json's north_star names: all N*F slots enter on rank 0's GPU, NCCL scatters the IQ slabs to
                the ranks over NVLink, every rank decodes its slab, NCCL gathers bytes + verdicts back to rank 0; all inside the timed region;
   roofline     dominant kernel (the Viterbi) against the HBM roofline; cpu_baseline: the SSE CPU oracle on the box's host cores in the three
@@ -243,6 +244,7 @@ def main():
     ap.add_argument("--host-threads", type=int, default=-1, help="host threads of the decimating e2e path (option host_decimate); -1 = from the CPUs this rank may use")
     ap.add_argument("--front-stage", type=int, default=-1, help="experiment: sample staging of the OFDM front end (0 direct, 1 register double buffer, 2 bulk async copy); -1 = library default")
     ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
+    ap.add_argument("--e2e-sweep", action="store_true", help="experiment: host thread counts x chunk sizes of the e2e modes, printed to stderr")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mgpu", action="store_true")
@@ -355,23 +357,36 @@ def main():
         ne = max(3, min(args.steps, 5))
         nth = args.host_threads if args.host_threads >= 0 else int(max(1, min(16, cores_rank - 2)))
         modes = {}
-        eng.set_option("host_decimate", 0)
-        ms_full = timed_max(step_e2e, ne)
-        assert (res_host[:, 0].numpy().astype(np.uint32) == 1).all()
-        modes["full_rate_copy"] = {"value": world * F * SLOT / (ms_full * 1e-3) / 1e6, "ms_per_step": ms_full,
-                                   "h2d_bytes_per_step": int(F * SLOT * 4 + F * 12), "d2h_bytes_per_step": int(F * PSDU + F * 28)}
+        d2h = int(F * PSDU + F * 28)
+        def run_mode(name, threads, mix, note=None):
+            res_host.zero_(); out_host[:U].zero_()
+            eng.set_option("host_decimate", threads); eng.set_option("host_decimate_mix", mix)
+            ms = timed_max(step_e2e, ne)
+            nbytes, chunks, gathered = eng.last_transfer()     # what the last call really sent (the adaptive mode decides per chunk)
+            eng.set_option("host_decimate", 0); eng.set_option("host_decimate_mix", 1)
+            assert (res_host[:, 0].numpy().astype(np.uint32) == 1).all() and (out_host[:U].numpy() == ps_u).all(), f"e2e {name}: results differ"
+            modes[name] = {"value": world * F * SLOT / (ms * 1e-3) / 1e6, "ms_per_step": ms, "h2d_bytes_per_step": int(nbytes + F * (20 if threads else 12)),
+                           "d2h_bytes_per_step": d2h, "chunks": chunks, "chunks_gathered_on_host": gathered}
+            if threads: modes[name]["host_threads_per_rank"] = threads
+        run_mode("full_rate_copy", 0, 1)
         if nth > 0:
-            res_host.zero_(); out_host.zero_()
-            eng.set_option("host_decimate", nth)
-            ms_dec = timed_max(step_e2e, ne)
-            eng.set_option("host_decimate", 0)
-            assert (res_host[:, 0].numpy().astype(np.uint32) == 1).all() and (out_host[:U].numpy() == ps_u).all()
-            modes["host_decimate"] = {"value": world * F * SLOT / (ms_dec * 1e-3) / 1e6, "ms_per_step": ms_dec, "host_threads_per_rank": nth,
-                                      "h2d_bytes_per_step": int(F * (SLOT // 2) * 4 + F * 20), "d2h_bytes_per_step": int(F * PSDU + F * 28)}
+            run_mode("host_decimate", nth, 0)
+            run_mode("host_decimate_adaptive", nth, 1)
+        if args.e2e_sweep:                                   # experiment: thread counts and chunk sizes of the adaptive mode, to stderr
+            for ch in (2048, 4096):
+                eng.set_option("chunk_frames", ch)
+                for th in sorted({4, 8, 12, nth, 16, 24, 32}):
+                    for mix in (0, 1):
+                        run_mode(f"sweep_chunk{ch}_t{th}_mix{mix}", th, mix)
+                        m = modes.pop(f"sweep_chunk{ch}_t{th}_mix{mix}")
+                        print(f"[e2e sweep] chunk {ch} threads {th} mix {mix}: {m['ms_per_step']:.2f} ms/step, {m['value'] / 1e3:.2f} G samples/s, gathered {m['chunks_gathered_on_host']}/{m['chunks']}, h2d {m['h2d_bytes_per_step'] / 1e9:.3f} GB", file=sys.stderr, flush=True)
+            eng.set_option("chunk_frames", args.chunk)
         best = max(modes, key=lambda k: modes[k]["value"])
         e2e = {"value": modes[best]["value"], "unit": "Msamples/s", "ms_per_step": modes[best]["ms_per_step"], "mode": best,
                "h2d_bytes_per_step": modes[best]["h2d_bytes_per_step"], "d2h_bytes_per_step": modes[best]["d2h_bytes_per_step"], "modes": modes,
-               "note": "host_decimate: T host threads per rank gather the even samples of each chunk (TDownSample2, samples.hpp:27-49) into pinned staging inside the timed region; full_rate_copy: the 40 Msps capture crosses PCIe as it is"}
+               "note": "full_rate_copy: the 40 Msps capture crosses PCIe as it is.  host_decimate: T host threads per rank gather the even samples of every chunk (TDownSample2, samples.hpp:27-49: "
+                       "the chain never reads the odd ones) into pinned staging inside the timed region, half the bytes cross.  host_decimate_adaptive: per chunk the library gathers, or sends the chunk as it is "
+                       "when the queued copies would run out before a gather could finish, so the link and the host cores are both kept busy; h2d_bytes_per_step is what the library reports it copied (sb200_last_transfer)"}
         del iq_host, out_host, res_host
 
     # ---- mgpu: rank 0 owns all N*F slots; NCCL scatter of IQ slabs, decode, NCCL gather of bytes + verdicts (north_star's partitioning) ----

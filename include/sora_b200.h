@@ -76,6 +76,9 @@ void sb200_destroy(sb200_handle* h);
 const char* sb200_last_error(const sb200_handle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 uint64_t sb200_launch_count(const sb200_handle* h);
+/* what the most recent sb200_rx11a_batch call with a HOST iq buffer really sent over the link: sample bytes copied host -> device, the number
+ * of pipeline chunks and how many of them the host threads gathered first (option host_decimate); bench.py's e2e.h2d_bytes_per_step */
+int sb200_last_transfer(const sb200_handle* h, uint64_t* h2d_bytes, uint32_t* chunks, uint32_t* chunks_gathered);
 /* device time (ms) of the kernels of the most recent *_batch / viterbi call, measured with CUDA events on `stream` */
 float sb200_last_kernel_ms(sb200_handle* h);
 /* per-kernel device times (ms) of the most recent sb200_rx11a_batch: [0] carrier sense, [1] OFDM front end,
@@ -91,6 +94,9 @@ int sb200_last_kernel_times(sb200_handle* h, float* ms4);
  * "host_decimate" (default 0 = off): number of host threads (the caller's included) that gather the even samples of every slot of a chunk
  * into pinned staging memory before the copy — TDownSample2 (Brick11/src/samples.hpp:27-49) keeps samples 0 and 2 of every 4, so the
  * 802.11a chain never reads the odd ones and only half of a host-resident 40 Msps capture has to cross PCIe.  Results are identical.
+ * "host_decimate_mix" (default 1): with host_decimate on, 1 = per chunk the call either gathers on the host threads or — when the copies
+ *   already queued would run out before a gather could finish — sends the chunk as it is, so that the link and the host cores are both kept
+ *   busy (link rate and gather cost are estimated from the call's own events); 0 = every chunk is gathered; 2 = alternate (tests).
  * Slot tables (frame_off/frame_len) are bounds-checked against iq_total_samples on EVERY call, host- or device-resident (a device table costs one
  * small reduction kernel and an 8-byte read-back).  "slot_table_immutable" (default 0): set to 1 to promise that a device-resident table is not
  * rewritten while the same pointers, count and total are passed again; only then is the check (and the host copy the chunked path needs) cached. */

@@ -169,6 +169,14 @@ struct sb200_handle {
     uint32_t front_stage = 0;                          // option: sample staging of k_front11a (0 direct loads, 1 register double buffer, 2 bulk async copy to shared memory)
     uint32_t host_decimate = 0;                        // option: host threads gathering the even samples of host-resident 40 Msps captures (0 = off)
     DecimPool* pool = nullptr; void* hstage[3] = {nullptr, nullptr, nullptr}; size_t hstage_cap = 0; cudaEvent_t ev_hfree[3] = {nullptr, nullptr, nullptr};
+    // host_decimate_mix (default 1 = adaptive): per chunk, the decimating path either gathers on the host threads (half the bytes cross) or,
+    // when the copies already queued would run out before a gather could finish, sends the chunk as it is — the link and the host cores are
+    // two resources and the call keeps both busy.  0 = every chunk gathered; 2 = alternate (tests).
+    uint32_t host_mix = 1;
+    std::vector<cudaEvent_t> ev_link; std::vector<uint64_t> link_bytes;     // one timed event per chunk copy of the current call, and its size
+    double link_bpms = 50e6;                           // estimate of the link rate, bytes per ms (largest rate seen between two consecutive copy ends)
+    double gather_ms_per_sample = 0.0;                 // running estimate of the host gather cost per 40 Msps sample (0 = not measured yet)
+    uint64_t last_h2d_bytes = 0, last_gathered_chunks = 0, last_chunks = 0;
     DevBuf doff; std::vector<uint64_t> doffh;
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
@@ -263,6 +271,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     for (int i = 0; i < 5; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     for (int i = 0; i < 2; i++) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); h->stage[i].release(); }
+    for (cudaEvent_t e : h->ev_link) cudaEventDestroy(e);
     delete h->pool; for (int i = 0; i < 3; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); if (h->ev_hfree[i]) cudaEventDestroy(h->ev_hfree[i]); }
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_front) cudaStreamDestroy(h->s_front);
@@ -270,6 +279,13 @@ extern "C" void sb200_destroy(sb200_handle* h) {
 }
 extern "C" const char* sb200_last_error(const sb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" uint64_t sb200_launch_count(const sb200_handle* h) { return h ? h->launches : 0; }
+extern "C" int sb200_last_transfer(const sb200_handle* h, uint64_t* h2d_bytes, uint32_t* chunks, uint32_t* chunks_gathered) {
+    if (!h) return SB200_E_INVALID;
+    if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
+    if (chunks) *chunks = (uint32_t)h->last_chunks;
+    if (chunks_gathered) *chunks_gathered = (uint32_t)h->last_gathered_chunks;
+    return SB200_OK;
+}
 extern "C" float sb200_last_kernel_ms(sb200_handle* h) {
     if (!h || !h->timed) return -1.f;
     float ms = -1.f;
@@ -415,7 +431,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
     if (!pipelined) {
         const uint32_t* d_iq;
         if (iq_dev) d_iq = (const uint32_t*)iq;
-        else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; }
+        else { CK(h->iq.need(iq_total * 4ull)); CK(cudaMemcpyAsync(h->iq.p, iq, iq_total * 4ull, cudaMemcpyHostToDevice, st)); d_iq = (const uint32_t*)h->iq.p; h->last_h2d_bytes = iq_total * 4ull; h->last_gathered_chunks = 0; h->last_chunks = 1; }
         int rc = launch_chunk(h, d_iq, d_off, d_len, 0, nframes, soft_stride, row, st, st, nullptr, taps, true, dc_init, 0, rate20 ? 0u : 1u, rate20 ? 1u : 0u);
         if (rc != SB200_OK) return rc;
         h->nk = 4;
@@ -423,64 +439,103 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         // host IQ: per-chunk sample range [lo, hi) staged through two device buffers; with host_decimate only the even samples of every slot
         // travel, gathered by the host threads into one of three pinned buffers while earlier chunks are on the wire / in the kernels
         const bool dec = !iq_dev && h->host_decimate > 0;
-        const uint64_t* d_off_k = d_off; std::vector<uint64_t>& doffh = h->doffh;
-        uint64_t stage_samples = 0;
+        const uint32_t mix = dec ? h->host_mix : 0u;
+        const uint64_t* d_off_dec = nullptr; std::vector<uint64_t>& doffh = h->doffh;
+        uint64_t stage_samples = 0, hstage_samples = 0;
+        const uint32_t nchunks = (nframes + chunk - 1) / chunk;
         if (!iq_dev) {
             if (dec) {
                 doffh.resize((size_t)nframes + 1); doffh[0] = 0;
                 for (uint32_t i = 0; i < nframes; i++) doffh[i + 1] = doffh[i] + (lenh[i] + 1u) / 2u;
             }
             for (uint32_t f0 = 0; f0 < nframes; f0 += chunk) {
-                uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; uint64_t lo = ~0ull, hi = 0;
-                if (dec) { lo = doffh[f0]; hi = doffh[f1]; }
-                else for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
-                if (hi - lo > stage_samples) stage_samples = hi - lo;
+                const uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes;
+                if (dec) { const uint64_t n = doffh[f1] - doffh[f0]; if (n > hstage_samples) hstage_samples = n; if (n > stage_samples) stage_samples = n; }
+                if (!dec || mix) {
+                    uint64_t lo = ~0ull, hi = 0;
+                    for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
+                    if (hi - lo > stage_samples) stage_samples = hi - lo;
+                }
             }
             CK(h->stage[0].need(stage_samples * 4ull + 16)); CK(h->stage[1].need(stage_samples * 4ull + 16));
             if (dec) {
                 if (!h->pool || h->pool->n != (int)h->host_decimate) { delete h->pool; h->pool = new (std::nothrow) DecimPool(); if (!h->pool) return h->fail(SB200_E_NOMEM, "host thread pool"); h->pool->start((int)h->host_decimate); }
-                if (h->hstage_cap < stage_samples * 4ull) {
+                if (h->hstage_cap < hstage_samples * 4ull) {
                     for (int i = 0; i < 3; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); h->hstage[i] = nullptr; }
                     h->hstage_cap = 0;
-                    const size_t want_b = stage_samples * 4ull + stage_samples / 2 + 256;
+                    const size_t want_b = hstage_samples * 4ull + hstage_samples / 2 + 256;
                     for (int i = 0; i < 3; i++) CK(cudaHostAlloc(&h->hstage[i], want_b, cudaHostAllocDefault));
                     h->hstage_cap = want_b;
                 }
                 for (int i = 0; i < 3; i++) if (!h->ev_hfree[i]) CK(cudaEventCreateWithFlags(&h->ev_hfree[i], cudaEventDisableTiming));
                 CK(h->doff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->doff.p, doffh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st));
-                d_off_k = (const uint64_t*)h->doff.p;
+                d_off_dec = (const uint64_t*)h->doff.p;
             }
+            while (h->ev_link.size() < nchunks) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev_link.push_back(e); }
+            h->link_bytes.assign(nchunks, 0);
         }
         CK(cudaEventRecord(h->ev_start, st));
         CK(cudaStreamWaitEvent(h->s_copy, h->ev_start, 0)); CK(cudaStreamWaitEvent(h->s_front, h->ev_start, 0));
-        uint32_t k = 0;
+        uint32_t k = 0, gk = 0, link_head = 0;            // chunk index, gathered chunks so far, first chunk whose copy may still be on the wire
+        uint64_t h2d_bytes = 0;
+        if (!iq_dev) h->gather_ms = 0.0;
         for (uint32_t f0 = 0; f0 < nframes; f0 += chunk, k++) {
             const uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; const int b = k & 1;
             const uint32_t* base = (const uint32_t*)iq;
-            if (dec) {
-                const int hb = (int)(k % 3u);
-                if (k == 0) h->gather_ms = 0.0;
-                if (k >= 3) CK(cudaEventSynchronize(h->ev_hfree[hb]));                      // pinned buffer hb is free once chunk k-3 has crossed the link
-                DecimPool::Job j{(const uint32_t*)iq, offh.data(), lenh.data(), doffh.data(), f0, f1, (uint32_t*)h->hstage[hb]};
-                const auto tg0 = std::chrono::steady_clock::now();
-                h->pool->run(j);
-                h->gather_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
-                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));
-                CK(cudaMemcpyAsync(h->stage[b].p, h->hstage[hb], (doffh[f1] - doffh[f0]) * 4ull, cudaMemcpyHostToDevice, h->s_copy));
-                CK(cudaEventRecord(h->ev_hfree[hb], h->s_copy));
+            const uint64_t* d_off_k = d_off; uint32_t sh_k = 1u;
+            if (!iq_dev) {
+                uint64_t lo = ~0ull, hi = 0;                 // the chunk's span in the capture, for the copy as it is
+                if (!dec || mix) for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
+                bool gather = dec;
+                if (dec && mix == 2u) gather = (k & 1u) != 0u;
+                else if (dec && mix) {
+                    // bytes still queued on the link: copies whose end event has not fired.  Two consecutive ends also give the link rate.
+                    uint64_t pend = 0;
+                    for (uint32_t i = link_head; i < k; i++) {
+                        const cudaError_t q = cudaEventQuery(h->ev_link[i]);
+                        if (q == cudaSuccess) {
+                            if (i == link_head) {
+                                float ms = 0.f;
+                                if (i > 0 && cudaEventElapsedTime(&ms, h->ev_link[i - 1], h->ev_link[i]) == cudaSuccess && ms > 0.f) {
+                                    const double r = (double)h->link_bytes[i] / ms;
+                                    h->link_bpms = r > h->link_bpms ? r : 0.95 * h->link_bpms + 0.05 * r;   // a gap before the copy only lowers r
+                                }
+                                link_head++;
+                            }
+                        } else if (q == cudaErrorNotReady) { (void)cudaGetLastError(); pend += h->link_bytes[i]; }
+                        else return h->fail(SB200_E_CUDA, "cudaEventQuery", q);
+                    }
+                    const double pend_ms = (double)pend / h->link_bpms;
+                    const double gather_est = h->gather_ms_per_sample * (double)(hi - lo);
+                    // not measured yet: the first chunk goes as it is (the link is idle anyway), the second is gathered and gives the estimate
+                    gather = h->gather_ms_per_sample > 0.0 ? pend_ms >= gather_est : k != 0u;
+                }
+                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));            // device buffer b is free once chunk k-2's front end has read it
+                if (gather) {
+                    const int hb = (int)(gk % 3u);
+                    if (gk >= 3) CK(cudaEventSynchronize(h->ev_hfree[hb]));                    // pinned buffer hb is free once the gathered chunk three back has crossed the link
+                    DecimPool::Job j{(const uint32_t*)iq, offh.data(), lenh.data(), doffh.data(), f0, f1, (uint32_t*)h->hstage[hb]};
+                    const auto tg0 = std::chrono::steady_clock::now();
+                    h->pool->run(j);
+                    const double gms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
+                    h->gather_ms += gms;
+                    const double per = gms / (double)(2u * (doffh[f1] - doffh[f0]) + 1u);
+                    h->gather_ms_per_sample = h->gather_ms_per_sample > 0.0 ? 0.75 * h->gather_ms_per_sample + 0.25 * per : per;
+                    h->link_bytes[k] = (doffh[f1] - doffh[f0]) * 4ull;
+                    CK(cudaMemcpyAsync(h->stage[b].p, h->hstage[hb], h->link_bytes[k], cudaMemcpyHostToDevice, h->s_copy));
+                    CK(cudaEventRecord(h->ev_hfree[hb], h->s_copy));
+                    base = (const uint32_t*)h->stage[b].p - doffh[f0]; d_off_k = d_off_dec; sh_k = 0u; gk++;
+                } else {
+                    h->link_bytes[k] = (hi - lo) * 4ull;
+                    CK(cudaMemcpyAsync(h->stage[b].p, (const uint32_t*)iq + lo, h->link_bytes[k], cudaMemcpyHostToDevice, h->s_copy));
+                    base = (const uint32_t*)h->stage[b].p - lo;
+                }
+                h2d_bytes += h->link_bytes[k];
+                CK(cudaEventRecord(h->ev_link[k], h->s_copy));
                 CK(cudaEventRecord(h->ev_h2d[b], h->s_copy));
                 CK(cudaStreamWaitEvent(h->s_front, h->ev_h2d[b], 0));
-                base = (const uint32_t*)h->stage[b].p - doffh[f0];
-            } else if (!iq_dev) {
-                uint64_t lo = ~0ull, hi = 0;
-                for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
-                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));        // buffer b free once chunk k-2's front end has read it
-                CK(cudaMemcpyAsync(h->stage[b].p, (const uint32_t*)iq + lo, (hi - lo) * 4ull, cudaMemcpyHostToDevice, h->s_copy));
-                CK(cudaEventRecord(h->ev_h2d[b], h->s_copy));
-                CK(cudaStreamWaitEvent(h->s_front, h->ev_h2d[b], 0));
-                base = (const uint32_t*)h->stage[b].p - lo;
             }
-            int rc = launch_chunk(h, base, d_off_k, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false, nullptr, k, dec ? 0u : 1u);
+            int rc = launch_chunk(h, base, d_off_k, d_len, f0, f1, soft_stride, row, h->s_front, st, h->ev_front[b], taps, false, nullptr, k, sh_k);
             if (rc != SB200_OK) return rc;
             // results of this chunk go back while the next chunks are still coming in (PCIe is full duplex): only the last chunk's
             // device-to-host copy is left exposed at the end of the call
@@ -493,8 +548,9 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
             }
             if (!res_dev_all) CK(cudaMemcpyAsync(res + f0, d_res_all + f0, n * sizeof(sb200_frame_result), cudaMemcpyDeviceToHost, st));
         }
+        if (!iq_dev) { h->last_h2d_bytes = h2d_bytes; h->last_gathered_chunks = gk; h->last_chunks = k; }
         h->nk = 0;
-        if (dec && getenv("SB200_TRACE")) fprintf(stderr, "[sb200] rx11a host_decimate: %u chunks, host gather %.2f ms in total (%u threads)\n", k, h->gather_ms, h->host_decimate);
+        if (dec && getenv("SB200_TRACE")) fprintf(stderr, "[sb200] rx11a host_decimate: %u chunks (%u gathered, %u sent as they are), host gather %.2f ms in total (%u threads), link estimate %.1f GB/s, %.1f MB copied\n", k, gk, k - gk, h->gather_ms, h->host_decimate, h->link_bpms / 1e6, h2d_bytes / 1e6);
     }
     const bool res_dev = res_dev_all;
     sb200_frame_result* d_res = d_res_all;
@@ -1328,6 +1384,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "vq_pad_smem")) { h->vq_pad_smem = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "front_stage")) { if (value > 2) return h->fail(SB200_E_INVALID, "front_stage is 0, 1 or 2"); h->front_stage = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
+    if (!strcmp(name, "host_decimate_mix")) { if (value > 2) return h->fail(SB200_E_INVALID, "host_decimate_mix: 0, 1 or 2"); h->host_mix = (uint32_t)value; h->gather_ms_per_sample = 0.0; return SB200_OK; }
     if (!strcmp(name, "slot_table_immutable")) { h->tab_immutable = value != 0; h->tab_off = nullptr; return SB200_OK; }
     if (!strcmp(name, "ht_mcs_limit")) { if (value < 9 || value > 15) return h->fail(SB200_E_INVALID, "ht_mcs_limit is the first 802.11n MCS index refused: 9 .. 15 (11 = the reference's parser, 15 = MCS 8..14)"); h->ht_mcs_limit = (uint32_t)value; return SB200_OK; }
     return h->fail(SB200_E_INVALID, "unknown option");

@@ -207,7 +207,21 @@ def test_chunked_pipeline_host_and_device(eng):
             r1, o1 = eng.rx11a_batch(flat, off, lo)
             eng.set_option("host_decimate", 0); r0, o0 = eng.rx11a_batch(flat, off, lo); eng.set_option("host_decimate", nthreads)
             assert (r1 == r0).all() and (o1 == o0).all()
+        # the mix of gathered chunks and chunks sent as they are: forced alternation, the adaptive rule (twice: the second call has its
+        # estimates), every chunk gathered — same results, and sb200_last_transfer reports what really crossed the link
+        slot_bytes = int(ln[0]) * 4; half_bytes = (int(ln[0]) + 1) // 2 * 4
+        for mix, ngath in ((2, 2), (1, None), (1, None), (0, 4)):
+            eng.set_option("host_decimate_mix", mix)
+            res, out = eng.rx11a_batch(flat, off, ln)
+            assert (res == ref).all() and (out == refo).all()
+            nbytes, chunks, gathered = eng.last_transfer()
+            assert chunks == 4 and (ngath is None or gathered == ngath)
+            if mix == 0: assert nbytes == 11 * half_bytes
+            if mix == 2: assert nbytes == (3 + 3) * slot_bytes + (3 + 2) * half_bytes          # chunks of 3, 3, 3, 2 slots: 0 and 2 as they are, 1 and 3 gathered
+            assert 11 * half_bytes <= nbytes <= 11 * slot_bytes
+        eng.set_option("host_decimate_mix", 1)
         eng.set_option("host_decimate", 0)
+        res, out = eng.rx11a_batch(flat, off, ln); assert eng.last_transfer() == (11 * slot_bytes, 4, 0)
         dev = torch.device("cuda", 0)
         t_iq = torch.from_numpy(flat).to(dev); t_off = torch.from_numpy(off.astype(np.int64)).to(dev); t_len = torch.from_numpy(ln.astype(np.int32)).to(dev)
         t_out = torch.zeros((11, 256), dtype=torch.uint8, device=dev); t_res = torch.zeros((11, 7), dtype=torch.int32, device=dev)
@@ -218,7 +232,7 @@ def test_chunked_pipeline_host_and_device(eng):
         assert (t_res.cpu().numpy().view(api.RESULT_DTYPE).reshape(-1) == ref).all()
         assert (t_out.cpu().numpy()[:, :180] == ps).all()
     finally:
-        eng.set_option("chunk_frames", 4096); eng.set_option("chunk_frames_device", 0); eng.set_option("slot_table_immutable", 0); eng.set_option("host_decimate", 0)
+        eng.set_option("chunk_frames", 4096); eng.set_option("chunk_frames_device", 0); eng.set_option("slot_table_immutable", 0); eng.set_option("host_decimate", 0); eng.set_option("host_decimate_mix", 1)
 
 def test_44msps_capture(eng):
     """sb200_rx11a_batch_ex(sample_rate_mhz=44): on-device 11:10 resampler + the 40 Msps chain == oracle doing the same."""
