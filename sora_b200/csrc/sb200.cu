@@ -107,33 +107,35 @@ bool is_device_ptr(const void* p) {
 namespace sb { void gather_even(const uint32_t* src, uint32_t n2, uint32_t* dst); }      // host_gather.cpp: dst[j] = src[2 j], streaming stores, SSE2 / AVX-512 chosen at run time
 static inline void decimate_slot(const uint32_t* src, uint32_t n2, uint32_t* dst) { sb::gather_even(src, n2, dst); }
 struct DecimPool {
+    // n worker threads; submit() hands them one chunk and returns, wait() blocks until it is gathered: the caller queues the previous chunk's
+    // copies and kernels in between, so the host cores never wait for the launch path (and the launch path never waits for them).
     struct Job { const uint32_t* iq; const uint64_t* off; const uint32_t* len; const uint64_t* doff; uint32_t f0, f1; uint32_t* dst; };
     std::vector<std::thread> th; std::mutex m; std::condition_variable cv, cv_done;
     Job job{}; uint64_t gen = 0; int pending = 0; bool stop = false; int n = 0;
+    std::chrono::steady_clock::time_point t_submit; double last_ms = 0.0;   // wall time from submit() to the last worker's end
     static void part(const Job& j, int w, int n) {
         const uint64_t cnt = j.f1 - j.f0; const uint32_t a = j.f0 + (uint32_t)(cnt * w / n), b = j.f0 + (uint32_t)(cnt * (w + 1) / n);
         for (uint32_t f = a; f < b; f++) decimate_slot(j.iq + j.off[f], (j.len[f] + 1u) / 2u, j.dst + (j.doff[f] - j.doff[j.f0]));
         _mm_sfence();                                   // streaming stores visible before the copy is queued
     }
-    void start(int nthreads) {                          // nthreads includes the calling thread
+    void start(int nthreads) {
         shutdown(); n = nthreads < 1 ? 1 : nthreads; stop = false;
-        for (int w = 1; w < n; w++) th.emplace_back([this, w]() {
+        for (int w = 0; w < n; w++) th.emplace_back([this, w]() {
             uint64_t seen = 0;
             for (;;) {
                 Job j;
                 { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; j = job; }
                 part(j, w, n);
-                { std::lock_guard<std::mutex> l(m); if (--pending == 0) cv_done.notify_one(); }
+                { std::lock_guard<std::mutex> l(m);
+                  if (--pending == 0) { last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_submit).count(); cv_done.notify_all(); } }
             }
         });
     }
-    void run(const Job& j) {
-        if (n <= 1) { part(j, 0, 1); return; }
-        { std::lock_guard<std::mutex> l(m); job = j; gen++; pending = n - 1; }
+    void submit(const Job& j) {                         // one job in flight at a time: wait() first
+        { std::lock_guard<std::mutex> l(m); job = j; gen++; pending = n; t_submit = std::chrono::steady_clock::now(); }
         cv.notify_all();
-        part(j, 0, n);
-        std::unique_lock<std::mutex> l(m); cv_done.wait(l, [&] { return pending == 0; });
     }
+    double wait() { std::unique_lock<std::mutex> l(m); cv_done.wait(l, [&] { return pending == 0; }); return last_ms; }
     void shutdown() {
         { std::lock_guard<std::mutex> l(m); stop = true; }
         cv.notify_all();
@@ -168,7 +170,7 @@ struct sb200_handle {
     const uint64_t* tab_off = nullptr; const uint32_t* tab_len = nullptr; uint32_t tab_n = 0, tab_max_len = 0; uint64_t tab_total = 0; bool tab_host = false;
     uint32_t front_stage = 0;                          // option: sample staging of k_front11a (0 direct loads, 1 register double buffer, 2 bulk async copy to shared memory)
     uint32_t host_decimate = 0;                        // option: host threads gathering the even samples of host-resident 40 Msps captures (0 = off)
-    DecimPool* pool = nullptr; void* hstage[3] = {nullptr, nullptr, nullptr}; size_t hstage_cap = 0; cudaEvent_t ev_hfree[3] = {nullptr, nullptr, nullptr};
+    DecimPool* pool = nullptr; void* hstage[4] = {nullptr, nullptr, nullptr, nullptr}; size_t hstage_cap = 0; cudaEvent_t ev_hfree[4] = {nullptr, nullptr, nullptr, nullptr};
     // host_decimate_mix (default 1 = adaptive): per chunk, the decimating path either gathers on the host threads (half the bytes cross) or,
     // when the copies already queued would run out before a gather could finish, sends the chunk as it is — the link and the host cores are
     // two resources and the call keeps both busy.  0 = every chunk gathered; 2 = alternate (tests).
@@ -177,11 +179,13 @@ struct sb200_handle {
     double link_bpms = 50e6;                           // estimate of the link rate, bytes per ms (largest rate seen between two consecutive copy ends)
     double gather_ms_per_sample = 0.0;                 // running estimate of the host gather cost per 40 Msps sample (0 = not measured yet)
     uint64_t last_h2d_bytes = 0, last_gathered_chunks = 0, last_chunks = 0;
+    std::vector<uint64_t> chunk_lo, chunk_hi; std::vector<int8_t> chunk_buf;   // per chunk of the current call: span in the capture, pinned buffer of a gathered chunk
     DevBuf doff; std::vector<uint64_t> doffh;
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
-    bool use_gring = false;                            // SB200_VITERBI=v5 / v6: history ring in global memory (v5: two lanes per code block, v6: four)
+    bool use_gring = false;                            // SB200_VITERBI=v5 / v6 / v7: history ring in global memory (v5: two lanes per code block, v6: four, v7: one)
+    bool use_lane = false;                             // SB200_VITERBI=v7: one lane per code block, 32 code blocks per warp, no lane exchange at all
     DevBuf vring;
     bool use_pair = false;                             // SB200_VITERBI=v4: two lanes per code block, 16 code blocks per warp (A/B against four lanes)
     bool use_v2 = false;                               // SB200_VITERBI=v2 selects the per-step-mark quad kernel (A/B against the history-carrying one)
@@ -246,7 +250,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6'); }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6' || e[1] == '7'); h->use_lane = e && e[0] == 'v' && e[1] == '7'; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
@@ -272,7 +276,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     for (int i = 0; i < 2; i++) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]); h->stage[i].release(); }
     for (cudaEvent_t e : h->ev_link) cudaEventDestroy(e);
-    delete h->pool; for (int i = 0; i < 3; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); if (h->ev_hfree[i]) cudaEventDestroy(h->ev_hfree[i]); }
+    delete h->pool; for (int i = 0; i < 4; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); if (h->ev_hfree[i]) cudaEventDestroy(h->ev_hfree[i]); }
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_front) cudaStreamDestroy(h->s_front);
     delete h;
@@ -348,6 +352,25 @@ static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t
     return SB200_OK;
 }
 
+// One launch of the history-carrying Viterbi for code rate CR in the variant the handle selects (SB200_VITERBI: four or two lanes per code
+// block, history ring in shared or in global memory).  vring_need() sizes the global ring for n code blocks first.
+static cudaError_t vring_need(sb200_handle* h, uint32_t n) {
+    if (!h->use_gring) return cudaSuccess;
+    const size_t per = h->use_lane ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
+    return h->vring.need((n + per - 1) / per * SB_VR_NB * per * 64);
+}
+template <int CR>
+static void launch_viterbi_re(sb200_handle* h, uint32_t n, cudaStream_t s, const uint8_t* soft, uint64_t soft_stride, const uint32_t* list, const uint32_t* cnt,
+                              const FrameInfo* info, const VitJob& job, uint8_t* out, uint64_t out_stride, uint32_t raw_off, uint32_t* nraw) {
+    const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
+    uint4* const ring = (uint4*)h->vring.p;
+    if (h->use_lane)                 k_viterbi_re<CR, 0, true><<<(n + 31) / 32, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
+    else if (h->use_gring && h->use_pair) k_viterbi_re<CR, 1, true><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
+    else if (h->use_gring)           k_viterbi_re<CR, 2, true><<<g, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
+    else if (h->use_pair)            k_viterbi_re<CR, 1><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw);
+    else                             k_viterbi_re<CR, 2><<<g, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw);
+}
+
 // Launch the decode kernels for frames [f0, f1) of a call.  `iq_base + off[f]` must address slot f.
 // sync + front end go to `sf`, the Viterbi launches to `sv` (sv waits for `front_done` when the streams differ).
 static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t f0, uint32_t f1,
@@ -374,14 +397,13 @@ static int launch_chunk(sb200_handle* h, const uint32_t* iq_base, const uint64_t
         k_viterbi_quad<CR_23><<<g, b, 0, sv>>>(d_soft, soft_stride, n, d_info, job, h->T, d_out, row, d_status, d_crc);
         h->launches += 5;
     } else {                                           // history-carrying kernel: work lists per code rate, one launch per rate, descrambler / frame sink
-        const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
-        if (h->use_gring) CK(h->vring.need((size_t)(h->use_pair ? gp : g) * SB_VR_NB * (h->use_pair ? 16 : 8) * 64));
+        CK(vring_need(h, n));
         uint32_t* d_list = (uint32_t*)h->vlist.p + 3 * (size_t)f0; uint32_t* d_cnt = (uint32_t*)h->vcnt.p + 4 * (size_t)chunk_idx;
         CK(cudaMemsetAsync(d_cnt, 0, 16, sv));
         k_vit_lists<<<(n + 255) / 256, 256, 0, sv>>>(d_info, n, d_cnt, d_list);
-        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_34, 1, true><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); else k_viterbi_re<CR_34, 2, true><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_34, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
-        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_12, 1, true><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); else k_viterbi_re<CR_12, 2, true><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_12, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
-        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_23, 1, true><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); else k_viterbi_re<CR_23, 2, true><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); else k_viterbi_re<CR_23, 2><<<g, 32, 0, sv>>>(d_soft, soft_stride, n, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status); } while (0);
+        launch_viterbi_re<CR_34>(h, n, sv, d_soft, soft_stride, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status);
+        launch_viterbi_re<CR_12>(h, n, sv, d_soft, soft_stride, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status);
+        launch_viterbi_re<CR_23>(h, n, sv, d_soft, soft_stride, d_list, d_cnt, d_info, job, d_out, row, 14u, d_status);
         k_sink11a<<<(n + 127) / 128, 128, 0, sv>>>(d_out, row, n, d_info, h->T, d_status, d_crc);
         h->launches += 7;
     }
@@ -437,7 +459,7 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         h->nk = 4;
     } else {
         // host IQ: per-chunk sample range [lo, hi) staged through two device buffers; with host_decimate only the even samples of every slot
-        // travel, gathered by the host threads into one of three pinned buffers while earlier chunks are on the wire / in the kernels
+        // travel, gathered by the host threads into one of four pinned buffers while earlier chunks are on the wire / in the kernels
         const bool dec = !iq_dev && h->host_decimate > 0;
         const uint32_t mix = dec ? h->host_mix : 0u;
         const uint64_t* d_off_dec = nullptr; std::vector<uint64_t>& doffh = h->doffh;
@@ -461,13 +483,13 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
             if (dec) {
                 if (!h->pool || h->pool->n != (int)h->host_decimate) { delete h->pool; h->pool = new (std::nothrow) DecimPool(); if (!h->pool) return h->fail(SB200_E_NOMEM, "host thread pool"); h->pool->start((int)h->host_decimate); }
                 if (h->hstage_cap < hstage_samples * 4ull) {
-                    for (int i = 0; i < 3; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); h->hstage[i] = nullptr; }
+                    for (int i = 0; i < 4; i++) { if (h->hstage[i]) cudaFreeHost(h->hstage[i]); h->hstage[i] = nullptr; }
                     h->hstage_cap = 0;
                     const size_t want_b = hstage_samples * 4ull + hstage_samples / 2 + 256;
-                    for (int i = 0; i < 3; i++) CK(cudaHostAlloc(&h->hstage[i], want_b, cudaHostAllocDefault));
+                    for (int i = 0; i < 4; i++) CK(cudaHostAlloc(&h->hstage[i], want_b, cudaHostAllocDefault));
                     h->hstage_cap = want_b;
                 }
-                for (int i = 0; i < 3; i++) if (!h->ev_hfree[i]) CK(cudaEventCreateWithFlags(&h->ev_hfree[i], cudaEventDisableTiming));
+                for (int i = 0; i < 4; i++) if (!h->ev_hfree[i]) CK(cudaEventCreateWithFlags(&h->ev_hfree[i], cudaEventDisableTiming));
                 CK(h->doff.need(nframes * 8ull)); CK(cudaMemcpyAsync(h->doff.p, doffh.data(), nframes * 8ull, cudaMemcpyHostToDevice, st));
                 d_off_dec = (const uint64_t*)h->doff.p;
             }
@@ -476,59 +498,80 @@ static int rx11a_run(sb200_handle* h, const int16_t* iq, uint64_t iq_total, cons
         }
         CK(cudaEventRecord(h->ev_start, st));
         CK(cudaStreamWaitEvent(h->s_copy, h->ev_start, 0)); CK(cudaStreamWaitEvent(h->s_front, h->ev_start, 0));
-        uint32_t k = 0, gk = 0, link_head = 0;            // chunk index, gathered chunks so far, first chunk whose copy may still be on the wire
+        uint32_t k = 0, gk = 0, gsub = 0, link_head = 0;  // chunk index, gathered chunks queued on the link / handed to the host threads, first chunk whose copy may still be on the wire
         uint64_t h2d_bytes = 0;
-        if (!iq_dev) h->gather_ms = 0.0;
+        std::vector<uint64_t>& clo = h->chunk_lo; std::vector<uint64_t>& chi = h->chunk_hi; std::vector<int8_t>& cbuf = h->chunk_buf;
+        if (!iq_dev) {
+            h->gather_ms = 0.0;
+            clo.assign(nchunks, 0); chi.assign(nchunks, 0); cbuf.assign(nchunks, -1);          // span of every chunk in the capture; pinned buffer of a gathered chunk (-1: sent as it is)
+            if (!dec || mix) for (uint32_t c = 0; c < nchunks; c++) {
+                const uint32_t f0 = c * chunk, f1 = f0 + chunk < nframes ? f0 + chunk : nframes; uint64_t lo = ~0ull, hi = 0;
+                for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
+                clo[c] = lo; chi[c] = hi;
+            }
+        }
+        struct InFlight { DecimPool* p = nullptr; bool on = false; ~InFlight() { if (p && on) p->wait(); } } inflight;   // no return while the host threads still read the caller's capture
+        inflight.p = h->pool;
+        // Decide how chunk c travels and, if it is to be gathered, hand it to the host threads now: the caller then queues the previous
+        // chunk's copies and kernels while they work.  `ahead` = bytes of the chunk that is about to be queued in front of it.
+        auto plan = [&](const uint32_t c, const uint64_t ahead) -> int {
+            const uint32_t f0 = c * chunk, f1 = f0 + chunk < nframes ? f0 + chunk : nframes;
+            bool gather = dec;
+            if (dec && mix == 2u) gather = (c & 1u) != 0u;
+            else if (dec && mix) {
+                // bytes still queued on the link: copies whose end event has not fired.  Two consecutive ends also give the link rate.
+                uint64_t pend = ahead;
+                for (uint32_t i = link_head; i + 1 < c; i++) {              // chunks 0 .. c-2 are queued; c-1 is `ahead`
+                    const cudaError_t q = cudaEventQuery(h->ev_link[i]);
+                    if (q == cudaSuccess) {
+                        if (i == link_head) {
+                            float ms = 0.f;
+                            if (i > 0 && cudaEventElapsedTime(&ms, h->ev_link[i - 1], h->ev_link[i]) == cudaSuccess && ms > 0.f) {
+                                const double r = (double)h->link_bytes[i] / ms;
+                                h->link_bpms = r > h->link_bpms ? r : 0.95 * h->link_bpms + 0.05 * r;   // a gap before the copy only lowers r
+                            }
+                            link_head++;
+                        }
+                    } else if (q == cudaErrorNotReady) { (void)cudaGetLastError(); pend += h->link_bytes[i]; }
+                    else return h->fail(SB200_E_CUDA, "cudaEventQuery", q);
+                }
+                const double pend_ms = (double)pend / h->link_bpms;
+                const double gather_est = h->gather_ms_per_sample * (double)(chi[c] - clo[c]);
+                // a gather whose copy would reach the link after it has run dry costs link time: send the chunk as it is instead.
+                // Not measured yet: the first chunk goes as it is (the link is idle anyway), the second is gathered and gives the estimate
+                gather = h->gather_ms_per_sample > 0.0 ? pend_ms >= gather_est : c != 0u;
+            }
+            if (!gather) return SB200_OK;
+            const int hb = (int)(gsub % 4u);
+            if (gsub >= 4) CK(cudaEventSynchronize(h->ev_hfree[hb]));                        // pinned buffer hb is free once the gathered chunk four back has crossed the link
+            DecimPool::Job j{(const uint32_t*)iq, offh.data(), lenh.data(), doffh.data(), f0, f1, (uint32_t*)h->hstage[hb]};
+            h->pool->submit(j); inflight.on = true;
+            cbuf[c] = (int8_t)hb; gsub++;
+            return SB200_OK;
+        };
+        if (!iq_dev) { const int rc = plan(0, 0); if (rc != SB200_OK) return rc; }
         for (uint32_t f0 = 0; f0 < nframes; f0 += chunk, k++) {
             const uint32_t f1 = f0 + chunk < nframes ? f0 + chunk : nframes; const int b = k & 1;
             const uint32_t* base = (const uint32_t*)iq;
             const uint64_t* d_off_k = d_off; uint32_t sh_k = 1u;
             if (!iq_dev) {
-                uint64_t lo = ~0ull, hi = 0;                 // the chunk's span in the capture, for the copy as it is
-                if (!dec || mix) for (uint32_t i = f0; i < f1; i++) { if (offh[i] < lo) lo = offh[i]; if (offh[i] + lenh[i] > hi) hi = offh[i] + lenh[i]; }
-                bool gather = dec;
-                if (dec && mix == 2u) gather = (k & 1u) != 0u;
-                else if (dec && mix) {
-                    // bytes still queued on the link: copies whose end event has not fired.  Two consecutive ends also give the link rate.
-                    uint64_t pend = 0;
-                    for (uint32_t i = link_head; i < k; i++) {
-                        const cudaError_t q = cudaEventQuery(h->ev_link[i]);
-                        if (q == cudaSuccess) {
-                            if (i == link_head) {
-                                float ms = 0.f;
-                                if (i > 0 && cudaEventElapsedTime(&ms, h->ev_link[i - 1], h->ev_link[i]) == cudaSuccess && ms > 0.f) {
-                                    const double r = (double)h->link_bytes[i] / ms;
-                                    h->link_bpms = r > h->link_bpms ? r : 0.95 * h->link_bpms + 0.05 * r;   // a gap before the copy only lowers r
-                                }
-                                link_head++;
-                            }
-                        } else if (q == cudaErrorNotReady) { (void)cudaGetLastError(); pend += h->link_bytes[i]; }
-                        else return h->fail(SB200_E_CUDA, "cudaEventQuery", q);
-                    }
-                    const double pend_ms = (double)pend / h->link_bpms;
-                    const double gather_est = h->gather_ms_per_sample * (double)(hi - lo);
-                    // not measured yet: the first chunk goes as it is (the link is idle anyway), the second is gathered and gives the estimate
-                    gather = h->gather_ms_per_sample > 0.0 ? pend_ms >= gather_est : k != 0u;
-                }
-                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));            // device buffer b is free once chunk k-2's front end has read it
-                if (gather) {
-                    const int hb = (int)(gk % 3u);
-                    if (gk >= 3) CK(cudaEventSynchronize(h->ev_hfree[hb]));                    // pinned buffer hb is free once the gathered chunk three back has crossed the link
-                    DecimPool::Job j{(const uint32_t*)iq, offh.data(), lenh.data(), doffh.data(), f0, f1, (uint32_t*)h->hstage[hb]};
-                    const auto tg0 = std::chrono::steady_clock::now();
-                    h->pool->run(j);
-                    const double gms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
+                const bool gathered = cbuf[k] >= 0;
+                if (gathered) {                              // the host threads finish this chunk; its cost per sample feeds the next decisions
+                    const double gms = h->pool->wait(); inflight.on = false;
                     h->gather_ms += gms;
                     const double per = gms / (double)(2u * (doffh[f1] - doffh[f0]) + 1u);
                     h->gather_ms_per_sample = h->gather_ms_per_sample > 0.0 ? 0.75 * h->gather_ms_per_sample + 0.25 * per : per;
-                    h->link_bytes[k] = (doffh[f1] - doffh[f0]) * 4ull;
-                    CK(cudaMemcpyAsync(h->stage[b].p, h->hstage[hb], h->link_bytes[k], cudaMemcpyHostToDevice, h->s_copy));
-                    CK(cudaEventRecord(h->ev_hfree[hb], h->s_copy));
+                }
+                h->link_bytes[k] = gathered ? (doffh[f1] - doffh[f0]) * 4ull : (chi[k] - clo[k]) * 4ull;
+                if (k + 1 < nchunks) { const int rc = plan(k + 1, h->link_bytes[k]); if (rc != SB200_OK) return rc; }
+                if (k >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_front[b], 0));            // device buffer b is free once chunk k-2's front end has read it
+                if (gathered) {
+                    CK(cudaMemcpyAsync(h->stage[b].p, h->hstage[cbuf[k]], h->link_bytes[k], cudaMemcpyHostToDevice, h->s_copy));
+                    CK(cudaEventRecord(h->ev_hfree[cbuf[k]], h->s_copy));
                     base = (const uint32_t*)h->stage[b].p - doffh[f0]; d_off_k = d_off_dec; sh_k = 0u; gk++;
                 } else {
-                    h->link_bytes[k] = (hi - lo) * 4ull;
-                    CK(cudaMemcpyAsync(h->stage[b].p, (const uint32_t*)iq + lo, h->link_bytes[k], cudaMemcpyHostToDevice, h->s_copy));
-                    base = (const uint32_t*)h->stage[b].p - lo;
+                    CK(cudaMemcpyAsync(h->stage[b].p, (const uint32_t*)iq + clo[k], h->link_bytes[k], cudaMemcpyHostToDevice, h->s_copy));
+                    base = (const uint32_t*)h->stage[b].p - clo[k];
                 }
                 h2d_bytes += h->link_bytes[k];
                 CK(cudaEventRecord(h->ev_link[k], h->s_copy));
@@ -875,14 +918,13 @@ static int rx11n_run(sb200_handle* h, const int16_t* iq0, const int16_t* iq1, ui
         k_viterbi_quad<CR_34><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
         if (h->ht_mcs_limit > 13u) k_viterbi_quad<CR_23><<<g, b, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, d_info, job, h->T, (uint8_t*)h->out.p, row, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
     } else {
-        const unsigned g = (nframes + SB_VR_FR - 1) / SB_VR_FR, gp = (nframes + 15) / 16;
-        if (h->use_gring) CK(h->vring.need((size_t)(h->use_pair ? gp : g) * SB_VR_NB * (h->use_pair ? 16 : 8) * 64));
+        CK(vring_need(h, nframes));
         CK(h->vlist.need(nframes * 12ull)); CK(h->vcnt.need(16));
         CK(cudaMemsetAsync(h->vcnt.p, 0, 16, st));
         k_vit_lists<<<(nframes + 255) / 256, 256, 0, st>>>(d_info, nframes, (uint32_t*)h->vcnt.p, (uint32_t*)h->vlist.p);
-        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_12, 1, true><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_12, 2, true><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0);
-        do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_34, 1, true><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_34, 2, true><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0);
-        if (h->ht_mcs_limit > 13u) { do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_23, 1, true><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_23, 2, true><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); else k_viterbi_re<CR_23, 2><<<g, 32, 0, st>>>((const uint8_t*)h->soft.p, soft_stride, nframes, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); } while (0); h->launches += 1; }
+        launch_viterbi_re<CR_12>(h, nframes, st, (const uint8_t*)h->soft.p, soft_stride, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        launch_viterbi_re<CR_34>(h, nframes, st, (const uint8_t*)h->soft.p, soft_stride, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p);
+        if (h->ht_mcs_limit > 13u) { launch_viterbi_re<CR_23>(h, nframes, st, (const uint8_t*)h->soft.p, soft_stride, (const uint32_t*)h->vlist.p, (const uint32_t*)h->vcnt.p, d_info, job, (uint8_t*)h->out.p, row, 14u, (uint32_t*)h->status.p); h->launches += 1; }
         k_sink11a<<<(nframes + 127) / 128, 128, 0, st>>>((uint8_t*)h->out.p, row, nframes, d_info, h->T, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);
         h->launches += 2;
     }
@@ -1446,11 +1488,10 @@ extern "C" int sb200_viterbi_k7(sb200_handle* h, const uint8_t* soft, uint64_t s
     VitJob job{}; job.code_rate = (uint32_t)code_rate; job.frame_len = frame_len_bytes; job.nsoft = nsoft; job.depth = depth; job.lookahead = lookahead; job.raw = 1;
     CK(cudaEventRecord(h->ev0, st));
     if (!h->use_v2) {
-        const unsigned g = (nblocks + SB_VR_FR - 1) / SB_VR_FR, gp = (nblocks + 15) / 16;
-        if (h->use_gring) CK(h->vring.need((size_t)(h->use_pair ? gp : g) * SB_VR_NB * (h->use_pair ? 16 : 8) * 64));
-        if (code_rate == CR_34) do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_34, 1, true><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_34, 2, true><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_34, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_34, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
-        else if (code_rate == CR_12) do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_12, 1, true><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_12, 2, true><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_12, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_12, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
-        else do { if (h->use_gring) { if (h->use_pair) k_viterbi_re<CR_23, 1, true><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); else k_viterbi_re<CR_23, 2, true><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p, (uint4*)h->vring.p); } else if (h->use_pair) k_viterbi_re<CR_23, 1><<<gp, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); else k_viterbi_re<CR_23, 2><<<g, 32, 0, st>>>(d_soft, d_stride, nblocks, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p); } while (0);
+        CK(vring_need(h, nblocks));
+        if (code_rate == CR_34) launch_viterbi_re<CR_34>(h, nblocks, st, d_soft, d_stride, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        else if (code_rate == CR_12) launch_viterbi_re<CR_12>(h, nblocks, st, d_soft, d_stride, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
+        else launch_viterbi_re<CR_23>(h, nblocks, st, d_soft, d_stride, nullptr, nullptr, nullptr, job, d_out, d_ostride, 0u, (uint32_t*)h->status.p);
     } else {
         const unsigned g = (nblocks + SB_VQ_FR - 1) / SB_VQ_FR, b = 32 * SB_VQ_WARPS;
         if (code_rate == CR_34) k_viterbi_quad<CR_34><<<g, b, 0, st>>>(d_soft, d_stride, nblocks, nullptr, job, h->T, d_out, d_ostride, (uint32_t*)h->status.p, (uint32_t*)h->crc.p);

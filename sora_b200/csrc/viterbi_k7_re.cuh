@@ -122,14 +122,17 @@ template <int CODE_RATE, int s> __device__ __forceinline__ uint32_t vr_bm(const 
 // collects the history bytes it passes, newest first, into the quad's scratch row `hb`: byte 0 = the kp decisions of the running block (right
 // aligned; absent when kp = 0), then one byte per block, bit 7 = the newest column of the block.  vr_emit turns the row into output bytes.
 // Kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the step loop.
-#define SB_VR_HB 48                                          // >= (7 + 31 + 256 + 6) / 8 + 2
-template <int FR, bool GR>
+#define SB_VR_HB 52                                          // >= (7 + 31 + 256 + 6) / 8 + 2; 13 words: rows of neighbouring lanes fall into different banks
+// SPLIT (one lane per code block): an entry is laid out [16-slot group][code block][16 bytes] so that a warp's 128-bit store is 512
+// contiguous bytes; otherwise [code block][64 bytes].  ring_b points at this code block's first 16 bytes of entry 0; EB = bytes per entry.
+template <int FR, bool SPLIT> __device__ __forceinline__ uint32_t vr_slot_off(const uint32_t A) { return SPLIT ? (A >> 4) * (FR * 16u) + (A & 15u) : A; }
+template <int FR, bool GR, bool SPLIT = false>
 __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ hb, uint32_t e, const uint32_t A0, const uint32_t t, uint32_t todo) {
     uint32_t A = A0, j = 0;
     uint32_t tt = t;                                         // time of the newest column not yet walked
     const uint32_t kp = t & 7u;
     if (kp) {                                                // running block: kp decisions in bits 0..kp-1, one slot-address bit changes per column
-        const uint32_t h = GR ? (uint32_t)__ldcg(ring_b + e * (FR * 64) + A) : (uint32_t)ring_b[e * (FR * 64) + A];
+        const uint32_t h = GR ? (uint32_t)__ldcg(ring_b + e * (FR * 64) + vr_slot_off<FR, SPLIT>(A)) : (uint32_t)ring_b[e * (FR * 64) + vr_slot_off<FR, SPLIT>(A)];
         const uint32_t take = min(kp, todo);
         for (uint32_t c = 0; c < take; c++) {                // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
             const uint32_t b = 5u - (tt - c - 1u) % 6u, d = (h >> (kp - 1u - c)) & 1u;
@@ -141,7 +144,7 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
     uint32_t ph = tt % 6u;                                   // phase of the block boundary the walk stands on
     const uint8_t* rp = ring_b + e * (FR * 64);
     while (todo >= 8u) {
-        const uint32_t h = GR ? (uint32_t)__ldcg(rp + A) : (uint32_t)rp[A];
+        const uint32_t h = GR ? (uint32_t)__ldcg(rp + vr_slot_off<FR, SPLIT>(A)) : (uint32_t)rp[vr_slot_off<FR, SPLIT>(A)];
         hb[j++] = (uint8_t)h;
         const uint32_t r = __brev(h) >> 24;                  // r bit i = h bit 7 - i = decision of column tt - i
         const uint32_t G = (r & 0x3Cu) | (r >> 6);           // slot-address bit (i - ph) mod 6 <- column tt - i, the two oldest overriding i = 0, 1
@@ -149,7 +152,7 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
         todo -= 8u; ph = ph >= 2u ? ph - 2u : ph + 4u;       // (tt - 8) mod 6
         rp = rp == ring_b ? ring_b + (SB_VR_NB - 1u) * (FR * 64) : rp - FR * 64;
     }
-    if (todo) hb[j++] = GR ? __ldcg(rp + A) : rp[A];         // oldest block of the window: only its newest `todo` columns count
+    if (todo) hb[j++] = GR ? __ldcg(rp + vr_slot_off<FR, SPLIT>(A)) : rp[vr_slot_off<FR, SPLIT>(A)];         // oldest block of the window: only its newest `todo` columns count
     hb[j] = 0; hb[j + 1] = 0;
 }
 // The nout / 8 decoded bytes of a window from the scratch row: bit k of the walk (k = 0 the newest column) sits at row bit (8 - kp) % 8 + k,
@@ -179,7 +182,7 @@ __device__ __forceinline__ uint32_t vr_best_core(const uint32_t (&R)[8 << (2 - L
             best = min(best, ((((v >> 9) << 1) | ((v >> tn) & 1u)) << 8) | ns);
         }
     }
-    best = min(best, __shfl_xor_sync(QM, best, 1));
+    if (LB >= 1) best = min(best, __shfl_xor_sync(QM, best, 1));
     if (LB == 2) best = min(best, __shfl_xor_sync(QM, best, 2));
     const uint32_t n = best & 63u;
     return ((n >> tm) | (n << (6u - tm))) & 63u;
@@ -195,6 +198,9 @@ __device__ __noinline__ uint32_t vr_best_slot16(uint32_t r0, uint32_t r1, uint32
     const uint32_t R[16] = {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15};
     return vr_best_core<1>(R, q, tm, tn, QM);
 }
+
+// one lane per code block: the 32 registers cannot travel as arguments; the scan is part of the (rare) trigger path
+__device__ __forceinline__ uint32_t vr_best_slot32(const uint32_t (&R)[32], const uint32_t tm, const uint32_t tn) { return vr_best_core<0>(R, 0u, tm, tn, 0u); }
 
 // sum of the two complementary branch metrics of step s: 28 with both coded bits, 14 with one
 template <int CODE_RATE, int s> __host__ __device__ constexpr uint32_t vr_ksum() {
@@ -236,7 +242,8 @@ struct VrDecoder {
             uint4 w;
             w.x = __byte_perm(R[8 * i + 0], R[8 * i + 1], 0x6420); w.y = __byte_perm(R[8 * i + 2], R[8 * i + 3], 0x6420);
             w.z = __byte_perm(R[8 * i + 4], R[8 * i + 5], 0x6420); w.w = __byte_perm(R[8 * i + 6], R[8 * i + 7], 0x6420);
-            if constexpr (GR) __stcg(ring_q + e * (FR * 4) + i, w); else ring_q[e * (FR * 4) + i] = w;
+            const uint32_t at = e * (FR * 4) + (LB == 0 ? i * FR : i);      // LB = 0: [group i][code block] (vr_slot_off)
+            if constexpr (GR) __stcg(ring_q + at, w); else ring_q[at] = w;
         }
     }
     __device__ __forceinline__ void clear_hist() {
@@ -247,9 +254,15 @@ struct VrDecoder {
     // viterbi.hpp:177-180 -> viterbicore.h:445-465: subtract (smallest byte & 0xFE) = the smallest m7; `mask` names the lanes that take part
     __device__ __forceinline__ void normalize(const unsigned mask) {
         uint32_t m = __vminu2(__vminu2(__vminu2(R[0], R[1]), __vminu2(R[2], R[3])), __vminu2(__vminu2(R[4], R[5]), __vminu2(R[6], R[7])));
-        if constexpr (NR == 16) m = __vminu2(m, __vminu2(__vminu2(__vminu2(R[8], R[9]), __vminu2(R[10], R[11])), __vminu2(__vminu2(R[12], R[13]), __vminu2(R[14], R[15]))));
+        if constexpr (NR >= 16) m = __vminu2(m, __vminu2(__vminu2(__vminu2(R[8], R[9]), __vminu2(R[10], R[11])), __vminu2(__vminu2(R[12], R[13]), __vminu2(R[14], R[15]))));
+        if constexpr (NR == 32) {
+            uint32_t m2 = __vminu2(__vminu2(__vminu2(R[16], R[17]), __vminu2(R[18], R[19])), __vminu2(__vminu2(R[20], R[21]), __vminu2(R[22], R[23])));
+            m2 = __vminu2(m2, __vminu2(__vminu2(__vminu2(R[24], R[25]), __vminu2(R[26], R[27])), __vminu2(__vminu2(R[28], R[29]), __vminu2(R[30], R[31]))));
+            m = __vminu2(m, m2);
+        }
         m = min(m & 0xFFFFu, m >> 16) >> 9;             // smallest m7 of this lane
-        m = min(m, __shfl_xor_sync(mask, m, 1)); if constexpr (LB == 2) m = min(m, __shfl_xor_sync(mask, m, 2));
+        if constexpr (LB >= 1) m = min(m, __shfl_xor_sync(mask, m, 1));
+        if constexpr (LB == 2) m = min(m, __shfl_xor_sync(mask, m, 2));
         const uint32_t mv = m * 0x02000200u;
 #pragma unroll
         for (int r = 0; r < NR; r++) R[r] -= mv;        // every half >= m << 9: no borrow between halves, histories untouched
@@ -257,7 +270,7 @@ struct VrDecoder {
     // windowed traceback from slot A0 at time t (viterbi.hpp:205-237): one lane of the quad walks the ring (vr_traceback)
     __device__ __forceinline__ void traceback(const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
         __syncwarp(QM);
-        if (q == 0) vr_traceback<FR, GR>(ring_b, hb, wslot, A0, t, la + nout);
+        if (q == 0) vr_traceback<FR, GR, LB == 0>(ring_b, hb, wslot, A0, t, la + nout);
         __syncwarp(QM);
         vr_emit(hb, op, out_cap, nraw, nout >> 3, t & 7u, la, (uint32_t)q, (uint32_t)NL);
         nraw += nout >> 3;
@@ -272,6 +285,7 @@ struct VrDecoder {
         if (nout) {                                     // uniform inside the quad
             uint32_t A0;
             if constexpr (LB == 2) A0 = vr_best_slot(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], (uint32_t)q, tm, (t - 1u) & 7u, QM);
+            else if constexpr (LB == 0) A0 = vr_best_slot32(R, tm, (t - 1u) & 7u);
             else A0 = vr_best_slot16(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8], R[9], R[10], R[11], R[12], R[13], R[14], R[15], (uint32_t)q, tm, (t - 1u) & 7u, QM);
             if (t & 7u) store_hist(wslot);              // mid-block: the partial histories of the running block (a block end has just stored its own)
             traceback(A0, t, la, nout);
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     d.nsoft = job.nsoft;
     if (valid && info) { const FrameInfo fi = info[f]; L = fi.length; d.nsoft = fi.soft_bytes; }
     if (!valid) d.nsoft = 0;
-    d.q = q; d.QM = (NL == 4 ? 0xFu : 0x3u) << (lane & ~(NL - 1));
+    d.q = q; d.QM = (NL == 4 ? 0xFu : NL == 2 ? 0x3u : 0x1u) << (lane & ~(NL - 1));
     d.depth = job.depth; d.look = job.lookahead;
     d.sp = soft + (size_t)f * soft_stride;
     d.op = out + (size_t)f * out_stride + raw_off;
@@ -364,8 +378,10 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
         const int K = vr_kcls(t);
         d.LC.sel[t][0] = vq_sel(0 ^ lc, 0 ^ K ^ lc); d.LC.sel[t][1] = vq_sel(1 ^ lc, 1 ^ K ^ lc);
     }
-    d.LC.bA[0] = (q >> (LB - 1)) & 1; d.LC.bB[0] = 1u - d.LC.bA[0];     // pair bit at T = 0 is address bit 5 (the top lane bit), at T = 1 (LB = 2) address bit 4
-    d.LC.bA[1] = q & 1;               d.LC.bB[1] = 1u - d.LC.bA[1];
+    if constexpr (LB >= 1) {
+        d.LC.bA[0] = (q >> (LB - 1)) & 1; d.LC.bB[0] = 1u - d.LC.bA[0]; // pair bit at T = 0 is address bit 5 (the top lane bit), at T = 1 (LB = 2) address bit 4
+        d.LC.bA[1] = q & 1;               d.LC.bB[1] = 1u - d.LC.bA[1];
+    } else { d.LC.bA[0] = d.LC.bA[1] = 0u; d.LC.bB[0] = d.LC.bB[1] = 0u; }   // one lane per code block: no lane-pair phase
     {   // history marks as run-time values (z is always 0, which the compiler cannot know): they must stay register operands
         const uint32_t z = (uint32_t)(soft_stride >> 63);
         d.kc[0] = 0x1C001C00u + z; d.kc[1] = 0x0E000E00u + z;
@@ -385,8 +401,8 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
     uint4* const ring0 = GR ? gring + (size_t)blockIdx.x * (SB_VR_NB * FR * 4) : &s_ring[0][0][0];      // this CTA's ring: [entry][code block][4 x 16 bytes]
-    d.ring_q = ring0 + fb * 4 + q * (4 / NL);           // + entry * (FR * 4): this lane's 16 / 32 bytes of the code block's 64
-    d.ring_b = (const uint8_t*)(ring0 + fb * 4);        // + entry * (FR * 64) + slot
+    d.ring_q = LB == 0 ? ring0 + fb : ring0 + fb * 4 + q * (4 / NL);     // + entry * (FR * 4): this lane's 16 / 32 / 64 bytes of the code block's 64 (LB = 0: + group * FR)
+    d.ring_b = (const uint8_t*)(LB == 0 ? ring0 + fb : ring0 + fb * 4);  // + entry * (FR * 64) + vr_slot_off(slot)
     d.hb = s_hb[fb];
 
     // lockstep part: all eight code blocks of the warp advance together, 24 or 6 steps at a time; the soft values of the next four chunks
