@@ -2,6 +2,7 @@
 // Single translation unit: the kernels live in the .cuh files included below.
 #include "../../include/sora_b200.h"
 #include "viterbi_k7_re.cuh"
+#include "viterbi_k7_lane.cuh"
 #include "rx11b_kernels.cuh"
 #include "rx11n_kernels.cuh"
 #include "tx11a_kernels.cuh"
@@ -185,6 +186,7 @@ struct sb200_handle {
     DevBuf slotchk;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
     bool use_gring = false;                            // SB200_VITERBI=v5 / v6 / v7: history ring in global memory (v5: two lanes per code block, v6: four, v7: one)
+    bool use_lane6 = false;                            // SB200_VITERBI=v8: viterbi_k7_lane.cuh — one lane per code block, six-column history blocks, 6-step loop body
     bool use_lane = false;                             // SB200_VITERBI=v7: one lane per code block, 32 code blocks per warp, no lane exchange at all
     DevBuf vring;
     bool use_pair = false;                             // SB200_VITERBI=v4: two lanes per code block, 16 code blocks per warp (A/B against four lanes)
@@ -250,7 +252,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6' || e[1] == '7'); h->use_lane = e && e[0] == 'v' && e[1] == '7'; }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6' || e[1] == '7'); h->use_lane = e && e[0] == 'v' && e[1] == '7'; h->use_lane6 = e && e[0] == 'v' && e[1] == '8'; if (h->use_lane6) h->use_gring = true; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
@@ -356,15 +358,16 @@ static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t
 // block, history ring in shared or in global memory).  vring_need() sizes the global ring for n code blocks first.
 static cudaError_t vring_need(sb200_handle* h, uint32_t n) {
     if (!h->use_gring) return cudaSuccess;
-    const size_t per = h->use_lane ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
-    return h->vring.need((n + per - 1) / per * SB_VR_NB * per * 64);
+    const size_t per = (h->use_lane || h->use_lane6) ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
+    return h->vring.need((n + per - 1) / per * (h->use_lane6 ? SB_VL_NB : SB_VR_NB) * per * 64);
 }
 template <int CR>
 static void launch_viterbi_re(sb200_handle* h, uint32_t n, cudaStream_t s, const uint8_t* soft, uint64_t soft_stride, const uint32_t* list, const uint32_t* cnt,
                               const FrameInfo* info, const VitJob& job, uint8_t* out, uint64_t out_stride, uint32_t raw_off, uint32_t* nraw) {
     const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
     uint4* const ring = (uint4*)h->vring.p;
-    if (h->use_lane)                 k_viterbi_re<CR, 0, true><<<(n + 31) / 32, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
+    if (h->use_lane6)                k_viterbi_lane<CR><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
+    else if (h->use_lane)            k_viterbi_re<CR, 0, true><<<(n + 31) / 32, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_gring && h->use_pair) k_viterbi_re<CR, 1, true><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_gring)           k_viterbi_re<CR, 2, true><<<g, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_pair)            k_viterbi_re<CR, 1><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw);

@@ -1,0 +1,243 @@
+// sora_b200 — batched K=7 (133,171) soft Viterbi, "lane" kernel for sm_100a: ONE LANE PER CODE BLOCK, six-column history blocks.
+//
+// Arithmetic contract: the same as viterbi_k7_re.cuh (bit-exact with kernel/bb/Brick11/src/viterbicore.h:269-556 driven like
+// kernel/bb/Brick11/src/viterbi.hpp:104-237); the add-compare-select is that file's vr_step — one fused VIADDMNMX.U16x2 and one
+// VIADD.16x2 per register and trellis step, the survivor history riding in the low byte of every 16-bit metric.
+//
+// What is different, and why (profiles/r2c_viterbi_v5_ncu.txt, r2c_viterbi_v7_ncu.txt):
+//   * A lane owns all 64 states of a code block (32 registers); a warp decodes 32 code blocks.  No lane ever needs another lane's
+//     metrics: no shuffle, no quad mask, no per-lane selector — every PRMT selector and pairing distance is a compile-time constant.
+//     The per-warp overhead of a step (branch-metric construction, fetch, loop) is spread over 32 code blocks instead of 8:
+//     0.58x the instructions of the four-lanes-per-block kernel for the same work (measured).
+//   * The 24-step unrolled stream of viterbi_k7_re.cuh (lcm of the 6-step trellis phase and its 8-column history block) does not
+//     survive this widening: 1 800 instructions of straight-line code per warp, every warp at another place in it — the measured
+//     kernels stall on instruction fetch (2.8 - 4.3 warps per issue slot waiting for instructions).  Here the history block is SIX
+//     columns, the trellis period itself: the loop body is one 6-step chunk (~8 KB of code for all warps of the SM), the history mark
+//     of a step is a constant of its phase, a block boundary always falls on phase 0, where slot address == state index, and the slot
+//     six columns back along a survivor is simply the bit-reversed history byte.
+//   * The survivor ring (50 entries x 64 bytes per code block = 100 KB per warp) cannot live in shared memory; it is a per-CTA slab of
+//     global memory, written with one fully coalesced 128-bit store per 16 states (512 contiguous bytes per warp and instruction)
+//     and read back by the traceback with ld.global.cg.  Every lane walks its own window — 32 walks per warp instruction, where the
+//     quad kernel has 8 — and packs the decoded bits on the way; there is no scratch row and no second pass.
+//     The ring is re-used in place, so L2 absorbs what fits; the rest is HBM traffic this kernel trades for instructions
+//     ("The Viterbi kernel").
+#pragma once
+#include "viterbi_k7_re.cuh"
+
+namespace sb {
+
+#define SB_VL_FR 32                        // code blocks per CTA (one warp), one lane each
+#define SB_VL_NB 50                        // ring entries of 6 columns: depth + lookahead + 7 <= 288 columns = 48 entries, + the running one + 1
+#define SB_VL_ENTRY (SB_VL_FR * 4)         // uint4 per ring entry of a CTA: [16-slot group][code block]
+
+// Windowed traceback from slot A0 at time t over la + nout columns (viterbi.hpp:205-237), by one lane for its own code block.
+// The newest block (kp = t mod 6 columns; 0 = a whole one) is in ring entry e.  Walking n columns back from a slot replaces its
+// top n address bits by the reversed history bits of those columns (column c was produced at phase (c - 1) mod 6, which replaces
+// address bit 5 - phase); the decoded bits are the history bits themselves, newest first.  The first la bits are only looked
+// through; after them every eight bits make one output byte, newest bit in bit 7, the LAST byte of the window first (op[first + nbytes - 1]).
+// A free function of plain values, kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the
+// step loop — and the decoder's registers must never have their address taken.
+__device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
+                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first) {
+    uint32_t A = A0, todo = la + nout, acc = 0, m = 0;
+    int nb = -(int)la;                                   // valid bits in acc (negative: still inside the look-ahead)
+    const uint32_t nbytes = nout >> 3;
+    uint32_t n = t % 6u; if (n == 0u) n = 6u;            // columns in the newest block
+    while (todo) {
+        const uint32_t h = (uint32_t)__ldcg(ring_b + e * (SB_VL_ENTRY * 16u) + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)) & 63u;
+        const uint32_t take = min(n, todo);              // < n only at the old end of the window: its newest `take` columns count
+        acc = (acc << take) | ((h & ((1u << n) - 1u)) >> (n - take)); nb += (int)take;
+        const uint32_t low = (1u << (6u - n)) - 1u;
+        A = (A & low) | ((__brev(h) >> 26) & ~low & 63u);
+        todo -= take; n = 6u; e = e ? e - 1u : SB_VL_NB - 1u;
+        if (nb >= 8) {
+            const uint32_t at = first + nbytes - 1u - m;
+            if (at < out_cap) op[at] = (uint8_t)(acc >> (nb - 8));
+            nb -= 8; m++;
+        }
+    }
+}
+
+template <int CODE_RATE>
+struct VlDecoder {
+    static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
+    static constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
+    static constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;                                // soft bytes per 6 steps
+    uint32_t R[32];        // slot address = register << 1 | half; state index of a slot at time t = rol6(address, t mod 6)
+    VrLane LC;             // selectors of vr_step: constants here (no lane part), kept in the struct the step function takes
+    uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves
+    uint32_t mk[5], mkH, mkL;   // history mark of phase T = 0x00010001 << T as registers (IMAD-side adds, see vr_step); phase 5 split by half
+    uint4* ring_q; const uint8_t* ring_b;
+    const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
+    uint32_t depth, look, end, ob, next_tb, nraw, wslot;
+    bool done;
+
+    __device__ __forceinline__ void fetch(const uint32_t pos, uint32_t (&a)[3]) const {
+        if (pos + CHUNK_BYTES > nsoft) { a[0] = a[1] = a[2] = 0; return; }
+        if constexpr (CODE_RATE == CR_34) { const uint2 v = __ldg((const uint2*)(sp + pos)); a[0] = v.x; a[1] = v.y; a[2] = 0; }
+        else if constexpr (CODE_RATE == CR_12) { a[0] = __ldg((const uint32_t*)(sp + pos)); a[1] = __ldg((const uint32_t*)(sp + pos + 4)); a[2] = __ldg((const uint32_t*)(sp + pos + 8)); }
+        else { uint32_t b[9];
+#pragma unroll
+               for (int i = 0; i < 9; i++) b[i] = __ldg(sp + pos + i);
+               a[0] = b[0] | (b[1] << 8) | (b[2] << 16); a[1] = b[3] | (b[4] << 8) | (b[5] << 16); a[2] = b[6] | (b[7] << 8) | (b[8] << 16); }
+    }
+    // the 64 history bytes of this code block (low byte of every half, slot-address order) into ring entry e
+    __device__ __forceinline__ void store_hist(const uint32_t e) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint4 w;
+            w.x = __byte_perm(R[8 * i + 0], R[8 * i + 1], 0x6420); w.y = __byte_perm(R[8 * i + 2], R[8 * i + 3], 0x6420);
+            w.z = __byte_perm(R[8 * i + 4], R[8 * i + 5], 0x6420); w.w = __byte_perm(R[8 * i + 6], R[8 * i + 7], 0x6420);
+            __stcg(ring_q + e * SB_VL_ENTRY + i * SB_VL_FR, w);
+        }
+    }
+    __device__ __forceinline__ void clear_hist() {
+#pragma unroll
+        for (int r = 0; r < 32; r++) R[r] &= 0xFE00FE00u;
+    }
+    __device__ __forceinline__ void next_slot() { wslot = wslot == SB_VL_NB - 1u ? 0u : wslot + 1u; }
+    // viterbi.hpp:177-180 -> viterbicore.h:445-465: subtract the smallest m7 from every metric
+    __device__ __forceinline__ void normalize() {
+        uint32_t m = R[0];
+#pragma unroll
+        for (int r = 1; r < 32; r++) m = __vminu2(m, R[r]);
+        m = min(m & 0xFFFFu, m >> 16) >> 9;
+        const uint32_t mv = m * 0x02000200u;
+#pragma unroll
+        for (int r = 0; r < 32; r++) R[r] -= mv;        // every half >= m << 9: no borrow between halves, histories untouched
+    }
+    // slot of the best state at time t (tm = t mod 6, tn = (t - 1) mod 6 = bit of the newest mark), viterbicore.h:468-520
+    __device__ __forceinline__ uint32_t best_slot(const uint32_t tm, const uint32_t tn) const { return vr_best_core<0>(R, 0u, tm, tn, 0u); }
+
+    // traceback trigger at time t (a puncture-group boundary), viterbi.hpp:182-203; tm = t mod 6
+    __device__ __forceinline__ void trigger(const uint32_t t, const uint32_t tm) {
+        if (t < next_tb) return;
+        uint32_t nout, la;
+        if (t >= end) { nout = end - ob - 6u; la = t - end; }
+        else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
+        if (nout) {
+            const uint32_t A0 = best_slot(tm, tm ? tm - 1u : 5u);
+            if (tm) store_hist(wslot);                  // mid-block: the partial histories of the running block (a block end has just stored its own)
+            vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw);
+            nraw += nout >> 3; ob += nout;
+        }
+        if (ob + 6u >= end && t >= end) done = true;
+        next_tb = min(end, ob + depth + look + 6u);
+        if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
+    }
+    template <int s> __device__ __forceinline__ void step(const uint32_t cb) {
+        const uint32_t KC = kc[vr_ksum<CODE_RATE, s>() == 28u ? 0 : 1];
+        if constexpr (s <= 4) vr_step<s, true, 0>(R, cb, LC, KC, mk[s], 0u, 0xFFFFFFFFu);
+        else vr_step<5, true, 0>(R, cb, LC, KC, mkH, mkL, 0xFFFFFFFFu);
+    }
+    // steps s .. 5 of the 6-step chunk that starts at time tb (a multiple of 6).  CHECK = false: no traceback trigger falls into the
+    // chunk for any lane of the warp (the hot loop); CHECK = true: every group boundary is checked, lanes that are not `live` only keep step.
+    // Normalisation (viterbi.hpp:177-180) comes when (t & 7) == 0 at a group boundary: t is even only after an odd s.
+    template <int s, bool CHECK> __device__ __forceinline__ void chunk(const uint32_t (&w)[3], const uint32_t tb, const bool live) {
+        if constexpr (s < 6) {
+            step<s>(vr_bm<CODE_RATE, s>(w));
+            const uint32_t t = tb + s + 1u;
+            if constexpr (s == 5) store_hist(wslot);
+            if constexpr ((s + 1) % GSTEPS == 0) {
+                if constexpr (s & 1) { if ((t & 7u) == 0u) normalize(); }
+                if constexpr (CHECK) { if (live && !done) trigger(t, (s + 1) % 6); }
+            }
+            if constexpr (s == 5) { clear_hist(); next_slot(); }
+            chunk<s + 1, CHECK>(w, tb, live);
+        }
+    }
+};
+
+// list / cnt: work list of this code rate (k_vit_lists) or null = frames 0 .. nframes-1 with the uniform parameters of `job`.
+// gring: SB_VL_NB * SB_VL_ENTRY uint4 per CTA.
+template <int CODE_RATE>
+__global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
+        const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
+        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring) {
+    using D = VlDecoder<CODE_RATE>;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
+    if (blockIdx.x * SB_VL_FR >= nvalid) return;        // whole CTA
+    const int lane = threadIdx.x & 31;
+    const uint32_t idx = blockIdx.x * SB_VL_FR + lane;
+    const bool valid = idx < nvalid;
+    const uint32_t f = !valid ? 0u : list ? __ldg(list + (size_t)CODE_RATE * nframes + idx) : idx;
+    uint32_t L = job.frame_len;
+    D d;
+    d.nsoft = job.nsoft;
+    if (valid && info) { const FrameInfo fi = info[f]; L = fi.length; d.nsoft = fi.soft_bytes; }
+    if (!valid) d.nsoft = 0;
+    d.depth = job.depth; d.look = job.lookahead;
+    d.sp = soft + (size_t)f * soft_stride;
+    d.op = out + (size_t)f * out_stride + raw_off;
+    d.out_cap = (uint32_t)(out_stride - raw_off < 0xFFFFFFFFull ? out_stride - raw_off : 0xFFFFFFFFull);
+#pragma unroll
+    for (int t = 0; t < 6; t++) {                        // no lane part in the slot address: the selectors are constants
+        const int K = vr_kcls(t);
+        d.LC.sel[t][0] = vq_sel(0, 0 ^ K); d.LC.sel[t][1] = vq_sel(1, 1 ^ K);
+    }
+    d.LC.bA[0] = d.LC.bA[1] = 0u; d.LC.bB[0] = d.LC.bB[1] = 0u;
+    {   // constants that must stay register operands (z is always 0, which the compiler cannot know): see vr_step
+        const uint32_t z = (uint32_t)(soft_stride >> 63);
+        d.kc[0] = 0x1C001C00u + z; d.kc[1] = 0x0E000E00u + z;
+#pragma unroll
+        for (int j = 0; j < 5; j++) d.mk[j] = (0x00010001u << j) + z;
+        d.mkH = 0x00200000u + z; d.mkL = 0x00000020u + z;
+    }
+    // initial metrics (viterbilut.h:22-32): state 0 -> 0x00, others 0x30; at t = 0 state == address; byte value v sits at v << 8
+#pragma unroll
+    for (int r = 0; r < 32; r++) d.R[r] = 0x30003000u;
+    d.R[0] = 0x30000000u;
+    d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
+    d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
+    uint4* const ring0 = gring + (size_t)blockIdx.x * (SB_VL_NB * SB_VL_ENTRY);
+    d.ring_q = ring0 + lane; d.ring_b = (const uint8_t*)(ring0 + lane);
+
+    // lockstep part: the 32 code blocks of the warp advance together, one 6-step chunk per iteration; the soft values of the next two
+    // chunks are always in registers
+    uint32_t tb = 0, pos = 0;                           // time and soft position at the start of the next chunk (uniform)
+    uint32_t w0[3], w1[3];
+    d.fetch(pos, w0); d.fetch(pos + D::CHUNK_BYTES, w1);
+    bool stale = false;                                 // out of input while others kept stepping (cannot happen with whole-symbol inputs)
+#pragma unroll 1
+    for (;;) {
+        const bool more = !d.done && pos + D::CHUNK_BYTES <= d.nsoft;
+        if (!__any_sync(FULL, more)) break;
+        if (!more && !d.done) stale = true;
+        uint32_t w2[3];
+        d.fetch(pos + 2u * D::CHUNK_BYTES, w2);
+        const bool quiet = d.done || (more && tb + 6u < d.next_tb);
+        if (__all_sync(FULL, quiet)) d.template chunk<0, false>(w0, tb, more);
+        else d.template chunk<0, true>(w0, tb, more);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { w0[i] = w1[i]; w1[i] = w2[i]; }
+        tb += 6u; pos += D::CHUNK_BYTES;
+    }
+    // tail: whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft): per lane, phases at run time
+    if (!d.done && !stale) {
+        uint32_t k = 0;                                 // steps into the chunk at tb
+        auto step_rt = [&](const uint32_t cb, const uint32_t KC) {
+            switch (k) { case 0: vr_step<0, false, 0>(d.R, cb, d.LC, KC, d.mk[0], 0u, FULL); break; case 1: vr_step<1, false, 0>(d.R, cb, d.LC, KC, d.mk[1], 0u, FULL); break;
+                         case 2: vr_step<2, false, 0>(d.R, cb, d.LC, KC, d.mk[2], 0u, FULL); break; case 3: vr_step<3, false, 0>(d.R, cb, d.LC, KC, d.mk[3], 0u, FULL); break;
+                         case 4: vr_step<4, false, 0>(d.R, cb, d.LC, KC, d.mk[4], 0u, FULL); break; default: vr_step<5, false, 0>(d.R, cb, d.LC, KC, d.mkH, d.mkL, FULL); }
+            k++;
+        };
+        while (!d.done && pos + D::GROUP <= d.nsoft) {
+            uint32_t g = __ldg(d.sp + pos) | ((uint32_t)__ldg(d.sp + pos + 1) << 8);
+            if (D::GROUP > 2) g |= (uint32_t)__ldg(d.sp + pos + 2) << 16;
+            if (D::GROUP > 3) g |= (uint32_t)__ldg(d.sp + pos + 3) << 24;
+            pos += D::GROUP;
+            step_rt(vq_bm_ab<0>(g), d.kc[0]);
+            if (D::GSTEPS >= 2) step_rt(vq_bm_a<2>(g), d.kc[1]);
+            if (D::GSTEPS >= 3) step_rt(vq_bm_b<3>(g), d.kc[1]);
+            const uint32_t t = tb + k;
+            if (k == 6u) d.store_hist(d.wslot);
+            if ((t & 7u) == 0u) d.normalize();
+            d.trigger(t, k == 6u ? 0u : k);
+            if (k == 6u) { d.clear_hist(); d.next_slot(); k = 0; tb += 6u; }
+        }
+    }
+    if (valid) nraw_out[f] = d.nraw;
+}
+
+} // namespace sb

@@ -1,0 +1,15 @@
+#!/bin/bash
+# GPU call 3: the lane kernel (SB200_VITERBI=v8): parity tests, bench A/B, full-size ncu capture.
+cd "$(dirname "$0")/.."; mkdir -p gpurun_out; T=r2d; V=${1:-v8}
+SB200_VITERBI=$V timeout 600 python -m pytest tests/test_gpu_rx11a.py tests/test_gpu_rx11n.py tests/test_gpu_11n_qam.py -x -q 2>&1 | tail -15 | tee gpurun_out/${T}_pytest_$V.txt
+SB200_VITERBI=$V python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>gpurun_out/${T}_bench_$V.err | tail -1 > gpurun_out/${T}_bench_$V.json
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_$V.json")); print("$V", round(d["value"]), "Msamples/s", d["kernel_ms"])
+except Exception as e: print("$V failed", e)
+PY
+tail -3 gpurun_out/${T}_bench_$V.err
+SB200_VITERBI=$V python bench_extra.py --config viterbi 2>/dev/null | tee gpurun_out/${T}_extra_viterbi_$V.jsonl | cut -c1-260
+SB200_VITERBI=$V timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_viterbi_lane -c 1 -f -o gpurun_out/${T}_viterbi_$V python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > /dev/null 2>&1
+ls -la gpurun_out | grep ${T}
