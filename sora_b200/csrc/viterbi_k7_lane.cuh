@@ -39,23 +39,29 @@ namespace sb {
 // step loop — and the decoder's registers must never have their address taken.
 __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
                                           const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first) {
-    uint32_t A = A0, todo = la + nout, acc = 0, m = 0;
+    constexpr uint32_t EB = SB_VL_ENTRY * 16u;          // bytes per ring entry of the CTA
+    uint32_t A = A0, todo = la + nout, acc = 0;
     int nb = -(int)la;                                   // valid bits in acc (negative: still inside the look-ahead)
-    const uint32_t nbytes = nout >> 3;
-    uint32_t n = t % 6u; if (n == 0u) n = 6u;            // columns in the newest block
-    while (todo) {
-        const uint32_t h = (uint32_t)__ldcg(ring_b + e * (SB_VL_ENTRY * 16u) + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)) & 63u;
-        const uint32_t take = min(n, todo);              // < n only at the old end of the window: its newest `take` columns count
-        acc = (acc << take) | ((h & ((1u << n) - 1u)) >> (n - take)); nb += (int)take;
-        const uint32_t low = (1u << (6u - n)) - 1u;
-        A = (A & low) | ((__brev(h) >> 26) & ~low & 63u);
-        todo -= take; n = 6u; e = e ? e - 1u : SB_VL_NB - 1u;
-        if (nb >= 8) {
-            const uint32_t at = first + nbytes - 1u - m;
-            if (at < out_cap) op[at] = (uint8_t)(acc >> (nb - 8));
-            nb -= 8; m++;
-        }
+    uint32_t at = first + (nout >> 3);                   // the next output byte goes to op[at - 1]
+    uint32_t eo = e * EB;                                // byte offset of the ring entry the walk stands in (32-bit arithmetic throughout)
+    auto emit = [&]() { if (nb >= 8) { --at; if (at < out_cap) op[at] = (uint8_t)(acc >> (nb - 8)); nb -= 8; } };   // at most one byte per block: nb < 8 before it
+    auto back = [&]() { eo = eo ? eo - EB : (SB_VL_NB - 1u) * EB; };
+    auto hist = [&]() { return (uint32_t)__ldcg(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u))) & 63u; };
+    const uint32_t kp = t % 6u;
+    if (kp) {                                            // running block: kp columns, history bits kp-1 .. 0 (todo >= 8 > kp always)
+        const uint32_t h = hist(), low = (1u << (6u - kp)) - 1u;
+        acc = h & ((1u << kp) - 1u); nb += (int)kp;
+        A = (A & low) | ((__brev(h) >> 26) & ~low);
+        todo -= kp; back(); emit();
     }
+#pragma unroll 1
+    while (todo >= 6u) {                                 // whole blocks: six decoded bits per look-up, the slot six columns back is the reversed byte
+        const uint32_t h = hist();
+        acc = (acc << 6) | h; nb += 6;
+        A = __brev(h) >> 26;
+        todo -= 6u; back(); emit();
+    }
+    if (todo) { acc = (acc << todo) | (hist() >> (6u - todo)); nb += (int)todo; emit(); }   // the old end of the window: only the newest columns of its block count
 }
 
 template <int CODE_RATE>
