@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--front-stage", type=int, default=-1, help="experiment: sample staging of the OFDM front end (0 direct, 1 register double buffer, 2 bulk async copy); -1 = library default")
     ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
     ap.add_argument("--e2e-sweep", action="store_true", help="experiment: host thread counts x chunk sizes of the e2e modes, printed to stderr")
+    ap.add_argument("--e2e-wc", action="store_true", help="experiment: also time the decimating modes with write-combined staging buffers (option host_stage_wc)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mgpu", action="store_true")
@@ -372,6 +373,10 @@ def main():
         if nth > 0:
             run_mode("host_decimate", nth, 0)
             run_mode("host_decimate_adaptive", nth, 1)
+        if nth > 0 and args.e2e_wc:                           # experiment: write-combined staging buffers
+            eng.set_option("host_stage_wc", 1)
+            run_mode("host_decimate_wc", nth, 0); run_mode("host_decimate_adaptive_wc", nth, 1)
+            eng.set_option("host_stage_wc", 0)
         if args.e2e_sweep:                                   # experiment: thread counts and chunk sizes of the adaptive mode, to stderr
             for ch in (2048, 4096):
                 eng.set_option("chunk_frames", ch)
