@@ -246,6 +246,7 @@ def main():
     ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
     ap.add_argument("--e2e-sweep", action="store_true", help="experiment: host thread counts x chunk sizes of the e2e modes, printed to stderr")
     ap.add_argument("--e2e-wc", action="store_true", help="experiment: also time the decimating modes with write-combined staging buffers (option host_stage_wc)")
+    ap.add_argument("--lane-min", type=int, default=-1, help="experiment: option viterbi_lane_min (smallest launch, in code blocks, the one-lane-per-code-block Viterbi takes); -1 = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mgpu", action="store_true")
@@ -280,6 +281,7 @@ def main():
     eng.set_option("slot_table_immutable", 1)             # the slot tables below are written once and never touched again
     if args.vq_pad_smem: eng.set_option("vq_pad_smem", args.vq_pad_smem)
     if args.front_stage >= 0: eng.set_option("front_stage", args.front_stage)
+    if args.lane_min >= 0: eng.set_option("viterbi_lane_min", args.lane_min)
     stream = torch.cuda.current_stream()
     # ---- HBM-resident input: U unique slots tiled to F (distinct addresses: 2.6 GB at F=65536 >> 126 MB L2) ----
     iq_unique_dev = torch.from_numpy(iq_u.reshape(U, -1)).to(dev)
@@ -318,6 +320,7 @@ def main():
     for _ in range(nk):
         step_dev(); ktimes += np.array(eng.last_kernel_times())
     ktimes /= nk
+    vit_kernel = eng.last_viterbi_kernel()                 # which Viterbi kernel the library chose for a launch of F code blocks
     eng.set_option("chunk_frames", args.chunk); eng.set_option("chunk_frames_device", args.chunk_device)
     t_wait = time.perf_counter()                           # a short run can end between two nvidia-smi lines: keep the same load on, untimed, until two have landed
     while clocks.p and clocks.seen() < 2 and time.perf_counter() - t_wait < 2.0:
@@ -446,7 +449,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        try: tj = json.load(open(tp)); traffic = tj.get("k_viterbi_re_dram_bytes_per_frame", 0) * F or None
+        try: tj = json.load(open(tp)); traffic = tj.get(vit_kernel + "_dram_bytes_per_frame", 0) * F or None
         except Exception: traffic = None
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -459,7 +462,7 @@ def main():
                                       + (f" ({oracle_gate.rerun} slots where the threaded oracle run disagreed were settled by a single-threaded oracle run)" if getattr(oracle_gate, "rerun", 0) else ""),
                        "numa": numa},
             "kernel_ms": {"carrier_sense": float(ktimes[0]), "ofdm_front_end": float(ktimes[1]), "viterbi_descramble_crc": vit_ms, "pack": float(ktimes[3])},
-            "roofline": {"bound": "hbm", "kernel": "k_viterbi_re<CR_34> (+ work lists, frame sink)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": f"{vit_kernel}<CR_34> (+ work lists, frame sink)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": how,
                          "note": "achieved = 4.154 B/sample x samples per launch / Viterbi kernel time; the chain is integer-ALU/issue bound, not HBM bound (DESIGN.md)"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e}

@@ -79,6 +79,9 @@ uint64_t sb200_launch_count(const sb200_handle* h);
 /* what the most recent sb200_rx11a_batch call with a HOST iq buffer really sent over the link: sample bytes copied host -> device, the number
  * of pipeline chunks and how many of them the host threads gathered first (option host_decimate); bench.py's e2e.h2d_bytes_per_step */
 int sb200_last_transfer(const sb200_handle* h, uint64_t* h2d_bytes, uint32_t* chunks, uint32_t* chunks_gathered);
+/* name of the Viterbi kernel the most recent launch used ("k_viterbi_lane": one lane per code block, large batches; "k_viterbi_re": four
+ * lanes per code block; option "viterbi_lane_min" = smallest launch, in code blocks, the first one takes) — bench.py's roofline.kernel */
+const char* sb200_last_viterbi_kernel(const sb200_handle* h);
 /* device time (ms) of the kernels of the most recent *_batch / viterbi call, measured with CUDA events on `stream` */
 float sb200_last_kernel_ms(sb200_handle* h);
 /* per-kernel device times (ms) of the most recent sb200_rx11a_batch: [0] carrier sense, [1] OFDM front end,

@@ -23,7 +23,7 @@ RESULT11N_DTYPE = np.dtype([("status", "<u4"), ("mcs", "<u4"), ("length", "<u4")
 
 EXPORTS = ["sb200_create", "sb200_destroy", "sb200_last_error", "sb200_launch_count", "sb200_last_kernel_ms",
            "sb200_last_kernel_times", "sb200_set_option", "sb200_rx11a_batch", "sb200_rx11a_batch_ex", "sb200_rx11a_stream", "sb200_rx11a_streams", "sb200_rx11b_batch", "sb200_viterbi_k7", "sb200_rx11a_taps",
-           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc", "sb200_fir_decimate2", "sb200_tx11b_fir37", "sb200_host_alloc", "sb200_host_free", "sb200_last_transfer"]
+           "sb200_rx11n_batch", "sb200_rx11n_taps", "sb200_rxblocks_unpack", "sb200_tx11a_batch", "sb200_tx11b_batch", "sb200_rx11b_streams", "sb200_rx11n_streams", "sb200_tx11n_batch", "sb200_rxblocks_desc", "sb200_fir_decimate2", "sb200_tx11b_fir37", "sb200_host_alloc", "sb200_host_free", "sb200_last_transfer", "sb200_last_viterbi_kernel"]
 
 class Sb200Error(RuntimeError):
     pass
@@ -41,6 +41,7 @@ def load_library():
         lib.sb200_launch_count.argtypes = [C.c_void_p]; lib.sb200_launch_count.restype = C.c_uint64
         lib.sb200_last_kernel_ms.argtypes = [C.c_void_p]; lib.sb200_last_kernel_ms.restype = C.c_float
         lib.sb200_last_kernel_times.argtypes = [C.c_void_p, C.c_void_p]; lib.sb200_last_kernel_times.restype = C.c_int
+        lib.sb200_last_viterbi_kernel.argtypes = [C.c_void_p]; lib.sb200_last_viterbi_kernel.restype = C.c_char_p
         lib.sb200_last_transfer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]; lib.sb200_last_transfer.restype = C.c_int
         lib.sb200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]; lib.sb200_set_option.restype = C.c_int
         lib.sb200_rx11a_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -106,6 +107,9 @@ class Engine:
         t = (C.c_float * 4)()
         self._check(self._lib.sb200_last_kernel_times(self._h, C.cast(t, C.c_void_p)), "sb200_last_kernel_times")
         return [float(x) for x in t]
+
+    def last_viterbi_kernel(self):
+        return self._lib.sb200_last_viterbi_kernel(self._h).decode()
 
     def last_transfer(self):
         """(sample bytes copied host -> device, pipeline chunks, chunks gathered on the host first) of the last host-buffer rx11a call."""

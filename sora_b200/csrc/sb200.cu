@@ -146,6 +146,8 @@ struct DecimPool {
     ~DecimPool() { shutdown(); }
 };
 
+#define SB200_LANE_MIN_DEFAULT 0xFFFFFFFFu            // until measured: off
+
 struct sb200_handle {
     int device = 0;
     uint32_t cca_thr = 1000 * 1000;
@@ -187,7 +189,10 @@ struct sb200_handle {
     DevBuf slotchk;
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
     bool use_gring = false;                            // SB200_VITERBI=v5 / v6 / v7: history ring in global memory (v5: two lanes per code block, v6: four, v7: one)
-    bool use_lane6 = false;                            // SB200_VITERBI=v8: viterbi_k7_lane.cuh — one lane per code block, six-column history blocks, 6-step loop body
+    // viterbi_k7_lane.cuh (one lane per code block, 32 per warp) needs a large batch to fill the machine: it decodes launches of at least
+    // lane_min code blocks, the four-lanes-per-code-block kernel the smaller ones.  Option "viterbi_lane_min"; SB200_VITERBI=v8 forces it (0), v3 forbids it.
+    uint32_t lane_min = SB200_LANE_MIN_DEFAULT;
+    const char* last_vit = "";                         // name of the Viterbi kernel the last launch used (sb200_last_viterbi_kernel)
     bool use_lane = false;                             // SB200_VITERBI=v7: one lane per code block, 32 code blocks per warp, no lane exchange at all
     DevBuf vring;
     bool use_pair = false;                             // SB200_VITERBI=v4: two lanes per code block, 16 code blocks per warp (A/B against four lanes)
@@ -253,7 +258,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6' || e[1] == '7'); h->use_lane = e && e[0] == 'v' && e[1] == '7'; h->use_lane6 = e && e[0] == 'v' && e[1] == '8'; if (h->use_lane6) h->use_gring = true; }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6' || e[1] == '7'); h->use_lane = e && e[0] == 'v' && e[1] == '7'; if (e && e[0] == 'v' && e[1] == '8') h->lane_min = 0; else if (e && e[0] == 'v') h->lane_min = 0xFFFFFFFFu; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     int rc = upload_tables(h);
     if (rc == SB200_OK && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) rc = SB200_E_CUDA;
@@ -286,6 +291,7 @@ extern "C" void sb200_destroy(sb200_handle* h) {
 }
 extern "C" const char* sb200_last_error(const sb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" uint64_t sb200_launch_count(const sb200_handle* h) { return h ? h->launches : 0; }
+extern "C" const char* sb200_last_viterbi_kernel(const sb200_handle* h) { return h ? h->last_vit : ""; }
 extern "C" int sb200_last_transfer(const sb200_handle* h, uint64_t* h2d_bytes, uint32_t* chunks, uint32_t* chunks_gathered) {
     if (!h) return SB200_E_INVALID;
     if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
@@ -358,16 +364,18 @@ static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t
 // One launch of the history-carrying Viterbi for code rate CR in the variant the handle selects (SB200_VITERBI: four or two lanes per code
 // block, history ring in shared or in global memory).  vring_need() sizes the global ring for n code blocks first.
 static cudaError_t vring_need(sb200_handle* h, uint32_t n) {
+    if (n >= h->lane_min) return h->vring.need((size_t)((n + SB_VL_FR - 1) / SB_VL_FR) * SB_VL_NB * SB_VL_ENTRY * 16);
     if (!h->use_gring) return cudaSuccess;
-    const size_t per = (h->use_lane || h->use_lane6) ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
-    return h->vring.need((n + per - 1) / per * (h->use_lane6 ? SB_VL_NB : SB_VR_NB) * per * 64);
+    const size_t per = h->use_lane ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
+    return h->vring.need((n + per - 1) / per * SB_VR_NB * per * 64);
 }
 template <int CR>
 static void launch_viterbi_re(sb200_handle* h, uint32_t n, cudaStream_t s, const uint8_t* soft, uint64_t soft_stride, const uint32_t* list, const uint32_t* cnt,
                               const FrameInfo* info, const VitJob& job, uint8_t* out, uint64_t out_stride, uint32_t raw_off, uint32_t* nraw) {
     const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
     uint4* const ring = (uint4*)h->vring.p;
-    if (h->use_lane6)                k_viterbi_lane<CR><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
+    h->last_vit = n >= h->lane_min ? "k_viterbi_lane" : "k_viterbi_re";
+    if (n >= h->lane_min)            k_viterbi_lane<CR><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_lane)            k_viterbi_re<CR, 0, true><<<(n + 31) / 32, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_gring && h->use_pair) k_viterbi_re<CR, 1, true><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_gring)           k_viterbi_re<CR, 2, true><<<g, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
@@ -1432,6 +1440,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "vq_pad_smem")) { h->vq_pad_smem = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "front_stage")) { if (value > 2) return h->fail(SB200_E_INVALID, "front_stage is 0, 1 or 2"); h->front_stage = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
+    if (!strcmp(name, "viterbi_lane_min")) { h->lane_min = value > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_stage_wc")) { h->hstage_wc = value != 0; return SB200_OK; }
     if (!strcmp(name, "host_decimate_mix")) { if (value > 2) return h->fail(SB200_E_INVALID, "host_decimate_mix: 0, 1 or 2"); h->host_mix = (uint32_t)value; h->gather_ms_per_sample = 0.0; return SB200_OK; }
     if (!strcmp(name, "slot_table_immutable")) { h->tab_immutable = value != 0; h->tab_off = nullptr; return SB200_OK; }

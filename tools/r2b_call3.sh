@@ -12,4 +12,10 @@ PY
 tail -3 gpurun_out/${T}_bench_$V.err
 SB200_VITERBI=$V python bench_extra.py --config viterbi 2>/dev/null | tee gpurun_out/${T}_extra_viterbi_$V.jsonl | cut -c1-260
 SB200_VITERBI=$V timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_viterbi_lane -c 1 -f -o gpurun_out/${T}_viterbi_$V python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > /dev/null 2>&1
+python tools/vit_crossover.py 2>&1 | tee gpurun_out/${T}_vit_crossover.jsonl
+SB200_TRACE=1 python bench.py --steps 5 --warmup 3 --no-cpu --e2e-wc 2>gpurun_out/${T}_bench_wc.err | tail -1 > gpurun_out/${T}_bench_wc.json
+python - <<PY
+import json
+d = json.load(open("gpurun_out/${T}_bench_wc.json")); print("value", round(d["value"]), "e2e", d["e2e"]["mode"], round(d["e2e"]["value"]), {k: (round(v["value"]), v.get("chunks_gathered_on_host")) for k, v in d["e2e"]["modes"].items()})
+PY
 ls -la gpurun_out | grep ${T}
