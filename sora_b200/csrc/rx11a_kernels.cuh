@@ -15,23 +15,9 @@
 // N_CBPS per symbol, contiguous per frame, ready for viterbi_k7_re.cuh.
 #pragma once
 #include "tables.cuh"
+#include "viterbi_k7_common.cuh"
 
 namespace sb {
-
-enum : uint32_t {
-    E_SUCCESS = 0, E_FRAME_OK = 1, E_FAILED = 0x8000FFFFu, E_PLCP_HEADER_FAIL = 0x80000005u,
-    E_CRC32_FAIL = 0x80000006u, E_CS_TIMEOUT = 0x80000007u, E_NO_FRAME = 0x8000F001u,
-};
-enum { CR_12 = 0, CR_23 = 1, CR_34 = 2 };
-
-struct FrameInfo {            // per-slot state handed from kernel to kernel (device memory)
-    uint32_t status;          // E_SUCCESS while decoding proceeds, else terminal code
-    uint32_t detect_vec;      // index of the first 20 Msps 4-sample vector routed to the demod branch
-    uint32_t rate_kbps, length, nsym_total, code_rate, ncbps;
-    uint32_t soft_bytes;      // deinterleaved soft values written for this frame
-    int32_t cfo_est; uint32_t peak_index;
-    int32_t dc_re, dc_im;     // CF_VecDC when the carrier sense ended (it persists across frames of one stream)
-};
 
 __device__ __forceinline__ int d_uatan2(const DevTables& T, int y, int x) {       // intalg.h:96-108
     unsigned ay = y > 0 ? (unsigned)y : 0u - (unsigned)y, ax = x > 0 ? (unsigned)x : 0u - (unsigned)x;

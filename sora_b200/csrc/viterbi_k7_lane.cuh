@@ -22,7 +22,7 @@
 //     The ring is re-used in place, so L2 absorbs what fits; the rest is HBM traffic this kernel trades for instructions
 //     ("The Viterbi kernel").
 #pragma once
-#include "viterbi_k7_re.cuh"
+#include "viterbi_k7_common.cuh"
 
 namespace sb {
 

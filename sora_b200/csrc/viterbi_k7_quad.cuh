@@ -27,20 +27,12 @@
 
 namespace sb {
 
-struct VitJob {               // uniform-parameter mode (standalone API); per-frame mode reads FrameInfo instead
-    uint32_t code_rate, frame_len, nsoft; uint32_t depth, lookahead; uint32_t raw; // raw=1: emit SERVICE+PSDU bytes undescrambled
-};
-
 
 #define SB_VQ_WARPS 1                      // warps per CTA
 #define SB_VQ_FR (8 * SB_VQ_WARPS)         // code blocks per CTA
 #define SB_VQ_RING_MAX 294                     // columns kept per code block: depth + lookahead + 7 (287 for 256/24) + up to 5 written before a
                                            // recorded traceback is served; multiple of 6
 
-__host__ __device__ constexpr int vq_rol6(int a, int t) { return ((a << t) | (a >> (6 - t))) & 63; }
-__host__ __device__ constexpr int vq_cls(int p) {            // (cA << 1) | cB of predecessor index p (bit 5 ignored)
-    return ((((p >> 1) ^ (p >> 2) ^ (p >> 4)) & 1) << 1) | ((p ^ (p >> 1) ^ (p >> 2)) & 1);
-}
 // static class of (reg r, half h) at phase T, lane part excluded (GF(2)-linear, so the lane part is XORed in later)
 // low four address bits of (register r, half h): reg bit 0 | half | reg bit 2 | reg bit 1 — the order in which the PRMT gather of the
 // survivor marks (vq_commit_marks) lays the 16 decisions of a lane down, so that ring bit index == address
@@ -48,8 +40,6 @@ __host__ __device__ constexpr int vq_cls(int p) {            // (cA << 1) | cB o
 template <int S> __host__ __device__ constexpr int vq_low4(int r, int h) { return S ? ((r & 1) << 3) | (h << 2) | (r >> 1) : (h << 3) | r; }
 template <int S> __host__ __device__ constexpr int vq_scls(int T, int r, int h) { return vq_cls(vq_rol6(vq_low4<S>(r, h), T) & 31); }
 __host__ __device__ constexpr int vq_lcls(int T, int q) { return vq_cls(vq_rol6(q << 4, T) & 31); }
-// PRMT selector building [0, byte i0, 0, byte i1] from (Cb, 0): the branch metric lands in the high byte of each half
-__host__ __device__ constexpr unsigned vq_sel(int i0, int i1) { return (unsigned)(4 | (i0 << 4) | (4 << 8) | (i1 << 12)); }
 
 struct VqLane {
     unsigned swz[6];       // per-phase byte swizzle applying this lane's class contribution
@@ -163,22 +153,6 @@ __device__ __forceinline__ uint32_t vq_commit_marks_b(const uint32_t (&R)[8]) {
 template <int T, int S>
 __device__ __forceinline__ void vq_step(uint32_t (&R)[8], uint32_t Cbase, const VqLane& L, unsigned qmask) {
     if (S) vq_step_b<T>(R, Cbase, L, qmask); else vq_step_a<T>(R, Cbase, L, qmask);
-}
-// branch-metric byte vectors (byte index = cA<<1 | cB) from soft values in bytes B0 (A) and B0+1 (B) of the packed word w
-__device__ __forceinline__ int vq_dp4a_us(uint32_t a, int b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-template <int B0> __device__ __forceinline__ uint32_t vq_bm_ab(uint32_t w) {
-    // x = tA + tB, y = tA - tB + 14;  bytes [x, y, 28 - y, 28 - x] = c00, c01, c10, c11
-    const int x = vq_dp4a_us(w, (int)(0x0202u << (8 * B0)), 0);
-    const int y = vq_dp4a_us(w, (int)(0xFE02u << (8 * B0)), 14);
-    return 0x1C1C0000u + (uint32_t)x * 0xFF000001u + (uint32_t)y * 0xFFFF0100u;
-}
-template <int B0> __device__ __forceinline__ uint32_t vq_bm_a(uint32_t w) {      // only A present: bytes [c0, c0, c1, c1]
-    const int s = vq_dp4a_us(w, (int)(0x01u << (8 * B0)), 0);
-    return 0x0E0E0000u + (uint32_t)s * (0x00000202u - 0x02020000u);
-}
-template <int B0> __device__ __forceinline__ uint32_t vq_bm_b(uint32_t w) {      // only B present: bytes [c0, c1, c0, c1]
-    const int s = vq_dp4a_us(w, (int)(0x01u << (8 * B0)), 0);
-    return 0x0E000E00u + (uint32_t)s * (0x00020002u - 0x02000200u);
 }
 
 template <int CODE_RATE>
