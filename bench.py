@@ -246,6 +246,7 @@ def main():
     ap.add_argument("--vq-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per Viterbi CTA (occupancy sweep)")
     ap.add_argument("--e2e-sweep", action="store_true", help="experiment: host thread counts x chunk sizes of the e2e modes, printed to stderr")
     ap.add_argument("--e2e-wc", action="store_true", help="experiment: also time the decimating modes with write-combined staging buffers (option host_stage_wc)")
+    ap.add_argument("--vl-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per lane-kernel CTA (occupancy sweep)")
     ap.add_argument("--lane-min", type=int, default=-1, help="experiment: option viterbi_lane_min (smallest launch, in code blocks, the one-lane-per-code-block Viterbi takes); -1 = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -282,6 +283,7 @@ def main():
     if args.vq_pad_smem: eng.set_option("vq_pad_smem", args.vq_pad_smem)
     if args.front_stage >= 0: eng.set_option("front_stage", args.front_stage)
     if args.lane_min >= 0: eng.set_option("viterbi_lane_min", args.lane_min)
+    if args.vl_pad_smem: eng.set_option("vl_pad_smem", args.vl_pad_smem)
     stream = torch.cuda.current_stream()
     # ---- HBM-resident input: U unique slots tiled to F (distinct addresses: 2.6 GB at F=65536 >> 126 MB L2) ----
     iq_unique_dev = torch.from_numpy(iq_u.reshape(U, -1)).to(dev)

@@ -12,6 +12,15 @@ PY
 tail -3 gpurun_out/${T}_bench_$V.err
 SB200_VITERBI=$V python bench_extra.py --config viterbi 2>/dev/null | tee gpurun_out/${T}_extra_viterbi_$V.jsonl | cut -c1-260
 SB200_VITERBI=$V timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_viterbi_lane -c 1 -f -o gpurun_out/${T}_viterbi_$V python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > /dev/null 2>&1
+for pad in 18000 28000 37000; do
+  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --lane-min 0 --vl-pad-smem $pad 2>/dev/null | tail -1 > gpurun_out/${T}_bench_pad$pad.json
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_pad$pad.json")); print("lane kernel, pad $pad", round(d["value"]), "Msamples/s", round(d["kernel_ms"]["viterbi_descramble_crc"], 3), "ms")
+except Exception as e: print("pad $pad failed", e)
+PY
+done
 python tools/vit_crossover.py 2>&1 | tee gpurun_out/${T}_vit_crossover.jsonl
 SB200_TRACE=1 python bench.py --steps 5 --warmup 3 --no-cpu --e2e-wc 2>gpurun_out/${T}_bench_wc.err | tail -1 > gpurun_out/${T}_bench_wc.json
 python - <<PY
