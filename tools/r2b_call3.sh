@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU call 3: the lane kernel (SB200_VITERBI=v8): parity tests, bench A/B, full-size ncu capture.
 cd "$(dirname "$0")/.."; mkdir -p gpurun_out; T=r2d; V=${1:-v8}
-SB200_VITERBI=$V timeout 600 python -m pytest tests/test_gpu_rx11a.py tests/test_gpu_rx11n.py tests/test_gpu_11n_qam.py -x -q 2>&1 | tail -15 | tee gpurun_out/${T}_pytest_$V.txt
+SB200_VITERBI=$V timeout 600 python -m pytest tests/test_gpu_rx11a.py tests/test_gpu_rx11n.py tests/test_gpu_11n_qam.py tests/test_gpu_zz_viterbi_variants.py -x -q 2>&1 | tail -15 | tee gpurun_out/${T}_pytest_$V.txt
 SB200_VITERBI=$V python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>gpurun_out/${T}_bench_$V.err | tail -1 > gpurun_out/${T}_bench_$V.json
 python - <<PY
 import json
