@@ -30,6 +30,32 @@ namespace sb {
 #define SB_VL_NB 50                        // ring entries of 6 columns: depth + lookahead + 7 <= 288 columns = 48 entries, + the running one + 1
 #define SB_VL_ENTRY (SB_VL_FR * 4)         // uint4 per ring entry of a CTA: [16-slot group][code block]
 
+// L2 eviction priority of the ring traffic and of the soft-value stream (kernel argument `flags`): the ring is re-used in place every 300
+// columns, the soft values are read once.  bit 0: ring stores and look-ups evict_last; bit 1: soft-value loads evict_first.
+#ifndef SB_HOST_EMU
+__device__ __forceinline__ uint64_t vl_policy(const int kind) {          // 0 normal, 1 evict_last, 2 evict_first
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void vl_st128(uint4* p, const uint4 w, const uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t vl_ld8(const uint8_t* p, const uint64_t pol) {
+    uint32_t v; asm volatile("ld.global.cg.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory"); return v;
+}
+__device__ __forceinline__ uint2 vl_ld64(const uint8_t* p, const uint64_t pol) {
+    uint2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol)); return v;
+}
+#else        // host emulation: plain memory
+inline uint64_t vl_policy(const int) { return 0; }
+inline void vl_st128(uint4* p, const uint4 w, const uint64_t) { *p = w; }
+inline uint32_t vl_ld8(const uint8_t* p, const uint64_t) { return *p; }
+inline uint2 vl_ld64(const uint8_t* p, const uint64_t) { return *(const uint2*)p; }
+#endif
+
 // Windowed traceback from slot A0 at time t over la + nout columns (viterbi.hpp:205-237), by one lane for its own code block.
 // The newest block (kp = t mod 6 columns; 0 = a whole one) is in ring entry e.  Walking n columns back from a slot replaces its
 // top n address bits by the reversed history bits of those columns (column c was produced at phase (c - 1) mod 6, which replaces
@@ -38,7 +64,7 @@ namespace sb {
 // A free function of plain values, kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the
 // step loop — and the decoder's registers must never have their address taken.
 __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
-                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first) {
+                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol) {
     constexpr uint32_t EB = SB_VL_ENTRY * 16u;          // bytes per ring entry of the CTA
     uint32_t A = A0, todo = la + nout, acc = 0;
     int nb = -(int)la;                                   // valid bits in acc (negative: still inside the look-ahead)
@@ -46,7 +72,7 @@ __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, ui
     uint32_t eo = e * EB;                                // byte offset of the ring entry the walk stands in (32-bit arithmetic throughout)
     auto emit = [&]() { if (nb >= 8) { --at; if (at < out_cap) op[at] = (uint8_t)(acc >> (nb - 8)); nb -= 8; } };   // at most one byte per block: nb < 8 before it
     auto back = [&]() { eo = eo ? eo - EB : (SB_VL_NB - 1u) * EB; };
-    auto hist = [&]() { return (uint32_t)__ldcg(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u))) & 63u; };
+    auto hist = [&]() { return vl_ld8(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)), pol) & 63u; };
     const uint32_t kp = t % 6u;
     if (kp) {                                            // running block: kp columns, history bits kp-1 .. 0 (todo >= 8 > kp always)
         const uint32_t h = hist(), low = (1u << (6u - kp)) - 1u;
@@ -73,14 +99,14 @@ struct VlDecoder {
     VrLane LC;             // selectors of vr_step: constants here (no lane part), kept in the struct the step function takes
     uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves
     uint32_t mk[5], mkH, mkL;   // history mark of phase T = 0x00010001 << T as registers (IMAD-side adds, see vr_step); phase 5 split by half
-    uint4* ring_q; const uint8_t* ring_b;
+    uint4* ring_q; const uint8_t* ring_b; uint64_t pol_ring, pol_soft;
     const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
     uint32_t depth, look, end, ob, next_tb, nraw, wslot;
     bool done;
 
     __device__ __forceinline__ void fetch(const uint32_t pos, uint32_t (&a)[3]) const {
         if (pos + CHUNK_BYTES > nsoft) { a[0] = a[1] = a[2] = 0; return; }
-        if constexpr (CODE_RATE == CR_34) { const uint2 v = __ldg((const uint2*)(sp + pos)); a[0] = v.x; a[1] = v.y; a[2] = 0; }
+        if constexpr (CODE_RATE == CR_34) { const uint2 v = vl_ld64(sp + pos, pol_soft); a[0] = v.x; a[1] = v.y; a[2] = 0; }
         else if constexpr (CODE_RATE == CR_12) { a[0] = __ldg((const uint32_t*)(sp + pos)); a[1] = __ldg((const uint32_t*)(sp + pos + 4)); a[2] = __ldg((const uint32_t*)(sp + pos + 8)); }
         else { uint32_t b[9];
 #pragma unroll
@@ -94,7 +120,7 @@ struct VlDecoder {
             uint4 w;
             w.x = __byte_perm(R[8 * i + 0], R[8 * i + 1], 0x6420); w.y = __byte_perm(R[8 * i + 2], R[8 * i + 3], 0x6420);
             w.z = __byte_perm(R[8 * i + 4], R[8 * i + 5], 0x6420); w.w = __byte_perm(R[8 * i + 6], R[8 * i + 7], 0x6420);
-            __stcg(ring_q + e * SB_VL_ENTRY + i * SB_VL_FR, w);
+            vl_st128(ring_q + e * SB_VL_ENTRY + i * SB_VL_FR, w, pol_ring);
         }
     }
     __device__ __forceinline__ void clear_hist() {
@@ -124,7 +150,7 @@ struct VlDecoder {
         if (nout) {
             const uint32_t A0 = best_slot(tm, tm ? tm - 1u : 5u);
             if (tm) store_hist(wslot);                  // mid-block: the partial histories of the running block (a block end has just stored its own)
-            vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw);
+            vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
             nraw += nout >> 3; ob += nout;
         }
         if (ob + 6u >= end && t >= end) done = true;
@@ -159,7 +185,7 @@ struct VlDecoder {
 template <int CODE_RATE>
 __global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
-        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring) {
+        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags) {
     using D = VlDecoder<CODE_RATE>;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
@@ -198,6 +224,7 @@ __global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
     uint4* const ring0 = gring + (size_t)blockIdx.x * (SB_VL_NB * SB_VL_ENTRY);
     d.ring_q = ring0 + lane; d.ring_b = (const uint8_t*)(ring0 + lane);
+    d.pol_ring = vl_policy((flags & 1u) ? 1 : 0); d.pol_soft = vl_policy((flags & 2u) ? 2 : 0);
 
     // lockstep part: the 32 code blocks of the warp advance together, one 6-step chunk per iteration; the soft values of the next two
     // chunks are always in registers

@@ -55,9 +55,9 @@ extern "C" int lane_emu_viterbi(const uint8_t* soft, uint64_t soft_stride, uint3
     std::vector<uint4> ring((size_t)ctas * SB_VL_NB * SB_VL_ENTRY);
     for (uint32_t c = 0; c < ctas; c++) for (unsigned lane = 0; lane < 32; lane++) {
         blockIdx.x = c; threadIdx.x = lane;
-        if (code_rate == sb::CR_12) sb::k_viterbi_lane<sb::CR_12>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data());
-        else if (code_rate == sb::CR_23) sb::k_viterbi_lane<sb::CR_23>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data());
-        else sb::k_viterbi_lane<sb::CR_34>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data());
+        if (code_rate == sb::CR_12) sb::k_viterbi_lane<sb::CR_12>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u);
+        else if (code_rate == sb::CR_23) sb::k_viterbi_lane<sb::CR_23>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u);
+        else sb::k_viterbi_lane<sb::CR_34>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u);
     }
     return 0;
 }

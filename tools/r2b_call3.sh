@@ -21,6 +21,15 @@ try:
 except Exception as e: print("pad $pad failed", e)
 PY
 done
+for hints in 1 2 3; do
+  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --lane-min 0 --vl-l2-hints $hints 2>/dev/null | tail -1 > gpurun_out/${T}_bench_hints$hints.json
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_hints$hints.json")); print("lane kernel, L2 hints $hints", round(d["value"]), "Msamples/s", round(d["kernel_ms"]["viterbi_descramble_crc"], 3), "ms")
+except Exception as e: print("hints $hints failed", e)
+PY
+done
 python tools/vit_crossover.py 2>&1 | tee gpurun_out/${T}_vit_crossover.jsonl
 SB200_TRACE=1 python bench.py --steps 5 --warmup 3 --no-cpu --e2e-wc 2>gpurun_out/${T}_bench_wc.err | tail -1 > gpurun_out/${T}_bench_wc.json
 python - <<PY
