@@ -28,6 +28,7 @@ namespace sb {
 
 #define SB_VL_FR 32                        // code blocks per CTA (one warp), one lane each
 #define SB_VL_NB 50                        // ring entries of 6 columns: depth + lookahead + 7 <= 288 columns = 48 entries, + the running one + 1
+#define SB_VL_NB8 38                       // ring entries of 8 columns: 288 / 8 = 36 entries, + the running one + 1
 #define SB_VL_ENTRY (SB_VL_FR * 4)         // uint4 per ring entry of a CTA: [16-slot group][code block]
 
 // L2 eviction priority of the ring traffic and of the soft-value stream (kernel argument `flags`): the ring is re-used in place every 300
@@ -90,8 +91,49 @@ __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, ui
     if (todo) { acc = (acc << todo) | (hist() >> (6u - todo)); nb += (int)todo; emit(); }   // the old end of the window: only the newest columns of its block count
 }
 
-template <int CODE_RATE>
+// The same walk over EIGHT-column history blocks (HB = 8: 64 B of ring per 8 columns instead of per 6, 38 entries instead of 50; the block
+// boundary then falls on any even phase).  Eight decoded bits per look-up; the slot eight columns back is the bit permutation of
+// viterbi_k7_re.cuh's vr_traceback: address bit (i - ph) mod 6 <- decision of column tt - i, the two oldest columns overriding i = 0, 1.
+__device__ __noinline__ void vl_traceback8(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
+                                           const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol) {
+    constexpr uint32_t EB = SB_VL_ENTRY * 16u;
+    uint32_t A = A0, todo = la + nout, acc = 0;
+    int nb = -(int)la;
+    uint32_t at = first + (nout >> 3);
+    uint32_t eo = e * EB;
+    auto emit = [&]() { if (nb >= 8) { --at; if (at < out_cap) op[at] = (uint8_t)(acc >> (nb - 8)); nb -= 8; } };   // nb < 8 before a block, < 16 after it
+    auto back = [&]() { eo = eo ? eo - EB : (SB_VL_NB8 - 1u) * EB; };
+    auto hist = [&]() { return vl_ld8(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)), pol); };
+    uint32_t tt = t;                                     // time of the newest column not yet walked
+    const uint32_t kp = t & 7u;
+    if (kp) {                                            // running block: kp columns, one slot-address bit changes per column
+        const uint32_t h = hist();
+        for (uint32_t c = 0; c < kp; c++) {              // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
+            const uint32_t b = 5u - (tt - c - 1u) % 6u, d = (h >> (kp - 1u - c)) & 1u;
+            A = (A & ~(1u << b)) | (d << b);
+        }
+        acc = h & ((1u << kp) - 1u); nb += (int)kp;
+        todo -= kp; tt -= kp; back(); emit();
+    }
+    uint32_t ph = tt % 6u;                               // phase of the block boundary the walk stands on
+#pragma unroll 1
+    while (todo >= 8u) {
+        const uint32_t h = hist();
+        acc = (acc << 8) | h; nb += 8;
+        const uint32_t r = __brev(h) >> 24;              // r bit i = h bit 7 - i = decision of column tt - i
+        const uint32_t G = (r & 0x3Cu) | (r >> 6);
+        A = ((G | (G << 6)) >> ph) & 63u;
+        todo -= 8u; ph = ph >= 2u ? ph - 2u : ph + 4u;   // (tt - 8) mod 6
+        back(); emit();
+    }
+    if (todo) { acc = (acc << todo) | (hist() >> (8u - todo)); nb += (int)todo; emit(); }
+}
+
+// HB: columns per history block, 6 (the trellis period: constants everywhere, the smallest loop body) or 8 (a quarter less ring traffic and
+// a smaller ring; the mark of a step and the block boundaries become run-time, warp-uniform values).
+template <int CODE_RATE, int HB>
 struct VlDecoder {
+    static constexpr uint32_t NB = HB == 6 ? SB_VL_NB : SB_VL_NB8;
     static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
     static constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
     static constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;                                // soft bytes per 6 steps
@@ -127,7 +169,7 @@ struct VlDecoder {
 #pragma unroll
         for (int r = 0; r < 32; r++) R[r] &= 0xFE00FE00u;
     }
-    __device__ __forceinline__ void next_slot() { wslot = wslot == SB_VL_NB - 1u ? 0u : wslot + 1u; }
+    __device__ __forceinline__ void next_slot() { wslot = wslot == NB - 1u ? 0u : wslot + 1u; }
     // viterbi.hpp:177-180 -> viterbicore.h:445-465: subtract the smallest m7 from every metric
     __device__ __forceinline__ void normalize() {
         uint32_t m = R[0];
@@ -148,18 +190,20 @@ struct VlDecoder {
         if (t >= end) { nout = end - ob - 6u; la = t - end; }
         else { nout = depth; la = look + (t - (ob + depth + look + 6u)) % 8u; }
         if (nout) {
-            const uint32_t A0 = best_slot(tm, tm ? tm - 1u : 5u);
-            if (tm) store_hist(wslot);                  // mid-block: the partial histories of the running block (a block end has just stored its own)
-            vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
+            const uint32_t A0 = best_slot(tm, HB == 6 ? (tm ? tm - 1u : 5u) : ((t - 1u) & 7u));
+            if (HB == 6 ? tm != 0u : (t & 7u) != 0u) store_hist(wslot);   // mid-block: the partial histories of the running block (a block end has just stored its own)
+            if constexpr (HB == 6) vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
+            else vl_traceback8(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
             nraw += nout >> 3; ob += nout;
         }
         if (ob + 6u >= end && t >= end) done = true;
         next_tb = min(end, ob + depth + look + 6u);
         if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
     }
-    template <int s> __device__ __forceinline__ void step(const uint32_t cb) {
+    template <int s> __device__ __forceinline__ void step(const uint32_t cb, const uint32_t tb) {
         const uint32_t KC = kc[vr_ksum<CODE_RATE, s>() == 28u ? 0 : 1];
-        if constexpr (s <= 4) vr_step<s, true, 0>(R, cb, LC, KC, mk[s], 0u, 0xFFFFFFFFu);
+        if constexpr (HB == 8) vr_step_rt<s, true, 0>(R, cb, LC, KC, 0x00010001u << ((tb + s) & 7u), 0xFFFFFFFFu);    // tb is warp-uniform: the mark lives in a uniform register
+        else if constexpr (s <= 4) vr_step<s, true, 0>(R, cb, LC, KC, mk[s], 0u, 0xFFFFFFFFu);
         else vr_step<5, true, 0>(R, cb, LC, KC, mkH, mkL, 0xFFFFFFFFu);
     }
     // steps s .. 5 of the 6-step chunk that starts at time tb (a multiple of 6).  CHECK = false: no traceback trigger falls into the
@@ -167,14 +211,16 @@ struct VlDecoder {
     // Normalisation (viterbi.hpp:177-180) comes when (t & 7) == 0 at a group boundary: t is even only after an odd s.
     template <int s, bool CHECK> __device__ __forceinline__ void chunk(const uint32_t (&w)[3], const uint32_t tb, const bool live) {
         if constexpr (s < 6) {
-            step<s>(vr_bm<CODE_RATE, s>(w));
+            step<s>(vr_bm<CODE_RATE, s>(w), tb);
             const uint32_t t = tb + s + 1u;
-            if constexpr (s == 5) store_hist(wslot);
+            // block boundary: HB = 6 after the last step of every chunk; HB = 8 when (t & 7) == 0, which only an odd s can reach (tb is even)
+            const bool blk = HB == 6 ? s == 5 : ((s & 1) && (t & 7u) == 0u);
+            if (blk) store_hist(wslot);
             if constexpr ((s + 1) % GSTEPS == 0) {
                 if constexpr (s & 1) { if ((t & 7u) == 0u) normalize(); }
                 if constexpr (CHECK) { if (live && !done) trigger(t, (s + 1) % 6); }
             }
-            if constexpr (s == 5) { clear_hist(); next_slot(); }
+            if (blk) { clear_hist(); next_slot(); }
             chunk<s + 1, CHECK>(w, tb, live);
         }
     }
@@ -182,11 +228,11 @@ struct VlDecoder {
 
 // list / cnt: work list of this code rate (k_vit_lists) or null = frames 0 .. nframes-1 with the uniform parameters of `job`.
 // gring: SB_VL_NB * SB_VL_ENTRY uint4 per CTA.
-template <int CODE_RATE>
+template <int CODE_RATE, int HB = 6>
 __global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags) {
-    using D = VlDecoder<CODE_RATE>;
+    using D = VlDecoder<CODE_RATE, HB>;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
     if (blockIdx.x * SB_VL_FR >= nvalid) return;        // whole CTA
@@ -222,7 +268,7 @@ __global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__
     d.R[0] = 0x30000000u;
     d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
-    uint4* const ring0 = gring + (size_t)blockIdx.x * (SB_VL_NB * SB_VL_ENTRY);
+    uint4* const ring0 = gring + (size_t)blockIdx.x * (D::NB * SB_VL_ENTRY);
     d.ring_q = ring0 + lane; d.ring_b = (const uint8_t*)(ring0 + lane);
     d.pol_ring = vl_policy((flags & 1u) ? 1 : 0); d.pol_soft = vl_policy((flags & 2u) ? 2 : 0);
 
@@ -250,24 +296,27 @@ __global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__
     if (!d.done && !stale) {
         uint32_t k = 0;                                 // steps into the chunk at tb
         auto step_rt = [&](const uint32_t cb, const uint32_t KC) {
-            switch (k) { case 0: vr_step<0, false, 0>(d.R, cb, d.LC, KC, d.mk[0], 0u, FULL); break; case 1: vr_step<1, false, 0>(d.R, cb, d.LC, KC, d.mk[1], 0u, FULL); break;
-                         case 2: vr_step<2, false, 0>(d.R, cb, d.LC, KC, d.mk[2], 0u, FULL); break; case 3: vr_step<3, false, 0>(d.R, cb, d.LC, KC, d.mk[3], 0u, FULL); break;
-                         case 4: vr_step<4, false, 0>(d.R, cb, d.LC, KC, d.mk[4], 0u, FULL); break; default: vr_step<5, false, 0>(d.R, cb, d.LC, KC, d.mkH, d.mkL, FULL); }
+            const uint32_t mark = 0x00010001u << (HB == 6 ? k : ((tb + k) & 7u));
+            switch (k) { case 0: vr_step_rt<0, false, 0>(d.R, cb, d.LC, KC, mark, FULL); break; case 1: vr_step_rt<1, false, 0>(d.R, cb, d.LC, KC, mark, FULL); break;
+                         case 2: vr_step_rt<2, false, 0>(d.R, cb, d.LC, KC, mark, FULL); break; case 3: vr_step_rt<3, false, 0>(d.R, cb, d.LC, KC, mark, FULL); break;
+                         case 4: vr_step_rt<4, false, 0>(d.R, cb, d.LC, KC, mark, FULL); break; default: vr_step_rt<5, false, 0>(d.R, cb, d.LC, KC, mark, FULL); }
             k++;
+            if ((tb + k) % (uint32_t)HB == 0u) d.store_hist(d.wslot);
         };
+        auto block_end = [&]() { if ((tb + k) % (uint32_t)HB == 0u) { d.clear_hist(); d.next_slot(); } };
         while (!d.done && pos + D::GROUP <= d.nsoft) {
             uint32_t g = __ldg(d.sp + pos) | ((uint32_t)__ldg(d.sp + pos + 1) << 8);
             if (D::GROUP > 2) g |= (uint32_t)__ldg(d.sp + pos + 2) << 16;
             if (D::GROUP > 3) g |= (uint32_t)__ldg(d.sp + pos + 3) << 24;
             pos += D::GROUP;
             step_rt(vq_bm_ab<0>(g), d.kc[0]);
-            if (D::GSTEPS >= 2) step_rt(vq_bm_a<2>(g), d.kc[1]);
-            if (D::GSTEPS >= 3) step_rt(vq_bm_b<3>(g), d.kc[1]);
+            if (D::GSTEPS >= 2) { block_end(); step_rt(vq_bm_a<2>(g), d.kc[1]); }
+            if (D::GSTEPS >= 3) { block_end(); step_rt(vq_bm_b<3>(g), d.kc[1]); }
             const uint32_t t = tb + k;
-            if (k == 6u) d.store_hist(d.wslot);
             if ((t & 7u) == 0u) d.normalize();
             d.trigger(t, k == 6u ? 0u : k);
-            if (k == 6u) { d.clear_hist(); d.next_slot(); k = 0; tb += 6u; }
+            block_end();
+            if (k == 6u) { k = 0; tb += 6u; }
         }
     }
     if (valid) nraw_out[f] = d.nraw;

@@ -19,9 +19,9 @@ def emu(tmp_path_factory):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DSB_HOST_EMU", "-Wno-unknown-pragmas", "-I", CSRC, "-o", so, SRC])
     lib = C.CDLL(so)
     lib.lane_emu_viterbi.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
-                                     C.c_void_p, C.c_void_p, C.c_void_p]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.lane_emu_viterbi.restype = C.c_int
-    def run(soft, cr, L, depth=256, look=24, lens=None, nsofts=None):
+    def run(soft, cr, L, depth=256, look=24, lens=None, nsofts=None, hb=6):
         soft = np.ascontiguousarray(soft, dtype=np.uint8); nb, ns = soft.shape
         stride = (ns + 15) // 16 * 16 + 16                              # the kernel fetches whole chunks: rows padded like the library's soft rows
         sp = np.zeros((nb, stride), np.uint8); sp[:, :ns] = soft
@@ -30,7 +30,7 @@ def emu(tmp_path_factory):
         lp = np.ascontiguousarray(lens, dtype=np.uint32) if lens is not None else None
         npp = np.ascontiguousarray(nsofts, dtype=np.uint32) if nsofts is not None else None
         rc = lib.lane_emu_viterbi(sp.ctypes.data, stride, ns, nb, cr, L, depth, look, out.ctypes.data, ostride, nraw.ctypes.data,
-                                  lp.ctypes.data if lp is not None else None, npp.ctypes.data if npp is not None else None)
+                                  lp.ctypes.data if lp is not None else None, npp.ctypes.data if npp is not None else None, hb)
         assert rc == 0
         return out[:, :L + 2], nraw
     return run
@@ -41,7 +41,10 @@ def _coded(rng, nblocks, L, rate):
     A, B = synth.conv_encode(bits)
     return bits, synth.puncture(A, B, rate)
 
-def test_code_words_clean_and_noisy(emu):
+HB = pytest.mark.parametrize("hb", (6, 8))             # columns per history block: both renderings of the kernel
+
+@HB
+def test_code_words_clean_and_noisy(emu, hb):
     rng = np.random.default_rng(3)
     for cr, rate in ((CR_12, (1, 2)), (CR_23, (2, 3)), (CR_34, (3, 4))):
         L = 700
@@ -49,13 +52,14 @@ def test_code_words_clean_and_noisy(emu):
         for flip in (0.0, 0.06, 0.5):
             soft = np.where(coded > 0, rng.integers(5, 8, coded.shape), rng.integers(0, 3, coded.shape)).astype(np.uint8)
             soft = np.where(rng.random(coded.shape) < flip, rng.integers(0, 8, coded.shape), soft).astype(np.uint8)
-            g, nraw = emu(soft, cr, L)
+            g, nraw = emu(soft, cr, L, hb=hb)
             assert (g == oracle_py.viterbi_blocks(soft, cr, L)).all(), (cr, flip)
             assert (nraw == L + 2).all()
             if flip == 0.0:
                 assert (np.unpackbits(g, axis=1, bitorder="little")[:, :8 * L + 16] == bits[:, :8 * L + 16]).all()
 
-def test_wrap_and_ragged_stress(emu):
+@HB
+def test_wrap_and_ragged_stress(emu, hb):
     """tests/test_gpu_rx11a.py::test_viterbi_wrap_and_ragged_stress on the emulated kernel."""
     rng = np.random.default_rng(11)
     for cr, per in ((CR_12, 2), (CR_23, 3), (CR_34, 4)):
@@ -67,11 +71,12 @@ def test_wrap_and_ragged_stress(emu):
             pats = [rng.integers(0, 8, (6, ns)), np.full((1, ns), 7), np.zeros((1, ns), int), np.tile([0, 7, 7, 0, 7], ns)[None, :ns], rng.integers(3, 5, (2, ns))]
             soft = np.concatenate(pats).astype(np.uint8)
             for depth, look in ((256, 24), (192, 36)):
-                g, _ = emu(soft, cr, L, depth, look)
+                g, _ = emu(soft, cr, L, depth, look, hb=hb)
                 o = oracle_py.viterbi_blocks(soft, cr, L, depth, look)
                 assert (g == o).all(), (cr, L, depth, np.argwhere(g != o)[:4])
 
-def test_blocks_of_different_lengths_side_by_side(emu):
+@HB
+def test_blocks_of_different_lengths_side_by_side(emu, hb):
     """The receive chains hand every code block its own length and soft-byte count (FrameInfo): 37 blocks — a full warp and part of the next —
     whose triggers and ends fall at different times; a short input (a truncated frame) among them decodes what it has, like the oracle."""
     rng = np.random.default_rng(5)
@@ -82,7 +87,7 @@ def test_blocks_of_different_lengths_side_by_side(emu):
         ns = int(nsofts.max())
         soft = rng.integers(0, 8, (37, ns)).astype(np.uint8)
         Lmax = int(lens.max())
-        g, nraw = emu(soft, cr, Lmax, lens=lens, nsofts=nsofts)
+        g, nraw = emu(soft, cr, Lmax, lens=lens, nsofts=nsofts, hb=hb)
         for i in range(37):
             L = int(lens[i]); n = int(nsofts[i])
             o = oracle_py.viterbi_blocks(soft[i:i + 1, :n], cr, L)[0]

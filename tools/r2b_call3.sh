@@ -21,6 +21,15 @@ try:
 except Exception as e: print("pad $pad failed", e)
 PY
 done
+for pad in 0 28000; do
+  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --lane-min 0 --vl-hist-block 8 --vl-pad-smem $pad 2>/dev/null | tail -1 > gpurun_out/${T}_bench_hb8_pad$pad.json
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_hb8_pad$pad.json")); print("lane kernel, 8-column blocks, pad $pad", round(d["value"]), "Msamples/s", round(d["kernel_ms"]["viterbi_descramble_crc"], 3), "ms")
+except Exception as e: print("hb8 pad $pad failed", e)
+PY
+done
 for hints in 1 2 3; do
   python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --lane-min 0 --vl-l2-hints $hints 2>/dev/null | tail -1 > gpurun_out/${T}_bench_hints$hints.json
   python - <<PY
