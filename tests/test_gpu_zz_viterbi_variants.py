@@ -28,20 +28,22 @@ def test_viterbi_variants_on_mixed_batches():
     soft = rng.integers(0, 8, (37, 4 * 451)).astype(np.uint8)           # 37 blocks: one full warp of the lane kernel plus five lanes of the next
     old = os.environ.get("SB200_VITERBI")
     try:
-        for v in ("v3", "v8", "v4", "v2"):
+        for v, hb in (("v3", 0), ("v8", 6), ("v8", 8), ("v4", 0), ("v2", 0)):   # v8: the lane kernel with 6- and with 8-column history blocks
             os.environ["SB200_VITERBI"] = v
             e = api.Engine(0)
+            if hb: e.set_option("vl_hist_block", hb)
             res, out = e.rx11a_batch(flat.reshape(-1, 2), off, ln)
+            assert e.last_viterbi_kernel() == ("k_viterbi_lane" if v == "v8" else "k_viterbi_re" if v != "v2" else e.last_viterbi_kernel())
             for k in ("status", "rate_kbps", "length", "crc32", "nsym"):
-                assert (res[k] == ores[k]).all(), (v, k, res[k], ores[k])
+                assert (res[k] == ores[k]).all(), (v, hb, k, res[k], ores[k])
             for i in range(len(res)):
                 if ores["status"][i] in (1, oracle_py.E_CRC32_FAIL):
-                    assert (out[i, :ores["length"][i]] == oout[i, :ores["length"][i]]).all(), (v, i)
+                    assert (out[i, :ores["length"][i]] == oout[i, :ores["length"][i]]).all(), (v, hb, i)
             for cr, per in ((api.CR_12, 2), (api.CR_23, 3), (api.CR_34, 4)):
                 ns = soft.shape[1] // per * per
                 for depth, look, L in ((256, 24, 100), (192, 36, 61)):
                     g = e.viterbi_k7(soft[:, :ns], cr, L, depth, look)
-                    assert (g == oracle_py.viterbi_blocks(soft[:, :ns], cr, L, depth, look)).all(), (v, cr, depth)
+                    assert (g == oracle_py.viterbi_blocks(soft[:, :ns], cr, L, depth, look)).all(), (v, hb, cr, depth)
             e.close()
     finally:
         if old is None: os.environ.pop("SB200_VITERBI", None)
