@@ -34,8 +34,10 @@ def test_viterbi_variants_on_mixed_batches():
             if hb: e.set_option("vl_hist_block", hb)
             res, out = e.rx11a_batch(flat.reshape(-1, 2), off, ln)
             assert e.last_viterbi_kernel() == ("k_viterbi_lane" if v == "v8" else "k_viterbi_re" if v != "v2" else e.last_viterbi_kernel())
-            for k in ("status", "rate_kbps", "length", "crc32", "nsym"):
-                assert (res[k] == ores[k]).all(), (v, hb, k, res[k], ores[k])
+            found = ores["status"] != oracle_py.E_NO_FRAME              # the fields of a slot without a frame are not defined
+            assert (res["status"] == ores["status"]).all(), (v, hb, res["status"], ores["status"])
+            for k in ("rate_kbps", "length", "crc32", "nsym"):
+                assert (res[k][found] == ores[k][found]).all(), (v, hb, k, res[k], ores[k])
             for i in range(len(res)):
                 if ores["status"][i] in (1, oracle_py.E_CRC32_FAIL):
                     assert (out[i, :ores["length"][i]] == oout[i, :ores["length"][i]]).all(), (v, hb, i)
