@@ -146,7 +146,7 @@ struct DecimPool {
     ~DecimPool() { shutdown(); }
 };
 
-#define SB200_LANE_MIN_DEFAULT 0xFFFFFFFFu            // until measured: off
+#define SB200_LANE_MIN_DEFAULT 32768u                 // measured (profiles/r2d_vit_crossover.jsonl): the lane kernel wins from 32 768 code blocks per launch on
 
 struct sb200_handle {
     int device = 0;
@@ -187,8 +187,8 @@ struct sb200_handle {
     DevBuf doff; std::vector<uint64_t> doffh;
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
-    uint32_t vl_hb = 6;                                // option vl_hist_block: columns per history block of the lane kernel (6 | 8)
-    uint32_t vl_flags = 0;                             // option vl_l2_hints: bit 0 ring traffic evict_last, bit 1 soft values evict_first (viterbi_k7_lane.cuh)
+    uint32_t vl_hb = 8;                                // option vl_hist_block: columns per history block of the lane kernel (6 | 8)
+    uint32_t vl_flags = 1;                             // option vl_l2_hints: bit 0 ring traffic evict_last, bit 1 soft values evict_first (viterbi_k7_lane.cuh)
     uint32_t vl_pad_smem = 0;                          // experiment knob: the same for the lane kernel (fewer resident warps = a smaller history-ring working set in L2)
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
     bool use_gring = false;                            // SB200_VITERBI=v5 / v6 / v7: history ring in global memory (v5: two lanes per code block, v6: four, v7: one)
@@ -1445,7 +1445,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "front_stage")) { if (value > 2) return h->fail(SB200_E_INVALID, "front_stage is 0, 1 or 2"); h->front_stage = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
     if (!strcmp(name, "vl_hist_block")) { if (value != 6 && value != 8) return h->fail(SB200_E_INVALID, "vl_hist_block: 6 or 8"); h->vl_hb = (uint32_t)value; return SB200_OK; }
-    if (!strcmp(name, "vl_l2_hints")) { h->vl_flags = (uint32_t)value & 3u; return SB200_OK; }
+    if (!strcmp(name, "vl_l2_hints")) { h->vl_flags = (uint32_t)value & 0xFF07u; return SB200_OK; }   // bit 0 ring evict_last, bit 1 soft evict_first, bit 2 no window prefetch, bits 8-15 prefetch skip
     if (!strcmp(name, "vl_pad_smem")) { if (value > 48 * 1024) return h->fail(SB200_E_INVALID, "vl_pad_smem <= 49152"); h->vl_pad_smem = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "viterbi_lane_min")) { h->lane_min = value > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_stage_wc")) { h->hstage_wc = value != 0; return SB200_OK; }

@@ -57,6 +57,30 @@ inline uint32_t vl_ld8(const uint8_t* p, const uint64_t) { return *p; }
 inline uint2 vl_ld64(const uint8_t* p, const uint64_t) { return *(const uint2*)p; }
 #endif
 
+// The rings of all resident warps together (150 - 230 MB) are larger than L2: by the time a window is walked, all but its newest entries
+// have been written back to HBM, and a walk that fetches them one dependent look-up at a time pays a DRAM round trip per look-up (the first
+// capture: 2.5 warps per issue slot waiting on them).  So the walk first asks for the whole older part of its window at once — this lane's
+// four 32-byte sectors of every entry from the SKIP-th newest on, `prefetch.global.L2`, nothing waits for them — and by the time it has
+// walked the newest entries (still in L2) the rest has arrived.  Costs 4 instructions per entry and lane and the sectors the walk would
+// not have touched (the walk reads one of this lane's four per entry).
+#define SB_VL_PF_SKIP 6
+template <uint32_t NBX>
+__device__ __forceinline__ void vl_prefetch_window(const uint8_t* ring_b, uint32_t eo, uint32_t nent, const uint32_t skip) {
+#ifndef SB_HOST_EMU
+    constexpr uint32_t EB = SB_VL_ENTRY * 16u;
+    for (uint32_t k = 0; k < nent; k++) {
+        if (k >= skip) {
+            const uint8_t* p = ring_b + eo;
+#pragma unroll
+            for (uint32_t g = 0; g < 4u; g++) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + g * (SB_VL_FR * 16u)));
+        }
+        eo = eo ? eo - EB : (NBX - 1u) * EB;
+    }
+#else
+    (void)ring_b; (void)eo; (void)nent; (void)skip;
+#endif
+}
+
 // Windowed traceback from slot A0 at time t over la + nout columns (viterbi.hpp:205-237), by one lane for its own code block.
 // The newest block (kp = t mod 6 columns; 0 = a whole one) is in ring entry e.  Walking n columns back from a slot replaces its
 // top n address bits by the reversed history bits of those columns (column c was produced at phase (c - 1) mod 6, which replaces
@@ -65,7 +89,7 @@ inline uint2 vl_ld64(const uint8_t* p, const uint64_t) { return *(const uint2*)p
 // A free function of plain values, kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the
 // step loop — and the decoder's registers must never have their address taken.
 __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
-                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol) {
+                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol, const uint32_t pf_skip) {
     constexpr uint32_t EB = SB_VL_ENTRY * 16u;          // bytes per ring entry of the CTA
     uint32_t A = A0, todo = la + nout, acc = 0;
     int nb = -(int)la;                                   // valid bits in acc (negative: still inside the look-ahead)
@@ -75,6 +99,7 @@ __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, ui
     auto back = [&]() { eo = eo ? eo - EB : (SB_VL_NB - 1u) * EB; };
     auto hist = [&]() { return vl_ld8(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)), pol) & 63u; };
     const uint32_t kp = t % 6u;
+    vl_prefetch_window<SB_VL_NB>(ring_b, eo, (todo + 5u) / 6u + 1u, pf_skip);
     if (kp) {                                            // running block: kp columns, history bits kp-1 .. 0 (todo >= 8 > kp always)
         const uint32_t h = hist(), low = (1u << (6u - kp)) - 1u;
         acc = h & ((1u << kp) - 1u); nb += (int)kp;
@@ -95,7 +120,7 @@ __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, ui
 // boundary then falls on any even phase).  Eight decoded bits per look-up; the slot eight columns back is the bit permutation of
 // viterbi_k7_re.cuh's vr_traceback: address bit (i - ph) mod 6 <- decision of column tt - i, the two oldest columns overriding i = 0, 1.
 __device__ __noinline__ void vl_traceback8(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
-                                           const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol) {
+                                           const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol, const uint32_t pf_skip) {
     constexpr uint32_t EB = SB_VL_ENTRY * 16u;
     uint32_t A = A0, todo = la + nout, acc = 0;
     int nb = -(int)la;
@@ -106,6 +131,7 @@ __device__ __noinline__ void vl_traceback8(const uint8_t* __restrict__ ring_b, u
     auto hist = [&]() { return vl_ld8(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)), pol); };
     uint32_t tt = t;                                     // time of the newest column not yet walked
     const uint32_t kp = t & 7u;
+    vl_prefetch_window<SB_VL_NB8>(ring_b, eo, (todo + 7u) / 8u + 1u, pf_skip);
     if (kp) {                                            // running block: kp columns, one slot-address bit changes per column
         const uint32_t h = hist();
         for (uint32_t c = 0; c < kp; c++) {              // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
@@ -141,7 +167,7 @@ struct VlDecoder {
     VrLane LC;             // selectors of vr_step: constants here (no lane part), kept in the struct the step function takes
     uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves
     uint32_t mk[5], mkH, mkL;   // history mark of phase T = 0x00010001 << T as registers (IMAD-side adds, see vr_step); phase 5 split by half
-    uint4* ring_q; const uint8_t* ring_b; uint64_t pol_ring, pol_soft;
+    uint4* ring_q; const uint8_t* ring_b; uint64_t pol_ring, pol_soft; uint32_t pf_skip;   // pf_skip: newest entries a walk does not prefetch (>= ring size: no prefetch)
     const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
     uint32_t depth, look, end, ob, next_tb, nraw, wslot;
     bool done;
@@ -192,8 +218,8 @@ struct VlDecoder {
         if (nout) {
             const uint32_t A0 = best_slot(tm, HB == 6 ? (tm ? tm - 1u : 5u) : ((t - 1u) & 7u));
             if (HB == 6 ? tm != 0u : (t & 7u) != 0u) store_hist(wslot);   // mid-block: the partial histories of the running block (a block end has just stored its own)
-            if constexpr (HB == 6) vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
-            else vl_traceback8(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
+            if constexpr (HB == 6) vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring, pf_skip);
+            else vl_traceback8(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring, pf_skip);
             nraw += nout >> 3; ob += nout;
         }
         if (ob + 6u >= end && t >= end) done = true;
@@ -271,6 +297,7 @@ __global__ void __launch_bounds__(32) k_viterbi_lane(const uint8_t* __restrict__
     uint4* const ring0 = gring + (size_t)blockIdx.x * (D::NB * SB_VL_ENTRY);
     d.ring_q = ring0 + lane; d.ring_b = (const uint8_t*)(ring0 + lane);
     d.pol_ring = vl_policy((flags & 1u) ? 1 : 0); d.pol_soft = vl_policy((flags & 2u) ? 2 : 0);
+    d.pf_skip = (flags & 4u) ? 0xFFFFu : ((flags >> 8) & 0xFFu) ? ((flags >> 8) & 0xFFu) : SB_VL_PF_SKIP;   // bit 2: no window prefetch; bits 8-15: skip count (0 = default)
 
     // lockstep part: the 32 code blocks of the warp advance together, one 6-step chunk per iteration; the soft values of the next two
     // chunks are always in registers
