@@ -259,7 +259,7 @@ struct VlDecoder {
 template <int CODE_RATE, int HB = 6>
 __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
-        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags) {
+        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags, uint32_t nsm) {
     using D = VlDecoder<CODE_RATE, HB>;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
@@ -301,6 +301,15 @@ __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restri
     d.pol_ring = vl_policy((flags & 1u) ? 1 : 0); d.pol_soft = vl_policy((flags & 2u) ? 2 : 0);
     d.pf_skip = (flags & 4u) ? 0xFFFFu : ((flags >> 8) & 0xFFu) ? ((flags >> 8) & 0xFFu) : SB_VL_PF_SKIP;   // bit 2: no window prefetch; bits 8-15: skip count (0 = default)
 
+    // Frames of one length, CTAs launched together: every resident warp would reach its traceback triggers at the same moment, and while a
+    // walk waits for its look-ups (~1 400 cycles each, 30 % of all stall samples in the first captures) the other warps of the scheduler
+    // would be waiting too.  The warps of a scheduler are started a quarter of a window period apart instead (flags bit 3 turns it off):
+    // launch slot j of this SM (blockIdx / SM count) sleeps 0 .. 3 quarters of depth * 250 ns — 250 ns is a trellis step at four warps per scheduler.
+    if (!(flags & 8u)) {
+        const uint32_t j = (blockIdx.x / max(nsm, 1u)) & 15u;
+        const uint32_t ns = (((j >> 2) + (j & 3u)) & 3u) * d.depth * 62u;   // distinct for the four warps of a scheduler whether slots map to schedulers as j % 4 or as j / 4
+        if (ns) __nanosleep(ns);
+    }
     // lockstep part: the 32 code blocks of the warp advance together, one 6-step chunk per iteration; the soft values of the next two
     // chunks are always in registers
     uint32_t tb = 0, pos = 0;                           // time and soft position at the start of the next chunk (uniform)
