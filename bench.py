@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--e2e-sweep", action="store_true", help="experiment: host thread counts x chunk sizes of the e2e modes, printed to stderr")
     ap.add_argument("--e2e-wc", action="store_true", help="experiment: also time the decimating modes with write-combined staging buffers (option host_stage_wc)")
     ap.add_argument("--vl-pad-smem", type=int, default=0, help="experiment: extra dynamic shared memory per lane-kernel CTA (occupancy sweep)")
+    ap.add_argument("--vl-defer", type=int, default=-1, help="experiment: 1 = the lane kernel's traceback spread over the step loop (one look-up per chunk), 0 = at the trigger; -1 = library default")
     ap.add_argument("--vl-hist-block", type=int, default=0, help="experiment: columns per history block of the lane kernel (6 | 8); 0 = library default")
     ap.add_argument("--vl-l2-hints", type=int, default=-1, help="experiment: L2 eviction hints of the lane kernel (bit 0 ring evict_last, bit 1 soft values evict_first); -1 = library default")
     ap.add_argument("--lane-min", type=int, default=-1, help="experiment: option viterbi_lane_min (smallest launch, in code blocks, the one-lane-per-code-block Viterbi takes); -1 = library default")
@@ -287,6 +288,7 @@ def main():
     if args.lane_min >= 0: eng.set_option("viterbi_lane_min", args.lane_min)
     if args.vl_pad_smem: eng.set_option("vl_pad_smem", args.vl_pad_smem)
     if args.vl_hist_block: eng.set_option("vl_hist_block", args.vl_hist_block)
+    if args.vl_defer >= 0: eng.set_option("vl_defer_walk", args.vl_defer)
     if args.vl_l2_hints >= 0: eng.set_option("vl_l2_hints", args.vl_l2_hints)
     stream = torch.cuda.current_stream()
     # ---- HBM-resident input: U unique slots tiled to F (distinct addresses: 2.6 GB at F=65536 >> 126 MB L2) ----

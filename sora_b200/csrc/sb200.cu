@@ -188,6 +188,7 @@ struct sb200_handle {
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
     uint32_t nsm = 148;                                // multiprocessors of the device (cudaDevAttrMultiProcessorCount)
+    bool vl_defer = false;                             // option vl_defer_walk: the traceback spread over the step loop, one look-up per chunk (8-column blocks only)
     uint32_t vl_hb = 8;                                // option vl_hist_block: columns per history block of the lane kernel (6 | 8)
     uint32_t vl_flags = 5;                             // option vl_l2_hints: bit 0 ring traffic evict_last, bit 1 soft values evict_first (viterbi_k7_lane.cuh)
     uint32_t vl_pad_smem = 0;                          // experiment knob: the same for the lane kernel (fewer resident warps = a smaller history-ring working set in L2)
@@ -369,7 +370,7 @@ static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t
 // One launch of the history-carrying Viterbi for code rate CR in the variant the handle selects (SB200_VITERBI: four or two lanes per code
 // block, history ring in shared or in global memory).  vring_need() sizes the global ring for n code blocks first.
 static cudaError_t vring_need(sb200_handle* h, uint32_t n) {
-    if (n >= h->lane_min) return h->vring.need((size_t)((n + SB_VL_FR - 1) / SB_VL_FR) * SB_VL_NB * SB_VL_ENTRY * 16);
+    if (n >= h->lane_min) return h->vring.need((size_t)((n + SB_VL_FR - 1) / SB_VL_FR) * SB_VL_NB8D * SB_VL_ENTRY * 16);   // the largest ring of the lane kernel's renderings
     if (!h->use_gring) return cudaSuccess;
     const size_t per = h->use_lane ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
     return h->vring.need((n + per - 1) / per * SB_VR_NB * per * 64);
@@ -380,7 +381,8 @@ static void launch_viterbi_re(sb200_handle* h, uint32_t n, cudaStream_t s, const
     const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
     uint4* const ring = (uint4*)h->vring.p;
     h->last_vit = n >= h->lane_min ? "k_viterbi_lane" : "k_viterbi_re";
-    if (n >= h->lane_min && h->vl_hb == 8) k_viterbi_lane<CR, 8><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
+    if (n >= h->lane_min && h->vl_hb == 8 && h->vl_defer) k_viterbi_lane<CR, 8, true><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
+    else if (n >= h->lane_min && h->vl_hb == 8) k_viterbi_lane<CR, 8><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
     else if (n >= h->lane_min)       k_viterbi_lane<CR, 6><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
     else if (h->use_lane)            k_viterbi_re<CR, 0, true><<<(n + 31) / 32, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_gring && h->use_pair) k_viterbi_re<CR, 1, true><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
@@ -1446,6 +1448,7 @@ extern "C" int sb200_set_option(sb200_handle* h, const char* name, uint64_t valu
     if (!strcmp(name, "vq_pad_smem")) { h->vq_pad_smem = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "front_stage")) { if (value > 2) return h->fail(SB200_E_INVALID, "front_stage is 0, 1 or 2"); h->front_stage = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "host_decimate")) { h->host_decimate = (uint32_t)(value > 256 ? 256 : value); return SB200_OK; }
+    if (!strcmp(name, "vl_defer_walk")) { h->vl_defer = value != 0; return SB200_OK; }
     if (!strcmp(name, "vl_hist_block")) { if (value != 6 && value != 8) return h->fail(SB200_E_INVALID, "vl_hist_block: 6 or 8"); h->vl_hb = (uint32_t)value; return SB200_OK; }
     if (!strcmp(name, "vl_l2_hints")) { h->vl_flags = (uint32_t)value & 0xFF0Fu; return SB200_OK; }   // bit 0 ring evict_last, bit 1 soft evict_first, bit 2 no window prefetch, bit 3 no start stagger, bits 8-15 prefetch skip
     if (!strcmp(name, "vl_pad_smem")) { if (value > 48 * 1024) return h->fail(SB200_E_INVALID, "vl_pad_smem <= 49152"); h->vl_pad_smem = (uint32_t)value; return SB200_OK; }

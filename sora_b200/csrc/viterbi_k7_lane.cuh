@@ -29,6 +29,8 @@ namespace sb {
 #define SB_VL_FR 32                        // code blocks per CTA (one warp), one lane each
 #define SB_VL_NB 50                        // ring entries of 6 columns: depth + lookahead + 7 <= 288 columns = 48 entries, + the running one + 1
 #define SB_VL_NB8 38                       // ring entries of 8 columns: 288 / 8 = 36 entries, + the running one + 1
+#define SB_VL_NB8D 67                      // the same when the walk is deferred (one look-up per 6-step chunk): entry e - k is read 6 k steps after the
+                                           // trigger, by when the writer is 0.75 k entries further: 1.75 x 37 entries, + 2
 #define SB_VL_ENTRY (SB_VL_FR * 4)         // uint4 per ring entry of a CTA: [16-slot group][code block]
 
 // L2 eviction priority of the ring traffic and of the soft-value stream (kernel argument `flags`): the ring is re-used in place every 300
@@ -157,9 +159,18 @@ __device__ __noinline__ void vl_traceback8(const uint8_t* __restrict__ ring_b, u
 
 // HB: columns per history block, 6 (the trellis period: constants everywhere, the smallest loop body) or 8 (a quarter less ring traffic and
 // a smaller ring; the mark of a step and the block boundaries become run-time, warp-uniform values).
-template <int CODE_RATE, int HB>
+// DEFER (HB = 8 only): the walk does not happen at the trigger.  Every look-up of a walk is a dependent L2 / HBM round trip of ~1 400 cycles,
+// 34 of them per window, and ncu's source view puts 30 % of all stall samples on the one instruction that consumes the loaded byte; other warps
+// do not cover that (starting them apart changes nothing, a walk prefetching its window neither — measured).  So the trigger only records where
+// the walk starts and issues its first load; after that the step loop performs ONE look-up per 6-step chunk — consume the byte loaded a chunk
+// ago, move to the slot eight columns back, issue the next load — and the forward pass never waits: a window's walk is finished 37 chunks =
+// 222 steps after its trigger, before the next trigger (256 steps).  The ring keeps 29 more entries for the walk to still find its oldest ones.
+template <int CODE_RATE, int HB, bool DEFER = false>
 struct VlDecoder {
-    static constexpr uint32_t NB = HB == 6 ? SB_VL_NB : SB_VL_NB8;
+    static_assert(!DEFER || HB == 8, "the deferred walk is written for 8-column history blocks");
+    static constexpr uint32_t NB = HB == 6 ? SB_VL_NB : DEFER ? SB_VL_NB8D : SB_VL_NB8;
+    uint32_t wk_todo, wk_A, wk_eo, wk_acc, wk_at, wk_ph, wk_h; int wk_nb;      // deferred walk: columns left (0 = none in flight), slot, ring entry
+                                                                               // offset, bit accumulator, next output byte, phase, the byte in flight, valid bits
     static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
     static constexpr uint32_t GSTEPS = CODE_RATE == CR_12 ? 1u : CODE_RATE == CR_34 ? 3u : 2u;  // trellis steps per group
     static constexpr uint32_t CHUNK_BYTES = 6u / GSTEPS * GROUP;                                // soft bytes per 6 steps
@@ -219,6 +230,7 @@ struct VlDecoder {
             const uint32_t A0 = best_slot(tm, HB == 6 ? (tm ? tm - 1u : 5u) : ((t - 1u) & 7u));
             if (HB == 6 ? tm != 0u : (t & 7u) != 0u) store_hist(wslot);   // mid-block: the partial histories of the running block (a block end has just stored its own)
             if constexpr (HB == 6) vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring, pf_skip);
+            else if constexpr (DEFER) walk_start(A0, t, la, nout);
             else vl_traceback8(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring, pf_skip);
             nraw += nout >> 3; ob += nout;
         }
@@ -226,6 +238,46 @@ struct VlDecoder {
         next_tb = min(end, ob + depth + look + 6u);
         if (next_tb <= t) next_tb = t + 1u;              // a frame shorter than the prefix: re-evaluate at every group
     }
+    // ---- deferred walk (DEFER): vl_traceback8 cut into its look-ups ----
+    __device__ __forceinline__ uint32_t walk_load() const {
+        return vl_ld8(ring_b + (wk_eo + (wk_A >> 4) * (SB_VL_FR * 16u) + (wk_A & 15u)), pol_ring);
+    }
+    __device__ __forceinline__ void walk_back() { wk_eo = wk_eo ? wk_eo - SB_VL_ENTRY * 16u : (NB - 1u) * (SB_VL_ENTRY * 16u); }
+    __device__ __forceinline__ void walk_emit() { if (wk_nb >= 8) { --wk_at; if (wk_at < out_cap) op[wk_at] = (uint8_t)(wk_acc >> (wk_nb - 8)); wk_nb -= 8; } }
+    // one look-up: consume the byte in flight, step eight columns back (or finish with the newest columns of the window's oldest block), load the next
+    __device__ __forceinline__ void walk_tick() {
+        if (wk_todo == 0u) return;
+        const uint32_t h = wk_h;
+        if (wk_todo >= 8u) {
+            wk_acc = (wk_acc << 8) | h; wk_nb += 8;
+            const uint32_t r = __brev(h) >> 24;                          // r bit i = h bit 7 - i = decision of column tt - i
+            const uint32_t G = (r & 0x3Cu) | (r >> 6);
+            wk_A = ((G | (G << 6)) >> wk_ph) & 63u;
+            wk_todo -= 8u; wk_ph = wk_ph >= 2u ? wk_ph - 2u : wk_ph + 4u;
+            walk_back(); walk_emit();
+            if (wk_todo) wk_h = walk_load();
+        } else { wk_acc = (wk_acc << wk_todo) | (h >> (8u - wk_todo)); wk_nb += (int)wk_todo; wk_todo = 0u; walk_emit(); }
+    }
+    __device__ __forceinline__ void walk_drain() { while (wk_todo) walk_tick(); }
+    // at a trigger: finish a walk that is still in flight (windows shorter than a walk: standalone calls with a small depth), take the running
+    // block at once (its entry was stored a moment ago), and leave the first whole-block load in flight
+    __device__ __forceinline__ void walk_start(const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
+        walk_drain();
+        wk_A = A0; wk_todo = la + nout; wk_acc = 0u; wk_nb = -(int)la; wk_at = nraw + (nout >> 3); wk_eo = wslot * (SB_VL_ENTRY * 16u);
+        uint32_t tt = t; const uint32_t kp = t & 7u;
+        if (kp) {
+            const uint32_t h = walk_load();
+            for (uint32_t c = 0; c < kp; c++) {                          // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
+                const uint32_t b = 5u - (tt - c - 1u) % 6u, d = (h >> (kp - 1u - c)) & 1u;
+                wk_A = (wk_A & ~(1u << b)) | (d << b);
+            }
+            wk_acc = h & ((1u << kp) - 1u); wk_nb += (int)kp;
+            wk_todo -= kp; tt -= kp; walk_back(); walk_emit();
+        }
+        wk_ph = tt % 6u;
+        if (wk_todo) wk_h = walk_load();
+    }
+
     template <int s> __device__ __forceinline__ void step(const uint32_t cb, const uint32_t tb) {
         const uint32_t KC = kc[vr_ksum<CODE_RATE, s>() == 28u ? 0 : 1];
         if constexpr (HB == 8) vr_step_rt<s, true, 0>(R, cb, LC, KC, 0x00010001u << ((tb + s) & 7u), 0xFFFFFFFFu);    // tb is warp-uniform: the mark lives in a uniform register
@@ -256,11 +308,11 @@ struct VlDecoder {
 // 16 resident one-warp CTAs per SM = 128 registers per thread, the out-of-line traceback included (without the bound the callee's own
 // registers are added on top and the SM holds 12 warps: measured 4.8 ms instead of 4.2).
 // gring: SB_VL_NB * SB_VL_ENTRY uint4 per CTA.
-template <int CODE_RATE, int HB = 6>
+template <int CODE_RATE, int HB = 6, bool DEFER = false>
 __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
         uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags, uint32_t nsm) {
-    using D = VlDecoder<CODE_RATE, HB>;
+    using D = VlDecoder<CODE_RATE, HB, DEFER>;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
     if (blockIdx.x * SB_VL_FR >= nvalid) return;        // whole CTA
@@ -294,7 +346,7 @@ __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restri
 #pragma unroll
     for (int r = 0; r < 32; r++) d.R[r] = 0x30003000u;
     d.R[0] = 0x30000000u;
-    d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
+    d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid; d.wk_todo = 0u;
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
     uint4* const ring0 = gring + (size_t)blockIdx.x * (D::NB * SB_VL_ENTRY);
     d.ring_q = ring0 + lane; d.ring_b = (const uint8_t*)(ring0 + lane);
@@ -323,6 +375,7 @@ __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restri
         if (!more && !d.done) stale = true;
         uint32_t w2[3];
         d.fetch(pos + 2u * D::CHUNK_BYTES, w2);
+        if constexpr (DEFER) d.walk_tick();                 // one look-up of the window in flight (its load was issued a chunk ago)
         const bool quiet = d.done || (more && tb + 6u < d.next_tb);
         if (__all_sync(FULL, quiet)) d.template chunk<0, false>(w0, tb, more);
         else d.template chunk<0, true>(w0, tb, more);
@@ -357,6 +410,7 @@ __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restri
             if (k == 6u) { k = 0; tb += 6u; }
         }
     }
+    if constexpr (DEFER) d.walk_drain();                    // the last window's walk
     if (valid) nraw_out[f] = d.nraw;
 }
 

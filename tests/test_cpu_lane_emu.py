@@ -41,7 +41,7 @@ def _coded(rng, nblocks, L, rate):
     A, B = synth.conv_encode(bits)
     return bits, synth.puncture(A, B, rate)
 
-HB = pytest.mark.parametrize("hb", (6, 8))             # columns per history block: both renderings of the kernel
+HB = pytest.mark.parametrize("hb", (6, 8, 9))          # columns per history block: 6, 8, and 9 = 8 with the walk spread over the step loop
 
 @HB
 def test_code_words_clean_and_noisy(emu, hb):

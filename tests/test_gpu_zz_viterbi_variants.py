@@ -28,10 +28,10 @@ def test_viterbi_variants_on_mixed_batches():
     soft = rng.integers(0, 8, (37, 4 * 451)).astype(np.uint8)           # 37 blocks: one full warp of the lane kernel plus five lanes of the next
     old = os.environ.get("SB200_VITERBI")
     try:
-        for v, hb in (("v3", 0), ("v8", 6), ("v8", 8), ("v4", 0), ("v2", 0)):   # v8: the lane kernel with 6- and with 8-column history blocks
+        for v, hb in (("v3", 0), ("v8", 6), ("v8", 8), ("v8", 9), ("v4", 0), ("v2", 0)):   # v8: the lane kernel with 6- / 8-column history blocks, 9 = 8 with the deferred walk
             os.environ["SB200_VITERBI"] = v
             e = api.Engine(0)
-            if hb: e.set_option("vl_hist_block", hb)
+            if hb: e.set_option("vl_hist_block", min(hb, 8)); e.set_option("vl_defer_walk", 1 if hb == 9 else 0)
             res, out = e.rx11a_batch(flat.reshape(-1, 2), off, ln)
             assert e.last_viterbi_kernel() == ("k_viterbi_lane" if v == "v8" else "k_viterbi_re" if v != "v2" else e.last_viterbi_kernel())
             found = ores["status"] != oracle_py.E_NO_FRAME              # the fields of a slot without a frame are not defined
