@@ -188,7 +188,7 @@ struct sb200_handle {
     bool tab_immutable = false;                        // option slot_table_immutable: device-resident slot tables may be cached by address
     DevBuf slotchk;
     uint32_t nsm = 148;                                // multiprocessors of the device (cudaDevAttrMultiProcessorCount)
-    bool vl_defer = false;                             // option vl_defer_walk: the traceback spread over the step loop, one look-up per chunk (8-column blocks only)
+    bool vl_defer = true;                              // option vl_defer_walk: the traceback spread over the step loop, one look-up per chunk (8-column blocks only)
     uint32_t vl_hb = 8;                                // option vl_hist_block: columns per history block of the lane kernel (6 | 8)
     uint32_t vl_flags = 5;                             // option vl_l2_hints: bit 0 ring traffic evict_last, bit 1 soft values evict_first (viterbi_k7_lane.cuh)
     uint32_t vl_pad_smem = 0;                          // experiment knob: the same for the lane kernel (fewer resident warps = a smaller history-ring working set in L2)
