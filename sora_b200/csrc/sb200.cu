@@ -146,7 +146,7 @@ struct DecimPool {
     ~DecimPool() { shutdown(); }
 };
 
-#define SB200_LANE_MIN_DEFAULT 32768u                 // measured (profiles/r2d_vit_crossover.jsonl): the lane kernel wins from 32 768 code blocks per launch on
+#define SB200_LANE_MIN_DEFAULT 16384u                 // measured (profiles/r2j_vit_crossover.jsonl): the lane kernel wins from 16 384 code blocks per launch on (0.85x at 16 384, 0.70x at 65 536)
 
 struct sb200_handle {
     int device = 0;

@@ -365,34 +365,25 @@ __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restri
     // lockstep part: the 32 code blocks of the warp advance together, one 6-step chunk per iteration; the soft values of the next two
     // chunks are always in registers
     uint32_t tb = 0, pos = 0;                           // time and soft position at the start of the next chunk (uniform)
-    // Soft values: w0 is the chunk being decoded, w1 the next one, and the loads of the two after that are in flight in la / lb, filled and
-    // drained in turn.  A register a load is still writing is not touched — not even by a move — until two chunks later (the first
-    // captures had 7 % of their stall samples on the move that rotated a just-loaded chunk forward): uniform branches on the iteration
-    // parity pick the register instead of a select, which would wait for both.
-    uint32_t w0[3], w1[3], la[3], lb[3];
-    d.fetch(pos, w0); d.fetch(pos + D::CHUNK_BYTES, w1); d.fetch(pos + 2u * D::CHUNK_BYTES, la);
-    bool odd = false;
+    // Soft values: w0 is the chunk being decoded, w1 the next one, w2 is loaded at the top of the iteration.  (Keeping a load in flight for
+    // two chunks in alternating registers, so that not even the rotating move touches it early, was measured: the move's stall samples went
+    // away and the kernel got 3 % slower — it is bound by the ALU pipe, and the parity branches cost more than the wait they removed.)
+    uint32_t w0[3], w1[3];
+    d.fetch(pos, w0); d.fetch(pos + D::CHUNK_BYTES, w1);
     bool stale = false;                                 // out of input while others kept stepping (cannot happen with whole-symbol inputs)
 #pragma unroll 1
     for (;;) {
         const bool more = !d.done && pos + D::CHUNK_BYTES <= d.nsoft;
         if (!__any_sync(FULL, more)) break;
         if (!more && !d.done) stale = true;
-        if (odd) d.fetch(pos + 3u * D::CHUNK_BYTES, la); else d.fetch(pos + 3u * D::CHUNK_BYTES, lb);
+        uint32_t w2[3];
+        d.fetch(pos + 2u * D::CHUNK_BYTES, w2);
         if constexpr (DEFER) d.walk_tick();                 // one look-up of the window in flight (its load was issued a chunk ago)
         const bool quiet = d.done || (more && tb + 6u < d.next_tb);
         if (__all_sync(FULL, quiet)) d.template chunk<0, false>(w0, tb, more);
         else d.template chunk<0, true>(w0, tb, more);
 #pragma unroll
-        for (int i = 0; i < 3; i++) w0[i] = w1[i];
-        if (odd) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) w1[i] = lb[i];      // loaded in the previous iteration
-        } else {
-#pragma unroll
-            for (int i = 0; i < 3; i++) w1[i] = la[i];
-        }
-        odd = !odd;
+        for (int i = 0; i < 3; i++) { w0[i] = w1[i]; w1[i] = w2[i]; }
         tb += 6u; pos += D::CHUNK_BYTES;
     }
     // tail: whole puncture groups that do not fill a 6-step chunk (standalone API with arbitrary nsoft): per lane, phases at run time
