@@ -193,12 +193,10 @@ struct sb200_handle {
     uint32_t vl_flags = 5;                             // option vl_l2_hints: bit 0 ring traffic evict_last, bit 1 soft values evict_first (viterbi_k7_lane.cuh)
     uint32_t vl_pad_smem = 0;                          // experiment knob: the same for the lane kernel (fewer resident warps = a smaller history-ring working set in L2)
     uint32_t vq_pad_smem = 0;                          // experiment knob: extra dynamic shared memory per Viterbi CTA (lowers occupancy)
-    bool use_gring = false;                            // SB200_VITERBI=v5 / v6 / v7: history ring in global memory (v5: two lanes per code block, v6: four, v7: one)
     // viterbi_k7_lane.cuh (one lane per code block, 32 per warp) needs a large batch to fill the machine: it decodes launches of at least
     // lane_min code blocks, the four-lanes-per-code-block kernel the smaller ones.  Option "viterbi_lane_min"; SB200_VITERBI=v8 forces it (0), v3 forbids it.
     uint32_t lane_min = SB200_LANE_MIN_DEFAULT;
     const char* last_vit = "";                         // name of the Viterbi kernel the last launch used (sb200_last_viterbi_kernel)
-    bool use_lane = false;                             // SB200_VITERBI=v7: one lane per code block, 32 code blocks per warp, no lane exchange at all
     DevBuf vring;
     bool use_pair = false;                             // SB200_VITERBI=v4: two lanes per code block, 16 code blocks per warp (A/B against four lanes)
     bool use_v2 = false;                               // SB200_VITERBI=v2 selects the per-step-mark quad kernel (A/B against the history-carrying one)
@@ -263,7 +261,7 @@ extern "C" int sb200_create(int device, const sb200_cfg* cfg, sb200_handle** out
     if (!h) return SB200_E_NOMEM;
     h->device = device;
     if (cfg && cfg->cca_pwr_threshold) h->cca_thr = cfg->cca_pwr_threshold;
-    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && (e[1] == '4' || e[1] == '5'); h->use_gring = e && e[0] == 'v' && (e[1] == '5' || e[1] == '6' || e[1] == '7'); h->use_lane = e && e[0] == 'v' && e[1] == '7'; if (e && e[0] == 'v' && e[1] == '8') h->lane_min = 0; else if (e && e[0] == 'v') h->lane_min = 0xFFFFFFFFu; }
+    { const char* e = getenv("SB200_VITERBI"); h->use_v2 = e && e[0] == 'v' && e[1] == '2'; h->use_pair = e && e[0] == 'v' && e[1] == '4'; if (e && e[0] == 'v' && e[1] == '8') h->lane_min = 0; else if (e && e[0] == 'v') h->lane_min = 0xFFFFFFFFu; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return SB200_E_CUDA; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->nsm = (uint32_t)v; }
     int rc = upload_tables(h);
@@ -367,26 +365,22 @@ static int slot_table(sb200_handle* h, const uint64_t* frame_off, const uint32_t
     return SB200_OK;
 }
 
-// One launch of the history-carrying Viterbi for code rate CR in the variant the handle selects (SB200_VITERBI: four or two lanes per code
-// block, history ring in shared or in global memory).  vring_need() sizes the global ring for n code blocks first.
+// One launch of the Viterbi for code rate CR: the lane kernel (viterbi_k7_lane.cuh) for launches of at least lane_min code blocks, in the
+// rendering the options select (8-column history blocks with the deferred walk unless told otherwise); below that the four-lanes-per-code-
+// block kernel (SB200_VITERBI=v4: two lanes, for A/B).  vring_need() sizes the lane kernel's history rings for n code blocks first.
 static cudaError_t vring_need(sb200_handle* h, uint32_t n) {
     if (n >= h->lane_min) return h->vring.need((size_t)((n + SB_VL_FR - 1) / SB_VL_FR) * SB_VL_NB8D * SB_VL_ENTRY * 16);   // the largest ring of the lane kernel's renderings
-    if (!h->use_gring) return cudaSuccess;
-    const size_t per = h->use_lane ? 32 : h->use_pair ? 16 : SB_VR_FR;      // code blocks per one-warp CTA
-    return h->vring.need((n + per - 1) / per * SB_VR_NB * per * 64);
+    return cudaSuccess;                                // the four- / two-lane kernels keep their ring in shared memory
 }
 template <int CR>
 static void launch_viterbi_re(sb200_handle* h, uint32_t n, cudaStream_t s, const uint8_t* soft, uint64_t soft_stride, const uint32_t* list, const uint32_t* cnt,
                               const FrameInfo* info, const VitJob& job, uint8_t* out, uint64_t out_stride, uint32_t raw_off, uint32_t* nraw) {
     const unsigned g = (n + SB_VR_FR - 1) / SB_VR_FR, gp = (n + 15) / 16;
-    uint4* const ring = (uint4*)h->vring.p;
+    uint4* const ring = (uint4*)h->vring.p;             // the lane kernel's history rings
     h->last_vit = n >= h->lane_min ? "k_viterbi_lane" : "k_viterbi_re";
     if (n >= h->lane_min && h->vl_hb == 8 && h->vl_defer) k_viterbi_lane<CR, 8, true><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
     else if (n >= h->lane_min && h->vl_hb == 8) k_viterbi_lane<CR, 8><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
     else if (n >= h->lane_min)       k_viterbi_lane<CR, 6><<<(n + SB_VL_FR - 1) / SB_VL_FR, 32, h->vl_pad_smem, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring, h->vl_flags, h->nsm);
-    else if (h->use_lane)            k_viterbi_re<CR, 0, true><<<(n + 31) / 32, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
-    else if (h->use_gring && h->use_pair) k_viterbi_re<CR, 1, true><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
-    else if (h->use_gring)           k_viterbi_re<CR, 2, true><<<g, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw, ring);
     else if (h->use_pair)            k_viterbi_re<CR, 1><<<gp, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw);
     else                             k_viterbi_re<CR, 2><<<g, 32, 0, s>>>(soft, soft_stride, n, list, cnt, info, job, out, out_stride, raw_off, nraw);
 }

@@ -42,16 +42,13 @@ namespace sb {
 // aligned; absent when kp = 0), then one byte per block, bit 7 = the newest column of the block.  vr_emit turns the row into output bytes.
 // Kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the step loop.
 #define SB_VR_HB 52                                          // >= (7 + 31 + 256 + 6) / 8 + 2; 13 words: rows of neighbouring lanes fall into different banks
-// SPLIT (one lane per code block): an entry is laid out [16-slot group][code block][16 bytes] so that a warp's 128-bit store is 512
-// contiguous bytes; otherwise [code block][64 bytes].  ring_b points at this code block's first 16 bytes of entry 0; EB = bytes per entry.
-template <int FR, bool SPLIT> __device__ __forceinline__ uint32_t vr_slot_off(const uint32_t A) { return SPLIT ? (A >> 4) * (FR * 16u) + (A & 15u) : A; }
-template <int FR, bool GR, bool SPLIT = false>
+template <int FR>
 __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ hb, uint32_t e, const uint32_t A0, const uint32_t t, uint32_t todo) {
     uint32_t A = A0, j = 0;
     uint32_t tt = t;                                         // time of the newest column not yet walked
     const uint32_t kp = t & 7u;
     if (kp) {                                                // running block: kp decisions in bits 0..kp-1, one slot-address bit changes per column
-        const uint32_t h = GR ? (uint32_t)__ldcg(ring_b + e * (FR * 64) + vr_slot_off<FR, SPLIT>(A)) : (uint32_t)ring_b[e * (FR * 64) + vr_slot_off<FR, SPLIT>(A)];
+        const uint32_t h = (uint32_t)ring_b[e * (FR * 64) + A];
         const uint32_t take = min(kp, todo);
         for (uint32_t c = 0; c < take; c++) {                // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
             const uint32_t b = 5u - (tt - c - 1u) % 6u, d = (h >> (kp - 1u - c)) & 1u;
@@ -63,7 +60,7 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
     uint32_t ph = tt % 6u;                                   // phase of the block boundary the walk stands on
     const uint8_t* rp = ring_b + e * (FR * 64);
     while (todo >= 8u) {
-        const uint32_t h = GR ? (uint32_t)__ldcg(rp + vr_slot_off<FR, SPLIT>(A)) : (uint32_t)rp[vr_slot_off<FR, SPLIT>(A)];
+        const uint32_t h = (uint32_t)rp[A];
         hb[j++] = (uint8_t)h;
         const uint32_t r = __brev(h) >> 24;                  // r bit i = h bit 7 - i = decision of column tt - i
         const uint32_t G = (r & 0x3Cu) | (r >> 6);           // slot-address bit (i - ph) mod 6 <- column tt - i, the two oldest overriding i = 0, 1
@@ -71,7 +68,7 @@ __device__ __noinline__ void vr_traceback(const uint8_t* __restrict__ ring_b, ui
         todo -= 8u; ph = ph >= 2u ? ph - 2u : ph + 4u;       // (tt - 8) mod 6
         rp = rp == ring_b ? ring_b + (SB_VR_NB - 1u) * (FR * 64) : rp - FR * 64;
     }
-    if (todo) hb[j++] = GR ? __ldcg(rp + vr_slot_off<FR, SPLIT>(A)) : rp[vr_slot_off<FR, SPLIT>(A)];         // oldest block of the window: only its newest `todo` columns count
+    if (todo) hb[j++] = rp[A];         // oldest block of the window: only its newest `todo` columns count
     hb[j] = 0; hb[j + 1] = 0;
 }
 // The nout / 8 decoded bytes of a window from the scratch row: bit k of the walk (k = 0 the newest column) sits at row bit (8 - kp) % 8 + k,
@@ -98,12 +95,8 @@ __device__ __noinline__ uint32_t vr_best_slot16(uint32_t r0, uint32_t r1, uint32
     return vr_best_core<1>(R, q, tm, tn, QM);
 }
 
-// one lane per code block: the 32 registers cannot travel as arguments; the scan is part of the (rare) trigger path
-__device__ __forceinline__ uint32_t vr_best_slot32(const uint32_t (&R)[32], const uint32_t tm, const uint32_t tn) { return vr_best_core<0>(R, 0u, tm, tn, 0u); }
 
-// GR: the history ring lives in global memory (L2-resident: every CTA re-uses its own 38 x FR x 64 bytes) instead of shared memory, so that
-// shared memory no longer caps the number of resident warps; the traceback then reads it with ld.global.cg after a __syncwarp.
-template <int CODE_RATE, int LB, bool GR = false>
+template <int CODE_RATE, int LB>
 struct VrDecoder {
     static constexpr int NR = 8 << (2 - LB), NL = 1 << LB, FR = 32 >> LB;                        // registers per lane, lanes per code block, code blocks per warp
     static constexpr uint32_t GROUP = CODE_RATE == CR_12 ? 2u : CODE_RATE == CR_34 ? 4u : 3u;   // soft bytes per puncture group
@@ -136,8 +129,7 @@ struct VrDecoder {
             uint4 w;
             w.x = __byte_perm(R[8 * i + 0], R[8 * i + 1], 0x6420); w.y = __byte_perm(R[8 * i + 2], R[8 * i + 3], 0x6420);
             w.z = __byte_perm(R[8 * i + 4], R[8 * i + 5], 0x6420); w.w = __byte_perm(R[8 * i + 6], R[8 * i + 7], 0x6420);
-            const uint32_t at = e * (FR * 4) + (LB == 0 ? i * FR : i);      // LB = 0: [group i][code block] (vr_slot_off)
-            if constexpr (GR) __stcg(ring_q + at, w); else ring_q[at] = w;
+            ring_q[e * (FR * 4) + i] = w;
         }
     }
     __device__ __forceinline__ void clear_hist() {
@@ -164,7 +156,7 @@ struct VrDecoder {
     // windowed traceback from slot A0 at time t (viterbi.hpp:205-237): one lane of the quad walks the ring (vr_traceback)
     __device__ __forceinline__ void traceback(const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout) {
         __syncwarp(QM);
-        if (q == 0) vr_traceback<FR, GR, LB == 0>(ring_b, hb, wslot, A0, t, la + nout);
+        if (q == 0) vr_traceback<FR>(ring_b, hb, wslot, A0, t, la + nout);
         __syncwarp(QM);
         vr_emit(hb, op, out_cap, nraw, nout >> 3, t & 7u, la, (uint32_t)q, (uint32_t)NL);
         nraw += nout >> 3;
@@ -179,7 +171,6 @@ struct VrDecoder {
         if (nout) {                                     // uniform inside the quad
             uint32_t A0;
             if constexpr (LB == 2) A0 = vr_best_slot(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], (uint32_t)q, tm, (t - 1u) & 7u, QM);
-            else if constexpr (LB == 0) A0 = vr_best_slot32(R, tm, (t - 1u) & 7u);
             else A0 = vr_best_slot16(R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8], R[9], R[10], R[11], R[12], R[13], R[14], R[15], (uint32_t)q, tm, (t - 1u) & 7u, QM);
             if (t & 7u) store_hist(wslot);              // mid-block: the partial histories of the running block (a block end has just stored its own)
             traceback(A0, t, la, nout);
@@ -241,13 +232,13 @@ __global__ void k_vit_lists(const FrameInfo* __restrict__ info, uint32_t nframes
 }
 
 // list / cnt: work list of this code rate (k_vit_lists) or null = frames 0 .. nframes-1 with the uniform parameters of `job`.
-template <int CODE_RATE, int LB = 2, bool GR = false>
+template <int CODE_RATE, int LB = 2>
 __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
-        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring = nullptr) {
-    using D = VrDecoder<CODE_RATE, LB, GR>;
+        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out) {
+    using D = VrDecoder<CODE_RATE, LB>;
     constexpr int FR = D::FR, NL = D::NL;               // code blocks per warp (8 | 16), lanes per code block (4 | 2)
-    __shared__ uint4 s_ring[GR ? 1 : SB_VR_NB][FR][4]; // entry: history bytes of the 64 slots of every code block over 8 columns (GR: in global memory, gring)
+    __shared__ uint4 s_ring[SB_VR_NB][FR][4];          // entry: history bytes of the 64 slots of every code block over 8 columns
     __shared__ uint8_t s_hb[FR][SB_VR_HB];             // traceback scratch: the history bytes a walk passed, per code block
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
@@ -294,9 +285,9 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
     if (q == 0) d.R[0] = 0x30000000u;
     d.end = L * 8u + 16u + 6u; d.ob = 0; d.nraw = 0; d.wslot = 0; d.done = !valid;
     d.next_tb = min(d.end, d.depth + d.look + 6u);      // first time a traceback can fire (viterbi.hpp:182-203)
-    uint4* const ring0 = GR ? gring + (size_t)blockIdx.x * (SB_VR_NB * FR * 4) : &s_ring[0][0][0];      // this CTA's ring: [entry][code block][4 x 16 bytes]
-    d.ring_q = LB == 0 ? ring0 + fb : ring0 + fb * 4 + q * (4 / NL);     // + entry * (FR * 4): this lane's 16 / 32 / 64 bytes of the code block's 64 (LB = 0: + group * FR)
-    d.ring_b = (const uint8_t*)(LB == 0 ? ring0 + fb : ring0 + fb * 4);  // + entry * (FR * 64) + vr_slot_off(slot)
+    uint4* const ring0 = &s_ring[0][0][0];              // this CTA's ring: [entry][code block][4 x 16 bytes]
+    d.ring_q = ring0 + fb * 4 + q * (4 / NL);     // + entry * (FR * 4): this lane's 16 / 32 / 64 bytes of the code block's 64 (LB = 0: + group * FR)
+    d.ring_b = (const uint8_t*)(ring0 + fb * 4);        // + entry * (FR * 64) + slot
     d.hb = s_hb[fb];
 
     // lockstep part: all eight code blocks of the warp advance together, 24 or 6 steps at a time; the soft values of the next four chunks
