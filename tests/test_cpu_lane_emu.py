@@ -94,3 +94,17 @@ def test_blocks_of_different_lengths_side_by_side(emu, hb):
             k = int(nraw[i])
             assert k <= L + 2 and (i == 7 or k == L + 2), (cr, i, k, L)
             assert (g[i, :k] == o[:k]).all(), (cr, i, L)
+
+@HB
+def test_short_windows(emu, hb):
+    """Traceback windows shorter than a deferred walk lasts (the standalone decoder accepts any depth that is a multiple of 8): a trigger then
+    finds the previous window's walk still in flight and has to finish it first; every window size must still give the oracle's bytes."""
+    rng = np.random.default_rng(21)
+    for cr, per in ((CR_12, 2), (CR_23, 3), (CR_34, 4)):
+        L = 90; ns = (8 * L + 22 + 5) * per                               # more groups than the block needs, for every rate
+        ns = ns // per * per
+        soft = rng.integers(0, 8, (5, ns)).astype(np.uint8)
+        for depth, look in ((8, 0), (8, 24), (16, 7), (64, 24), (128, 40), (248, 32)):
+            g, _ = emu(soft, cr, L, depth, look, hb=hb)
+            o = oracle_py.viterbi_blocks(soft, cr, L, depth, look)
+            assert (g == o).all(), (cr, depth, look, np.argwhere(g != o)[:4])
