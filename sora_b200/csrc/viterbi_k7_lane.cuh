@@ -4,23 +4,25 @@
 // kernel/bb/Brick11/src/viterbi.hpp:104-237); the add-compare-select is that file's vr_step — one fused VIADDMNMX.U16x2 and one
 // VIADD.16x2 per register and trellis step, the survivor history riding in the low byte of every 16-bit metric.
 //
-// What is different, and why (profiles/r2c_viterbi_v5_ncu.txt, r2c_viterbi_v7_ncu.txt):
+// What is different, and why (profiles/r2c_viterbi_v5_ncu.txt, r2c_viterbi_v7_ncu.txt, r2b_final_viterbi_ncu.txt):
 //   * A lane owns all 64 states of a code block (32 registers); a warp decodes 32 code blocks.  No lane ever needs another lane's
 //     metrics: no shuffle, no quad mask, no per-lane selector — every PRMT selector and pairing distance is a compile-time constant.
 //     The per-warp overhead of a step (branch-metric construction, fetch, loop) is spread over 32 code blocks instead of 8:
-//     0.58x the instructions of the four-lanes-per-block kernel for the same work (measured).
+//     0.63x the instructions of the four-lanes-per-block kernel for the same work (measured).
 //   * The 24-step unrolled stream of viterbi_k7_re.cuh (lcm of the 6-step trellis phase and its 8-column history block) does not
 //     survive this widening: 1 800 instructions of straight-line code per warp, every warp at another place in it — the measured
-//     kernels stall on instruction fetch (2.8 - 4.3 warps per issue slot waiting for instructions).  Here the history block is SIX
-//     columns, the trellis period itself: the loop body is one 6-step chunk (~8 KB of code for all warps of the SM), the history mark
-//     of a step is a constant of its phase, a block boundary always falls on phase 0, where slot address == state index, and the slot
-//     six columns back along a survivor is simply the bit-reversed history byte.
-//   * The survivor ring (50 entries x 64 bytes per code block = 100 KB per warp) cannot live in shared memory; it is a per-CTA slab of
-//     global memory, written with one fully coalesced 128-bit store per 16 states (512 contiguous bytes per warp and instruction)
-//     and read back by the traceback with ld.global.cg.  Every lane walks its own window — 32 walks per warp instruction, where the
-//     quad kernel has 8 — and packs the decoded bits on the way; there is no scratch row and no second pass.
-//     The ring is re-used in place, so L2 absorbs what fits; the rest is HBM traffic this kernel trades for instructions
-//     ("The Viterbi kernel").
+//     kernels stall on instruction fetch (2.8 - 4.3 warps per issue slot waiting for instructions).  Here the loop body is ONE 6-step
+//     chunk.  With six-column history blocks (HB = 6) everything in it is a constant of the phase; with eight-column blocks (HB = 8, the
+//     default: a quarter less ring traffic, fewer look-ups per window) the mark of a step is a warp-uniform run-time shift and the block
+//     ends are three uniform branches.
+//   * The survivor ring (up to 67 entries x 64 bytes per code block = 134 KB per warp) cannot live in shared memory; it is a per-CTA slab
+//     of global memory, written with one fully coalesced 128-bit store per 16 states (512 contiguous bytes per warp and instruction)
+//     and read back with ld.global.cg.  Every lane walks its own window — 32 walks per warp instruction, where the quad kernel has 8 —
+//     and packs the decoded bits on the way; there is no scratch row and no second pass.  The rings of all resident warps do not fit
+//     L2: this is HBM traffic (6 GB written, 4.6 GB read per 65 536 frames) that the kernel trades for instructions.
+//   * The walk is a chain of dependent look-ups of ~1 400 cycles each.  DEFER (default) takes it off the critical path: the trigger only
+//     starts it, the step loop does one look-up per chunk (VlDecoder::walk_tick), the forward pass never waits.
+//   DESIGN.md, "The Viterbi kernel", has the measurements behind each of these.
 #pragma once
 #include "viterbi_k7_common.cuh"
 
@@ -59,30 +61,6 @@ inline uint32_t vl_ld8(const uint8_t* p, const uint64_t) { return *p; }
 inline uint2 vl_ld64(const uint8_t* p, const uint64_t) { return *(const uint2*)p; }
 #endif
 
-// The rings of all resident warps together (150 - 230 MB) are larger than L2: by the time a window is walked, all but its newest entries
-// have been written back to HBM, and a walk that fetches them one dependent look-up at a time pays a DRAM round trip per look-up (the first
-// capture: 2.5 warps per issue slot waiting on them).  So the walk first asks for the whole older part of its window at once — this lane's
-// four 32-byte sectors of every entry from the SKIP-th newest on, `prefetch.global.L2`, nothing waits for them — and by the time it has
-// walked the newest entries (still in L2) the rest has arrived.  Costs 4 instructions per entry and lane and the sectors the walk would
-// not have touched (the walk reads one of this lane's four per entry).
-#define SB_VL_PF_SKIP 6
-template <uint32_t NBX>
-__device__ __forceinline__ void vl_prefetch_window(const uint8_t* ring_b, uint32_t eo, uint32_t nent, const uint32_t skip) {
-#ifndef SB_HOST_EMU
-    constexpr uint32_t EB = SB_VL_ENTRY * 16u;
-    for (uint32_t k = 0; k < nent; k++) {
-        if (k >= skip) {
-            const uint8_t* p = ring_b + eo;
-#pragma unroll
-            for (uint32_t g = 0; g < 4u; g++) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + g * (SB_VL_FR * 16u)));
-        }
-        eo = eo ? eo - EB : (NBX - 1u) * EB;
-    }
-#else
-    (void)ring_b; (void)eo; (void)nent; (void)skip;
-#endif
-}
-
 // Windowed traceback from slot A0 at time t over la + nout columns (viterbi.hpp:205-237), by one lane for its own code block.
 // The newest block (kp = t mod 6 columns; 0 = a whole one) is in ring entry e.  Walking n columns back from a slot replaces its
 // top n address bits by the reversed history bits of those columns (column c was produced at phase (c - 1) mod 6, which replaces
@@ -91,7 +69,7 @@ __device__ __forceinline__ void vl_prefetch_window(const uint8_t* ring_b, uint32
 // A free function of plain values, kept out of line: it runs once per `depth` steps and must not sit in the instruction stream of the
 // step loop — and the decoder's registers must never have their address taken.
 __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
-                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol, const uint32_t pf_skip) {
+                                          const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol) {
     constexpr uint32_t EB = SB_VL_ENTRY * 16u;          // bytes per ring entry of the CTA
     uint32_t A = A0, todo = la + nout, acc = 0;
     int nb = -(int)la;                                   // valid bits in acc (negative: still inside the look-ahead)
@@ -101,7 +79,6 @@ __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, ui
     auto back = [&]() { eo = eo ? eo - EB : (SB_VL_NB - 1u) * EB; };
     auto hist = [&]() { return vl_ld8(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)), pol) & 63u; };
     const uint32_t kp = t % 6u;
-    vl_prefetch_window<SB_VL_NB>(ring_b, eo, (todo + 5u) / 6u + 1u, pf_skip);
     if (kp) {                                            // running block: kp columns, history bits kp-1 .. 0 (todo >= 8 > kp always)
         const uint32_t h = hist(), low = (1u << (6u - kp)) - 1u;
         acc = h & ((1u << kp) - 1u); nb += (int)kp;
@@ -122,7 +99,7 @@ __device__ __noinline__ void vl_traceback(const uint8_t* __restrict__ ring_b, ui
 // boundary then falls on any even phase).  Eight decoded bits per look-up; the slot eight columns back is the bit permutation of
 // viterbi_k7_re.cuh's vr_traceback: address bit (i - ph) mod 6 <- decision of column tt - i, the two oldest columns overriding i = 0, 1.
 __device__ __noinline__ void vl_traceback8(const uint8_t* __restrict__ ring_b, uint8_t* __restrict__ op, const uint32_t out_cap, uint32_t e,
-                                           const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol, const uint32_t pf_skip) {
+                                           const uint32_t A0, const uint32_t t, const uint32_t la, const uint32_t nout, const uint32_t first, const uint64_t pol) {
     constexpr uint32_t EB = SB_VL_ENTRY * 16u;
     uint32_t A = A0, todo = la + nout, acc = 0;
     int nb = -(int)la;
@@ -133,7 +110,6 @@ __device__ __noinline__ void vl_traceback8(const uint8_t* __restrict__ ring_b, u
     auto hist = [&]() { return vl_ld8(ring_b + (eo + (A >> 4) * (SB_VL_FR * 16u) + (A & 15u)), pol); };
     uint32_t tt = t;                                     // time of the newest column not yet walked
     const uint32_t kp = t & 7u;
-    vl_prefetch_window<SB_VL_NB8>(ring_b, eo, (todo + 7u) / 8u + 1u, pf_skip);
     if (kp) {                                            // running block: kp columns, one slot-address bit changes per column
         const uint32_t h = hist();
         for (uint32_t c = 0; c < kp; c++) {              // column tt - c was produced at phase (tt - c - 1) mod 6: bit 5 - phase is replaced
@@ -178,7 +154,7 @@ struct VlDecoder {
     VrLane LC;             // selectors of vr_step: constants here (no lane part), kept in the struct the step function takes
     uint32_t kc[2];        // 28 << 8 and 14 << 8 in both halves
     uint32_t mk[5], mkH, mkL;   // history mark of phase T = 0x00010001 << T as registers (IMAD-side adds, see vr_step); phase 5 split by half
-    uint4* ring_q; const uint8_t* ring_b; uint64_t pol_ring, pol_soft; uint32_t pf_skip;   // pf_skip: newest entries a walk does not prefetch (>= ring size: no prefetch)
+    uint4* ring_q; const uint8_t* ring_b; uint64_t pol_ring, pol_soft;
     const uint8_t* sp; uint8_t* op; uint32_t out_cap, nsoft;
     uint32_t depth, look, end, ob, next_tb, nraw, wslot;
     bool done;
@@ -229,9 +205,9 @@ struct VlDecoder {
         if (nout) {
             const uint32_t A0 = best_slot(tm, HB == 6 ? (tm ? tm - 1u : 5u) : ((t - 1u) & 7u));
             if (HB == 6 ? tm != 0u : (t & 7u) != 0u) store_hist(wslot);   // mid-block: the partial histories of the running block (a block end has just stored its own)
-            if constexpr (HB == 6) vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring, pf_skip);
+            if constexpr (HB == 6) vl_traceback(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
             else if constexpr (DEFER) walk_start(A0, t, la, nout);
-            else vl_traceback8(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring, pf_skip);
+            else vl_traceback8(ring_b, op, out_cap, wslot, A0, t, la, nout, nraw, pol_ring);
             nraw += nout >> 3; ob += nout;
         }
         if (ob + 6u >= end && t >= end) done = true;
@@ -311,7 +287,7 @@ struct VlDecoder {
 template <int CODE_RATE, int HB = 6, bool DEFER = false>
 __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restrict__ soft, uint64_t soft_stride, uint32_t nframes,
         const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt, const FrameInfo* __restrict__ info, VitJob job,
-        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags, uint32_t nsm) {
+        uint8_t* __restrict__ out, uint64_t out_stride, uint32_t raw_off, uint32_t* __restrict__ nraw_out, uint4* __restrict__ gring, uint32_t flags) {
     using D = VlDecoder<CODE_RATE, HB, DEFER>;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const uint32_t nvalid = list ? __ldg(cnt + CODE_RATE) : (job.code_rate == (uint32_t)CODE_RATE ? nframes : 0u);
@@ -351,17 +327,7 @@ __global__ void __launch_bounds__(32, 16) k_viterbi_lane(const uint8_t* __restri
     uint4* const ring0 = gring + (size_t)blockIdx.x * (D::NB * SB_VL_ENTRY);
     d.ring_q = ring0 + lane; d.ring_b = (const uint8_t*)(ring0 + lane);
     d.pol_ring = vl_policy((flags & 1u) ? 1 : 0); d.pol_soft = vl_policy((flags & 2u) ? 2 : 0);
-    d.pf_skip = (flags & 4u) ? 0xFFFFu : ((flags >> 8) & 0xFFu) ? ((flags >> 8) & 0xFFu) : SB_VL_PF_SKIP;   // bit 2: no window prefetch; bits 8-15: skip count (0 = default)
 
-    // Frames of one length, CTAs launched together: every resident warp would reach its traceback triggers at the same moment, and while a
-    // walk waits for its look-ups (~1 400 cycles each, 30 % of all stall samples in the first captures) the other warps of the scheduler
-    // would be waiting too.  The warps of a scheduler are started a quarter of a window period apart instead (flags bit 3 turns it off):
-    // launch slot j of this SM (blockIdx / SM count) sleeps 0 .. 3 quarters of depth * 250 ns — 250 ns is a trellis step at four warps per scheduler.
-    if (!(flags & 8u)) {
-        const uint32_t j = (blockIdx.x / max(nsm, 1u)) & 15u;
-        const uint32_t ns = (((j >> 2) + (j & 3u)) & 3u) * d.depth * 62u;   // distinct for the four warps of a scheduler whether slots map to schedulers as j % 4 or as j / 4
-        if (ns) __nanosleep(ns);
-    }
     // lockstep part: the 32 code blocks of the warp advance together, one 6-step chunk per iteration; the soft values of the next two
     // chunks are always in registers
     uint32_t tb = 0, pos = 0;                           // time and soft position at the start of the next chunk (uniform)

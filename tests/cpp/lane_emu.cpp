@@ -39,7 +39,6 @@ template <class T> static inline void __stcg(T* p, const T& v) { *p = v; }
 static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int) { return v; }   // never reached with one lane per code block
 static inline bool __any_sync(unsigned, bool p) { return p; }                    // one lane at a time: the vote is its own predicate
 static inline bool __all_sync(unsigned, bool p) { return p; }
-static inline void __nanosleep(unsigned) {}
 
 #include "viterbi_k7_lane.cuh"
 
@@ -56,8 +55,8 @@ extern "C" int lane_emu_viterbi(const uint8_t* soft, uint64_t soft_stride, uint3
     std::vector<uint4> ring((size_t)ctas * SB_VL_NB8D * SB_VL_ENTRY);
     for (uint32_t c = 0; c < ctas; c++) for (unsigned lane = 0; lane < 32; lane++) {
         blockIdx.x = c; threadIdx.x = lane;
-#define SB_EMU_RUND(CR) sb::k_viterbi_lane<CR, 8, true>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u, 148u)
-#define SB_EMU_RUN(CR, HB) sb::k_viterbi_lane<CR, HB>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u, 148u)
+#define SB_EMU_RUND(CR) sb::k_viterbi_lane<CR, 8, true>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u)
+#define SB_EMU_RUN(CR, HB) sb::k_viterbi_lane<CR, HB>(soft, soft_stride, nblocks, nullptr, nullptr, info, job, out, out_stride, 0u, nraw, ring.data(), 0u)
         if (hb == 6) { if (code_rate == sb::CR_12) SB_EMU_RUN(sb::CR_12, 6); else if (code_rate == sb::CR_23) SB_EMU_RUN(sb::CR_23, 6); else SB_EMU_RUN(sb::CR_34, 6); }
         else if (hb == 9) { if (code_rate == sb::CR_12) SB_EMU_RUND(sb::CR_12); else if (code_rate == sb::CR_23) SB_EMU_RUND(sb::CR_23); else SB_EMU_RUND(sb::CR_34); }
         else         { if (code_rate == sb::CR_12) SB_EMU_RUN(sb::CR_12, 8); else if (code_rate == sb::CR_23) SB_EMU_RUN(sb::CR_23, 8); else SB_EMU_RUN(sb::CR_34, 8); }
