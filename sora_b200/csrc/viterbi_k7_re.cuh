@@ -353,12 +353,29 @@ __global__ void __launch_bounds__(32) k_viterbi_re(const uint8_t* __restrict__ s
 // Descrambler + frame sink after the Viterbi kernel, one thread per frame (T11aDesc, scramble.hpp:269-355; TBB11aFrameSink, PHY_11a.hpp:609-702):
 // raw bytes (SERVICE + scrambled PSDU) sit at row + 14 so that the PSDU starts 16-byte aligned at row + 16; the descrambled PSDU goes to row + 0.
 // The first SERVICE byte is dropped, the second seeds the register (byte >> 1), then out = byte ^ lut[reg], reg advances by eight bits per byte.
+// Both recurrences are taken off the per-byte dependency chain: the masks a 7-bit register produces byte after byte are one cycle of 127
+// values (x^7 + x^4 + 1 is primitive, 8 and 127 are coprime), so the mask of byte i is s_seq[(position of the seed + i) mod 127] — four
+// independent look-ups per word — and the CRC-32 goes four bytes per step through the three derived tables of the sliced form
+// (T_k[i] = T_{k-1}[i] >> 8 ^ T_0[T_{k-1}[i] & 0xFF]); the words that touch the FCS or the end of the data take the byte-wise path.
 __global__ void __launch_bounds__(128) k_sink11a(uint8_t* __restrict__ out, uint64_t out_stride, uint32_t nframes, const FrameInfo* __restrict__ info,
                                                  DevTables T, uint32_t* __restrict__ status_io, uint32_t* __restrict__ crc_out) {
-    __shared__ uint32_t s_crc[256];                    // CRC-32 (reflected 0xEDB88320, core/inc/CRC32.h:76)
+    __shared__ uint32_t s_crc[4][256];                 // CRC-32 (reflected 0xEDB88320, core/inc/CRC32.h:76) and its three sliced companions
     __shared__ uint8_t s_scr[128];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = __ldg(T.crc32 + i);
+    __shared__ uint8_t s_seq[136];                     // [0, 127): the cycle of masks, [127, 130): its first three again, [132, 136): zeros (the all-zero register)
+    __shared__ uint8_t s_pos[128];                     // 7-bit register -> position of its first mask in the cycle (register 0: 132)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[0][i] = __ldg(T.crc32 + i);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_scr[i] = __ldg(T.scramble + i);
+    __syncthreads();
+    for (int k = 1; k < 4; k++) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) { const uint32_t v = s_crc[k - 1][i]; s_crc[k][i] = (v >> 8) ^ s_crc[0][v & 0xFFu]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t reg = 1;
+        for (int k = 0; k < 127; k++) { const uint32_t m = s_scr[reg]; s_seq[k] = (uint8_t)m; s_pos[reg] = (uint8_t)k; reg = m >> 1; }
+        s_seq[127] = s_seq[0]; s_seq[128] = s_seq[1]; s_seq[129] = s_seq[2]; s_seq[130] = s_seq[131] = 0;
+        s_seq[132] = s_seq[133] = s_seq[134] = s_seq[135] = 0; s_pos[0] = 132;
+    }
     __syncthreads();
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
@@ -368,7 +385,8 @@ __global__ void __launch_bounds__(128) k_sink11a(uint8_t* __restrict__ out, uint
     uint8_t* row = out + (size_t)f * out_stride;
     uint32_t verdict = E_FAILED, fcs = 0, crc = 0xFFFFFFFFu;
     if (nraw >= 2u) {
-        uint32_t reg = row[15] >> 1;
+        const uint32_t reg0 = row[15] >> 1;
+        uint32_t p = s_pos[reg0]; const uint32_t pstep = reg0 ? 4u : 0u;
         const uint32_t have = min(nraw - 2u, L);        // PSDU bytes available
         const uint32_t cap = (uint32_t)(out_stride < 0xFFFFFFFFull ? out_stride : 0xFFFFFFFFull);
         for (uint32_t i0 = 0; i0 < have; i0 += 16u) {
@@ -376,19 +394,23 @@ __global__ void __launch_bounds__(128) k_sink11a(uint8_t* __restrict__ out, uint
             uint32_t w[4] = {v.x, v.y, v.z, v.w}, o4[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint32_t ow = 0;
+                const uint32_t m = (uint32_t)s_seq[p] | ((uint32_t)s_seq[p + 1] << 8) | ((uint32_t)s_seq[p + 2] << 16) | ((uint32_t)s_seq[p + 3] << 24);
+                p += pstep; if (p >= 127u && pstep) p -= 127u;
+                const uint32_t ow = w[j] ^ m, i = i0 + 4u * j;
+                o4[j] = ow;
+                if (i + 7u < L && i + 3u < have) {       // the whole word is data under the CRC
+                    const uint32_t c = crc ^ ow;
+                    crc = s_crc[3][c & 0xFFu] ^ s_crc[2][(c >> 8) & 0xFFu] ^ s_crc[1][(c >> 16) & 0xFFu] ^ s_crc[0][c >> 24];
+                } else {
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const uint32_t i = i0 + 4u * j + b;
-                    reg = s_scr[reg];
-                    const uint32_t o = ((w[j] >> (8 * b)) & 0xFFu) ^ reg; reg >>= 1;
-                    ow |= o << (8 * b);
-                    if (i < have) {
-                        if (i + 4u < L) crc = (crc >> 8) ^ s_crc[(crc ^ o) & 0xFFu];
-                        else if (L >= 4u) fcs |= o << (8u * (i + 4u - L));
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t ib = i + b, o = (ow >> (8 * b)) & 0xFFu;
+                        if (ib < have) {
+                            if (ib + 4u < L) crc = (crc >> 8) ^ s_crc[0][(crc ^ o) & 0xFFu];
+                            else if (L >= 4u) fcs |= o << (8u * (ib + 4u - L));
+                        }
                     }
                 }
-                o4[j] = ow;
             }
             if (i0 + 16u <= have && i0 + 16u <= cap) *(uint4*)(row + i0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             else for (uint32_t i = i0; i < have && i < cap; i++) row[i] = (uint8_t)(o4[(i - i0) >> 2] >> (8u * ((i - i0) & 3u)));
